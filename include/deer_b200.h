@@ -1,0 +1,193 @@
+/*
+ * deer_b200.h -- C ABI of libdeer_b200.so (hand-written sm_100a CUDA for the DEER hot path).
+ *
+ * The reference (kalgeee/Uncertainty-Aware-Multimodal-Emotion-Recognition) is pure PyTorch and has NO
+ * FFI/operator interface; its boundary is the Python class/dict API, which the
+ * host package mirrors.  This header is the boundary a maintainer would bind instead of the stock ATen
+ * calls; every entry point cites the reference call site it replaces (paths relative to the reference
+ * repository root).  INTEGRATION.md shows the ctypes stub.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless stated; fp32 row-major.
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous on it and never synchronise,
+ *     never allocate and never free (graph-capture safe).  Scratch memory is caller-provided.
+ *   - return 0 on success; <0 on error: -1 invalid argument, -2 unsupported shape, -(1000+e) CUDA error e.
+ *     deer_last_error() returns a thread-local description.
+ *   - ld* are leading dimensions in ELEMENTS.
+ */
+#ifndef DEER_B200_H
+#define DEER_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DEER_OK 0
+#define DEER_ERR_INVALID (-1)
+#define DEER_ERR_UNSUPPORTED (-2)
+
+/* activation codes for fused epilogues */
+#define DEER_ACT_NONE 0
+#define DEER_ACT_RELU 1
+#define DEER_ACT_TANH 2
+#define DEER_ACT_SIGMOID 3
+
+/* GEMM engines */
+#define DEER_GEMM_AUTO 0   /* tcgen05 when the shape/alignment allows it, SIMT otherwise */
+#define DEER_GEMM_SIMT 1   /* fp32 CUDA-core tiles (exact fp32; small or unaligned shapes) */
+#define DEER_GEMM_TF32 2   /* tcgen05.mma kind::tf32, fp32 accumulate in TMEM, TMA-fed */
+
+int deer_version(void);
+const char* deer_last_error(void);
+/* number of kernels launched by this library since process start (bench.py `gpu_launches`) */
+long long deer_launch_count(void);
+
+/* ---- dense contractions: every nn.Linear on the path (encoders.py:93-107,443-475,597-625;
+ *      fusion.py:98-103,201-219,286-304; deer.py:48-56,215-222; complete_project.py:61-417), the
+ *      time-batched LSTM input projections (encoders.py:82,380) and the Conv1d taps (encoders.py:450-459).
+ *      C[b] = act(opA(A[b]) * opB(B[b]) + bias[b] + beta * C[b])      (beta in {0,1}; beta=1 chains K-blocks of a
+ *      concatenated input -- Linear(cat[a,b]) = a W1^T + b W2^T -- and accumulates weight gradients)
+ *      opA(A) is M x K: transA=0 -> A stored [M,K] (lda>=K); transA=1 -> A stored [K,M] (lda>=M).
+ *      opB(B) is K x N: transB=0 -> B stored [K,N] (ldb>=N); transB=1 -> B stored [N,K] (ldb>=K)  (nn.Linear weight).
+ *      batch>=1 with element strides sA/sB/sC/sBias (may be negative or zero). bias may be NULL. */
+int deer_gemm(const float* A, long long lda, int transA, const float* B, long long ldb, int transB,
+              float* C, long long ldc, int M, int N, int K, const float* bias, int act, float beta,
+              int batch, long long sA, long long sB, long long sC, long long sBias, int engine, void* stream);
+
+/* ---- activation backward + bias gradient (autograd of the Linear+act blocks above).
+ *      dz = dy * act'(y) (dz may alias dy; dz may be NULL when act==NONE); dbias[n] += sum_m dz[m,n] if dbias. */
+int deer_bias_act_bwd(const float* dy, long long ld_dy, const float* y, long long ld_y, float* dz, long long ld_dz,
+                      float* dbias, int M, int N, int act, void* stream);
+
+/* ---- nn.LayerNorm (encoders.py:106,474,624; fusion.py:102,218,303; complete_project.py:70,88,329,340) */
+int deer_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* rstd,
+                       int M, int N, float eps, void* stream);
+int deer_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean, const float* rstd,
+                       float* dx, float* dgamma, float* dbeta, int M, int N, void* stream);
+
+/* ---- nn.Dropout with a counter-based generator (Philox-4x32-10 keyed by seed, indexed by element).
+ *      y = x * keep/(1-p); the same call regenerates the mask for backward. x may alias y.
+ *      step_ptr (device, may be NULL): a 64-bit step counter mixed into the Philox counter so that a captured
+ *      CUDA graph draws a fresh mask on every replay. */
+int deer_dropout(const float* x, float* y, long long n, float p, unsigned long long seed, unsigned long long offset,
+                 const unsigned long long* step_ptr, void* stream);
+
+/* ---- attention pooling over time (encoders.py:93-98,383-384; :462-467,543-544; :597-602,738-746).
+ *      rowdot: s[m] = sum_j h[m,j]*w[j] + b[0]   (the Linear(D/2 -> 1) scorer head) */
+int deer_rowdot_fwd(const float* h, const float* w, const float* b, float* s, long long M, int N, void* stream);
+int deer_rowdot_bwd(const float* ds, const float* h, const float* w, float* dh, float* dw, float* db,
+                    long long M, int N, void* stream);
+/*      pool: p = softmax_t(s[b,:]); if mask: p = p*mask / (sum_t p*mask + 1e-10); out[b,:] = sum_t p[b,t] * x[b,t,:]
+ *      x element (b,t,d) at x[b*xs_b + t*xs_t + d]; s element (b,t) at s[b*ss_b + t*ss_t]; mask [B,T] contiguous or NULL;
+ *      if premask, x is multiplied by mask before use (text path, encoders.py:734-735). wts [B,T] out. */
+int deer_attn_pool_fwd(const float* x, long long xs_b, long long xs_t, const float* s, long long ss_b, long long ss_t,
+                       const float* mask, float* out, float* wts, int B, int T, int D, void* stream);
+/*      dx (b,t,d) = wts*dout (same strides as x, overwritten or accumulated per `accumulate`), ds (same strides as s) */
+int deer_attn_pool_bwd(const float* dout, const float* x, long long xs_b, long long xs_t, const float* s, long long ss_b,
+                       long long ss_t, const float* mask, const float* wts, float* dx, float* ds, int B, int T, int D,
+                       int accumulate, void* stream);
+
+/* ---- layout helpers */
+/* y[t,b,:] = x[b,t,:] (batch-first -> time-major) and the inverse */
+int deer_permute_bt(const float* x, float* y, int B, int T, int D, void* stream);
+/* y[m,:] = x[m,:] * mask[m]  (text mask, encoders.py:734-735); backward is the same call on dy */
+int deer_rowscale(const float* x, const float* mask, float* y, long long M, int D, void* stream);
+/* Conv1d(k=3,pad=1) lowering on channels-last x [B,T,C]: col [B*T, 3C], tap k holds x[b,t+k-1,:] (zero outside) */
+int deer_im2col3(const float* x, float* col, int B, int T, int C, void* stream);
+int deer_col2im3(const float* dcol, float* dx, int B, int T, int C, void* stream);
+/* w [Cout,Cin,3] (nn.Conv1d layout) <-> wk [Cout,3,Cin]; dir=0 pack, dir=1 unpack with accumulate into w */
+int deer_conv3_weight_pack(const float* w, float* wk, int Cout, int Cin, int dir, void* stream);
+
+/* ---- nn.BatchNorm1d + ReLU on channels-last rows x [M,C] (encoders.py:452,457).
+ *      training: batch statistics (biased variance) and running-stat update (momentum, unbiased variance);
+ *      eval: running statistics.  stats [2,C] scratch (mean, biased var). */
+int deer_bn_stats(const float* x, float* stats, long long M, int C, void* stream);
+int deer_bn_update_running(const float* stats, float* running_mean, float* running_var,
+                           long long* num_batches_tracked /* int64 counter or NULL */, long long M, int C,
+                           float momentum, void* stream);
+int deer_bn_relu_fwd(const float* x, const float* mean, const float* var, const float* gamma, const float* beta,
+                     float* y, long long M, int C, float eps, void* stream);
+/*      training-mode backward (through the batch statistics) when batch_stats!=0, else plain affine backward.
+ *      scratch [2,C] floats, zeroed by the call. dgamma/dbeta accumulate. */
+int deer_bn_relu_bwd(const float* dy, const float* x, const float* y, const float* mean, const float* var,
+                     const float* gamma, float* dx, float* dgamma, float* dbeta, float* scratch, long long M, int C,
+                     float eps, int batch_stats, void* stream);
+
+/* ---- 2-token multi-head self attention core (fusion.py:293-298,328-332): qkv [B,2,3E] packed (q|k|v) after in_proj,
+ *      ctx [B,2,E] before out_proj, attw [B,2,2] head-averaged weights. */
+/*      ctx_mean [B,E] = mean over the two tokens of ctx (fusion.py:335 commutes with the linear out_proj); either of
+ *      ctx / ctx_mean may be NULL.  Backward takes the matching upstream gradients (either may be NULL). */
+int deer_mha2_fwd(const float* qkv, float* ctx, float* ctx_mean, float* attw, float* probs, int B, int E, int heads,
+                  void* stream);
+int deer_mha2_bwd(const float* dctx, const float* dctx_mean, const float* dattw, const float* qkv, const float* probs,
+                  float* dqkv, int B, int E, int heads, void* stream);
+
+/* ---- bidirectional LSTM layer recurrence (encoders.py:82-89,380), time-major.
+ *      gates [T,B,2,4H]: on entry the input projection x_t W_ih^T + b_ih + b_hh for both directions (dir 0 forward in
+ *      time, dir 1 reverse), on exit the post-activation gates i,f,g,o (kept for backward).
+ *      w_hh_fwd / w_hh_rev [4H,H] each (weight_hh_l{k}, weight_hh_l{k}_reverse); h_out [T,B,2H] (dir 0 in [0,H), dir 1 in [H,2H)); c_out [T,B,2,H] cell states or NULL
+ *      (inference: not kept; c_work [B,2,H] scratch then required). */
+int deer_lstm_fwd(float* gates, const float* w_hh_fwd, const float* w_hh_rev, float* h_out, float* c_out, float* c_work,
+                  int T, int B, int H, int engine, void* stream);
+/*      backward: dh_out [T,B,2H] upstream gradient; gates (post-activation) is overwritten by the pre-activation
+ *      gradients dgates [T,B,2,4H]; dh_work,dc_work [B,2,H] scratch. dW_hh, dW_ih, db and dx are then plain GEMMs /
+ *      column sums over dgates done by the caller. */
+int deer_lstm_bwd(float* gates, const float* w_hh_fwd, const float* w_hh_rev, const float* c_all, const float* dh_out,
+                  float* dh_work, float* dc_work, int T, int B, int H, int engine, void* stream);
+
+/* ---- NIG head transform (deer.py:90-98; complete_project.py:399-407). evidence [N,4] -> 7 arrays [N] */
+int deer_nig_head_fwd(const float* evidence, float* mu, float* nu, float* alpha, float* beta, float* aleatoric,
+                      float* epistemic, float* total, long long N, void* stream);
+int deer_nig_head_bwd(const float* evidence, const float* dmu, const float* dnu, const float* dalpha,
+                      const float* dbeta, const float* daleatoric, const float* depistemic, const float* dtotal,
+                      float* devidence, long long N, void* stream);
+
+/* ---- DEER loss (losses.py:72-348): two phases so the ECE bin statistics and batch means are exact.
+ *      Inputs either raw evidence [B,D,4] (from_evidence=1: the softplus head is fused) or the four NIG arrays [B,D].
+ *      stats [D, DEER_LOSS_NSTAT] must be zero on entry of phase 1; between the phases a data-parallel caller may
+ *      all-reduce `stats` (sum) and pass the GLOBAL batch size to phase 2 for exact global-batch semantics.
+ *      phase 2 writes losses[D*5+2] = per dim (total,nll,reg,kl,ece), cross_dim, total and the gradient
+ *      (d total / d evidence [B,D,4], or d/d(gamma,nu,alpha,beta) [B,D] x4) scaled by grad_scale. */
+#define DEER_LOSS_NSTAT 40
+int deer_nig_loss_stats(const float* evidence, const float* gamma, const float* nu, const float* alpha,
+                        const float* beta, const float* targets, const float* bin_edges, float* stats,
+                        float* nig_out /* [7,B,D] or NULL */, long long B, int D, int from_evidence, float eps,
+                        void* stream);
+int deer_nig_loss_finish(const float* evidence, const float* gamma, const float* nu, const float* alpha,
+                         const float* beta, const float* targets, const float* bin_edges, const float* stats,
+                         const float* task_weights /* [D] or NULL */, float reg_w, float kl_w, float ece_w,
+                         float cross_w, float eps, long long B_local, long long B_global, int D, int from_evidence,
+                         float grad_scale, float* losses, float* d_out /* [B,D,4] */, void* stream);
+/*      Amini-style variant, deer.py:111-195 (L3): stats-free single pass + mean; losses[5] */
+int deer_amini_loss(const float* mu, const float* nu, const float* alpha, const float* beta, const float* targets,
+                    float evidence_w, float kl_w, long long N, float* losses, float* dparams /* [4,N] or NULL */,
+                    float* scratch /* [8] zeroed by call */, void* stream);
+
+/* ---- trainer step (training.py:121-150,219,224): global grad norm, clip, AdamW over flat buffers */
+int deer_sumsq(const float* x, long long n, float* out /* accumulates */, void* stream);
+/*      clip coefficient = min(1, max_norm / (sqrt(*sumsq * inv_world^2...) + 1e-6)) computed on device from *sumsq */
+int deer_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+               float eps, float weight_decay, int step, const float* sumsq, float max_norm, float grad_scale,
+               void* stream);
+
+/* ---- generic elementwise helpers used by the pooled model (complete_project.py:282-293,364,439-459) */
+/* y = a*x1 + b*x2 (x2 may be NULL) */
+int deer_axpby(const float* x1, const float* x2, float* y, long long n, float a, float b, void* stream);
+/* out[m,:] = w[m*ldw]*s[m,:] + (1-u[m*ldu])*c[m,:]   and its backward */
+int deer_mix_fwd(const float* w, long long ldw, const float* u, long long ldu, const float* s, const float* c, float* out,
+                 long long M, int N, void* stream);
+int deer_mix_bwd(const float* dout, const float* w, long long ldw, const float* u, long long ldu, const float* s,
+                 const float* c, float* dw, long long lddw, float* du, long long lddu, float* ds, float* dc, long long M,
+                 int N, void* stream);
+/* out = g*a + (1-g)*b and backward */
+int deer_gate_fwd(const float* g, const float* a, const float* b, float* out, long long n, void* stream);
+int deer_gate_bwd(const float* dout, const float* g, const float* a, const float* b, float* dg, float* da, float* db,
+                  long long n, void* stream);
+/* row softmax over N<=32 columns and backward */
+int deer_softmax_rows_fwd(const float* x, float* y, long long M, int N, void* stream);
+int deer_softmax_rows_bwd(const float* dy, const float* y, float* dx, long long M, int N, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEER_B200_H */

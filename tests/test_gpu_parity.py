@@ -1,0 +1,295 @@
+"""GPU parity: the CUDA path (through the C ABI) against (1) golden vectors produced by the unmodified reference and
+(2) the CPU oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): NIG parameters and loss within 1e-3 relative, gradient cosine >= 0.999.
+The fp32 engines are held to a tighter TOL_FP32; the tcgen05/TF32 engines to the north-star 1e-3."""
+import numpy as np
+import pytest
+import torch
+
+import deer_b200
+from deer_b200 import ops
+from gen_common import det_normal, nig_inputs, probe, seq_inputs
+from helpers import assert_close, check_param_grads, cosine, load_fixture_weights, rel_l2
+from oracle import deer_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+TOL_FP32 = 2e-4
+DEV = "cuda"
+
+
+def cu(t):
+    return t.to(torch.float32).to(DEV)
+
+
+@pytest.fixture(autouse=True)
+def _engine():
+    ops.set_gemm_engine(ops.ENGINE_AUTO)
+    yield
+
+
+# ----------------------------------------------------------------------------- primitives
+@pytest.mark.parametrize("M,N,K,ta,tb", [(5, 7, 3, 0, 1), (130, 70, 84, 0, 1), (64, 64, 64, 1, 0), (33, 129, 65, 0, 0),
+                                         (200, 4, 64, 0, 1), (96, 100, 4100, 1, 0), (17, 31, 29, 1, 1)])
+def test_gemm_simt(M, N, K, ta, tb):
+    g = torch.Generator().manual_seed(M * 131 + N)
+    A = torch.randn((K, M) if ta else (M, K), generator=g)
+    B = torch.randn((N, K) if tb else (K, N), generator=g)
+    bias = torch.randn(N, generator=g)
+    C0 = torch.randn(M, N, generator=g)
+    ref = (A.t() if ta else A).double() @ (B.t() if tb else B).double()
+    for act, beta in ((0, 0.0), (1, 0.0), (2, 1.0), (0, 1.0)):
+        C = cu(C0).clone()
+        ops.gemm(cu(A), A.shape[1], ta, cu(B), B.shape[1], tb, C, N, M, N, K, bias=cu(bias), act=act, beta=beta,
+                 engine=ops.ENGINE_SIMT)
+        r = ref + bias.double() + beta * C0.double()
+        r = {0: r, 1: torch.relu(r), 2: torch.tanh(r)}[act]
+        assert_close(C, r, 1e-5, f"gemm act={act} beta={beta}")
+
+
+def test_layernorm_and_linear_autograd():
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(37, 96, generator=g)
+    w = torch.randn(128, 96, generator=g) * 0.1
+    b = torch.randn(128, generator=g) * 0.1
+    lg, lb = torch.rand(128, generator=g) + 0.5, torch.randn(128, generator=g) * 0.1
+    pr = torch.randn(37, 128, generator=g)
+
+    def run(fl, fn, args):
+        args = [a.clone().requires_grad_(True) for a in args]
+        y = fn(*args)
+        (y * pr.to(y)).sum().backward()
+        return y, [a.grad for a in args]
+    yr, gr = run(None, lambda x, w, b, lg, lb: O.layer_norm(torch.relu(O.linear(x, w, b)), lg, lb),
+                 [t.double() for t in (x, w, b, lg, lb)])
+    yc, gc = run(None, lambda x, w, b, lg, lb: ops.layer_norm(ops.linear(x, w, b, "relu"), lg, lb),
+                 [cu(t) for t in (x, w, b, lg, lb)])
+    assert_close(yc, yr, TOL_FP32, "y")
+    for a, r, n in zip(gc, gr, "x w b lg lb".split()):
+        assert_close(a, r, TOL_FP32, "grad " + n)
+
+
+def test_linear_concat_inputs_matches_cat():
+    g = torch.Generator().manual_seed(4)
+    a, b = torch.randn(9, 40, generator=g), torch.randn(9, 24, generator=g)
+    w, bias = torch.randn(32, 64, generator=g) * 0.2, torch.randn(32, generator=g)
+    ad, bd, wd = a.double().requires_grad_(True), b.double().requires_grad_(True), w.double().requires_grad_(True)
+    yr = torch.tanh(O.linear(torch.cat([ad, bd], 1), wd, bias.double()))
+    yr.sum().backward()
+    ac, bc, wc = cu(a).requires_grad_(True), cu(b).requires_grad_(True), cu(w).requires_grad_(True)
+    yc = ops.linear([ac, bc], wc, cu(bias), "tanh")
+    yc.sum().backward()
+    assert_close(yc, yr, TOL_FP32)
+    assert_close(ac.grad, ad.grad, TOL_FP32)
+    assert_close(bc.grad, bd.grad, TOL_FP32)
+    assert_close(wc.grad, wd.grad, TOL_FP32)
+
+
+def test_dropout_statistics_and_backward_mask():
+    x = torch.ones(1 << 20, device=DEV, requires_grad=True)
+    ops.manual_seed(123)
+    y = ops.dropout(x, 0.3, True)
+    keep = float((y != 0).float().mean())
+    assert abs(keep - 0.7) < 5e-3
+    assert abs(float(y.mean()) - 1.0) < 1e-2
+    y.sum().backward()
+    assert torch.equal((x.grad != 0), (y != 0))
+    ops.manual_seed(123)
+    y2 = ops.dropout(torch.ones(1 << 20, device=DEV), 0.3, True)
+    assert torch.equal(y2, y.detach())
+    assert ops.dropout(x, 0.3, False) is x
+
+
+# ----------------------------------------------------------------------------- modules vs golden fixtures
+@pytest.mark.parametrize("name", ["audio_small", "audio_full_t12"])
+def test_audio_encoder_golden(golden, name):
+    fx = golden(name)
+    m = fx.meta
+    enc = load_fixture_weights(deer_b200.EnhancedAudioEncoder({"hidden_dim": m["hidden"], "dropout": 0.0}), fx).to(DEV)
+    x = cu(seq_inputs(m["B"], m["T"], 2, 2, seed=m["seed"])[0]).requires_grad_(True)
+    h_tm = enc.lstm_forward(x)
+    assert_close(h_tm.permute(1, 0, 2), fx.t("lstm_out"), TOL_FP32, "lstm_out")
+    y = enc(x)
+    assert_close(y, fx.t("out"), TOL_FP32, "out")
+    (y * cu(probe("audio_out", y.shape, m["seed"]))).sum().backward()
+    assert_close(x.grad, fx.t("dx"), TOL_FP32, "dx")
+    check_param_grads(enc, fx, m["seed"], TOL_FP32)
+
+
+@pytest.mark.parametrize("name", ["video_small_train", "video_small_eval", "video_small_f1"])
+def test_video_encoder_golden(golden, name):
+    fx = golden(name)
+    m = fx.meta
+    enc = deer_b200.EnhancedVideoEncoder({"hidden_dim": m["hidden"], "dropout": 0.0, "frame_feature_dim": m["din"]})
+    enc = load_fixture_weights(enc, fx).to(DEV)
+    enc.train(m["training"])
+    x = cu(seq_inputs(m["B"], 2, m["F"], 2, Dv=m["din"], seed=m["seed"])[1]).requires_grad_(True)
+    y = enc(x)
+    assert_close(y, fx.t("out"), TOL_FP32, "out")
+    (y * cu(probe("video_out", y.shape, m["seed"]))).sum().backward()
+    assert_close(x.grad, fx.t("dx"), TOL_FP32, "dx")
+    check_param_grads(enc, fx, m["seed"], TOL_FP32)
+    if m["training"] and m["F"] > 1:
+        sd = enc.state_dict()
+        for k in fx.keys("post:"):
+            assert_close(sd[k[5:]], fx.t(k), 1e-5, k)
+        assert int(sd["temporal_cnn.1.num_batches_tracked"]) == 1
+
+
+def test_text_encoder_golden(golden):
+    fx = golden("text_small")
+    m = fx.meta
+    enc = load_fixture_weights(deer_b200.EnhancedTextEncoder({"hidden_dim": m["hidden"], "dropout": 0.0}), fx).to(DEV)
+    _, _, tok, mask, ling, _ = seq_inputs(m["B"], 2, 2, m["T"], seed=m["seed"])
+    tok, ling = cu(tok).requires_grad_(True), cu(ling).requires_grad_(True)
+    y = enc(tok, cu(mask), ling)
+    assert_close(y, fx.t("out"), TOL_FP32, "out")
+    (y * cu(probe("text_out", y.shape, m["seed"]))).sum().backward()
+    assert_close(tok.grad, fx.t("dtok"), TOL_FP32, "dtok")
+    assert_close(ling.grad, fx.t("dling"), TOL_FP32, "dling")
+    check_param_grads(enc, fx, m["seed"], TOL_FP32)
+
+
+def test_fusion_golden(golden):
+    fx = golden("fusion_small")
+    da, dv, dt, fd, idim, heads = fx.meta["dims"]
+    B, seed = fx.meta["B"], fx.meta["seed"]
+    fus = deer_b200.HierarchicalMultimodalFusion(da, dv, dt, fusion_dim=fd, intermediate_dim=idim,
+                                                 num_attention_heads=heads, dropout=0.0)
+    fus = load_fixture_weights(fus, fx).to(DEV)
+    a = cu(det_normal("in:fa", (B, da), seed)).requires_grad_(True)
+    v = cu(det_normal("in:fv", (B, dv), seed)).requires_grad_(True)
+    t = cu(det_normal("in:ft", (B, dt), seed)).requires_grad_(True)
+    out = fus(a, v, t)
+    keys = ("fused_features", "audiovisual_features", "trimodal_features", "trimodal_attention_weights")
+    for k in keys:
+        assert_close(out[k], fx.t(k), TOL_FP32, k)
+    assert_close(out["av_attention_weights"]["audio_to_video"], fx.t("a2v"), 1e-6)
+    assert_close(out["av_attention_weights"]["video_to_audio"], fx.t("v2a"), 1e-6)
+    assert out["uncertainty_weights"] is None
+    sum((out[k] * cu(probe(k, out[k].shape, seed))).sum() for k in keys).backward()
+    assert_close(a.grad, fx.t("da"), TOL_FP32, "da")
+    assert_close(v.grad, fx.t("dv"), TOL_FP32, "dv")
+    assert_close(t.grad, fx.t("dt"), TOL_FP32, "dt")
+    check_param_grads(fus, fx, seed, TOL_FP32)
+    # Q/K rows of the seq-1 cross attention get exactly zero gradient; uncertainty_gate.* is never touched
+    E = idim
+    gw = fus.audio_visual_fusion.cross_attention.in_proj_weight.grad
+    assert float(gw[:2 * E].abs().max()) == 0.0
+    for n, p in fus.named_parameters():
+        if n.startswith("uncertainty_gate"):
+            assert p.grad is None
+
+
+def test_head_golden(golden):
+    fx = golden("head_small")
+    m = fx.meta
+    head = load_fixture_weights(deer_b200.MultiDimensionalDEER(m["din"], 3, m["hidden"], 0.0), fx).to(DEV)
+    x = cu(det_normal("in:hx", (m["B"], m["din"]), m["seed"])).requires_grad_(True)
+    out = head(x)
+    ref_keys = [k for k in fx.arrays if not k.startswith(("grad:", "gsum:", "ghead:")) and k != "dx"]
+    assert len(ref_keys) == 23
+    for k in ref_keys:
+        assert_close(out[k], fx.t(k), TOL_FP32, k)
+    sum((out[k] * cu(probe(k, out[k].shape, m["seed"]))).sum() for k in ref_keys).backward()
+    assert_close(x.grad, fx.t("dx"), TOL_FP32, "dx")
+    check_param_grads(head, fx, m["seed"], TOL_FP32)
+
+
+@pytest.mark.parametrize("name", ["loss_b64", "loss_b1000", "loss_b3"])
+@pytest.mark.parametrize("fused", [True, False])
+def test_losses_golden(golden, name, fused):
+    fx = golden(name)
+    e, y = nig_inputs(fx.meta["B"], fx.meta["seed"])
+    e, y = cu(e).requires_grad_(True), cu(y)
+    nig = ops.nig_head(e)
+    from deer_b200.deer import nig_dict
+    pred = nig_dict(e, nig, ["valence", "arousal", "dominance"])
+    if not fused:
+        pred.pop("_deer_evidence")
+    out = deer_b200.MultiTaskDEERLoss()(pred, y)
+    for k in fx.keys("mt:"):
+        if k == "mt:devidence":
+            continue
+        ref = float(fx.arrays[k])
+        got = float(out[k[3:]])
+        assert abs(got - ref) <= TOL_FP32 * max(abs(ref), 1e-3) * 5, (k, got, ref)
+    out["total_loss"].backward()
+    assert_close(e.grad, fx.t("mt:devidence"), TOL_FP32 * 5, "devidence")
+    assert cosine(e.grad, fx.t("mt:devidence")) > 0.99999
+    # single-dimension DEERLoss (L1) and the Amini-style deer.DEERLoss (L3)
+    single = deer_b200.DEERLoss()({"mu": nig[0][:, 0:1], "nu": nig[1][:, 0:1], "alpha": nig[2][:, 0:1],
+                                   "beta": nig[3][:, 0:1]}, y[:, 0:1])
+    for k in fx.keys("l1:"):
+        ref, got = float(fx.arrays[k]), float(single[k[3:]])
+        assert abs(got - ref) <= 1e-3 * max(abs(ref), 1e-3), (k, got, ref)
+    e.grad = None
+    nig2 = ops.nig_head(e)
+    am = deer_b200.AminiDEERLoss()({"mu": nig2[0], "nu": nig2[1], "alpha": nig2[2], "beta": nig2[3]}, y)
+    for k in fx.keys("l3:"):
+        if k != "l3:devidence":
+            ref, got = float(fx.arrays[k]), float(am[k[3:]])
+            assert abs(got - ref) <= 1e-3 * max(abs(ref), 1e-3), (k, got, ref)
+    am["total_loss"].backward()
+    assert_close(e.grad, fx.t("l3:devidence"), 1e-3, "l3 devidence")
+
+
+# ----------------------------------------------------------------------------- the full sequence composite
+def _run_composite(model, batch, engine):
+    ops.set_gemm_engine(engine)
+    audio, video, text, mask, ling, y = batch
+    model.zero_grad(set_to_none=True)
+    out = model(cu(audio), cu(video), cu(text), cu(mask), cu(ling))
+    loss = model.compute_loss(out, cu(y))
+    loss["total_loss"].backward()
+    return out, loss
+
+
+def test_sequence_composite_golden_and_oracle(golden):
+    fx = golden("seq_full_b4")
+    m = fx.meta
+    model = load_fixture_weights(deer_b200.SequenceDEERModel(dropout=0.0), fx).to(DEV)
+    model.train()
+    batch = seq_inputs(m["B"], m["Ta"], m["Tv"], m["Tt"], seed=m["seed"])
+    out, loss = _run_composite(model, batch, ops.ENGINE_AUTO)
+    for k in ("audio_encoded", "video_encoded", "text_encoded", "fused_features"):
+        assert_close(out[k], fx.t(k), TOL, k)
+    for k in fx.keys("out:"):
+        assert_close(out[k[4:]], fx.t(k), TOL, k)
+    for k in fx.keys("loss:"):
+        if k.endswith("batch_size"):
+            continue
+        ref, got = float(fx.arrays[k]), float(loss[k[5:]])
+        assert abs(got - ref) <= TOL * max(abs(ref), 1e-2), (k, got, ref)
+    check_param_grads(model, fx, m["seed"], 5 * TOL)
+    # full gradient cosine against the oracle (float64 CPU) on the same inputs
+    sd = {k: (v.clone().requires_grad_(True) if v.dtype == torch.float64 else v) for k, v in fx.state_dict().items()}
+    _, oloss = O.sequence_model_loss(*batch[:5], batch[5], sd, training=True)
+    oloss["total_loss"].backward()
+    flat_c, flat_o = [], []
+    for n, p in model.named_parameters():
+        og = sd[n].grad
+        if og is None:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, n
+            continue
+        if float(og.abs().max()) == 0.0:
+            continue
+        c = cosine(p.grad, og)
+        assert c >= 0.999, (n, c)
+        flat_c.append(p.grad.flatten().double().cpu())
+        flat_o.append(og.flatten())
+    assert cosine(torch.cat(flat_c), torch.cat(flat_o)) >= 0.999
+
+
+def test_composite_ragged_and_eval_vs_oracle(golden):
+    """eval() mode (BatchNorm running statistics), ragged text masks, batch that is not a tile multiple."""
+    fx = golden("seq_full_b4")
+    model = load_fixture_weights(deer_b200.SequenceDEERModel(dropout=0.0), fx).to(DEV).eval()
+    batch = seq_inputs(7, 33, 9, 17, seed=99)
+    with torch.no_grad():
+        out = model(*[cu(t) for t in batch[:5]])
+    sd = fx.state_dict()
+    ref = O.sequence_model(*batch[:5], sd, training=False)
+    for k in ("mu_all", "uncertainty_all", "valence_nu", "arousal_alpha", "dominance_beta", "fused_features"):
+        assert_close(out[k], ref[k], TOL, k)

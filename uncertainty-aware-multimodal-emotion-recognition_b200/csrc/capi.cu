@@ -1,0 +1,61 @@
+// Library-level entry points: version, error string, launch counter, and the GEMM dispatcher.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace deer {
+
+std::atomic<long long> g_launches{0};
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int gemm_simt(const float* A, long long lda, int transA, const float* B, long long ldb, int transB, float* C,
+              long long ldc, int M, int N, int K, const float* bias, int act, float beta, int batch, long long sA,
+              long long sB, long long sC, long long sBias, cudaStream_t stream);
+// returns DEER_ERR_UNSUPPORTED (without setting an error) when the shape/alignment cannot use the TMA path
+int gemm_tcgen05(const float* A, long long lda, int transA, const float* B, long long ldb, int transB, float* C,
+                 long long ldc, int M, int N, int K, const float* bias, int act, float beta, int batch, long long sA,
+                 long long sB, long long sC, long long sBias, cudaStream_t stream);
+bool gemm_tcgen05_supported(const float* A, long long lda, int transA, const float* B, long long ldb, int transB,
+                            const float* C, long long ldc, int M, int N, int K, int batch, long long sA, long long sB,
+                            long long sC);
+
+}  // namespace deer
+
+using namespace deer;
+
+extern "C" {
+
+int deer_version(void) { return 100; }
+const char* deer_last_error(void) { return g_err; }
+long long deer_launch_count(void) { return g_launches.load(); }
+
+int deer_gemm(const float* A, long long lda, int transA, const float* B, long long ldb, int transB, float* C,
+              long long ldc, int M, int N, int K, const float* bias, int act, float beta, int batch, long long sA,
+              long long sB, long long sC, long long sBias, int engine, void* stream) {
+  DEER_CHECK_ARG(A && B && C, "gemm: null pointer");
+  DEER_CHECK_ARG(M > 0 && N > 0 && K > 0 && batch > 0, "gemm: empty shape");
+  DEER_CHECK_ARG(lda >= (transA ? M : K) && ldb >= (transB ? K : N) && ldc >= N, "gemm: leading dimension too small");
+  DEER_CHECK_ARG(act >= 0 && act <= 3, "gemm: bad activation");
+  DEER_CHECK_ARG(beta == 0.f || beta == 1.f, "gemm: beta must be 0 or 1");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (engine == DEER_GEMM_SIMT)
+    return gemm_simt(A, lda, transA, B, ldb, transB, C, ldc, M, N, K, bias, act, beta, batch, sA, sB, sC, sBias, st);
+  const bool ok = gemm_tcgen05_supported(A, lda, transA, B, ldb, transB, C, ldc, M, N, K, batch, sA, sB, sC);
+  if (engine == DEER_GEMM_TF32 && !ok) {
+    set_error("gemm: shape/alignment not supported by the tcgen05 engine (M=%d N=%d K=%d lda=%lld ldb=%lld)", M, N, K,
+              lda, ldb);
+    return DEER_ERR_UNSUPPORTED;
+  }
+  if (ok)
+    return gemm_tcgen05(A, lda, transA, B, ldb, transB, C, ldc, M, N, K, bias, act, beta, batch, sA, sB, sC, sBias, st);
+  return gemm_simt(A, lda, transA, B, ldb, transB, C, ldc, M, N, K, bias, act, beta, batch, sA, sB, sC, sBias, st);
+}
+
+}  // extern "C"

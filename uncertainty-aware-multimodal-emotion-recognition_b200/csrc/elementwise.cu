@@ -1,0 +1,413 @@
+// Memory-bound helpers: activation backward + bias gradient, dropout, scorer dot, layout moves, small combiners.
+// All are streaming kernels: coalesced along the innermost dimension, float4 where the shape allows,
+// grids sized from the data (>= 2 waves of 148 SMs at the benchmark shapes).
+#include "common.cuh"
+
+namespace deer {
+
+// ------------------------------------------------------------------ bias/act backward
+__global__ void __launch_bounds__(256) bias_act_bwd_kernel(const float* __restrict__ dy, long long ld_dy,
+                                                           const float* __restrict__ y, long long ld_y,
+                                                           float* __restrict__ dz, long long ld_dz,
+                                                           float* __restrict__ dbias, int M, int N, int act,
+                                                           int rows_per_block) {
+  __shared__ float red[8][33];
+  const int n = blockIdx.x * 32 + threadIdx.x;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(M, r0 + rows_per_block);
+  float s = 0.f;
+  if (n < N) {
+    for (int m = r0 + threadIdx.y; m < r1; m += 8) {
+      float g = dy[(long long)m * ld_dy + n];
+      if (act != DEER_ACT_NONE) g *= act_grad_from_out(y[(long long)m * ld_y + n], act);
+      if (dz) dz[(long long)m * ld_dz + n] = g;
+      s += g;
+    }
+  }
+  if (dbias) {
+    red[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && n < N) {
+      float t = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; i++) t += red[i][threadIdx.x];
+      atomicAdd(dbias + n, t);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ Philox-4x32-10
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0;
+    key.y += W1;
+  }
+  return ctr;
+}
+
+__global__ void __launch_bounds__(256) dropout_kernel(const float* __restrict__ x, float* __restrict__ y, long long n,
+                                                      float p, float scale, unsigned long long seed,
+                                                      unsigned long long offset,
+                                                      const unsigned long long* __restrict__ step_ptr) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // group of 4 elements
+  const long long i = q * 4;
+  if (i >= n) return;
+  const unsigned long long c = (unsigned long long)q + offset;
+  const unsigned long long st = step_ptr ? *step_ptr : 0ull;  // device-side step counter: new mask per graph replay
+  const uint4 r = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)st, (uint32_t)(st >> 32)),
+                                make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+  const uint32_t thr = (uint32_t)fminf(p * 4294967296.f, 4294967040.f);
+#pragma unroll
+  for (int j = 0; j < 4; j++)
+    if (i + j < n) y[i + j] = rr[j] >= thr ? x[i + j] * scale : 0.f;
+}
+
+// ------------------------------------------------------------------ scorer head: s[m] = h[m,:].w + b
+__global__ void __launch_bounds__(256) rowdot_fwd_kernel(const float* __restrict__ h, const float* __restrict__ w,
+                                                         const float* __restrict__ b, float* __restrict__ s,
+                                                         long long M, int N) {
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const float* hr = h + row * N;
+  float acc = 0.f;
+  for (int j = lane; j < N; j += 32) acc = fmaf(hr[j], w[j], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) s[row] = acc + b[0];
+}
+
+// dh[m,j] = ds[m]*w[j]; dw[j] += sum_m ds[m]*h[m,j]; db += sum_m ds[m]
+__global__ void __launch_bounds__(256) rowdot_bwd_kernel(const float* __restrict__ ds, const float* __restrict__ h,
+                                                         const float* __restrict__ w, float* __restrict__ dh,
+                                                         float* __restrict__ dw, float* __restrict__ db, long long M,
+                                                         int N, int rows_per_block) {
+  __shared__ float red[8][33];
+  const int n = blockIdx.x * 32 + threadIdx.x;
+  const long long r0 = (long long)blockIdx.y * rows_per_block;
+  const long long r1 = min(M, r0 + (long long)rows_per_block);
+  float s = 0.f, sb = 0.f;
+  const float wn = n < N ? w[n] : 0.f;
+  for (long long m = r0 + threadIdx.y; m < r1; m += 8) {
+    const float d = ds[m];
+    if (n < N) {
+      s = fmaf(d, h[m * N + n], s);
+      if (dh) dh[m * N + n] = d * wn;
+    }
+    sb += d;
+  }
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && n < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) t += red[i][threadIdx.x];
+    atomicAdd(dw + n, t);
+  }
+  if (blockIdx.x == 0) {  // block-uniform: one column-block also reduces db = sum_m ds[m]
+    __syncthreads();
+    red[threadIdx.y][threadIdx.x] = (threadIdx.x == 0) ? sb : 0.f;
+    __syncthreads();
+    if (threadIdx.y == 0 && threadIdx.x == 0) {
+      float t = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; i++) t += red[i][0];
+      atomicAdd(db, t);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ layout moves
+// y[t,b,:] = x[b,t,:]
+__global__ void __launch_bounds__(256) permute_bt_kernel(const float* __restrict__ x, float* __restrict__ y, int B,
+                                                         int T, int D) {
+  const long long total = (long long)B * T * D;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int d = (int)(i % D);
+    const long long r = i / D;  // output row = t*B + b
+    const int b = (int)(r % B);
+    const int t = (int)(r / B);
+    y[i] = x[((long long)b * T + t) * D + d];
+  }
+}
+
+__global__ void __launch_bounds__(256) rowscale_kernel(const float* __restrict__ x, const float* __restrict__ mask,
+                                                       float* __restrict__ y, long long M, int D) {
+  const long long total = M * D;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x)
+    y[i] = x[i] * mask[i / D];
+}
+
+// col[(b,t), k*C + c] = x[b, t+k-1, c]
+__global__ void __launch_bounds__(256) im2col3_kernel(const float* __restrict__ x, float* __restrict__ col, int B, int T,
+                                                      int C) {
+  const long long total = (long long)B * T * 3 * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long r = i / C;
+    const int k = (int)(r % 3);
+    r /= 3;
+    const int t = (int)(r % T);
+    const int b = (int)(r / T);
+    const int ts = t + k - 1;
+    col[i] = (ts >= 0 && ts < T) ? x[((long long)b * T + ts) * C + c] : 0.f;
+  }
+}
+// dx[b,t,c] = sum_k dcol[(b,t-k+1), k*C + c]
+__global__ void __launch_bounds__(256) col2im3_kernel(const float* __restrict__ dcol, float* __restrict__ dx, int B,
+                                                      int T, int C) {
+  const long long total = (long long)B * T * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long r = i / C;
+    const int t = (int)(r % T);
+    const int b = (int)(r / T);
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const int tt = t - k + 1;
+      if (tt >= 0 && tt < T) s += dcol[(((long long)b * T + tt) * 3 + k) * C + c];
+    }
+    dx[i] = s;
+  }
+}
+// dir 0: wk[o,k,i] = w[o,i,k];  dir 1: w[o,i,k] += wk[o,k,i]
+__global__ void __launch_bounds__(256) conv3_pack_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                         int Cout, int Cin, int dir) {
+  const long long total = (long long)Cout * Cin * 3;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    if (dir == 0) {  // i indexes wk [o,k,ci]
+      const int ci = (int)(i % Cin);
+      const int k = (int)((i / Cin) % 3);
+      const long long o = i / (3LL * Cin);
+      dst[i] = src[(o * Cin + ci) * 3 + k];
+    } else {  // i indexes w [o,ci,k]
+      const int k = (int)(i % 3);
+      const int ci = (int)((i / 3) % Cin);
+      const long long o = i / (3LL * Cin);
+      dst[i] += src[(o * 3 + k) * Cin + ci];
+    }
+  }
+}
+
+// ------------------------------------------------------------------ small combiners (pooled model)
+__global__ void __launch_bounds__(256) axpby_kernel(const float* __restrict__ x1, const float* __restrict__ x2,
+                                                    float* __restrict__ y, long long n, float a, float b) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = a * x1[i] + (x2 ? b * x2[i] : 0.f);
+}
+
+__global__ void __launch_bounds__(256) mix_fwd_kernel(const float* __restrict__ w, long long ldw,
+                                                      const float* __restrict__ u, long long ldu,
+                                                      const float* __restrict__ s, const float* __restrict__ c,
+                                                      float* __restrict__ out, long long M, int N) {
+  const long long total = M * N;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long m = i / N;
+    out[i] = w[m * ldw] * s[i] + (1.f - u[m * ldu]) * c[i];
+  }
+}
+// one warp per row
+__global__ void __launch_bounds__(256) mix_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ w,
+                                                      long long ldw, const float* __restrict__ u, long long ldu,
+                                                      const float* __restrict__ s, const float* __restrict__ c,
+                                                      float* __restrict__ dw, long long lddw, float* __restrict__ du,
+                                                      long long lddu, float* __restrict__ ds, float* __restrict__ dc,
+                                                      long long M, int N) {
+  const long long m = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (m >= M) return;
+  const float wm = w[m * ldw], um = u[m * ldu];
+  float aw = 0.f, au = 0.f;
+  for (int j = lane; j < N; j += 32) {
+    const long long i = m * N + j;
+    const float g = dout[i];
+    aw = fmaf(g, s[i], aw);
+    au = fmaf(g, c[i], au);
+    ds[i] = g * wm;
+    dc[i] = g * (1.f - um);
+  }
+  aw = warp_sum(aw);
+  au = warp_sum(au);
+  if (lane == 0) {
+    dw[m * lddw] = aw;
+    du[m * lddu] = -au;
+  }
+}
+
+__global__ void __launch_bounds__(256) gate_fwd_kernel(const float* __restrict__ g, const float* __restrict__ a,
+                                                       const float* __restrict__ b, float* __restrict__ out,
+                                                       long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = g[i] * a[i] + (1.f - g[i]) * b[i];
+}
+__global__ void __launch_bounds__(256) gate_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ g,
+                                                       const float* __restrict__ a, const float* __restrict__ b,
+                                                       float* __restrict__ dg, float* __restrict__ da,
+                                                       float* __restrict__ db, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float d = dout[i], gi = g[i];
+    dg[i] = d * (a[i] - b[i]);
+    da[i] = d * gi;
+    db[i] = d * (1.f - gi);
+  }
+}
+
+__global__ void __launch_bounds__(256) softmax_rows_fwd_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                               long long M, int N) {
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  float mx = -INFINITY;
+  for (int j = 0; j < N; j++) mx = fmaxf(mx, x[m * N + j]);
+  float s = 0.f;
+  for (int j = 0; j < N; j++) s += expf(x[m * N + j] - mx);
+  const float inv = 1.f / s;
+  for (int j = 0; j < N; j++) y[m * N + j] = expf(x[m * N + j] - mx) * inv;
+}
+__global__ void __launch_bounds__(256) softmax_rows_bwd_kernel(const float* __restrict__ dy,
+                                                               const float* __restrict__ y, float* __restrict__ dx,
+                                                               long long M, int N) {
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  float dot = 0.f;
+  for (int j = 0; j < N; j++) dot = fmaf(dy[m * N + j], y[m * N + j], dot);
+  for (int j = 0; j < N; j++) dx[m * N + j] = y[m * N + j] * (dy[m * N + j] - dot);
+}
+
+static inline int grid_for(long long n, int per_block = 256, int max_blocks = kNumSMs * 16) {
+  long long g = cdiv(n, per_block);
+  if (g > max_blocks) g = max_blocks;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace deer
+
+using namespace deer;
+
+extern "C" {
+
+int deer_bias_act_bwd(const float* dy, long long ld_dy, const float* y, long long ld_y, float* dz, long long ld_dz,
+                      float* dbias, int M, int N, int act, void* stream) {
+  DEER_CHECK_ARG(dy && M > 0 && N > 0, "bias_act_bwd: null/empty");
+  DEER_CHECK_ARG(act == DEER_ACT_NONE || y, "bias_act_bwd: act needs y");
+  const int rpb = 256;
+  dim3 grid((unsigned)cdiv(N, 32), (unsigned)cdiv(M, rpb));
+  DEER_LAUNCH(bias_act_bwd_kernel, grid, dim3(32, 8), 0, stream, dy, ld_dy, y, ld_y, dz, ld_dz, dbias, M, N, act, rpb);
+  return DEER_OK;
+}
+
+int deer_dropout(const float* x, float* y, long long n, float p, unsigned long long seed, unsigned long long offset,
+                 const unsigned long long* step_ptr, void* stream) {
+  DEER_CHECK_ARG(x && y && n > 0 && p >= 0.f && p < 1.f, "dropout: bad args");
+  const long long groups = cdiv(n, 4);
+  DEER_LAUNCH(dropout_kernel, (unsigned)cdiv(groups, 256), 256, 0, stream, x, y, n, p, 1.f / (1.f - p), seed, offset,
+              step_ptr);
+  return DEER_OK;
+}
+
+int deer_rowdot_fwd(const float* h, const float* w, const float* b, float* s, long long M, int N, void* stream) {
+  DEER_CHECK_ARG(h && w && b && s && M > 0 && N > 0, "rowdot_fwd: bad args");
+  DEER_LAUNCH(rowdot_fwd_kernel, (unsigned)cdiv(M, 8), 256, 0, stream, h, w, b, s, M, N);
+  return DEER_OK;
+}
+
+int deer_rowdot_bwd(const float* ds, const float* h, const float* w, float* dh, float* dw, float* db, long long M,
+                    int N, void* stream) {
+  DEER_CHECK_ARG(ds && h && w && dw && db && M > 0 && N > 0, "rowdot_bwd: bad args");
+  const int rpb = 256;
+  dim3 grid((unsigned)cdiv(N, 32), (unsigned)cdiv(M, rpb));
+  DEER_LAUNCH(rowdot_bwd_kernel, grid, dim3(32, 8), 0, stream, ds, h, w, dh, dw, db, M, N, rpb);
+  return DEER_OK;
+}
+
+int deer_permute_bt(const float* x, float* y, int B, int T, int D, void* stream) {
+  DEER_CHECK_ARG(x && y && B > 0 && T > 0 && D > 0, "permute_bt: bad args");
+  DEER_LAUNCH(permute_bt_kernel, grid_for((long long)B * T * D), 256, 0, stream, x, y, B, T, D);
+  return DEER_OK;
+}
+
+int deer_rowscale(const float* x, const float* mask, float* y, long long M, int D, void* stream) {
+  DEER_CHECK_ARG(x && mask && y && M > 0 && D > 0, "rowscale: bad args");
+  DEER_LAUNCH(rowscale_kernel, grid_for(M * D), 256, 0, stream, x, mask, y, M, D);
+  return DEER_OK;
+}
+
+int deer_im2col3(const float* x, float* col, int B, int T, int C, void* stream) {
+  DEER_CHECK_ARG(x && col && B > 0 && T > 0 && C > 0, "im2col3: bad args");
+  DEER_LAUNCH(im2col3_kernel, grid_for((long long)B * T * 3 * C), 256, 0, stream, x, col, B, T, C);
+  return DEER_OK;
+}
+
+int deer_col2im3(const float* dcol, float* dx, int B, int T, int C, void* stream) {
+  DEER_CHECK_ARG(dcol && dx && B > 0 && T > 0 && C > 0, "col2im3: bad args");
+  DEER_LAUNCH(col2im3_kernel, grid_for((long long)B * T * C), 256, 0, stream, dcol, dx, B, T, C);
+  return DEER_OK;
+}
+
+int deer_conv3_weight_pack(const float* w, float* wk, int Cout, int Cin, int dir, void* stream) {
+  DEER_CHECK_ARG(w && wk && Cout > 0 && Cin > 0, "conv3_weight_pack: bad args");
+  DEER_LAUNCH(conv3_pack_kernel, grid_for((long long)Cout * Cin * 3), 256, 0, stream, w, wk, Cout, Cin, dir);
+  return DEER_OK;
+}
+
+int deer_axpby(const float* x1, const float* x2, float* y, long long n, float a, float b, void* stream) {
+  DEER_CHECK_ARG(x1 && y && n > 0, "axpby: bad args");
+  DEER_LAUNCH(axpby_kernel, grid_for(n), 256, 0, stream, x1, x2, y, n, a, b);
+  return DEER_OK;
+}
+
+int deer_mix_fwd(const float* w, long long ldw, const float* u, long long ldu, const float* s, const float* c,
+                 float* out, long long M, int N, void* stream) {
+  DEER_CHECK_ARG(w && u && s && c && out && M > 0 && N > 0, "mix_fwd: bad args");
+  DEER_LAUNCH(mix_fwd_kernel, grid_for(M * N), 256, 0, stream, w, ldw, u, ldu, s, c, out, M, N);
+  return DEER_OK;
+}
+
+int deer_mix_bwd(const float* dout, const float* w, long long ldw, const float* u, long long ldu, const float* s,
+                 const float* c, float* dw, long long lddw, float* du, long long lddu, float* ds, float* dc,
+                 long long M, int N, void* stream) {
+  DEER_CHECK_ARG(dout && w && u && s && c && dw && du && ds && dc && M > 0 && N > 0, "mix_bwd: bad args");
+  DEER_LAUNCH(mix_bwd_kernel, (unsigned)cdiv(M, 8), 256, 0, stream, dout, w, ldw, u, ldu, s, c, dw, lddw, du, lddu, ds,
+              dc, M, N);
+  return DEER_OK;
+}
+
+int deer_gate_fwd(const float* g, const float* a, const float* b, float* out, long long n, void* stream) {
+  DEER_CHECK_ARG(g && a && b && out && n > 0, "gate_fwd: bad args");
+  DEER_LAUNCH(gate_fwd_kernel, grid_for(n), 256, 0, stream, g, a, b, out, n);
+  return DEER_OK;
+}
+
+int deer_gate_bwd(const float* dout, const float* g, const float* a, const float* b, float* dg, float* da, float* db,
+                  long long n, void* stream) {
+  DEER_CHECK_ARG(dout && g && a && b && dg && da && db && n > 0, "gate_bwd: bad args");
+  DEER_LAUNCH(gate_bwd_kernel, grid_for(n), 256, 0, stream, dout, g, a, b, dg, da, db, n);
+  return DEER_OK;
+}
+
+int deer_softmax_rows_fwd(const float* x, float* y, long long M, int N, void* stream) {
+  DEER_CHECK_ARG(x && y && M > 0 && N > 0 && N <= 32, "softmax_rows_fwd: bad args");
+  DEER_LAUNCH(softmax_rows_fwd_kernel, (unsigned)cdiv(M, 256), 256, 0, stream, x, y, M, N);
+  return DEER_OK;
+}
+
+int deer_softmax_rows_bwd(const float* dy, const float* y, float* dx, long long M, int N, void* stream) {
+  DEER_CHECK_ARG(dy && y && dx && M > 0 && N > 0 && N <= 32, "softmax_rows_bwd: bad args");
+  DEER_LAUNCH(softmax_rows_bwd_kernel, (unsigned)cdiv(M, 256), 256, 0, stream, dy, y, dx, M, N);
+  return DEER_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,447 @@
+// Normal-Inverse-Gamma head + DEER loss, fused.
+//
+//   head   (deer.py:90-98, complete_project.py:399-407): gamma=e0, nu=softplus(e1)+1e-6, alpha=softplus(e2)+1,
+//          beta=softplus(e3)+1e-6, aleatoric=beta/(alpha-1), epistemic=beta/(nu(alpha-1)).
+//   loss   (losses.py:72-348): per dimension  nll + reg_w*reg + kl_w*kl + ece_w*ece, cross-dimension consistency,
+//          divided by the number of dimensions.  Exact formulas: SURVEY.md appendix A.
+//
+// Two streaming phases over flat (sample,dim) elements, element e = b*D + d, one float4 of evidence each:
+//   phase 1 (deer_nig_loss_stats)  reads 16 B evidence + 4 B target, optionally writes 7x4 B NIG outputs, and
+//           reduces 35 statistics per dimension (sums for nll/reg/kl/mean-u, 10 ECE bins x {count, sum conf,
+//           sum |err|}).  Scalar sums live in registers across the grid-stride loop; ECE bins live in
+//           per-thread-private shared-memory columns (no atomics in the loop); one block reduction and
+//           35*D global atomics per block at the end.
+//   phase 2 (deer_nig_loss_finish) turns the statistics into the loss scalars (block 0) and streams the
+//           analytic gradient: reads 16+4 B, writes 16 B per element.
+// A data-parallel caller all-reduces `stats` between the phases (B_global = global batch).
+#include "common.cuh"
+
+namespace deer {
+
+constexpr int NSTAT = DEER_LOSS_NSTAT;  // 0 nll,1 reg,2 kl_alpha,3 kl_beta,4 sum u, 5..14 cnt, 15..24 conf, 25..34 err
+constexpr int LOSS_THREADS = 192;       // multiple of every supported D (1,2,3,4,6,8)
+constexpr int NBINS = 10;
+
+struct Nig {
+  float gamma, nu, alpha, beta;
+};
+
+__device__ __forceinline__ Nig load_nig(const float* __restrict__ evidence, const float* __restrict__ gamma,
+                                        const float* __restrict__ nu, const float* __restrict__ alpha,
+                                        const float* __restrict__ beta, long long e, int from_evidence, float4& raw) {
+  Nig p;
+  if (from_evidence) {
+    raw = reinterpret_cast<const float4*>(evidence)[e];
+    p.gamma = raw.x;
+    p.nu = softplus_f(raw.y) + 1e-6f;
+    p.alpha = softplus_f(raw.z) + 1.0f;
+    p.beta = softplus_f(raw.w) + 1e-6f;
+  } else {
+    raw = make_float4(0.f, 0.f, 0.f, 0.f);
+    p.gamma = gamma[e];
+    p.nu = nu[e];
+    p.alpha = alpha[e];
+    p.beta = beta[e];
+  }
+  return p;
+}
+
+__device__ __forceinline__ int ece_bin(float conf, const float* __restrict__ edges) {
+  // (edges[k], edges[k+1]]  (losses.py:207-215); -1 when outside every bin (NaN / conf<=0)
+  int k = -1;
+#pragma unroll
+  for (int i = 0; i < NBINS; i++)
+    if (conf > edges[i] && conf <= edges[i + 1]) k = i;
+  return k;
+}
+
+__global__ void __launch_bounds__(LOSS_THREADS) nig_loss_stats_kernel(
+    const float* __restrict__ evidence, const float* __restrict__ gamma, const float* __restrict__ nu,
+    const float* __restrict__ alpha, const float* __restrict__ beta, const float* __restrict__ targets,
+    const float* __restrict__ bin_edges, float* __restrict__ stats, float* __restrict__ nig_out, long long total, int D,
+    int from_evidence, float eps) {
+  __shared__ float bins[3 * NBINS][LOSS_THREADS];  // private column per thread: conflict-free, no atomics
+  __shared__ float sedges[NBINS + 1];
+  __shared__ float red[5][LOSS_THREADS];
+  const int tid = threadIdx.x;
+  if (tid <= NBINS) sedges[tid] = bin_edges[tid];
+#pragma unroll
+  for (int i = 0; i < 3 * NBINS; i++) bins[i][tid] = 0.f;
+  __syncthreads();
+  const float two_pi_eps = (float)(6.283185307179586 + (double)eps);
+  float a_nll = 0.f, a_reg = 0.f, a_kla = 0.f, a_klb = 0.f, a_u = 0.f;
+  const long long stride = (long long)gridDim.x * LOSS_THREADS;  // multiple of D -> dimension fixed per thread
+  for (long long e = (long long)blockIdx.x * LOSS_THREADS + tid; e < total; e += stride) {
+    float4 raw;
+    const Nig p = load_nig(evidence, gamma, nu, alpha, beta, e, from_evidence, raw);
+    const float y = targets[e];
+    const float err = y - p.gamma;
+    const float e2 = err * err;
+    const float S = p.beta + 0.5f * p.nu * e2 + eps;
+    const float lb = logf(p.beta + eps);
+    const float lp = 0.5f * logf(p.nu / two_pi_eps) + p.alpha * lb - lgammaf(p.alpha + eps) -
+                     (p.alpha + 0.5f) * logf(S);
+    a_nll -= lp;
+    a_reg += e2 * (2.f * p.beta + p.nu * e2);
+    const float am1 = p.alpha - 1.f;
+    a_kla += am1 * am1;
+    const float dl = lb - logf(1.f + eps);
+    a_klb += dl * dl;
+    const float u = p.beta / (am1 + eps);
+    a_u += p.beta / (am1 + 1e-8f);
+    const float conf = 1.f / (1.f + u);
+    const int k = ece_bin(conf, sedges);
+    if (k >= 0) {
+      bins[k][tid] += 1.f;
+      bins[NBINS + k][tid] += conf;
+      bins[2 * NBINS + k][tid] += fabsf(err);
+    }
+    if (nig_out) {
+      const float alea = p.beta / am1;
+      const float epis = p.beta / (p.nu * am1);
+      nig_out[e] = p.gamma;
+      nig_out[total + e] = p.nu;
+      nig_out[2 * total + e] = p.alpha;
+      nig_out[3 * total + e] = p.beta;
+      nig_out[4 * total + e] = alea;
+      nig_out[5 * total + e] = epis;
+      nig_out[6 * total + e] = alea + epis;
+    }
+  }
+  red[0][tid] = a_nll;
+  red[1][tid] = a_reg;
+  red[2][tid] = a_kla;
+  red[3][tid] = a_klb;
+  red[4][tid] = a_u;
+  __syncthreads();
+  // thread (d, s) for s < 35 sums the columns of threads whose dimension is d (tid % D == d)
+  const int first_e_dim = (int)(((long long)blockIdx.x * LOSS_THREADS) % D);
+  for (int w = tid; w < D * 35; w += LOSS_THREADS) {
+    const int d = w / 35, s = w % 35;
+    // threads t with (first_e_dim + t) % D == d
+    int t0 = (d - first_e_dim) % D;
+    if (t0 < 0) t0 += D;
+    float acc = 0.f;
+    const float* src = s < 5 ? red[s] : bins[s - 5];
+    for (int t = t0; t < LOSS_THREADS; t += D) acc += src[t];
+    if (acc != 0.f) atomicAdd(stats + d * NSTAT + s, acc);
+  }
+}
+
+struct DimCoef {
+  float sign[NBINS];  // ECE bin signs
+  float cross;        // d cross_dim / d ubar_d
+  float w;            // task weight
+};
+
+__global__ void __launch_bounds__(256) nig_loss_finish_kernel(
+    const float* __restrict__ evidence, const float* __restrict__ gamma, const float* __restrict__ nu,
+    const float* __restrict__ alpha, const float* __restrict__ beta, const float* __restrict__ targets,
+    const float* __restrict__ bin_edges, const float* __restrict__ stats, const float* __restrict__ task_weights,
+    float reg_w, float kl_w, float ece_w, float cross_w, float eps, long long total_local, long long B_global, int D,
+    int from_evidence, float grad_scale, float* __restrict__ losses, float* __restrict__ d_out) {
+  __shared__ DimCoef coef[8];
+  __shared__ float sedges[NBINS + 1];
+  __shared__ float ubar[8];
+  const int tid = threadIdx.x;
+  const float invN = 1.f / (float)B_global;
+  if (tid <= NBINS) sedges[tid] = bin_edges[tid];
+  if (tid < D) ubar[tid] = stats[tid * NSTAT + 4] * invN;
+  __syncthreads();
+  if (tid < D) {
+    const float* st = stats + tid * NSTAT;
+    float ece = 0.f;
+    for (int k = 0; k < NBINS; k++) {
+      const float cnt = st[5 + k], sc = st[15 + k], se = st[25 + k];
+      float sg = 0.f;
+      if (cnt > 0.f) {
+        const float diff = sc / cnt - (1.f - se / cnt);
+        ece += (cnt * invN) * fabsf(diff);
+        sg = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
+      }
+      coef[tid].sign[k] = sg;
+    }
+    float cs = 0.f;
+    for (int j = 0; j < D; j++)
+      if (j != tid) cs += ubar[tid] - ubar[j];
+    const int npairs = D * (D - 1) / 2;
+    coef[tid].cross = npairs > 0 ? 2.f * cs / (float)npairs : 0.f;
+    const float w = task_weights ? task_weights[tid] : 1.f;
+    coef[tid].w = w;
+    if (blockIdx.x == 0 && losses) {
+      const float nll = st[0] * invN, reg = st[1] * invN;
+      const float kl = st[2] * invN + 0.1f * st[3] * invN;
+      float* L = losses + tid * 5;
+      L[0] = nll + reg_w * reg + kl_w * kl + ece_w * ece;
+      L[1] = nll;
+      L[2] = reg;
+      L[3] = kl;
+      L[4] = ece;
+    }
+  }
+  __syncthreads();
+  if (blockIdx.x == 0 && tid == 0 && losses) {
+    float cd = 0.f;
+    for (int i = 0; i < D; i++)
+      for (int j = i + 1; j < D; j++) cd += (ubar[i] - ubar[j]) * (ubar[i] - ubar[j]);
+    const int npairs = D * (D - 1) / 2;
+    if (npairs > 0) cd /= (float)npairs;
+    float tot = 0.f;
+    for (int i = 0; i < D; i++) tot += coef[i].w * losses[i * 5];
+    if (cross_w > 0.f && D > 1) tot += cross_w * cd;
+    losses[D * 5] = cd;
+    losses[D * 5 + 1] = tot / (float)D;
+  }
+  if (d_out == nullptr) return;
+  const float invD = 1.f / (float)D;
+  const float base = grad_scale * invD * invN;
+  for (long long e = (long long)blockIdx.x * blockDim.x + tid; e < total_local;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int d = (int)(e % D);
+    float4 raw;
+    const Nig p = load_nig(evidence, gamma, nu, alpha, beta, e, from_evidence, raw);
+    const float y = targets[e];
+    const float err = y - p.gamma, e2 = err * err;
+    const float S = p.beta + 0.5f * p.nu * e2 + eps;
+    const float ah = p.alpha + 0.5f;
+    const float be = p.beta + eps;
+    const float w = coef[d].w;
+    // nll
+    float dg = -ah * p.nu * err / S;
+    float dn = -0.5f / p.nu + ah * e2 * 0.5f / S;
+    float da = -logf(be) + digamma_f(p.alpha + eps) + logf(S);
+    float db = -p.alpha / be + ah / S;
+    // reg
+    dg += reg_w * (-(4.f * p.beta * err + 4.f * p.nu * e2 * err));
+    dn += reg_w * e2 * e2;
+    db += reg_w * 2.f * e2;
+    // kl
+    const float am1 = p.alpha - 1.f;
+    da += kl_w * 2.f * am1;
+    db += kl_w * 0.2f * (logf(be) - logf(1.f + eps)) / be;
+    // ece
+    const float den = am1 + eps;
+    const float u = p.beta / den;
+    const float conf = 1.f / (1.f + u);
+    if (ece_w > 0.f) {
+      const int k = ece_bin(conf, sedges);
+      if (k >= 0) {
+        const float sg = coef[d].sign[k] * ece_w;
+        const float dconf_du = -conf * conf;
+        db += sg * dconf_du / den;
+        da += sg * dconf_du * (-u / den);
+        dg += sg * (err > 0.f ? -1.f : (err < 0.f ? 1.f : 0.f));
+      }
+    }
+    dg *= w;
+    dn *= w;
+    da *= w;
+    db *= w;
+    // cross-dimension consistency: d/d ubar_d * (1/N) * du/d(alpha,beta), u = beta/(alpha-1+1e-8)
+    if (cross_w > 0.f && D > 1) {
+      const float den8 = am1 + 1e-8f;
+      const float c = cross_w * coef[d].cross;
+      db += c / den8;
+      da += c * (-p.beta / (den8 * den8));
+    }
+    float4 o;
+    if (from_evidence) {
+      o.x = base * dg;
+      o.y = base * dn * softplus_grad_f(raw.y);
+      o.z = base * da * softplus_grad_f(raw.z);
+      o.w = base * db * softplus_grad_f(raw.w);
+    } else {
+      o = make_float4(base * dg, base * dn, base * da, base * db);
+    }
+    reinterpret_cast<float4*>(d_out)[e] = o;
+  }
+}
+
+// ------------------------------------------------------------------ stand-alone head
+__global__ void __launch_bounds__(256) nig_head_fwd_kernel(const float* __restrict__ evidence, float* __restrict__ mu,
+                                                           float* __restrict__ nu, float* __restrict__ alpha,
+                                                           float* __restrict__ beta, float* __restrict__ alea,
+                                                           float* __restrict__ epis, float* __restrict__ tot,
+                                                           long long N) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < N; e += (long long)gridDim.x * blockDim.x) {
+    const float4 r = reinterpret_cast<const float4*>(evidence)[e];
+    const float n = softplus_f(r.y) + 1e-6f, a = softplus_f(r.z) + 1.0f, b = softplus_f(r.w) + 1e-6f;
+    const float al = b / (a - 1.f), ep = b / (n * (a - 1.f));
+    mu[e] = r.x;
+    nu[e] = n;
+    alpha[e] = a;
+    beta[e] = b;
+    alea[e] = al;
+    epis[e] = ep;
+    tot[e] = al + ep;
+  }
+}
+
+__global__ void __launch_bounds__(256) nig_head_bwd_kernel(const float* __restrict__ evidence,
+                                                           const float* __restrict__ dmu, const float* __restrict__ dnu,
+                                                           const float* __restrict__ dalpha,
+                                                           const float* __restrict__ dbeta,
+                                                           const float* __restrict__ dalea,
+                                                           const float* __restrict__ depis,
+                                                           const float* __restrict__ dtot, float* __restrict__ dev,
+                                                           long long N) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < N; e += (long long)gridDim.x * blockDim.x) {
+    const float4 r = reinterpret_cast<const float4*>(evidence)[e];
+    const float n = softplus_f(r.y) + 1e-6f, a = softplus_f(r.z) + 1.0f, b = softplus_f(r.w) + 1e-6f;
+    const float am1 = a - 1.f;
+    const float gal = (dalea ? dalea[e] : 0.f) + (dtot ? dtot[e] : 0.f);  // grad wrt aleatoric
+    const float gep = (depis ? depis[e] : 0.f) + (dtot ? dtot[e] : 0.f);  // grad wrt epistemic
+    // aleatoric = b/am1 ; epistemic = b/(n*am1)
+    float gn = (dnu ? dnu[e] : 0.f) + gep * (-b / (n * n * am1));
+    float ga = (dalpha ? dalpha[e] : 0.f) + gal * (-b / (am1 * am1)) + gep * (-b / (n * am1 * am1));
+    float gb = (dbeta ? dbeta[e] : 0.f) + gal / am1 + gep / (n * am1);
+    float4 o;
+    o.x = dmu ? dmu[e] : 0.f;
+    o.y = gn * softplus_grad_f(r.y);
+    o.z = ga * softplus_grad_f(r.z);
+    o.w = gb * softplus_grad_f(r.w);
+    reinterpret_cast<float4*>(dev)[e] = o;
+  }
+}
+
+// ------------------------------------------------------------------ Amini-style loss (deer.py:111-195)
+__global__ void __launch_bounds__(256) amini_loss_kernel(const float* __restrict__ mu, const float* __restrict__ nu,
+                                                         const float* __restrict__ alpha,
+                                                         const float* __restrict__ beta,
+                                                         const float* __restrict__ targets, float ew, float kw,
+                                                         long long N, float* __restrict__ dparams,
+                                                         float* __restrict__ scratch) {
+  __shared__ float red[32];
+  float s_nll = 0.f, s_reg = 0.f, s_kl = 0.f, s_mse = 0.f;
+  const float invN = 1.f / (float)N;
+  const float PI = 3.14159265358979f;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < N; e += (long long)gridDim.x * blockDim.x) {
+    const float m = mu[e], n = nu[e], a = alpha[e], b = beta[e];
+    const float err = targets[e] - m, se = err * err;
+    const float S = b + n * se * 0.5f, ah = a + 0.5f;
+    const float lga = lgammaf(a), lgah = lgammaf(ah);
+    s_nll += 0.5f * logf(PI / n) - a * logf(2.f * b) + lga - lgah + ah * logf(S);
+    const float num = n * se + 2.f * b * (1.f + n), den = 2.f * n * (1.f + n);
+    s_reg += num / den;
+    const float kl = 0.5f * (n - 1.f) + a * logf(b) - lga + lgah - 0.5f * logf(2.f * PI * b);
+    s_kl += fmaxf(kl, 0.f);
+    s_mse += se;
+    if (dparams) {
+      const float psa = digamma_f(a), psah = digamma_f(ah);
+      float dm = ah * (-n * err) / S;
+      float dn = -0.5f / n + ah * se * 0.5f / S;
+      float da = -logf(2.f * b) + psa - psah + logf(S);
+      float db = -a / b + ah / S;
+      dm += ew * (-2.f * n * err / den);
+      dn += ew * ((se + 2.f * b) / den - num * (2.f + 4.f * n) / (den * den));
+      db += ew * (1.f / n);
+      if (kl > 0.f) {
+        dn += kw * 0.5f;
+        da += kw * (logf(b) - psa + psah);
+        db += kw * (a / b - 0.5f / b);
+      }
+      dparams[e] = dm * invN;
+      dparams[N + e] = dn * invN;
+      dparams[2 * N + e] = da * invN;
+      dparams[3 * N + e] = db * invN;
+    }
+  }
+  s_nll = block_sum(s_nll, red);
+  s_reg = block_sum(s_reg, red);
+  s_kl = block_sum(s_kl, red);
+  s_mse = block_sum(s_mse, red);
+  if (threadIdx.x == 0) {
+    atomicAdd(scratch + 0, s_nll);
+    atomicAdd(scratch + 1, s_reg);
+    atomicAdd(scratch + 2, s_kl);
+    atomicAdd(scratch + 3, s_mse);
+  }
+}
+__global__ void amini_finish_kernel(const float* scratch, float ew, float kw, long long N, float* losses) {
+  const float invN = 1.f / (float)N;
+  const float nll = scratch[0] * invN, reg = scratch[1] * invN, kl = scratch[2] * invN, mse = scratch[3] * invN;
+  losses[0] = nll + ew * reg + kw * kl;
+  losses[1] = nll;
+  losses[2] = reg;
+  losses[3] = kl;
+  losses[4] = mse;
+}
+
+static int stream_grid(long long n, int threads) {
+  long long g = cdiv(n, threads);
+  const long long cap = (long long)kNumSMs * 8;
+  if (g > cap) g = cap;
+  return (int)(g < 1 ? 1 : g);
+}
+
+}  // namespace deer
+
+using namespace deer;
+
+extern "C" {
+
+int deer_nig_head_fwd(const float* evidence, float* mu, float* nu, float* alpha, float* beta, float* aleatoric,
+                      float* epistemic, float* total, long long N, void* stream) {
+  DEER_CHECK_ARG(evidence && mu && nu && alpha && beta && aleatoric && epistemic && total && N > 0,
+                 "nig_head_fwd: bad args");
+  DEER_LAUNCH(nig_head_fwd_kernel, stream_grid(N, 256), 256, 0, stream, evidence, mu, nu, alpha, beta, aleatoric,
+              epistemic, total, N);
+  return DEER_OK;
+}
+
+int deer_nig_head_bwd(const float* evidence, const float* dmu, const float* dnu, const float* dalpha,
+                      const float* dbeta, const float* daleatoric, const float* depistemic, const float* dtotal,
+                      float* devidence, long long N, void* stream) {
+  DEER_CHECK_ARG(evidence && devidence && N > 0, "nig_head_bwd: bad args");
+  DEER_LAUNCH(nig_head_bwd_kernel, stream_grid(N, 256), 256, 0, stream, evidence, dmu, dnu, dalpha, dbeta, daleatoric,
+              depistemic, dtotal, devidence, N);
+  return DEER_OK;
+}
+
+int deer_nig_loss_stats(const float* evidence, const float* gamma, const float* nu, const float* alpha,
+                        const float* beta, const float* targets, const float* bin_edges, float* stats, float* nig_out,
+                        long long B, int D, int from_evidence, float eps, void* stream) {
+  DEER_CHECK_ARG(targets && bin_edges && stats && B > 0, "nig_loss_stats: bad args");
+  DEER_CHECK_ARG(from_evidence ? evidence != nullptr : (gamma && nu && alpha && beta), "nig_loss_stats: inputs");
+  if (D < 1 || D > 8 || LOSS_THREADS % D != 0) {
+    set_error("nig_loss_stats: D=%d unsupported (need a divisor of %d, <=8)", D, LOSS_THREADS);
+    return DEER_ERR_UNSUPPORTED;
+  }
+  const long long total = B * D;
+  DEER_LAUNCH(nig_loss_stats_kernel, stream_grid(total, LOSS_THREADS), LOSS_THREADS, 0, stream, evidence, gamma, nu,
+              alpha, beta, targets, bin_edges, stats, nig_out, total, D, from_evidence, eps);
+  return DEER_OK;
+}
+
+int deer_nig_loss_finish(const float* evidence, const float* gamma, const float* nu, const float* alpha,
+                         const float* beta, const float* targets, const float* bin_edges, const float* stats,
+                         const float* task_weights, float reg_w, float kl_w, float ece_w, float cross_w, float eps,
+                         long long B_local, long long B_global, int D, int from_evidence, float grad_scale,
+                         float* losses, float* d_out, void* stream) {
+  DEER_CHECK_ARG(targets && bin_edges && stats && B_local > 0 && B_global >= B_local, "nig_loss_finish: bad args");
+  DEER_CHECK_ARG(from_evidence ? evidence != nullptr : (gamma && nu && alpha && beta), "nig_loss_finish: inputs");
+  DEER_CHECK_ARG(losses || d_out, "nig_loss_finish: nothing to do");
+  if (D < 1 || D > 8) {
+    set_error("nig_loss_finish: D=%d unsupported", D);
+    return DEER_ERR_UNSUPPORTED;
+  }
+  const long long total = B_local * D;
+  DEER_LAUNCH(nig_loss_finish_kernel, stream_grid(total, 256), 256, 0, stream, evidence, gamma, nu, alpha, beta,
+              targets, bin_edges, stats, task_weights, reg_w, kl_w, ece_w, cross_w, eps, total, B_global, D,
+              from_evidence, grad_scale, losses, d_out);
+  return DEER_OK;
+}
+
+int deer_amini_loss(const float* mu, const float* nu, const float* alpha, const float* beta, const float* targets,
+                    float evidence_w, float kl_w, long long N, float* losses, float* dparams, float* scratch,
+                    void* stream) {
+  DEER_CHECK_ARG(mu && nu && alpha && beta && targets && losses && scratch && N > 0, "amini_loss: bad args");
+  cudaError_t e = cudaMemsetAsync(scratch, 0, 8 * sizeof(float), (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_status(e, "amini memset");
+  DEER_LAUNCH(amini_loss_kernel, stream_grid(N, 256), 256, 0, stream, mu, nu, alpha, beta, targets, evidence_w, kl_w, N,
+              dparams, scratch);
+  DEER_LAUNCH(amini_finish_kernel, 1, 1, 0, stream, scratch, evidence_w, kl_w, N, losses);
+  return DEER_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,804 @@
+"""torch.autograd.Function wrappers over the C ABI (include/deer_b200.h).
+
+PyTorch is plumbing here: it owns device memory, streams and the autograd tape; every floating-point
+operation on the path runs in a hand-written sm_100a kernel of libdeer_b200.so.  All functions require
+fp32 CUDA tensors and raise otherwise (no CPU / eager fallback).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import call, ptr
+
+ACT = {"none": 0, None: 0, "relu": 1, "tanh": 2, "sigmoid": 3}
+ENGINE_AUTO, ENGINE_SIMT, ENGINE_TF32 = 0, 1, 2
+
+_state = {"engine": ENGINE_AUTO, "lstm_engine": ENGINE_AUTO}
+
+
+def set_gemm_engine(engine: int):
+    """0 auto (tcgen05 where the shape allows), 1 fp32 SIMT everywhere, 2 force tcgen05 (raises if unsupported)."""
+    _state["engine"] = int(engine)
+
+
+def set_lstm_engine(engine: int):
+    _state["lstm_engine"] = int(engine)
+
+
+def _req(t: torch.Tensor, name: str):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.DeerError(f"deer_b200: `{name}` must be a CUDA tensor (no CPU fallback on this path)")
+    if t.dtype != torch.float32:
+        raise _lib.DeerError(f"deer_b200: `{name}` must be float32, got {t.dtype}")
+    return t
+
+
+def _rows2d(t: torch.Tensor):
+    """View t [..., K] as a 2-D row matrix without copying when rows are evenly strided; returns (tensor, M, K, ld)."""
+    K = t.shape[-1]
+    if t.dim() == 2 and t.stride(1) == 1 and t.stride(0) >= K:
+        return t, t.shape[0], K, t.stride(0)
+    t2 = t.reshape(-1, K)
+    if t2.stride(1) != 1 or (t2.shape[0] > 1 and t2.stride(0) < K):
+        t2 = t2.contiguous()
+    return t2, t2.shape[0], K, (t2.stride(0) if t2.shape[0] > 1 else K)
+
+
+def gemm(A, lda, transA, B, ldb, transB, C, ldc, M, N, K, bias=None, act=0, beta=0.0, batch=1, sA=0, sB=0, sC=0,
+         sBias=0, engine=None):
+    call("deer_gemm", ptr(A) if isinstance(A, torch.Tensor) else A, lda, int(transA),
+         ptr(B) if isinstance(B, torch.Tensor) else B, ldb, int(transB),
+         ptr(C) if isinstance(C, torch.Tensor) else C, ldc, M, N, K, ptr(bias), act, float(beta), batch, sA, sB, sC,
+         sBias, _state["engine"] if engine is None else engine)
+
+
+def _colw(w: torch.Tensor, k0: int, k1: int):
+    """Pointer/ld of the column block w[:, k0:k1] of a row-major weight."""
+    return w.data_ptr() + 4 * k0, w.stride(0)
+
+
+# ----------------------------------------------------------------------------------------------- Linear
+class _Linear(torch.autograd.Function):
+    """y = act(sum_i x_i W[:, blk_i]^T + b): nn.Linear applied to the (virtual) concatenation of the inputs."""
+
+    @staticmethod
+    def forward(ctx, w, b, act, n_in, *xs):
+        _req(w, "weight")
+        N, Ktot = w.shape
+        rows = []
+        k0 = 0
+        y = None
+        lead = xs[0].shape[:-1]
+        for i, x in enumerate(xs):
+            x2, M, K, ld = _rows2d(_req(x, "input"))
+            if y is None:
+                y = torch.empty((M, N), device=w.device, dtype=torch.float32)
+            last = i == len(xs) - 1
+            gemm(x2, ld, 0, w.data_ptr() + 4 * k0, w.stride(0), 1, y, N, M, N, K,
+                 bias=b if last else None, act=act if last else 0, beta=0.0 if i == 0 else 1.0)
+            rows.append((x2, ld, k0, K))
+            k0 += K
+        assert k0 == Ktot, f"input widths {k0} != weight in-features {Ktot}"
+        ctx.act = act
+        ctx.has_bias = b is not None
+        ctx.meta = [(ld, k, K) for (_, ld, k, K) in rows]
+        ctx.in_shapes = [x.shape for x in xs]
+        ctx.save_for_backward(w, y if act != 0 else None, *[r[0] for r in rows])
+        return y.view(*lead, N)
+
+    @staticmethod
+    def backward(ctx, dy):
+        w, y, *xs = ctx.saved_tensors
+        N, Ktot = w.shape
+        dy2, M, _, ld_dy = _rows2d(dy if dy.is_contiguous() else dy.contiguous())
+        db = torch.zeros(N, device=w.device, dtype=torch.float32) if (ctx.has_bias and ctx.needs_input_grad[1]) else None
+        if ctx.act != 0:
+            dz = torch.empty_like(dy2)
+            call("deer_bias_act_bwd", ptr(dy2), ld_dy, ptr(y), N, ptr(dz), N, ptr(db), M, N, ctx.act)
+        else:
+            dz = dy2
+            if db is not None:
+                call("deer_bias_act_bwd", ptr(dy2), ld_dy, None, 0, None, 0, ptr(db), M, N, 0)
+        dw = torch.zeros_like(w) if ctx.needs_input_grad[0] else None
+        dxs = []
+        for i, x2 in enumerate(xs):
+            ld, k0, K = ctx.meta[i]
+            if ctx.needs_input_grad[4 + i]:
+                dx = torch.empty((M, K), device=w.device, dtype=torch.float32)
+                gemm(dz, N, 0, w.data_ptr() + 4 * k0, w.stride(0), 0, dx, K, M, K, N)
+                dxs.append(dx.view(ctx.in_shapes[i]))
+            else:
+                dxs.append(None)
+            if dw is not None:
+                gemm(dz, N, 1, x2, ld, 0, dw.data_ptr() + 4 * k0, Ktot, N, K, M, beta=1.0)
+        return (dw, db, None, None, *dxs)
+
+
+def linear(x, w, b=None, act="none"):
+    xs = x if isinstance(x, (list, tuple)) else [x]
+    return _Linear.apply(w, b, ACT[act], len(xs), *xs)
+
+
+# ----------------------------------------------------------------------------------------------- LayerNorm
+class _LayerNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, g, b, eps):
+        x2, M, N, ld = _rows2d(_req(x, "input"))
+        if ld != N:
+            x2 = x2.contiguous()
+        y = torch.empty((M, N), device=x.device, dtype=torch.float32)
+        mean = torch.empty(M, device=x.device, dtype=torch.float32)
+        rstd = torch.empty(M, device=x.device, dtype=torch.float32)
+        call("deer_layernorm_fwd", ptr(x2), ptr(g), ptr(b), ptr(y), ptr(mean), ptr(rstd), M, N, float(eps))
+        ctx.save_for_backward(x2, g, mean, rstd)
+        ctx.shape = x.shape
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, g, mean, rstd = ctx.saved_tensors
+        M, N = x2.shape
+        dy2 = dy.reshape(M, N)
+        if not dy2.is_contiguous():
+            dy2 = dy2.contiguous()
+        dx = torch.empty_like(x2)
+        dg = torch.zeros_like(g)
+        db = torch.zeros_like(g)
+        call("deer_layernorm_bwd", ptr(dy2), ptr(x2), ptr(g), ptr(mean), ptr(rstd), ptr(dx), ptr(dg), ptr(db), M, N)
+        return dx.view(ctx.shape), dg, db, None
+
+
+def layer_norm(x, g, b, eps=1e-5):
+    return _LayerNorm.apply(x, g, b, eps)
+
+
+# ----------------------------------------------------------------------------------------------- Dropout
+_dropout_state = {"seed": 0x5EED, "offset": 0, "step": None}
+
+
+def manual_seed(seed: int):
+    _dropout_state["seed"] = int(seed)
+    _dropout_state["offset"] = 0
+
+
+def set_dropout_step_tensor(t: Optional[torch.Tensor]):
+    """int64 CUDA scalar the trainer increments once per step; mixed into the Philox counter so CUDA-graph replays
+    draw fresh masks.  None disables it."""
+    _dropout_state["step"] = t
+
+
+def begin_step():
+    """Restart the per-step element offsets (call once per forward so graph capture and eager agree)."""
+    _dropout_state["offset"] = 0
+
+
+class _Dropout(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, p, seed, offset):
+        xc = _req(x, "input").contiguous()
+        y = torch.empty_like(xc)
+        st = _dropout_state["step"]
+        call("deer_dropout", ptr(xc), ptr(y), xc.numel(), float(p), seed, offset, ptr(st))
+        ctx.p, ctx.seed, ctx.offset, ctx.step = p, seed, offset, st
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dyc = dy.contiguous()
+        dx = torch.empty_like(dyc)
+        call("deer_dropout", ptr(dyc), ptr(dx), dyc.numel(), float(ctx.p), ctx.seed, ctx.offset, ptr(ctx.step))
+        return dx, None, None, None
+
+
+def dropout(x, p: float, training: bool):
+    if not training or p <= 0.0:
+        return x
+    off = _dropout_state["offset"]
+    _dropout_state["offset"] = off + (x.numel() + 3) // 4
+    return _Dropout.apply(x, p, _dropout_state["seed"], off)
+
+
+# ----------------------------------------------------------------------------------------------- attention pooling
+class _RowDot(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, h, w, b):
+        h2, M, N, ld = _rows2d(_req(h, "hidden"))
+        if ld != N:
+            h2 = h2.contiguous()
+        s = torch.empty(M, device=h.device, dtype=torch.float32)
+        call("deer_rowdot_fwd", ptr(h2), ptr(w), ptr(b), ptr(s), M, N)
+        ctx.save_for_backward(h2, w)
+        ctx.shape = h.shape
+        return s.view(h.shape[:-1])
+
+    @staticmethod
+    def backward(ctx, ds):
+        h2, w = ctx.saved_tensors
+        M, N = h2.shape
+        dsc = ds.reshape(M).contiguous()
+        dh = torch.empty_like(h2)
+        dw = torch.zeros_like(w)
+        db = torch.zeros(1, device=h2.device, dtype=torch.float32)
+        call("deer_rowdot_bwd", ptr(dsc), ptr(h2), ptr(w), ptr(dh), ptr(dw), ptr(db), M, N)
+        return dh.view(ctx.shape), dw, db
+
+
+def rowdot(h, w, b):
+    """s[...] = h[..., :] . w + b   (w is the [1,N] weight of a Linear(N,1), b its [1] bias)."""
+    return _RowDot.apply(h, w, b)
+
+
+class _AttnPool(torch.autograd.Function):
+    """x [B,T,D] (any b/t strides, unit d stride), scores s [B,T] (any strides), mask [B,T] or None."""
+
+    @staticmethod
+    def forward(ctx, x, s, mask):
+        _req(x, "x"), _req(s, "scores")
+        B, T, D = x.shape
+        if x.stride(2) != 1:
+            x = x.contiguous()
+        m = None if mask is None else _req(mask, "mask").contiguous()
+        out = torch.empty((B, D), device=x.device, dtype=torch.float32)
+        wts = torch.empty((B, T), device=x.device, dtype=torch.float32)
+        call("deer_attn_pool_fwd", ptr(x), x.stride(0), x.stride(1), ptr(s), s.stride(0), s.stride(1), ptr(m), ptr(out),
+             ptr(wts), B, T, D)
+        ctx.save_for_backward(x, s, m, wts)
+        ctx.mark_non_differentiable(wts)
+        return out, wts
+
+    @staticmethod
+    def backward(ctx, dout, _dw):
+        x, s, m, wts = ctx.saved_tensors
+        B, T, D = x.shape
+        dx = torch.empty_strided(x.shape, x.stride(), device=x.device, dtype=torch.float32)
+        ds = torch.empty_strided(s.shape, s.stride(), device=x.device, dtype=torch.float32)
+        call("deer_attn_pool_bwd", ptr(dout.contiguous()), ptr(x), x.stride(0), x.stride(1), ptr(s), s.stride(0),
+             s.stride(1), ptr(m), ptr(wts), ptr(dx), ptr(ds), B, T, D, 0)
+        return dx, ds, None
+
+
+def attn_pool(x, s, mask=None):
+    return _AttnPool.apply(x, s, mask)
+
+
+class _RowScale(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, mask):
+        xc = _req(x, "x").contiguous()
+        m = _req(mask, "mask").contiguous()
+        D = xc.shape[-1]
+        y = torch.empty_like(xc)
+        call("deer_rowscale", ptr(xc), ptr(m), ptr(y), xc.numel() // D, D)
+        ctx.save_for_backward(m)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (m,) = ctx.saved_tensors
+        dyc = dy.contiguous()
+        D = dyc.shape[-1]
+        dx = torch.empty_like(dyc)
+        call("deer_rowscale", ptr(dyc), ptr(m), ptr(dx), dyc.numel() // D, D)
+        return dx, None
+
+
+def rowscale(x, mask):
+    return _RowScale.apply(x, mask)
+
+
+class _PermuteBT(torch.autograd.Function):
+    """[B,T,D] contiguous -> [T,B,D] contiguous."""
+
+    @staticmethod
+    def forward(ctx, x):
+        xc = _req(x, "x").contiguous()
+        B, T, D = xc.shape
+        y = torch.empty((T, B, D), device=x.device, dtype=torch.float32)
+        call("deer_permute_bt", ptr(xc), ptr(y), B, T, D)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dyc = dy.contiguous()
+        T, B, D = dyc.shape
+        dx = torch.empty((B, T, D), device=dy.device, dtype=torch.float32)
+        call("deer_permute_bt", ptr(dyc), ptr(dx), T, B, D)
+        return dx
+
+
+def to_time_major(x):
+    return _PermuteBT.apply(x)
+
+
+# ----------------------------------------------------------------------------------------------- BiLSTM layer
+class _BiLSTMLayer(torch.autograd.Function):
+    """One bidirectional nn.LSTM layer on a time-major input x [T,B,I] -> h [T,B,2H]."""
+
+    @staticmethod
+    def forward(ctx, x, wif, whf, bif, bhf, wir, whr, bir, bhr):
+        x = _req(x, "x").contiguous()
+        T, B, In = x.shape
+        H = whf.shape[1]
+        dev = x.device
+        keep = torch.is_grad_enabled() and any(t.requires_grad for t in (x, wif, whf, bif, bhf, wir, whr, bir, bhr))
+        gates = torch.empty((T, B, 2, 4 * H), device=dev, dtype=torch.float32)
+        bsum = torch.empty((2, 4 * H), device=dev, dtype=torch.float32)
+        call("deer_axpby", ptr(bif), ptr(bhf), bsum.data_ptr(), 4 * H, 1.0, 1.0)
+        call("deer_axpby", ptr(bir), ptr(bhr), bsum.data_ptr() + 16 * H, 4 * H, 1.0, 1.0)
+        M = T * B
+        for d, wi in enumerate((wif, wir)):
+            gemm(x, In, 0, wi, wi.stride(0), 1, gates.data_ptr() + 16 * H * d, 8 * H, M, 4 * H, In,
+                 bias=bsum[d])
+        h = torch.empty((T, B, 2 * H), device=dev, dtype=torch.float32)
+        whf_c, whr_c = whf.contiguous(), whr.contiguous()
+        if keep:
+            c_all = torch.empty((T, B, 2, H), device=dev, dtype=torch.float32)
+            call("deer_lstm_fwd", ptr(gates), ptr(whf_c), ptr(whr_c), ptr(h), ptr(c_all), None, T, B, H,
+                 _state["lstm_engine"])
+            ctx.save_for_backward(x, wif, whf_c, wir, whr_c, gates, c_all, h)
+        else:
+            c_work = torch.empty((B, 2, H), device=dev, dtype=torch.float32)
+            call("deer_lstm_fwd", ptr(gates), ptr(whf_c), ptr(whr_c), ptr(h), None, ptr(c_work), T, B, H,
+                 _state["lstm_engine"])
+        ctx.dims = (T, B, In, H)
+        return h
+
+    @staticmethod
+    def backward(ctx, dh):
+        x, wif, whf, wir, whr, gates, c_all, h = ctx.saved_tensors
+        T, B, In, H = ctx.dims
+        dev = x.device
+        dh = dh.contiguous()
+        dh_work = torch.empty((B, 2, H), device=dev, dtype=torch.float32)
+        dc_work = torch.empty((B, 2, H), device=dev, dtype=torch.float32)
+        # gates is consumed: it becomes the pre-activation gradient buffer [T,B,2,4H]
+        call("deer_lstm_bwd", ptr(gates), ptr(whf), ptr(whr), ptr(c_all), ptr(dh), ptr(dh_work), ptr(dc_work), T, B, H,
+             _state["lstm_engine"])
+        M = T * B
+        G = 4 * H
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty((T, B, In), device=dev, dtype=torch.float32)
+            for d, wi in enumerate((wif, wir)):
+                gemm(gates.data_ptr() + 4 * G * d, 2 * G, 0, wi, wi.stride(0), 0, dx, In, M, In, G,
+                     beta=0.0 if d == 0 else 1.0)
+        grads = []
+        for d, (wi, wh) in enumerate(((wif, whf), (wir, whr))):
+            gp = gates.data_ptr() + 4 * G * d
+            dwi = torch.zeros_like(wi)
+            gemm(gp, 2 * G, 1, x, In, 0, dwi, In, G, In, M, beta=1.0)
+            dwh = torch.zeros_like(wh)
+            if T > 1:
+                Mr = (T - 1) * B
+                if d == 0:   # rows t=1.. pair with h[t-1]
+                    gemm(gp + 4 * B * 2 * G, 2 * G, 1, h.data_ptr(), 2 * H, 0, dwh, H, G, H, Mr, beta=1.0)
+                else:        # rows t=..T-2 pair with h[t+1]
+                    gemm(gp, 2 * G, 1, h.data_ptr() + 4 * (B * 2 * H + H), 2 * H, 0, dwh, H, G, H, Mr, beta=1.0)
+            db = torch.zeros(G, device=dev, dtype=torch.float32)
+            call("deer_bias_act_bwd", gp, 2 * G, None, 0, None, 0, ptr(db), M, G, 0)
+            grads.append((dwi, dwh, db))
+        (dwif, dwhf, dbf), (dwir, dwhr, dbr) = grads
+        return dx, dwif, dwhf, dbf, dbf, dwir, dwhr, dbr, dbr
+
+
+def bilstm_layer(x_tm, wif, whf, bif, bhf, wir, whr, bir, bhr):
+    return _BiLSTMLayer.apply(x_tm, wif, whf, bif, bhf, wir, whr, bir, bhr)
+
+
+# ----------------------------------------------------------------------------------------------- Conv1d(k=3) + BN
+class _Conv1dK3(torch.autograd.Function):
+    """nn.Conv1d(Cin,Cout,3,padding=1) on channels-last x [B,T,Cin] -> [B,T,Cout]; w [Cout,Cin,3]."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        x = _req(x, "x").contiguous()
+        B, T, Cin = x.shape
+        Cout = w.shape[0]
+        col = torch.empty((B * T, 3 * Cin), device=x.device, dtype=torch.float32)
+        call("deer_im2col3", ptr(x), ptr(col), B, T, Cin)
+        wk = torch.empty((Cout, 3 * Cin), device=x.device, dtype=torch.float32)
+        call("deer_conv3_weight_pack", ptr(w.contiguous()), ptr(wk), Cout, Cin, 0)
+        y = torch.empty((B, T, Cout), device=x.device, dtype=torch.float32)
+        gemm(col, 3 * Cin, 0, wk, 3 * Cin, 1, y, Cout, B * T, Cout, 3 * Cin, bias=b)
+        ctx.save_for_backward(col, wk)
+        ctx.dims = (B, T, Cin, Cout)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        col, wk = ctx.saved_tensors
+        B, T, Cin, Cout = ctx.dims
+        dy = dy.contiguous()
+        M = B * T
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dcol = torch.empty_like(col)
+            gemm(dy, Cout, 0, wk, 3 * Cin, 0, dcol, 3 * Cin, M, 3 * Cin, Cout)
+            dx = torch.empty((B, T, Cin), device=dy.device, dtype=torch.float32)
+            call("deer_col2im3", ptr(dcol), ptr(dx), B, T, Cin)
+        dwk = torch.zeros_like(wk)
+        gemm(dy, Cout, 1, col, 3 * Cin, 0, dwk, 3 * Cin, Cout, 3 * Cin, M, beta=1.0)
+        dw = torch.zeros((Cout, Cin, 3), device=dy.device, dtype=torch.float32)
+        call("deer_conv3_weight_pack", ptr(dwk), ptr(dw), Cout, Cin, 1)
+        db = torch.zeros(Cout, device=dy.device, dtype=torch.float32)
+        call("deer_bias_act_bwd", ptr(dy), Cout, None, 0, None, 0, ptr(db), M, Cout, 0)
+        return dx, dw, db
+
+
+def conv1d_k3(x, w, b):
+    return _Conv1dK3.apply(x, w, b)
+
+
+class _BNReLU(torch.autograd.Function):
+    """nn.BatchNorm1d (channels-last rows) followed by ReLU."""
+
+    @staticmethod
+    def forward(ctx, x, g, b, running_mean, running_var, nbt, training, momentum, eps):
+        x = _req(x, "x").contiguous()
+        C = x.shape[-1]
+        M = x.numel() // C
+        y = torch.empty_like(x)
+        if training:
+            stats = torch.empty((2, C), device=x.device, dtype=torch.float32)
+            call("deer_bn_stats", ptr(x), ptr(stats), M, C)
+            call("deer_bn_update_running", ptr(stats), ptr(running_mean), ptr(running_var),
+                 None if nbt is None else nbt.data_ptr(), M, C, float(momentum))
+            mean, var = stats[0], stats[1]
+        else:
+            mean, var = running_mean, running_var
+        call("deer_bn_relu_fwd", ptr(x), ptr(mean), ptr(var), ptr(g), ptr(b), ptr(y), M, C, float(eps))
+        ctx.save_for_backward(x, y, mean.clone() if not training else mean, var.clone() if not training else var, g)
+        ctx.cfg = (M, C, float(eps), bool(training))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y, mean, var, g = ctx.saved_tensors
+        M, C, eps, training = ctx.cfg
+        dy = dy.contiguous()
+        dx = torch.empty_like(x)
+        dg = torch.zeros_like(g)
+        db = torch.zeros_like(g)
+        scratch = torch.empty((2, C), device=x.device, dtype=torch.float32)
+        call("deer_bn_relu_bwd", ptr(dy), ptr(x), ptr(y), ptr(mean), ptr(var), ptr(g), ptr(dx), ptr(dg), ptr(db),
+             ptr(scratch), M, C, eps, int(training))
+        return dx, dg, db, None, None, None, None, None, None
+
+
+def batchnorm_relu(x, g, b, running_mean, running_var, nbt, training, momentum=0.1, eps=1e-5):
+    return _BNReLU.apply(x, g, b, running_mean, running_var, nbt, training, momentum, eps)
+
+
+# ----------------------------------------------------------------------------------------------- 2-token MHA core
+class _MHA2(torch.autograd.Function):
+    """qkv [B,2,3E] (packed q|k|v per token) -> (token-mean context [B,E], head-averaged weights [B,2,2])."""
+
+    @staticmethod
+    def forward(ctx, qkv, heads):
+        qkv = _req(qkv, "qkv").contiguous()
+        B, two, E3 = qkv.shape
+        assert two == 2
+        E = E3 // 3
+        cmean = torch.empty((B, E), device=qkv.device, dtype=torch.float32)
+        attw = torch.empty((B, 2, 2), device=qkv.device, dtype=torch.float32)
+        probs = torch.empty((B, heads, 2, 2), device=qkv.device, dtype=torch.float32)
+        call("deer_mha2_fwd", ptr(qkv), None, ptr(cmean), ptr(attw), ptr(probs), B, E, heads)
+        ctx.save_for_backward(qkv, probs)
+        ctx.heads = heads
+        return cmean, attw
+
+    @staticmethod
+    def backward(ctx, dcmean, dattw):
+        qkv, probs = ctx.saved_tensors
+        B, _, E3 = qkv.shape
+        dqkv = torch.empty_like(qkv)
+        call("deer_mha2_bwd", None, ptr(dcmean.contiguous()), ptr(dattw.contiguous()) if dattw is not None else None,
+             ptr(qkv), ptr(probs), ptr(dqkv), B, E3 // 3, ctx.heads)
+        return dqkv, None
+
+
+def mha2_core(qkv, heads):
+    return _MHA2.apply(qkv, heads)
+
+
+# ----------------------------------------------------------------------------------------------- grouped Linear
+class _GroupedLinear(torch.autograd.Function):
+    """out[:, g, :] = act(x_g W_g^T + b_g) for g in range(G); out [M,G,N].  Inputs may be strided row views
+    (e.g. slices out[:, g, :] of a previous grouped output), so chains of per-head layers need no copies."""
+
+    @staticmethod
+    def forward(ctx, act, G, *args):
+        ws, bs, xs = args[:G], args[G:2 * G], args[2 * G:]
+        N = ws[0].shape[0]
+        rows = [_rows2d(_req(x, "input")) for x in xs]
+        M = rows[0][1]
+        out = torch.empty((M, G, N), device=ws[0].device, dtype=torch.float32)
+        for g in range(G):
+            x2, _, K, ld = rows[g]
+            gemm(x2, ld, 0, ws[g], ws[g].stride(0), 1, out.data_ptr() + 4 * g * N, G * N, M, N, K, bias=bs[g], act=act)
+        ctx.act, ctx.G = act, G
+        ctx.meta = [(r[3], r[2]) for r in rows]
+        ctx.in_shapes = [x.shape for x in xs]
+        ctx.save_for_backward(out if act != 0 else None, *ws, *[r[0] for r in rows])
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        G, act = ctx.G, ctx.act
+        saved = ctx.saved_tensors
+        out, ws, xs = saved[0], saved[1:1 + G], saved[1 + G:]
+        dout = dout.contiguous()
+        M, _, N = dout.shape
+        dev = dout.device
+        dbs = [torch.zeros(N, device=dev, dtype=torch.float32) if ctx.needs_input_grad[2 + G + g] else None
+               for g in range(G)]
+        dz = torch.empty_like(dout) if act != 0 else dout
+        for g in range(G):
+            off = 4 * g * N
+            if act != 0:
+                call("deer_bias_act_bwd", dout.data_ptr() + off, G * N, out.data_ptr() + off, G * N,
+                     dz.data_ptr() + off, G * N, ptr(dbs[g]), M, N, act)
+            elif dbs[g] is not None:
+                call("deer_bias_act_bwd", dout.data_ptr() + off, G * N, None, 0, None, 0, ptr(dbs[g]), M, N, 0)
+        dws, dxs = [], []
+        for g in range(G):
+            ld, K = ctx.meta[g]
+            zp = dz.data_ptr() + 4 * g * N
+            if ctx.needs_input_grad[2 + g]:
+                dw = torch.zeros_like(ws[g])
+                gemm(zp, G * N, 1, xs[g], ld, 0, dw, K, N, K, M, beta=1.0)
+                dws.append(dw)
+            else:
+                dws.append(None)
+            if ctx.needs_input_grad[2 + 2 * G + g]:
+                dx = torch.empty((M, K), device=dev, dtype=torch.float32)
+                gemm(zp, G * N, 0, ws[g], ws[g].stride(0), 0, dx, K, M, K, N)
+                dxs.append(dx.view(ctx.in_shapes[g]))
+            else:
+                dxs.append(None)
+        return (None, None, *dws, *dbs, *dxs)
+
+
+def grouped_linear(xs: Sequence[torch.Tensor], ws: Sequence[torch.Tensor], bs: Sequence[torch.Tensor], act="none"):
+    G = len(ws)
+    return _GroupedLinear.apply(ACT[act], G, *ws, *bs, *xs)
+
+
+# ----------------------------------------------------------------------------------------------- NIG head + losses
+class _NigHead(torch.autograd.Function):
+    """evidence [...,4] -> stacked [7, ...] = (mu, nu, alpha, beta, aleatoric, epistemic, total)."""
+
+    @staticmethod
+    def forward(ctx, evidence):
+        e = _req(evidence, "evidence").contiguous()
+        n = e.numel() // 4
+        out = torch.empty((7, n), device=e.device, dtype=torch.float32)
+        p = [out[i].data_ptr() for i in range(7)]
+        call("deer_nig_head_fwd", ptr(e), *p, n)
+        ctx.save_for_backward(e)
+        return out.view(7, *e.shape[:-1])
+
+    @staticmethod
+    def backward(ctx, dout):
+        (e,) = ctx.saved_tensors
+        n = e.numel() // 4
+        d = dout.contiguous().view(7, n)
+        de = torch.empty_like(e)
+        call("deer_nig_head_bwd", ptr(e), *[d[i].data_ptr() for i in range(7)], ptr(de), n)
+        return de
+
+
+def nig_head(evidence):
+    return _NigHead.apply(evidence)
+
+
+_edges_cache = {}
+
+
+def ece_edges(device):
+    """torch.linspace(0,1,11) exactly as losses.py:207 builds it (computed once on the host)."""
+    key = str(device)
+    if key not in _edges_cache:
+        _edges_cache[key] = torch.linspace(0, 1, 11, dtype=torch.float32).to(device)
+    return _edges_cache[key]
+
+
+def nig_loss_raw(evidence, params, targets, *, weights=(0.1, 0.01, 0.05, 0.05), eps=1e-8, task_weights=None,
+                 want_nig=False, want_grad=True, grad_scale=1.0, stats_hook=None, global_batch=None):
+    """Fused DEER multitask loss on either raw evidence [B,D,4] or params=(gamma,nu,alpha,beta) each [B,D].
+
+    Returns (losses [5D+2], grad, nig_out [7,B,D] or None, stats [D,40]).  `stats_hook(stats)` runs between the two
+    phases (the data-parallel trainer all-reduces the statistics there)."""
+    from_ev = evidence is not None
+    t = _req(targets, "targets").contiguous()
+    B, D = t.shape
+    dev = t.device
+    if from_ev:
+        e = _req(evidence, "evidence").contiguous()
+        g = n = a = b = None
+    else:
+        e = None
+        g, n, a, b = [_req(p, "nig param").contiguous() for p in params]
+    stats = torch.zeros((D, 40), device=dev, dtype=torch.float32)
+    nig_out = torch.empty((7, B, D), device=dev, dtype=torch.float32) if want_nig else None
+    edges = ece_edges(dev)
+    call("deer_nig_loss_stats", ptr(e), ptr(g), ptr(n), ptr(a), ptr(b), ptr(t), ptr(edges), ptr(stats), ptr(nig_out),
+         B, D, int(from_ev), float(eps))
+    if stats_hook is not None:
+        stats_hook(stats)
+    losses = torch.empty(5 * D + 2, device=dev, dtype=torch.float32)
+    grad = torch.empty((B, D, 4), device=dev, dtype=torch.float32) if want_grad else None
+    tw = None if task_weights is None else torch.as_tensor(task_weights, dtype=torch.float32, device=dev)
+    rw, kw, ew, cw = weights
+    call("deer_nig_loss_finish", ptr(e), ptr(g), ptr(n), ptr(a), ptr(b), ptr(t), ptr(edges), ptr(stats), ptr(tw),
+         float(rw), float(kw), float(ew), float(cw), float(eps), B, int(global_batch or B), D, int(from_ev),
+         float(grad_scale), ptr(losses), ptr(grad))
+    return losses, grad, nig_out, stats
+
+
+class _MultiTaskLoss(torch.autograd.Function):
+    """losses.MultiTaskDEERLoss on contiguous [B,D] NIG parameter arrays.  Only `total` carries gradient."""
+
+    @staticmethod
+    def forward(ctx, gamma, nu, alpha, beta, targets, weights, eps, task_weights):
+        losses, grad, _, _ = nig_loss_raw(None, (gamma, nu, alpha, beta), targets, weights=weights, eps=eps,
+                                          task_weights=task_weights)
+        ctx.save_for_backward(grad)
+        return losses
+
+    @staticmethod
+    def backward(ctx, dlosses):
+        (grad,) = ctx.saved_tensors  # [B,D,4] = d total / d(gamma,nu,alpha,beta)
+        D = grad.shape[1]
+        s = dlosses[5 * D + 1]
+        g = grad * s
+        return g[..., 0], g[..., 1], g[..., 2], g[..., 3], None, None, None, None
+
+
+def multitask_loss(gamma, nu, alpha, beta, targets, weights=(0.1, 0.01, 0.05, 0.05), eps=1e-8, task_weights=None):
+    return _MultiTaskLoss.apply(gamma, nu, alpha, beta, targets, weights, eps, task_weights)
+
+
+class _FusedHeadLoss(torch.autograd.Function):
+    """evidence [B,D,4] + targets -> (nig_out [7,B,D] (non-differentiable), losses [5D+2]); head and loss fused."""
+
+    @staticmethod
+    def forward(ctx, evidence, targets, weights, eps, task_weights):
+        losses, grad, nig_out, _ = nig_loss_raw(evidence, None, targets, weights=weights, eps=eps,
+                                                task_weights=task_weights, want_nig=True)
+        ctx.save_for_backward(grad)
+        ctx.mark_non_differentiable(nig_out)
+        return nig_out, losses
+
+    @staticmethod
+    def backward(ctx, _dnig, dlosses):
+        (grad,) = ctx.saved_tensors
+        D = grad.shape[1]
+        return grad * dlosses[5 * D + 1], None, None, None, None
+
+
+def fused_head_loss(evidence, targets, weights=(0.1, 0.01, 0.05, 0.05), eps=1e-8, task_weights=None):
+    return _FusedHeadLoss.apply(evidence, targets, weights, eps, task_weights)
+
+
+class _AminiLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mu, nu, alpha, beta, targets, ew, kw):
+        args = [_req(t, "nig").contiguous() for t in (mu, nu, alpha, beta)]
+        t = _req(targets, "targets").contiguous()
+        n = t.numel()
+        dev = t.device
+        losses = torch.empty(5, device=dev, dtype=torch.float32)
+        dparams = torch.empty((4, n), device=dev, dtype=torch.float32)
+        scratch = torch.empty(8, device=dev, dtype=torch.float32)
+        call("deer_amini_loss", *[ptr(a) for a in args], ptr(t), float(ew), float(kw), n, ptr(losses), ptr(dparams),
+             ptr(scratch))
+        ctx.save_for_backward(dparams)
+        ctx.shape = mu.shape
+        return losses
+
+    @staticmethod
+    def backward(ctx, dl):
+        (dp,) = ctx.saved_tensors
+        g = dp * dl[0]
+        sh = ctx.shape
+        return g[0].view(sh), g[1].view(sh), g[2].view(sh), g[3].view(sh), None, None, None
+
+
+def amini_loss(mu, nu, alpha, beta, targets, evidence_weight=1.0, kl_weight=1.0):
+    return _AminiLoss.apply(mu, nu, alpha, beta, targets, evidence_weight, kl_weight)
+
+
+# ----------------------------------------------------------------------------------------------- small combiners
+class _Mix(torch.autograd.Function):
+    """out = w[:,None]*s + (1-u[:,None])*c with w,u column views (complete_project.py:282-293)."""
+
+    @staticmethod
+    def forward(ctx, w, u, s, c):
+        s, c = _req(s, "s").contiguous(), _req(c, "c").contiguous()
+        M, N = s.shape
+        out = torch.empty_like(s)
+        call("deer_mix_fwd", ptr(w), w.stride(0), ptr(u), u.stride(0), ptr(s), ptr(c), ptr(out), M, N)
+        ctx.save_for_backward(w, u, s, c)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        w, u, s, c = ctx.saved_tensors
+        M, N = s.shape
+        dw = torch.empty(M, device=s.device, dtype=torch.float32)
+        du = torch.empty(M, device=s.device, dtype=torch.float32)
+        ds, dc = torch.empty_like(s), torch.empty_like(c)
+        call("deer_mix_bwd", ptr(dout.contiguous()), ptr(w), w.stride(0), ptr(u), u.stride(0), ptr(s), ptr(c), ptr(dw),
+             1, ptr(du), 1, ptr(ds), ptr(dc), M, N)
+        return dw.view(w.shape), du.view(u.shape), ds, dc
+
+
+def mix(w, u, s, c):
+    return _Mix.apply(w, u, s, c)
+
+
+class _Gate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, g, a, b):
+        g, a, b = [_req(t, "gate").contiguous() for t in (g, a, b)]
+        out = torch.empty_like(a)
+        call("deer_gate_fwd", ptr(g), ptr(a), ptr(b), ptr(out), a.numel())
+        ctx.save_for_backward(g, a, b)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        g, a, b = ctx.saved_tensors
+        dg, da, db = torch.empty_like(g), torch.empty_like(a), torch.empty_like(b)
+        call("deer_gate_bwd", ptr(dout.contiguous()), ptr(g), ptr(a), ptr(b), ptr(dg), ptr(da), ptr(db), a.numel())
+        return dg, da, db
+
+
+def gate(g, a, b):
+    return _Gate.apply(g, a, b)
+
+
+class _SoftmaxRows(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _req(x, "x").contiguous()
+        M, N = x.shape
+        y = torch.empty_like(x)
+        call("deer_softmax_rows_fwd", ptr(x), ptr(y), M, N)
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        M, N = y.shape
+        dx = torch.empty_like(y)
+        call("deer_softmax_rows_bwd", ptr(dy.contiguous()), ptr(y), ptr(dx), M, N)
+        return dx
+
+
+def softmax_rows(x):
+    return _SoftmaxRows.apply(x)
+
+
+class _Add(torch.autograd.Function):
+    """a + b through deer_axpby (residual connections, complete_project.py:73)."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        a, b = _req(a, "a").contiguous(), _req(b, "b").contiguous()
+        y = torch.empty_like(a)
+        call("deer_axpby", ptr(a), ptr(b), ptr(y), a.numel(), 1.0, 1.0)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        return dy, dy
+
+
+def add(a, b):
+    return _Add.apply(a, b)

@@ -1,0 +1,59 @@
+"""The sequence composite named by BASELINE.json `north_star`: audio BiLSTM encoder (84-D x T frames), video (256-D
+x F) and text (768-D x L) feature encoders, hierarchical attention fusion, evidential NIG head for valence / arousal
+/ dominance, DEER multitask loss.  The reference never wires these modules together itself;
+the wiring below follows its call stack (section 3.3) and its trainer-facing API (`forward(a,v,t)` or one dict,
+`compute_loss`, `get_predictions_and_uncertainties`; section 8b)."""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .deer import MultiDimensionalDEER
+from .encoders import EnhancedAudioEncoder, EnhancedTextEncoder, EnhancedVideoEncoder
+from .fusion import HierarchicalMultimodalFusion
+from .losses import MultiTaskDEERLoss
+
+
+class SequenceDEERModel(nn.Module):
+    def __init__(self, hidden_dim: int = 512, video_feature_dim: int = 256, dropout: float = 0.3,
+                 attention_heads: int = 8, emotion_dims: int = 3):
+        super().__init__()
+        self.audio_encoder = EnhancedAudioEncoder({"hidden_dim": hidden_dim, "dropout": dropout})
+        self.video_encoder = EnhancedVideoEncoder({"hidden_dim": hidden_dim, "dropout": dropout,
+                                                   "frame_feature_dim": video_feature_dim})
+        self.text_encoder = EnhancedTextEncoder({"hidden_dim": hidden_dim, "dropout": dropout})
+        self.fusion = HierarchicalMultimodalFusion(hidden_dim, hidden_dim, hidden_dim, fusion_dim=hidden_dim,
+                                                   intermediate_dim=hidden_dim // 2,
+                                                   num_attention_heads=attention_heads, dropout=dropout)
+        self.deer = MultiDimensionalDEER(hidden_dim, emotion_dims, hidden_dim // 2, dropout)
+        self.loss_fn = MultiTaskDEERLoss()
+
+    def forward(self, audio, video=None, text=None, attention_mask: Optional[torch.Tensor] = None,
+                linguistic_features: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        if isinstance(audio, dict):
+            d = audio
+            audio = d.get("audio", d.get("audio_features"))
+            video = d.get("video", d.get("video_features"))
+            text = d.get("text", d.get("text_features"))
+            attention_mask = d.get("attention_mask", attention_mask)
+            linguistic_features = d.get("linguistic_features", linguistic_features)
+        ops.begin_step()
+        a = self.audio_encoder(audio)
+        v = self.video_encoder(video)
+        t = self.text_encoder(text, attention_mask, linguistic_features)
+        fus = self.fusion(a, v, t)
+        out = self.deer(fus["fused_features"])
+        out["fused_features"] = fus["fused_features"]
+        out["audio_encoded"], out["video_encoded"], out["text_encoded"] = a, v, t
+        out["attention_weights"] = fus["trimodal_attention_weights"]
+        return out
+
+    def compute_loss(self, predictions: Dict[str, torch.Tensor], targets: torch.Tensor) -> Dict[str, torch.Tensor]:
+        return self.loss_fn(predictions, targets)
+
+    @staticmethod
+    def get_predictions_and_uncertainties(outputs: Dict[str, torch.Tensor]):
+        return outputs["mu_all"], outputs.get("calibrated_uncertainty", outputs["uncertainty_all"])
