@@ -273,7 +273,8 @@ def test_sequence_composite_golden_and_oracle(golden):
         if og is None:
             assert p.grad is None or float(p.grad.abs().max()) == 0.0, n
             continue
-        if float(og.abs().max()) == 0.0:
+        if float(og.abs().max()) < 1e-12:   # exactly-zero derivative up to round-off (bias before a softmax, ...)
+            assert float(p.grad.abs().max()) < 1e-5, n
             continue
         c = cosine(p.grad, og)
         assert c >= 0.999, (n, c)

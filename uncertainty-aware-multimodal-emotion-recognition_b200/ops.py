@@ -323,7 +323,7 @@ class _BiLSTMLayer(torch.autograd.Function):
         T, B, In = x.shape
         H = whf.shape[1]
         dev = x.device
-        keep = torch.is_grad_enabled() and any(t.requires_grad for t in (x, wif, whf, bif, bhf, wir, whr, bir, bhr))
+        keep = any(ctx.needs_input_grad)
         gates = torch.empty((T, B, 2, 4 * H), device=dev, dtype=torch.float32)
         bsum = torch.empty((2, 4 * H), device=dev, dtype=torch.float32)
         call("deer_axpby", ptr(bif), ptr(bhf), bsum.data_ptr(), 4 * H, 1.0, 1.0)

@@ -1,0 +1,130 @@
+"""Data-parallel trainer step around the hot path (reference: src/training/training.py:121-150 AdamW parameter
+groups, :176-245 train_epoch, :219 clip_grad_norm_, :224 optimizer.step).  The reference has no distributed code
+(`setup_distributed_training` is `pass`, training.py:541-545); this is the north-star subsystem (4):
+
+  * one process per GPU, batch sharded across ranks, weights and optimizer state replicated;
+  * parameters and gradients live in ONE flat fp32 buffer each (encoder group first, then the rest), so the
+    exchange step is a single NCCL all-reduce over the flat gradient buffer and the optimizer is two fused
+    clip+AdamW launches (one per LR group) with the clip coefficient computed on the device - no host syncs;
+  * the DEER loss is evaluated with exact GLOBAL-batch semantics: its 3x40 sufficient statistics (ECE bins, batch
+    means) are all-reduced between the two loss phases, so N ranks x B/N samples give the same loss and gradients as
+    one rank with B samples (BatchNorm statistics in the video encoder stay per-replica, as in stock DDP).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from . import ops
+from ._lib import call, ptr
+from .deer import EVIDENCE_KEY
+
+
+class FlatBuffers:
+    """Re-homes every parameter of `model` (and its .grad) into views of two flat fp32 buffers."""
+
+    def __init__(self, model: nn.Module, group_fn):
+        named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
+        order = sorted(range(len(named)), key=lambda i: (group_fn(named[i][0]), i))
+        self.names = [named[i][0] for i in order]
+        params = [named[i][1] for i in order]
+        dev = params[0].device
+        # 16-byte aligned slots so float4 / TMA consumers can address any tensor
+        offs, off = [], 0
+        for p in params:
+            offs.append(off)
+            off += (p.numel() + 3) // 4 * 4
+        self.numel = off
+        self.params = torch.zeros(off, device=dev, dtype=torch.float32)
+        self.grads = torch.zeros(off, device=dev, dtype=torch.float32)
+        self.group_bounds: List[tuple] = []
+        g_prev, start = None, 0
+        for p, o, n in zip(params, offs, self.names):
+            g = group_fn(n)
+            if g != g_prev and g_prev is not None:
+                self.group_bounds.append((g_prev, start, o))
+                start = o
+            g_prev = g
+            self.params[o:o + p.numel()].copy_(p.data.reshape(-1))
+            p.data = self.params[o:o + p.numel()].view_as(p)
+            p.grad = self.grads[o:o + p.numel()].view_as(p)
+        self.group_bounds.append((g_prev, start, off))
+        self.payload = sum(p.numel() for p in params)
+
+
+def reference_lr_group(name: str) -> int:
+    """training.py:128-142: names containing 'encoder' train at 0.5 x lr (group 0); everything else at lr (group 1)."""
+    return 0 if "encoder" in name else 1
+
+
+class DEERDataParallelTrainer:
+    def __init__(self, model: nn.Module, learning_rate: float = 1e-4, weight_decay: float = 1e-5,
+                 gradient_clip: float = 1.0, betas=(0.9, 0.999), eps: float = 1e-8,
+                 process_group=None, exact_global_loss: bool = True, loss_weights=(0.1, 0.01, 0.05, 0.05)):
+        self.model = model
+        self.lr, self.wd, self.clip, self.betas, self.eps = learning_rate, weight_decay, gradient_clip, betas, eps
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.exact_global_loss = exact_global_loss
+        self.loss_weights = loss_weights
+        self.flat = FlatBuffers(model, reference_lr_group)
+        dev = self.flat.params.device
+        self.m = torch.zeros_like(self.flat.params)
+        self.v = torch.zeros_like(self.flat.params)
+        self.sumsq = torch.zeros(1, device=dev, dtype=torch.float32)
+        self.step_count = 0
+        self.step_tensor = torch.zeros(1, device=dev, dtype=torch.int64)
+        ops.set_dropout_step_tensor(self.step_tensor)
+        self.group_lr = {0: 0.5, 1: 1.0}
+        self.last_losses: Optional[torch.Tensor] = None
+
+    # ------------------------------------------------------------------ pieces
+    def _allreduce(self, t: torch.Tensor):
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.pg)
+
+    def forward_backward(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
+        """fwd + fused head/loss + bwd; gradients are accumulated into the flat buffer.  Returns losses [5D+2]."""
+        model = self.model
+        self.flat.grads.zero_()
+        out = model(batch["audio_features"], batch["video_features"], batch["text_features"],
+                    batch.get("attention_mask"), batch.get("linguistic_features"))
+        ev = out[EVIDENCE_KEY]
+        targets = batch["targets"]
+        B = targets.shape[0]
+        hook = self._allreduce if (self.exact_global_loss and self.world > 1) else None
+        gb = B * self.world if self.exact_global_loss else B
+        # with exact global semantics local gradients are SUMMED across ranks; otherwise they are averaged
+        scale = 1.0 if self.exact_global_loss else 1.0 / self.world
+        losses, dE, _, _ = ops.nig_loss_raw(ev.detach(), None, targets, weights=self.loss_weights, want_grad=True,
+                                            grad_scale=scale, stats_hook=hook, global_batch=gb)
+        ev.backward(dE)
+        self.last_losses = losses
+        return losses
+
+    def optimizer_step(self):
+        self.step_count += 1
+        f = self.flat
+        self._allreduce(f.grads)
+        self.sumsq.zero_()
+        call("deer_sumsq", ptr(f.grads), f.numel, ptr(self.sumsq))
+        for g, lo, hi in f.group_bounds:
+            n = hi - lo
+            if n <= 0:
+                continue
+            call("deer_adamw", f.params.data_ptr() + 4 * lo, f.grads.data_ptr() + 4 * lo, self.m.data_ptr() + 4 * lo,
+                 self.v.data_ptr() + 4 * lo, n, float(self.lr * self.group_lr[g]), float(self.betas[0]),
+                 float(self.betas[1]), float(self.eps), float(self.wd), self.step_count, ptr(self.sumsq),
+                 float(self.clip), 1.0)
+        self.step_tensor.add_(1)
+
+    def train_step(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
+        losses = self.forward_backward(batch)
+        self.optimizer_step()
+        return losses
+
+    def grad_norm(self) -> torch.Tensor:
+        return self.sumsq.sqrt()
