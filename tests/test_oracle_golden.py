@@ -195,3 +195,23 @@ def test_linguistic_features(golden):
     mask = torch.from_numpy(fx.arrays["mask"])
     got = O.linguistic_features(ids, mask)
     assert torch.equal(got, torch.from_numpy(fx.arrays["feats"]))
+
+
+def test_torch_baseline_matches_oracle(golden):
+    """The CPU baseline that bench.py times (oracle/torch_baseline.py, stock torch.nn layers as the reference uses)
+    computes the same numbers as the golden-pinned oracle."""
+    from oracle import torch_baseline as TB
+    fx = golden("seq_full_b4")
+    m = fx.meta
+    model = TB.SequenceBaseline(dropout=0.0).double()
+    missing, unexpected = model.load_state_dict(fx.state_dict(), strict=False)
+    assert not missing and all(k.startswith("fusion.uncertainty_gate") for k in unexpected), (missing, unexpected)
+    model.train()
+    audio, video, text, mask, ling, y = seq_inputs(m["B"], 40, 12, 16, seed=3)
+    pred = model(audio, video, text, mask, ling)
+    loss = TB.multitask_loss(pred, y)
+    ref_out, ref_loss = O.sequence_model_loss(audio, video, text, mask, ling, y, fx.state_dict(), training=True)
+    for d in O.DIMS:
+        for k in ("mu", "nu", "alpha", "beta"):
+            close(pred[f"{d}_{k}"], ref_out[f"{d}_{k}"], 1e-8, 1e-10)
+    close(loss, ref_loss["total_loss"], 1e-8, 1e-10)
