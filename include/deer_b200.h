@@ -41,6 +41,9 @@ int deer_version(void);
 const char* deer_last_error(void);
 /* number of kernels launched by this library since process start (bench.py `gpu_launches`) */
 long long deer_launch_count(void);
+/* process-wide tuning switches (testing / ablation) */
+#define DEER_OPT_TMA_TF32_ROUND 1 /* 1 (default): TMA loads fp32 operands as TFLOAT32 (rounded); 0: raw fp32 bits */
+int deer_set_option(int option, int value);
 
 /* ---- dense contractions: every nn.Linear on the path (encoders.py:93-107,443-475,597-625;
  *      fusion.py:98-103,201-219,286-304; deer.py:48-56,215-222; complete_project.py:61-417), the

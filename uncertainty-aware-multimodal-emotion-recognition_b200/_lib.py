@@ -22,6 +22,7 @@ _PROTOS = {
     "deer_version": [],
     "deer_last_error": [],
     "deer_launch_count": [],
+    "deer_set_option": [I, I],
     "deer_gemm": [P, L, I, P, L, I, P, L, I, I, I, P, I, F, I, L, L, L, L, I, P],
     "deer_bias_act_bwd": [P, L, P, L, P, L, P, I, I, I, P],
     "deer_layernorm_fwd": [P, P, P, P, P, P, I, I, F, P],
@@ -112,3 +113,7 @@ def ptr(t):
 
 def call(name: str, *args):
     check(getattr(load(), name)(*args, stream()), name)
+
+
+def set_option(option: int, value: int):
+    check(load().deer_set_option(option, value), "deer_set_option")

@@ -22,6 +22,7 @@ int gemm_simt(const float* A, long long lda, int transA, const float* B, long lo
 int gemm_tcgen05(const float* A, long long lda, int transA, const float* B, long long ldb, int transB, float* C,
                  long long ldc, int M, int N, int K, const float* bias, int act, float beta, int batch, long long sA,
                  long long sB, long long sC, long long sBias, cudaStream_t stream);
+void gemm_tcgen05_set_round(int on);
 bool gemm_tcgen05_supported(const float* A, long long lda, int transA, const float* B, long long ldb, int transB,
                             const float* C, long long ldc, int M, int N, int K, int batch, long long sA, long long sB,
                             long long sC);
@@ -35,6 +36,17 @@ extern "C" {
 int deer_version(void) { return 100; }
 const char* deer_last_error(void) { return g_err; }
 long long deer_launch_count(void) { return g_launches.load(); }
+
+int deer_set_option(int option, int value) {
+  switch (option) {
+    case DEER_OPT_TMA_TF32_ROUND:
+      gemm_tcgen05_set_round(value);
+      return DEER_OK;
+    default:
+      set_error("set_option: unknown option %d", option);
+      return DEER_ERR_INVALID;
+  }
+}
 
 int deer_gemm(const float* A, long long lda, int transA, const float* B, long long ldb, int transB, float* C,
               long long ldc, int M, int N, int K, const float* bias, int act, float beta, int batch, long long sA,

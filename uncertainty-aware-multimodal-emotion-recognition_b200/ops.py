@@ -16,7 +16,15 @@ from ._lib import call, ptr
 ACT = {"none": 0, None: 0, "relu": 1, "tanh": 2, "sigmoid": 3}
 ENGINE_AUTO, ENGINE_SIMT, ENGINE_TF32 = 0, 1, 2
 
-_state = {"engine": ENGINE_AUTO, "lstm_engine": ENGINE_AUTO}
+# Precision policy (DESIGN.md "numerics"): the time-batched contractions (M = B*T rows: LSTM input projections,
+# pooling scorers, Conv1d taps) and every backward GEMM run on the tcgen05 TF32 engine; the FORWARD of the small
+# post-pooling layers (M = B rows; ~25 chained GEMMs through fusion and the NIG head, <1% of the FLOPs) stays on the
+# exact-fp32 engine, because TF32 rounding compounding through that chain is what pushes the NIG parameters past the
+# 1e-3 relative tolerance.  The same layers' backward GEMMs are also kept exact by default: their (cancellation-
+# prone) outputs feed the bias / scorer gradients whose per-tensor cosine otherwise sits at 0.9992, too close to the
+# 0.999 gate (tools/precision_probe.py).
+_state = {"engine": ENGINE_AUTO, "lstm_engine": ENGINE_AUTO, "exact_small_fwd": True, "exact_small_bwd": True,
+          "small_rows": 8192}
 
 
 def set_gemm_engine(engine: int):
@@ -26,6 +34,25 @@ def set_gemm_engine(engine: int):
 
 def set_lstm_engine(engine: int):
     _state["lstm_engine"] = int(engine)
+
+
+def set_exact_small_forward(on: bool, small_rows: int = 8192, backward: Optional[bool] = None):
+    _state["exact_small_fwd"] = bool(on)
+    _state["exact_small_bwd"] = bool(on if backward is None else backward)
+    _state["small_rows"] = int(small_rows)
+
+
+def _bwd_engine(M: int):
+    if _state["engine"] == ENGINE_AUTO and _state["exact_small_bwd"] and M < _state["small_rows"]:
+        return ENGINE_SIMT
+    return None
+
+
+def _fwd_engine(M: int):
+    """Engine for a FORWARD nn.Linear with M rows under the precision policy."""
+    if _state["engine"] == ENGINE_AUTO and _state["exact_small_fwd"] and M < _state["small_rows"]:
+        return ENGINE_SIMT
+    return None
 
 
 def _req(t: torch.Tensor, name: str):
@@ -78,7 +105,7 @@ class _Linear(torch.autograd.Function):
                 y = torch.empty((M, N), device=w.device, dtype=torch.float32)
             last = i == len(xs) - 1
             gemm(x2, ld, 0, w.data_ptr() + 4 * k0, w.stride(0), 1, y, N, M, N, K,
-                 bias=b if last else None, act=act if last else 0, beta=0.0 if i == 0 else 1.0)
+                 bias=b if last else None, act=act if last else 0, beta=0.0 if i == 0 else 1.0, engine=_fwd_engine(M))
             rows.append((x2, ld, k0, K))
             k0 += K
         assert k0 == Ktot, f"input widths {k0} != weight in-features {Ktot}"
@@ -108,12 +135,12 @@ class _Linear(torch.autograd.Function):
             ld, k0, K = ctx.meta[i]
             if ctx.needs_input_grad[4 + i]:
                 dx = torch.empty((M, K), device=w.device, dtype=torch.float32)
-                gemm(dz, N, 0, w.data_ptr() + 4 * k0, w.stride(0), 0, dx, K, M, K, N)
+                gemm(dz, N, 0, w.data_ptr() + 4 * k0, w.stride(0), 0, dx, K, M, K, N, engine=_bwd_engine(M))
                 dxs.append(dx.view(ctx.in_shapes[i]))
             else:
                 dxs.append(None)
             if dw is not None:
-                gemm(dz, N, 1, x2, ld, 0, dw.data_ptr() + 4 * k0, Ktot, N, K, M, beta=1.0)
+                gemm(dz, N, 1, x2, ld, 0, dw.data_ptr() + 4 * k0, Ktot, N, K, M, beta=1.0, engine=_bwd_engine(M))
         return (dw, db, None, None, *dxs)
 
 
@@ -518,7 +545,8 @@ class _GroupedLinear(torch.autograd.Function):
         out = torch.empty((M, G, N), device=ws[0].device, dtype=torch.float32)
         for g in range(G):
             x2, _, K, ld = rows[g]
-            gemm(x2, ld, 0, ws[g], ws[g].stride(0), 1, out.data_ptr() + 4 * g * N, G * N, M, N, K, bias=bs[g], act=act)
+            gemm(x2, ld, 0, ws[g], ws[g].stride(0), 1, out.data_ptr() + 4 * g * N, G * N, M, N, K, bias=bs[g], act=act,
+                 engine=_fwd_engine(M))
         ctx.act, ctx.G = act, G
         ctx.meta = [(r[3], r[2]) for r in rows]
         ctx.in_shapes = [x.shape for x in xs]
@@ -549,13 +577,13 @@ class _GroupedLinear(torch.autograd.Function):
             zp = dz.data_ptr() + 4 * g * N
             if ctx.needs_input_grad[2 + g]:
                 dw = torch.zeros_like(ws[g])
-                gemm(zp, G * N, 1, xs[g], ld, 0, dw, K, N, K, M, beta=1.0)
+                gemm(zp, G * N, 1, xs[g], ld, 0, dw, K, N, K, M, beta=1.0, engine=_bwd_engine(M))
                 dws.append(dw)
             else:
                 dws.append(None)
             if ctx.needs_input_grad[2 + 2 * G + g]:
                 dx = torch.empty((M, K), device=dev, dtype=torch.float32)
-                gemm(zp, G * N, 0, ws[g], ws[g].stride(0), 0, dx, K, M, K, N)
+                gemm(zp, G * N, 0, ws[g], ws[g].stride(0), 0, dx, K, M, K, N, engine=_bwd_engine(M))
                 dxs.append(dx.view(ctx.in_shapes[g]))
             else:
                 dxs.append(None)
