@@ -36,6 +36,9 @@ extern "C" {
 #define DEER_GEMM_AUTO 0   /* tcgen05 when the shape/alignment allows it, SIMT otherwise */
 #define DEER_GEMM_SIMT 1   /* fp32 CUDA-core tiles (exact fp32; small or unaligned shapes) */
 #define DEER_GEMM_TF32 2   /* tcgen05.mma kind::tf32, fp32 accumulate in TMEM, TMA-fed */
+/* LSTM recurrence engines (deer_lstm_fwd/bwd `engine`): DEER_GEMM_SIMT = exact-fp32 stepwise; DEER_GEMM_AUTO/TF32 =
+ * persistent 8-CTA-cluster tcgen05 kernel when H == 256 (stepwise otherwise); 3 = stepwise with TF32 step GEMMs */
+#define DEER_LSTM_STEPWISE_TF32 3
 
 int deer_version(void);
 const char* deer_last_error(void);

@@ -13,6 +13,33 @@ namespace deer {
 int gemm_simt(const float* A, long long lda, int transA, const float* B, long long ldb, int transB, float* C,
               long long ldc, int M, int N, int K, const float* bias, int act, float beta, int batch, long long sA,
               long long sB, long long sC, long long sBias, cudaStream_t stream);
+int gemm_tcgen05(const float* A, long long lda, int transA, const float* B, long long ldb, int transB, float* C,
+                 long long ldc, int M, int N, int K, const float* bias, int act, float beta, int batch, long long sA,
+                 long long sB, long long sC, long long sBias, cudaStream_t stream);
+bool gemm_tcgen05_supported(const float* A, long long lda, int transA, const float* B, long long ldb, int transB,
+                            const float* C, long long ldc, int M, int N, int K, int batch, long long sA, long long sB,
+                            long long sC);
+
+bool lstm_persistent_supported(const float* gates, const float* h_out, const float* c_all, const float* w_fwd,
+                               const float* w_rev, int T, int B, int H);
+int lstm_fwd_persistent(float* gates, const float* w_fwd, const float* w_rev, float* h_out, float* c_all, int T, int B,
+                        int keep, cudaStream_t stream);
+
+// recurrent step GEMM for both directions: fp32 SIMT (one batched launch) or TF32 tcgen05 (one launch per direction)
+static int step_gemm(bool tf32, const float* A, long long lda, const float* B, long long ldb, int transB, float* C,
+                     long long ldc, int M, int N, int K, float beta, long long sA, long long sB, long long sC,
+                     cudaStream_t stream) {
+  if (tf32 && gemm_tcgen05_supported(A, lda, 0, B, ldb, transB, C, ldc, M, N, K, 1, 0, 0, 0) &&
+      gemm_tcgen05_supported(A + sA, lda, 0, B + sB, ldb, transB, C + sC, ldc, M, N, K, 1, 0, 0, 0)) {
+    for (int d = 0; d < 2; d++) {
+      int rc = gemm_tcgen05(A + d * sA, lda, 0, B + d * sB, ldb, transB, C + d * sC, ldc, M, N, K, nullptr,
+                            DEER_ACT_NONE, beta, 1, 0, 0, 0, 0, stream);
+      if (rc) return rc;
+    }
+    return DEER_OK;
+  }
+  return gemm_simt(A, lda, 0, B, ldb, transB, C, ldc, M, N, K, nullptr, DEER_ACT_NONE, beta, 2, sA, sB, sC, 0, stream);
+}
 
 // one thread per (b, dir, j)
 __global__ void __launch_bounds__(256) lstm_cell_fwd_kernel(float* __restrict__ gates, float* __restrict__ h_out,
@@ -88,7 +115,7 @@ __global__ void __launch_bounds__(256) lstm_cell_bwd_kernel(float* __restrict__ 
 }
 
 int lstm_fwd_stepwise(float* gates, const float* w_hh, long long w_stride, float* h_out, float* c_all, float* c_work, int T, int B, int H,
-                      cudaStream_t stream) {
+                      bool tf32, cudaStream_t stream) {
   const long long n = (long long)B * 2 * H;
   const unsigned grid = (unsigned)cdiv(n, 256);
   const long long row_h = (long long)B * 2 * H, row_g = (long long)B * 8 * H;
@@ -100,8 +127,7 @@ int lstm_fwd_stepwise(float* gates, const float* w_hh, long long w_stride, float
       const long long sA = (long long)(p1 - p0) * row_h + H;
       float* C = gates + t0 * row_g;
       const long long sC = (long long)(t1 - t0) * row_g + 4 * H;
-      int rc = gemm_simt(A, 2 * H, 0, w_hh, H, 1, C, 8 * H, B, 4 * H, H, nullptr, DEER_ACT_NONE, 1.f, 2, sA,
-                         w_stride, sC, 0, stream);
+      int rc = step_gemm(tf32, A, 2 * H, w_hh, H, 1, C, 8 * H, B, 4 * H, H, 1.f, sA, w_stride, sC, stream);
       if (rc) return rc;
     }
     DEER_LAUNCH(lstm_cell_fwd_kernel, grid, 256, 0, stream, gates, h_out, c_all, c_work, step, T, B, H);
@@ -110,7 +136,7 @@ int lstm_fwd_stepwise(float* gates, const float* w_hh, long long w_stride, float
 }
 
 int lstm_bwd_stepwise(float* gates, const float* w_hh, long long w_stride, const float* c_all, const float* dh_out, float* dh_work,
-                      float* dc_work, int T, int B, int H, cudaStream_t stream) {
+                      float* dc_work, int T, int B, int H, bool tf32, cudaStream_t stream) {
   const long long n = (long long)B * 2 * H;
   const unsigned grid = (unsigned)cdiv(n, 256);
   const long long row_g = (long long)B * 8 * H;
@@ -122,8 +148,7 @@ int lstm_bwd_stepwise(float* gates, const float* w_hh, long long w_stride, const
       const int t0 = step, t1 = T - 1 - step;
       const float* A = gates + t0 * row_g;
       const long long sA = (long long)(t1 - t0) * row_g + 4 * H;
-      int rc = gemm_simt(A, 8 * H, 0, w_hh, H, 0, dh_work, 2 * H, B, H, 4 * H, nullptr, DEER_ACT_NONE, 0.f, 2, sA,
-                         w_stride, H, 0, stream);
+      int rc = step_gemm(tf32, A, 8 * H, w_hh, H, 0, dh_work, 2 * H, B, H, 4 * H, 0.f, sA, w_stride, H, stream);
       if (rc) return rc;
     }
   }
@@ -140,18 +165,21 @@ int deer_lstm_fwd(float* gates, const float* w_hh_fwd, const float* w_hh_rev, fl
                   int T, int B, int H, int engine, void* stream) {
   DEER_CHECK_ARG(gates && w_hh_fwd && w_hh_rev && h_out && T > 0 && B > 0 && H > 0, "lstm_fwd: bad args");
   DEER_CHECK_ARG(c_out || c_work, "lstm_fwd: need c_out or c_work");
-  (void)engine;
+  // engine: SIMT = exact-fp32 stepwise reference; AUTO/TF32 = persistent cluster kernel (tcgen05) when H == 256;
+  // DEER_LSTM_STEPWISE_TF32 keeps the stepwise schedule but with the tcgen05 GEMM per step (ablation).
+  if (engine != DEER_GEMM_SIMT && engine != DEER_LSTM_STEPWISE_TF32 &&
+      lstm_persistent_supported(gates, h_out, c_out, w_hh_fwd, w_hh_rev, T, B, H))
+    return lstm_fwd_persistent(gates, w_hh_fwd, w_hh_rev, h_out, c_out, T, B, c_out != nullptr, (cudaStream_t)stream);
   return lstm_fwd_stepwise(gates, w_hh_fwd, (long long)(w_hh_rev - w_hh_fwd), h_out, c_out, c_work, T, B, H,
-                           (cudaStream_t)stream);
+                           engine == DEER_LSTM_STEPWISE_TF32, (cudaStream_t)stream);
 }
 
 int deer_lstm_bwd(float* gates, const float* w_hh_fwd, const float* w_hh_rev, const float* c_all, const float* dh_out,
                   float* dh_work, float* dc_work, int T, int B, int H, int engine, void* stream) {
   DEER_CHECK_ARG(gates && w_hh_fwd && w_hh_rev && c_all && dh_out && dh_work && dc_work && T > 0 && B > 0 && H > 0,
                  "lstm_bwd: bad args");
-  (void)engine;
   return lstm_bwd_stepwise(gates, w_hh_fwd, (long long)(w_hh_rev - w_hh_fwd), c_all, dh_out, dh_work, dc_work, T, B, H,
-                           (cudaStream_t)stream);
+                           engine == DEER_LSTM_STEPWISE_TF32, (cudaStream_t)stream);
 }
 
 }  // extern "C"

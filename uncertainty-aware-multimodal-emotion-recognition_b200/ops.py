@@ -28,8 +28,10 @@ _state = {"engine": ENGINE_AUTO, "lstm_engine": ENGINE_AUTO, "exact_small_fwd": 
 
 
 def set_gemm_engine(engine: int):
-    """0 auto (tcgen05 where the shape allows), 1 fp32 SIMT everywhere, 2 force tcgen05 (raises if unsupported)."""
+    """0 auto (tcgen05 where the shape allows), 1 fp32 SIMT everywhere, 2 force tcgen05 (raises if unsupported).
+    The LSTM recurrence follows: SIMT -> exact fp32 stepwise; otherwise the TF32 engines."""
     _state["engine"] = int(engine)
+    _state["lstm_engine"] = ENGINE_SIMT if int(engine) == ENGINE_SIMT else ENGINE_AUTO
 
 
 def set_lstm_engine(engine: int):
