@@ -37,8 +37,10 @@ extern "C" {
 #define DEER_GEMM_SIMT 1   /* fp32 CUDA-core tiles (exact fp32; small or unaligned shapes) */
 #define DEER_GEMM_TF32 2   /* tcgen05.mma kind::tf32, fp32 accumulate in TMEM, TMA-fed */
 /* LSTM recurrence engines (deer_lstm_fwd/bwd `engine`): DEER_GEMM_SIMT = exact-fp32 stepwise; DEER_GEMM_AUTO/TF32 =
- * persistent 8-CTA-cluster tcgen05 kernel when H == 256 (stepwise otherwise); 3 = stepwise with TF32 step GEMMs */
+ * persistent 4-CTA-cluster tcgen05 kernels (forward FP16, backward BF16 operands, fp32 accumulation, DSMEM exchange)
+ * when H == 256 (stepwise otherwise); 3 = stepwise with TF32 step GEMMs; 4 = round-1 8-CTA TF32 forward kernel */
 #define DEER_LSTM_STEPWISE_TF32 3
+#define DEER_LSTM_PERSISTENT_V1 4
 
 int deer_version(void);
 const char* deer_last_error(void);
@@ -46,7 +48,12 @@ const char* deer_last_error(void);
 long long deer_launch_count(void);
 /* process-wide tuning switches (testing / ablation) */
 #define DEER_OPT_TMA_TF32_ROUND 1 /* 1 (default): TMA loads fp32 operands as TFLOAT32 (rounded); 0: raw fp32 bits */
+#define DEER_OPT_LSTM_TS 2        /* 1 (default): resident recurrent weights in TMEM (tcgen05.mma A from TMEM); 0: in smem */
+#define DEER_OPT_LSTM_TILE 3      /* 0 (default): auto; 16 or 32: batch columns per cluster of the persistent LSTM */
 int deer_set_option(int option, int value);
+/* debugging aid: device buffer of >= 32 int64 that receives a clock64() trace of four steps of the persistent LSTM
+ * kernels' block 0 (NULL disables; tools/lstm_probe.py --prof) */
+int deer_lstm_set_profile_buffer(long long* device_buf);
 
 /* ---- dense contractions: every nn.Linear on the path (encoders.py:93-107,443-475,597-625;
  *      fusion.py:98-103,201-219,286-304; deer.py:48-56,215-222; complete_project.py:61-417), the

@@ -1,8 +1,9 @@
-"""Persistent tcgen05 cluster LSTM (csrc/lstm_persistent.cu) against the exact-fp32 stepwise engine and the oracle."""
+"""Persistent tcgen05 cluster LSTM kernels (csrc/lstm_cluster.cu: forward and BPTT; csrc/lstm_persistent.cu: the earlier
+TF32 forward) against the exact-fp32 stepwise engine and the oracle."""
 import pytest
 import torch
 
-from deer_b200 import ops
+from deer_b200 import _lib, ops
 from helpers import assert_close, cosine
 from oracle import deer_oracle as O
 
@@ -35,21 +36,67 @@ def run(x, ws, engine, grad):
     return h, None
 
 
-@pytest.mark.parametrize("B,T,In", [(4, 6, 84), (64, 20, 84), (70, 9, 512), (130, 33, 84)])
+ENGINE_V1 = 4  # DEER_LSTM_PERSISTENT_V1
+
+
+@pytest.fixture(autouse=True)
+def _restore_lstm_options():
+    yield
+    _lib.set_option(2, 1)   # DEER_OPT_LSTM_TS
+    _lib.set_option(3, 0)   # DEER_OPT_LSTM_TILE
+    ops.set_gemm_engine(ops.ENGINE_AUTO)
+
+
+@pytest.mark.parametrize("B,T,In", [(1, 1, 84), (4, 2, 84), (4, 6, 84), (64, 20, 84), (70, 9, 512), (130, 33, 84)])
 @pytest.mark.parametrize("grad", [False, True])
-def test_persistent_matches_stepwise(B, T, In, grad):
+@pytest.mark.parametrize("ts,tile", [(1, 0), (0, 16), (1, 32), (0, 32)])
+def test_cluster_matches_stepwise(B, T, In, grad, ts, tile):
+    """ts: resident weights in TMEM (1) or shared memory (0); tile: batch columns per cluster (0 = auto)."""
     H = 256
     ws = make_layer(In, H, B + T)
     x = torch.randn(B, T, In, generator=torch.Generator().manual_seed(B))
     ops.set_gemm_engine(ops.ENGINE_SIMT)     # exact input projection for both runs: isolates the recurrence
     h_ref, g_ref = run(x, ws, ops.ENGINE_SIMT, grad)
+    _lib.set_option(2, ts)
+    _lib.set_option(3, tile)
     h_per, g_per = run(x, ws, ops.ENGINE_AUTO, grad)
-    ops.set_gemm_engine(ops.ENGINE_AUTO)
     assert_close(h_per, h_ref, 1e-3, "h")
     assert float((h_per - h_ref).abs().max()) < 2e-3
     if grad:
         for a, b_ in zip(g_per, g_ref):
-            assert cosine(a, b_) > 0.9999
+            if float(b_.abs().max()) == 0.0:     # T == 1: no recurrent-weight gradient
+                assert float(a.abs().max()) == 0.0
+            else:
+                assert cosine(a, b_) > 0.9999
+
+
+@pytest.mark.parametrize("B,T,In", [(64, 20, 84), (70, 9, 512)])
+def test_persistent_v1_matches_stepwise(B, T, In):
+    H = 256
+    ws = make_layer(In, H, B + T)
+    x = torch.randn(B, T, In, generator=torch.Generator().manual_seed(B))
+    ops.set_gemm_engine(ops.ENGINE_SIMT)
+    h_ref, _ = run(x, ws, ops.ENGINE_SIMT, False)
+    h_per, _ = run(x, ws, ENGINE_V1, False)
+    assert_close(h_per, h_ref, 1e-3, "h")
+
+
+def test_cluster_bptt_full_length_vs_oracle():
+    """T=300 recurrence, forward (FP16 operands) and BPTT (BF16 operands) against fp64 autograd of the oracle."""
+    B, T, In, H = 6, 300, 84, 256
+    ws = make_layer(In, H, 99)
+    x = torch.randn(B, T, In, generator=torch.Generator().manual_seed(2))
+    h, grads = run(x, ws, ops.ENGINE_AUTO, True)
+    xd = x.double().requires_grad_(True)
+    wd = [w.double().requires_grad_(True) for w in ws]
+    f = O.lstm_direction(xd, *wd[:4], False)
+    r = O.lstm_direction(xd, *wd[4:], True)
+    ref = torch.cat([f, r], dim=-1).permute(1, 0, 2)
+    assert_close(h, ref, 1e-3, "h vs oracle")
+    pr = torch.randn(h.shape, generator=torch.Generator().manual_seed(5)).double()
+    (ref * pr).sum().backward()
+    for got, want in zip(grads, [xd.grad] + [w.grad for w in wd]):
+        assert cosine(got, want) > 0.999
 
 
 def test_persistent_full_length_vs_oracle():

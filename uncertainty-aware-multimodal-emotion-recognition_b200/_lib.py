@@ -23,6 +23,7 @@ _PROTOS = {
     "deer_last_error": [],
     "deer_launch_count": [],
     "deer_set_option": [I, I],
+    "deer_lstm_set_profile_buffer": [P],
     "deer_gemm": [P, L, I, P, L, I, P, L, I, I, I, P, I, F, I, L, L, L, L, I, P],
     "deer_bias_act_bwd": [P, L, P, L, P, L, P, I, I, I, P],
     "deer_layernorm_fwd": [P, P, P, P, P, P, I, I, F, P],

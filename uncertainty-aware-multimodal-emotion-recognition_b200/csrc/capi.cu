@@ -23,6 +23,8 @@ int gemm_tcgen05(const float* A, long long lda, int transA, const float* B, long
                  long long ldc, int M, int N, int K, const float* bias, int act, float beta, int batch, long long sA,
                  long long sB, long long sC, long long sBias, cudaStream_t stream);
 void gemm_tcgen05_set_round(int on);
+void lstm_cluster_set_option(int ts, int tile);
+void lstm_cluster_set_profile(long long* buf);
 bool gemm_tcgen05_supported(const float* A, long long lda, int transA, const float* B, long long ldb, int transB,
                             const float* C, long long ldc, int M, int N, int K, int batch, long long sA, long long sB,
                             long long sC);
@@ -37,10 +39,21 @@ int deer_version(void) { return 100; }
 const char* deer_last_error(void) { return g_err; }
 long long deer_launch_count(void) { return g_launches.load(); }
 
+int deer_lstm_set_profile_buffer(long long* device_buf) {
+  lstm_cluster_set_profile(device_buf);
+  return DEER_OK;
+}
+
 int deer_set_option(int option, int value) {
   switch (option) {
     case DEER_OPT_TMA_TF32_ROUND:
       gemm_tcgen05_set_round(value);
+      return DEER_OK;
+    case DEER_OPT_LSTM_TS:
+      lstm_cluster_set_option(value, -1);
+      return DEER_OK;
+    case DEER_OPT_LSTM_TILE:
+      lstm_cluster_set_option(-1, value);
       return DEER_OK;
     default:
       set_error("set_option: unknown option %d", option);

@@ -84,15 +84,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
 
   if (warp == 0) {
     // ===================================================================== TMA producer
-    if (lane == 0) {
-      for (int i = 0; i < num_kb; i++) {
-        const int s = i % STAGES;
-        const uint32_t ph = (i / STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        uint8_t* sa = smem + s * STAGE_BYTES;
-        uint8_t* sb = sa + TILE_BYTES;
+    const bool leader = elect_one();
+    for (int i = 0; i < num_kb; i++) {
+      const int s = i % STAGES;
+      const uint32_t ph = (i / STAGES) & 1;
+      mbar_wait(&empty_bar[s], ph ^ 1);
+      uint8_t* sa = smem + s * STAGE_BYTES;
+      uint8_t* sb = sa + TILE_BYTES;
+      const int k0 = (kb_begin + i) * BLOCK_K;
+      if (leader) {
         mbar_expect_tx(&full_bar[s], STAGE_BYTES);
-        const int k0 = (kb_begin + i) * BLOCK_K;
         if (!A_MN) {
           tma_load_2d(sa, &tmap_a, &full_bar[s], k0, m0);  // box {32 k, 128 rows}
         } else {
@@ -108,11 +109,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
             tma_load_2d(sb + j * 4096, &tmap_b, &full_bar[s], n0 + 32 * j, k0);
         }
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
-    if (lane == 0) {
+    // whole warp runs the loop (warp-uniform control flow keeps the tcgen05 operands in uniform registers: a lane-0
+    // branch makes ptxas wrap every MMA in an ELECT/R2UR waterfall, ~60 cycles per instruction); one lane issues
+    {
       constexpr uint32_t idesc = make_idesc(A_MN ? 1 : 0, B_MN ? 1 : 0, BLOCK_M, BLOCK_N);
+      const uint32_t tb = warp_uniform(tmem_base);
+      const bool leader = elect_one();
       for (int i = 0; i < num_kb; i++) {
         const int s = i % STAGES;
         const uint32_t ph = (i / STAGES) & 1;
@@ -120,18 +126,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
         const uint32_t sb = sa + TILE_BYTES;
+        if (leader) {
 #pragma unroll
-        for (int k = 0; k < BLOCK_K / UMMA_K; k++) {
-          // K-major : 8-row x 128 B swizzle atoms stacked every 1024 B (SBO); +32 B per K step inside the atom.
-          // MN-major: rows are k, 128 B = 32 mn elements; 32-element MN chunks every 4096 B (LBO); the 8 k-rows of
-          //           one instruction are two 4-row (512 B) swizzle atoms (SBO); +1024 B per K step.
-          const uint64_t ad = A_MN ? make_smem_desc(sa + k * 1024, 4096, 512, 1) : make_smem_desc(sa + k * 32, 16, 1024, 2);
-          const uint64_t bd = B_MN ? make_smem_desc(sb + k * 1024, 4096, 512, 1) : make_smem_desc(sb + k * 32, 16, 1024, 2);
-          umma_tf32(tmem_base, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < BLOCK_K / UMMA_K; k++) {
+            // K-major : 8-row x 128 B swizzle atoms stacked every 1024 B (SBO); +32 B per K step inside the atom.
+            // MN-major: rows are k, 128 B = 32 mn elements; 32-element MN chunks every 4096 B (LBO); the 8 k-rows of
+            //           one instruction are two 4-row (512 B) swizzle atoms (SBO); +1024 B per K step.
+            const uint64_t ad = A_MN ? make_smem_desc(sa + k * 1024, 4096, 512, 1) : make_smem_desc(sa + k * 32, 16, 1024, 2);
+            const uint64_t bd = B_MN ? make_smem_desc(sb + k * 1024, 4096, 512, 1) : make_smem_desc(sb + k * 32, 16, 1024, 2);
+            umma_tf32(tb, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);  // smem slot reusable once these MMAs have read it
         }
-        umma_commit(&empty_bar[s]);  // smem slot reusable once these MMAs have read it
+        __syncwarp();
       }
-      umma_commit(tmem_full_bar);    // accumulator complete
+      if (leader) umma_commit(tmem_full_bar);  // accumulator complete
+      __syncwarp();
     }
   } else {
     // ===================================================================== epilogue (warps 2..5)

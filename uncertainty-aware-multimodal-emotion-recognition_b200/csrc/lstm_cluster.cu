@@ -1,0 +1,695 @@
+// Persistent bidirectional-LSTM recurrence, forward and backward-through-time, for H = 256
+// (encoders.py:82-89: nn.LSTM(84|512 -> 256, num_layers=2, bidirectional); call :380; autograd of it).
+//
+// One thread-block CLUSTER of 4 CTAs owns one (direction, N-row batch tile) recurrence for all T steps; no per-step
+// launch, no grid sync, nothing but the h / dh exchange crosses CTAs:
+//
+//   forward   gates_t^T[4H, N] = pre_t^T + W_hh[4H,256] h_{t-1}^T[256, N]
+//     * CTA r owns hidden units 64r..64r+63: their 256 gate rows of W_hh stay resident for the whole sequence as the
+//       A operand of tcgen05.mma (FP16, either 128 KB of 128B-swizzled shared memory or 256 TMEM columns); rows are
+//       ordered 4*unit+gate so the four gates of a unit sit in four adjacent TMEM lanes of one warp.  FP16 operands
+//       carry the same 11 significant bits as TF32 for h in (-1,1) and for the weights, at twice the tensor rate and
+//       half the exchange bytes; accumulation is FP32 in TMEM.
+//     * per step: 2 accumulators (M128 x N) x 16 K-steps; the gate epilogue reads its TMEM lane (one gate row, N batch
+//       columns), adds the time-batched input projection (prefetched one step ahead), applies sigmoid/tanh on the
+//       MUFU pipe, transposes through a per-warp shared tile so one thread holds i,f,g,o of (unit, N/4 columns),
+//       updates the cell state held in REGISTERS across all T steps and writes h_t / gates / c_t.
+//     * h_t is all-gathered through DISTRIBUTED SHARED MEMORY: every warp packs its 8 units x N columns into 16-byte
+//       FP16 chunks and stores them straight into the swizzled B-operand buffer of all 4 CTAs (st.shared::cluster),
+//       then releases one remote mbarrier arrival per destination; buffers are double-buffered so no "free" handshake
+//       is needed (a peer can only be one step ahead).
+//
+//   backward  dh_{t-1}^T[256, N] = W_hh^T[256, 4H] dpre_t^T[4H, N]
+//     * CTA r owns the same 64 units: it holds dc in registers, turns (dh_out_t + dh_rec, saved gates, c_t, c_{t-1})
+//       into the pre-activation gradients dpre_t of ITS 256 gate rows (written to HBM for the weight-gradient GEMMs
+//       and, as BF16, into the B-operand tile), multiplies by its K-slice of W_hh^T (A operand [256 hid x 256 k],
+//       BF16, resident) and REDUCE-SCATTERS the partial dh over DSMEM: each accumulator row is stored to the CTA that
+//       owns that hidden unit; the owner sums the 4 partials at the start of the next step.
+//
+// Warp roles (288 threads): warps 0..7 compute (TMEM lane group = warp % 4, accumulator = warp / 4), warp 8 lane 0
+// issues tcgen05.mma / tcgen05.commit.  Grid = 4 x ceil(B/N) x 2 directions CTAs (B=256, N=16: 128 CTAs).
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "tc_ptx.cuh"
+
+namespace deer {
+namespace tc {
+
+constexpr int QH = 256;        // hidden size
+constexpr int QC = 4;          // cluster size
+constexpr int QU = QH / QC;    // hidden units per CTA (64)
+constexpr int QTHREADS = 288;  // 8 compute warps + 1 control warp
+constexpr int QW_BYTES = 2 * 128 * QH * 2;  // resident A operand: 2 accumulators x 128 rows x 256 k x 16 bit = 128 KB
+constexpr int Q_WCOL = 64;     // TMEM column where the resident A operand starts (TS mode)
+
+// ------------------------------------------------------------------------------------------------- extra PTX
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_v4(uint32_t raddr, uint4 v) {
+  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(raddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+// async-proxy bulk copy local shared -> (remote) shared of a cluster peer; completes `bytes` on the peer's mbarrier
+__device__ __forceinline__ void bulk_copy_to_peer(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes,
+                                                  uint32_t mbar_cluster) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   dst_cluster),
+               "r"(src_cta), "r"(bytes), "r"(mbar_cluster)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t raddr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (++spins > (1u << 26)) {
+      printf("deer lstm_cluster: cluster mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void umma_f16_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tmem_ld_row(uint32_t taddr, float* v) {
+  if constexpr (N == 16) {
+    tmem_ld16(taddr, v);
+  } else {
+    tmem_ld32(taddr, v);
+  }
+}
+// kind::f16 instruction descriptor: D fp32, A/B format fmt (0 = F16, 1 = BF16), both K-major
+__host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t fmt, int M, int N) {
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ uint32_t pack_bf2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+template <bool BF>
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  return BF ? pack_bf2(a, b) : pack_h2(a, b);
+}
+
+// byte offset of 16-byte chunk `c` (0..7) of row `row` inside a K-major SWIZZLE_128B tile whose 8-row groups are 1024 B apart
+__device__ __forceinline__ uint32_t sw128(int row, int c) {
+  return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((c ^ (row & 7)) << 4));
+}
+
+template <int N>
+struct QLayout {
+  static constexpr int NQ = N / 4;                   // batch columns per cell thread
+  static constexpr int ROWF = N + 4;                 // padded fp32 row (floats) of the transpose / partial tiles
+  static constexpr int HB_BYTES = N * QH * 2;        // one B-operand tile: N rows x 256 k x 16 bit
+  static constexpr int ACT_BYTES = 8 * 32 * ROWF * 4;  // forward: per-warp activation transpose tiles
+  static constexpr int SH_BYTES = 2 * 8 * N * 16;      // forward: double-buffered per-warp fp16 h blocks [N cols][8 units]
+  static constexpr int PART_BYTES = QC * QU * ROWF * 4;  // backward: one buffer of partial-dh slots [src][unit][N]
+  static constexpr int PSTAGE_BYTES = 2 * 8 * 32 * ROWF * 4;  // backward: double-buffered per-warp partial rows
+};
+
+struct LstmClusterParams {
+  float* gates;        // [T,B,2,4H]  fwd: in pre-activations, out (keep) activated gates; bwd: in gates, out dpre
+  const float* w_fwd;  // [4H,H]
+  const float* w_rev;  // [4H,H]
+  float* h_out;        // fwd: [T,B,2H] out
+  float* c_all;        // [T,B,2,H] fwd: out or null; bwd: in
+  const float* dh_out; // bwd: [T,B,2H]
+  int T, B, ntiles, keep;
+  long long* prof;     // optional clock64 trace of block 0 (tools/lstm_probe.py --prof), else null
+};
+constexpr int Q_PROF_S0 = 64, Q_PROF_STEPS = 4, Q_PROF_SLOTS = 8;
+#define Q_PROF(slot)                                                                               \
+  do {                                                                                             \
+    if (p.prof && blockIdx.x == 0 && s >= Q_PROF_S0 && s < Q_PROF_S0 + Q_PROF_STEPS)               \
+      p.prof[(s - Q_PROF_S0) * Q_PROF_SLOTS + (slot)] = clock64();                                 \
+  } while (0)
+
+// ================================================================================================ forward
+template <int N, bool TS>
+__global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
+    lstm_fwd_cluster_kernel(const LstmClusterParams p) {
+  using L = QLayout<N>;
+  constexpr int NQ = L::NQ, ROWF = L::ROWF;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* wsm = smem;                                   // SS: 128 KB resident W (unused in TS mode)
+  uint8_t* hbuf = smem + (TS ? 0 : QW_BYTES);            // 2 x HB_BYTES
+  float* stage_act = reinterpret_cast<float*>(hbuf + 2 * L::HB_BYTES);
+  __half* stage_h = reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(stage_act) + L::ACT_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stage_h) + L::SH_BYTES);
+  uint64_t* h_full = bars;        // [2]
+  uint64_t* mma_done = bars + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t r = cluster_ctarank();
+  const int cid = blockIdx.x / QC;
+  const int tile = cid % p.ntiles, dir = cid / p.ntiles;
+  const int b0 = tile * N;
+  const int T = p.T, B = p.B;
+  const float* __restrict__ W = dir ? p.w_rev : p.w_fwd;
+
+  // ---- one-time setup
+  if (threadIdx.x == 0) {
+    mbar_init(&h_full[0], 1);
+    mbar_init(&h_full[1], 1);
+    mbar_init(mma_done, 1);
+    fence_barrier_init();
+    // each phase of h_full[b] = one arming arrival + N x 256 fp16 of h landing from the 4 CTAs (async proxy)
+    if (T > 1) mbar_expect_tx(&h_full[0], L::HB_BYTES);
+    if (T > 2) mbar_expect_tx(&h_full[1], L::HB_BYTES);
+  }
+  if (warp == 8) tmem_alloc(tmem_slot, TS ? 512 : 64);
+  if constexpr (!TS) {
+    // W_hh rows of this CTA -> fp16, K-major SWIZZLE_128B: [acc a][k-block 4][128 rows x 128 B]; row m = 4*unit + gate
+    for (int idx = threadIdx.x; idx < 2 * 128 * 32; idx += QTHREADS) {
+      const int kc = idx & 31, m = (idx >> 5) & 127, a = idx >> 12;
+      const int g = m & 3, u = a * 32 + (m >> 2);
+      const float4* src = reinterpret_cast<const float4*>(W + (size_t)(g * QH + (int)r * QU + u) * QH + kc * 8);
+      const float4 x0 = __ldg(src), x1 = __ldg(src + 1);
+      uint4 v;
+      v.x = pack_h2(x0.x, x0.y); v.y = pack_h2(x0.z, x0.w); v.z = pack_h2(x1.x, x1.y); v.w = pack_h2(x1.z, x1.w);
+      *reinterpret_cast<uint4*>(wsm + a * 65536 + (kc >> 3) * 16384 + sw128(m, kc & 7)) = v;
+    }
+    fence_proxy_async_smem();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if constexpr (TS) {
+    if (warp < 8) {
+      // resident A operand in TMEM: lane = row m of accumulator a, 128 columns = 256 fp16 (2 per column, low half first)
+      const int a = warp >> 2, sub = warp & 3, m = sub * 32 + lane;
+      const int g = m & 3, u = a * 32 + (m >> 2);
+      const float* src = W + (size_t)(g * QH + (int)r * QU + u) * QH;
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ch++) {
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+          const float4 x = __ldg(reinterpret_cast<const float4*>(src + ch * 64) + i);
+          reinterpret_cast<uint32_t*>(v)[2 * i] = pack_h2(x.x, x.y);
+          reinterpret_cast<uint32_t*>(v)[2 * i + 1] = pack_h2(x.z, x.w);
+        }
+        tmem_st32(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(Q_WCOL + a * 128 + ch * 32), v);
+      }
+      tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
+  cluster_sync_all();  // every CTA's barriers are initialised before any peer signals them
+
+  if (warp == 8) {
+    // =================================================================== MMA issuer (whole warp, one elected lane issues)
+    {
+      constexpr uint32_t idesc = make_idesc_f16(0, 128, N);
+      const uint32_t tb = warp_uniform(tmem_base);
+      const bool leader = elect_one();
+      for (int s = 0; s < T; s++) {
+        if (s == 0) {
+          if (leader) mbar_arrive(mma_done);  // h_{-1} = 0: the gates of step 0 are the input projection alone
+          continue;
+        }
+        mbar_wait(&h_full[(s - 1) & 1], (uint32_t)(((s - 1) >> 1) & 1));
+        if (leader) Q_PROF(0);
+        if (leader && s + 2 < T) mbar_expect_tx(&h_full[(s - 1) & 1], L::HB_BYTES);  // re-arm for h_{s+1}
+        tc_fence_after();
+        const uint32_t hb = smem_u32(hbuf) + ((s - 1) & 1) * L::HB_BYTES;
+        if (leader) {
+#pragma unroll
+        for (int a = 0; a < 2; a++) {
+#pragma unroll
+          for (int k = 0; k < 16; k++) {
+            // B operand, K-major no-swizzle: [32 k-chunks][N rows][16 B]; 8x16B core matrices, SBO 128 B, LBO N*16 B
+            const uint64_t bd = make_smem_desc(hb + (2 * k) * (N * 16), N * 16, 128, 0);
+            if constexpr (TS) {
+              umma_f16_ts(tb + a * N, tb + Q_WCOL + a * 128 + k * 8, bd, idesc, k > 0 ? 1u : 0u);
+            } else {
+              const uint64_t ad =
+                  make_smem_desc(smem_u32(wsm) + a * 65536 + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024, 2);
+              umma_f16_ss(tb + a * N, ad, bd, idesc, k > 0 ? 1u : 0u);
+            }
+          }
+        }
+        umma_commit(mma_done);
+        Q_PROF(1);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // =================================================================== gate / cell epilogue
+    const int a = warp >> 2, sub = warp & 3;
+    const int j = lane >> 2, g = lane & 3;        // gate-row role: unit j of this warp, gate g
+    const int ul = a * 32 + sub * 8 + j;          // unit inside the CTA
+    const int ug = (int)r * QU + ul;              // unit inside the direction
+    const uint32_t tacc = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(a * N);
+    float* sa = stage_act + warp * (32 * ROWF);
+    __half* sh_base = stage_h + warp * (2 * N * 8);
+    const float sc = (g == 2) ? 2.f : 1.f;        // tanh(x) = 2*sigmoid(2x) - 1 keeps the warp convergent
+    const int q = g;                              // cell role: columns [q*NQ, q*NQ+NQ) of unit j
+    float cst[NQ];
+#pragma unroll
+    for (int i = 0; i < NQ; i++) cst[i] = 0.f;
+    float pre[N];
+    auto load_pre = [&](int s) {
+      const int t = dir ? T - 1 - s : s;
+      const float* src = p.gates + (((long long)t * B + b0) * 2 + dir) * (4 * QH) + g * QH + ug;
+#pragma unroll
+      for (int n = 0; n < N; n++) pre[n] = (b0 + n < B) ? __ldcs(src + (long long)n * (8 * QH)) : 0.f;
+    };
+    load_pre(0);
+    for (int s = 0; s < T; s++) {
+      const int t = dir ? T - 1 - s : s;
+      __half* sh = sh_base + (s & 1) * (N * 8);
+      mbar_wait(mma_done, (uint32_t)(s & 1));
+      if (warp == 0 && lane == 0) Q_PROF(2);
+      tc_fence_after();
+      float x[N];
+      if (s > 0) {
+        tmem_ld_row<N>(tacc, x);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int n = 0; n < N; n++) x[n] = 0.f;
+      }
+      tc_fence_before();
+      float* grow = p.gates + (((long long)t * B + b0) * 2 + dir) * (4 * QH) + g * QH + ug;
+#pragma unroll
+      for (int n = 0; n < N; n++) {
+        const float z = (x[n] + pre[n]) * sc;
+        x[n] = fmaf(sc, __fdividef(1.f, 1.f + __expf(-z)), 1.f - sc);
+        if (p.keep && b0 + n < B) grow[(long long)n * (8 * QH)] = x[n];
+      }
+#pragma unroll
+      for (int n = 0; n < N; n += 4)
+        *reinterpret_cast<float4*>(sa + lane * ROWF + n) = make_float4(x[n], x[n + 1], x[n + 2], x[n + 3]);
+      if (s + 1 < T) load_pre(s + 1);  // in flight across the cell update and the exchange
+      __syncwarp();
+      if (warp == 0 && lane == 0) Q_PROF(3);
+      float gi[NQ], gf[NQ], gg[NQ], go[NQ];
+#pragma unroll
+      for (int i = 0; i < NQ; i += 4) {
+        const float4 vi = *reinterpret_cast<const float4*>(sa + (4 * j + 0) * ROWF + q * NQ + i);
+        const float4 vf = *reinterpret_cast<const float4*>(sa + (4 * j + 1) * ROWF + q * NQ + i);
+        const float4 vg = *reinterpret_cast<const float4*>(sa + (4 * j + 2) * ROWF + q * NQ + i);
+        const float4 vo = *reinterpret_cast<const float4*>(sa + (4 * j + 3) * ROWF + q * NQ + i);
+        gi[i] = vi.x; gi[i + 1] = vi.y; gi[i + 2] = vi.z; gi[i + 3] = vi.w;
+        gf[i] = vf.x; gf[i + 1] = vf.y; gf[i + 2] = vf.z; gf[i + 3] = vf.w;
+        gg[i] = vg.x; gg[i + 1] = vg.y; gg[i + 2] = vg.z; gg[i + 3] = vg.w;
+        go[i] = vo.x; go[i + 1] = vo.y; go[i + 2] = vo.z; go[i + 3] = vo.w;
+      }
+      const long long row0 = (long long)t * B + b0 + q * NQ;
+#pragma unroll
+      for (int i = 0; i < NQ; i++) {
+        const float cn = fmaf(gf[i], cst[i], gi[i] * gg[i]);
+        cst[i] = cn;
+        const float hv = go[i] * tanh_f(cn);
+        const bool ok = b0 + q * NQ + i < B;
+        if (ok) {
+          p.h_out[(row0 + i) * (2 * QH) + dir * QH + ug] = hv;
+          if (p.c_all) p.c_all[((row0 + i) * 2 + dir) * QH + ug] = cn;
+        }
+        sh[(q * NQ + i) * 8 + j] = __float2half_rn(hv);
+      }
+      if (warp == 0 && lane == 0) Q_PROF(4);
+      if (s + 1 < T) {
+        // all-gather: this warp's [N cols x 8 units] fp16 block is k-chunk 8r+4a+sub of every CTA's B operand; one
+        // async-proxy bulk copy per destination, completion counted on the destination's h_full barrier
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane < QC) {
+          const uint32_t dst = smem_u32(hbuf) + (s & 1) * L::HB_BYTES + ((int)r * 8 + 4 * a + sub) * (N * 16);
+          bulk_copy_to_peer(mapa_u32(dst, (uint32_t)lane), smem_u32(sh), N * 16,
+                            mapa_u32(smem_u32(&h_full[s & 1]), (uint32_t)lane));
+        }
+        if (warp == 0 && lane == 0) Q_PROF(5);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // no CTA retires while a peer may still address its shared memory
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TS ? 512 : 64);
+  }
+}
+
+// ================================================================================================ backward
+template <int N, bool TS>
+__global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
+    lstm_bwd_cluster_kernel(const LstmClusterParams p) {
+  using L = QLayout<N>;
+  constexpr int NQ = L::NQ, ROWF = L::ROWF;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* wsm = smem;                                   // SS: 128 KB resident W^T slice
+  uint8_t* bsm = smem + (TS ? 0 : QW_BYTES);             // B operand: dpre tile [N rows x 256 k] bf16
+  float* part = reinterpret_cast<float*>(bsm + L::HB_BYTES);  // [2][QC src][QU units][ROWF]
+  float* pstage = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(part) + 2 * L::PART_BYTES);  // [8 warps][2][32][ROWF]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(pstage) + L::PSTAGE_BYTES);
+  uint64_t* part_full = bars;     // [2]
+  uint64_t* b_ready = bars + 2;
+  uint64_t* mma_done = bars + 3;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t r = cluster_ctarank();
+  const int cid = blockIdx.x / QC;
+  const int tile = cid % p.ntiles, dir = cid / p.ntiles;
+  const int b0 = tile * N;
+  const int T = p.T, B = p.B;
+  const float* __restrict__ W = dir ? p.w_rev : p.w_fwd;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&part_full[0], 1);
+    mbar_init(&part_full[1], 1);
+    mbar_init(b_ready, 8);
+    mbar_init(mma_done, 1);
+    fence_barrier_init();
+    // each phase of part_full[b] = one arming arrival + the 4 sources' [64 x ROWF] partial-dh rows (async proxy)
+    if (T > 1) mbar_expect_tx(&part_full[0], L::PART_BYTES);
+    if (T > 2) mbar_expect_tx(&part_full[1], L::PART_BYTES);
+  }
+  if (warp == 8) tmem_alloc(tmem_slot, TS ? 512 : 64);
+  if constexpr (!TS) {
+    // A[m = hidden unit (2 x 128)][k = 4*unit_local + gate] = W_hh[gate*256 + 64r + unit_local][m], bf16, K-major SW128
+    for (int idx = threadIdx.x; idx < 2 * 32 * 128; idx += QTHREADS) {
+      const int m = idx & 127, kc = (idx >> 7) & 31, a = idx >> 12;
+      float f[8];
+#pragma unroll
+      for (int e = 0; e < 8; e++) {
+        const int ul = kc * 2 + (e >> 2), g = e & 3;
+        f[e] = __ldg(W + (size_t)(g * QH + (int)r * QU + ul) * QH + a * 128 + m);
+      }
+      uint4 v;
+      v.x = pack_bf2(f[0], f[1]); v.y = pack_bf2(f[2], f[3]); v.z = pack_bf2(f[4], f[5]); v.w = pack_bf2(f[6], f[7]);
+      *reinterpret_cast<uint4*>(wsm + a * 65536 + (kc >> 3) * 16384 + sw128(m, kc & 7)) = v;
+    }
+    fence_proxy_async_smem();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if constexpr (TS) {
+    if (warp < 8) {
+      const int a = warp >> 2, sub = warp & 3, m = a * 128 + sub * 32 + lane;
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ch++) {  // 64 k = 16 units x 4 gates per chunk
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; i++) {
+          const int k0 = ch * 64 + 2 * i;
+          const float f0 = __ldg(W + (size_t)((k0 & 3) * QH + (int)r * QU + (k0 >> 2)) * QH + m);
+          const float f1 = __ldg(W + (size_t)(((k0 + 1) & 3) * QH + (int)r * QU + ((k0 + 1) >> 2)) * QH + m);
+          reinterpret_cast<uint32_t*>(v)[i] = pack_bf2(f0, f1);
+        }
+        tmem_st32(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(Q_WCOL + a * 128 + ch * 32), v);
+      }
+      tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
+  cluster_sync_all();
+
+  if (warp == 8) {
+    // =================================================================== MMA issuer (whole warp, one elected lane issues)
+    {
+      constexpr uint32_t idesc = make_idesc_f16(1, 128, N);
+      const uint32_t tb = warp_uniform(tmem_base);
+      const bool leader = elect_one();
+      for (int s = 0; s + 1 < T; s++) {
+        mbar_wait(b_ready, (uint32_t)(s & 1));
+        if (leader) Q_PROF(0);
+        // every cell thread has consumed the partials of step s-1: re-arm that buffer for step s+1
+        if (leader && s >= 1 && s + 2 < T) mbar_expect_tx(&part_full[(s - 1) & 1], L::PART_BYTES);
+        tc_fence_after();
+        const uint32_t bb = smem_u32(bsm);
+        if (leader) {
+#pragma unroll
+        for (int a = 0; a < 2; a++) {
+#pragma unroll
+          for (int k = 0; k < 16; k++) {
+            const uint64_t bd = make_smem_desc(bb + (k >> 2) * (N * 128) + (k & 3) * 32, 16, 1024, 2);
+            if constexpr (TS) {
+              umma_f16_ts(tb + a * N, tb + Q_WCOL + a * 128 + k * 8, bd, idesc, k > 0 ? 1u : 0u);
+            } else {
+              const uint64_t ad =
+                  make_smem_desc(smem_u32(wsm) + a * 65536 + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024, 2);
+              umma_f16_ss(tb + a * N, ad, bd, idesc, k > 0 ? 1u : 0u);
+            }
+          }
+        }
+        umma_commit(mma_done);
+        Q_PROF(1);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    const int a = warp >> 2, sub = warp & 3;
+    const int j = lane >> 2, q = lane & 3;        // cell role: unit j of this warp, columns [q*NQ, q*NQ+NQ)
+    const int ul = a * 32 + sub * 8 + j;
+    const int ug = (int)r * QU + ul;
+    // row role (partial-dh scatter): accumulator a, TMEM lane sub*32+lane -> hidden unit a*128 + sub*32 + lane
+    const uint32_t tacc = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(a * N);
+    const uint32_t dst_cta = (uint32_t)(2 * a + (sub >> 1));
+    float dc[NQ];
+#pragma unroll
+    for (int i = 0; i < NQ; i++) dc[i] = 0.f;
+
+    float vi[NQ], vf[NQ], vg[NQ], vo[NQ], vc[NQ], vcp[NQ], vdh[NQ];
+    auto load_step = [&](int s) {
+      const int t = dir ? s : T - 1 - s;            // reverse of the forward order
+      const int tp = dir ? t + 1 : t - 1;           // forward-previous time step (c_{prev})
+      const bool first = dir ? (t == T - 1) : (t == 0);
+#pragma unroll
+      for (int i = 0; i < NQ; i++) {
+        const int b = b0 + q * NQ + i;
+        if (b < B) {
+          const long long row = (long long)t * B + b;
+          const float* gp = p.gates + (row * 2 + dir) * (4 * QH) + ug;
+          vi[i] = __ldcs(gp); vf[i] = __ldcs(gp + QH); vg[i] = __ldcs(gp + 2 * QH); vo[i] = __ldcs(gp + 3 * QH);
+          vc[i] = __ldcs(p.c_all + (row * 2 + dir) * QH + ug);
+          vcp[i] = first ? 0.f : __ldcs(p.c_all + (((long long)tp * B + b) * 2 + dir) * QH + ug);
+          vdh[i] = __ldcs(p.dh_out + row * (2 * QH) + dir * QH + ug);
+        } else {
+          vi[i] = vf[i] = vg[i] = vo[i] = vc[i] = vcp[i] = vdh[i] = 0.f;
+        }
+      }
+    };
+    load_step(0);
+    for (int s = 0; s < T; s++) {
+      const int t = dir ? s : T - 1 - s;
+      float dh[NQ];
+#pragma unroll
+      for (int i = 0; i < NQ; i++) dh[i] = vdh[i];
+      if (s > 0) {
+        mbar_wait(&part_full[(s - 1) & 1], (uint32_t)(((s - 1) >> 1) & 1));
+        if (warp == 0 && lane == 0) Q_PROF(2);
+        const float* ps = part + ((s - 1) & 1) * (QC * QU * ROWF) + ul * ROWF + q * NQ;
+#pragma unroll
+        for (int src = 0; src < QC; src++) {
+#pragma unroll
+          for (int i = 0; i < NQ; i += 4) {
+            const float4 v = *reinterpret_cast<const float4*>(ps + src * (QU * ROWF) + i);
+            dh[i] += v.x; dh[i + 1] += v.y; dh[i + 2] += v.z; dh[i + 3] += v.w;
+          }
+        }
+      }
+      float* gout = p.gates + (((long long)t * B + b0 + q * NQ) * 2 + dir) * (4 * QH) + ug;
+      const int kb = ul >> 4, ch = (ul & 15) >> 1;
+#pragma unroll
+      for (int i = 0; i < NQ; i++) {
+        const float tc_ = tanh_f(vc[i]);
+        const float d_o = dh[i] * tc_;
+        const float dcc = fmaf(dh[i] * vo[i], 1.f - tc_ * tc_, dc[i]);
+        dc[i] = dcc * vf[i];
+        const float pi = dcc * vg[i] * vi[i] * (1.f - vi[i]);
+        const float pf = dcc * vcp[i] * vf[i] * (1.f - vf[i]);
+        const float pg = dcc * vi[i] * (1.f - vg[i] * vg[i]);
+        const float po = d_o * vo[i] * (1.f - vo[i]);
+        if (b0 + q * NQ + i < B) {
+          float* gp = gout + (long long)i * (8 * QH);
+          gp[0] = pi; gp[QH] = pf; gp[2 * QH] = pg; gp[3 * QH] = po;
+        }
+        if (s + 1 < T) {
+          const int n = q * NQ + i;
+          uint2 v;
+          v.x = pack_bf2(pi, pf);
+          v.y = pack_bf2(pg, po);
+          *reinterpret_cast<uint2*>(bsm + kb * (N * 128) + sw128(n, ch) + (ul & 1) * 8) = v;
+        }
+      }
+      if (s + 1 < T) {
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(b_ready);
+        if (warp == 0 && lane == 0) Q_PROF(3);
+        load_step(s + 1);  // next step's operands stream in while the tensor core and the exchange run
+        mbar_wait(mma_done, (uint32_t)(s & 1));
+        if (warp == 0 && lane == 0) Q_PROF(4);
+        tc_fence_after();
+        float x[N];
+        tmem_ld_row<N>(tacc, x);
+        tmem_ld_wait();
+        // reduce-scatter: this warp's 32 accumulator rows (hidden units of CTA dst_cta) go to that CTA's slot
+        // [buf][src r][rows] with one async-proxy bulk copy; completion is counted on its part_full barrier
+        float* st = pstage + (warp * 2 + (s & 1)) * (32 * ROWF);
+#pragma unroll
+        for (int n = 0; n < N; n += 4)
+          *reinterpret_cast<float4*>(st + lane * ROWF + n) = make_float4(x[n], x[n + 1], x[n + 2], x[n + 3]);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          const uint32_t slot =
+              smem_u32(part) + (uint32_t)(((s & 1) * QC + (int)r) * QU + (sub & 1) * 32) * (ROWF * 4);
+          bulk_copy_to_peer(mapa_u32(slot, dst_cta), smem_u32(st), 32 * ROWF * 4,
+                            mapa_u32(smem_u32(&part_full[s & 1]), dst_cta));
+        }
+        if (warp == 0 && lane == 0) Q_PROF(5);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TS ? 512 : 64);
+  }
+}
+
+template <int N, bool TS>
+constexpr int fwd_smem_bytes() {
+  using L = QLayout<N>;
+  // >= 120 KB even in TS mode: one CTA per SM, so a 512-column TMEM allocation can never wait on a co-resident CTA
+  constexpr int need = (TS ? 0 : QW_BYTES) + 2 * L::HB_BYTES + L::ACT_BYTES + L::SH_BYTES + 64 + 1024;
+  return need > 120 * 1024 ? need : 120 * 1024;
+}
+template <int N, bool TS>
+constexpr int bwd_smem_bytes() {
+  using L = QLayout<N>;
+  constexpr int need = (TS ? 0 : QW_BYTES) + L::HB_BYTES + 2 * L::PART_BYTES + L::PSTAGE_BYTES + 64 + 1024;
+  return need > 120 * 1024 ? need : 120 * 1024;
+}
+
+}  // namespace tc
+
+static int g_lstm_ts = 1;      // resident operand in TMEM (1) or in shared memory (0)
+static int g_lstm_tile = 0;    // 0 auto, else forced N (16 or 32)
+static long long* g_lstm_prof = nullptr;
+void lstm_cluster_set_profile(long long* buf) { g_lstm_prof = buf; }
+void lstm_cluster_set_option(int ts, int tile) {
+  if (ts >= 0) g_lstm_ts = ts ? 1 : 0;
+  if (tile >= 0) g_lstm_tile = tile;
+}
+
+bool lstm_cluster_supported(const float* gates, const float* w_fwd, const float* w_rev, int H) {
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  return H == tc::QH && al16(gates) && al16(w_fwd) && al16(w_rev);
+}
+
+static int pick_tile(int B) {
+  if (g_lstm_tile == 16 || g_lstm_tile == 32) return g_lstm_tile;
+  // 4-CTA clusters: at most ~33 are co-resident on 148 SMs; prefer the narrow tile while one wave still covers B
+  return (2 * ((B + 15) / 16) <= 32) ? 16 : 32;
+}
+
+template <int N, bool TS>
+static int launch_fwd(const tc::LstmClusterParams& p, cudaStream_t stream) {
+  constexpr int smem = tc::fwd_smem_bytes<N, TS>();
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(tc::lstm_fwd_cluster_kernel<N, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return cuda_status(e, "lstm_fwd_cluster smem attribute");
+    attr = true;
+  }
+  DEER_LAUNCH((tc::lstm_fwd_cluster_kernel<N, TS>), tc::QC * p.ntiles * 2, tc::QTHREADS, smem, stream, p);
+  return DEER_OK;
+}
+template <int N, bool TS>
+static int launch_bwd(const tc::LstmClusterParams& p, cudaStream_t stream) {
+  constexpr int smem = tc::bwd_smem_bytes<N, TS>();
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(tc::lstm_bwd_cluster_kernel<N, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return cuda_status(e, "lstm_bwd_cluster smem attribute");
+    attr = true;
+  }
+  DEER_LAUNCH((tc::lstm_bwd_cluster_kernel<N, TS>), tc::QC * p.ntiles * 2, tc::QTHREADS, smem, stream, p);
+  return DEER_OK;
+}
+
+int lstm_fwd_cluster(float* gates, const float* w_fwd, const float* w_rev, float* h_out, float* c_all, int T, int B,
+                     int keep, cudaStream_t stream) {
+  const int N = pick_tile(B);
+  tc::LstmClusterParams p{gates, w_fwd, w_rev, h_out, c_all, nullptr, T, B, (B + N - 1) / N, keep, g_lstm_prof};
+  if (N == 16) return g_lstm_ts ? launch_fwd<16, true>(p, stream) : launch_fwd<16, false>(p, stream);
+  return g_lstm_ts ? launch_fwd<32, true>(p, stream) : launch_fwd<32, false>(p, stream);
+}
+
+int lstm_bwd_cluster(float* gates, const float* w_fwd, const float* w_rev, const float* c_all, const float* dh_out,
+                     int T, int B, cudaStream_t stream) {
+  const int N = pick_tile(B);
+  tc::LstmClusterParams p{gates, w_fwd, w_rev, nullptr, const_cast<float*>(c_all), dh_out, T, B, (B + N - 1) / N, 1,
+                          g_lstm_prof};
+  if (N == 16) return g_lstm_ts ? launch_bwd<16, true>(p, stream) : launch_bwd<16, false>(p, stream);
+  return launch_bwd<32, true>(p, stream);  // the N=32 tiles + 128 KB of smem-resident weights exceed 227 KB
+}
+
+}  // namespace deer
