@@ -290,36 +290,84 @@ def main():
         dist.destroy_process_group()
 
 
-def roofline_probe(torch, ops, dev, pk):
-    """Time the dominant kernel alone (CUDA events on the launching stream): the per-step recurrent GEMM of the LSTM,
-    gates_t[B,2,4H] += h_{t-1}[B,2,H] W_hh^T, both directions in one launch."""
-    B, H = TRAIN_B, 256
-    n_buf = 16  # rotate operands so each launch misses L2-resident outputs of the previous one
-    gates = torch.randn(n_buf, B, 2, 4 * H, device=dev)
-    h = torch.randn(n_buf, B, 2 * H, device=dev)
-    w = torch.randn(2, 4 * H, H, device=dev) * 0.05
-
-    def launch(i):
-        j = i % n_buf
-        ops.gemm(h[j], 2 * H, 0, w, H, 1, gates[j], 8 * H, B, 4 * H, H, beta=1.0, batch=2, sA=H, sB=4 * H * H, sC=4 * H)
-
-    for i in range(10):
-        launch(i)
+def _time_launches(torch, fn, n, warm=5):
+    for i in range(warm):
+        fn(i)
     torch.cuda.synchronize()
-    n = 200
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(n):
-        launch(i)
+        fn(i)
     e1.record()
     torch.cuda.synchronize()
-    us = e0.elapsed_time(e1) * 1e3 / n
-    flop = 2.0 * B * 4 * H * H * 2
+    return e0.elapsed_time(e1) * 1e3 / n   # us per launch
+
+
+def roofline_probe(torch, ops, dev, pk):
+    """Kernels timed alone with CUDA events on the launching stream (operands rotate through buffers larger than L2).
+
+    Headline = the dominant kernel family of the training step, the tcgen05 GEMM, on its largest instance: the
+    time-batched layer-1 LSTM input projection gates[B*T,1024] = h0[B*T,512] W_ih^T (one direction).
+    Extra entries: the fused NIG head+loss kernels at a size where HBM traffic dominates (north-star target: fraction
+    of HBM peak) and the persistent LSTM recurrence (latency-bound: us per step)."""
+    B, T, H = TRAIN_B, TA, 256
+    M, N, K = B * T, 4 * H, 2 * H
+    nbuf = 3   # 3 x (157 MB A + 315 MB C) > 126 MB L2
+    A = [torch.randn(M, K, device=dev) for _ in range(nbuf)]
+    W = torch.randn(N, K, device=dev) * 0.05
+    bias = torch.randn(N, device=dev)
+    C = [torch.empty(M, 2 * N, device=dev) for _ in range(nbuf)]
+
+    def gemm_launch(i):
+        j = i % nbuf
+        ops.gemm(A[j], K, 0, W, K, 1, C[j], 2 * N, M, N, K, bias=bias)
+
+    us = _time_launches(torch, gemm_launch, 12)
+    flop = 2.0 * M * N * K
     achieved = flop / (us * 1e-6) / 1e12
-    return {"kernel": "gemm_simt_kernel<false,true> (LSTM recurrent step, both directions)", "bound": "tensor",
-            "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops"],
-            "traffic": None, "us_per_launch": us, "flop_per_launch": flop,
-            "peak_source": f"{pk['source']} cuBLAS bf16 burst (MEASURED_PEAKS.json)"}
+    tf32_peak = pk["bf16_tflops"] / 2
+    roof = {"kernel": "tc::gemm_tf32_kernel<0,0> (layer-1 LSTM input projection, [76800,512]x[512,1024], TF32 operands)",
+            "bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+            "frac": achieved / pk["bf16_tflops"], "frac_of_tf32_peak": achieved / tf32_peak, "traffic": None,
+            "us_per_launch": us, "flop_per_launch": flop,
+            "peak_source": f"{pk['source']} cuBLAS bf16 burst (MEASURED_PEAKS.json); TF32 dense peak is half of it"}
+    del A, C
+    torch.cuda.empty_cache()
+
+    # ---- fused NIG head + loss (two phases) at 2^22 samples x 3 dims: 192 B/sample algorithmic traffic
+    n = 1 << 22
+    ev = [torch.randn(n, 3, 4, device=dev) for _ in range(2)]
+    tg = [torch.tanh(torch.randn(n, 3, device=dev)) for _ in range(2)]
+
+    def nig_launch(i):
+        ops.nig_loss_raw(ev[i % 2], None, tg[i % 2], want_nig=True, want_grad=True)
+
+    us_n = _time_launches(torch, nig_launch, 10, warm=3)
+    nbytes = 192.0 * n
+    roof["nig_head_loss"] = {"kernel": "deer::nig_loss_stats_kernel + nig_loss_finish_kernel (B=2^22, 3 dims, train)",
+                             "bound": "hbm", "achieved": nbytes / (us_n * 1e-6) / 1e9, "peak": pk["hbm_gbs"],
+                             "unit": "GB/s", "frac": nbytes / (us_n * 1e-6) / 1e9 / pk["hbm_gbs"],
+                             "us_per_call": us_n, "algorithmic_bytes": nbytes}
+    del ev, tg
+    torch.cuda.empty_cache()
+
+    # ---- persistent LSTM recurrence (one layer, both directions), latency-bound
+    from deer_b200._lib import call, ptr
+    gates = torch.randn(T, B, 2, 4 * H, device=dev)
+    w = [torch.randn(4 * H, H, device=dev) * 0.05 for _ in range(2)]
+    h = torch.empty(T, B, 2 * H, device=dev)
+    c = torch.empty(T, B, 2, H, device=dev)
+    dh = torch.randn(T, B, 2 * H, device=dev) * 1e-3
+    scr = [torch.empty(B, 2, H, device=dev) for _ in range(2)]
+    us_f = _time_launches(torch, lambda i: call("deer_lstm_fwd", ptr(gates), ptr(w[0]), ptr(w[1]), ptr(h), ptr(c), None,
+                                                T, B, H, 0), 5, warm=2)
+    us_b = _time_launches(torch, lambda i: call("deer_lstm_bwd", ptr(gates), ptr(w[0]), ptr(w[1]), ptr(c), ptr(dh),
+                                                ptr(scr[0]), ptr(scr[1]), T, B, H, 0), 5, warm=2)
+    rflop = 2.0 * B * 2 * 4 * H * H * T
+    roof["lstm_recurrence"] = {"kernel": "tc::lstm_fwd_cluster_kernel / lstm_bwd_cluster_kernel (B=256, T=300, H=256, 2 dirs)",
+                               "bound": "latency (serial over T)", "fwd_us_per_step": us_f / T, "bwd_us_per_step": us_b / T,
+                               "fwd_tflops": rflop / (us_f * 1e-6) / 1e12, "bwd_tflops": rflop / (us_b * 1e-6) / 1e12}
+    return roof
 
 
 if __name__ == "__main__":

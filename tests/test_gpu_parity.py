@@ -31,7 +31,10 @@ def _engine():
 
 # ----------------------------------------------------------------------------- primitives
 @pytest.mark.parametrize("M,N,K,ta,tb", [(5, 7, 3, 0, 1), (130, 70, 84, 0, 1), (64, 64, 64, 1, 0), (33, 129, 65, 0, 0),
-                                         (200, 4, 64, 0, 1), (96, 100, 4100, 1, 0), (17, 31, 29, 1, 1)])
+                                         (200, 4, 64, 0, 1), (96, 100, 4100, 1, 0), (17, 31, 29, 1, 1),
+                                         # >= 148 64x64 tiles: the large-tile kernel (the rest use the 32x32 split-K one)
+                                         (1100, 900, 70, 0, 1), (900, 1100, 33, 1, 0), (256, 512, 512, 0, 1),
+                                         (512, 256, 256, 1, 0), (256, 768, 640, 0, 0)])
 def test_gemm_simt(M, N, K, ta, tb):
     g = torch.Generator().manual_seed(M * 131 + N)
     A = torch.randn((K, M) if ta else (M, K), generator=g)
@@ -115,8 +118,12 @@ def test_audio_encoder_golden(golden, name):
     y = enc(x)
     assert_close(y, fx.t("out"), TOL_FP32, "out")
     (y * cu(probe("audio_out", y.shape, m["seed"]))).sum().backward()
-    assert_close(x.grad, fx.t("dx"), TOL_FP32, "dx")
-    check_param_grads(enc, fx, m["seed"], TOL_FP32)
+    # H=256 runs the persistent cluster kernels: BPTT multiplies BF16 operands (fp32 accumulate), so its gradients are
+    # held to the north-star tolerance rather than the fp32-engine one
+    gtol = 2 * TOL if m["hidden"] == 512 else TOL_FP32
+    assert_close(x.grad, fx.t("dx"), gtol, "dx")
+    assert cosine(x.grad, fx.t("dx")) > 0.99999
+    check_param_grads(enc, fx, m["seed"], gtol)
 
 
 @pytest.mark.parametrize("name", ["video_small_train", "video_small_eval", "video_small_f1"])
@@ -296,3 +303,26 @@ def test_composite_ragged_and_eval_vs_oracle(golden):
     ref = O.sequence_model(*batch[:5], sd, training=False)
     for k in ("mu_all", "uncertainty_all", "valence_nu", "arousal_alpha", "dominance_beta", "fused_features"):
         assert_close(out[k], ref[k], TOL, k)
+
+
+def test_trainer_direct_grad_accumulation_matches_autograd():
+    """The trainer lets the backward kernels accumulate into the flat gradient buffer (ops.set_direct_grad_accumulation);
+    the result must equal the autograd-accumulated gradients."""
+    import deer_b200
+    from deer_b200.trainer import DEERDataParallelTrainer
+    from gen_common import seq_inputs
+
+    grads = []
+    for direct in (False, True):
+        torch.manual_seed(3)
+        model = deer_b200.SequenceDEERModel(dropout=0.0).to(DEV).train()
+        tr = DEERDataParallelTrainer(model)
+        tr.direct_grad = direct
+        b = [t.float().to(DEV) for t in seq_inputs(6, 9, 5, 7, seed=11)]
+        batch = {"audio_features": b[0], "video_features": b[1], "text_features": b[2], "attention_mask": b[3],
+                 "linguistic_features": b[4], "targets": b[5]}
+        tr.forward_backward(batch)
+        grads.append(tr.flat.grads.clone())
+        assert not ops._state["direct_grad"]
+    assert float(grads[0].norm()) > 0
+    assert_close(grads[1], grads[0], 1e-5, "flat gradient buffer")

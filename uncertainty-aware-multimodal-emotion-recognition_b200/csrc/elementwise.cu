@@ -303,8 +303,13 @@ int deer_bias_act_bwd(const float* dy, long long ld_dy, const float* y, long lon
                       float* dbias, int M, int N, int act, void* stream) {
   DEER_CHECK_ARG(dy && M > 0 && N > 0, "bias_act_bwd: null/empty");
   DEER_CHECK_ARG(act == DEER_ACT_NONE || y, "bias_act_bwd: act needs y");
-  const int rpb = 256;
-  dim3 grid((unsigned)cdiv(N, 32), (unsigned)cdiv(M, rpb));
+  // rows per block: enough blocks for ~4 per SM even when N is a few hundred columns (the post-pooling layers)
+  const long long gx = cdiv(N, 32);
+  long long want_gy = cdiv(4 * kNumSMs, gx);
+  int rpb = (int)cdiv(M, want_gy);
+  rpb = ((rpb + 7) / 8) * 8;
+  if (rpb < 8) rpb = 8;
+  dim3 grid((unsigned)gx, (unsigned)cdiv(M, rpb));
   DEER_LAUNCH(bias_act_bwd_kernel, grid, dim3(32, 8), 0, stream, dy, ld_dy, y, ld_y, dz, ld_dz, dbias, M, N, act, rpb);
   return DEER_OK;
 }

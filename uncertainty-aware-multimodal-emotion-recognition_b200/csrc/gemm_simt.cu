@@ -112,9 +112,136 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const float* __restrict_
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Small-problem variant: 32x32 output tile per CTA, FOUR 64-thread groups that each reduce a quarter of K (intra-CTA
+// split-K, partials summed through shared memory), register prefetch of the next k-tile.  The ~100 post-pooling
+// GEMMs of a step (M = batch rows, N,K <= 768) have too few 64x64 tiles to occupy 148 SMs and a serial K loop that
+// is pure load->sync->FMA latency; this shape gives 4x more CTAs and a 4x shorter dependent chain, still exact fp32
+// and with the full bias / beta / activation epilogue (no atomics).
+constexpr int SM_T = 32, SM_K = 16, SM_G = 4, SM_LD = SM_T + 4;
+
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256) gemm_small_kernel(const float* __restrict__ A, long long lda,
+                                                         const float* __restrict__ B, long long ldb,
+                                                         float* __restrict__ C, long long ldc, int M, int N, int K,
+                                                         const float* __restrict__ bias, int act, float beta,
+                                                         long long sA, long long sB, long long sC, long long sBias) {
+  __shared__ __align__(16) float sm[2 * SM_G * SM_K * SM_LD];  // operand tiles, later the 3 x 1024 partial sums
+  float(*As)[SM_K][SM_LD] = reinterpret_cast<float(*)[SM_K][SM_LD]>(sm);
+  float(*Bs)[SM_K][SM_LD] = reinterpret_cast<float(*)[SM_K][SM_LD]>(sm + SM_G * SM_K * SM_LD);
+  const int batch = blockIdx.z;
+  A += batch * sA;
+  B += batch * sB;
+  C += batch * sC;
+  if (bias) bias += batch * sBias;
+  const int m0 = blockIdx.y * SM_T, n0 = blockIdx.x * SM_T;
+  const int g = threadIdx.x >> 6, t = threadIdx.x & 63;
+  const int tx = t & 7, ty = t >> 3;  // 8x8 threads, 4x4 outputs each
+  // K range of this group, in whole k-tiles
+  const int ktiles = (K + SM_K - 1) / SM_K;
+  const int per = (ktiles + SM_G - 1) / SM_G;
+  const int kbeg = g * per * SM_K;
+  const int kend = min(K, (g + 1) * per * SM_K);
+
+  // element (row r of the 32-wide tile dim, k) handled by this thread in load slot j (8 slots per operand)
+  float ra[8], rb[8];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      int m, k;
+      if (!TA) { k = t & 15; m = (t >> 4) + 4 * j; } else { m = t & 31; k = (t >> 5) + 2 * j; }
+      const int gm = m0 + m, gk = k0 + k;
+      ra[j] = (gm < M && gk < kend) ? (TA ? __ldg(A + (long long)gk * lda + gm) : __ldg(A + (long long)gm * lda + gk)) : 0.f;
+      int n, kk;
+      if (TB) { kk = t & 15; n = (t >> 4) + 4 * j; } else { n = t & 31; kk = (t >> 5) + 2 * j; }
+      const int gn = n0 + n, gk2 = k0 + kk;
+      rb[j] = (gn < N && gk2 < kend) ? (TB ? __ldg(B + (long long)gn * ldb + gk2) : __ldg(B + (long long)gk2 * ldb + gn)) : 0.f;
+    }
+  };
+  auto stash = [&]() {
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      int m, k;
+      if (!TA) { k = t & 15; m = (t >> 4) + 4 * j; } else { m = t & 31; k = (t >> 5) + 2 * j; }
+      As[g][k][m] = ra[j];
+      int n, kk;
+      if (TB) { kk = t & 15; n = (t >> 4) + 4 * j; } else { n = t & 31; kk = (t >> 5) + 2 * j; }
+      Bs[g][kk][n] = rb[j];
+    }
+  };
+  auto group_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(g + 1) : "memory"); };
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc[i][j] = 0.f;
+
+  if (kbeg < kend) {
+    fetch(kbeg);
+    for (int k0 = kbeg; k0 < kend; k0 += SM_K) {
+      stash();
+      group_sync();
+      if (k0 + SM_K < kend) fetch(k0 + SM_K);  // in flight while this tile is multiplied
+#pragma unroll
+      for (int k = 0; k < SM_K; k++) {
+        const float4 a = *reinterpret_cast<const float4*>(&As[g][k][ty * 4]);
+        const float4 b = *reinterpret_cast<const float4*>(&Bs[g][k][tx * 4]);
+        const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+          for (int j = 0; j < 4; j++) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      }
+      group_sync();
+    }
+  }
+  // ---- cross-group reduction through shared memory (reuses the operand tiles: 4608 floats >= 3 x 1024 partials)
+  __syncthreads();
+  float* red = sm;
+  if (g > 0) {
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) red[(g - 1) * 1024 + (ty * 4 + i) * 32 + tx * 4 + j] = acc[i][j];
+  }
+  __syncthreads();
+  if (g == 0) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int gm = m0 + ty * 4 + i;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int gn = n0 + tx * 4 + j;
+        const int o = (ty * 4 + i) * 32 + tx * 4 + j;
+        float v = acc[i][j] + red[o] + red[1024 + o] + red[2048 + o];
+        if (gm < M && gn < N) {
+          float* c = C + (long long)gm * ldc + gn;
+          if (bias) v += bias[gn];
+          if (beta != 0.f) v += beta * (*c);
+          *c = act_apply(v, act);
+        }
+      }
+    }
+  }
+}
+
 int gemm_simt(const float* A, long long lda, int transA, const float* B, long long ldb, int transB, float* C,
               long long ldc, int M, int N, int K, const float* bias, int act, float beta, int batch, long long sA,
               long long sB, long long sC, long long sBias, cudaStream_t stream) {
+  // small problems (fewer 64x64 tiles than SMs): 32x32 tiles with intra-CTA split-K
+  if ((long long)((N + BN - 1) / BN) * ((M + BM - 1) / BM) * batch < kNumSMs && K <= 4096) {
+    dim3 sgrid((N + SM_T - 1) / SM_T, (M + SM_T - 1) / SM_T, batch);
+#define GOS(TA, TB)                                                                                              \
+  DEER_LAUNCH((gemm_small_kernel<TA, TB>), sgrid, 256, 0, stream, A, lda, B, ldb, C, ldc, M, N, K, bias, act, beta, \
+              sA, sB, sC, sBias)
+    if (!transA && !transB) GOS(false, false);
+    else if (!transA && transB) GOS(false, true);
+    else if (transA && !transB) GOS(true, false);
+    else GOS(true, true);
+#undef GOS
+    return DEER_OK;
+  }
   const int gx = (N + BN - 1) / BN, gy = (M + BM - 1) / BM;
   int splitk = 1;
   if (beta == 1.f && act == DEER_ACT_NONE) {

@@ -24,7 +24,24 @@ ENGINE_AUTO, ENGINE_SIMT, ENGINE_TF32 = 0, 1, 2
 # prone) outputs feed the bias / scorer gradients whose per-tensor cosine otherwise sits at 0.9992, too close to the
 # 0.999 gate (tools/precision_probe.py).
 _state = {"engine": ENGINE_AUTO, "lstm_engine": ENGINE_AUTO, "exact_small_fwd": True, "exact_small_bwd": True,
-          "small_rows": 8192}
+          "small_rows": 8192, "direct_grad": False}
+
+
+def set_direct_grad_accumulation(on: bool):
+    """Trainer mode: parameter gradients are ACCUMULATED by the backward kernels straight into the pre-allocated
+    `param.grad` (views of the trainer's flat gradient buffer, zeroed once per step) and the autograd functions
+    return None for them - no per-parameter temporary, zero-fill or `grad += new` launch."""
+    _state["direct_grad"] = bool(on)
+
+
+def _acc(param, like=None):
+    """(buffer the kernels accumulate d/dparam into, whether it is param.grad itself)."""
+    if param is None:
+        return None, False
+    g = param.grad if (_state["direct_grad"] and param.is_leaf) else None
+    if _state["direct_grad"] and g is not None and g.is_contiguous() and g.dtype == torch.float32 and g.is_cuda:
+        return g, True
+    return torch.zeros_like(param if like is None else like), False
 
 
 def set_gemm_engine(engine: int):
@@ -113,6 +130,7 @@ class _Linear(torch.autograd.Function):
         assert k0 == Ktot, f"input widths {k0} != weight in-features {Ktot}"
         ctx.act = act
         ctx.has_bias = b is not None
+        ctx.params = (w, b)
         ctx.meta = [(ld, k, K) for (_, ld, k, K) in rows]
         ctx.in_shapes = [x.shape for x in xs]
         ctx.save_for_backward(w, y if act != 0 else None, *[r[0] for r in rows])
@@ -123,7 +141,8 @@ class _Linear(torch.autograd.Function):
         w, y, *xs = ctx.saved_tensors
         N, Ktot = w.shape
         dy2, M, _, ld_dy = _rows2d(dy if dy.is_contiguous() else dy.contiguous())
-        db = torch.zeros(N, device=w.device, dtype=torch.float32) if (ctx.has_bias and ctx.needs_input_grad[1]) else None
+        pw, pb = ctx.params
+        db, db_direct = _acc(pb) if (ctx.has_bias and ctx.needs_input_grad[1]) else (None, False)
         if ctx.act != 0:
             dz = torch.empty_like(dy2)
             call("deer_bias_act_bwd", ptr(dy2), ld_dy, ptr(y), N, ptr(dz), N, ptr(db), M, N, ctx.act)
@@ -131,7 +150,7 @@ class _Linear(torch.autograd.Function):
             dz = dy2
             if db is not None:
                 call("deer_bias_act_bwd", ptr(dy2), ld_dy, None, 0, None, 0, ptr(db), M, N, 0)
-        dw = torch.zeros_like(w) if ctx.needs_input_grad[0] else None
+        dw, dw_direct = _acc(pw) if ctx.needs_input_grad[0] else (None, False)
         dxs = []
         for i, x2 in enumerate(xs):
             ld, k0, K = ctx.meta[i]
@@ -143,7 +162,7 @@ class _Linear(torch.autograd.Function):
                 dxs.append(None)
             if dw is not None:
                 gemm(dz, N, 1, x2, ld, 0, dw.data_ptr() + 4 * k0, Ktot, N, K, M, beta=1.0, engine=_bwd_engine(M))
-        return (dw, db, None, None, *dxs)
+        return (None if dw_direct else dw, None if db_direct else db, None, None, *dxs)
 
 
 def linear(x, w, b=None, act="none"):
@@ -164,6 +183,7 @@ class _LayerNorm(torch.autograd.Function):
         call("deer_layernorm_fwd", ptr(x2), ptr(g), ptr(b), ptr(y), ptr(mean), ptr(rstd), M, N, float(eps))
         ctx.save_for_backward(x2, g, mean, rstd)
         ctx.shape = x.shape
+        ctx.params = (g, b)
         return y.view(x.shape)
 
     @staticmethod
@@ -174,10 +194,10 @@ class _LayerNorm(torch.autograd.Function):
         if not dy2.is_contiguous():
             dy2 = dy2.contiguous()
         dx = torch.empty_like(x2)
-        dg = torch.zeros_like(g)
-        db = torch.zeros_like(g)
+        dg, dg_direct = _acc(ctx.params[0])
+        db, db_direct = _acc(ctx.params[1])
         call("deer_layernorm_bwd", ptr(dy2), ptr(x2), ptr(g), ptr(mean), ptr(rstd), ptr(dx), ptr(dg), ptr(db), M, N)
-        return dx.view(ctx.shape), dg, db, None
+        return dx.view(ctx.shape), None if dg_direct else dg, None if db_direct else db, None
 
 
 def layer_norm(x, g, b, eps=1e-5):
@@ -241,6 +261,7 @@ class _RowDot(torch.autograd.Function):
         call("deer_rowdot_fwd", ptr(h2), ptr(w), ptr(b), ptr(s), M, N)
         ctx.save_for_backward(h2, w)
         ctx.shape = h.shape
+        ctx.params = (w, b)
         return s.view(h.shape[:-1])
 
     @staticmethod
@@ -249,10 +270,10 @@ class _RowDot(torch.autograd.Function):
         M, N = h2.shape
         dsc = ds.reshape(M).contiguous()
         dh = torch.empty_like(h2)
-        dw = torch.zeros_like(w)
-        db = torch.zeros(1, device=h2.device, dtype=torch.float32)
+        dw, dw_direct = _acc(ctx.params[0])
+        db, db_direct = _acc(ctx.params[1])
         call("deer_rowdot_bwd", ptr(dsc), ptr(h2), ptr(w), ptr(dh), ptr(dw), ptr(db), M, N)
-        return dh.view(ctx.shape), dw, db
+        return dh.view(ctx.shape), None if dw_direct else dw, None if db_direct else db
 
 
 def rowdot(h, w, b):
@@ -373,6 +394,7 @@ class _BiLSTMLayer(torch.autograd.Function):
             call("deer_lstm_fwd", ptr(gates), ptr(whf_c), ptr(whr_c), ptr(h), None, ptr(c_work), T, B, H,
                  _state["lstm_engine"])
         ctx.dims = (T, B, In, H)
+        ctx.params = (wif, whf, bif, bhf, wir, whr, bir, bhr)
         return h
 
     @staticmethod
@@ -395,11 +417,12 @@ class _BiLSTMLayer(torch.autograd.Function):
                 gemm(gates.data_ptr() + 4 * G * d, 2 * G, 0, wi, wi.stride(0), 0, dx, In, M, In, G,
                      beta=0.0 if d == 0 else 1.0)
         grads = []
+        P = ctx.params
         for d, (wi, wh) in enumerate(((wif, whf), (wir, whr))):
             gp = gates.data_ptr() + 4 * G * d
-            dwi = torch.zeros_like(wi)
+            dwi, dwi_direct = _acc(P[4 * d], wi)
             gemm(gp, 2 * G, 1, x, In, 0, dwi, In, G, In, M, beta=1.0)
-            dwh = torch.zeros_like(wh)
+            dwh, dwh_direct = _acc(P[4 * d + 1], wh)
             if T > 1:
                 Mr = (T - 1) * B
                 if d == 0:   # rows t=1.. pair with h[t-1]
@@ -408,9 +431,17 @@ class _BiLSTMLayer(torch.autograd.Function):
                     gemm(gp, 2 * G, 1, h.data_ptr() + 4 * (B * 2 * H + H), 2 * H, 0, dwh, H, G, H, Mr, beta=1.0)
             db = torch.zeros(G, device=dev, dtype=torch.float32)
             call("deer_bias_act_bwd", gp, 2 * G, None, 0, None, 0, ptr(db), M, G, 0)
-            grads.append((dwi, dwh, db))
-        (dwif, dwhf, dbf), (dwir, dwhr, dbr) = grads
-        return dx, dwif, dwhf, dbf, dbf, dwir, dwhr, dbr, dbr
+            dbs = []
+            for pb in (P[4 * d + 2], P[4 * d + 3]):   # b_ih and b_hh receive the same gradient
+                tgt, direct = _acc(pb)
+                if direct:
+                    call("deer_axpby", ptr(db), ptr(tgt), ptr(tgt), G, 1.0, 1.0)
+                    dbs.append(None)
+                else:
+                    dbs.append(db)
+            grads.append((None if dwi_direct else dwi, None if dwh_direct else dwh, dbs[0], dbs[1]))
+        (dwif, dwhf, dbif, dbhf), (dwir, dwhr, dbir, dbhr) = grads
+        return dx, dwif, dwhf, dbif, dbhf, dwir, dwhr, dbir, dbhr
 
 
 def bilstm_layer(x_tm, wif, whf, bif, bhf, wir, whr, bir, bhr):
@@ -434,6 +465,7 @@ class _Conv1dK3(torch.autograd.Function):
         gemm(col, 3 * Cin, 0, wk, 3 * Cin, 1, y, Cout, B * T, Cout, 3 * Cin, bias=b)
         ctx.save_for_backward(col, wk)
         ctx.dims = (B, T, Cin, Cout)
+        ctx.params = (w, b)
         return y
 
     @staticmethod
@@ -450,11 +482,11 @@ class _Conv1dK3(torch.autograd.Function):
             call("deer_col2im3", ptr(dcol), ptr(dx), B, T, Cin)
         dwk = torch.zeros_like(wk)
         gemm(dy, Cout, 1, col, 3 * Cin, 0, dwk, 3 * Cin, Cout, 3 * Cin, M, beta=1.0)
-        dw = torch.zeros((Cout, Cin, 3), device=dy.device, dtype=torch.float32)
+        dw, dw_direct = _acc(ctx.params[0])
         call("deer_conv3_weight_pack", ptr(dwk), ptr(dw), Cout, Cin, 1)
-        db = torch.zeros(Cout, device=dy.device, dtype=torch.float32)
+        db, db_direct = _acc(ctx.params[1])
         call("deer_bias_act_bwd", ptr(dy), Cout, None, 0, None, 0, ptr(db), M, Cout, 0)
-        return dx, dw, db
+        return dx, None if dw_direct else dw, None if db_direct else db
 
 
 def conv1d_k3(x, w, b):
@@ -481,6 +513,7 @@ class _BNReLU(torch.autograd.Function):
         call("deer_bn_relu_fwd", ptr(x), ptr(mean), ptr(var), ptr(g), ptr(b), ptr(y), M, C, float(eps))
         ctx.save_for_backward(x, y, mean.clone() if not training else mean, var.clone() if not training else var, g)
         ctx.cfg = (M, C, float(eps), bool(training))
+        ctx.params = (g, b)
         return y
 
     @staticmethod
@@ -489,12 +522,12 @@ class _BNReLU(torch.autograd.Function):
         M, C, eps, training = ctx.cfg
         dy = dy.contiguous()
         dx = torch.empty_like(x)
-        dg = torch.zeros_like(g)
-        db = torch.zeros_like(g)
+        dg, dg_direct = _acc(ctx.params[0])
+        db, db_direct = _acc(ctx.params[1])
         scratch = torch.empty((2, C), device=x.device, dtype=torch.float32)
         call("deer_bn_relu_bwd", ptr(dy), ptr(x), ptr(y), ptr(mean), ptr(var), ptr(g), ptr(dx), ptr(dg), ptr(db),
              ptr(scratch), M, C, eps, int(training))
-        return dx, dg, db, None, None, None, None, None, None
+        return dx, None if dg_direct else dg, None if db_direct else db, None, None, None, None, None, None
 
 
 def batchnorm_relu(x, g, b, running_mean, running_var, nbt, training, momentum=0.1, eps=1e-5):
@@ -550,6 +583,7 @@ class _GroupedLinear(torch.autograd.Function):
             gemm(x2, ld, 0, ws[g], ws[g].stride(0), 1, out.data_ptr() + 4 * g * N, G * N, M, N, K, bias=bs[g], act=act,
                  engine=_fwd_engine(M))
         ctx.act, ctx.G = act, G
+        ctx.params = (ws, bs)
         ctx.meta = [(r[3], r[2]) for r in rows]
         ctx.in_shapes = [x.shape for x in xs]
         ctx.save_for_backward(out if act != 0 else None, *ws, *[r[0] for r in rows])
@@ -563,8 +597,9 @@ class _GroupedLinear(torch.autograd.Function):
         dout = dout.contiguous()
         M, _, N = dout.shape
         dev = dout.device
-        dbs = [torch.zeros(N, device=dev, dtype=torch.float32) if ctx.needs_input_grad[2 + G + g] else None
-               for g in range(G)]
+        pws, pbs = ctx.params
+        db_acc = [_acc(pbs[g]) if ctx.needs_input_grad[2 + G + g] else (None, False) for g in range(G)]
+        dbs = [a[0] for a in db_acc]
         dz = torch.empty_like(dout) if act != 0 else dout
         for g in range(G):
             off = 4 * g * N
@@ -578,9 +613,9 @@ class _GroupedLinear(torch.autograd.Function):
             ld, K = ctx.meta[g]
             zp = dz.data_ptr() + 4 * g * N
             if ctx.needs_input_grad[2 + g]:
-                dw = torch.zeros_like(ws[g])
+                dw, direct = _acc(pws[g])
                 gemm(zp, G * N, 1, xs[g], ld, 0, dw, K, N, K, M, beta=1.0, engine=_bwd_engine(M))
-                dws.append(dw)
+                dws.append(None if direct else dw)
             else:
                 dws.append(None)
             if ctx.needs_input_grad[2 + 2 * G + g]:
@@ -589,6 +624,7 @@ class _GroupedLinear(torch.autograd.Function):
                 dxs.append(dx.view(ctx.in_shapes[g]))
             else:
                 dxs.append(None)
+        dbs = [None if a[1] else a[0] for a in db_acc]
         return (None, None, *dws, *dbs, *dxs)
 
 

@@ -78,6 +78,7 @@ class DEERDataParallelTrainer:
         self.step_count = 0
         self.step_tensor = torch.zeros(1, device=dev, dtype=torch.int64)
         ops.set_dropout_step_tensor(self.step_tensor)
+        self.direct_grad = True   # backward kernels accumulate straight into the flat gradient buffer
         self.group_lr = {0: 0.5, 1: 1.0}
         self.last_losses: Optional[torch.Tensor] = None
 
@@ -90,6 +91,14 @@ class DEERDataParallelTrainer:
         """fwd + fused head/loss + bwd; gradients are accumulated into the flat buffer.  Returns losses [5D+2]."""
         model = self.model
         self.flat.grads.zero_()
+        ops.set_direct_grad_accumulation(self.direct_grad)
+        try:
+            return self._forward_backward(batch)
+        finally:
+            ops.set_direct_grad_accumulation(False)
+
+    def _forward_backward(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
+        model = self.model
         out = model(batch["audio_features"], batch["video_features"], batch["text_features"],
                     batch.get("attention_mask"), batch.get("linguistic_features"))
         ev = out[EVIDENCE_KEY]
