@@ -353,16 +353,19 @@ def roofline_probe(torch, ops, dev, pk):
 
     # ---- persistent LSTM recurrence (one layer, both directions), latency-bound
     from deer_b200._lib import call, ptr
-    gates = torch.randn(T, B, 2, 4 * H, device=dev)
+    Bp = (B + 31) // 32 * 32
+    pre = torch.randn(T, B, 2, 4 * H, device=dev)
     w = [torch.randn(4 * H, H, device=dev) * 0.05 for _ in range(2)]
     h = torch.empty(T, B, 2 * H, device=dev)
-    c = torch.empty(T, B, 2, H, device=dev)
+    gact = torch.empty(T * 2 * Bp * 4 * H, device=dev)
+    c = torch.empty(T * 2 * Bp * H, device=dev)
     dh = torch.randn(T, B, 2 * H, device=dev) * 1e-3
-    scr = [torch.empty(B, 2, H, device=dev) for _ in range(2)]
-    us_f = _time_launches(torch, lambda i: call("deer_lstm_fwd", ptr(gates), ptr(w[0]), ptr(w[1]), ptr(h), ptr(c), None,
-                                                T, B, H, 0), 5, warm=2)
-    us_b = _time_launches(torch, lambda i: call("deer_lstm_bwd", ptr(gates), ptr(w[0]), ptr(w[1]), ptr(c), ptr(dh),
-                                                ptr(scr[0]), ptr(scr[1]), T, B, H, 0), 5, warm=2)
+    dpre = torch.empty(T, B, 2, 4 * H, device=dev)
+    db = torch.zeros(2, 4 * H, device=dev)
+    us_f = _time_launches(torch, lambda i: call("deer_lstm_cluster_fwd", ptr(pre), ptr(w[0]), ptr(w[1]), ptr(h), ptr(gact),
+                                                ptr(c), T, B, H), 5, warm=2)
+    us_b = _time_launches(torch, lambda i: call("deer_lstm_cluster_bwd", ptr(gact), ptr(c), ptr(dh), ptr(w[0]), ptr(w[1]),
+                                                ptr(dpre), ptr(db), T, B, H), 5, warm=2)
     rflop = 2.0 * B * 2 * 4 * H * H * T
     roof["lstm_recurrence"] = {"kernel": "tc::lstm_fwd_cluster_kernel / lstm_bwd_cluster_kernel (B=256, T=300, H=256, 2 dirs)",
                                "bound": "latency (serial over T)", "fwd_us_per_step": us_f / T, "bwd_us_per_step": us_b / T,

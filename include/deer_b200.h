@@ -37,8 +37,9 @@ extern "C" {
 #define DEER_GEMM_SIMT 1   /* fp32 CUDA-core tiles (exact fp32; small or unaligned shapes) */
 #define DEER_GEMM_TF32 2   /* tcgen05.mma kind::tf32, fp32 accumulate in TMEM, TMA-fed */
 /* LSTM recurrence engines (deer_lstm_fwd/bwd `engine`): DEER_GEMM_SIMT = exact-fp32 stepwise; DEER_GEMM_AUTO/TF32 =
- * persistent 4-CTA-cluster tcgen05 kernels (forward FP16, backward BF16 operands, fp32 accumulation, DSMEM exchange)
- * when H == 256 (stepwise otherwise); 3 = stepwise with TF32 step GEMMs; 4 = round-1 8-CTA TF32 forward kernel */
+ * round-1 8-CTA TF32 persistent forward kernel when H == 256 (stepwise otherwise; backward always stepwise);
+ * 3 = stepwise with TF32 step GEMMs; 4 = same as AUTO.  These natural-layout entry points are the on-device reference;
+ * the production path is deer_lstm_cluster_fwd/bwd below. */
 #define DEER_LSTM_STEPWISE_TF32 3
 #define DEER_LSTM_PERSISTENT_V1 4
 
@@ -148,6 +149,20 @@ int deer_lstm_fwd(float* gates, const float* w_hh_fwd, const float* w_hh_rev, fl
 int deer_lstm_bwd(float* gates, const float* w_hh_fwd, const float* w_hh_rev, const float* c_all, const float* dh_out,
                   float* dh_work, float* dc_work, int T, int B, int H, int engine, void* stream);
 
+/* ---- persistent cluster kernels for the same layer (production path, H == 256; csrc/lstm_cluster.cu).
+ *      Layouts: pre_il / dpre_il are GATE-INTERLEAVED [T,B,2,H,4] (column 4*unit+gate): run the input projection with
+ *      row-interleaved W_ih and bias (deer_gate_rows_interleave), and un-interleave the weight gradients computed from
+ *      dpre_il.  gact (activated gates) and c_blk (cell states) are opaque workspaces private to the fwd/bwd pair:
+ *      T*2*Bp*4H and T*2*Bp*H floats with Bp = B rounded up to a multiple of 32; NULL for inference.
+ *      db_il [2,H,4] accumulates (atomics) the bias gradient = column sums of dpre_il; may be NULL. */
+int deer_lstm_cluster_tile(int B);  /* batch columns per 4-CTA cluster the kernels will use for batch B (16 or 32) */
+int deer_lstm_cluster_fwd(const float* pre_il, const float* w_hh_fwd, const float* w_hh_rev, float* h_out, float* gact,
+                          float* c_blk, int T, int B, int H, void* stream);
+int deer_lstm_cluster_bwd(const float* gact, const float* c_blk, const float* dh_out, const float* w_hh_fwd,
+                          const float* w_hh_rev, float* dpre_il, float* db_il, int T, int B, int H, void* stream);
+/*      rows g*H+u of src [4H,K] -> rows 4u+g of dst (inverse=0) or back (inverse=1); accumulate!=0 adds into dst */
+int deer_gate_rows_interleave(const float* src, float* dst, int H, int K, int inverse, int accumulate, void* stream);
+
 /* ---- NIG head transform (deer.py:90-98; complete_project.py:399-407). evidence [N,4] -> 7 arrays [N] */
 int deer_nig_head_fwd(const float* evidence, float* mu, float* nu, float* alpha, float* beta, float* aleatoric,
                       float* epistemic, float* total, long long N, void* stream);
@@ -196,6 +211,10 @@ int deer_mix_bwd(const float* dout, const float* w, long long ldw, const float* 
 int deer_gate_fwd(const float* g, const float* a, const float* b, float* out, long long n, void* stream);
 int deer_gate_bwd(const float* dout, const float* g, const float* a, const float* b, float* dg, float* da, float* db,
                   long long n, void* stream);
+/* y[m,n] = x[m,n] / t[n] (temperature scaling, complete_project.py:449); backward: dx = dy/t, dt[n] += -sum_m dy x / t^2 */
+int deer_coldiv_fwd(const float* x, const float* t, float* y, long long M, int N, void* stream);
+int deer_coldiv_bwd(const float* dy, const float* x, const float* t, float* dx, float* dt /* accumulates, may be NULL */,
+                    long long M, int N, void* stream);
 /* row softmax over N<=32 columns and backward */
 int deer_softmax_rows_fwd(const float* x, float* y, long long M, int N, void* stream);
 int deer_softmax_rows_bwd(const float* dy, const float* y, float* dx, long long M, int N, void* stream);

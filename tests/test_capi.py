@@ -68,3 +68,17 @@ def test_state_dict_keys_match_reference(golden):
         assert k in sd, k
         assert tuple(sd[k].shape) == tuple(shp), (k, sd[k].shape, shp)
     assert sum(p.numel() for p in model.parameters()) == 9262642
+
+
+def test_pooled_state_dict_keys_match_reference(golden):
+    """CompleteDEERModel (complete_project.py:462): identical parameter names/shapes, 3,918,324 parameters; also
+    importable under the `complete_model` name the reference trainer uses (training.py:31)."""
+    fx = golden("pooled_b16")
+    from deer_b200 import complete_model, complete_project
+    assert complete_model.CompleteDEERModel is complete_project.CompleteDEERModel
+    model = complete_project.CompleteDEERModel(complete_project.ModelConfig())
+    sd = model.state_dict()
+    assert set(sd) == set(fx.shapes)
+    for k, shp in fx.shapes.items():
+        assert tuple(sd[k].shape) == tuple(shp), (k, sd[k].shape, shp)
+    assert sum(p.numel() for p in model.parameters()) == 3918324

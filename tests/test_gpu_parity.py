@@ -326,3 +326,81 @@ def test_trainer_direct_grad_accumulation_matches_autograd():
         assert not ops._state["direct_grad"]
     assert float(grads[0].norm()) > 0
     assert_close(grads[1], grads[0], 1e-5, "flat gradient buffer")
+
+
+def test_pooled_model_golden(golden):
+    """CompleteDEERModel (complete_project.py:462-588) + MultiTaskDEERLoss against the reference's own outputs, loss
+    components and parameter gradients (tests/golden/pooled_b16.npz, generated from the unmodified reference)."""
+    from gen_common import pooled_inputs
+    fx = golden("pooled_b16")
+    m = fx.meta
+    cfg = deer_b200.ModelConfig(dropout=0.0)
+    model = load_fixture_weights(deer_b200.CompleteDEERModel(cfg), fx).to(DEV).train()
+    for mod in model.modules():      # UncertaintyEstimator has a hard-coded Dropout(0.2) (complete_project.py:193);
+        if isinstance(mod, torch.nn.Dropout):   # the golden generator zeroes every dropout the same way
+            mod.p = 0.0
+    a, v, t, y = pooled_inputs(m["B"], m["seed"])
+    out = model(cu(a), cu(v), cu(t))
+    for k in fx.keys("out:"):
+        assert_close(out[k[4:]], fx.t(k), TOL, k)
+    assert out["valence_mu"].shape == (m["B"],) and out["mu_all"].shape == (m["B"], 3)
+    loss = model.compute_loss(out, cu(y))
+    for k in fx.keys("loss:"):
+        if k.endswith("batch_size"):
+            continue
+        ref, got = float(fx.arrays[k]), float(loss[k[5:]])
+        assert abs(got - ref) <= TOL * max(abs(ref), 1e-2), (k, got, ref)
+    loss["total_loss"].backward()
+    check_param_grads(model, fx, m["seed"], 5 * TOL)
+    for k, has in m["has_grad"].items():
+        p = dict(model.named_parameters())[k]
+        if not has:   # query/key projections (single-key attention), calibration layer: exactly no gradient
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
+    # dict-argument call used by the reference driver (run_multimodal_deer.py:719) and the uncertainty accessor
+    with torch.no_grad():
+        out2 = model.eval()({"audio": cu(a), "video": cu(v), "text": cu(t)})
+    pred, unc = model.get_predictions_and_uncertainties(out2)
+    assert "gamma" in out2 and pred.shape == (m["B"], 3) and unc.shape == (m["B"], 3)
+    assert_close(out2["mu_all"], fx.t("out:mu_all"), TOL, "eval mu_all")
+
+
+def test_pooled_model_train_dropout_runs():
+    """Training-mode dropout path (incl. the per-head attention-weight dropout, complete_project.py:172)."""
+    torch.manual_seed(0)
+    model = deer_b200.CompleteDEERModel(deer_b200.ModelConfig()).to(DEV).train()
+    B = 64
+    out = model(torch.randn(B, 84, device=DEV), torch.randn(B, 256, device=DEV), torch.randn(B, 768, device=DEV))
+    loss = model.compute_loss(out, torch.tanh(torch.randn(B, 3, device=DEV)))
+    loss["total_loss"].backward()
+    assert torch.isfinite(loss["total_loss"])
+    g = model.audio_encoder.input_projection[0].weight.grad
+    assert g is not None and torch.isfinite(g).all() and float(g.abs().max()) > 0
+
+
+@pytest.mark.parametrize("B,scale", [(257, 1.5), (4099, 6.0), (65, 12.0)])
+def test_fused_loss_wide_range_vs_oracle(B, scale):
+    """The fused head+loss kernels use MUFU-based softplus / lgamma / digamma: check them far outside the golden
+    fixtures' evidence range (softplus linear branch at x>20, alpha from 1+1e-5 to ~70, tiny nu and beta) against the
+    fp32-precision oracle evaluated in float64 (losses.py:72-348)."""
+    g = torch.Generator().manual_seed(B)
+    e = torch.randn(B, 3, 4, generator=g, dtype=torch.float64) * scale
+    # keep alpha - 1 = softplus(e2) >= ~7e-3: (alpha - 1) is formed in fp32 (ulp(1) = 1.2e-7), so below that the
+    # reference's own fp32 result is ill-conditioned at the 1e-3 level
+    e[:, :, 2] = e[:, :, 2].clamp(min=-5.0)
+    y = torch.tanh(torch.randn(B, 3, generator=g, dtype=torch.float64))
+    ed = e.clone().requires_grad_(True)
+    pred = {}
+    for i, d in enumerate(("valence", "arousal", "dominance")):
+        for k, v in O.nig_from_evidence(ed[:, i:i + 1, :]).items():
+            pred[f"{d}_{k}"] = v
+    ref = O.multitask_deer_loss(pred, y)
+    ref["total_loss"].backward()
+    ec = cu(e).requires_grad_(True)
+    nig_out, losses = ops.fused_head_loss(ec, cu(y))
+    losses[-1].backward()
+    assert abs(float(losses[-1]) - float(ref["total_loss"])) <= TOL * abs(float(ref["total_loss"]))
+    for i, d in enumerate(("valence", "arousal", "dominance")):
+        for j, k in enumerate(("mu", "nu", "alpha", "beta")):
+            assert_close(nig_out[j][:, i], pred[f"{d}_{k}"].detach()[:, 0], 1e-5, f"{d}_{k}")
+    assert cosine(ec.grad, ed.grad) > 0.99999
+    assert_close(ec.grad, ed.grad, TOL, "d loss / d evidence")

@@ -49,7 +49,24 @@ def main():
     dh_out = (torch.randn(T, B, 2 * H, generator=g) * 1e-3).to(dev)
     tag = f"ts={a.ts} tile={a.tile} B={B} T={T} engine={a.engine}"
 
+    Bp = (B + 31) // 32 * 32
+    G = 4 * H
+
+    def il(t):      # [...,4H] natural -> interleaved
+        return t.view(*t.shape[:-1], 4, H).transpose(-1, -2).contiguous().view(t.shape)
+
+    def nat(t):     # interleaved -> natural
+        return t.view(*t.shape[:-1], H, 4).transpose(-1, -2).contiguous().view(t.shape)
+
     def fwd(engine):
+        if engine == AUTO:
+            pre_il = il(pre)
+            h = torch.empty(T, B, 2 * H, device=dev)
+            gact = torch.empty(T * 2 * Bp * G, device=dev)
+            c = torch.empty(T * 2 * Bp * H, device=dev)
+            call("deer_lstm_cluster_fwd", ptr(pre_il), ptr(w[0]), ptr(w[1]), ptr(h), ptr(gact), ptr(c), T, B, H)
+            torch.cuda.synchronize()
+            return gact, h, c
         gates = pre.clone()
         h = torch.empty(T, B, 2 * H, device=dev)
         c = torch.empty(T, B, 2, H, device=dev)
@@ -58,26 +75,32 @@ def main():
         return gates, h, c
 
     def bwd(engine, gates, c):
+        if engine == AUTO:
+            dpre = torch.empty(T, B, 2, G, device=dev)
+            db = torch.zeros(2, G, device=dev)
+            call("deer_lstm_cluster_bwd", ptr(gates), ptr(c), ptr(dh_out), ptr(w[0]), ptr(w[1]), ptr(dpre), ptr(db), T, B, H)
+            torch.cuda.synchronize()
+            return nat(dpre), nat(db)
         gt = gates.clone()
         dhw = torch.empty(B, 2, H, device=dev)
         dcw = torch.empty(B, 2, H, device=dev)
         call("deer_lstm_bwd", ptr(gt), ptr(w[0]), ptr(w[1]), ptr(c), ptr(dh_out), ptr(dhw), ptr(dcw), T, B, H, engine)
         torch.cuda.synchronize()
-        return gt
+        return gt, gt.sum(dim=(0, 1))
 
     g_ref, h_ref, c_ref = fwd(SIMT)
     g_new, h_new, c_new = fwd(a.engine)
-    print(f"[{tag}] fwd: h rel={rel(h_new, h_ref):.3e} max={float((h_new - h_ref).abs().max()):.3e} "
-          f"gates rel={rel(g_new, g_ref):.3e} c rel={rel(c_new, c_ref):.3e}", flush=True)
+    print(f"[{tag}] fwd: h rel={rel(h_new, h_ref):.3e} max={float((h_new - h_ref).abs().max()):.3e}", flush=True)
     # per-time-step error growth (first bad step localises protocol bugs)
     per_t = ((h_new - h_ref).abs().amax(dim=(1, 2))).cpu()
     bad = (per_t > 5e-3).nonzero().flatten()
     print(f"[{tag}] fwd: first bad t (fwd dir view) = {bad[:4].tolist() if len(bad) else None}; "
           f"err t0={float(per_t[0]):.2e} t1={float(per_t[min(1, T - 1)]):.2e} tmid={float(per_t[T // 2]):.2e}", flush=True)
     if not a.skip_bwd:
-        d_ref = bwd(SIMT, g_ref, c_ref)
-        d_new = bwd(a.engine, g_ref, c_ref)
-        print(f"[{tag}] bwd: dgates rel={rel(d_new, d_ref):.3e} cos={cos(d_new, d_ref):.7f}", flush=True)
+        d_ref, db_ref = bwd(SIMT, g_ref, c_ref)
+        d_new, db_new = bwd(a.engine, g_new, c_new)
+        print(f"[{tag}] bwd: dgates rel={rel(d_new, d_ref):.3e} cos={cos(d_new, d_ref):.7f} db rel={rel(db_new, db_ref):.3e}",
+              flush=True)
         pt = ((d_new - d_ref).flatten(1).norm(dim=1) / d_ref.flatten(1).norm(dim=1).clamp_min(1e-30)).cpu()
         print(f"[{tag}] bwd: per-t rel err t=T-1 {float(pt[-1]):.2e} T-2 {float(pt[-2]):.2e} mid {float(pt[T // 2]):.2e} "
               f"t=0 {float(pt[0]):.2e}", flush=True)
@@ -89,7 +112,7 @@ def main():
             if what == "fwd":
                 fwd(a.engine)
             else:
-                bwd(a.engine, g_ref, c_ref)
+                bwd(a.engine, g_new, c_new)
             lib.deer_lstm_set_profile_buffer(None)
             v = buf.cpu().view(4, 8)
             for i in range(4):
@@ -108,18 +131,17 @@ def main():
             e1.record()
             torch.cuda.synchronize()
             return e0.elapsed_time(e1) / n
-        gates = pre.clone()
+        pre_il = il(pre)
         h = torch.empty(T, B, 2 * H, device=dev)
-        c = torch.empty(T, B, 2, H, device=dev)
-        tf = timeit(lambda: call("deer_lstm_fwd", ptr(gates), ptr(w[0]), ptr(w[1]), ptr(h), ptr(c), None, T, B, H, a.engine))
-        ti = timeit(lambda: call("deer_lstm_fwd", ptr(gates), ptr(w[0]), ptr(w[1]), ptr(h), None, ptr(c), T, B, H, a.engine))
+        tf = timeit(lambda: call("deer_lstm_cluster_fwd", ptr(pre_il), ptr(w[0]), ptr(w[1]), ptr(h), ptr(g_new), ptr(c_new),
+                                 T, B, H))
+        ti = timeit(lambda: call("deer_lstm_cluster_fwd", ptr(pre_il), ptr(w[0]), ptr(w[1]), ptr(h), None, None, T, B, H))
         msg = f"[{tag}] time: fwd(keep) {tf:.3f} ms = {tf * 1e3 / T:.2f} us/step; fwd(infer) {ti:.3f} ms"
         if not a.skip_bwd:
-            dhw = torch.empty(B, 2, H, device=dev)
-            dcw = torch.empty(B, 2, H, device=dev)
-            gt = g_ref.clone()
-            tb = timeit(lambda: call("deer_lstm_bwd", ptr(gt), ptr(w[0]), ptr(w[1]), ptr(c_ref), ptr(dh_out), ptr(dhw),
-                                     ptr(dcw), T, B, H, a.engine))
+            dpre = torch.empty(T, B, 2, G, device=dev)
+            db = torch.zeros(2, G, device=dev)
+            tb = timeit(lambda: call("deer_lstm_cluster_bwd", ptr(g_new), ptr(c_new), ptr(dh_out), ptr(w[0]), ptr(w[1]),
+                                     ptr(dpre), ptr(db), T, B, H))
             msg += f"; bwd {tb:.3f} ms = {tb * 1e3 / T:.2f} us/step"
         print(msg, flush=True)
 

@@ -1,6 +1,7 @@
 """deer_b200: hand-written sm_100a CUDA (libdeer_b200.so, C ABI) behind the reference's module/loss API for the
 batched forward+backward of the multimodal DEER model.  See DESIGN.md / INTEGRATION.md."""
 from . import _lib, ops  # noqa: F401
+from .complete_project import CompleteDEERModel, ModelCheckpoint, ModelConfig, create_complete_deer_model  # noqa: F401
 from .deer import DEERLayer, DEERLoss as AminiDEERLoss, MultiDimensionalDEER  # noqa: F401
 from .encoders import (AudioEncoder, EnhancedAudioEncoder, EnhancedTextEncoder, EnhancedVideoEncoder,  # noqa: F401
                        TextEncoder, VideoEncoder)

@@ -46,6 +46,10 @@ _PROTOS = {
     "deer_mha2_bwd": [P, P, P, P, P, P, I, I, I, P],
     "deer_lstm_fwd": [P, P, P, P, P, P, I, I, I, I, P],
     "deer_lstm_bwd": [P, P, P, P, P, P, P, I, I, I, I, P],
+    "deer_lstm_cluster_tile": [I],
+    "deer_lstm_cluster_fwd": [P, P, P, P, P, P, I, I, I, P],
+    "deer_lstm_cluster_bwd": [P, P, P, P, P, P, P, I, I, I, P],
+    "deer_gate_rows_interleave": [P, P, I, I, I, I, P],
     "deer_nig_head_fwd": [P, P, P, P, P, P, P, P, L, P],
     "deer_nig_head_bwd": [P, P, P, P, P, P, P, P, P, L, P],
     "deer_nig_loss_stats": [P, P, P, P, P, P, P, P, P, L, I, I, F, P],
@@ -58,6 +62,8 @@ _PROTOS = {
     "deer_mix_bwd": [P, P, L, P, L, P, P, P, L, P, L, P, P, L, I, P],
     "deer_gate_fwd": [P, P, P, P, L, P],
     "deer_gate_bwd": [P, P, P, P, P, P, P, L, P],
+    "deer_coldiv_fwd": [P, P, P, L, I, P],
+    "deer_coldiv_bwd": [P, P, P, P, P, L, I, P],
     "deer_softmax_rows_fwd": [P, P, L, I, P],
     "deer_softmax_rows_bwd": [P, P, P, L, I, P],
 }

@@ -293,11 +293,79 @@ static inline int grid_for(long long n, int per_block = 256, int max_blocks = kN
   return (int)g;
 }
 
+// y[m,n] = x[m,n] / t[n]   (temperature scaling, complete_project.py:449) and its backward
+__global__ void __launch_bounds__(256) coldiv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ t,
+                                                         float* __restrict__ y, long long M, int N) {
+  const long long total = M * N;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x)
+    y[i] = x[i] / t[i % N];
+}
+// dx = dy / t;  dt[n] += -sum_m dy[m,n] x[m,n] / t[n]^2   (one block per column; N is tiny)
+__global__ void __launch_bounds__(256) coldiv_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                         const float* __restrict__ t, float* __restrict__ dx,
+                                                         float* __restrict__ dt, long long M, int N) {
+  __shared__ float red[32];
+  const int n = blockIdx.x;
+  const float tn = t[n];
+  float acc = 0.f;
+  for (long long m = threadIdx.x; m < M; m += blockDim.x) {
+    const float g = dy[m * N + n];
+    dx[m * N + n] = g / tn;
+    acc += g * x[m * N + n];
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0 && dt) dt[n] += -acc / (tn * tn);
+}
+
+// nn.LSTM gate rows (row g*H+u of a [4H,K] matrix) <-> gate-interleaved rows (4u+g) used by the persistent LSTM
+// kernels; inverse=1 maps interleaved -> natural; accumulate adds into dst (gradient un-permutation into .grad)
+__global__ void __launch_bounds__(256) gate_rows_interleave_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                                   int H, int K, int inverse, int accumulate) {
+  const long long total = 4LL * H * K;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % K);
+    const int row = (int)(i / K);             // index in the SOURCE row order
+    int drow;
+    if (!inverse) {                           // src natural (g*H+u) -> dst interleaved (4u+g)
+      const int g = row / H, u = row % H;
+      drow = 4 * u + g;
+    } else {                                  // src interleaved -> dst natural
+      const int u = row >> 2, g = row & 3;
+      drow = g * H + u;
+    }
+    const float v = src[i];
+    float* d = dst + (long long)drow * K + k;
+    *d = accumulate ? *d + v : v;
+  }
+}
+
 }  // namespace deer
 
 using namespace deer;
 
 extern "C" {
+
+int deer_coldiv_fwd(const float* x, const float* t, float* y, long long M, int N, void* stream) {
+  DEER_CHECK_ARG(x && t && y && M > 0 && N > 0, "coldiv_fwd: bad args");
+  DEER_LAUNCH(coldiv_fwd_kernel, grid_for(M * N), 256, 0, stream, x, t, y, M, N);
+  return DEER_OK;
+}
+
+int deer_coldiv_bwd(const float* dy, const float* x, const float* t, float* dx, float* dt, long long M, int N,
+                    void* stream) {
+  DEER_CHECK_ARG(dy && x && t && dx && M > 0 && N > 0, "coldiv_bwd: bad args");
+  DEER_LAUNCH(coldiv_bwd_kernel, (unsigned)N, 256, 0, stream, dy, x, t, dx, dt, M, N);
+  return DEER_OK;
+}
+
+int deer_gate_rows_interleave(const float* src, float* dst, int H, int K, int inverse, int accumulate, void* stream) {
+  DEER_CHECK_ARG(src && dst && H > 0 && K > 0 && src != dst, "gate_rows_interleave: bad args");
+  DEER_LAUNCH(gate_rows_interleave_kernel, grid_for(4LL * H * K), 256, 0, stream, src, dst, H, K, inverse, accumulate);
+  return DEER_OK;
+}
+
 
 int deer_bias_act_bwd(const float* dy, long long ld_dy, const float* y, long long ld_y, float* dz, long long ld_dz,
                       float* dbias, int M, int N, int act, void* stream) {

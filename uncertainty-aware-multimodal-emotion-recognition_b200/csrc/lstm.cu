@@ -25,12 +25,6 @@ bool lstm_persistent_supported(const float* gates, const float* h_out, const flo
 int lstm_fwd_persistent(float* gates, const float* w_fwd, const float* w_rev, float* h_out, float* c_all, int T, int B,
                         int keep, cudaStream_t stream);
 
-bool lstm_cluster_supported(const float* gates, const float* w_fwd, const float* w_rev, int H);
-int lstm_fwd_cluster(float* gates, const float* w_fwd, const float* w_rev, float* h_out, float* c_all, int T, int B,
-                     int keep, cudaStream_t stream);
-int lstm_bwd_cluster(float* gates, const float* w_fwd, const float* w_rev, const float* c_all, const float* dh_out,
-                     int T, int B, cudaStream_t stream);
-
 // recurrent step GEMM for both directions: fp32 SIMT (one batched launch) or TF32 tcgen05 (one launch per direction)
 static int step_gemm(bool tf32, const float* A, long long lda, const float* B, long long ldb, int transB, float* C,
                      long long ldc, int M, int N, int K, float beta, long long sA, long long sB, long long sC,
@@ -171,12 +165,9 @@ int deer_lstm_fwd(float* gates, const float* w_hh_fwd, const float* w_hh_rev, fl
                   int T, int B, int H, int engine, void* stream) {
   DEER_CHECK_ARG(gates && w_hh_fwd && w_hh_rev && h_out && T > 0 && B > 0 && H > 0, "lstm_fwd: bad args");
   DEER_CHECK_ARG(c_out || c_work, "lstm_fwd: need c_out or c_work");
-  // engine: SIMT = exact-fp32 stepwise reference; AUTO/TF32 = persistent 4-CTA-cluster kernel (tcgen05 kind::f16, DSMEM
-  // h exchange) when H == 256; DEER_LSTM_PERSISTENT_V1 = the earlier 8-CTA TF32 kernel with the h exchange through
-  // L2/TMA multicast; DEER_LSTM_STEPWISE_TF32 keeps the stepwise schedule with the tcgen05 GEMM per step (ablations).
-  if (engine != DEER_GEMM_SIMT && engine != DEER_LSTM_STEPWISE_TF32 && engine != DEER_LSTM_PERSISTENT_V1 &&
-      lstm_cluster_supported(gates, w_hh_fwd, w_hh_rev, H))
-    return lstm_fwd_cluster(gates, w_hh_fwd, w_hh_rev, h_out, c_out, T, B, c_out != nullptr, (cudaStream_t)stream);
+  // natural-layout engines: SIMT = exact-fp32 stepwise reference; AUTO/TF32/DEER_LSTM_PERSISTENT_V1 = the round-1
+  // 8-CTA TF32 forward kernel (h exchange through L2/TMA multicast) when H == 256; DEER_LSTM_STEPWISE_TF32 = stepwise
+  // with the tcgen05 GEMM per step.  The production path is deer_lstm_cluster_fwd/bwd (lstm_cluster.cu).
   if (engine != DEER_GEMM_SIMT && engine != DEER_LSTM_STEPWISE_TF32 &&
       lstm_persistent_supported(gates, h_out, c_out, w_hh_fwd, w_hh_rev, T, B, H))
     return lstm_fwd_persistent(gates, w_hh_fwd, w_hh_rev, h_out, c_out, T, B, c_out != nullptr, (cudaStream_t)stream);
@@ -188,9 +179,6 @@ int deer_lstm_bwd(float* gates, const float* w_hh_fwd, const float* w_hh_rev, co
                   float* dh_work, float* dc_work, int T, int B, int H, int engine, void* stream) {
   DEER_CHECK_ARG(gates && w_hh_fwd && w_hh_rev && c_all && dh_out && dh_work && dc_work && T > 0 && B > 0 && H > 0,
                  "lstm_bwd: bad args");
-  if (engine != DEER_GEMM_SIMT && engine != DEER_LSTM_STEPWISE_TF32 && engine != DEER_LSTM_PERSISTENT_V1 &&
-      lstm_cluster_supported(gates, w_hh_fwd, w_hh_rev, H))
-    return lstm_bwd_cluster(gates, w_hh_fwd, w_hh_rev, c_all, dh_out, T, B, (cudaStream_t)stream);
   return lstm_bwd_stepwise(gates, w_hh_fwd, (long long)(w_hh_rev - w_hh_fwd), c_all, dh_out, dh_work, dc_work, T, B, H,
                            engine == DEER_LSTM_STEPWISE_TF32, (cudaStream_t)stream);
 }

@@ -153,13 +153,20 @@ struct QLayout {
   static constexpr int PSTAGE_BYTES = 2 * 8 * 32 * ROWF * 4;  // backward: double-buffered per-warp partial rows
 };
 
+// Layouts.  `pre` / `dpre` are GATE-INTERLEAVED [T,B,2,H,4] (column 4*unit+gate: the input-projection GEMM runs on
+// row-interleaved W_ih), so one warp's 8 units x 4 gates of a sample are one 128-byte line.  The activated gates and
+// the cell states saved for BPTT are private to the forward/backward kernel pair and stored BLOCKED in the order the
+// cell threads hold them: gact [T,2,ntiles,4 CTA,8 warp,4 gate,N/4,32 lane], c [T,2,ntiles,4,8,N/4,32] -- every
+// global access of the kernels' inner loops is a fully coalesced 128-byte warp access.
 struct LstmClusterParams {
-  float* gates;        // [T,B,2,4H]  fwd: in pre-activations, out (keep) activated gates; bwd: in gates, out dpre
-  const float* w_fwd;  // [4H,H]
+  float* gates;        // fwd: pre-activations in; bwd: dpre out           [T,B,2,H,4]
+  const float* w_fwd;  // [4H,H] (natural nn.LSTM row order g*H+u)
   const float* w_rev;  // [4H,H]
   float* h_out;        // fwd: [T,B,2H] out
-  float* c_all;        // [T,B,2,H] fwd: out or null; bwd: in
+  float* gact;         // blocked activated gates: fwd out (or null), bwd in
+  float* c_all;        // blocked cell states: fwd out (or null), bwd in
   const float* dh_out; // bwd: [T,B,2H]
+  float* db;           // bwd: [2,H,4] bias gradient (column sums of dpre), accumulated with atomics; may be null
   int T, B, ntiles, keep;
   long long* prof;     // optional clock64 trace of block 0 (tools/lstm_probe.py --prof), else null
 };
@@ -301,12 +308,16 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
 #pragma unroll
     for (int i = 0; i < NQ; i++) cst[i] = 0.f;
     float pre[N];
+    const int il0 = 4 * ((int)r * QU + a * 32 + sub * 8);  // first interleaved gate column of this warp
     auto load_pre = [&](int s) {
       const int t = dir ? T - 1 - s : s;
-      const float* src = p.gates + (((long long)t * B + b0) * 2 + dir) * (4 * QH) + g * QH + ug;
+      const float* src = p.gates + (((long long)t * B + b0) * 2 + dir) * (4 * QH) + il0 + lane;
 #pragma unroll
       for (int n = 0; n < N; n++) pre[n] = (b0 + n < B) ? __ldcs(src + (long long)n * (8 * QH)) : 0.f;
     };
+    // blocked save area of this warp: ((((t*2+dir)*ntiles+tile)*4+r)*8+warp) blocks of 4*NQ*32 (gates) / NQ*32 (c)
+    const long long blk_w = ((long long)dir * p.ntiles + tile) * 32 + (int)r * 8 + warp;
+    const long long blk_t = 2LL * p.ntiles * 32;
     load_pre(0);
     for (int s = 0; s < T; s++) {
       const int t = dir ? T - 1 - s : s;
@@ -323,12 +334,10 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
         for (int n = 0; n < N; n++) x[n] = 0.f;
       }
       tc_fence_before();
-      float* grow = p.gates + (((long long)t * B + b0) * 2 + dir) * (4 * QH) + g * QH + ug;
 #pragma unroll
       for (int n = 0; n < N; n++) {
         const float z = (x[n] + pre[n]) * sc;
         x[n] = fmaf(sc, __fdividef(1.f, 1.f + __expf(-z)), 1.f - sc);
-        if (p.keep && b0 + n < B) grow[(long long)n * (8 * QH)] = x[n];
       }
 #pragma unroll
       for (int n = 0; n < N; n += 4)
@@ -349,16 +358,25 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
         go[i] = vo.x; go[i + 1] = vo.y; go[i + 2] = vo.z; go[i + 3] = vo.w;
       }
       const long long row0 = (long long)t * B + b0 + q * NQ;
+      const long long blk = (long long)t * blk_t + blk_w;
+      if (p.keep) {
+        float* gs = p.gact + blk * (4 * NQ * 32) + lane;
+#pragma unroll
+        for (int i = 0; i < NQ; i++) {
+          __stcs(gs + (0 * NQ + i) * 32, gi[i]);
+          __stcs(gs + (1 * NQ + i) * 32, gf[i]);
+          __stcs(gs + (2 * NQ + i) * 32, gg[i]);
+          __stcs(gs + (3 * NQ + i) * 32, go[i]);
+        }
+      }
+      float* cs = p.keep ? p.c_all + blk * (NQ * 32) + lane : nullptr;
 #pragma unroll
       for (int i = 0; i < NQ; i++) {
         const float cn = fmaf(gf[i], cst[i], gi[i] * gg[i]);
         cst[i] = cn;
         const float hv = go[i] * tanh_f(cn);
-        const bool ok = b0 + q * NQ + i < B;
-        if (ok) {
-          p.h_out[(row0 + i) * (2 * QH) + dir * QH + ug] = hv;
-          if (p.c_all) p.c_all[((row0 + i) * 2 + dir) * QH + ug] = cn;
-        }
+        if (b0 + q * NQ + i < B) p.h_out[(row0 + i) * (2 * QH) + dir * QH + ug] = hv;
+        if (p.keep) __stcs(cs + i * 32, cn);
         sh[(q * NQ + i) * 8 + j] = __float2half_rn(hv);
       }
       if (warp == 0 && lane == 0) Q_PROF(4);
@@ -511,24 +529,28 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
 #pragma unroll
     for (int i = 0; i < NQ; i++) dc[i] = 0.f;
 
+    const long long blk_w = ((long long)dir * p.ntiles + tile) * 32 + (int)r * 8 + warp;
+    const long long blk_t = 2LL * p.ntiles * 32;
+    float sdb[4] = {0.f, 0.f, 0.f, 0.f};          // bias gradient of (unit, 4 gates) over this thread's columns, all t
     float vi[NQ], vf[NQ], vg[NQ], vo[NQ], vc[NQ], vcp[NQ], vdh[NQ];
     auto load_step = [&](int s) {
       const int t = dir ? s : T - 1 - s;            // reverse of the forward order
       const int tp = dir ? t + 1 : t - 1;           // forward-previous time step (c_{prev})
       const bool first = dir ? (t == T - 1) : (t == 0);
+      const long long blk = (long long)t * blk_t + blk_w;
+      const float* gs = p.gact + blk * (4 * NQ * 32) + lane;
+      const float* cs = p.c_all + blk * (NQ * 32) + lane;
+      const float* cps = p.c_all + ((long long)tp * blk_t + blk_w) * (NQ * 32) + lane;
 #pragma unroll
       for (int i = 0; i < NQ; i++) {
+        vi[i] = __ldcs(gs + (0 * NQ + i) * 32);
+        vf[i] = __ldcs(gs + (1 * NQ + i) * 32);
+        vg[i] = __ldcs(gs + (2 * NQ + i) * 32);
+        vo[i] = __ldcs(gs + (3 * NQ + i) * 32);
+        vc[i] = __ldcs(cs + i * 32);
+        vcp[i] = first ? 0.f : __ldcs(cps + i * 32);
         const int b = b0 + q * NQ + i;
-        if (b < B) {
-          const long long row = (long long)t * B + b;
-          const float* gp = p.gates + (row * 2 + dir) * (4 * QH) + ug;
-          vi[i] = __ldcs(gp); vf[i] = __ldcs(gp + QH); vg[i] = __ldcs(gp + 2 * QH); vo[i] = __ldcs(gp + 3 * QH);
-          vc[i] = __ldcs(p.c_all + (row * 2 + dir) * QH + ug);
-          vcp[i] = first ? 0.f : __ldcs(p.c_all + (((long long)tp * B + b) * 2 + dir) * QH + ug);
-          vdh[i] = __ldcs(p.dh_out + row * (2 * QH) + dir * QH + ug);
-        } else {
-          vi[i] = vf[i] = vg[i] = vo[i] = vc[i] = vcp[i] = vdh[i] = 0.f;
-        }
+        vdh[i] = (b < B) ? __ldcs(p.dh_out + ((long long)t * B + b) * (2 * QH) + dir * QH + ug) : 0.f;
       }
     };
     load_step(0);
@@ -550,7 +572,7 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
           }
         }
       }
-      float* gout = p.gates + (((long long)t * B + b0 + q * NQ) * 2 + dir) * (4 * QH) + ug;
+      float* gout = p.gates + (((long long)t * B + b0 + q * NQ) * 2 + dir) * (4 * QH) + 4 * ug;
       const int kb = ul >> 4, ch = (ul & 15) >> 1;
 #pragma unroll
       for (int i = 0; i < NQ; i++) {
@@ -563,8 +585,8 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
         const float pg = dcc * vi[i] * (1.f - vg[i] * vg[i]);
         const float po = d_o * vo[i] * (1.f - vo[i]);
         if (b0 + q * NQ + i < B) {
-          float* gp = gout + (long long)i * (8 * QH);
-          gp[0] = pi; gp[QH] = pf; gp[2 * QH] = pg; gp[3 * QH] = po;
+          __stcs(reinterpret_cast<float4*>(gout + (long long)i * (8 * QH)), make_float4(pi, pf, pg, po));
+          sdb[0] += pi; sdb[1] += pf; sdb[2] += pg; sdb[3] += po;
         }
         if (s + 1 < T) {
           const int n = q * NQ + i;
@@ -602,6 +624,18 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
                             mapa_u32(smem_u32(&part_full[s & 1]), dst_cta));
         }
         if (warp == 0 && lane == 0) Q_PROF(5);
+      }
+    }
+    if (p.db) {
+      // db[dir, unit, gate] += sum over this cluster's samples and all T steps: fold the 4 column groups of a unit
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        sdb[e] += __shfl_xor_sync(0xffffffffu, sdb[e], 1);
+        sdb[e] += __shfl_xor_sync(0xffffffffu, sdb[e], 2);
+      }
+      if (q == 0) {
+#pragma unroll
+        for (int e = 0; e < 4; e++) atomicAdd(p.db + dir * (4 * QH) + 4 * ug + e, sdb[e]);
       }
     }
   }
@@ -675,21 +709,54 @@ static int launch_bwd(const tc::LstmClusterParams& p, cudaStream_t stream) {
   return DEER_OK;
 }
 
-int lstm_fwd_cluster(float* gates, const float* w_fwd, const float* w_rev, float* h_out, float* c_all, int T, int B,
-                     int keep, cudaStream_t stream) {
+int lstm_cluster_tile(int B) { return pick_tile(B); }
+
+int lstm_fwd_cluster(const float* pre_il, const float* w_fwd, const float* w_rev, float* h_out, float* gact,
+                     float* c_blk, int T, int B, cudaStream_t stream) {
   const int N = pick_tile(B);
-  tc::LstmClusterParams p{gates, w_fwd, w_rev, h_out, c_all, nullptr, T, B, (B + N - 1) / N, keep, g_lstm_prof};
+  const int keep = (gact != nullptr && c_blk != nullptr) ? 1 : 0;
+  tc::LstmClusterParams p{const_cast<float*>(pre_il), w_fwd, w_rev, h_out, gact, c_blk, nullptr, nullptr, T, B,
+                          (B + N - 1) / N, keep, g_lstm_prof};
   if (N == 16) return g_lstm_ts ? launch_fwd<16, true>(p, stream) : launch_fwd<16, false>(p, stream);
   return g_lstm_ts ? launch_fwd<32, true>(p, stream) : launch_fwd<32, false>(p, stream);
 }
 
-int lstm_bwd_cluster(float* gates, const float* w_fwd, const float* w_rev, const float* c_all, const float* dh_out,
-                     int T, int B, cudaStream_t stream) {
+int lstm_bwd_cluster(const float* gact, const float* c_blk, const float* dh_out, const float* w_fwd, const float* w_rev,
+                     float* dpre_il, float* db_il, int T, int B, cudaStream_t stream) {
   const int N = pick_tile(B);
-  tc::LstmClusterParams p{gates, w_fwd, w_rev, nullptr, const_cast<float*>(c_all), dh_out, T, B, (B + N - 1) / N, 1,
-                          g_lstm_prof};
+  tc::LstmClusterParams p{dpre_il, w_fwd, w_rev, nullptr, const_cast<float*>(gact), const_cast<float*>(c_blk), dh_out,
+                          db_il, T, B, (B + N - 1) / N, 1, g_lstm_prof};
   if (N == 16) return g_lstm_ts ? launch_bwd<16, true>(p, stream) : launch_bwd<16, false>(p, stream);
   return launch_bwd<32, true>(p, stream);  // the N=32 tiles + 128 KB of smem-resident weights exceed 227 KB
 }
 
 }  // namespace deer
+
+using namespace deer;
+
+extern "C" {
+
+int deer_lstm_cluster_tile(int B) { return B > 0 ? lstm_cluster_tile(B) : DEER_ERR_INVALID; }
+
+int deer_lstm_cluster_fwd(const float* pre_il, const float* w_hh_fwd, const float* w_hh_rev, float* h_out, float* gact,
+                          float* c_blk, int T, int B, int H, void* stream) {
+  DEER_CHECK_ARG(pre_il && w_hh_fwd && w_hh_rev && h_out && T > 0 && B > 0, "lstm_cluster_fwd: bad args");
+  DEER_CHECK_ARG((gact == nullptr) == (c_blk == nullptr), "lstm_cluster_fwd: gact and c_blk go together");
+  if (!lstm_cluster_supported(pre_il, w_hh_fwd, w_hh_rev, H)) {
+    set_error("lstm_cluster_fwd: needs H == 256 and 16-byte aligned pointers");
+    return DEER_ERR_UNSUPPORTED;
+  }
+  return lstm_fwd_cluster(pre_il, w_hh_fwd, w_hh_rev, h_out, gact, c_blk, T, B, (cudaStream_t)stream);
+}
+
+int deer_lstm_cluster_bwd(const float* gact, const float* c_blk, const float* dh_out, const float* w_hh_fwd,
+                          const float* w_hh_rev, float* dpre_il, float* db_il, int T, int B, int H, void* stream) {
+  DEER_CHECK_ARG(gact && c_blk && dh_out && w_hh_fwd && w_hh_rev && dpre_il && T > 0 && B > 0, "lstm_cluster_bwd: bad args");
+  if (!lstm_cluster_supported(dpre_il, w_hh_fwd, w_hh_rev, H)) {
+    set_error("lstm_cluster_bwd: needs H == 256 and 16-byte aligned pointers");
+    return DEER_ERR_UNSUPPORTED;
+  }
+  return lstm_bwd_cluster(gact, c_blk, dh_out, w_hh_fwd, w_hh_rev, dpre_il, db_il, T, B, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -24,18 +24,70 @@ constexpr int NBINS = 10;
 
 struct Nig {
   float gamma, nu, alpha, beta;
+  float sn, sa, sb;  // softplus'(raw) of nu / alpha / beta (chain rule back to the evidence)
 };
+
+// The loss kernels are instruction-bound unless the transcendentals stay on the MUFU pipe: ex2/lg2/rcp based
+// versions (relative error ~1e-6, far inside the 1e-3 gate) replace libm's expf/log1pf/lgammaf/digamma loops.
+// softplus(x) (torch: beta=1, threshold=20) and its derivative sigmoid(x) from ONE exponential e = exp(-|x|):
+//   softplus = max(x,0) + log1p(e),  log1p(e) = log(u) * e / (u - 1) with u = 1 + e (exact to rounding for tiny e)
+__device__ __forceinline__ void softplus_fast(float x, float& sp, float& sg) {
+  if (x > 20.f) {
+    sp = x;
+    sg = 1.f;
+    return;
+  }
+  const float e = __expf(-fabsf(x));
+  const float u = 1.f + e;
+  const float l = (u == 1.f) ? e : __logf(u) * __fdividef(e, u - 1.f);
+  const float r = __fdividef(1.f, u);
+  sp = fmaxf(x, 0.f) + l;
+  sg = x >= 0.f ? r : e * r;
+}
+// lgamma(a), a >= 1: shift a by 7 with one product, then Stirling (|err| < 3e-6 absolute for a in [1, 1e5])
+__device__ __forceinline__ float lgamma_ge1_fast(float a) {
+  float lp = 0.f;
+  if (a < 8.f) {
+    lp = __logf(a * (a + 1.f) * (a + 2.f) * (a + 3.f) * (a + 4.f) * (a + 5.f) * (a + 6.f));
+    a += 7.f;
+  }
+  const float r = __fdividef(1.f, a), r2 = r * r;
+  const float s = r * (0.0833333333f - r2 * (0.00277777778f - r2 * 0.000793650794f));
+  return (a - 0.5f) * __logf(a) - a + 0.918938533f + s - lp;
+}
+// digamma(x), x >= 1: psi(x) = psi(x+6) - sum_{i<6} 1/(x+i), the sum as ONE quotient p'(x)/p(x)
+__device__ __forceinline__ float digamma_ge1_fast(float x) {
+  float corr = 0.f;
+  if (x < 8.f) {
+    float sm = 0.f, pr = 1.f;
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+      const float t = x + (float)i;
+      sm = fmaf(sm, t, pr);
+      pr *= t;
+    }
+    corr = __fdividef(sm, pr);
+    x += 6.f;
+  }
+  const float r = __fdividef(1.f, x), r2 = r * r;
+  return __logf(x) - 0.5f * r - r2 * (0.0833333333f - r2 * (0.00833333333f - r2 * 0.00396825397f)) - corr;
+}
 
 __device__ __forceinline__ Nig load_nig(const float* __restrict__ evidence, const float* __restrict__ gamma,
                                         const float* __restrict__ nu, const float* __restrict__ alpha,
                                         const float* __restrict__ beta, long long e, int from_evidence, float4& raw) {
   Nig p;
+  p.sn = p.sa = p.sb = 1.f;
   if (from_evidence) {
-    raw = reinterpret_cast<const float4*>(evidence)[e];
+    raw = __ldcs(reinterpret_cast<const float4*>(evidence) + e);
+    float sp;
     p.gamma = raw.x;
-    p.nu = softplus_f(raw.y) + 1e-6f;
-    p.alpha = softplus_f(raw.z) + 1.0f;
-    p.beta = softplus_f(raw.w) + 1e-6f;
+    softplus_fast(raw.y, sp, p.sn);
+    p.nu = sp + 1e-6f;
+    softplus_fast(raw.z, sp, p.sa);
+    p.alpha = sp + 1.0f;
+    softplus_fast(raw.w, sp, p.sb);
+    p.beta = sp + 1e-6f;
   } else {
     raw = make_float4(0.f, 0.f, 0.f, 0.f);
     p.gamma = gamma[e];
@@ -48,10 +100,11 @@ __device__ __forceinline__ Nig load_nig(const float* __restrict__ evidence, cons
 
 __device__ __forceinline__ int ece_bin(float conf, const float* __restrict__ edges) {
   // (edges[k], edges[k+1]]  (losses.py:207-215); -1 when outside every bin (NaN / conf<=0)
-  int k = -1;
-#pragma unroll
-  for (int i = 0; i < NBINS; i++)
-    if (conf > edges[i] && conf <= edges[i + 1]) k = i;
+  // closed-form guess, then at most one step against the exact fp32 edges (torch.linspace(0,1,11), losses.py:207)
+  int k = min(max((int)ceilf(conf * 10.f) - 1, 0), NBINS - 1);
+  if (!(conf > edges[k])) k -= 1;
+  else if (conf > edges[k + 1]) k += 1;
+  if (k < 0 || k >= NBINS || !(conf > edges[k] && conf <= edges[k + 1])) k = -1;
   return k;
 }
 
@@ -68,28 +121,29 @@ __global__ void __launch_bounds__(LOSS_THREADS) nig_loss_stats_kernel(
 #pragma unroll
   for (int i = 0; i < 3 * NBINS; i++) bins[i][tid] = 0.f;
   __syncthreads();
-  const float two_pi_eps = (float)(6.283185307179586 + (double)eps);
+  const float inv_two_pi_eps = (float)(1.0 / (6.283185307179586 + (double)eps));
+  const float log1eps = logf(1.f + eps);
   float a_nll = 0.f, a_reg = 0.f, a_kla = 0.f, a_klb = 0.f, a_u = 0.f;
   const long long stride = (long long)gridDim.x * LOSS_THREADS;  // multiple of D -> dimension fixed per thread
   for (long long e = (long long)blockIdx.x * LOSS_THREADS + tid; e < total; e += stride) {
     float4 raw;
     const Nig p = load_nig(evidence, gamma, nu, alpha, beta, e, from_evidence, raw);
-    const float y = targets[e];
+    const float y = __ldcs(targets + e);
     const float err = y - p.gamma;
     const float e2 = err * err;
     const float S = p.beta + 0.5f * p.nu * e2 + eps;
-    const float lb = logf(p.beta + eps);
-    const float lp = 0.5f * logf(p.nu / two_pi_eps) + p.alpha * lb - lgammaf(p.alpha + eps) -
-                     (p.alpha + 0.5f) * logf(S);
+    const float lb = __logf(p.beta + eps);
+    const float lp = 0.5f * __logf(p.nu * inv_two_pi_eps) + p.alpha * lb - lgamma_ge1_fast(p.alpha + eps) -
+                     (p.alpha + 0.5f) * __logf(S);
     a_nll -= lp;
     a_reg += e2 * (2.f * p.beta + p.nu * e2);
     const float am1 = p.alpha - 1.f;
     a_kla += am1 * am1;
-    const float dl = lb - logf(1.f + eps);
+    const float dl = lb - log1eps;
     a_klb += dl * dl;
-    const float u = p.beta / (am1 + eps);
-    a_u += p.beta / (am1 + 1e-8f);
-    const float conf = 1.f / (1.f + u);
+    const float u = __fdividef(p.beta, am1 + eps);
+    a_u += __fdividef(p.beta, am1 + 1e-8f);
+    const float conf = __fdividef(1.f, 1.f + u);
     const int k = ece_bin(conf, sedges);
     if (k >= 0) {
       bins[k][tid] += 1.f;
@@ -97,15 +151,15 @@ __global__ void __launch_bounds__(LOSS_THREADS) nig_loss_stats_kernel(
       bins[2 * NBINS + k][tid] += fabsf(err);
     }
     if (nig_out) {
-      const float alea = p.beta / am1;
-      const float epis = p.beta / (p.nu * am1);
-      nig_out[e] = p.gamma;
-      nig_out[total + e] = p.nu;
-      nig_out[2 * total + e] = p.alpha;
-      nig_out[3 * total + e] = p.beta;
-      nig_out[4 * total + e] = alea;
-      nig_out[5 * total + e] = epis;
-      nig_out[6 * total + e] = alea + epis;
+      const float alea = __fdividef(p.beta, am1);
+      const float epis = __fdividef(alea, p.nu);
+      __stcs(nig_out + e, p.gamma);
+      __stcs(nig_out + total + e, p.nu);
+      __stcs(nig_out + 2 * total + e, p.alpha);
+      __stcs(nig_out + 3 * total + e, p.beta);
+      __stcs(nig_out + 4 * total + e, alea);
+      __stcs(nig_out + 5 * total + e, epis);
+      __stcs(nig_out + 6 * total + e, alea + epis);
     }
   }
   red[0][tid] = a_nll;
@@ -195,22 +249,24 @@ __global__ void __launch_bounds__(256) nig_loss_finish_kernel(
   if (d_out == nullptr) return;
   const float invD = 1.f / (float)D;
   const float base = grad_scale * invD * invN;
+  const float log1eps = logf(1.f + eps);
   for (long long e = (long long)blockIdx.x * blockDim.x + tid; e < total_local;
        e += (long long)gridDim.x * blockDim.x) {
     const int d = (int)(e % D);
     float4 raw;
     const Nig p = load_nig(evidence, gamma, nu, alpha, beta, e, from_evidence, raw);
-    const float y = targets[e];
+    const float y = __ldcs(targets + e);
     const float err = y - p.gamma, e2 = err * err;
     const float S = p.beta + 0.5f * p.nu * e2 + eps;
     const float ah = p.alpha + 0.5f;
     const float be = p.beta + eps;
     const float w = coef[d].w;
+    const float rS = __fdividef(1.f, S), rbe = __fdividef(1.f, be), lbe = __logf(be);
     // nll
-    float dg = -ah * p.nu * err / S;
-    float dn = -0.5f / p.nu + ah * e2 * 0.5f / S;
-    float da = -logf(be) + digamma_f(p.alpha + eps) + logf(S);
-    float db = -p.alpha / be + ah / S;
+    float dg = -ah * p.nu * err * rS;
+    float dn = __fdividef(-0.5f, p.nu) + ah * e2 * 0.5f * rS;
+    float da = -lbe + digamma_ge1_fast(p.alpha + eps) + __logf(S);
+    float db = -p.alpha * rbe + ah * rS;
     // reg
     dg += reg_w * (-(4.f * p.beta * err + 4.f * p.nu * e2 * err));
     dn += reg_w * e2 * e2;
@@ -218,18 +274,19 @@ __global__ void __launch_bounds__(256) nig_loss_finish_kernel(
     // kl
     const float am1 = p.alpha - 1.f;
     da += kl_w * 2.f * am1;
-    db += kl_w * 0.2f * (logf(be) - logf(1.f + eps)) / be;
+    db += kl_w * 0.2f * (lbe - log1eps) * rbe;
     // ece
     const float den = am1 + eps;
-    const float u = p.beta / den;
-    const float conf = 1.f / (1.f + u);
+    const float rden = __fdividef(1.f, den);
+    const float u = p.beta * rden;
+    const float conf = __fdividef(1.f, 1.f + u);
     if (ece_w > 0.f) {
       const int k = ece_bin(conf, sedges);
       if (k >= 0) {
         const float sg = coef[d].sign[k] * ece_w;
         const float dconf_du = -conf * conf;
-        db += sg * dconf_du / den;
-        da += sg * dconf_du * (-u / den);
+        db += sg * dconf_du * rden;
+        da += sg * dconf_du * (-u * rden);
         dg += sg * (err > 0.f ? -1.f : (err < 0.f ? 1.f : 0.f));
       }
     }
@@ -239,21 +296,21 @@ __global__ void __launch_bounds__(256) nig_loss_finish_kernel(
     db *= w;
     // cross-dimension consistency: d/d ubar_d * (1/N) * du/d(alpha,beta), u = beta/(alpha-1+1e-8)
     if (cross_w > 0.f && D > 1) {
-      const float den8 = am1 + 1e-8f;
+      const float r8 = __fdividef(1.f, am1 + 1e-8f);
       const float c = cross_w * coef[d].cross;
-      db += c / den8;
-      da += c * (-p.beta / (den8 * den8));
+      db += c * r8;
+      da += c * (-p.beta * r8 * r8);
     }
     float4 o;
     if (from_evidence) {
       o.x = base * dg;
-      o.y = base * dn * softplus_grad_f(raw.y);
-      o.z = base * da * softplus_grad_f(raw.z);
-      o.w = base * db * softplus_grad_f(raw.w);
+      o.y = base * dn * p.sn;
+      o.z = base * da * p.sa;
+      o.w = base * db * p.sb;
     } else {
       o = make_float4(base * dg, base * dn, base * da, base * db);
     }
-    reinterpret_cast<float4*>(d_out)[e] = o;
+    __stcs(reinterpret_cast<float4*>(d_out) + e, o);
   }
 }
 

@@ -444,7 +444,96 @@ class _BiLSTMLayer(torch.autograd.Function):
         return dx, dwif, dwhf, dbif, dbhf, dwir, dwhr, dbir, dbhr
 
 
+class _BiLSTMLayerCluster(torch.autograd.Function):
+    """Same layer on the persistent 4-CTA-cluster kernels (csrc/lstm_cluster.cu, H == 256).
+
+    The kernels read/write the gate dimension INTERLEAVED (column 4*unit+gate), so the input projection runs on
+    row-interleaved copies of W_ih / (b_ih+b_hh) and the weight gradients computed from the interleaved dpre are
+    un-interleaved (accumulating) into their targets.  The bias gradient comes out of the BPTT kernel itself."""
+
+    @staticmethod
+    def forward(ctx, x, wif, whf, bif, bhf, wir, whr, bir, bhr):
+        x = _req(x, "x").contiguous()
+        T, B, In = x.shape
+        H = whf.shape[1]
+        G = 4 * H
+        dev = x.device
+        keep = any(ctx.needs_input_grad)
+        wi_il = torch.empty((2, G, In), device=dev, dtype=torch.float32)
+        b_il = torch.empty((2, G), device=dev, dtype=torch.float32)
+        bsum = torch.empty(G, device=dev, dtype=torch.float32)
+        for d, (wi, bi, bh) in enumerate(((wif, bif, bhf), (wir, bir, bhr))):
+            call("deer_gate_rows_interleave", ptr(wi.contiguous()), ptr(wi_il[d]), H, In, 0, 0)
+            call("deer_axpby", ptr(bi), ptr(bh), ptr(bsum), G, 1.0, 1.0)
+            call("deer_gate_rows_interleave", ptr(bsum), ptr(b_il[d]), H, 1, 0, 0)
+        pre = torch.empty((T, B, 2, G), device=dev, dtype=torch.float32)
+        M = T * B
+        for d in range(2):
+            gemm(x, In, 0, wi_il[d], In, 1, pre.data_ptr() + 4 * G * d, 2 * G, M, G, In, bias=b_il[d])
+        h = torch.empty((T, B, 2 * H), device=dev, dtype=torch.float32)
+        whf_c, whr_c = whf.contiguous(), whr.contiguous()
+        if keep:
+            Bp = (B + 31) // 32 * 32
+            gact = torch.empty(T * 2 * Bp * G, device=dev, dtype=torch.float32)
+            c_blk = torch.empty(T * 2 * Bp * H, device=dev, dtype=torch.float32)
+            call("deer_lstm_cluster_fwd", ptr(pre), ptr(whf_c), ptr(whr_c), ptr(h), ptr(gact), ptr(c_blk), T, B, H)
+            ctx.save_for_backward(x, wi_il, whf_c, whr_c, gact, c_blk, h)
+            ctx.pre = pre   # reused as the dpre buffer
+        else:
+            call("deer_lstm_cluster_fwd", ptr(pre), ptr(whf_c), ptr(whr_c), ptr(h), None, None, T, B, H)
+        ctx.dims = (T, B, In, H)
+        ctx.params = (wif, whf, bif, bhf, wir, whr, bir, bhr)
+        return h
+
+    @staticmethod
+    def backward(ctx, dh):
+        x, wi_il, whf, whr, gact, c_blk, h = ctx.saved_tensors
+        T, B, In, H = ctx.dims
+        G = 4 * H
+        dev = x.device
+        dh = dh.contiguous()
+        dpre = ctx.pre
+        ctx.pre = None
+        db_il = torch.zeros((2, G), device=dev, dtype=torch.float32)
+        call("deer_lstm_cluster_bwd", ptr(gact), ptr(c_blk), ptr(dh), ptr(whf), ptr(whr), ptr(dpre), ptr(db_il), T, B, H)
+        M = T * B
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty((T, B, In), device=dev, dtype=torch.float32)
+            for d in range(2):
+                gemm(dpre.data_ptr() + 4 * G * d, 2 * G, 0, wi_il[d], In, 0, dx, In, M, In, G,
+                     beta=0.0 if d == 0 else 1.0)
+        P = ctx.params
+        out = []
+        for d in range(2):
+            gp = dpre.data_ptr() + 4 * G * d
+            dwi_il = torch.zeros((G, In), device=dev, dtype=torch.float32)
+            gemm(gp, 2 * G, 1, x, In, 0, dwi_il, In, G, In, M, beta=1.0)
+            dwi, dwi_direct = _acc(P[4 * d])
+            call("deer_gate_rows_interleave", ptr(dwi_il), ptr(dwi), H, In, 1, 1)
+            dwh_il = torch.zeros((G, H), device=dev, dtype=torch.float32)
+            if T > 1:
+                Mr = (T - 1) * B
+                if d == 0:   # rows t=1.. pair with h[t-1]
+                    gemm(gp + 4 * B * 2 * G, 2 * G, 1, h.data_ptr(), 2 * H, 0, dwh_il, H, G, H, Mr, beta=1.0)
+                else:        # rows t=..T-2 pair with h[t+1]
+                    gemm(gp, 2 * G, 1, h.data_ptr() + 4 * (B * 2 * H + H), 2 * H, 0, dwh_il, H, G, H, Mr, beta=1.0)
+            dwh, dwh_direct = _acc(P[4 * d + 1])
+            call("deer_gate_rows_interleave", ptr(dwh_il), ptr(dwh), H, H, 1, 1)
+            dbs = []
+            for pb in (P[4 * d + 2], P[4 * d + 3]):   # b_ih and b_hh receive the same gradient
+                tgt, direct = _acc(pb)
+                call("deer_gate_rows_interleave", ptr(db_il[d]), ptr(tgt), H, 1, 1, 1)
+                dbs.append(None if direct else tgt)
+            out.append((None if dwi_direct else dwi, None if dwh_direct else dwh, dbs[0], dbs[1]))
+        (dwif, dwhf, dbif, dbhf), (dwir, dwhr, dbir, dbhr) = out
+        return dx, dwif, dwhf, dbif, dbhf, dwir, dwhr, dbir, dbhr
+
+
 def bilstm_layer(x_tm, wif, whf, bif, bhf, wir, whr, bir, bhr):
+    """engine AUTO/TF32: persistent cluster kernels when H == 256; SIMT: exact-fp32 stepwise; others: see lstm.cu."""
+    if _state["lstm_engine"] in (ENGINE_AUTO, ENGINE_TF32) and whf.shape[1] == 256:
+        return _BiLSTMLayerCluster.apply(x_tm, wif, whf, bif, bhf, wir, whr, bir, bhr)
     return _BiLSTMLayer.apply(x_tm, wif, whf, bif, bhf, wir, whr, bir, bhr)
 
 
@@ -849,6 +938,33 @@ class _SoftmaxRows(torch.autograd.Function):
 
 def softmax_rows(x):
     return _SoftmaxRows.apply(x)
+
+
+class _ColDiv(torch.autograd.Function):
+    """y[m,n] = x[m,n] / t[n]  (UncertaintyCalibrationLayer temperature scaling, complete_project.py:449)."""
+
+    @staticmethod
+    def forward(ctx, x, t):
+        x = _req(x, "x").contiguous()
+        M, N = x.shape
+        y = torch.empty_like(x)
+        call("deer_coldiv_fwd", ptr(x), ptr(t), ptr(y), M, N)
+        ctx.save_for_backward(x, t)
+        ctx.params = (t,)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, t = ctx.saved_tensors
+        M, N = x.shape
+        dx = torch.empty_like(x)
+        dt, direct = _acc(ctx.params[0]) if ctx.needs_input_grad[1] else (None, False)
+        call("deer_coldiv_bwd", ptr(dy.contiguous()), ptr(x), ptr(t), ptr(dx), ptr(dt), M, N)
+        return dx, None if direct else dt
+
+
+def coldiv(x, t):
+    return _ColDiv.apply(x, t)
 
 
 class _Add(torch.autograd.Function):
