@@ -145,6 +145,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
     }
   } else {
     // ===================================================================== epilogue (warps 2..5)
+    // TMEM holds one accumulator ROW per thread; storing it directly would make every warp store touch 32 rows
+    // (32 half-used sectors per request: measured 32 sectors/request, the kernel was L1-wavefront bound).  Each warp
+    // instead transposes its 32x32 chunk through a padded shared-memory tile (the operand ring is idle once
+    // tmem_full fires) and writes 4 complete 128-byte row segments per store instruction.
     const int g = warp & 3;          // TMEM lane group this warp may access
     const int row = g * 32 + lane;
     const int gm = m0 + row;
@@ -152,23 +156,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
     tc_fence_after();
     const bool row_ok = gm < p.M;
     float* crow = p.C + (long long)gm * p.ldc;
+    constexpr int TLD = 36;          // padded tile row (floats): conflict-free 128-bit writes by row and reads by column
+    float* tile = reinterpret_cast<float*>(smem) + g * (32 * TLD);
+    const int cq = (lane & 7) * 4;   // column quad of this lane in the read-back phase
+    const int rsub = lane >> 3;      // row within each group of 4 rows
 #pragma unroll 1
     for (int c = 0; c < BLOCK_N / 32; c++) {
       const int gn0 = n0 + c * 32;
       if (gn0 >= p.N) break;  // warp-uniform
       const bool full = gn0 + 32 <= p.N;
-      // beta*C: issue the eight independent 128-bit loads of this row chunk before touching TMEM so their L2 latency
-      // overlaps the accumulator read instead of serialising load -> add -> store per vector
-      float4 oldv[8];
-      if (p.beta != 0.f && p.splits == 1 && full && row_ok) {
-#pragma unroll
-        for (int j = 0; j < 8; j++) oldv[j] = __ldcg(reinterpret_cast<const float4*>(crow + gn0) + j);
-      }
       float v[32];
       tmem_ld32(tmem_base + ((uint32_t)(g * 32) << 16) + (uint32_t)(c * 32), v);
       tmem_ld_wait();
-      if (!row_ok) continue;
       if (p.splits > 1) {
+        if (!row_ok) continue;
         // split-K partial sums: accumulate semantics (beta == 1, no activation); split 0 carries the bias
 #pragma unroll
         for (int j = 0; j < 32; j++) {
@@ -180,22 +181,31 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
         }
       } else if (full) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          if (p.bias) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + gn0 + j));
-            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(tile + lane * TLD + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        __syncwarp();
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + gn0 + cq));
+#pragma unroll
+        for (int it = 0; it < 8; it++) {
+          const int r = it * 4 + rsub;
+          const int grow = m0 + g * 32 + r;
+          if (grow < p.M) {
+            float4 o = *reinterpret_cast<const float4*>(tile + r * TLD + cq);
+            float4* dst = reinterpret_cast<float4*>(p.C + (long long)grow * p.ldc + gn0 + cq);
+            o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
+            if (p.beta != 0.f) {
+              const float4 old = __ldcg(dst);
+              o.x += p.beta * old.x; o.y += p.beta * old.y; o.z += p.beta * old.z; o.w += p.beta * old.w;
+            }
+            o.x = act_apply(o.x, p.act); o.y = act_apply(o.y, p.act);
+            o.z = act_apply(o.z, p.act); o.w = act_apply(o.w, p.act);
+            *dst = o;
           }
-          float4* dst = reinterpret_cast<float4*>(crow + gn0 + j);
-          if (p.beta != 0.f) {
-            const float4 old = oldv[j >> 2];
-            o.x += p.beta * old.x; o.y += p.beta * old.y; o.z += p.beta * old.z; o.w += p.beta * old.w;
-          }
-          o.x = act_apply(o.x, p.act); o.y = act_apply(o.y, p.act);
-          o.z = act_apply(o.z, p.act); o.w = act_apply(o.w, p.act);
-          *dst = o;
         }
+        __syncwarp();
       } else {
+        if (!row_ok) continue;
 #pragma unroll
         for (int j = 0; j < 32; j++) {
           if (gn0 + j < p.N) {

@@ -156,8 +156,8 @@ struct QLayout {
 // Layouts.  `pre` / `dpre` are GATE-INTERLEAVED [T,B,2,H,4] (column 4*unit+gate: the input-projection GEMM runs on
 // row-interleaved W_ih), so one warp's 8 units x 4 gates of a sample are one 128-byte line.  The activated gates and
 // the cell states saved for BPTT are private to the forward/backward kernel pair and stored BLOCKED in the order the
-// cell threads hold them: gact [T,2,ntiles,4 CTA,8 warp,4 gate,N/4,32 lane], c [T,2,ntiles,4,8,N/4,32] -- every
-// global access of the kernels' inner loops is a fully coalesced 128-byte warp access.
+// cell threads hold them: gact [T,2,ntiles,4 CTA,8 warp,4 gate,N/16,32 lane,4], c [T,2,ntiles,4,8,N/16,32,4] -- every
+// access to them is one 128-bit load/store per thread, 512 contiguous bytes per warp.
 struct LstmClusterParams {
   float* gates;        // fwd: pre-activations in; bwd: dpre out           [T,B,2,H,4]
   const float* w_fwd;  // [4H,H] (natural nn.LSTM row order g*H+u)
@@ -360,24 +360,27 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
       const long long row0 = (long long)t * B + b0 + q * NQ;
       const long long blk = (long long)t * blk_t + blk_w;
       if (p.keep) {
-        float* gs = p.gact + blk * (4 * NQ * 32) + lane;
+        float4* gs = reinterpret_cast<float4*>(p.gact + blk * (4 * NQ * 32)) + lane;
 #pragma unroll
-        for (int i = 0; i < NQ; i++) {
-          __stcs(gs + (0 * NQ + i) * 32, gi[i]);
-          __stcs(gs + (1 * NQ + i) * 32, gf[i]);
-          __stcs(gs + (2 * NQ + i) * 32, gg[i]);
-          __stcs(gs + (3 * NQ + i) * 32, go[i]);
+        for (int i = 0; i < NQ; i += 4) {
+          __stcs(gs + (0 * NQ + i) * 8, make_float4(gi[i], gi[i + 1], gi[i + 2], gi[i + 3]));
+          __stcs(gs + (1 * NQ + i) * 8, make_float4(gf[i], gf[i + 1], gf[i + 2], gf[i + 3]));
+          __stcs(gs + (2 * NQ + i) * 8, make_float4(gg[i], gg[i + 1], gg[i + 2], gg[i + 3]));
+          __stcs(gs + (3 * NQ + i) * 8, make_float4(go[i], go[i + 1], go[i + 2], go[i + 3]));
         }
       }
-      float* cs = p.keep ? p.c_all + blk * (NQ * 32) + lane : nullptr;
 #pragma unroll
       for (int i = 0; i < NQ; i++) {
         const float cn = fmaf(gf[i], cst[i], gi[i] * gg[i]);
         cst[i] = cn;
         const float hv = go[i] * tanh_f(cn);
         if (b0 + q * NQ + i < B) p.h_out[(row0 + i) * (2 * QH) + dir * QH + ug] = hv;
-        if (p.keep) __stcs(cs + i * 32, cn);
         sh[(q * NQ + i) * 8 + j] = __float2half_rn(hv);
+      }
+      if (p.keep) {
+        float4* cs = reinterpret_cast<float4*>(p.c_all + blk * (NQ * 32)) + lane;
+#pragma unroll
+        for (int i = 0; i < NQ; i += 4) __stcs(cs + i * 8, make_float4(cst[i], cst[i + 1], cst[i + 2], cst[i + 3]));
       }
       if (warp == 0 && lane == 0) Q_PROF(4);
       if (s + 1 < T) {
@@ -538,17 +541,24 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
       const int tp = dir ? t + 1 : t - 1;           // forward-previous time step (c_{prev})
       const bool first = dir ? (t == T - 1) : (t == 0);
       const long long blk = (long long)t * blk_t + blk_w;
-      const float* gs = p.gact + blk * (4 * NQ * 32) + lane;
-      const float* cs = p.c_all + blk * (NQ * 32) + lane;
-      const float* cps = p.c_all + ((long long)tp * blk_t + blk_w) * (NQ * 32) + lane;
+      const float4* gs = reinterpret_cast<const float4*>(p.gact + blk * (4 * NQ * 32)) + lane;
+      const float4* cs = reinterpret_cast<const float4*>(p.c_all + blk * (NQ * 32)) + lane;
+      const float4* cps = reinterpret_cast<const float4*>(p.c_all + ((long long)tp * blk_t + blk_w) * (NQ * 32)) + lane;
+#pragma unroll
+      for (int i = 0; i < NQ; i += 4) {
+        const float4 a0 = __ldcs(gs + (0 * NQ + i) * 8), a1 = __ldcs(gs + (1 * NQ + i) * 8);
+        const float4 a2 = __ldcs(gs + (2 * NQ + i) * 8), a3 = __ldcs(gs + (3 * NQ + i) * 8);
+        const float4 a4 = __ldcs(cs + i * 8);
+        const float4 a5 = first ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldcs(cps + i * 8);
+        vi[i] = a0.x; vi[i + 1] = a0.y; vi[i + 2] = a0.z; vi[i + 3] = a0.w;
+        vf[i] = a1.x; vf[i + 1] = a1.y; vf[i + 2] = a1.z; vf[i + 3] = a1.w;
+        vg[i] = a2.x; vg[i + 1] = a2.y; vg[i + 2] = a2.z; vg[i + 3] = a2.w;
+        vo[i] = a3.x; vo[i + 1] = a3.y; vo[i + 2] = a3.z; vo[i + 3] = a3.w;
+        vc[i] = a4.x; vc[i + 1] = a4.y; vc[i + 2] = a4.z; vc[i + 3] = a4.w;
+        vcp[i] = a5.x; vcp[i + 1] = a5.y; vcp[i + 2] = a5.z; vcp[i + 3] = a5.w;
+      }
 #pragma unroll
       for (int i = 0; i < NQ; i++) {
-        vi[i] = __ldcs(gs + (0 * NQ + i) * 32);
-        vf[i] = __ldcs(gs + (1 * NQ + i) * 32);
-        vg[i] = __ldcs(gs + (2 * NQ + i) * 32);
-        vo[i] = __ldcs(gs + (3 * NQ + i) * 32);
-        vc[i] = __ldcs(cs + i * 32);
-        vcp[i] = first ? 0.f : __ldcs(cps + i * 32);
         const int b = b0 + q * NQ + i;
         vdh[i] = (b < B) ? __ldcs(p.dh_out + ((long long)t * B + b) * (2 * QH) + dir * QH + ug) : 0.f;
       }

@@ -73,6 +73,44 @@ __device__ __forceinline__ float digamma_ge1_fast(float x) {
   return __logf(x) - 0.5f * r - r2 * (0.0833333333f - r2 * (0.00833333333f - r2 * 0.00396825397f)) - corr;
 }
 
+// raw operands of one (sample, dim) element; fetched for several elements before any of them is processed so that
+// each thread keeps LOSS_UNROLL independent 128-bit loads in flight (the kernels are otherwise latency-bound)
+struct RawNig {
+  float4 v;  // evidence, or (gamma, nu, alpha, beta)
+  float y;
+};
+__device__ __forceinline__ RawNig fetch_nig(const float* __restrict__ evidence, const float* __restrict__ gamma,
+                                            const float* __restrict__ nu, const float* __restrict__ alpha,
+                                            const float* __restrict__ beta, const float* __restrict__ targets,
+                                            long long e, int from_evidence) {
+  RawNig r;
+  if (from_evidence) r.v = __ldcs(reinterpret_cast<const float4*>(evidence) + e);
+  else r.v = make_float4(__ldcs(gamma + e), __ldcs(nu + e), __ldcs(alpha + e), __ldcs(beta + e));
+  r.y = __ldcs(targets + e);
+  return r;
+}
+__device__ __forceinline__ Nig derive_nig(const RawNig& r, int from_evidence) {
+  Nig p;
+  p.sn = p.sa = p.sb = 1.f;
+  if (from_evidence) {
+    float sp;
+    p.gamma = r.v.x;
+    softplus_fast(r.v.y, sp, p.sn);
+    p.nu = sp + 1e-6f;
+    softplus_fast(r.v.z, sp, p.sa);
+    p.alpha = sp + 1.0f;
+    softplus_fast(r.v.w, sp, p.sb);
+    p.beta = sp + 1e-6f;
+  } else {
+    p.gamma = r.v.x;
+    p.nu = r.v.y;
+    p.alpha = r.v.z;
+    p.beta = r.v.w;
+  }
+  return p;
+}
+constexpr int LOSS_UNROLL = 4;
+
 __device__ __forceinline__ Nig load_nig(const float* __restrict__ evidence, const float* __restrict__ gamma,
                                         const float* __restrict__ nu, const float* __restrict__ alpha,
                                         const float* __restrict__ beta, long long e, int from_evidence, float4& raw) {
@@ -125,10 +163,19 @@ __global__ void __launch_bounds__(LOSS_THREADS) nig_loss_stats_kernel(
   const float log1eps = logf(1.f + eps);
   float a_nll = 0.f, a_reg = 0.f, a_kla = 0.f, a_klb = 0.f, a_u = 0.f;
   const long long stride = (long long)gridDim.x * LOSS_THREADS;  // multiple of D -> dimension fixed per thread
-  for (long long e = (long long)blockIdx.x * LOSS_THREADS + tid; e < total; e += stride) {
-    float4 raw;
-    const Nig p = load_nig(evidence, gamma, nu, alpha, beta, e, from_evidence, raw);
-    const float y = __ldcs(targets + e);
+  for (long long eb = (long long)blockIdx.x * LOSS_THREADS + tid; eb < total; eb += LOSS_UNROLL * stride) {
+    RawNig rr[LOSS_UNROLL];
+#pragma unroll
+    for (int q = 0; q < LOSS_UNROLL; q++) {
+      const long long eq = eb + q * stride;
+      rr[q] = fetch_nig(evidence, gamma, nu, alpha, beta, targets, eq < total ? eq : eb, from_evidence);
+    }
+#pragma unroll
+    for (int q = 0; q < LOSS_UNROLL; q++) {
+    const long long e = eb + q * stride;
+    if (e >= total) break;
+    const Nig p = derive_nig(rr[q], from_evidence);
+    const float y = rr[q].y;
     const float err = y - p.gamma;
     const float e2 = err * err;
     const float S = p.beta + 0.5f * p.nu * e2 + eps;
@@ -161,6 +208,7 @@ __global__ void __launch_bounds__(LOSS_THREADS) nig_loss_stats_kernel(
       __stcs(nig_out + 5 * total + e, epis);
       __stcs(nig_out + 6 * total + e, alea + epis);
     }
+    }
   }
   red[0][tid] = a_nll;
   red[1][tid] = a_reg;
@@ -188,7 +236,7 @@ struct DimCoef {
   float w;            // task weight
 };
 
-__global__ void __launch_bounds__(256) nig_loss_finish_kernel(
+__global__ void __launch_bounds__(LOSS_THREADS) nig_loss_finish_kernel(
     const float* __restrict__ evidence, const float* __restrict__ gamma, const float* __restrict__ nu,
     const float* __restrict__ alpha, const float* __restrict__ beta, const float* __restrict__ targets,
     const float* __restrict__ bin_edges, const float* __restrict__ stats, const float* __restrict__ task_weights,
@@ -250,12 +298,21 @@ __global__ void __launch_bounds__(256) nig_loss_finish_kernel(
   const float invD = 1.f / (float)D;
   const float base = grad_scale * invD * invN;
   const float log1eps = logf(1.f + eps);
-  for (long long e = (long long)blockIdx.x * blockDim.x + tid; e < total_local;
-       e += (long long)gridDim.x * blockDim.x) {
-    const int d = (int)(e % D);
-    float4 raw;
-    const Nig p = load_nig(evidence, gamma, nu, alpha, beta, e, from_evidence, raw);
-    const float y = __ldcs(targets + e);
+  const long long stride = (long long)gridDim.x * LOSS_THREADS;  // multiple of D: the dimension is fixed per thread
+  const int d = (int)(((long long)blockIdx.x * LOSS_THREADS + tid) % D);
+  for (long long eb = (long long)blockIdx.x * LOSS_THREADS + tid; eb < total_local; eb += LOSS_UNROLL * stride) {
+    RawNig rr[LOSS_UNROLL];
+#pragma unroll
+    for (int q = 0; q < LOSS_UNROLL; q++) {
+      const long long eq = eb + q * stride;
+      rr[q] = fetch_nig(evidence, gamma, nu, alpha, beta, targets, eq < total_local ? eq : eb, from_evidence);
+    }
+#pragma unroll
+    for (int q = 0; q < LOSS_UNROLL; q++) {
+    const long long e = eb + q * stride;
+    if (e >= total_local) break;
+    const Nig p = derive_nig(rr[q], from_evidence);
+    const float y = rr[q].y;
     const float err = y - p.gamma, e2 = err * err;
     const float S = p.beta + 0.5f * p.nu * e2 + eps;
     const float ah = p.alpha + 0.5f;
@@ -311,6 +368,7 @@ __global__ void __launch_bounds__(256) nig_loss_finish_kernel(
       o = make_float4(base * dg, base * dn, base * da, base * db);
     }
     __stcs(reinterpret_cast<float4*>(d_out) + e, o);
+    }
   }
 }
 
@@ -483,7 +541,7 @@ int deer_nig_loss_finish(const float* evidence, const float* gamma, const float*
     return DEER_ERR_UNSUPPORTED;
   }
   const long long total = B_local * D;
-  DEER_LAUNCH(nig_loss_finish_kernel, stream_grid(total, 256), 256, 0, stream, evidence, gamma, nu, alpha, beta,
+  DEER_LAUNCH(nig_loss_finish_kernel, stream_grid(total, LOSS_THREADS), LOSS_THREADS, 0, stream, evidence, gamma, nu, alpha, beta,
               targets, bin_edges, stats, task_weights, reg_w, kl_w, ece_w, cross_w, eps, total, B_global, D,
               from_evidence, grad_scale, losses, d_out);
   return DEER_OK;
