@@ -55,6 +55,19 @@ class FlatBuffers:
         self.payload = sum(p.numel() for p in params)
 
 
+def shard_batch(batch: Dict[str, torch.Tensor], rank: int, world: int) -> Dict[str, torch.Tensor]:
+    """Contiguous equal shard of a global batch: rank r gets rows [r*B/world, (r+1)*B/world).
+    Equal shard sizes keep mean-of-means == global mean for the batch-mean loss terms."""
+    out = {}
+    for k, v in batch.items():
+        B = v.shape[0]
+        if B % world != 0:
+            raise ValueError(f"global batch {B} is not divisible by world size {world}")
+        n = B // world
+        out[k] = v[rank * n:(rank + 1) * n]
+    return out
+
+
 def reference_lr_group(name: str) -> int:
     """training.py:128-142: names containing 'encoder' train at 0.5 x lr (group 0); everything else at lr (group 1)."""
     return 0 if "encoder" in name else 1
@@ -99,8 +112,7 @@ class DEERDataParallelTrainer:
 
     def _forward_backward(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
         model = self.model
-        out = model(batch["audio_features"], batch["video_features"], batch["text_features"],
-                    batch.get("attention_mask"), batch.get("linguistic_features"))
+        out = model(batch)   # both models accept the reference's batch dict (preprocessing.py:461-491)
         ev = out[EVIDENCE_KEY]
         targets = batch["targets"]
         B = targets.shape[0]
