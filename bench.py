@@ -213,19 +213,46 @@ def main():
     final_loss = float(trainer.last_losses[-1])
 
     # ------------------------------------------------------------------ e2e: pinned host -> device every step
+    # Public API path: pinned host batch -> H2D copy -> trainer.train_step -> D2H read of the loss, every step inside
+    # the timed region.  The copy of step i+1 is issued on a side stream while step i computes (double-buffered
+    # device batches), which is how a real input pipeline feeds the trainer; every byte still crosses PCIe per step.
     host = [synth_batch(TRAIN_B, None, gen, pinned=True) for _ in range(2)]
     h2d = sum(v.numel() * v.element_size() for v in host[0].values())
+    copy_stream = torch.cuda.Stream(device=dev)
+    dev_bufs = [{k: torch.empty_like(v, device=dev) for k, v in host[0].items()} for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+
+    def stage(i):
+        j = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[j])          # the step that last read this buffer has finished
+            for k, v in host[j].items():
+                dev_bufs[j][k].copy_(v, non_blocking=True)
+            ready[j].record(copy_stream)
 
     def e2e_fn(i):
-        hb = host[i % 2]
-        db = {k: v.to(dev, non_blocking=True) for k, v in hb.items()}
-        losses = trainer.train_step(db)
+        j = i % 2
+        stage(i + 1)                                     # prefetch the next step's batch
+        torch.cuda.current_stream().wait_event(ready[j])
+        losses = trainer.train_step(dev_bufs[j])
+        consumed[j].record()
         _ = losses[-1].item()  # D2H read of the step's loss
 
+    for j in range(2):
+        consumed[j].record()
+    stage(0)
     for i in range(2):
         e2e_fn(i)
-    e2e_ms = timed(e2e_fn, K) / K
+    torch.cuda.synchronize()
+    stage_base = 2
+
+    def e2e_timed(i):
+        e2e_fn(stage_base + i)
+
+    e2e_ms = timed(e2e_timed, K) / K
     e2e_value = TRAIN_B * world / (e2e_ms / 1e3)
+    torch.cuda.synchronize()
 
     # ------------------------------------------------------------------ inference B=1024
     model.eval()

@@ -68,6 +68,20 @@ int deer_gemm(const float* A, long long lda, int transA, const float* B, long lo
               float* C, long long ldc, int M, int N, int K, const float* bias, int act, float beta,
               int batch, long long sA, long long sB, long long sC, long long sBias, int engine, void* stream);
 
+/* ---- 16-bit-operand engine for the time-batched LSTM contractions (csrc/gemm_h16.cu): same contract as deer_gemm
+ *      (batch = 1) but A and B are both FP16 (a_bf16 = b_bf16 = 0) or both BF16 (= 1) matrices; accumulation and C
+ *      are fp32.  C16 (optional, may be NULL) receives a 16-bit copy of C (row pitch ldc16 elements) for the next GEMM.
+ *      All pointers 16-byte aligned; lda/ldb multiples of 8 elements, ldc/ldc16 multiples of 4. */
+int deer_gemm_h16(const void* A, long long lda, int transA, int a_bf16, const void* B, long long ldb, int transB,
+                  int b_bf16, float* C, long long ldc, void* C16, long long ldc16, int c16_bf16, int M, int N, int K,
+                  const float* bias, int act, float beta, void* stream);
+/*      debugging aid: >= 8 int64 device counters (block 0): cycles waiting on empty / tmem_empty / full / tmem_full and
+ *      cycles spent in the epilogue (NULL disables) */
+int deer_gemm_h16_set_profile_buffer(long long* device_buf);
+/*      fp32 [rows, cols] (pitch ld_src) -> 16-bit [rows, cols_pad] (pitch ld_dst), columns >= cols zero-filled */
+int deer_cast16(const float* src, long long ld_src, void* dst, long long ld_dst, long long rows, int cols, int cols_pad,
+                int bf16, void* stream);
+
 /* ---- activation backward + bias gradient (autograd of the Linear+act blocks above).
  *      dz = dy * act'(y) (dz may alias dy; dz may be NULL when act==NONE); dbias[n] += sum_m dz[m,n] if dbias. */
 int deer_bias_act_bwd(const float* dy, long long ld_dy, const float* y, long long ld_y, float* dz, long long ld_dz,

@@ -404,3 +404,49 @@ def test_fused_loss_wide_range_vs_oracle(B, scale):
             assert_close(nig_out[j][:, i], pred[f"{d}_{k}"].detach()[:, 0], 1e-5, f"{d}_{k}")
     assert cosine(ec.grad, ed.grad) > 0.99999
     assert_close(ec.grad, ed.grad, TOL, "d loss / d evidence")
+
+
+@pytest.mark.parametrize("M,N,K,ta,tb", [(300, 520, 200, 0, 1), (128, 256, 64, 0, 1), (1000, 84, 4100, 1, 0),
+                                         (260, 300, 130, 0, 0), (130, 512, 96, 1, 1), (2050, 1024, 84, 0, 1)])
+@pytest.mark.parametrize("a_bf,b_bf", [(0, 0), (1, 1)])
+def test_gemm_h16(M, N, K, ta, tb, a_bf, b_bf):
+    """16-bit-operand persistent tcgen05 engine: all operand majors, FP16/BF16 mixes, K/M/N tails, bias + activation +
+    beta epilogue, split-K accumulation and the 16-bit shadow output, against fp64 on the SAME rounded operands."""
+    g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
+    Kp, Mp, Np = (K + 7) // 8 * 8, (M + 7) // 8 * 8, (N + 7) // 8 * 8
+    A = torch.randn(M, K, generator=g) * 0.5
+    B = torch.randn(N, K, generator=g) * 0.5
+    da, db_ = (torch.bfloat16 if a_bf else torch.float16), (torch.bfloat16 if b_bf else torch.float16)
+    # stored operands (zero-padded to a 16-byte pitch): [M,Kp] or [K,Mp] for A, [N,Kp] or [K,Np] for B
+    if ta:
+        As = torch.zeros(K, Mp, dtype=da); As[:, :M] = A.t().to(da); lda = Mp
+        Ar = As[:, :M].double().t()
+    else:
+        As = torch.zeros(M, Kp, dtype=da); As[:, :K] = A.to(da); lda = Kp
+        Ar = As[:, :K].double()
+    if tb:
+        Bs = torch.zeros(N, Kp, dtype=db_); Bs[:, :K] = B.to(db_); ldb = Kp
+        Br = Bs[:, :K].double()
+    else:
+        Bs = torch.zeros(K, Np, dtype=db_); Bs[:, :N] = B.t().to(db_); ldb = Np
+        Br = Bs[:, :N].double().t()
+    ref = Ar @ Br.t()
+    bias = torch.randn(N, generator=g)
+    C0 = torch.randn(M, N, generator=g)
+    Ad, Bd = As.to(DEV), Bs.to(DEV)
+    ldc = (N + 3) // 4 * 4
+    for act, beta in ((0, 0.0), (2, 0.0), (0, 1.0), (1, 0.0)):
+        C = torch.zeros(M, ldc, device=DEV)
+        C[:, :N] = cu(C0)
+        use_bias = bias if N % 4 == 0 else None     # the TMA epilogue loads the bias as 16-byte vectors
+        ops.gemm_h16(Ad, lda, ta, Bd, ldb, tb, C, ldc, M, N, K, a_bf16=bool(a_bf), b_bf16=bool(b_bf),
+                     bias=None if use_bias is None else cu(use_bias), act=act, beta=beta)
+        r = ref + (0 if use_bias is None else use_bias.double()) + beta * C0.double()
+        r = {0: r, 1: torch.relu(r), 2: torch.tanh(r)}[act]
+        assert_close(C[:, :N], r, 2e-5, f"gemm_h16 act={act} beta={beta}")
+        assert float(C[:, N:].abs().max() if ldc > N else 0.0) == 0.0      # TMA clips the N tail
+    # cast helper
+    x = torch.randn(37, 84, generator=g)
+    x16 = ops.cast16(cu(x))
+    assert x16.shape == (37, 88) and float(x16[:, 84:].abs().max()) == 0.0
+    assert torch.equal(x16[:, :84].cpu(), x.to(torch.float16))

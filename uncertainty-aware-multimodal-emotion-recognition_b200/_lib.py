@@ -25,6 +25,9 @@ _PROTOS = {
     "deer_set_option": [I, I],
     "deer_lstm_set_profile_buffer": [P],
     "deer_gemm": [P, L, I, P, L, I, P, L, I, I, I, P, I, F, I, L, L, L, L, I, P],
+    "deer_gemm_h16": [P, L, I, I, P, L, I, I, P, L, P, L, I, I, I, I, P, I, F, P],
+    "deer_cast16": [P, L, P, L, L, I, I, I, P],
+    "deer_gemm_h16_set_profile_buffer": [P],
     "deer_bias_act_bwd": [P, L, P, L, P, L, P, I, I, I, P],
     "deer_layernorm_fwd": [P, P, P, P, P, P, I, I, F, P],
     "deer_layernorm_bwd": [P, P, P, P, P, P, P, P, I, I, P],

@@ -94,6 +94,16 @@ __device__ __forceinline__ float act_apply(float v, int act) {
     default: return v;
   }
 }
+// out-of-line 4-wide activation for GEMM epilogues: the common case (no activation) never enters it and the libm
+// slow paths of tanhf/expf stay out of the unrolled store loops (instruction-cache footprint)
+static __device__ __noinline__ float4 act_apply4(float4 v, int act) {
+  v.x = act_apply(v.x, act);
+  v.y = act_apply(v.y, act);
+  v.z = act_apply(v.z, act);
+  v.w = act_apply(v.w, act);
+  return v;
+}
+static __device__ __noinline__ float act_apply1(float v, int act) { return act_apply(v, act); }
 // derivative expressed through the activation OUTPUT y
 __device__ __forceinline__ float act_grad_from_out(float y, int act) {
   switch (act) {

@@ -1,0 +1,479 @@
+// Persistent tcgen05 GEMM engine for 16-bit operands (both FP16 or both BF16), FP32 accumulation.
+//
+//   C = act(opA(A) opB(B) + bias + beta*C)     C fp32 in HBM (+ optional 16-bit shadow copy C16 for the next GEMM)
+//
+// Used for the time-batched LSTM contractions (input projections, dx, dW_ih, dW_hh), whose operands exist as 16-bit
+// shadows written by their producers (the persistent LSTM kernels emit h as FP16 and dpre as BF16; weights and the
+// network input are cast once per step).  For this model's value ranges FP16 carries the same 11 significant bits as
+// TF32; gradients use BF16 for the exponent range.  Versus the TF32 engine: half the operand bytes through L2 (the
+// TF32 engine is L2-bandwidth bound at 128 B/cycle/SM) and twice the tensor rate.
+//
+//   tile 128 x 256, K block 64 (one 128-byte swizzle row), 4-stage TMA ring (4 x 48 KB), M128 N256 K16 MMAs
+//   persistent CTAs (one per SM) over (tile, K-split) work items; TWO 256-column TMEM accumulators so the epilogue of
+//   work item i overlaps the main loop of item i+1
+//   warp 0  TMA producer     warp 1  MMA issuer (owns TMEM)     warps 2..9  epilogue (2 per TMEM lane group)
+//   epilogue: tcgen05.ld -> shared-memory transpose -> bias / beta*C / activation -> 128-byte coalesced row segments
+//   (fp32 and, optionally, 16-bit); split-K partials go out as fp32 atomics (beta == 1, no activation)
+// Both operand majors: K-major (row = M/N index, K contiguous: one box per stage) and MN-major (row = k, M/N contiguous:
+// 64-element boxes; what dY^T X and dY W need) -- no transposition pass anywhere.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <stdlib.h>
+
+#include "tc_ptx.cuh"
+
+namespace deer {
+namespace h16 {
+
+using namespace deer::tc;
+
+constexpr int BM = 128, BN = 256, BK = 64, UK = 16, STAGES = 4;
+constexpr int A_BYTES = BM * BK * 2;          // 16 KB
+constexpr int B_BYTES = BN * BK * 2;          // 32 KB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int STAGING_BYTES = 8 * 4096;     // one 32x32 fp32 tile (128B-swizzled, TMA-store source) per epilogue warp
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 256 + 1024;
+constexpr int NUM_THREADS = 320;            // TMA warp, MMA warp, 8 epilogue warps
+
+struct Params {
+  float* C;
+  long long ldc;
+  void* C16;            // optional 16-bit copy of C (row pitch ldc16 elements)
+  long long ldc16;
+  int c16_bf;           // 1: bf16, 0: fp16
+  const float* bias;
+  int M, N, K;
+  int act;
+  float beta;
+  int splits, kb_per_split, tiles_m, tiles_n;
+  uint32_t idesc;
+  long long* prof;      // optional per-role wait/busy cycle counters of block 0 (debug), else null
+  int debug;            // bit 0: skip the fp32 stores (timing experiments only)
+};
+#define H16_T0() const long long _t0 = p.prof ? clock64() : 0
+#define H16_ACC(slot)                                                   \
+  do {                                                                  \
+    if (p.prof && blockIdx.x == 0 && lane == 0) p.prof[slot] += clock64() - _t0; \
+  } while (0)
+
+__device__ __forceinline__ void umma_16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                        uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+    gemm_h16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const __grid_constant__ CUtensorMap tmap_c, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment for the 128B swizzle atoms, applied as an OFFSET on the __shared__ array: going through
+  // uintptr_t would make every later access a generic LD/ST instead of LDS/STS
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  float* staging = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + STAGING_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;       // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_kb = (p.K + BK - 1) / BK;
+  const int total_work = p.tiles_m * p.tiles_n * p.splits;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_b);
+    prefetch_tmap(&tmap_c);
+    for (int s = 0; s < STAGES; s++) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; b++) {
+      mbar_init(&tmem_full[b], 1);
+      mbar_init(&tmem_empty[b], 8);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto decode = [&](int w, int& m0, int& n0, int& kb0, int& nkb) {
+    const int split = w % p.splits, tile = w / p.splits;
+    m0 = (tile / p.tiles_n) * BM;
+    n0 = (tile % p.tiles_n) * BN;
+    kb0 = split * p.kb_per_split;
+    nkb = min(total_kb, kb0 + p.kb_per_split) - kb0;
+  };
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    const bool leader = elect_one();
+    uint32_t g = 0;  // running stage counter across work items
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      int m0, n0, kb0, nkb;
+      decode(w, m0, n0, kb0, nkb);
+      for (int i = 0; i < nkb; i++, g++) {
+        const int s = g % STAGES;
+        {
+          H16_T0();
+          mbar_wait(&empty_bar[s], ((g / STAGES) & 1) ^ 1);
+          H16_ACC(0);
+        }
+        if (leader) {
+          uint8_t* sa = smem + s * STAGE_BYTES;
+          uint8_t* sb = sa + A_BYTES;
+          const int k0 = (kb0 + i) * BK;
+          mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+          if (!A_MN) {
+            tma_load_2d(sa, &tmap_a, &full_bar[s], k0, m0);            // box {64 k, 128 rows}
+          } else {
+#pragma unroll
+            for (int j = 0; j < BM / 64; j++)                           // box {64 m, 64 k} x2
+              tma_load_2d(sa + j * 8192, &tmap_a, &full_bar[s], m0 + 64 * j, k0);
+          }
+          if (!B_MN) {
+            tma_load_2d(sb, &tmap_b, &full_bar[s], k0, n0);            // box {64 k, 256 rows}
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; j++)                           // box {64 n, 64 k} x4
+              tma_load_2d(sb + j * 8192, &tmap_b, &full_bar[s], n0 + 64 * j, k0);
+          }
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    const uint32_t tb = warp_uniform(tmem_base);
+    const bool leader = elect_one();
+    uint32_t g = 0;
+    int it = 0;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x, it++) {
+      int m0, n0, kb0, nkb;
+      decode(w, m0, n0, kb0, nkb);
+      const int acc = it & 1;
+      {
+        H16_T0();
+        mbar_wait(&tmem_empty[acc], (uint32_t)(((it >> 1) & 1) ^ 1));   // epilogue drained this accumulator
+        H16_ACC(1);
+      }
+      tc_fence_after();
+      for (int i = 0; i < nkb; i++, g++) {
+        const int s = g % STAGES;
+        {
+          H16_T0();
+          mbar_wait(&full_bar[s], (g / STAGES) & 1);
+          H16_ACC(2);
+        }
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+        const uint32_t sb = sa + A_BYTES;
+        if (leader) {
+#pragma unroll
+          for (int k = 0; k < BK / UK; k++) {
+            // K-major : 8-row x 128 B swizzle atoms every 1024 B (SBO); +32 B per K step inside the atom
+            // MN-major: rows are k (128 B = 64 mn elements); 64-element mn chunks every 8192 B (LBO); 8-k-row atoms
+            //           every 1024 B (SBO); +2048 B (16 k rows) per K step
+            const uint64_t ad = A_MN ? make_smem_desc(sa + k * 2048, 8192, 1024, 2) : make_smem_desc(sa + k * 32, 16, 1024, 2);
+            const uint64_t bd = B_MN ? make_smem_desc(sb + k * 2048, 8192, 1024, 2) : make_smem_desc(sb + k * 32, 16, 1024, 2);
+            umma_16(tb + acc * BN, ad, bd, p.idesc, (i > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);
+          if (i == nkb - 1) umma_commit(&tmem_full[acc]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================================================================== epilogue (warps 2..9)
+    // Two warps per TMEM lane group, each taking every other 32-column chunk: tcgen05.ld (one accumulator row per
+    // lane) -> bias / activation in registers -> 128B-swizzled shared tile -> ONE TMA tensor store (or TMA reduce-add
+    // for beta == 1 and for split-K partial sums) per 32x32 chunk.  No per-element global store instructions, no
+    // atomics, and tile tails are clipped by the TMA unit.  (Measured: the previous LDS/STG read-back loop was
+    // instruction-issue bound at ~0.35 instructions per output float and cost as much as the whole main loop.)
+    const int gq = warp & 3;                 // TMEM lane group of this warp
+    const int half = (warp - 2) >> 2;        // which of the two warps of the group
+    uint8_t* tile = reinterpret_cast<uint8_t*>(staging) + (warp - 2) * 4096;   // [32 rows][128 B], SWIZZLE_128B
+    const int act = p.act;
+    const bool reduce = p.beta != 0.f || p.splits > 1;
+    int it = 0;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x, it++) {
+      int m0, n0, kb0, nkb;
+      decode(w, m0, n0, kb0, nkb);
+      const int acc = it & 1;
+      {
+        H16_T0();
+        mbar_wait(&tmem_full[acc], (uint32_t)((it >> 1) & 1));
+        if (warp == 2) H16_ACC(3);
+      }
+      tc_fence_after();
+      H16_T0();
+      const int row_base = m0 + gq * 32;
+      const bool add_bias = p.bias != nullptr && (w % p.splits) == 0;
+#pragma unroll 1
+      for (int c = half; c < BN / 32; c += 2) {
+        const int gn0 = n0 + c * 32;
+        if (gn0 >= p.N || row_base >= p.M) break;  // warp-uniform: nothing of this chunk exists
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(gq * 32) << 16) + (uint32_t)(acc * BN + c * 32), v);
+        tmem_ld_wait();
+        if (add_bias) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (gn0 + j < p.N) {   // bias is 16-byte aligned and N is a multiple of 4 (checked on the host)
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + gn0 + j));
+              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+            }
+          }
+        }
+        if (act != DEER_ACT_NONE) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 o = act_apply4(make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]), act);
+            v[j] = o.x; v[j + 1] = o.y; v[j + 2] = o.z; v[j + 3] = o.w;
+          }
+        }
+        // the previous TMA store of this warp has finished READING the tile (waited below before the loop continues)
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+          *reinterpret_cast<float4*>(tile + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+              make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (reduce) tma_reduce_add_2d(&tmap_c, tile, gn0, row_base);
+          else tma_store_2d(&tmap_c, tile, gn0, row_base);
+          tma_store_commit();
+          tma_store_wait_read();
+        }
+        __syncwarp();
+      }
+      // every TMEM read of this accumulator has completed (tcgen05.wait::ld): hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (warp == 2) H16_ACC(4);
+    }
+    if (lane == 0) tma_store_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      ptr = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(ptr);
+  }();
+  return fn;
+}
+// 2-D map over a row-major 16-bit matrix: `rows` rows of `cols` contiguous elements, pitch `ld` elements
+static bool make_map16(CUtensorMap* map, const void* base, int bf, long long rows, long long cols, long long ld,
+                       int box_cols, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, bf ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                  const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+// 2-D map over the fp32 output: box = one 32x32 chunk, 128B swizzle (matches the epilogue's shared tile)
+static bool make_map_c(CUtensorMap* map, float* base, long long rows, long long cols, long long ld) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+}  // namespace h16
+
+static long long* g_h16_prof = nullptr;
+void gemm_h16_set_profile(long long* buf) { g_h16_prof = buf; }
+
+int gemm_h16(const void* A, long long lda, int transA, int a_bf, const void* B, long long ldb, int transB, int b_bf,
+             float* C, long long ldc, void* C16, long long ldc16, int c16_bf, int M, int N, int K, const float* bias,
+             int act, float beta, cudaStream_t stream) {
+  using namespace h16;
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  if (!al16(A) || !al16(B) || !al16(C) || (lda & 7) || (ldb & 7) || (ldc & 3) || (bias && !al16(bias)) ||
+      (C16 && (!al16(C16) || (ldc16 & 3)))) {
+    set_error("gemm_h16: operands must be 16-byte aligned with leading dimensions that are multiples of 16 bytes");
+    return DEER_ERR_UNSUPPORTED;
+  }
+  if (C16 != nullptr || (beta != 0.f && act != DEER_ACT_NONE) || (bias && (N & 3))) {
+    set_error("gemm_h16: unsupported epilogue (16-bit copy of C, activation on an accumulating GEMM, or bias with N % 4)");
+    return DEER_ERR_UNSUPPORTED;
+  }
+  CUtensorMap ma, mb, mc;
+  bool ok = make_map_c(&mc, C, M, N, ldc);
+  if (!ok) {
+    set_error("gemm_h16: cuTensorMapEncodeTiled failed for C (M=%d N=%d ldc=%lld)", M, N, ldc);
+    return DEER_ERR_UNSUPPORTED;
+  }
+  if (!transA) ok = make_map16(&ma, A, a_bf, M, K, lda, BK, BM);   // stored [M,K]: K-major
+  else ok = make_map16(&ma, A, a_bf, K, M, lda, 64, BK);           // stored [K,M]: MN-major
+  if (transB) ok = ok && make_map16(&mb, B, b_bf, N, K, ldb, BK, BN);  // stored [N,K]: K-major
+  else ok = ok && make_map16(&mb, B, b_bf, K, N, ldb, 64, BK);         // stored [K,N]: MN-major
+  if (!ok) {
+    set_error("gemm_h16: cuTensorMapEncodeTiled failed (M=%d N=%d K=%d lda=%lld ldb=%lld)", M, N, K, lda, ldb);
+    return DEER_ERR_UNSUPPORTED;
+  }
+  const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
+  const int total_kb = (K + BK - 1) / BK;
+  int splits = 1;
+  if (beta == 1.f && act == DEER_ACT_NONE && C16 == nullptr) {
+    const int tiles = tiles_m * tiles_n;
+    if (tiles < kNumSMs && total_kb >= 32) {
+      splits = (2 * kNumSMs + tiles - 1) / tiles;
+      const int max_splits = total_kb / 8;
+      if (splits > max_splits) splits = max_splits;
+      if (splits < 1) splits = 1;
+    }
+  }
+  int per = (total_kb + splits - 1) / splits;
+  splits = (total_kb + per - 1) / per;
+  // instruction descriptor: D fp32, A/B formats, majors, N = 256, M = 128
+  const uint32_t idesc = (1u << 4) | ((uint32_t)(a_bf ? 1 : 0) << 7) | ((uint32_t)(b_bf ? 1 : 0) << 10) |
+                         ((uint32_t)(transA ? 1 : 0) << 15) | ((uint32_t)(transB ? 0 : 1) << 16) |
+                         ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  Params p{C, ldc, C16, ldc16, c16_bf, bias, M, N, K, act, beta, splits, per, tiles_m, tiles_n, idesc, g_h16_prof, getenv("DEER_H16_DEBUG") ? atoi(getenv("DEER_H16_DEBUG")) : 0};
+  const int work = tiles_m * tiles_n * splits;
+  const int grid = work < kNumSMs ? work : kNumSMs;
+#define DEER_H16_GO(AM, BMN)                                                                                       \
+  do {                                                                                                             \
+    static bool attr = false;                                                                                      \
+    if (!attr) {                                                                                                   \
+      cudaError_t e = cudaFuncSetAttribute(gemm_h16_kernel<AM, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                           SMEM_BYTES);                                                            \
+      if (e != cudaSuccess) return cuda_status(e, "gemm_h16 smem attribute");                                      \
+      attr = true;                                                                                                 \
+    }                                                                                                              \
+    DEER_LAUNCH((gemm_h16_kernel<AM, BMN>), grid, NUM_THREADS, SMEM_BYTES, stream, ma, mb, mc, p);                     \
+  } while (0)
+  if (!transA && transB) DEER_H16_GO(false, false);
+  else if (!transA && !transB) DEER_H16_GO(false, true);
+  else if (transA && transB) DEER_H16_GO(true, false);
+  else DEER_H16_GO(true, true);
+#undef DEER_H16_GO
+  return DEER_OK;
+}
+
+// fp32 -> 16-bit cast of a row-major matrix; dst row pitch ld_dst >= cols (columns cols..cols_pad-1 are zero-filled)
+__global__ void __launch_bounds__(256) cast16_kernel(const float* __restrict__ src, long long ld_src,
+                                                     uint16_t* __restrict__ dst, long long ld_dst, long long rows,
+                                                     int cols, int cols_pad, int bf) {
+  const long long per_row = cols_pad / 2;
+  const long long total = rows * per_row;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / per_row;
+    const int c = (int)(i % per_row) * 2;
+    const float a = c < cols ? src[r * ld_src + c] : 0.f;
+    const float b = c + 1 < cols ? src[r * ld_src + c + 1] : 0.f;
+    uint32_t v;
+    if (bf) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+      v = *reinterpret_cast<uint32_t*>(&h);
+    } else {
+      __half2 h = __floats2half2_rn(a, b);
+      v = *reinterpret_cast<uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint32_t*>(dst + r * ld_dst + c) = v;
+  }
+}
+
+}  // namespace deer
+
+using namespace deer;
+
+extern "C" {
+
+int deer_gemm_h16(const void* A, long long lda, int transA, int a_bf16, const void* B, long long ldb, int transB,
+                  int b_bf16, float* C, long long ldc, void* C16, long long ldc16, int c16_bf16, int M, int N, int K,
+                  const float* bias, int act, float beta, void* stream) {
+  DEER_CHECK_ARG(A && B && C, "gemm_h16: null pointer");
+  DEER_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm_h16: empty shape");
+  DEER_CHECK_ARG(lda >= (transA ? M : K) && ldb >= (transB ? K : N) && ldc >= N, "gemm_h16: leading dimension too small");
+  DEER_CHECK_ARG(act >= 0 && act <= 3, "gemm_h16: bad activation");
+  DEER_CHECK_ARG(beta == 0.f || beta == 1.f, "gemm_h16: beta must be 0 or 1");
+  // tcgen05.mma kind::f16 takes ONE 16-bit format for both operands (a mixed descriptor traps as an illegal instruction)
+  DEER_CHECK_ARG((a_bf16 != 0) == (b_bf16 != 0), "gemm_h16: A and B must both be FP16 or both be BF16");
+  return gemm_h16(A, lda, transA, a_bf16, B, ldb, transB, b_bf16, C, ldc, C16, ldc16, c16_bf16, M, N, K, bias, act, beta,
+                  (cudaStream_t)stream);
+}
+
+int deer_gemm_h16_set_profile_buffer(long long* device_buf) {
+  gemm_h16_set_profile(device_buf);
+  return DEER_OK;
+}
+
+int deer_cast16(const float* src, long long ld_src, void* dst, long long ld_dst, long long rows, int cols, int cols_pad,
+                int bf16, void* stream) {
+  DEER_CHECK_ARG(src && dst && rows > 0 && cols > 0 && cols_pad >= cols && (cols_pad & 1) == 0 && ld_dst >= cols_pad &&
+                     (ld_dst & 1) == 0,
+                 "cast16: bad args");
+  long long g = cdiv(rows * (cols_pad / 2), 256);
+  if (g > kNumSMs * 16) g = kNumSMs * 16;
+  DEER_LAUNCH(cast16_kernel, (unsigned)g, 256, 0, stream, src, ld_src, reinterpret_cast<uint16_t*>(dst), ld_dst, rows, cols,
+              cols_pad, bf16);
+  return DEER_OK;
+}
+
+}  // extern "C"

@@ -53,7 +53,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
                      const Params p) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment required by the 128B swizzle atoms
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment for the 128B swizzle atoms, applied as an OFFSET on the __shared__ array: going through
+  // uintptr_t would make every later access a generic LD/ST instead of LDS/STS
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
@@ -198,8 +200,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
               const float4 old = __ldcg(dst);
               o.x += p.beta * old.x; o.y += p.beta * old.y; o.z += p.beta * old.z; o.w += p.beta * old.w;
             }
-            o.x = act_apply(o.x, p.act); o.y = act_apply(o.y, p.act);
-            o.z = act_apply(o.z, p.act); o.w = act_apply(o.w, p.act);
+            if (p.act != DEER_ACT_NONE) o = act_apply4(o, p.act);
             *dst = o;
           }
         }
@@ -212,7 +213,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
             float x = v[j];
             if (p.bias) x += __ldg(p.bias + gn0 + j);
             if (p.beta != 0.f) x += p.beta * crow[gn0 + j];
-            crow[gn0 + j] = act_apply(x, p.act);
+            crow[gn0 + j] = p.act != DEER_ACT_NONE ? act_apply1(x, p.act) : x;
           }
         }
       }

@@ -78,10 +78,7 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t pa
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait_cluster(bar, parity)) {
-    if (++spins > (1u << 26)) {
-      printf("deer lstm_cluster: cluster mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-      __trap();
-    }
+    if (++spins > (1u << 26)) mbar_timeout_trap();
   }
 }
 __device__ __forceinline__ void umma_f16_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
@@ -184,7 +181,9 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
   using L = QLayout<N>;
   constexpr int NQ = L::NQ, ROWF = L::ROWF;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment for the 128B swizzle atoms, applied as an OFFSET on the __shared__ array: going through
+  // uintptr_t would make every later access a generic LD/ST instead of LDS/STS
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* wsm = smem;                                   // SS: 128 KB resident W (unused in TS mode)
   uint8_t* hbuf = smem + (TS ? 0 : QW_BYTES);            // 2 x HB_BYTES
   float* stage_act = reinterpret_cast<float*>(hbuf + 2 * L::HB_BYTES);
@@ -413,7 +412,9 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
   using L = QLayout<N>;
   constexpr int NQ = L::NQ, ROWF = L::ROWF;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment for the 128B swizzle atoms, applied as an OFFSET on the __shared__ array: going through
+  // uintptr_t would make every later access a generic LD/ST instead of LDS/STS
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* wsm = smem;                                   // SS: 128 KB resident W^T slice
   uint8_t* bsm = smem + (TS ? 0 : QW_BYTES);             // B operand: dpre tile [N rows x 256 k] bf16
   float* part = reinterpret_cast<float*>(bsm + L::HB_BYTES);  // [2][QC src][QU units][ROWF]

@@ -41,7 +41,9 @@ __global__ void __cluster_dims__(LC, 1, 1) __launch_bounds__(LTHREADS, 1)
                                const __grid_constant__ CUtensorMap tmap_w_rev,
                                const __grid_constant__ CUtensorMap tmap_h, const LstmParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment for the 128B swizzle atoms, applied as an OFFSET on the __shared__ array: going through
+  // uintptr_t would make every later access a generic LD/ST instead of LDS/STS
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* wbuf = smem;                       // 8 K-blocks x [128 n-rows x 128 B]
   uint8_t* hbuf = smem + LW_BYTES;            // 8 K-blocks x [64 rows x 128 B]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + LW_BYTES + LHB_BYTES);

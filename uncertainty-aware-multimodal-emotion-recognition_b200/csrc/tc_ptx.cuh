@@ -29,14 +29,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a protocol bug traps (launch failure reported to the host) instead of hanging the GPU.
+// kept out of line: the printf call sequence at every wait site bloats the hot loops past the instruction cache
+static __device__ __noinline__ void mbar_timeout_trap() {
+  printf("deer_b200: mbarrier wait timed out (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z,
+         threadIdx.x);
+  __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 27)) {
-      printf("deer gemm_tcgen05: mbarrier wait timed out (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y,
-             blockIdx.z, threadIdx.x);
-      __trap();
-    }
+    if (++spins > (1u << 27)) mbar_timeout_trap();
   }
 }
 __device__ __forceinline__ void fence_barrier_init() {

@@ -101,6 +101,26 @@ def gemm(A, lda, transA, B, ldb, transB, C, ldc, M, N, K, bias=None, act=0, beta
          sBias, _state["engine"] if engine is None else engine)
 
 
+def cast16(x: torch.Tensor, bf16: bool = False, pad_to: int = 8) -> torch.Tensor:
+    """fp32 [..., K] -> fp16/bf16 [rows, Kp] shadow (Kp = K rounded up to `pad_to`, zero-filled) for deer_gemm_h16."""
+    x2, M, K, ld = _rows2d(_req(x, "x"))
+    Kp = (K + pad_to - 1) // pad_to * pad_to
+    out = torch.empty((M, Kp), device=x.device, dtype=torch.bfloat16 if bf16 else torch.float16)
+    call("deer_cast16", ptr(x2), ld, out.data_ptr(), Kp, M, K, Kp, int(bf16))
+    return out
+
+
+def _p16(t):
+    return t.data_ptr() if isinstance(t, torch.Tensor) else t
+
+
+def gemm_h16(A, lda, transA, B, ldb, transB, C, ldc, M, N, K, *, a_bf16=False, b_bf16=False, bias=None, act=0,
+             beta=0.0, C16=None, ldc16=0, c16_bf16=False):
+    """deer_gemm_h16: 16-bit operands (pointers or tensors), fp32 accumulate/output, optional 16-bit copy of C."""
+    call("deer_gemm_h16", _p16(A), lda, int(transA), int(a_bf16), _p16(B), ldb, int(transB), int(b_bf16),
+         _p16(C), ldc, None if C16 is None else _p16(C16), ldc16, int(c16_bf16), M, N, K, ptr(bias), act, float(beta))
+
+
 def _colw(w: torch.Tensor, k0: int, k1: int):
     """Pointer/ld of the column block w[:, k0:k1] of a row-major weight."""
     return w.data_ptr() + 4 * k0, w.stride(0)
