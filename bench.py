@@ -390,9 +390,9 @@ def roofline_probe(torch, ops, dev, pk):
     dpre = torch.empty(T, B, 2, 4 * H, device=dev)
     db = torch.zeros(2, 4 * H, device=dev)
     us_f = _time_launches(torch, lambda i: call("deer_lstm_cluster_fwd", ptr(pre), ptr(w[0]), ptr(w[1]), ptr(h), ptr(gact),
-                                                ptr(c), T, B, H), 5, warm=2)
+                                                ptr(c), None, None, T, B, H), 5, warm=2)
     us_b = _time_launches(torch, lambda i: call("deer_lstm_cluster_bwd", ptr(gact), ptr(c), ptr(dh), ptr(w[0]), ptr(w[1]),
-                                                ptr(dpre), ptr(db), T, B, H), 5, warm=2)
+                                                ptr(dpre), ptr(db), None, T, B, H), 5, warm=2)
     rflop = 2.0 * B * 2 * 4 * H * H * T
     roof["lstm_recurrence"] = {"kernel": "tc::lstm_fwd_cluster_kernel / lstm_bwd_cluster_kernel (B=256, T=300, H=256, 2 dirs)",
                                "bound": "latency (serial over T)", "fwd_us_per_step": us_f / T, "bwd_us_per_step": us_b / T,

@@ -170,10 +170,13 @@ int deer_lstm_bwd(float* gates, const float* w_hh_fwd, const float* w_hh_rev, co
  *      T*2*Bp*4H and T*2*Bp*H floats with Bp = B rounded up to a multiple of 32; NULL for inference.
  *      db_il [2,H,4] accumulates (atomics) the bias gradient = column sums of dpre_il; may be NULL. */
 int deer_lstm_cluster_tile(int B);  /* batch columns per 4-CTA cluster the kernels will use for batch B (16 or 32) */
+/*      h_f16 / h_bf16 (forward) and dpre_bf16 (backward): optional 16-bit shadow copies of h [T,B,2H] and dpre_il
+ *      [T,B,2,H,4] written by the same kernels as operands for deer_gemm_h16 (NULL to skip). */
 int deer_lstm_cluster_fwd(const float* pre_il, const float* w_hh_fwd, const float* w_hh_rev, float* h_out, float* gact,
-                          float* c_blk, int T, int B, int H, void* stream);
+                          float* c_blk, void* h_f16, void* h_bf16, int T, int B, int H, void* stream);
 int deer_lstm_cluster_bwd(const float* gact, const float* c_blk, const float* dh_out, const float* w_hh_fwd,
-                          const float* w_hh_rev, float* dpre_il, float* db_il, int T, int B, int H, void* stream);
+                          const float* w_hh_rev, float* dpre_il, float* db_il, void* dpre_bf16, int T, int B, int H,
+                          void* stream);
 /*      rows g*H+u of src [4H,K] -> rows 4u+g of dst (inverse=0) or back (inverse=1); accumulate!=0 adds into dst */
 int deer_gate_rows_interleave(const float* src, float* dst, int H, int K, int inverse, int accumulate, void* stream);
 

@@ -113,14 +113,16 @@ def test_audio_encoder_golden(golden, name):
     m = fx.meta
     enc = load_fixture_weights(deer_b200.EnhancedAudioEncoder({"hidden_dim": m["hidden"], "dropout": 0.0}), fx).to(DEV)
     x = cu(seq_inputs(m["B"], m["T"], 2, 2, seed=m["seed"])[0]).requires_grad_(True)
+    # H=256 runs the persistent cluster kernels and the 16-bit tcgen05 GEMM engine (FP16 operands forward, BF16 in
+    # BPTT and the weight gradients, fp32 accumulation): held to the north-star tolerance, not the fp32-engine one
+    fast = m["hidden"] == 512
+    otol = TOL if fast else TOL_FP32
     h_tm = enc.lstm_forward(x)
-    assert_close(h_tm.permute(1, 0, 2), fx.t("lstm_out"), TOL_FP32, "lstm_out")
+    assert_close(h_tm.permute(1, 0, 2), fx.t("lstm_out"), otol, "lstm_out")
     y = enc(x)
-    assert_close(y, fx.t("out"), TOL_FP32, "out")
+    assert_close(y, fx.t("out"), otol, "out")
     (y * cu(probe("audio_out", y.shape, m["seed"]))).sum().backward()
-    # H=256 runs the persistent cluster kernels: BPTT multiplies BF16 operands (fp32 accumulate), so its gradients are
-    # held to the north-star tolerance rather than the fp32-engine one
-    gtol = 2 * TOL if m["hidden"] == 512 else TOL_FP32
+    gtol = 3 * TOL if fast else TOL_FP32
     assert_close(x.grad, fx.t("dx"), gtol, "dx")
     assert cosine(x.grad, fx.t("dx")) > 0.99999
     check_param_grads(enc, fx, m["seed"], gtol)

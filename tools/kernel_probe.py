@@ -42,7 +42,7 @@ if which in ("all", "lstm"):
     dpre = torch.empty(T, B, 2, 4 * H, device=dev)
     db = torch.zeros(2, 4 * H, device=dev)
     for _ in range(reps):
-        call("deer_lstm_cluster_fwd", ptr(pre), ptr(w[0]), ptr(w[1]), ptr(h), ptr(gact), ptr(c), T, B, H)
-        call("deer_lstm_cluster_bwd", ptr(gact), ptr(c), ptr(dh), ptr(w[0]), ptr(w[1]), ptr(dpre), ptr(db), T, B, H)
+        call("deer_lstm_cluster_fwd", ptr(pre), ptr(w[0]), ptr(w[1]), ptr(h), ptr(gact), ptr(c), None, None, T, B, H)
+        call("deer_lstm_cluster_bwd", ptr(gact), ptr(c), ptr(dh), ptr(w[0]), ptr(w[1]), ptr(dpre), ptr(db), None, T, B, H)
 torch.cuda.synchronize()
 print("kernel_probe done", which)

@@ -64,7 +64,7 @@ def main():
             h = torch.empty(T, B, 2 * H, device=dev)
             gact = torch.empty(T * 2 * Bp * G, device=dev)
             c = torch.empty(T * 2 * Bp * H, device=dev)
-            call("deer_lstm_cluster_fwd", ptr(pre_il), ptr(w[0]), ptr(w[1]), ptr(h), ptr(gact), ptr(c), T, B, H)
+            call("deer_lstm_cluster_fwd", ptr(pre_il), ptr(w[0]), ptr(w[1]), ptr(h), ptr(gact), ptr(c), None, None, T, B, H)
             torch.cuda.synchronize()
             return gact, h, c
         gates = pre.clone()
@@ -78,7 +78,7 @@ def main():
         if engine == AUTO:
             dpre = torch.empty(T, B, 2, G, device=dev)
             db = torch.zeros(2, G, device=dev)
-            call("deer_lstm_cluster_bwd", ptr(gates), ptr(c), ptr(dh_out), ptr(w[0]), ptr(w[1]), ptr(dpre), ptr(db), T, B, H)
+            call("deer_lstm_cluster_bwd", ptr(gates), ptr(c), ptr(dh_out), ptr(w[0]), ptr(w[1]), ptr(dpre), ptr(db), None, T, B, H)
             torch.cuda.synchronize()
             return nat(dpre), nat(db)
         gt = gates.clone()
@@ -133,15 +133,14 @@ def main():
             return e0.elapsed_time(e1) / n
         pre_il = il(pre)
         h = torch.empty(T, B, 2 * H, device=dev)
-        tf = timeit(lambda: call("deer_lstm_cluster_fwd", ptr(pre_il), ptr(w[0]), ptr(w[1]), ptr(h), ptr(g_new), ptr(c_new),
-                                 T, B, H))
-        ti = timeit(lambda: call("deer_lstm_cluster_fwd", ptr(pre_il), ptr(w[0]), ptr(w[1]), ptr(h), None, None, T, B, H))
+        tf = timeit(lambda: call("deer_lstm_cluster_fwd", ptr(pre_il), ptr(w[0]), ptr(w[1]), ptr(h), ptr(g_new), ptr(c_new), None, None, T, B, H))
+        ti = timeit(lambda: call("deer_lstm_cluster_fwd", ptr(pre_il), ptr(w[0]), ptr(w[1]), ptr(h), None, None, None, None, T, B, H))
         msg = f"[{tag}] time: fwd(keep) {tf:.3f} ms = {tf * 1e3 / T:.2f} us/step; fwd(infer) {ti:.3f} ms"
         if not a.skip_bwd:
             dpre = torch.empty(T, B, 2, G, device=dev)
             db = torch.zeros(2, G, device=dev)
             tb = timeit(lambda: call("deer_lstm_cluster_bwd", ptr(g_new), ptr(c_new), ptr(dh_out), ptr(w[0]), ptr(w[1]),
-                                     ptr(dpre), ptr(db), T, B, H))
+                                     ptr(dpre), ptr(db), None, T, B, H))
             msg += f"; bwd {tb:.3f} ms = {tb * 1e3 / T:.2f} us/step"
         print(msg, flush=True)
 

@@ -164,6 +164,11 @@ struct LstmClusterParams {
   float* c_all;        // blocked cell states: fwd out (or null), bwd in
   const float* dh_out; // bwd: [T,B,2H]
   float* db;           // bwd: [2,H,4] bias gradient (column sums of dpre), accumulated with atomics; may be null
+  // optional 16-bit shadows for the tcgen05 16-bit GEMM engine (null to skip): forward h as FP16 and/or BF16
+  // [T,B,2H]; backward dpre as BF16 [T,B,2,H,4]
+  __half* h16;
+  __nv_bfloat16* hb16;
+  __nv_bfloat16* dpre16;
   int T, B, ntiles, keep;
   long long* prof;     // optional clock64 trace of block 0 (tools/lstm_probe.py --prof), else null
 };
@@ -381,6 +386,27 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
 #pragma unroll
         for (int i = 0; i < NQ; i += 4) __stcs(cs + i * 8, make_float4(cst[i], cst[i + 1], cst[i + 2], cst[i + 3]));
       }
+      if (p.h16 || p.hb16) {
+        // the warp's [N cols x 8 units] fp16 block doubles as the source of the 16-bit shadows of h: one 16-byte
+        // store per sample row
+        __syncwarp();
+        if (lane < N && b0 + lane < B) {
+          const uint4 hv8 = *reinterpret_cast<const uint4*>(sh + lane * 8);
+          const long long o = ((long long)t * B + b0 + lane) * (2 * QH) + dir * QH + (int)r * QU + a * 32 + sub * 8;
+          if (p.h16) *reinterpret_cast<uint4*>(p.h16 + o) = hv8;
+          if (p.hb16) {
+            const __half2* hp = reinterpret_cast<const __half2*>(&hv8);
+            uint4 bv;
+            uint32_t* bp = reinterpret_cast<uint32_t*>(&bv);
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+              const float2 f = __half22float2(hp[e]);
+              bp[e] = pack_bf2(f.x, f.y);
+            }
+            *reinterpret_cast<uint4*>(p.hb16 + o) = bv;
+          }
+        }
+      }
       if (warp == 0 && lane == 0) Q_PROF(4);
       if (s + 1 < T) {
         // all-gather: this warp's [N cols x 8 units] fp16 block is k-chunk 8r+4a+sub of every CTA's B operand; one
@@ -595,15 +621,17 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
         const float pf = dcc * vcp[i] * vf[i] * (1.f - vf[i]);
         const float pg = dcc * vi[i] * (1.f - vg[i] * vg[i]);
         const float po = d_o * vo[i] * (1.f - vo[i]);
+        uint2 v;
+        v.x = pack_bf2(pi, pf);
+        v.y = pack_bf2(pg, po);
         if (b0 + q * NQ + i < B) {
           __stcs(reinterpret_cast<float4*>(gout + (long long)i * (8 * QH)), make_float4(pi, pf, pg, po));
+          if (p.dpre16)
+            *reinterpret_cast<uint2*>(p.dpre16 + (((long long)t * B + b0 + q * NQ + i) * 2 + dir) * (4 * QH) + 4 * ug) = v;
           sdb[0] += pi; sdb[1] += pf; sdb[2] += pg; sdb[3] += po;
         }
         if (s + 1 < T) {
           const int n = q * NQ + i;
-          uint2 v;
-          v.x = pack_bf2(pi, pf);
-          v.y = pack_bf2(pg, po);
           *reinterpret_cast<uint2*>(bsm + kb * (N * 128) + sw128(n, ch) + (ul & 1) * 8) = v;
         }
       }
@@ -723,20 +751,22 @@ static int launch_bwd(const tc::LstmClusterParams& p, cudaStream_t stream) {
 int lstm_cluster_tile(int B) { return pick_tile(B); }
 
 int lstm_fwd_cluster(const float* pre_il, const float* w_fwd, const float* w_rev, float* h_out, float* gact,
-                     float* c_blk, int T, int B, cudaStream_t stream) {
+                     float* c_blk, void* h16, void* hb16, int T, int B, cudaStream_t stream) {
   const int N = pick_tile(B);
   const int keep = (gact != nullptr && c_blk != nullptr) ? 1 : 0;
-  tc::LstmClusterParams p{const_cast<float*>(pre_il), w_fwd, w_rev, h_out, gact, c_blk, nullptr, nullptr, T, B,
+  tc::LstmClusterParams p{const_cast<float*>(pre_il), w_fwd, w_rev, h_out, gact, c_blk, nullptr, nullptr,
+                          reinterpret_cast<__half*>(h16), reinterpret_cast<__nv_bfloat16*>(hb16), nullptr, T, B,
                           (B + N - 1) / N, keep, g_lstm_prof};
   if (N == 16) return g_lstm_ts ? launch_fwd<16, true>(p, stream) : launch_fwd<16, false>(p, stream);
   return g_lstm_ts ? launch_fwd<32, true>(p, stream) : launch_fwd<32, false>(p, stream);
 }
 
 int lstm_bwd_cluster(const float* gact, const float* c_blk, const float* dh_out, const float* w_fwd, const float* w_rev,
-                     float* dpre_il, float* db_il, int T, int B, cudaStream_t stream) {
+                     float* dpre_il, float* db_il, void* dpre16, int T, int B, cudaStream_t stream) {
   const int N = pick_tile(B);
   tc::LstmClusterParams p{dpre_il, w_fwd, w_rev, nullptr, const_cast<float*>(gact), const_cast<float*>(c_blk), dh_out,
-                          db_il, T, B, (B + N - 1) / N, 1, g_lstm_prof};
+                          db_il, nullptr, nullptr, reinterpret_cast<__nv_bfloat16*>(dpre16), T, B, (B + N - 1) / N, 1,
+                          g_lstm_prof};
   if (N == 16) return g_lstm_ts ? launch_bwd<16, true>(p, stream) : launch_bwd<16, false>(p, stream);
   return launch_bwd<32, true>(p, stream);  // the N=32 tiles + 128 KB of smem-resident weights exceed 227 KB
 }
@@ -750,24 +780,28 @@ extern "C" {
 int deer_lstm_cluster_tile(int B) { return B > 0 ? lstm_cluster_tile(B) : DEER_ERR_INVALID; }
 
 int deer_lstm_cluster_fwd(const float* pre_il, const float* w_hh_fwd, const float* w_hh_rev, float* h_out, float* gact,
-                          float* c_blk, int T, int B, int H, void* stream) {
+                          float* c_blk, void* h_f16, void* h_bf16, int T, int B, int H, void* stream) {
   DEER_CHECK_ARG(pre_il && w_hh_fwd && w_hh_rev && h_out && T > 0 && B > 0, "lstm_cluster_fwd: bad args");
   DEER_CHECK_ARG((gact == nullptr) == (c_blk == nullptr), "lstm_cluster_fwd: gact and c_blk go together");
   if (!lstm_cluster_supported(pre_il, w_hh_fwd, w_hh_rev, H)) {
     set_error("lstm_cluster_fwd: needs H == 256 and 16-byte aligned pointers");
     return DEER_ERR_UNSUPPORTED;
   }
-  return lstm_fwd_cluster(pre_il, w_hh_fwd, w_hh_rev, h_out, gact, c_blk, T, B, (cudaStream_t)stream);
+  DEER_CHECK_ARG(((reinterpret_cast<uintptr_t>(h_f16) | reinterpret_cast<uintptr_t>(h_bf16)) & 15) == 0,
+                 "lstm_cluster_fwd: 16-bit shadows must be 16-byte aligned");
+  return lstm_fwd_cluster(pre_il, w_hh_fwd, w_hh_rev, h_out, gact, c_blk, h_f16, h_bf16, T, B, (cudaStream_t)stream);
 }
 
 int deer_lstm_cluster_bwd(const float* gact, const float* c_blk, const float* dh_out, const float* w_hh_fwd,
-                          const float* w_hh_rev, float* dpre_il, float* db_il, int T, int B, int H, void* stream) {
+                          const float* w_hh_rev, float* dpre_il, float* db_il, void* dpre_bf16, int T, int B, int H,
+                          void* stream) {
   DEER_CHECK_ARG(gact && c_blk && dh_out && w_hh_fwd && w_hh_rev && dpre_il && T > 0 && B > 0, "lstm_cluster_bwd: bad args");
   if (!lstm_cluster_supported(dpre_il, w_hh_fwd, w_hh_rev, H)) {
     set_error("lstm_cluster_bwd: needs H == 256 and 16-byte aligned pointers");
     return DEER_ERR_UNSUPPORTED;
   }
-  return lstm_bwd_cluster(gact, c_blk, dh_out, w_hh_fwd, w_hh_rev, dpre_il, db_il, T, B, (cudaStream_t)stream);
+  DEER_CHECK_ARG((reinterpret_cast<uintptr_t>(dpre_bf16) & 15) == 0, "lstm_cluster_bwd: dpre_bf16 must be 16-byte aligned");
+  return lstm_bwd_cluster(gact, c_blk, dh_out, w_hh_fwd, w_hh_rev, dpre_il, db_il, dpre_bf16, T, B, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -24,7 +24,12 @@ ENGINE_AUTO, ENGINE_SIMT, ENGINE_TF32 = 0, 1, 2
 # prone) outputs feed the bias / scorer gradients whose per-tensor cosine otherwise sits at 0.9992, too close to the
 # 0.999 gate (tools/precision_probe.py).
 _state = {"engine": ENGINE_AUTO, "lstm_engine": ENGINE_AUTO, "exact_small_fwd": True, "exact_small_bwd": True,
-          "small_rows": 8192, "direct_grad": False}
+          "small_rows": 8192, "direct_grad": False, "lstm_gemm16": True}
+
+
+def set_lstm_gemm16(on: bool):
+    """Route the LSTM layer's time-batched GEMMs through the 16-bit tcgen05 engine (default) or the TF32 engine."""
+    _state["lstm_gemm16"] = bool(on)
 
 
 def set_direct_grad_accumulation(on: bool):
@@ -469,7 +474,12 @@ class _BiLSTMLayerCluster(torch.autograd.Function):
 
     The kernels read/write the gate dimension INTERLEAVED (column 4*unit+gate), so the input projection runs on
     row-interleaved copies of W_ih / (b_ih+b_hh) and the weight gradients computed from the interleaved dpre are
-    un-interleaved (accumulating) into their targets.  The bias gradient comes out of the BPTT kernel itself."""
+    un-interleaved (accumulating) into their targets.  The bias gradient comes out of the BPTT kernel itself.
+
+    The five time-batched contractions of the layer (input projection, dx, dW_ih, dW_hh x2 directions) run on the
+    16-bit tcgen05 engine (deer_gemm_h16): forward operands FP16 (same 11 significant bits as TF32 for these value
+    ranges), backward operands BF16.  The LSTM kernels write the 16-bit shadows of h and dpre themselves; x and the
+    weights are cast once per call."""
 
     @staticmethod
     def forward(ctx, x, wif, whf, bif, bhf, wir, whr, bir, bhr):
@@ -479,6 +489,7 @@ class _BiLSTMLayerCluster(torch.autograd.Function):
         G = 4 * H
         dev = x.device
         keep = any(ctx.needs_input_grad)
+        use16 = _state["lstm_gemm16"] and _state["engine"] == ENGINE_AUTO   # a forced engine (tests) is respected
         wi_il = torch.empty((2, G, In), device=dev, dtype=torch.float32)
         b_il = torch.empty((2, G), device=dev, dtype=torch.float32)
         bsum = torch.empty(G, device=dev, dtype=torch.float32)
@@ -488,20 +499,33 @@ class _BiLSTMLayerCluster(torch.autograd.Function):
             call("deer_gate_rows_interleave", ptr(bsum), ptr(b_il[d]), H, 1, 0, 0)
         pre = torch.empty((T, B, 2, G), device=dev, dtype=torch.float32)
         M = T * B
-        for d in range(2):
-            gemm(x, In, 0, wi_il[d], In, 1, pre.data_ptr() + 4 * G * d, 2 * G, M, G, In, bias=b_il[d])
+        x16 = None
+        if use16:
+            x16 = cast16(x)                                   # [M, Kp] fp16
+            Kp = x16.shape[1]
+            w16 = cast16(wi_il.view(2 * G, In))               # [2G, Kp] fp16
+            for d in range(2):
+                gemm_h16(x16, Kp, 0, w16.data_ptr() + 2 * d * G * Kp, Kp, 1, pre.data_ptr() + 4 * G * d, 2 * G, M, G, In,
+                         bias=b_il[d])
+        else:
+            for d in range(2):
+                gemm(x, In, 0, wi_il[d], In, 1, pre.data_ptr() + 4 * G * d, 2 * G, M, G, In, bias=b_il[d])
         h = torch.empty((T, B, 2 * H), device=dev, dtype=torch.float32)
         whf_c, whr_c = whf.contiguous(), whr.contiguous()
         if keep:
             Bp = (B + 31) // 32 * 32
             gact = torch.empty(T * 2 * Bp * G, device=dev, dtype=torch.float32)
             c_blk = torch.empty(T * 2 * Bp * H, device=dev, dtype=torch.float32)
-            call("deer_lstm_cluster_fwd", ptr(pre), ptr(whf_c), ptr(whr_c), ptr(h), ptr(gact), ptr(c_blk), T, B, H)
+            hb16 = torch.empty((T, B, 2 * H), device=dev, dtype=torch.bfloat16) if use16 else None
+            call("deer_lstm_cluster_fwd", ptr(pre), ptr(whf_c), ptr(whr_c), ptr(h), ptr(gact), ptr(c_blk), None,
+                 None if hb16 is None else hb16.data_ptr(), T, B, H)
             ctx.save_for_backward(x, wi_il, whf_c, whr_c, gact, c_blk, h)
             ctx.pre = pre   # reused as the dpre buffer
+            ctx.hb16 = hb16
         else:
-            call("deer_lstm_cluster_fwd", ptr(pre), ptr(whf_c), ptr(whr_c), ptr(h), None, None, T, B, H)
+            call("deer_lstm_cluster_fwd", ptr(pre), ptr(whf_c), ptr(whr_c), ptr(h), None, None, None, None, T, B, H)
         ctx.dims = (T, B, In, H)
+        ctx.use16 = use16
         ctx.params = (wif, whf, bif, bhf, wir, whr, bir, bhr)
         return h
 
@@ -513,12 +537,25 @@ class _BiLSTMLayerCluster(torch.autograd.Function):
         dev = x.device
         dh = dh.contiguous()
         dpre = ctx.pre
-        ctx.pre = None
-        db_il = torch.zeros((2, G), device=dev, dtype=torch.float32)
-        call("deer_lstm_cluster_bwd", ptr(gact), ptr(c_blk), ptr(dh), ptr(whf), ptr(whr), ptr(dpre), ptr(db_il), T, B, H)
+        hb16 = ctx.hb16
+        ctx.pre = ctx.hb16 = None
+        use16 = ctx.use16
         M = T * B
+        db_il = torch.zeros((2, G), device=dev, dtype=torch.float32)
+        dpre16 = torch.empty((T, B, 2, G), device=dev, dtype=torch.bfloat16) if use16 else None
+        call("deer_lstm_cluster_bwd", ptr(gact), ptr(c_blk), ptr(dh), ptr(whf), ptr(whr), ptr(dpre), ptr(db_il),
+             None if dpre16 is None else dpre16.data_ptr(), T, B, H)
         dx = None
-        if ctx.needs_input_grad[0]:
+        if use16:
+            xb16 = cast16(x, bf16=True)                        # [M, Kp] bf16: B operand of dW_ih (MN-major)
+            Kp = xb16.shape[1]
+            if ctx.needs_input_grad[0]:
+                wb16 = cast16(wi_il.view(2 * G, In), bf16=True)   # [2G, Kp] bf16: B operand of dx (MN-major [K=G, N=In])
+                dx = torch.empty((T, B, In), device=dev, dtype=torch.float32)
+                for d in range(2):
+                    gemm_h16(dpre16.data_ptr() + 2 * G * d, 2 * G, 0, wb16.data_ptr() + 2 * d * G * Kp, Kp, 0, dx, In,
+                             M, In, G, a_bf16=True, b_bf16=True, beta=0.0 if d == 0 else 1.0)
+        elif ctx.needs_input_grad[0]:
             dx = torch.empty((T, B, In), device=dev, dtype=torch.float32)
             for d in range(2):
                 gemm(dpre.data_ptr() + 4 * G * d, 2 * G, 0, wi_il[d], In, 0, dx, In, M, In, G,
@@ -528,16 +565,27 @@ class _BiLSTMLayerCluster(torch.autograd.Function):
         for d in range(2):
             gp = dpre.data_ptr() + 4 * G * d
             dwi_il = torch.zeros((G, In), device=dev, dtype=torch.float32)
-            gemm(gp, 2 * G, 1, x, In, 0, dwi_il, In, G, In, M, beta=1.0)
+            dwh_il = torch.zeros((G, H), device=dev, dtype=torch.float32)
+            Mr = (T - 1) * B
+            if use16:
+                gp16 = dpre16.data_ptr() + 2 * G * d
+                gemm_h16(gp16, 2 * G, 1, xb16, Kp, 0, dwi_il, In, G, In, M, a_bf16=True, b_bf16=True, beta=1.0)
+                if T > 1:
+                    if d == 0:   # rows t=1.. pair with h[t-1]
+                        gemm_h16(gp16 + 2 * B * 2 * G, 2 * G, 1, hb16.data_ptr(), 2 * H, 0, dwh_il, H, G, H, Mr,
+                                 a_bf16=True, b_bf16=True, beta=1.0)
+                    else:        # rows t=..T-2 pair with h[t+1]
+                        gemm_h16(gp16, 2 * G, 1, hb16.data_ptr() + 2 * (B * 2 * H + H), 2 * H, 0, dwh_il, H, G, H, Mr,
+                                 a_bf16=True, b_bf16=True, beta=1.0)
+            else:
+                gemm(gp, 2 * G, 1, x, In, 0, dwi_il, In, G, In, M, beta=1.0)
+                if T > 1:
+                    if d == 0:
+                        gemm(gp + 4 * B * 2 * G, 2 * G, 1, h.data_ptr(), 2 * H, 0, dwh_il, H, G, H, Mr, beta=1.0)
+                    else:
+                        gemm(gp, 2 * G, 1, h.data_ptr() + 4 * (B * 2 * H + H), 2 * H, 0, dwh_il, H, G, H, Mr, beta=1.0)
             dwi, dwi_direct = _acc(P[4 * d])
             call("deer_gate_rows_interleave", ptr(dwi_il), ptr(dwi), H, In, 1, 1)
-            dwh_il = torch.zeros((G, H), device=dev, dtype=torch.float32)
-            if T > 1:
-                Mr = (T - 1) * B
-                if d == 0:   # rows t=1.. pair with h[t-1]
-                    gemm(gp + 4 * B * 2 * G, 2 * G, 1, h.data_ptr(), 2 * H, 0, dwh_il, H, G, H, Mr, beta=1.0)
-                else:        # rows t=..T-2 pair with h[t+1]
-                    gemm(gp, 2 * G, 1, h.data_ptr() + 4 * (B * 2 * H + H), 2 * H, 0, dwh_il, H, G, H, Mr, beta=1.0)
             dwh, dwh_direct = _acc(P[4 * d + 1])
             call("deer_gate_rows_interleave", ptr(dwh_il), ptr(dwh), H, H, 1, 1)
             dbs = []
