@@ -231,13 +231,23 @@ def main():
                 dev_bufs[j][k].copy_(v, non_blocking=True)
             ready[j].record(copy_stream)
 
+    loss_host = [torch.zeros(1).pin_memory() for _ in range(2)]     # pinned landing buffers for the per-step loss
+    loss_done = [torch.cuda.Event() for _ in range(2)]
+    loss_log = []
+
     def e2e_fn(i):
         j = i % 2
         stage(i + 1)                                     # prefetch the next step's batch
         torch.cuda.current_stream().wait_event(ready[j])
         losses = trainer.train_step(dev_bufs[j])
         consumed[j].record()
-        _ = losses[-1].item()  # D2H read of the step's loss
+        # D2H read of the step's loss: asynchronous copy into pinned memory every step; the host consumes the value
+        # one step later (after its event), so kernel launches of step i+1 are never held back by a device sync
+        loss_host[j].copy_(losses[-1:], non_blocking=True)
+        loss_done[j].record()
+        if i > 0:
+            loss_done[1 - j].synchronize()
+            loss_log.append(float(loss_host[1 - j]))
 
     for j in range(2):
         consumed[j].record()
@@ -253,6 +263,7 @@ def main():
     e2e_ms = timed(e2e_timed, K) / K
     e2e_value = TRAIN_B * world / (e2e_ms / 1e3)
     torch.cuda.synchronize()
+    assert len(loss_log) >= K and all(v == v for v in loss_log[-K:]), "e2e loop must deliver a finite loss every step"
 
     # ------------------------------------------------------------------ inference B=1024
     model.eval()
@@ -333,32 +344,38 @@ def _time_launches(torch, fn, n, warm=5):
 def roofline_probe(torch, ops, dev, pk):
     """Kernels timed alone with CUDA events on the launching stream (operands rotate through buffers larger than L2).
 
-    Headline = the dominant kernel family of the training step, the tcgen05 GEMM, on its largest instance: the
+    Headline = the dense-contraction engine of the training step (16-bit tcgen05 GEMM) on its largest instance: the
     time-batched layer-1 LSTM input projection gates[B*T,1024] = h0[B*T,512] W_ih^T (one direction).
     Extra entries: the fused NIG head+loss kernels at a size where HBM traffic dominates (north-star target: fraction
     of HBM peak) and the persistent LSTM recurrence (latency-bound: us per step)."""
     B, T, H = TRAIN_B, TA, 256
     M, N, K = B * T, 4 * H, 2 * H
-    nbuf = 3   # 3 x (157 MB A + 315 MB C) > 126 MB L2
-    A = [torch.randn(M, K, device=dev) for _ in range(nbuf)]
-    W = torch.randn(N, K, device=dev) * 0.05
+    nbuf = 3   # 3 x (79 MB A + 315 MB C) > 126 MB L2
+    A = [(torch.randn(M, K, device=dev) * 0.5).half() for _ in range(nbuf)]
+    W = (torch.randn(N, K, device=dev) * 0.05).half()
     bias = torch.randn(N, device=dev)
     C = [torch.empty(M, 2 * N, device=dev) for _ in range(nbuf)]
 
     def gemm_launch(i):
         j = i % nbuf
-        ops.gemm(A[j], K, 0, W, K, 1, C[j], 2 * N, M, N, K, bias=bias)
+        ops.gemm_h16(A[j], K, 0, W, K, 1, C[j], 2 * N, M, N, K, bias=bias)
 
     us = _time_launches(torch, gemm_launch, 12)
     flop = 2.0 * M * N * K
     achieved = flop / (us * 1e-6) / 1e12
-    tf32_peak = pk["bf16_tflops"] / 2
-    roof = {"kernel": "tc::gemm_tf32_kernel<0,0> (layer-1 LSTM input projection, [76800,512]x[512,1024], TF32 operands)",
+    roof = {"kernel": "h16::gemm_h16_kernel<0,0> (layer-1 LSTM input projection, [76800,512]x[512,1024]^T, FP16 operands, "
+                      "fp32 accumulate/output, bias epilogue)",
             "bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-            "frac": achieved / pk["bf16_tflops"], "frac_of_tf32_peak": achieved / tf32_peak, "traffic": None,
-            "us_per_launch": us, "flop_per_launch": flop,
-            "peak_source": f"{pk['source']} cuBLAS bf16 burst (MEASURED_PEAKS.json); TF32 dense peak is half of it"}
-    del A, C
+            "frac": achieved / pk["bf16_tflops"], "traffic": None, "us_per_launch": us, "flop_per_launch": flop,
+            "algorithmic_bytes_per_launch": float(M * K * 2 + N * K * 2 + M * N * 4),
+            "peak_source": f"{pk['source']} cuBLAS bf16 burst (MEASURED_PEAKS.json)"}
+    # the same contraction on the TF32 engine (operands fp32 in HBM), for reference
+    A32 = torch.randn(M, K, device=dev)
+    W32 = torch.randn(N, K, device=dev) * 0.05
+    us32 = _time_launches(torch, lambda i: ops.gemm(A32, K, 0, W32, K, 1, C[i % nbuf], 2 * N, M, N, K, bias=bias), 8)
+    roof["tf32_engine_same_shape"] = {"kernel": "tc::gemm_tf32_kernel<0,0>", "us_per_launch": us32,
+                                      "achieved": flop / (us32 * 1e-6) / 1e12, "unit": "TFLOP/s"}
+    del A, C, A32, W32
     torch.cuda.empty_cache()
 
     # ---- fused NIG head + loss (two phases) at 2^22 samples x 3 dims: 192 B/sample algorithmic traffic

@@ -146,8 +146,10 @@ struct QLayout {
   static constexpr int HB_BYTES = N * QH * 2;        // one B-operand tile: N rows x 256 k x 16 bit
   static constexpr int ACT_BYTES = 8 * 32 * ROWF * 4;  // forward: per-warp activation transpose tiles
   static constexpr int SH_BYTES = 2 * 8 * N * 16;      // forward: double-buffered per-warp fp16 h blocks [N cols][8 units]
-  static constexpr int PART_BYTES = QC * QU * ROWF * 4;  // backward: one buffer of partial-dh slots [src][unit][N]
-  static constexpr int PSTAGE_BYTES = 2 * 8 * 32 * ROWF * 4;  // backward: double-buffered per-warp partial rows
+  // backward: the partial dh rows travel as BF16 (DSMEM moves ~20 B/cycle/SM, so the reduce-scatter volume is the
+  // longest stage of a BPTT step; BF16 halves it and matches the operand precision of the MMA that follows)
+  static constexpr int PART_BYTES = QC * QU * N * 2;        // one buffer of partial-dh slots [src][unit][N] bf16
+  static constexpr int PSTAGE_BYTES = 2 * 8 * 32 * N * 2;   // double-buffered per-warp partial rows [32][N] bf16
 };
 
 // Layouts.  `pre` / `dpre` are GATE-INTERLEAVED [T,B,2,H,4] (column 4*unit+gate: the input-projection GEMM runs on
@@ -346,7 +348,7 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
 #pragma unroll
       for (int n = 0; n < N; n += 4)
         *reinterpret_cast<float4*>(sa + lane * ROWF + n) = make_float4(x[n], x[n + 1], x[n + 2], x[n + 3]);
-      if (s + 1 < T) load_pre(s + 1);  // in flight across the cell update and the exchange
+      if (s + 1 < T) load_pre(s + 1);  // a full step ahead of its use: DRAM latency never lands on the critical path
       __syncwarp();
       if (warp == 0 && lane == 0) Q_PROF(3);
       float gi[NQ], gf[NQ], gg[NQ], go[NQ];
@@ -361,35 +363,51 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
         gg[i] = vg.x; gg[i + 1] = vg.y; gg[i + 2] = vg.z; gg[i + 3] = vg.w;
         go[i] = vo.x; go[i + 1] = vo.y; go[i + 2] = vo.z; go[i + 3] = vo.w;
       }
+      float hv[NQ];
+#pragma unroll
+      for (int i = 0; i < NQ; i++) {
+        const float cn = fmaf(gf[i], cst[i], gi[i] * gg[i]);
+        cst[i] = cn;
+        hv[i] = go[i] * tanh_f(cn);
+        sh[(q * NQ + i) * 8 + j] = __float2half_rn(hv[i]);
+      }
+      if (warp == 0 && lane == 0) Q_PROF(4);
+      if (s + 1 < T) {
+        // all-gather FIRST (it is the only thing the next step waits for): this warp's [N cols x 8 units] fp16 block is
+        // k-chunk 8r+4a+sub of every CTA's B operand; one async-proxy bulk copy per destination, completion counted on
+        // the destination's h_full barrier
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane < QC) {
+          const uint32_t dst = smem_u32(hbuf) + (s & 1) * L::HB_BYTES + ((int)r * 8 + 4 * a + sub) * (N * 16);
+          bulk_copy_to_peer(mapa_u32(dst, (uint32_t)lane), smem_u32(sh), N * 16,
+                            mapa_u32(smem_u32(&h_full[s & 1]), (uint32_t)lane));
+        }
+        if (warp == 0 && lane == 0) Q_PROF(5);
+      } else {
+        __syncwarp();
+      }
+      // ---- everything below is off the recurrence's critical path: global stores of this step's results
       const long long row0 = (long long)t * B + b0 + q * NQ;
       const long long blk = (long long)t * blk_t + blk_w;
+#pragma unroll
+      for (int i = 0; i < NQ; i++)
+        if (b0 + q * NQ + i < B) p.h_out[(row0 + i) * (2 * QH) + dir * QH + ug] = hv[i];
       if (p.keep) {
         float4* gs = reinterpret_cast<float4*>(p.gact + blk * (4 * NQ * 32)) + lane;
+        float4* cs = reinterpret_cast<float4*>(p.c_all + blk * (NQ * 32)) + lane;
 #pragma unroll
         for (int i = 0; i < NQ; i += 4) {
           __stcs(gs + (0 * NQ + i) * 8, make_float4(gi[i], gi[i + 1], gi[i + 2], gi[i + 3]));
           __stcs(gs + (1 * NQ + i) * 8, make_float4(gf[i], gf[i + 1], gf[i + 2], gf[i + 3]));
           __stcs(gs + (2 * NQ + i) * 8, make_float4(gg[i], gg[i + 1], gg[i + 2], gg[i + 3]));
           __stcs(gs + (3 * NQ + i) * 8, make_float4(go[i], go[i + 1], go[i + 2], go[i + 3]));
+          __stcs(cs + i * 8, make_float4(cst[i], cst[i + 1], cst[i + 2], cst[i + 3]));
         }
-      }
-#pragma unroll
-      for (int i = 0; i < NQ; i++) {
-        const float cn = fmaf(gf[i], cst[i], gi[i] * gg[i]);
-        cst[i] = cn;
-        const float hv = go[i] * tanh_f(cn);
-        if (b0 + q * NQ + i < B) p.h_out[(row0 + i) * (2 * QH) + dir * QH + ug] = hv;
-        sh[(q * NQ + i) * 8 + j] = __float2half_rn(hv);
-      }
-      if (p.keep) {
-        float4* cs = reinterpret_cast<float4*>(p.c_all + blk * (NQ * 32)) + lane;
-#pragma unroll
-        for (int i = 0; i < NQ; i += 4) __stcs(cs + i * 8, make_float4(cst[i], cst[i + 1], cst[i + 2], cst[i + 3]));
       }
       if (p.h16 || p.hb16) {
         // the warp's [N cols x 8 units] fp16 block doubles as the source of the 16-bit shadows of h: one 16-byte
-        // store per sample row
-        __syncwarp();
+        // store per sample row (the tile is double-buffered and only READ by the bulk copies in flight)
         if (lane < N && b0 + lane < B) {
           const uint4 hv8 = *reinterpret_cast<const uint4*>(sh + lane * 8);
           const long long o = ((long long)t * B + b0 + lane) * (2 * QH) + dir * QH + (int)r * QU + a * 32 + sub * 8;
@@ -406,19 +424,6 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
             *reinterpret_cast<uint4*>(p.hb16 + o) = bv;
           }
         }
-      }
-      if (warp == 0 && lane == 0) Q_PROF(4);
-      if (s + 1 < T) {
-        // all-gather: this warp's [N cols x 8 units] fp16 block is k-chunk 8r+4a+sub of every CTA's B operand; one
-        // async-proxy bulk copy per destination, completion counted on the destination's h_full barrier
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane < QC) {
-          const uint32_t dst = smem_u32(hbuf) + (s & 1) * L::HB_BYTES + ((int)r * 8 + 4 * a + sub) * (N * 16);
-          bulk_copy_to_peer(mapa_u32(dst, (uint32_t)lane), smem_u32(sh), N * 16,
-                            mapa_u32(smem_u32(&h_full[s & 1]), (uint32_t)lane));
-        }
-        if (warp == 0 && lane == 0) Q_PROF(5);
       }
     }
   }
@@ -443,8 +448,8 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* wsm = smem;                                   // SS: 128 KB resident W^T slice
   uint8_t* bsm = smem + (TS ? 0 : QW_BYTES);             // B operand: dpre tile [N rows x 256 k] bf16
-  float* part = reinterpret_cast<float*>(bsm + L::HB_BYTES);  // [2][QC src][QU units][ROWF]
-  float* pstage = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(part) + 2 * L::PART_BYTES);  // [8 warps][2][32][ROWF]
+  __nv_bfloat16* part = reinterpret_cast<__nv_bfloat16*>(bsm + L::HB_BYTES);  // [2][QC src][QU units][N]
+  __nv_bfloat16* pstage = part + 2 * (L::PART_BYTES / 2);                      // [8 warps][2][32][N]
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(pstage) + L::PSTAGE_BYTES);
   uint64_t* part_full = bars;     // [2]
   uint64_t* b_ready = bars + 2;
@@ -599,48 +604,57 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
       if (s > 0) {
         mbar_wait(&part_full[(s - 1) & 1], (uint32_t)(((s - 1) >> 1) & 1));
         if (warp == 0 && lane == 0) Q_PROF(2);
-        const float* ps = part + ((s - 1) & 1) * (QC * QU * ROWF) + ul * ROWF + q * NQ;
+        const __nv_bfloat16* ps = part + ((s - 1) & 1) * (QC * QU * N) + ul * N + q * NQ;
 #pragma unroll
         for (int src = 0; src < QC; src++) {
 #pragma unroll
           for (int i = 0; i < NQ; i += 4) {
-            const float4 v = *reinterpret_cast<const float4*>(ps + src * (QU * ROWF) + i);
-            dh[i] += v.x; dh[i + 1] += v.y; dh[i + 2] += v.z; dh[i + 3] += v.w;
+            const uint2 v = *reinterpret_cast<const uint2*>(ps + src * (QU * N) + i);
+            const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v.x));
+            const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v.y));
+            dh[i] += lo.x; dh[i + 1] += lo.y; dh[i + 2] += hi.x; dh[i + 3] += hi.y;
           }
         }
       }
       float* gout = p.gates + (((long long)t * B + b0 + q * NQ) * 2 + dir) * (4 * QH) + 4 * ug;
       const int kb = ul >> 4, ch = (ul & 15) >> 1;
+      float4 dp[NQ];
+      uint2 dp16[NQ];
 #pragma unroll
       for (int i = 0; i < NQ; i++) {
         const float tc_ = tanh_f(vc[i]);
         const float d_o = dh[i] * tc_;
         const float dcc = fmaf(dh[i] * vo[i], 1.f - tc_ * tc_, dc[i]);
         dc[i] = dcc * vf[i];
-        const float pi = dcc * vg[i] * vi[i] * (1.f - vi[i]);
-        const float pf = dcc * vcp[i] * vf[i] * (1.f - vf[i]);
-        const float pg = dcc * vi[i] * (1.f - vg[i] * vg[i]);
-        const float po = d_o * vo[i] * (1.f - vo[i]);
-        uint2 v;
-        v.x = pack_bf2(pi, pf);
-        v.y = pack_bf2(pg, po);
-        if (b0 + q * NQ + i < B) {
-          __stcs(reinterpret_cast<float4*>(gout + (long long)i * (8 * QH)), make_float4(pi, pf, pg, po));
-          if (p.dpre16)
-            *reinterpret_cast<uint2*>(p.dpre16 + (((long long)t * B + b0 + q * NQ + i) * 2 + dir) * (4 * QH) + 4 * ug) = v;
-          sdb[0] += pi; sdb[1] += pf; sdb[2] += pg; sdb[3] += po;
-        }
+        dp[i].x = dcc * vg[i] * vi[i] * (1.f - vi[i]);
+        dp[i].y = dcc * vcp[i] * vf[i] * (1.f - vf[i]);
+        dp[i].z = dcc * vi[i] * (1.f - vg[i] * vg[i]);
+        dp[i].w = d_o * vo[i] * (1.f - vo[i]);
+        dp16[i].x = pack_bf2(dp[i].x, dp[i].y);
+        dp16[i].y = pack_bf2(dp[i].z, dp[i].w);
         if (s + 1 < T) {
           const int n = q * NQ + i;
-          *reinterpret_cast<uint2*>(bsm + kb * (N * 128) + sw128(n, ch) + (ul & 1) * 8) = v;
+          *reinterpret_cast<uint2*>(bsm + kb * (N * 128) + sw128(n, ch) + (ul & 1) * 8) = dp16[i];
         }
       }
       if (s + 1 < T) {
+        // hand the BF16 dpre tile to the tensor core FIRST; the global stores of dpre follow off the critical path
         fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(b_ready);
         if (warp == 0 && lane == 0) Q_PROF(3);
+      }
+#pragma unroll
+      for (int i = 0; i < NQ; i++) {
+        if (b0 + q * NQ + i < B) {
+          __stcs(reinterpret_cast<float4*>(gout + (long long)i * (8 * QH)), dp[i]);
+          if (p.dpre16)
+            *reinterpret_cast<uint2*>(p.dpre16 + (((long long)t * B + b0 + q * NQ + i) * 2 + dir) * (4 * QH) + 4 * ug) = dp16[i];
+          sdb[0] += dp[i].x; sdb[1] += dp[i].y; sdb[2] += dp[i].z; sdb[3] += dp[i].w;
+        }
+      }
+      if (s + 1 < T) {
         load_step(s + 1);  // next step's operands stream in while the tensor core and the exchange run
         mbar_wait(mma_done, (uint32_t)(s & 1));
         if (warp == 0 && lane == 0) Q_PROF(4);
@@ -650,16 +664,20 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
         tmem_ld_wait();
         // reduce-scatter: this warp's 32 accumulator rows (hidden units of CTA dst_cta) go to that CTA's slot
         // [buf][src r][rows] with one async-proxy bulk copy; completion is counted on its part_full barrier
-        float* st = pstage + (warp * 2 + (s & 1)) * (32 * ROWF);
+        __nv_bfloat16* st = pstage + (warp * 2 + (s & 1)) * (32 * N);
 #pragma unroll
-        for (int n = 0; n < N; n += 4)
-          *reinterpret_cast<float4*>(st + lane * ROWF + n) = make_float4(x[n], x[n + 1], x[n + 2], x[n + 3]);
+        for (int n = 0; n < N; n += 8) {
+          uint4 v;
+          v.x = pack_bf2(x[n], x[n + 1]); v.y = pack_bf2(x[n + 2], x[n + 3]);
+          v.z = pack_bf2(x[n + 4], x[n + 5]); v.w = pack_bf2(x[n + 6], x[n + 7]);
+          *reinterpret_cast<uint4*>(st + lane * N + n) = v;
+        }
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
           const uint32_t slot =
-              smem_u32(part) + (uint32_t)(((s & 1) * QC + (int)r) * QU + (sub & 1) * 32) * (ROWF * 4);
-          bulk_copy_to_peer(mapa_u32(slot, dst_cta), smem_u32(st), 32 * ROWF * 4,
+              smem_u32(part) + (uint32_t)(((s & 1) * QC + (int)r) * QU + (sub & 1) * 32) * (N * 2);
+          bulk_copy_to_peer(mapa_u32(slot, dst_cta), smem_u32(st), 32 * N * 2,
                             mapa_u32(smem_u32(&part_full[s & 1]), dst_cta));
         }
         if (warp == 0 && lane == 0) Q_PROF(5);
