@@ -143,6 +143,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-pooled", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     if args.impl == "reference":
@@ -289,6 +290,10 @@ def main():
     # ------------------------------------------------------------------ roofline of the dominant kernel
     roof = roofline_probe(torch, ops, dev, pk)
 
+    # ------------------------------------------------------------------ BASELINE configs[4]: pooled CompleteDEERModel on
+    # multi-dataset-shaped batches (84/256/768-D vectors + targets[3] + dataset_id), batch sweep, train step + inference
+    pooled = pooled_sweep(torch, deer_b200, DEERDataParallelTrainer, dev) if (world == 1 and not args.no_pooled) else None
+
     line = {
         "metric": "deer_train_step_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": world,
         "steps": K, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -313,6 +318,8 @@ def main():
         "roofline": roof,
         "peaks": pk,
     }
+    if pooled is not None:
+        line["pooled_model_sweep"] = pooled
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import torch_baseline as TB
         sb = 32
@@ -326,6 +333,29 @@ def main():
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def pooled_sweep(torch, deer_b200, Trainer, dev, batches=(64, 1024, 16384, 65536)):
+    """Pooled-feature model (complete_project.py:462, 3,918,324 parameters): samples/s of the trainer step and of the
+    eval forward per batch size (inputs resident; 5 timed steps each)."""
+    torch.manual_seed(7)
+    model = deer_b200.CompleteDEERModel(deer_b200.ModelConfig()).to(dev).train()
+    tr = Trainer(model, learning_rate=1e-4, weight_decay=1e-5, gradient_clip=1.0)
+    out = []
+    for Bp in batches:
+        g = torch.Generator().manual_seed(Bp)
+        batch = {"audio_features": torch.randn(Bp, 84, generator=g).to(dev),
+                 "video_features": torch.randn(Bp, 256, generator=g).to(dev),
+                 "text_features": torch.randn(Bp, 768, generator=g).to(dev),
+                 "targets": torch.tanh(torch.randn(Bp, 3, generator=g)).to(dev)}
+        model.train()
+        us_t = _time_launches(torch, lambda i: tr.train_step(batch), 5, warm=2)
+        model.eval()
+        with torch.no_grad():
+            us_i = _time_launches(torch, lambda i: model(batch), 5, warm=2)
+        out.append({"batch": Bp, "train_samples_per_s": Bp / (us_t * 1e-6), "train_ms": us_t / 1e3,
+                    "infer_samples_per_s": Bp / (us_i * 1e-6), "infer_ms": us_i / 1e3})
+    return out
 
 
 def _time_launches(torch, fn, n, warm=5):
