@@ -1,7 +1,7 @@
 """Flat module name imported by run_multimodal_deer.py:80.  The driver calls
 `evaluate_deer_model(model, test_loaders, device=, save_predictions=True, save_dir=)` (:532-538) and json.dumps the
 result; the reference's own signature differs (evaluation.py:785).  Forward passes run on the
-CUDA path; the statistics are host NumPy (out of the hot path)."""
+CUDA path; the statistics are device-side reductions (deer_b200.metrics)."""
 import os
 
 import numpy as np
@@ -29,11 +29,11 @@ def collect_predictions(model, loaders, device):
             (a, v, t), y = _unpack(batch, device)
             out = model(a, v, t)
             p, u = model.get_predictions_and_uncertainties(out)
-            P.append(p.float().cpu().numpy())
-            U.append(u.float().cpu().numpy())
-            Y.append(y.float().cpu().numpy())
+            P.append(p.float())
+            U.append(u.float())
+            Y.append(y.to(device, dtype=torch.float32, non_blocking=True))
     model.train(was_training)
-    return np.concatenate(P), np.concatenate(U), np.concatenate(Y)
+    return torch.cat(P), torch.cat(U), torch.cat(Y)  # stay on the device: the metric reductions are kernels
 
 
 def evaluate_deer_model(model, dataloader, device=None, config=None, save_predictions: bool = False, save_dir=None):
@@ -43,5 +43,6 @@ def evaluate_deer_model(model, dataloader, device=None, config=None, save_predic
     results["n_samples"] = int(preds.shape[0])
     if save_predictions and save_dir:
         os.makedirs(save_dir, exist_ok=True)
-        np.savez(os.path.join(save_dir, "predictions.npz"), predictions=preds, uncertainties=uncs, targets=tgts)
+        np.savez(os.path.join(save_dir, "predictions.npz"), predictions=preds.cpu().numpy(),
+                 uncertainties=uncs.cpu().numpy(), targets=tgts.cpu().numpy())
     return results

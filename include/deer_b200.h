@@ -236,6 +236,37 @@ int deer_coldiv_bwd(const float* dy, const float* x, const float* t, float* dx, 
 int deer_softmax_rows_fwd(const float* x, float* y, long long M, int N, void* stream);
 int deer_softmax_rows_bwd(const float* dy, const float* y, float* dx, long long M, int N, void* stream);
 
+/* ---- text-side integer features: EnhancedTextEncoder.extract_linguistic_features (encoders.py:648-699).
+ *      input_ids / attention_mask [B,T] int64 (a token is valid when its mask is non-zero), features [B,10] fp32:
+ *      {n/max_length, unique/n, n/(max id + 1), max multiplicity, frac ids in [999,1030], frac ids in [100,999], 0,0,0,0};
+ *      all-zero row for a sample with no valid token.  Replaces the reference's O(B) Python loop; bit-exact. T <= 1024. */
+int deer_linguistic_features(const long long* input_ids, const long long* attention_mask, float* features, int B, int T,
+                             int max_length, void* stream);
+
+/* ---- validation metrics (src/utils/metrics.py), device-side reductions
+ *      moments[d][8] (fp64, zeroed by the call) = {n, sum t, sum p, sum t^2, sum p^2, sum t*p, sum |t-p|, sum (t-p)^2}
+ *      over the rows where neither value is NaN; CCC (:59-103), MAE (:105-114), RMSE (:116-125) and Cohen's d
+ *      (:190-211) are closed forms of these. pred/target contiguous [N,D], D in {1,2,3,4,6,8}. */
+#define DEER_METRICS_NMOM 8
+int deer_metrics_moments(const float* pred, const float* target, long long N, int D, double* moments, void* stream);
+/*      uncertainty_calibration_error (:214-279) in three device stages; the host only turns 2*(n_bins+1) order
+ *      statistics into quantile edges (numpy's linear interpolation) and the bin sums into the final scalar.
+ *      prepare: err_mean[b] = mean_d |pred-target|, keys[b] = order-preserving code of mean_d uncert (0xffffffff for a
+ *               dropped sample: NaN error, NaN/inf uncertainty, :245), *n_valid = kept samples (zeroed by the call)
+ *      select : values[r] = the ranks_host[r]-th smallest kept uncertainty mean (0-based, exact; 8-bit radix select,
+ *               4 passes over `keys`); ranks_host is a HOST array, R <= DEER_UCE_MAX_RANKS
+ *      bins   : bin_sums[3][n_bins] (fp64, zeroed by the call) = {count, sum (1-u), sum (1-err)} over edges[j] <= u <
+ *               edges[j+1]; edges is a DEVICE array of n_bins+1 fp64 */
+#define DEER_UCE_MAX_RANKS 24
+#define DEER_UCE_MAX_BINS 64
+#define DEER_UCE_WORKSPACE_BYTES 65536
+int deer_uce_prepare(const float* pred, const float* target, const float* uncert, long long N, int D, float* err_mean,
+                     unsigned* keys, unsigned long long* n_valid, void* stream);
+int deer_uce_select(const unsigned* keys, long long N, const long long* ranks_host, int R, float* values,
+                    void* workspace, long long workspace_bytes, void* stream);
+int deer_uce_bins(const unsigned* keys, const float* err_mean, long long N, int n_bins, const double* edges,
+                  double* bin_sums, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

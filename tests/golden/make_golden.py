@@ -290,8 +290,72 @@ def make_ling(R, B, T, seed, name):
     save(name, {}, {"ids": ids, "mask": mask, "feats": feats}, {"B": B, "T": T, "seed": seed})
 
 
+def make_ling_wide(R, B, T, seed, name):
+    """Realistic vocabulary range (BERT ids up to 30521), repeated tokens, punctuation / special ranges, an all-masked row,
+    a mask with holes (not only a prefix)."""
+    enc = R.encoders.EnhancedTextEncoder({"hidden_dim": 64, "dropout": 0.0})
+    g = torch.Generator().manual_seed(seed)
+    ids = torch.randint(0, 30522, (B, T), generator=g)
+    small = torch.randint(95, 1040, (B, T), generator=g)
+    pick = torch.rand((B, T), generator=g) < 0.5
+    ids = torch.where(pick, small, ids)
+    rep = torch.rand((B, T), generator=g) < 0.3
+    ids = torch.where(rep, ids[:, :1].expand(B, T), ids)
+    lens = torch.randint(0, T + 1, (B,), generator=g)
+    lens[0] = T
+    lens[1] = 0
+    lens[2] = 1
+    mask = (torch.arange(T)[None, :] < lens[:, None]).long()
+    holes = torch.rand((B, T), generator=g) < 0.2
+    mask[B // 2:] = mask[B // 2:] * (~holes[B // 2:]).long()
+    feats = enc.extract_linguistic_features(ids, mask)
+    save(name, {}, {"ids": ids, "mask": mask, "feats": feats}, {"B": B, "T": T, "seed": seed})
+
+
+def make_metrics(N, D, seed, name, nan_frac=0.0):
+    """src/utils/metrics.py run unmodified on float32 arrays (what evaluation.py hands it after .cpu().numpy())."""
+    sys.path[:0] = [f"{REF}/src/utils"]
+    import metrics as M
+    rng = np.random.default_rng(seed)
+    tgt = np.tanh(rng.standard_normal((N, D))).astype(np.float32)
+    pred = (0.7 * tgt + 0.3 * rng.standard_normal((N, D)) + 0.05).astype(np.float32)
+    unc = np.abs(0.4 * rng.standard_normal((N, D)) + 0.3).astype(np.float32)
+    if nan_frac > 0:
+        pred[rng.random((N, D)) < nan_frac] = np.nan
+        unc[rng.random((N, D)) < nan_frac] = np.inf
+        unc[rng.random((N, D)) < nan_frac] = np.nan
+        # ties in the uncertainties, so quantile edges land exactly on sample values
+        unc[: N // 4] = np.round(unc[: N // 4], 1)
+    dm = M.DEERMetrics()
+    arr = {"pred": pred, "tgt": tgt, "unc": unc}
+    arr["ccc"] = np.array([dm.concordance_correlation_coefficient(tgt[:, i], pred[:, i]) for i in range(D)])
+    arr["mae"] = np.array([dm.mean_absolute_error(tgt[:, i], pred[:, i]) for i in range(D)])
+    arr["rmse"] = np.array([dm.root_mean_squared_error(tgt[:, i], pred[:, i]) for i in range(D)])
+    with np.errstate(all="ignore"):
+        arr["uce"] = np.array(M.uncertainty_calibration_error(pred, tgt, unc))
+        arr["uce5"] = np.array(M.uncertainty_calibration_error(pred, tgt, unc, n_bins=5))
+    if nan_frac == 0 and D == 3:
+        ev = dm.evaluate_predictions(pred, tgt, unc)
+        arr["ev_ccc"] = np.array([ev.ccc_valence, ev.ccc_arousal, ev.ccc_dominance])
+        arr["ev_mae"] = np.array([ev.mae_valence, ev.mae_arousal, ev.mae_dominance])
+        arr["ev_ece"] = np.array(ev.ece)
+        arr["ev_cohens_d"] = np.array([ev.statistical_significance[f"cohens_d_{d}"]
+                                       for d in ("valence", "arousal", "dominance")])
+    save(name, {}, arr, {"N": N, "D": D, "seed": seed})
+
+
 def main():
     torch.set_num_threads(8)
+    only = set(sys.argv[1:])
+    if only & {"metrics", "ling_wide"} or "new" in only:
+        R = import_reference()
+        make_ling_wide(R, 32, 64, 21, "ling_b32")
+        make_metrics(1000, 3, 31, "metrics_n1000")
+        make_metrics(37, 3, 32, "metrics_n37")
+        make_metrics(4099, 3, 33, "metrics_nan", nan_frac=0.02)
+        make_metrics(513, 1, 34, "metrics_d1")
+        make_metrics(7, 3, 35, "metrics_tiny")
+        return
     R = import_reference()
     make_audio(R, 64, 3, 7, 1, "audio_small", True)
     make_audio(R, 512, 2, 12, 2, "audio_full_t12", False)

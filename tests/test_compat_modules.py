@@ -50,13 +50,20 @@ def test_flat_module_names_resolve(compat_path):
             assert hasattr(m, n), (mod, n)
 
 
-def test_host_metrics_and_loaders(compat_path):
+@pytest.mark.gpu
+def test_compat_metrics_take_numpy(compat_path):
+    """`from metrics import DEERMetrics` (run_multimodal_deer.py:81): NumPy in, device-side reductions."""
     metrics = importlib.import_module("metrics")
     m = metrics.DEERMetrics()
     x = np.linspace(-1, 1, 50)
-    assert abs(m.concordance_correlation_coefficient(x, x) - 1.0) < 1e-12
-    assert abs(m.concordance_correlation_coefficient(x, -x) + 1.0) < 1e-12
+    assert abs(m.concordance_correlation_coefficient(x, x) - 1.0) < 1e-6
+    assert abs(m.concordance_correlation_coefficient(x, -x) + 1.0) < 1e-6
     assert m.concordance_correlation_coefficient(x, x + 0.5) < 1.0
+    r = m.evaluate_predictions(np.stack([x, x, x], 1), np.stack([x, -x, x + 0.5], 1), np.abs(np.stack([x, x, x], 1)))
+    assert abs(r.ccc_valence - 1.0) < 1e-6 and abs(r.ccc_arousal + 1.0) < 1e-6 and 0 <= r.ece <= 2
+
+
+def test_host_loaders(compat_path):
     pre = importlib.import_module("preprocessing")
     tr, va, te = pre.create_enhanced_dataloaders(config={"model": {"audio_dim": 84, "video_dim": 256, "text_dim": 768}},
                                                  batch_size=8)

@@ -69,6 +69,11 @@ _PROTOS = {
     "deer_coldiv_bwd": [P, P, P, P, P, L, I, P],
     "deer_softmax_rows_fwd": [P, P, L, I, P],
     "deer_softmax_rows_bwd": [P, P, P, L, I, P],
+    "deer_linguistic_features": [P, P, P, I, I, I, P],
+    "deer_metrics_moments": [P, P, L, I, P, P],
+    "deer_uce_prepare": [P, P, P, L, I, P, P, P, P],
+    "deer_uce_select": [P, L, P, I, P, P, L, P],
+    "deer_uce_bins": [P, P, L, I, P, P, P],
 }
 _RESTYPES = {"deer_last_error": ctypes.c_char_p, "deer_launch_count": L}
 

@@ -21,56 +21,73 @@ namespace deer {
 constexpr int NSTAT = DEER_LOSS_NSTAT;  // 0 nll,1 reg,2 kl_alpha,3 kl_beta,4 sum u, 5..14 cnt, 15..24 conf, 25..34 err
 constexpr int LOSS_THREADS = 192;       // multiple of every supported D (1,2,3,4,6,8)
 constexpr int NBINS = 10;
+constexpr long long DEER_NIG_MAX_ELEMENTS = (1ll << 31) - (1ll << 24);  // 32-bit element indices + unroll slack
+constexpr long long DEER_NIG_L2_KEEP_BYTES = 72ll << 20;  // operand footprint up to which pass 1 pins its loads in L2
 
 struct Nig {
   float gamma, nu, alpha, beta;
   float sn, sa, sb;  // softplus'(raw) of nu / alpha / beta (chain rule back to the evidence)
 };
 
-// The loss kernels are instruction-bound unless the transcendentals stay on the MUFU pipe: ex2/lg2/rcp based
-// versions (relative error ~1e-6, far inside the 1e-3 gate) replace libm's expf/log1pf/lgammaf/digamma loops.
+// The loss kernels are instruction-issue bound (ncu: 70 % issue-active at 47 % occupancy), so the transcendentals are
+// single MUFU instructions with flush-to-zero semantics (no denormal pre/post-scaling around ex2/lg2/rcp) and every
+// data-dependent branch is a select; relative error ~1e-6, far inside the 1e-3 gate.
+__device__ __forceinline__ float fex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float flg2(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float frcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fexp(float x) { return fex2(x * 1.4426950408889634f); }
+__device__ __forceinline__ float flog(float x) { return flg2(x) * 0.6931471805599453f; }
 // softplus(x) (torch: beta=1, threshold=20) and its derivative sigmoid(x) from ONE exponential e = exp(-|x|):
 //   softplus = max(x,0) + log1p(e),  log1p(e) = log(u) * e / (u - 1) with u = 1 + e (exact to rounding for tiny e)
 __device__ __forceinline__ void softplus_fast(float x, float& sp, float& sg) {
-  if (x > 20.f) {
-    sp = x;
-    sg = 1.f;
-    return;
-  }
-  const float e = __expf(-fabsf(x));
+  const float e = fexp(-fabsf(x));
   const float u = 1.f + e;
-  const float l = (u == 1.f) ? e : __logf(u) * __fdividef(e, u - 1.f);
-  const float r = __fdividef(1.f, u);
-  sp = fmaxf(x, 0.f) + l;
-  sg = x >= 0.f ? r : e * r;
+  const float l = (u == 1.f) ? e : flog(u) * (e * frcp(u - 1.f));
+  const float r = frcp(u);
+  const bool lin = x > 20.f;
+  sp = lin ? x : fmaxf(x, 0.f) + l;
+  sg = lin ? 1.f : (x >= 0.f ? r : e * r);
 }
-// lgamma(a), a >= 1: shift a by 7 with one product, then Stirling (|err| < 3e-6 absolute for a in [1, 1e5])
+__device__ __forceinline__ float softplus_only(float x) {
+  const float e = fexp(-fabsf(x));
+  const float u = 1.f + e;
+  const float l = (u == 1.f) ? e : flog(u) * (e * frcp(u - 1.f));
+  return x > 20.f ? x : fmaxf(x, 0.f) + l;
+}
+// lgamma(a), a >= 1: shift a < 5 by 4 with one product, then Stirling through a^-7 (truncation < 5e-10 at a = 5;
+// fp32 rounding of (a-1/2) ln a dominates: < 1e-6 absolute for a in [1, 1e5])
 __device__ __forceinline__ float lgamma_ge1_fast(float a) {
-  float lp = 0.f;
-  if (a < 8.f) {
-    lp = __logf(a * (a + 1.f) * (a + 2.f) * (a + 3.f) * (a + 4.f) * (a + 5.f) * (a + 6.f));
-    a += 7.f;
-  }
-  const float r = __fdividef(1.f, a), r2 = r * r;
-  const float s = r * (0.0833333333f - r2 * (0.00277777778f - r2 * 0.000793650794f));
-  return (a - 0.5f) * __logf(a) - a + 0.918938533f + s - lp;
+  const bool sh = a < 5.f;
+  const float as = sh ? a : 1.f;
+  const float lp = sh ? flog(as * (as + 1.f) * ((as + 2.f) * (as + 3.f))) : 0.f;
+  a = sh ? a + 4.f : a;
+  const float r = frcp(a), r2 = r * r;
+  const float s = r * (0.0833333333f - r2 * (0.00277777778f - r2 * (0.000793650794f - r2 * 0.000595238095f)));
+  return (a - 0.5f) * flog(a) - a + 0.918938533f + s - lp;
 }
-// digamma(x), x >= 1: psi(x) = psi(x+6) - sum_{i<6} 1/(x+i), the sum as ONE quotient p'(x)/p(x)
+// digamma(x), x >= 1: psi(x) = psi(x+4) - sum_{i<4} 1/(x+i), the sum as ONE quotient p'(x)/p(x); series through x^-8
 __device__ __forceinline__ float digamma_ge1_fast(float x) {
-  float corr = 0.f;
-  if (x < 8.f) {
-    float sm = 0.f, pr = 1.f;
-#pragma unroll
-    for (int i = 0; i < 6; i++) {
-      const float t = x + (float)i;
-      sm = fmaf(sm, t, pr);
-      pr *= t;
-    }
-    corr = __fdividef(sm, pr);
-    x += 6.f;
-  }
-  const float r = __fdividef(1.f, x), r2 = r * r;
-  return __logf(x) - 0.5f * r - r2 * (0.0833333333f - r2 * (0.00833333333f - r2 * 0.00396825397f)) - corr;
+  const bool sh = x < 5.f;
+  const float t0 = sh ? x : 1.f, t1 = t0 + 1.f, t2 = t0 + 2.f, t3 = t0 + 3.f;
+  const float p01 = t0 * t1, p23 = t2 * t3;
+  // d/dx [t0 t1 t2 t3] = (t0 + t1) p23 + (t2 + t3) p01
+  const float corr = sh ? ((t0 + t1) * p23 + (t2 + t3) * p01) * frcp(p01 * p23) : 0.f;
+  x = sh ? x + 4.f : x;
+  const float r = frcp(x), r2 = r * r;
+  return flog(x) - 0.5f * r -
+         r2 * (0.0833333333f - r2 * (0.00833333333f - r2 * (0.00396825397f - r2 * 0.00416666667f))) - corr;
 }
 
 // raw operands of one (sample, dim) element; fetched for several elements before any of them is processed so that
@@ -79,14 +96,42 @@ struct RawNig {
   float4 v;  // evidence, or (gamma, nu, alpha, beta)
   float y;
 };
+// L2 residency control.  The loss is two passes over the same 20 B per element; when the operands fit in L2 the first
+// pass loads them with an evict_last policy so that the second pass (streaming loads, which demote the lines again) is
+// served from L2 and HBM sees each operand once.
+__device__ __forceinline__ unsigned long long l2_evict_last_policy() {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ float4 ld_keep_f4(const float4* p, unsigned long long pol) {
+  float4 v;
+  asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ float ld_keep_f(const float* p, unsigned long long pol) {
+  float v;
+  asm volatile("ld.global.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+  return v;
+}
+template <bool KEEP>
 __device__ __forceinline__ RawNig fetch_nig(const float* __restrict__ evidence, const float* __restrict__ gamma,
                                             const float* __restrict__ nu, const float* __restrict__ alpha,
                                             const float* __restrict__ beta, const float* __restrict__ targets,
-                                            long long e, int from_evidence) {
+                                            int e, int from_evidence, unsigned long long pol) {
   RawNig r;
-  if (from_evidence) r.v = __ldcs(reinterpret_cast<const float4*>(evidence) + e);
-  else r.v = make_float4(__ldcs(gamma + e), __ldcs(nu + e), __ldcs(alpha + e), __ldcs(beta + e));
-  r.y = __ldcs(targets + e);
+  if (KEEP) {
+    if (from_evidence) r.v = ld_keep_f4(reinterpret_cast<const float4*>(evidence) + e, pol);
+    else r.v = make_float4(ld_keep_f(gamma + e, pol), ld_keep_f(nu + e, pol), ld_keep_f(alpha + e, pol),
+                           ld_keep_f(beta + e, pol));
+    r.y = ld_keep_f(targets + e, pol);
+  } else {
+    if (from_evidence) r.v = __ldcs(reinterpret_cast<const float4*>(evidence) + e);
+    else r.v = make_float4(__ldcs(gamma + e), __ldcs(nu + e), __ldcs(alpha + e), __ldcs(beta + e));
+    r.y = __ldcs(targets + e);
+  }
   return r;
 }
 __device__ __forceinline__ Nig derive_nig(const RawNig& r, int from_evidence) {
@@ -137,19 +182,23 @@ __device__ __forceinline__ Nig load_nig(const float* __restrict__ evidence, cons
 }
 
 __device__ __forceinline__ int ece_bin(float conf, const float* __restrict__ edges) {
-  // (edges[k], edges[k+1]]  (losses.py:207-215); -1 when outside every bin (NaN / conf<=0)
+  // (edges[k], edges[k+1]]  (losses.py:207-215); -1 when outside every bin (NaN / conf <= 0 / conf > 1)
   // closed-form guess, then at most one step against the exact fp32 edges (torch.linspace(0,1,11), losses.py:207)
-  int k = min(max((int)ceilf(conf * 10.f) - 1, 0), NBINS - 1);
-  if (!(conf > edges[k])) k -= 1;
-  else if (conf > edges[k + 1]) k += 1;
-  if (k < 0 || k >= NBINS || !(conf > edges[k] && conf <= edges[k + 1])) k = -1;
-  return k;
+  int k = min(max(__float2int_ru(conf * 10.f) - 1, 0), NBINS - 1);
+  k += (int)(conf > edges[k + 1]) - (int)!(conf > edges[k]);
+  return (conf > 0.f && conf <= 1.f) ? k : -1;
 }
 
-__global__ void __launch_bounds__(LOSS_THREADS) nig_loss_stats_kernel(
+struct NigPlanes {
+  float* p[7];  // gamma, nu, alpha, beta, aleatoric, epistemic, total: [B*D] each
+};
+
+// element indices are 32-bit inside the kernels (the entry points reject B*D >= 2^31 - grid slack)
+template <bool KEEP>
+__global__ void __launch_bounds__(LOSS_THREADS, 6) nig_loss_stats_kernel(
     const float* __restrict__ evidence, const float* __restrict__ gamma, const float* __restrict__ nu,
     const float* __restrict__ alpha, const float* __restrict__ beta, const float* __restrict__ targets,
-    const float* __restrict__ bin_edges, float* __restrict__ stats, float* __restrict__ nig_out, long long total, int D,
+    const float* __restrict__ bin_edges, float* __restrict__ stats, const NigPlanes planes, int nig_out, int total, int D,
     int from_evidence, float eps) {
   __shared__ float bins[3 * NBINS][LOSS_THREADS];  // private column per thread: conflict-free, no atomics
   __shared__ float sedges[NBINS + 1];
@@ -162,35 +211,28 @@ __global__ void __launch_bounds__(LOSS_THREADS) nig_loss_stats_kernel(
   const float inv_two_pi_eps = (float)(1.0 / (6.283185307179586 + (double)eps));
   const float log1eps = logf(1.f + eps);
   float a_nll = 0.f, a_reg = 0.f, a_kla = 0.f, a_klb = 0.f, a_u = 0.f;
-  const long long stride = (long long)gridDim.x * LOSS_THREADS;  // multiple of D -> dimension fixed per thread
-  for (long long eb = (long long)blockIdx.x * LOSS_THREADS + tid; eb < total; eb += LOSS_UNROLL * stride) {
-    RawNig rr[LOSS_UNROLL];
-#pragma unroll
-    for (int q = 0; q < LOSS_UNROLL; q++) {
-      const long long eq = eb + q * stride;
-      rr[q] = fetch_nig(evidence, gamma, nu, alpha, beta, targets, eq < total ? eq : eb, from_evidence);
-    }
-#pragma unroll
-    for (int q = 0; q < LOSS_UNROLL; q++) {
-    const long long e = eb + q * stride;
-    if (e >= total) break;
-    const Nig p = derive_nig(rr[q], from_evidence);
-    const float y = rr[q].y;
+  const unsigned long long pol = KEEP ? l2_evict_last_policy() : 0ull;
+  const int stride = (int)gridDim.x * LOSS_THREADS;  // multiple of D -> dimension fixed per thread
+  // one element: everything except the shared-memory bin update order is independent across elements, so the
+  // unrolled main loop (no bounds checks, no early exit) lets the compiler interleave LOSS_UNROLL dependency chains
+  auto element = [&](const RawNig& raw, int e) {
+    const Nig p = derive_nig(raw, from_evidence);
+    const float y = raw.y;
     const float err = y - p.gamma;
     const float e2 = err * err;
     const float S = p.beta + 0.5f * p.nu * e2 + eps;
-    const float lb = __logf(p.beta + eps);
-    const float lp = 0.5f * __logf(p.nu * inv_two_pi_eps) + p.alpha * lb - lgamma_ge1_fast(p.alpha + eps) -
-                     (p.alpha + 0.5f) * __logf(S);
+    const float lb = flog(p.beta + eps);
+    const float lp = 0.5f * flog(p.nu * inv_two_pi_eps) + p.alpha * lb - lgamma_ge1_fast(p.alpha + eps) -
+                     (p.alpha + 0.5f) * flog(S);
     a_nll -= lp;
     a_reg += e2 * (2.f * p.beta + p.nu * e2);
     const float am1 = p.alpha - 1.f;
     a_kla += am1 * am1;
     const float dl = lb - log1eps;
     a_klb += dl * dl;
-    const float u = __fdividef(p.beta, am1 + eps);
-    a_u += __fdividef(p.beta, am1 + 1e-8f);
-    const float conf = __fdividef(1.f, 1.f + u);
+    const float u = p.beta * frcp(am1 + eps);
+    a_u += p.beta * frcp(am1 + 1e-8f);
+    const float conf = frcp(1.f + u);
     const int k = ece_bin(conf, sedges);
     if (k >= 0) {
       bins[k][tid] += 1.f;
@@ -198,18 +240,29 @@ __global__ void __launch_bounds__(LOSS_THREADS) nig_loss_stats_kernel(
       bins[2 * NBINS + k][tid] += fabsf(err);
     }
     if (nig_out) {
-      const float alea = __fdividef(p.beta, am1);
-      const float epis = __fdividef(alea, p.nu);
-      __stcs(nig_out + e, p.gamma);
-      __stcs(nig_out + total + e, p.nu);
-      __stcs(nig_out + 2 * total + e, p.alpha);
-      __stcs(nig_out + 3 * total + e, p.beta);
-      __stcs(nig_out + 4 * total + e, alea);
-      __stcs(nig_out + 5 * total + e, epis);
-      __stcs(nig_out + 6 * total + e, alea + epis);
+      const float alea = p.beta * frcp(am1);
+      const float epis = alea * frcp(p.nu);
+      // plane bases live in the constant bank: one IMAD.WIDE per store address
+      __stcs(planes.p[0] + e, p.gamma);
+      __stcs(planes.p[1] + e, p.nu);
+      __stcs(planes.p[2] + e, p.alpha);
+      __stcs(planes.p[3] + e, p.beta);
+      __stcs(planes.p[4] + e, alea);
+      __stcs(planes.p[5] + e, epis);
+      __stcs(planes.p[6] + e, alea + epis);
     }
-    }
+  };
+  int eb = (int)blockIdx.x * LOSS_THREADS + tid;
+  for (; eb + (LOSS_UNROLL - 1) * stride < total; eb += LOSS_UNROLL * stride) {
+    RawNig rr[LOSS_UNROLL];
+#pragma unroll
+    for (int q = 0; q < LOSS_UNROLL; q++)
+      rr[q] = fetch_nig<KEEP>(evidence, gamma, nu, alpha, beta, targets, eb + q * stride, from_evidence, pol);
+#pragma unroll
+    for (int q = 0; q < LOSS_UNROLL; q++) element(rr[q], eb + q * stride);
   }
+  for (; eb < total; eb += stride)
+    element(fetch_nig<KEEP>(evidence, gamma, nu, alpha, beta, targets, eb, from_evidence, pol), eb);
   red[0][tid] = a_nll;
   red[1][tid] = a_reg;
   red[2][tid] = a_kla;
@@ -217,7 +270,7 @@ __global__ void __launch_bounds__(LOSS_THREADS) nig_loss_stats_kernel(
   red[4][tid] = a_u;
   __syncthreads();
   // thread (d, s) for s < 35 sums the columns of threads whose dimension is d (tid % D == d)
-  const int first_e_dim = (int)(((long long)blockIdx.x * LOSS_THREADS) % D);
+  const int first_e_dim = ((int)blockIdx.x * LOSS_THREADS) % D;
   for (int w = tid; w < D * 35; w += LOSS_THREADS) {
     const int d = w / 35, s = w % 35;
     // threads t with (first_e_dim + t) % D == d
@@ -236,11 +289,11 @@ struct DimCoef {
   float w;            // task weight
 };
 
-__global__ void __launch_bounds__(LOSS_THREADS) nig_loss_finish_kernel(
+__global__ void __launch_bounds__(LOSS_THREADS, 6) nig_loss_finish_kernel(
     const float* __restrict__ evidence, const float* __restrict__ gamma, const float* __restrict__ nu,
     const float* __restrict__ alpha, const float* __restrict__ beta, const float* __restrict__ targets,
     const float* __restrict__ bin_edges, const float* __restrict__ stats, const float* __restrict__ task_weights,
-    float reg_w, float kl_w, float ece_w, float cross_w, float eps, long long total_local, long long B_global, int D,
+    float reg_w, float kl_w, float ece_w, float cross_w, float eps, int total_local, long long B_global, int D,
     int from_evidence, float grad_scale, float* __restrict__ losses, float* __restrict__ d_out) {
   __shared__ DimCoef coef[8];
   __shared__ float sedges[NBINS + 1];
@@ -250,27 +303,34 @@ __global__ void __launch_bounds__(LOSS_THREADS) nig_loss_finish_kernel(
   if (tid <= NBINS) sedges[tid] = bin_edges[tid];
   if (tid < D) ubar[tid] = stats[tid * NSTAT + 4] * invN;
   __syncthreads();
-  if (tid < D) {
-    const float* st = stats + tid * NSTAT;
-    float ece = 0.f;
-    for (int k = 0; k < NBINS; k++) {
-      const float cnt = st[5 + k], sc = st[15 + k], se = st[25 + k];
-      float sg = 0.f;
-      if (cnt > 0.f) {
-        const float diff = sc / cnt - (1.f - se / cnt);
-        ece += (cnt * invN) * fabsf(diff);
-        sg = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
-      }
-      coef[tid].sign[k] = sg;
+  __shared__ float ece_part[8][NBINS];
+  if (tid < D * NBINS) {  // one thread per (dimension, bin): no serial chain of dependent global loads and divisions
+    const int dd = tid / NBINS, k = tid % NBINS;
+    const float* st = stats + dd * NSTAT;
+    const float cnt = st[5 + k], sc = st[15 + k], se = st[25 + k];
+    float sg = 0.f, part = 0.f;
+    if (cnt > 0.f) {
+      const float diff = sc / cnt - (1.f - se / cnt);
+      part = (cnt * invN) * fabsf(diff);
+      sg = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
     }
+    coef[dd].sign[k] = sg;
+    ece_part[dd][k] = part;
+  }
+  if (tid < D) {
     float cs = 0.f;
     for (int j = 0; j < D; j++)
       if (j != tid) cs += ubar[tid] - ubar[j];
     const int npairs = D * (D - 1) / 2;
     coef[tid].cross = npairs > 0 ? 2.f * cs / (float)npairs : 0.f;
-    const float w = task_weights ? task_weights[tid] : 1.f;
-    coef[tid].w = w;
-    if (blockIdx.x == 0 && losses) {
+    coef[tid].w = task_weights ? task_weights[tid] : 1.f;
+  }
+  __syncthreads();
+  if (blockIdx.x == 0 && losses) {
+    if (tid < D) {
+      const float* st = stats + tid * NSTAT;
+      float ece = 0.f;
+      for (int k = 0; k < NBINS; k++) ece += ece_part[tid][k];
       const float nll = st[0] * invN, reg = st[1] * invN;
       const float kl = st[2] * invN + 0.1f * st[3] * invN;
       float* L = losses + tid * 5;
@@ -280,49 +340,40 @@ __global__ void __launch_bounds__(LOSS_THREADS) nig_loss_finish_kernel(
       L[3] = kl;
       L[4] = ece;
     }
-  }
-  __syncthreads();
-  if (blockIdx.x == 0 && tid == 0 && losses) {
-    float cd = 0.f;
-    for (int i = 0; i < D; i++)
-      for (int j = i + 1; j < D; j++) cd += (ubar[i] - ubar[j]) * (ubar[i] - ubar[j]);
-    const int npairs = D * (D - 1) / 2;
-    if (npairs > 0) cd /= (float)npairs;
-    float tot = 0.f;
-    for (int i = 0; i < D; i++) tot += coef[i].w * losses[i * 5];
-    if (cross_w > 0.f && D > 1) tot += cross_w * cd;
-    losses[D * 5] = cd;
-    losses[D * 5 + 1] = tot / (float)D;
+    __syncthreads();
+    if (tid == 0) {
+      float cd = 0.f;
+      for (int i = 0; i < D; i++)
+        for (int j = i + 1; j < D; j++) cd += (ubar[i] - ubar[j]) * (ubar[i] - ubar[j]);
+      const int npairs = D * (D - 1) / 2;
+      if (npairs > 0) cd /= (float)npairs;
+      float tot = 0.f;
+      for (int i = 0; i < D; i++) tot += coef[i].w * losses[i * 5];
+      if (cross_w > 0.f && D > 1) tot += cross_w * cd;
+      losses[D * 5] = cd;
+      losses[D * 5 + 1] = tot / (float)D;
+    }
   }
   if (d_out == nullptr) return;
   const float invD = 1.f / (float)D;
   const float base = grad_scale * invD * invN;
   const float log1eps = logf(1.f + eps);
-  const long long stride = (long long)gridDim.x * LOSS_THREADS;  // multiple of D: the dimension is fixed per thread
-  const int d = (int)(((long long)blockIdx.x * LOSS_THREADS + tid) % D);
-  for (long long eb = (long long)blockIdx.x * LOSS_THREADS + tid; eb < total_local; eb += LOSS_UNROLL * stride) {
-    RawNig rr[LOSS_UNROLL];
-#pragma unroll
-    for (int q = 0; q < LOSS_UNROLL; q++) {
-      const long long eq = eb + q * stride;
-      rr[q] = fetch_nig(evidence, gamma, nu, alpha, beta, targets, eq < total_local ? eq : eb, from_evidence);
-    }
-#pragma unroll
-    for (int q = 0; q < LOSS_UNROLL; q++) {
-    const long long e = eb + q * stride;
-    if (e >= total_local) break;
-    const Nig p = derive_nig(rr[q], from_evidence);
-    const float y = rr[q].y;
+  const int stride = (int)gridDim.x * LOSS_THREADS;  // multiple of D: the dimension is fixed per thread
+  const int d = ((int)blockIdx.x * LOSS_THREADS + tid) % D;
+  const float w = coef[d].w;
+  const float cross_c = (cross_w > 0.f && D > 1) ? cross_w * coef[d].cross : 0.f;
+  auto element = [&](const RawNig& raw, int e) {
+    const Nig p = derive_nig(raw, from_evidence);
+    const float y = raw.y;
     const float err = y - p.gamma, e2 = err * err;
     const float S = p.beta + 0.5f * p.nu * e2 + eps;
     const float ah = p.alpha + 0.5f;
     const float be = p.beta + eps;
-    const float w = coef[d].w;
-    const float rS = __fdividef(1.f, S), rbe = __fdividef(1.f, be), lbe = __logf(be);
+    const float rS = frcp(S), rbe = frcp(be), lbe = flog(be);
     // nll
     float dg = -ah * p.nu * err * rS;
-    float dn = __fdividef(-0.5f, p.nu) + ah * e2 * 0.5f * rS;
-    float da = -lbe + digamma_ge1_fast(p.alpha + eps) + __logf(S);
+    float dn = -0.5f * frcp(p.nu) + ah * e2 * 0.5f * rS;
+    float da = -lbe + digamma_ge1_fast(p.alpha + eps) + flog(S);
     float db = -p.alpha * rbe + ah * rS;
     // reg
     dg += reg_w * (-(4.f * p.beta * err + 4.f * p.nu * e2 * err));
@@ -334,9 +385,9 @@ __global__ void __launch_bounds__(LOSS_THREADS) nig_loss_finish_kernel(
     db += kl_w * 0.2f * (lbe - log1eps) * rbe;
     // ece
     const float den = am1 + eps;
-    const float rden = __fdividef(1.f, den);
+    const float rden = frcp(den);
     const float u = p.beta * rden;
-    const float conf = __fdividef(1.f, 1.f + u);
+    const float conf = frcp(1.f + u);
     if (ece_w > 0.f) {
       const int k = ece_bin(conf, sedges);
       if (k >= 0) {
@@ -353,10 +404,9 @@ __global__ void __launch_bounds__(LOSS_THREADS) nig_loss_finish_kernel(
     db *= w;
     // cross-dimension consistency: d/d ubar_d * (1/N) * du/d(alpha,beta), u = beta/(alpha-1+1e-8)
     if (cross_w > 0.f && D > 1) {
-      const float r8 = __fdividef(1.f, am1 + 1e-8f);
-      const float c = cross_w * coef[d].cross;
-      db += c * r8;
-      da += c * (-p.beta * r8 * r8);
+      const float r8 = frcp(am1 + 1e-8f);
+      db += cross_c * r8;
+      da += cross_c * (-p.beta * r8 * r8);
     }
     float4 o;
     if (from_evidence) {
@@ -368,8 +418,18 @@ __global__ void __launch_bounds__(LOSS_THREADS) nig_loss_finish_kernel(
       o = make_float4(base * dg, base * dn, base * da, base * db);
     }
     __stcs(reinterpret_cast<float4*>(d_out) + e, o);
-    }
+  };
+  int eb = (int)blockIdx.x * LOSS_THREADS + tid;
+  for (; eb + (LOSS_UNROLL - 1) * stride < total_local; eb += LOSS_UNROLL * stride) {
+    RawNig rr[LOSS_UNROLL];
+#pragma unroll
+    for (int q = 0; q < LOSS_UNROLL; q++)
+      rr[q] = fetch_nig<false>(evidence, gamma, nu, alpha, beta, targets, eb + q * stride, from_evidence, 0ull);
+#pragma unroll
+    for (int q = 0; q < LOSS_UNROLL; q++) element(rr[q], eb + q * stride);
   }
+  for (; eb < total_local; eb += stride)
+    element(fetch_nig<false>(evidence, gamma, nu, alpha, beta, targets, eb, from_evidence, 0ull), eb);
 }
 
 // ------------------------------------------------------------------ stand-alone head
@@ -482,6 +542,22 @@ __global__ void amini_finish_kernel(const float* scratch, float ew, float kw, lo
   losses[4] = mse;
 }
 
+// grid of the two loss passes: exactly the number of co-resident blocks (one wave; the grid-stride loops cover the
+// rest), never 8 blocks per SM when only 6 fit - the partial second wave ran at a third of the occupancy
+template <typename K>
+static int resident_grid(K kernel, long long n, int threads) {
+  static int per_sm = 0;  // per template instantiation (one kernel each)
+  if (per_sm == 0) {
+    int b = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kernel, threads, 0) != cudaSuccess || b < 1) b = 4;
+    per_sm = b;
+  }
+  long long g = cdiv(n, (long long)threads * LOSS_UNROLL);  // every thread gets a full unrolled trip when it can
+  const long long cap = (long long)kNumSMs * per_sm;
+  if (g > cap) g = cap;
+  return (int)(g < 1 ? 1 : g);
+}
+
 static int stream_grid(long long n, int threads) {
   long long g = cdiv(n, threads);
   const long long cap = (long long)kNumSMs * 8;
@@ -523,8 +599,24 @@ int deer_nig_loss_stats(const float* evidence, const float* gamma, const float* 
     return DEER_ERR_UNSUPPORTED;
   }
   const long long total = B * D;
-  DEER_LAUNCH(nig_loss_stats_kernel, stream_grid(total, LOSS_THREADS), LOSS_THREADS, 0, stream, evidence, gamma, nu,
-              alpha, beta, targets, bin_edges, stats, nig_out, total, D, from_evidence, eps);
+  if (total > DEER_NIG_MAX_ELEMENTS) {
+    set_error("nig_loss_stats: B*D=%lld exceeds %lld", total, (long long)DEER_NIG_MAX_ELEMENTS);
+    return DEER_ERR_UNSUPPORTED;
+  }
+  NigPlanes planes;
+  for (int i = 0; i < 7; i++) planes.p[i] = nig_out ? nig_out + (long long)i * total : nullptr;
+  const int has_out = nig_out != nullptr;
+  // operands (20 B per element) small enough to stay in the 126 MB L2 between the two passes?
+  const bool keep = total * 20 <= (long long)DEER_NIG_L2_KEEP_BYTES;
+  if (keep) {
+    DEER_LAUNCH(nig_loss_stats_kernel<true>, resident_grid(nig_loss_stats_kernel<true>, total, LOSS_THREADS),
+                LOSS_THREADS, 0, stream, evidence, gamma, nu, alpha, beta, targets, bin_edges, stats, planes, has_out,
+                (int)total, D, from_evidence, eps);
+  } else {
+    DEER_LAUNCH(nig_loss_stats_kernel<false>, resident_grid(nig_loss_stats_kernel<false>, total, LOSS_THREADS),
+                LOSS_THREADS, 0, stream, evidence, gamma, nu, alpha, beta, targets, bin_edges, stats, planes, has_out,
+                (int)total, D, from_evidence, eps);
+  }
   return DEER_OK;
 }
 
@@ -541,8 +633,13 @@ int deer_nig_loss_finish(const float* evidence, const float* gamma, const float*
     return DEER_ERR_UNSUPPORTED;
   }
   const long long total = B_local * D;
-  DEER_LAUNCH(nig_loss_finish_kernel, stream_grid(total, LOSS_THREADS), LOSS_THREADS, 0, stream, evidence, gamma, nu, alpha, beta,
-              targets, bin_edges, stats, task_weights, reg_w, kl_w, ece_w, cross_w, eps, total, B_global, D,
+  if (total > DEER_NIG_MAX_ELEMENTS) {
+    set_error("nig_loss_finish: B*D=%lld exceeds %lld", total, (long long)DEER_NIG_MAX_ELEMENTS);
+    return DEER_ERR_UNSUPPORTED;
+  }
+  DEER_LAUNCH(nig_loss_finish_kernel, resident_grid(nig_loss_finish_kernel, total, LOSS_THREADS), LOSS_THREADS, 0,
+              stream, evidence, gamma, nu, alpha, beta,
+              targets, bin_edges, stats, task_weights, reg_w, kl_w, ece_w, cross_w, eps, (int)total, B_global, D,
               from_evidence, grad_scale, losses, d_out);
   return DEER_OK;
 }

@@ -156,10 +156,17 @@ class EnhancedTextEncoder(nn.Module):
         self.output_projection = nn.Sequential(nn.Linear(d + d // 4, d), nn.ReLU(), nn.Dropout(self.dropout),
                                                nn.LayerNorm(d))
 
+    def extract_linguistic_features(self, input_ids: torch.Tensor, attention_mask: torch.Tensor) -> torch.Tensor:
+        """encoders.py:648-699: [B,T] int64 token ids -> [B,10] integer statistics, one kernel instead of a Python loop
+        over the batch with device syncs."""
+        return ops.linguistic_features(input_ids, attention_mask, self.max_length)
+
     def forward(self, token_embeddings: torch.Tensor, attention_mask: Optional[torch.Tensor] = None,
-                linguistic_features: Optional[torch.Tensor] = None) -> torch.Tensor:
+                linguistic_features: Optional[torch.Tensor] = None,
+                input_ids: Optional[torch.Tensor] = None) -> torch.Tensor:
         """token_embeddings [B,T,768] (what BERT's last_hidden_state would be), attention_mask [B,T] 0/1,
-        linguistic_features [B,10] (encoders.py:648-699; zeros when omitted)."""
+        linguistic_features [B,10] (encoders.py:648-699): given, or computed on the device from `input_ids` [B,T]
+        int64, or zeros when both are omitted."""
         if not torch.is_floating_point(token_embeddings):
             raise NotImplementedError("deer_b200: BERT / token-id embedding is outside the CUDA hot path; pass 768-D token "
                                       "embeddings [B,T,768]")
@@ -168,6 +175,8 @@ class EnhancedTextEncoder(nn.Module):
         if attention_mask is None:
             attention_mask = torch.ones((B, T), device=dev, dtype=torch.float32)
         m = attention_mask.to(torch.float32)
+        if linguistic_features is None and input_ids is not None:
+            linguistic_features = self.extract_linguistic_features(input_ids, attention_mask)
         if linguistic_features is None:
             linguistic_features = torch.zeros((B, 10), device=dev, dtype=torch.float32)
         x = ops.rowscale(token_embeddings, m)

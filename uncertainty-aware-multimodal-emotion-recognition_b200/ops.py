@@ -364,6 +364,26 @@ def rowscale(x, mask):
     return _RowScale.apply(x, mask)
 
 
+def linguistic_features(input_ids: torch.Tensor, attention_mask: torch.Tensor, max_length: int = 128) -> torch.Tensor:
+    """EnhancedTextEncoder.extract_linguistic_features (encoders.py:648-699) as one integer kernel: [B,T] int64 token
+    ids + mask -> [B,10] fp32 (no gradient path, as in the reference)."""
+    if not (input_ids.is_cuda and attention_mask.is_cuda):
+        raise _lib.DeerError("deer_b200: `input_ids` / `attention_mask` must be CUDA tensors (no CPU fallback)")
+    if input_ids.dtype != torch.int64:
+        raise _lib.DeerError(f"deer_b200: `input_ids` must be int64, got {input_ids.dtype}")
+    if input_ids.shape != attention_mask.shape or input_ids.dim() != 2:
+        raise _lib.DeerError("deer_b200: `input_ids` and `attention_mask` must both be [B,T]")
+    ids = input_ids.contiguous()
+    m = attention_mask.contiguous()
+    if m.dtype != torch.int64:
+        m = (m != 0).to(torch.int64)
+    B, T = ids.shape
+    out = torch.empty((B, 10), device=ids.device, dtype=torch.float32)
+    if B > 0:
+        call("deer_linguistic_features", ids.data_ptr(), m.data_ptr(), ptr(out), B, T, int(max_length))
+    return out
+
+
 class _PermuteBT(torch.autograd.Function):
     """[B,T,D] contiguous -> [T,B,D] contiguous."""
 
