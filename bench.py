@@ -196,14 +196,23 @@ def main():
     NB = 4  # rotating resident batches: 4 x 89 MB > 126 MB L2
     batches = [synth_batch(TRAIN_B, dev, gen) for _ in range(NB)]
 
+    use_graph = not args.no_graph
+    # launches of one step, counted on an eager step (a graph replay issues the same kernels with one host call)
+    trainer.train_step(batches[0])
+    l0 = _lib.launch_count()
+    trainer.train_step(batches[0])
+    launches_per_step = _lib.launch_count() - l0
+    # the whole step (fwd + loss + bwd + all-reduce + clip + AdamW) captured once per resident batch and replayed
+    replays = [trainer.capture(b) for b in batches] if use_graph else None
+
     def train_fn(i):
-        trainer.train_step(batches[i % NB])
+        if use_graph:
+            replays[i % NB]()
+        else:
+            trainer.train_step(batches[i % NB])
 
     for i in range(W):
         train_fn(i)
-    l0 = _lib.launch_count()
-    train_fn(0)
-    launches_per_step = _lib.launch_count() - l0
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -236,11 +245,13 @@ def main():
     loss_done = [torch.cuda.Event() for _ in range(2)]
     loss_log = []
 
+    e2e_replays = [trainer.capture(b) for b in dev_bufs] if use_graph else None
+
     def e2e_fn(i):
         j = i % 2
         stage(i + 1)                                     # prefetch the next step's batch
         torch.cuda.current_stream().wait_event(ready[j])
-        losses = trainer.train_step(dev_bufs[j])
+        losses = e2e_replays[j]() if use_graph else trainer.train_step(dev_bufs[j])
         consumed[j].record()
         # D2H read of the step's loss: asynchronous copy into pinned memory every step; the host consumes the value
         # one step later (after its event), so kernel launches of step i+1 are never held back by a device sync
@@ -270,17 +281,28 @@ def main():
     model.eval()
     ibatches = [synth_batch(INFER_B, dev, gen) for _ in range(2)]
 
-    def infer_fn(i):
+    def infer_eager(i):
         b = ibatches[i % 2]
         with torch.no_grad():
             model(b["audio_features"], b["video_features"], b["text_features"], b["attention_mask"],
                   b["linguistic_features"])
 
     for i in range(2):
-        infer_fn(i)
+        infer_eager(i)
     l0 = _lib.launch_count()
-    infer_fn(0)
+    infer_eager(0)
     infer_launches = _lib.launch_count() - l0
+    if use_graph:
+        from deer_b200.trainer import capture_forward
+        ireplays = [capture_forward(model, b["audio_features"], b["video_features"], b["text_features"],
+                                    b["attention_mask"], b["linguistic_features"])[0] for b in ibatches]
+
+    def infer_fn(i):
+        if use_graph:
+            ireplays[i % 2]()
+        else:
+            infer_eager(i)
+
     infer_ms = timed(infer_fn, max(3, K // 2)) / max(3, K // 2)
     infer_value = INFER_B * world / (infer_ms / 1e3)
     model.train()
@@ -292,7 +314,8 @@ def main():
 
     # ------------------------------------------------------------------ BASELINE configs[4]: pooled CompleteDEERModel on
     # multi-dataset-shaped batches (84/256/768-D vectors + targets[3] + dataset_id), batch sweep, train step + inference
-    pooled = pooled_sweep(torch, deer_b200, DEERDataParallelTrainer, dev) if (world == 1 and not args.no_pooled) else None
+    pooled = (pooled_sweep(torch, deer_b200, DEERDataParallelTrainer, dev, use_graph)
+              if (world == 1 and not args.no_pooled) else None)
 
     line = {
         "metric": "deer_train_step_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": world,
@@ -308,6 +331,7 @@ def main():
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4},
+        "cuda_graph": use_graph,
         "gpu_launches": int(launches_per_step * K),
         "launches_per_step": int(launches_per_step),
         "inference": {"value": infer_value, "unit": "samples/s", "batch_per_gpu": INFER_B, "ms_per_step": infer_ms,
@@ -335,7 +359,7 @@ def main():
         dist.destroy_process_group()
 
 
-def pooled_sweep(torch, deer_b200, Trainer, dev, batches=(64, 1024, 16384, 65536)):
+def pooled_sweep(torch, deer_b200, Trainer, dev, use_graph=True, batches=(64, 1024, 16384, 65536)):
     """Pooled-feature model (complete_project.py:462, 3,918,324 parameters): samples/s of the trainer step and of the
     eval forward per batch size (inputs resident; 5 timed steps each)."""
     torch.manual_seed(7)
@@ -349,10 +373,16 @@ def pooled_sweep(torch, deer_b200, Trainer, dev, batches=(64, 1024, 16384, 65536
                  "text_features": torch.randn(Bp, 768, generator=g).to(dev),
                  "targets": torch.tanh(torch.randn(Bp, 3, generator=g)).to(dev)}
         model.train()
-        us_t = _time_launches(torch, lambda i: tr.train_step(batch), 5, warm=2)
+        step = tr.capture(batch) if use_graph else (lambda: tr.train_step(batch))
+        us_t = _time_launches(torch, lambda i: step(), 10, warm=2)
         model.eval()
+        if use_graph:
+            from deer_b200.trainer import capture_forward
+            fwd = capture_forward(model, batch)[0]
+        else:
+            fwd = lambda: model(batch)  # noqa: E731
         with torch.no_grad():
-            us_i = _time_launches(torch, lambda i: model(batch), 5, warm=2)
+            us_i = _time_launches(torch, lambda i: fwd(), 10, warm=2)
         out.append({"batch": Bp, "train_samples_per_s": Bp / (us_t * 1e-6), "train_ms": us_t / 1e3,
                     "infer_samples_per_s": Bp / (us_i * 1e-6), "infer_ms": us_i / 1e3})
     return out

@@ -211,9 +211,12 @@ int deer_amini_loss(const float* mu, const float* nu, const float* alpha, const 
 /* ---- trainer step (training.py:121-150,219,224): global grad norm, clip, AdamW over flat buffers */
 int deer_sumsq(const float* x, long long n, float* out /* accumulates */, void* stream);
 /*      clip coefficient = min(1, max_norm / (sqrt(*sumsq * inv_world^2...) + 1e-6)) computed on device from *sumsq */
+/*      step_dev (device int64, may be NULL): when given the update uses step = *step_dev + 1 and `step` is ignored;
+ *      lr_dev (device float, may be NULL): when given the learning rate is lr * *lr_dev.  Both exist so that a
+ *      CUDA-graph capture of the training step stays valid across steps and LR-schedule changes. */
 int deer_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                float eps, float weight_decay, int step, const float* sumsq, float max_norm, float grad_scale,
-               void* stream);
+               const long long* step_dev, const float* lr_dev, void* stream);
 
 /* ---- generic elementwise helpers used by the pooled model (complete_project.py:282-293,364,439-459) */
 /* y = a*x1 + b*x2 (x2 may be NULL) */

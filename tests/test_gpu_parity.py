@@ -452,3 +452,71 @@ def test_gemm_h16(M, N, K, ta, tb, a_bf, b_bf):
     x16 = ops.cast16(cu(x))
     assert x16.shape == (37, 88) and float(x16[:, 84:].abs().max()) == 0.0
     assert torch.equal(x16[:, :84].cpu(), x.to(torch.float16))
+
+
+@pytest.mark.gpu
+def test_graph_replay_matches_eager_training():
+    """CUDA-graph replay of the whole trainer step (fwd + loss + bwd + clip + AdamW) follows the eager step on changing
+    data (dropout 0 so neither draws masks).  Float atomics in the gradient reductions make two runs differ in the
+    last bits and early Adam steps (update ~ lr * sign(g)) amplify that, hence the loose per-step tolerance; the
+    device-side step counter / learning rate are checked exactly in test_adamw_device_step_and_lr."""
+    import copy
+    import deer_b200
+    from deer_b200.trainer import DEERDataParallelTrainer
+    torch.manual_seed(3)
+    base = deer_b200.CompleteDEERModel(deer_b200.ModelConfig(dropout=0.0)).cuda().train()
+    m1, m2 = copy.deepcopy(base), copy.deepcopy(base)
+    t1 = DEERDataParallelTrainer(m1, learning_rate=1e-3)
+    t2 = DEERDataParallelTrainer(m2, learning_rate=1e-3)
+    g = torch.Generator().manual_seed(0)
+
+    def batch():
+        return {"audio_features": torch.randn(32, 84, generator=g).cuda(),
+                "video_features": torch.randn(32, 256, generator=g).cuda(),
+                "text_features": torch.randn(32, 768, generator=g).cuda(),
+                "targets": torch.tanh(torch.randn(32, 3, generator=g)).cuda()}
+
+    data = [batch() for _ in range(7)]
+    for i, b in enumerate(data):
+        if i == 4:
+            t1.lr = 5e-4
+            t2.lr = 5e-4
+        l1 = t1.train_step(b).clone()
+        l2 = t2.train_step_auto(b).clone()       # eager, eager, then captured + replayed
+        assert torch.allclose(l1, l2, rtol=5e-3, atol=1e-5), (i, l1, l2)
+    assert t2._auto and next(iter(t2._auto.values()))["replay"] is not None
+    assert int(t1.step_tensor) == int(t2.step_tensor) == 7
+    p1, p2 = t1.flat.params, t2.flat.params
+    assert float((p1 - p2).norm() / p1.norm()) <= 1e-3
+
+
+@pytest.mark.gpu
+def test_adamw_device_step_and_lr():
+    """deer_adamw with the step count and learning rate read from device memory (graph replay) == host scalars."""
+    from deer_b200._lib import call, ptr
+    g = torch.Generator().manual_seed(1)
+    n = 10007
+    p0 = torch.randn(n, generator=g).cuda()
+    gr = torch.randn(n, generator=g).cuda() * 0.1
+    m0 = torch.randn(n, generator=g).cuda() * 0.01
+    v0 = torch.rand(n, generator=g).cuda() * 0.01
+    ss = (gr * gr).sum().reshape(1)
+    for step in (1, 2, 57, 1000):
+        pa, ma, va = p0.clone(), m0.clone(), v0.clone()
+        pb, mb, vb = p0.clone(), m0.clone(), v0.clone()
+        call("deer_adamw", ptr(pa), ptr(gr), ptr(ma), ptr(va), n, 3e-4 * 0.5, 0.9, 0.999, 1e-8, 1e-5, step, ptr(ss), 1.0,
+             1.0, None, None)
+        st = torch.tensor([step - 1], device="cuda", dtype=torch.int64)
+        lr = torch.tensor([3e-4], device="cuda", dtype=torch.float32)
+        call("deer_adamw", ptr(pb), ptr(gr), ptr(mb), ptr(vb), n, 0.5, 0.9, 0.999, 1e-8, 1e-5, 0, ptr(ss), 1.0, 1.0,
+             st.data_ptr(), ptr(lr))
+        assert torch.equal(ma, mb) and torch.equal(va, vb)
+        assert float((pa - pb).abs().max()) <= 2e-6 * 3e-4 + 1e-7 * float((pa - p0).abs().max()), step
+        # and against torch.optim.AdamW semantics (training.py:121-150) in fp64
+        clip = min(1.0, 1.0 / (float(ss.sqrt()) + 1e-6))
+        gd, pd_, md, vd = gr.double() * clip, p0.double(), m0.double(), v0.double()
+        md = 0.9 * md + 0.1 * gd
+        vd = 0.999 * vd + 0.001 * gd * gd
+        lr_ = 1.5e-4
+        want = pd_ * (1 - lr_ * 1e-5) - lr_ / (1 - 0.9 ** step) * md / (vd.sqrt() / (1 - 0.999 ** step) ** 0.5 + 1e-8)
+        assert float((pb.double() - want).abs().max()) <= 1e-5 * lr_ + 1e-6 * float((want - pd_).abs().max()) + 1e-7

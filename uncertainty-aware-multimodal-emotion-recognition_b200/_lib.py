@@ -59,7 +59,7 @@ _PROTOS = {
     "deer_nig_loss_finish": [P, P, P, P, P, P, P, P, P, F, F, F, F, F, L, L, I, I, F, P, P, P],
     "deer_amini_loss": [P, P, P, P, P, F, F, L, P, P, P, P],
     "deer_sumsq": [P, L, P, P],
-    "deer_adamw": [P, P, P, P, L, F, F, F, F, F, I, P, F, F, P],
+    "deer_adamw": [P, P, P, P, L, F, F, F, F, F, I, P, F, F, P, P, P],
     "deer_axpby": [P, P, P, L, F, F, P],
     "deer_mix_fwd": [P, L, P, L, P, P, P, L, I, P],
     "deer_mix_bwd": [P, P, L, P, L, P, P, P, L, P, L, P, P, L, I, P],

@@ -50,21 +50,16 @@ __device__ __forceinline__ float frcp(float x) {
 __device__ __forceinline__ float fexp(float x) { return fex2(x * 1.4426950408889634f); }
 __device__ __forceinline__ float flog(float x) { return flg2(x) * 0.6931471805599453f; }
 // softplus(x) (torch: beta=1, threshold=20) and its derivative sigmoid(x) from ONE exponential e = exp(-|x|):
-//   softplus = max(x,0) + log1p(e),  log1p(e) = log(u) * e / (u - 1) with u = 1 + e (exact to rounding for tiny e)
+//   softplus = max(x,0) + log1p(e),  log1p(e) = log(u) + (e - (u - 1)) / u with u = fl(1 + e): the first-order
+//   correction of the rounding of 1 + e (both differences are exact in fp32), reusing the reciprocal sigmoid needs
 __device__ __forceinline__ void softplus_fast(float x, float& sp, float& sg) {
   const float e = fexp(-fabsf(x));
   const float u = 1.f + e;
-  const float l = (u == 1.f) ? e : flog(u) * (e * frcp(u - 1.f));
   const float r = frcp(u);
+  const float l = fmaf(e - (u - 1.f), r, flog(u));
   const bool lin = x > 20.f;
   sp = lin ? x : fmaxf(x, 0.f) + l;
   sg = lin ? 1.f : (x >= 0.f ? r : e * r);
-}
-__device__ __forceinline__ float softplus_only(float x) {
-  const float e = fexp(-fabsf(x));
-  const float u = 1.f + e;
-  const float l = (u == 1.f) ? e : flog(u) * (e * frcp(u - 1.f));
-  return x > 20.f ? x : fmaxf(x, 0.f) + l;
 }
 // lgamma(a), a >= 1: shift a < 5 by 4 with one product, then Stirling through a^-7 (truncation < 5e-10 at a = 5;
 // fp32 rounding of (a-1/2) ln a dominates: < 1e-6 absolute for a in [1, 1e5])
@@ -83,9 +78,11 @@ __device__ __forceinline__ float digamma_ge1_fast(float x) {
   const float t0 = sh ? x : 1.f, t1 = t0 + 1.f, t2 = t0 + 2.f, t3 = t0 + 3.f;
   const float p01 = t0 * t1, p23 = t2 * t3;
   // d/dx [t0 t1 t2 t3] = (t0 + t1) p23 + (t2 + t3) p01
-  const float corr = sh ? ((t0 + t1) * p23 + (t2 + t3) * p01) * frcp(p01 * p23) : 0.f;
+  const float p = p01 * p23;
   x = sh ? x + 4.f : x;
-  const float r = frcp(x), r2 = r * r;
+  const float R = frcp(p * x);  // one MUFU for both 1/p and 1/x (p <= 1680, x < 1e5 on this path)
+  const float corr = sh ? ((t0 + t1) * p23 + (t2 + t3) * p01) * (x * R) : 0.f;
+  const float r = p * R, r2 = r * r;
   return flog(x) - 0.5f * r -
          r2 * (0.0833333333f - r2 * (0.00833333333f - r2 * (0.00396825397f - r2 * 0.00416666667f))) - corr;
 }
@@ -230,9 +227,11 @@ __global__ void __launch_bounds__(LOSS_THREADS, 6) nig_loss_stats_kernel(
     a_kla += am1 * am1;
     const float dl = lb - log1eps;
     a_klb += dl * dl;
-    const float u = p.beta * frcp(am1 + eps);
-    a_u += p.beta * frcp(am1 + 1e-8f);
-    const float conf = frcp(1.f + u);
+    const float den = am1 + eps;
+    const float rdc = frcp(den * (den + p.beta));  // 1/den and conf = 1/(1+u) = den/(den+beta) from one reciprocal
+    const float u = p.beta * ((den + p.beta) * rdc);
+    a_u += eps == 1e-8f ? u : p.beta * frcp(am1 + 1e-8f);
+    const float conf = den * (den * rdc);
     const int k = ece_bin(conf, sedges);
     if (k >= 0) {
       bins[k][tid] += 1.f;
@@ -240,8 +239,9 @@ __global__ void __launch_bounds__(LOSS_THREADS, 6) nig_loss_stats_kernel(
       bins[2 * NBINS + k][tid] += fabsf(err);
     }
     if (nig_out) {
-      const float alea = p.beta * frcp(am1);
-      const float epis = alea * frcp(p.nu);
+      const float ran = frcp(am1 * p.nu);
+      const float alea = p.beta * (p.nu * ran);
+      const float epis = p.beta * ran;
       // plane bases live in the constant bank: one IMAD.WIDE per store address
       __stcs(planes.p[0] + e, p.gamma);
       __stcs(planes.p[1] + e, p.nu);
@@ -361,6 +361,7 @@ __global__ void __launch_bounds__(LOSS_THREADS, 6) nig_loss_finish_kernel(
   const int stride = (int)gridDim.x * LOSS_THREADS;  // multiple of D: the dimension is fixed per thread
   const int d = ((int)blockIdx.x * LOSS_THREADS + tid) % D;
   const float w = coef[d].w;
+  const bool eps_is_1e8 = eps == 1e-8f;
   const float cross_c = (cross_w > 0.f && D > 1) ? cross_w * coef[d].cross : 0.f;
   auto element = [&](const RawNig& raw, int e) {
     const Nig p = derive_nig(raw, from_evidence);
@@ -369,10 +370,16 @@ __global__ void __launch_bounds__(LOSS_THREADS, 6) nig_loss_finish_kernel(
     const float S = p.beta + 0.5f * p.nu * e2 + eps;
     const float ah = p.alpha + 0.5f;
     const float be = p.beta + eps;
-    const float rS = frcp(S), rbe = frcp(be), lbe = flog(be);
+    // reciprocals in pairs: 1/a = b * rcp(ab), 1/b = a * rcp(ab) (the MUFU pipe is the busiest one in this kernel)
+    const float rSb = frcp(S * be);
+    const float rS = be * rSb, rbe = S * rSb, lbe = flog(be);
+    const float am1 = p.alpha - 1.f;
+    const float den = am1 + eps;
+    const float rnd = frcp(p.nu * den);
+    const float rnu = den * rnd, rden = p.nu * rnd;
     // nll
     float dg = -ah * p.nu * err * rS;
-    float dn = -0.5f * frcp(p.nu) + ah * e2 * 0.5f * rS;
+    float dn = -0.5f * rnu + ah * e2 * 0.5f * rS;
     float da = -lbe + digamma_ge1_fast(p.alpha + eps) + flog(S);
     float db = -p.alpha * rbe + ah * rS;
     // reg
@@ -380,31 +387,26 @@ __global__ void __launch_bounds__(LOSS_THREADS, 6) nig_loss_finish_kernel(
     dn += reg_w * e2 * e2;
     db += reg_w * 2.f * e2;
     // kl
-    const float am1 = p.alpha - 1.f;
     da += kl_w * 2.f * am1;
     db += kl_w * 0.2f * (lbe - log1eps) * rbe;
     // ece
-    const float den = am1 + eps;
-    const float rden = frcp(den);
     const float u = p.beta * rden;
     const float conf = frcp(1.f + u);
-    if (ece_w > 0.f) {
+    if (ece_w > 0.f) {  // uniform
       const int k = ece_bin(conf, sedges);
-      if (k >= 0) {
-        const float sg = coef[d].sign[k] * ece_w;
-        const float dconf_du = -conf * conf;
-        db += sg * dconf_du * rden;
-        da += sg * dconf_du * (-u * rden);
-        dg += sg * (err > 0.f ? -1.f : (err < 0.f ? 1.f : 0.f));
-      }
+      const float sg = k >= 0 ? coef[d].sign[max(k, 0)] * ece_w : 0.f;
+      const float t = -sg * conf * conf * rden;  // sg * dconf/du * 1/den
+      db += t;
+      da -= t * u;
+      dg += err > 0.f ? -sg : (err < 0.f ? sg : 0.f);
     }
     dg *= w;
     dn *= w;
     da *= w;
     db *= w;
     // cross-dimension consistency: d/d ubar_d * (1/N) * du/d(alpha,beta), u = beta/(alpha-1+1e-8)
-    if (cross_w > 0.f && D > 1) {
-      const float r8 = frcp(am1 + 1e-8f);
+    if (cross_w > 0.f && D > 1) {  // uniform
+      const float r8 = eps_is_1e8 ? rden : frcp(am1 + 1e-8f);  // same denominator under the default epsilon
       db += cross_c * r8;
       da += cross_c * (-p.beta * r8 * r8);
     }

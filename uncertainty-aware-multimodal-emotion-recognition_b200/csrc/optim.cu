@@ -26,7 +26,16 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
                                                     float* __restrict__ m, float* __restrict__ v, long long n, float lr,
                                                     float beta1, float beta2, float eps, float wd, float bc1,
                                                     float bc2_sqrt, const float* __restrict__ sumsq, float max_norm,
-                                                    float grad_scale) {
+                                                    float grad_scale, const long long* __restrict__ step_dev,
+                                                    const float* __restrict__ lr_dev) {
+  // CUDA-graph replays: the step count (bias corrections) and the learning rate come from device memory, so one
+  // captured training step stays valid across steps and LR-schedule changes
+  if (step_dev) {
+    const float t = (float)(*step_dev + 1);
+    bc1 = 1.f - exp2f(t * log2f(beta1));
+    bc2_sqrt = sqrtf(1.f - exp2f(t * log2f(beta2)));
+  }
+  if (lr_dev) lr *= *lr_dev;
   float clip = 1.f;
   if (sumsq && max_norm > 0.f) {
     const float total_norm = sqrtf(*sumsq) * grad_scale;
@@ -65,15 +74,15 @@ int deer_sumsq(const float* x, long long n, float* out, void* stream) {
 
 int deer_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                float eps, float weight_decay, int step, const float* sumsq, float max_norm, float grad_scale,
-               void* stream) {
-  DEER_CHECK_ARG(p && g && m && v && n > 0 && step >= 1, "adamw: bad args");
-  const float bc1 = 1.f - powf(beta1, (float)step);
-  const float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
+               const long long* step_dev, const float* lr_dev, void* stream) {
+  DEER_CHECK_ARG(p && g && m && v && n > 0 && (step >= 1 || step_dev), "adamw: bad args");
+  const float bc1 = step_dev ? 1.f : 1.f - powf(beta1, (float)step);
+  const float bc2_sqrt = step_dev ? 1.f : sqrtf(1.f - powf(beta2, (float)step));
   long long gr = cdiv(n, 256 * 4);
   if (gr > kNumSMs * 8) gr = kNumSMs * 8;
   if (gr < 1) gr = 1;
   DEER_LAUNCH(adamw_kernel, (unsigned)gr, 256, 0, stream, p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1,
-              bc2_sqrt, sumsq, max_norm, grad_scale);
+              bc2_sqrt, sumsq, max_norm, grad_scale, step_dev, lr_dev);
   return DEER_OK;
 }
 

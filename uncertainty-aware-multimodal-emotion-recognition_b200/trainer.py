@@ -73,12 +73,35 @@ def reference_lr_group(name: str) -> int:
     return 0 if "encoder" in name else 1
 
 
+def capture_forward(model: nn.Module, *inputs, warmup: int = 2, **kw_inputs):
+    """CUDA-graph capture of an inference forward on static input tensors (refill them in place).  Returns
+    (replay, outputs): `replay()` re-runs the captured launches and returns the static `outputs`."""
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.no_grad():
+        with torch.cuda.stream(side):
+            for _ in range(max(warmup, 1)):
+                model(*inputs, **kw_inputs)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = model(*inputs, **kw_inputs)
+
+    def replay():
+        graph.replay()
+        return out
+
+    return replay, out
+
+
 class DEERDataParallelTrainer:
     def __init__(self, model: nn.Module, learning_rate: float = 1e-4, weight_decay: float = 1e-5,
                  gradient_clip: float = 1.0, betas=(0.9, 0.999), eps: float = 1e-8,
                  process_group=None, exact_global_loss: bool = True, loss_weights=(0.1, 0.01, 0.05, 0.05)):
         self.model = model
-        self.lr, self.wd, self.clip, self.betas, self.eps = learning_rate, weight_decay, gradient_clip, betas, eps
+        self._lr = float(learning_rate)
+        self.wd, self.clip, self.betas, self.eps = weight_decay, gradient_clip, betas, eps
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
         self.exact_global_loss = exact_global_loss
@@ -89,7 +112,13 @@ class DEERDataParallelTrainer:
         self.v = torch.zeros_like(self.flat.params)
         self.sumsq = torch.zeros(1, device=dev, dtype=torch.float32)
         self.step_count = 0
+        # device-side step counter and learning rate: a captured CUDA graph of the step replays unchanged while
+        # both advance (dropout masks, AdamW bias corrections, LR schedule)
         self.step_tensor = torch.zeros(1, device=dev, dtype=torch.int64)
+        self.lr_tensor = torch.full((1,), float(learning_rate), device=dev, dtype=torch.float32)
+        self._graphs: Dict[int, tuple] = {}
+        self._auto: Dict[tuple, dict] = {}
+        self._graph_pool = None
         ops.set_dropout_step_tensor(self.step_tensor)
         self.direct_grad = True   # backward kernels accumulate straight into the flat gradient buffer
         self.group_lr = {0: 0.5, 1: 1.0}
@@ -126,6 +155,17 @@ class DEERDataParallelTrainer:
         self.last_losses = losses
         return losses
 
+    @property
+    def lr(self) -> float:
+        return self._lr
+
+    @lr.setter
+    def lr(self, value: float):
+        """Learning-rate schedule hook: updates the device scalar the (possibly graph-captured) AdamW launches read."""
+        self._lr = float(value)
+        if hasattr(self, "lr_tensor"):
+            self.lr_tensor.fill_(self._lr)
+
     def optimizer_step(self):
         self.step_count += 1
         f = self.flat
@@ -136,16 +176,70 @@ class DEERDataParallelTrainer:
             n = hi - lo
             if n <= 0:
                 continue
+            # lr = group multiplier x *lr_tensor, step = *step_tensor + 1: both read on the device
             call("deer_adamw", f.params.data_ptr() + 4 * lo, f.grads.data_ptr() + 4 * lo, self.m.data_ptr() + 4 * lo,
-                 self.v.data_ptr() + 4 * lo, n, float(self.lr * self.group_lr[g]), float(self.betas[0]),
-                 float(self.betas[1]), float(self.eps), float(self.wd), self.step_count, ptr(self.sumsq),
-                 float(self.clip), 1.0)
+                 self.v.data_ptr() + 4 * lo, n, float(self.group_lr[g]), float(self.betas[0]),
+                 float(self.betas[1]), float(self.eps), float(self.wd), 0, ptr(self.sumsq),
+                 float(self.clip), 1.0, self.step_tensor.data_ptr(), ptr(self.lr_tensor))
         self.step_tensor.add_(1)
 
     def train_step(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
         losses = self.forward_backward(batch)
         self.optimizer_step()
         return losses
+
+    # ------------------------------------------------------------------ CUDA-graph replay of the whole step
+    def capture(self, batch: Dict[str, torch.Tensor], warmup: int = 2):
+        """Capture fwd + loss + bwd + exchange + clip + AdamW on the tensors of `batch` (which become the static
+        input buffers: refill them in place, e.g. with `copy_` from pinned host memory) into one CUDA graph.
+        The ~300 kernel launches of a step then cost one `cudaGraphLaunch`; the step counter, dropout masks and the
+        learning rate keep advancing because the kernels read them from device memory.  Returns a callable that
+        replays the step and returns the (static) losses tensor."""
+        key = tuple(sorted((k, v.data_ptr(), tuple(v.shape)) for k, v in batch.items() if torch.is_tensor(v)))
+        hit = self._graphs.get(hash(key))
+        if hit is not None:
+            return hit[2]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):       # lazily created state (TMA descriptors, smem opt-ins, NCCL buffers)
+                self.train_step(batch)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        if self._graph_pool is None:
+            self._graph_pool = torch.cuda.graph_pool_handle()
+        with torch.cuda.graph(graph, pool=self._graph_pool):
+            losses = self.train_step(batch)
+        self.step_count -= 1   # the capture pass itself launched nothing
+
+        def replay() -> torch.Tensor:
+            self.step_count += 1
+            graph.replay()
+            self.last_losses = losses
+            return losses
+
+        self._graphs[hash(key)] = (graph, losses, replay)
+        return replay
+
+    def train_step_auto(self, batch: Dict[str, torch.Tensor], eager_steps: int = 2) -> torch.Tensor:
+        """train_step for a stream of freshly allocated batches (a DataLoader): the first `eager_steps` batches of a
+        given shape run eagerly (they double as the warm-up), then the step is captured once on static input buffers
+        and every later batch of that shape is copied into them and replayed.  Batches of another shape (the last,
+        short one of an epoch) get their own entry."""
+        tens = {k: v for k, v in batch.items() if torch.is_tensor(v)}
+        sig = tuple(sorted((k, tuple(v.shape), v.dtype) for k, v in tens.items()))
+        ent = self._auto.setdefault(sig, {"seen": 0, "static": None, "replay": None})
+        if ent["replay"] is None:
+            ent["seen"] += 1
+            if ent["seen"] <= eager_steps or not all(v.is_cuda for v in tens.values()):
+                return self.train_step(batch)
+            ent["static"] = {k: v.clone() for k, v in tens.items()}
+            ent["replay"] = self.capture(ent["static"], warmup=0)
+            # the capture pass launched nothing: fall through and replay this batch
+        for k, v in tens.items():
+            ent["static"][k].copy_(v, non_blocking=True)
+        return ent["replay"]()
 
     def grad_norm(self) -> torch.Tensor:
         return self.sumsq.sqrt()
