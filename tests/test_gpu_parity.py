@@ -34,7 +34,10 @@ def _engine():
                                          (200, 4, 64, 0, 1), (96, 100, 4100, 1, 0), (17, 31, 29, 1, 1),
                                          # >= 148 64x64 tiles: the large-tile kernel (the rest use the 32x32 split-K one)
                                          (1100, 900, 70, 0, 1), (900, 1100, 33, 1, 0), (256, 512, 512, 0, 1),
-                                         (512, 256, 256, 1, 0), (256, 768, 640, 0, 0)])
+                                         (512, 256, 256, 1, 0), (256, 768, 640, 0, 0),
+                                         # cp.async-pipelined small kernel: every operand orientation with M/N/K tails
+                                         (36, 52, 100, 1, 1), (100, 36, 68, 0, 0), (44, 28, 200, 1, 0),
+                                         (130, 72, 132, 0, 1), (256, 384, 256, 0, 1), (256, 256, 1536, 0, 0)])
 def test_gemm_simt(M, N, K, ta, tb):
     g = torch.Generator().manual_seed(M * 131 + N)
     A = torch.randn((K, M) if ta else (M, K), generator=g)
@@ -511,7 +514,7 @@ def test_adamw_device_step_and_lr():
         call("deer_adamw", ptr(pb), ptr(gr), ptr(mb), ptr(vb), n, 0.5, 0.9, 0.999, 1e-8, 1e-5, 0, ptr(ss), 1.0, 1.0,
              st.data_ptr(), ptr(lr))
         assert torch.equal(ma, mb) and torch.equal(va, vb)
-        assert float((pa - pb).abs().max()) <= 2e-6 * 3e-4 + 1e-7 * float((pa - p0).abs().max()), step
+        assert float((pa - pb).abs().max()) <= 2.5e-7 * float(p0.abs().max()), step   # 1-2 ulp of the parameter
         # and against torch.optim.AdamW semantics (training.py:121-150) in fp64
         clip = min(1.0, 1.0 / (float(ss.sqrt()) + 1e-6))
         gd, pd_, md, vd = gr.double() * clip, p0.double(), m0.double(), v0.double()
@@ -519,4 +522,4 @@ def test_adamw_device_step_and_lr():
         vd = 0.999 * vd + 0.001 * gd * gd
         lr_ = 1.5e-4
         want = pd_ * (1 - lr_ * 1e-5) - lr_ / (1 - 0.9 ** step) * md / (vd.sqrt() / (1 - 0.999 ** step) ** 0.5 + 1e-8)
-        assert float((pb.double() - want).abs().max()) <= 1e-5 * lr_ + 1e-6 * float((want - pd_).abs().max()) + 1e-7
+        assert float((pb.double() - want).abs().max()) <= 1e-4 * lr_ + 2.5e-7 * float(p0.abs().max())
