@@ -356,7 +356,19 @@ def main():
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # captured graphs hold NCCL work: drop them, drain the device, meet the other ranks, then leave without the
+        # process-group teardown (destroy_process_group after graph-captured collectives hung at exit on NCCL 2.28)
+        replays = e2e_replays = None
+        trainer._graphs.clear()
+        trainer._auto.clear()
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def pooled_sweep(torch, deer_b200, Trainer, dev, use_graph=True, batches=(64, 1024, 16384, 65536)):
