@@ -412,7 +412,9 @@ def test_fused_loss_wide_range_vs_oracle(B, scale):
 
 
 @pytest.mark.parametrize("M,N,K,ta,tb", [(300, 520, 200, 0, 1), (128, 256, 64, 0, 1), (1000, 84, 4100, 1, 0),
-                                         (260, 300, 130, 0, 0), (130, 512, 96, 1, 1), (2050, 1024, 84, 0, 1)])
+                                         (260, 300, 130, 0, 0), (130, 512, 96, 1, 1), (2050, 1024, 84, 0, 1),
+                                         # CTA-pair (cta_group::2) kernel over several persistent rounds / split-K
+                                         (40000, 520, 512, 0, 1), (1024, 512, 9000, 1, 0), (700, 1024, 1024, 0, 0)])
 @pytest.mark.parametrize("a_bf,b_bf", [(0, 0), (1, 1)])
 def test_gemm_h16(M, N, K, ta, tb, a_bf, b_bf):
     """16-bit-operand persistent tcgen05 engine: all operand majors, FP16/BF16 mixes, K/M/N tails, bias + activation +

@@ -23,6 +23,7 @@ int gemm_tcgen05(const float* A, long long lda, int transA, const float* B, long
                  long long ldc, int M, int N, int K, const float* bias, int act, float beta, int batch, long long sA,
                  long long sB, long long sC, long long sBias, cudaStream_t stream);
 extern int g_small_engine;
+extern int g_h16_pair;
 void gemm_tcgen05_set_round(int on);
 void lstm_cluster_set_option(int ts, int tile);
 void lstm_cluster_set_profile(long long* buf);
@@ -55,6 +56,9 @@ int deer_set_option(int option, int value) {
       return DEER_OK;
     case DEER_OPT_LSTM_TILE:
       lstm_cluster_set_option(-1, value);
+      return DEER_OK;
+    case DEER_OPT_H16_PAIR:
+      g_h16_pair = value ? 1 : 0;
       return DEER_OK;
     case DEER_OPT_SMALL_GEMM:
       g_small_engine = value == 1 ? 1 : 2;

@@ -299,6 +299,313 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
   }
 }
 
+// ------------------------------------------------------------------------------------------------- CTA-pair engine
+// cta_group::2 variant: a cluster of two CTAs (one TPC) owns a 256 x 256 output tile.  Each CTA stages its own 128
+// rows of A and HALF of the B tile (128 of the 256 N rows); the leader CTA's single thread issues M256 N256 K16 MMAs
+// that read both CTAs' shared memory and write 128 accumulator rows into each CTA's TMEM.  Per CTA and k-block the
+// shared-memory traffic drops from 48 KB written + 48 KB read to 32 + 32 KB: the single-CTA kernel is bound by exactly
+// that traffic (TMA fill + tensor-core operand reads against 128 B/clk/SM), not by the tensor pipe.
+//   full barriers live in the leader (both CTAs' TMA loads signal them, .cta_group::2); the MMA commits multicast to the
+//   slot-empty and accumulator-full barriers of BOTH CTAs; both CTAs' epilogue warps arrive on the leader's
+//   accumulator-empty barrier.  Everything else (roles, TMEM double buffering, TMA-store epilogue) is as above.
+constexpr int P_STAGES = 5;
+constexpr int P_STAGING_BYTES = 2 * STAGING_BYTES;   // TWO 32x32 fp32 store tiles per epilogue warp (double buffered)
+constexpr int PB_BYTES = (BN / 2) * BK * 2;            // 16 KB: this CTA's half of the B tile
+constexpr int P_STAGE_BYTES = A_BYTES + PB_BYTES;      // 32 KB
+constexpr int P_SMEM_BYTES = P_STAGES * P_STAGE_BYTES + P_STAGING_BYTES + 256 + 1024;
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;        // shared::cluster address of the same offset in the even CTA
+
+__device__ __forceinline__ void umma_16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
+// TMA tile load whose completion bytes are counted on the LEADER CTA's mbarrier (same offset, peer bit cleared)
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
+          "r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// arrive on the barrier at the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(bar)), "r"(rank));
+  // default semantics (release at CTA scope): the .release.cluster form compiles to MEMBAR.ALL.GPU + ERRBAR, which
+  // waited on the warp's outstanding global traffic (11 % of the stall samples); the hand-back only orders TMEM reads,
+  // and those are complete (tcgen05.wait::ld + tcgen05.fence::before_thread_sync) before this arrive
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+}
+
+// 16 TMEM lanes x 32 columns in the mma-accumulator fragment layout: lane t holds row t/4 (registers 4n, 4n+1) and row
+// t/4 + 8 (registers 4n+2, 4n+3) at columns 8n + 2*(t%4) + {0,1}, n = 0..3.  Four lanes therefore own 32 contiguous
+// bytes of one output row: a warp-wide 8-byte store writes eight full 32-byte sectors, straight from registers.
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void red_add_v2(float* p, float a, float b) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
+
+template <bool A_MN, bool B_MN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+    gemm_h16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                         const __grid_constant__ CUtensorMap tmap_c, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  float* staging = reinterpret_cast<float*>(smem + P_STAGES * P_STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + P_STAGES * P_STAGE_BYTES + P_STAGING_BYTES);
+  uint64_t* empty_bar = full_bar + P_STAGES;
+  uint64_t* tmem_full = empty_bar + P_STAGES;  // [2]
+  uint64_t* tmem_empty = tmem_full + 2;        // [2]  (the leader's copy is the live one)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const int total_kb = (p.K + BK - 1) / BK;
+  const int total_work = p.tiles_m * p.tiles_n * p.splits;   // tiles_m counts 256-row pair tiles here
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_b);
+    prefetch_tmap(&tmap_c);
+    for (int s = 0; s < P_STAGES; s++) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; b++) {
+      mbar_init(&tmem_full[b], 1);
+      mbar_init(&tmem_empty[b], 16);   // 8 epilogue warps of each CTA
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_pair(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // both CTAs' barriers exist before any remote arrival / multicast commit
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto decode = [&](int w, int& m0, int& n0, int& kb0, int& nkb) {
+    const int split = w % p.splits, tile = w / p.splits;
+    m0 = (tile / p.tiles_n) * (2 * BM);
+    n0 = (tile % p.tiles_n) * BN;
+    kb0 = split * p.kb_per_split;
+    nkb = min(total_kb, kb0 + p.kb_per_split) - kb0;
+  };
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer (both CTAs)
+    const bool leader = elect_one();
+    uint32_t g = 0;
+    for (int w = cluster_id; w < total_work; w += num_clusters) {
+      int m0, n0, kb0, nkb;
+      decode(w, m0, n0, kb0, nkb);
+      const int mr = m0 + (int)rank * BM;          // this CTA's 128 rows of A
+      const int nr = n0 + (int)rank * (BN / 2);    // this CTA's 128 rows of B
+      for (int i = 0; i < nkb; i++, g++) {
+        const int s = g % P_STAGES;
+        mbar_wait(&empty_bar[s], ((g / P_STAGES) & 1) ^ 1);
+        if (leader) {
+          uint8_t* sa = smem + s * P_STAGE_BYTES;
+          uint8_t* sb = sa + A_BYTES;
+          const int k0 = (kb0 + i) * BK;
+          if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * P_STAGE_BYTES);   // both CTAs' bytes land on this barrier
+          if (!A_MN) {
+            tma_load_2d_pair(sa, &tmap_a, &full_bar[s], k0, mr);            // box {64 k, 128 rows}
+          } else {
+#pragma unroll
+            for (int j = 0; j < BM / 64; j++)                                // box {64 m, 64 k} x2
+              tma_load_2d_pair(sa + j * 8192, &tmap_a, &full_bar[s], mr + 64 * j, k0);
+          }
+          if (!B_MN) {
+            tma_load_2d_pair(sb, &tmap_b, &full_bar[s], k0, nr);            // box {64 k, 128 rows}
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 128; j++)                               // box {64 n, 64 k} x2
+              tma_load_2d_pair(sb + j * 8192, &tmap_b, &full_bar[s], nr + 64 * j, k0);
+          }
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer (leader CTA only)
+    if (rank == 0) {
+      const uint32_t tb = warp_uniform(tmem_base);
+      const bool leader = elect_one();
+      uint32_t g = 0;
+      int it = 0;
+      for (int w = cluster_id; w < total_work; w += num_clusters, it++) {
+        int m0, n0, kb0, nkb;
+        decode(w, m0, n0, kb0, nkb);
+        const int acc = it & 1;
+        mbar_wait(&tmem_empty[acc], (uint32_t)(((it >> 1) & 1) ^ 1));   // both CTAs drained this accumulator
+        tc_fence_after();
+        for (int i = 0; i < nkb; i++, g++) {
+          const int s = g % P_STAGES;
+          mbar_wait(&full_bar[s], (g / P_STAGES) & 1);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * P_STAGE_BYTES);
+          const uint32_t sb = sa + A_BYTES;
+          if (leader) {
+#pragma unroll
+            for (int k = 0; k < BK / UK; k++) {
+              const uint64_t ad = A_MN ? make_smem_desc(sa + k * 2048, 8192, 1024, 2) : make_smem_desc(sa + k * 32, 16, 1024, 2);
+              const uint64_t bd = B_MN ? make_smem_desc(sb + k * 2048, 8192, 1024, 2) : make_smem_desc(sb + k * 32, 16, 1024, 2);
+              umma_16_pair(tb + acc * BN, ad, bd, p.idesc, (i > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit_pair(&empty_bar[s]);
+            if (i == nkb - 1) umma_commit_pair(&tmem_full[acc]);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ===================================================================== epilogue (warps 2..9, both CTAs)
+    const int gq = warp & 3;
+    const int half = (warp - 2) >> 2;
+    uint8_t* tile0 = reinterpret_cast<uint8_t*>(staging) + (warp - 2) * 8192;   // two 4 KB tiles per warp
+    uint32_t nstore = 0;                                                         // stores issued by this warp
+    const int act = p.act;
+    const bool reduce = p.beta != 0.f || p.splits > 1;
+    int it = 0;
+    for (int w = cluster_id; w < total_work; w += num_clusters, it++) {
+      int m0, n0, kb0, nkb;
+      decode(w, m0, n0, kb0, nkb);
+      const int acc = it & 1;
+      mbar_wait(&tmem_full[acc], (uint32_t)((it >> 1) & 1));
+      tc_fence_after();
+      const int row_base = m0 + (int)rank * BM + gq * 32;
+      const bool add_bias = p.bias != nullptr && (w % p.splits) == 0;
+      if (p.debug & 4) {
+        // ---- direct epilogue (ablation, DEER_H16_DEBUG=4; measured SLOWER than the TMA-store epilogue: 110 vs 100 us): TMEM -> registers (accumulator-fragment layout) -> full-sector global stores.  No
+        // shared-memory staging and no TMA store: the TMA unit and the shared-memory port stay with the operand ring
+        // (measured: the TMA-store epilogue added 37 us to the 64 us the rest of the kernel needs at K = 512).
+        const int lr = lane >> 2, lc = (lane & 3) * 2;
+#pragma unroll 1
+        for (int c = half; c < BN / 32; c += 2) {
+          const int gn0 = n0 + c * 32;
+          if (gn0 >= p.N || row_base >= p.M) break;
+          float v[32];
+          const uint32_t ta = tmem_base + ((uint32_t)(gq * 32) << 16) + (uint32_t)(acc * BN + c * 32);
+          tmem_ld_16x256b_x4(ta, v);
+          tmem_ld_16x256b_x4(ta + (16u << 16), v + 16);
+          tmem_ld_wait();
+          if (p.debug & 2) continue;
+#pragma unroll
+          for (int n = 0; n < 4; n++) {
+            const int col = gn0 + 8 * n + lc;
+            if (col >= p.N) continue;   // N is even (checked on the host): col + 1 < N as well
+            float2 b2 = make_float2(0.f, 0.f);
+            if (add_bias) b2 = __ldg(reinterpret_cast<const float2*>(p.bias + col));
+#pragma unroll
+            for (int h2 = 0; h2 < 2; h2++) {
+#pragma unroll
+              for (int q = 0; q < 2; q++) {
+                const int row = row_base + 16 * h2 + 8 * q + lr;
+                float x = v[16 * h2 + 4 * n + 2 * q] + b2.x, y = v[16 * h2 + 4 * n + 2 * q + 1] + b2.y;
+                if (act != DEER_ACT_NONE) {
+                  x = act_apply1(x, act);
+                  y = act_apply1(y, act);
+                }
+                if (row < p.M && !(p.debug & 1)) {
+                  float* dst = p.C + (long long)row * p.ldc + col;
+                  if (reduce) red_add_v2(dst, x, y);
+                  else __stcs(reinterpret_cast<float2*>(dst), make_float2(x, y));
+                }
+              }
+            }
+          }
+        }
+      } else
+#pragma unroll 1
+      for (int c = half; c < BN / 32; c += 2) {
+        const int gn0 = n0 + c * 32;
+        if (gn0 >= p.N || row_base >= p.M) break;
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(gq * 32) << 16) + (uint32_t)(acc * BN + c * 32), v);
+        tmem_ld_wait();
+        if (add_bias) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (gn0 + j < p.N) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + gn0 + j));
+              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+            }
+          }
+        }
+        if (act != DEER_ACT_NONE) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 o = act_apply4(make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]), act);
+            v[j] = o.x; v[j + 1] = o.y; v[j + 2] = o.z; v[j + 3] = o.w;
+          }
+        }
+        if (p.debug & 2) continue;   // timing experiments: TMEM read only
+        // double-buffered store tiles: before overwriting a tile only the store issued TWO chunks ago must have been
+        // read out by the TMA unit; the previous chunk's store keeps draining while this one is staged (the wait
+        // right after every store was 29 % of all stall samples)
+        uint8_t* tile = tile0 + (nstore & 1) * 4096;
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+          *reinterpret_cast<float4*>(tile + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+              make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0 && !(p.debug & 1)) {
+          if (reduce) tma_reduce_add_2d(&tmap_c, tile, gn0, row_base);
+          else tma_store_2d(&tmap_c, tile, gn0, row_base);
+          tma_store_commit();
+        }
+        nstore++;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);   // the leader's MMA warp owns the hand-back barrier
+    }
+    if (lane == 0) tma_store_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // the leader's MMAs read this CTA's shared memory; nobody leaves or frees TMEM early
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, 512);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -345,6 +652,7 @@ static bool make_map_c(CUtensorMap* map, float* base, long long rows, long long 
 }  // namespace h16
 
 static long long* g_h16_prof = nullptr;
+int g_h16_pair = 1;   // 1 (default): cta_group::2 CTA-pair kernel when M > 128; 0: single-CTA kernel (DEER_OPT_H16_PAIR)
 void gemm_h16_set_profile(long long* buf) { g_h16_prof = buf; }
 
 int gemm_h16(const void* A, long long lda, int transA, int a_bf, const void* B, long long ldb, int transB, int b_bf,
@@ -375,13 +683,22 @@ int gemm_h16(const void* A, long long lda, int transA, int a_bf, const void* B, 
     set_error("gemm_h16: cuTensorMapEncodeTiled failed (M=%d N=%d K=%d lda=%lld ldb=%lld)", M, N, K, lda, ldb);
     return DEER_ERR_UNSUPPORTED;
   }
-  const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
+  const bool pair = g_h16_pair && M > BM && (N & 1) == 0 && (ldc & 1) == 0;
+  if (pair && transB) {   // the pair kernel stages HALF of the K-major B tile per CTA: box of 128 rows
+    if (!make_map16(&mb, B, b_bf, N, K, ldb, BK, BN / 2)) {
+      set_error("gemm_h16: cuTensorMapEncodeTiled failed for B (pair box)");
+      return DEER_ERR_UNSUPPORTED;
+    }
+  }
+  const int tile_rows = pair ? 2 * BM : BM;
+  const int tiles_m = (M + tile_rows - 1) / tile_rows, tiles_n = (N + BN - 1) / BN;
   const int total_kb = (K + BK - 1) / BK;
   int splits = 1;
   if (beta == 1.f && act == DEER_ACT_NONE && C16 == nullptr) {
     const int tiles = tiles_m * tiles_n;
-    if (tiles < kNumSMs && total_kb >= 32) {
-      splits = (2 * kNumSMs + tiles - 1) / tiles;
+    const int units = pair ? kNumSMs / 2 : kNumSMs;   // schedulable CTAs / CTA pairs
+    if (tiles < units && total_kb >= 32) {
+      splits = (2 * units + tiles - 1) / tiles;
       const int max_splits = total_kb / 8;
       if (splits > max_splits) splits = max_splits;
       if (splits < 1) splits = 1;
@@ -392,9 +709,29 @@ int gemm_h16(const void* A, long long lda, int transA, int a_bf, const void* B, 
   // instruction descriptor: D fp32, A/B formats, majors, N = 256, M = 128
   const uint32_t idesc = (1u << 4) | ((uint32_t)(a_bf ? 1 : 0) << 7) | ((uint32_t)(b_bf ? 1 : 0) << 10) |
                          ((uint32_t)(transA ? 1 : 0) << 15) | ((uint32_t)(transB ? 0 : 1) << 16) |
-                         ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+                         ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(tile_rows >> 4) << 24);
   Params p{C, ldc, C16, ldc16, c16_bf, bias, M, N, K, act, beta, splits, per, tiles_m, tiles_n, idesc, g_h16_prof, getenv("DEER_H16_DEBUG") ? atoi(getenv("DEER_H16_DEBUG")) : 0};
   const int work = tiles_m * tiles_n * splits;
+  if (pair) {
+    const int clusters = work < kNumSMs / 2 ? work : kNumSMs / 2;
+#define DEER_H16_PAIR_GO(AM, BMN)                                                                                    \
+  do {                                                                                                               \
+    static bool attr = false;                                                                                        \
+    if (!attr) {                                                                                                     \
+      cudaError_t e = cudaFuncSetAttribute(gemm_h16_pair_kernel<AM, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                           P_SMEM_BYTES);                                                            \
+      if (e != cudaSuccess) return cuda_status(e, "gemm_h16 pair smem attribute");                                   \
+      attr = true;                                                                                                   \
+    }                                                                                                                \
+    DEER_LAUNCH((gemm_h16_pair_kernel<AM, BMN>), 2 * clusters, NUM_THREADS, P_SMEM_BYTES, stream, ma, mb, mc, p);    \
+  } while (0)
+    if (!transA && transB) DEER_H16_PAIR_GO(false, false);
+    else if (!transA && !transB) DEER_H16_PAIR_GO(false, true);
+    else if (transA && transB) DEER_H16_PAIR_GO(true, false);
+    else DEER_H16_PAIR_GO(true, true);
+#undef DEER_H16_PAIR_GO
+    return DEER_OK;
+  }
   const int grid = work < kNumSMs ? work : kNumSMs;
 #define DEER_H16_GO(AM, BMN)                                                                                       \
   do {                                                                                                             \
