@@ -524,9 +524,8 @@ class _BiLSTMLayerCluster(torch.autograd.Function):
             x16 = cast16(x)                                   # [M, Kp] fp16
             Kp = x16.shape[1]
             w16 = cast16(wi_il.view(2 * G, In))               # [2G, Kp] fp16
-            for d in range(2):
-                gemm_h16(x16, Kp, 0, w16.data_ptr() + 2 * d * G * Kp, Kp, 1, pre.data_ptr() + 4 * G * d, 2 * G, M, G, In,
-                         bias=b_il[d])
+            # both directions in ONE contraction: pre[M, 2G] = x16 [M, Kp] . w16[2G, Kp]^T (full 8 KB output rows)
+            gemm_h16(x16, Kp, 0, w16, Kp, 1, pre, 2 * G, M, 2 * G, In, bias=b_il.view(-1))
         else:
             for d in range(2):
                 gemm(x, In, 0, wi_il[d], In, 1, pre.data_ptr() + 4 * G * d, 2 * G, M, G, In, bias=b_il[d])
@@ -572,9 +571,8 @@ class _BiLSTMLayerCluster(torch.autograd.Function):
             if ctx.needs_input_grad[0]:
                 wb16 = cast16(wi_il.view(2 * G, In), bf16=True)   # [2G, Kp] bf16: B operand of dx (MN-major [K=G, N=In])
                 dx = torch.empty((T, B, In), device=dev, dtype=torch.float32)
-                for d in range(2):
-                    gemm_h16(dpre16.data_ptr() + 2 * G * d, 2 * G, 0, wb16.data_ptr() + 2 * d * G * Kp, Kp, 0, dx, In,
-                             M, In, G, a_bf16=True, b_bf16=True, beta=0.0 if d == 0 else 1.0)
+                # dx = dpre16 [M, 2G] . wb16 [2G, In]: the sum over the two directions is the K = 2G contraction itself
+                gemm_h16(dpre16, 2 * G, 0, wb16, Kp, 0, dx, In, M, In, 2 * G, a_bf16=True, b_bf16=True, beta=0.0)
         elif ctx.needs_input_grad[0]:
             dx = torch.empty((T, B, In), device=dev, dtype=torch.float32)
             for d in range(2):
@@ -582,14 +580,18 @@ class _BiLSTMLayerCluster(torch.autograd.Function):
                      beta=0.0 if d == 0 else 1.0)
         P = ctx.params
         out = []
+        dwi_il2 = None
+        if use16:
+            # dW_ih of both directions at once: [2G, In] = dpre16 [M, 2G]^T . xb16 [M, In]
+            dwi_il2 = torch.zeros((2, G, In), device=dev, dtype=torch.float32)
+            gemm_h16(dpre16, 2 * G, 1, xb16, Kp, 0, dwi_il2, In, 2 * G, In, M, a_bf16=True, b_bf16=True, beta=1.0)
         for d in range(2):
             gp = dpre.data_ptr() + 4 * G * d
-            dwi_il = torch.zeros((G, In), device=dev, dtype=torch.float32)
+            dwi_il = dwi_il2[d] if use16 else torch.zeros((G, In), device=dev, dtype=torch.float32)
             dwh_il = torch.zeros((G, H), device=dev, dtype=torch.float32)
             Mr = (T - 1) * B
             if use16:
                 gp16 = dpre16.data_ptr() + 2 * G * d
-                gemm_h16(gp16, 2 * G, 1, xb16, Kp, 0, dwi_il, In, G, In, M, a_bf16=True, b_bf16=True, beta=1.0)
                 if T > 1:
                     if d == 0:   # rows t=1.. pair with h[t-1]
                         gemm_h16(gp16 + 2 * B * 2 * G, 2 * G, 1, hb16.data_ptr(), 2 * H, 0, dwh_il, H, G, H, Mr,
