@@ -413,38 +413,75 @@ def _time_launches(torch, fn, n, warm=5):
     return e0.elapsed_time(e1) * 1e3 / n   # us per launch
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/)
+NCU_TRAFFIC = {}
+
+
 def roofline_probe(torch, ops, dev, pk):
     """Kernels timed alone with CUDA events on the launching stream (operands rotate through buffers larger than L2).
 
     Headline = the dense-contraction engine of the training step (16-bit tcgen05 GEMM) on its largest instance: the
-    time-batched layer-1 LSTM input projection gates[B*T,1024] = h0[B*T,512] W_ih^T (one direction).
+    time-batched layer-1 LSTM input projection of both directions, gates[B*T,2048] = h0[B*T,512] W_ih^T.
     Extra entries: the fused NIG head+loss kernels at a size where HBM traffic dominates (north-star target: fraction
     of HBM peak) and the persistent LSTM recurrence (latency-bound: us per step)."""
     B, T, H = TRAIN_B, TA, 256
-    M, N, K = B * T, 4 * H, 2 * H
-    nbuf = 3   # 3 x (79 MB A + 315 MB C) > 126 MB L2
+    M, N, K = B * T, 8 * H, 2 * H     # both directions in one contraction: pre[T*B, 2*4H] = h0[T*B, 512] W_ih^T
+    nbuf = 3   # 3 x (79 MB A + 629 MB C) > 126 MB L2
     A = [(torch.randn(M, K, device=dev) * 0.5).half() for _ in range(nbuf)]
     W = (torch.randn(N, K, device=dev) * 0.05).half()
     bias = torch.randn(N, device=dev)
-    C = [torch.empty(M, 2 * N, device=dev) for _ in range(nbuf)]
+    C = [torch.empty(M, N, device=dev) for _ in range(nbuf)]
 
     def gemm_launch(i):
         j = i % nbuf
-        ops.gemm_h16(A[j], K, 0, W, K, 1, C[j], 2 * N, M, N, K, bias=bias)
+        ops.gemm_h16(A[j], K, 0, W, K, 1, C[j], N, M, N, K, bias=bias)
 
     us = _time_launches(torch, gemm_launch, 12)
     flop = 2.0 * M * N * K
     achieved = flop / (us * 1e-6) / 1e12
-    roof = {"kernel": "h16::gemm_h16_kernel<0,0> (layer-1 LSTM input projection, [76800,512]x[512,1024]^T, FP16 operands, "
-                      "fp32 accumulate/output, bias epilogue)",
-            "bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-            "frac": achieved / pk["bf16_tflops"], "traffic": None, "us_per_launch": us, "flop_per_launch": flop,
-            "algorithmic_bytes_per_launch": float(M * K * 2 + N * K * 2 + M * N * 4),
-            "peak_source": f"{pk['source']} cuBLAS bf16 burst (MEASURED_PEAKS.json)"}
+    alg_bytes = float(M * K * 2 + N * K * 2 + M * N * 4)
+    # With an fp32 output this contraction sits on the ridge of the roofline: its algorithmic traffic (A + W read once,
+    # C written once) needs slightly LONGER at the measured HBM peak than its FLOPs need at the measured bf16 peak, so
+    # the binding roof is HBM; the tensor-pipe fraction is reported next to it.
+    hbm_floor_us = alg_bytes / (pk["hbm_gbs"] * 1e3)
+    tensor_floor_us = flop / (pk["bf16_tflops"] * 1e6)
+    gbs = alg_bytes / (us * 1e-6) / 1e9
+    hbm_bound = hbm_floor_us >= tensor_floor_us
+    roof = {"kernel": "h16::gemm_h16_pair_kernel<0,0> (layer-1 LSTM input projection of both directions, "
+                      "[76800,512]x[2048,512]^T, FP16 operands, fp32 accumulate/output, bias epilogue; cta_group::2)",
+            "bound": "hbm" if hbm_bound else "tensor",
+            "achieved": gbs if hbm_bound else achieved, "peak": pk["hbm_gbs"] if hbm_bound else pk["bf16_tflops"],
+            "unit": "GB/s" if hbm_bound else "TFLOP/s",
+            "frac": (gbs / pk["hbm_gbs"]) if hbm_bound else (achieved / pk["bf16_tflops"]),
+            "traffic": NCU_TRAFFIC.get("gemm_h16_pair"), "us_per_launch": us,
+            "flop_per_launch": flop, "algorithmic_bytes_per_launch": alg_bytes,
+            "hbm_floor_us": hbm_floor_us, "tensor_floor_us": tensor_floor_us,
+            "tensor": {"achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                       "frac": achieved / pk["bf16_tflops"]},
+            "peak_source": f"{pk['source']} HBM copy bandwidth / cuBLAS bf16 burst (MEASURED_PEAKS.json)"}
+    # the other instances of the same engine in the step (small outputs: tensor-bound)
+    others = {}
+    G2, In = 8 * H, 2 * H
+    dpre16 = (torch.randn(M, G2, device=dev) * 0.05).bfloat16()
+    wb16 = (torch.randn(G2, In, device=dev) * 0.05).bfloat16()
+    xb16 = (torch.randn(M, In, device=dev) * 0.5).bfloat16()
+    dx = torch.empty(M, In, device=dev)
+    dw = torch.zeros(G2, In, device=dev)
+    t = _time_launches(torch, lambda i: ops.gemm_h16(dpre16, G2, 0, wb16, In, 0, dx, In, M, In, G2, a_bf16=True,
+                                                    b_bf16=True), 8)
+    others["dx [76800,2048]x[2048,512] (bf16)"] = {"us_per_launch": t, "achieved": 2.0 * M * In * G2 / t / 1e6,
+                                                   "unit": "TFLOP/s", "frac": 2.0 * M * In * G2 / t / 1e6 / pk["bf16_tflops"]}
+    t = _time_launches(torch, lambda i: ops.gemm_h16(dpre16, G2, 1, xb16, In, 0, dw, In, G2, In, M, a_bf16=True,
+                                                    b_bf16=True, beta=1.0), 8)
+    others["dW_ih [76800,2048]^T x [76800,512] (bf16, split-K)"] = {
+        "us_per_launch": t, "achieved": 2.0 * M * In * G2 / t / 1e6, "unit": "TFLOP/s",
+        "frac": 2.0 * M * In * G2 / t / 1e6 / pk["bf16_tflops"]}
+    roof["same_engine_other_shapes"] = others
+    del dpre16, wb16, xb16, dx, dw
     # the same contraction on the TF32 engine (operands fp32 in HBM), for reference
     A32 = torch.randn(M, K, device=dev)
     W32 = torch.randn(N, K, device=dev) * 0.05
-    us32 = _time_launches(torch, lambda i: ops.gemm(A32, K, 0, W32, K, 1, C[i % nbuf], 2 * N, M, N, K, bias=bias), 8)
+    us32 = _time_launches(torch, lambda i: ops.gemm(A32, K, 0, W32, K, 1, C[i % nbuf], N, M, N, K, bias=bias), 8)
     roof["tf32_engine_same_shape"] = {"kernel": "tc::gemm_tf32_kernel<0,0>", "us_per_launch": us32,
                                       "achieved": flop / (us32 * 1e-6) / 1e12, "unit": "TFLOP/s"}
     del A, C, A32, W32

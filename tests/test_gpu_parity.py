@@ -525,3 +525,40 @@ def test_adamw_device_step_and_lr():
         lr_ = 1.5e-4
         want = pd_ * (1 - lr_ * 1e-5) - lr_ / (1 - 0.9 ** step) * md / (vd.sqrt() / (1 - 0.999 ** step) ** 0.5 + 1e-8)
         assert float((pb.double() - want).abs().max()) <= 1e-4 * lr_ + 2.5e-7 * float(p0.abs().max())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("pair", [0, 1])
+@pytest.mark.parametrize("M,N,K,ta,tb", [(3000, 256, 512, 0, 1), (1300, 520, 200, 0, 0), (1024, 512, 9000, 1, 0),
+                                         (700, 300, 132, 1, 1), (12800, 512, 1536, 0, 1), (300, 128, 64, 0, 1)])
+def test_gemm_tf32_engines(M, N, K, ta, tb, pair):
+    """TF32 tcgen05 engines through deer_gemm: the 128x128-tile kernel and the cta_group::2 CTA-pair kernel (256x256
+    tiles), all operand majors, M/N/K tails, bias + activation and the accumulating (beta = 1, split-K) epilogue."""
+    from deer_b200 import _lib
+    _lib.set_option(6, pair)
+    try:
+        g = torch.Generator().manual_seed(M + N + K)
+        lda = ((M if ta else K) + 3) // 4 * 4
+        ldb = ((K if tb else N) + 3) // 4 * 4
+        A = torch.zeros((K if ta else M), lda)
+        sc = 1.5 * K ** -0.25      # pre-activations of order 1 (a saturated tanh would hide / amplify nothing useful)
+        A[:, :(M if ta else K)] = torch.randn((K if ta else M), (M if ta else K), generator=g) * sc
+        Bm = torch.zeros((N if tb else K), ldb)
+        Bm[:, :(K if tb else N)] = torch.randn((N if tb else K), (K if tb else N), generator=g) * sc
+        opA = (A[:, :M].t() if ta else A[:, :K]).double()
+        opB = (Bm[:, :K].t() if tb else Bm[:, :N]).double()
+        ref = opA @ opB
+        bias = torch.randn(N, generator=g)
+        C0 = torch.randn(M, N, generator=g)
+        ldc = (N + 3) // 4 * 4
+        for act, beta in ((0, 0.0), (2, 0.0), (0, 1.0)):
+            C = torch.zeros(M, ldc, device=DEV)
+            C[:, :N] = cu(C0)
+            use_bias = bias if N % 4 == 0 else None
+            ops.gemm(cu(A), lda, ta, cu(Bm), ldb, tb, C, ldc, M, N, K, bias=None if use_bias is None else cu(use_bias),
+                     act=act, beta=beta, engine=ops.ENGINE_TF32)
+            r = ref + (0 if use_bias is None else use_bias.double()) + beta * C0.double()
+            r = torch.tanh(r) if act == 2 else r
+            assert_close(C[:, :N], r, 1e-3, f"tf32 pair={pair} act={act} beta={beta}")
+    finally:
+        _lib.set_option(6, 1)

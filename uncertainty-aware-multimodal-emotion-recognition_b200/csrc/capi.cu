@@ -24,6 +24,11 @@ int gemm_tcgen05(const float* A, long long lda, int transA, const float* B, long
                  long long sB, long long sC, long long sBias, cudaStream_t stream);
 extern int g_small_engine;
 extern int g_h16_pair;
+extern int g_tf32_pair;
+bool gemm_tf32_pair_supported(int transA, int transB, int M, int N, int K, long long ldc, const float* bias, int act,
+                              float beta);
+int gemm_tf32_pair(const float* A, long long lda, int transA, const float* B, long long ldb, int transB, float* C,
+                   long long ldc, int M, int N, int K, const float* bias, int act, float beta, cudaStream_t stream);
 void gemm_tcgen05_set_round(int on);
 void lstm_cluster_set_option(int ts, int tile);
 void lstm_cluster_set_profile(long long* buf);
@@ -57,6 +62,9 @@ int deer_set_option(int option, int value) {
     case DEER_OPT_LSTM_TILE:
       lstm_cluster_set_option(-1, value);
       return DEER_OK;
+    case DEER_OPT_TF32_PAIR:
+      g_tf32_pair = value ? 1 : 0;
+      return DEER_OK;
     case DEER_OPT_H16_PAIR:
       g_h16_pair = value ? 1 : 0;
       return DEER_OK;
@@ -86,6 +94,8 @@ int deer_gemm(const float* A, long long lda, int transA, const float* B, long lo
               lda, ldb);
     return DEER_ERR_UNSUPPORTED;
   }
+  if (ok && gemm_tf32_pair_supported(transA, transB, M, N, K, ldc, bias, act, beta))
+    return gemm_tf32_pair(A, lda, transA, B, ldb, transB, C, ldc, M, N, K, bias, act, beta, st);
   if (ok)
     return gemm_tcgen05(A, lda, transA, B, ldb, transB, C, ldc, M, N, K, bias, act, beta, batch, sA, sB, sC, sBias, st);
   return gemm_simt(A, lda, transA, B, ldb, transB, C, ldc, M, N, K, bias, act, beta, batch, sA, sB, sC, sBias, st);

@@ -315,14 +315,23 @@ constexpr int P_STAGE_BYTES = A_BYTES + PB_BYTES;      // 32 KB
 constexpr int P_SMEM_BYTES = P_STAGES * P_STAGE_BYTES + P_STAGING_BYTES + 256 + 1024;
 constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;        // shared::cluster address of the same offset in the even CTA
 
-__device__ __forceinline__ void umma_16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                             uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
+template <int ELEM>
+__device__ __forceinline__ void umma_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  if (ELEM == 2)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
 }
 __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
   asm volatile(
@@ -374,7 +383,10 @@ __device__ __forceinline__ void red_add_v2(float* p, float a, float b) {
   asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
 }
 
-template <bool A_MN, bool B_MN>
+// ELEM = operand element size: 2 (FP16 / BF16, kind::f16, 64-element k-blocks) or 4 (fp32 read as TF32, kind::tf32,
+// 32-element k-blocks).  In BYTES both look the same to the pipeline (128-byte swizzle rows, 32 bytes of K per MMA);
+// only the MN-major box geometry differs (TF32 needs the 32-byte-atom swizzle: 32x32 boxes instead of 64x64).
+template <int ELEM, bool A_MN, bool B_MN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
     gemm_h16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const __grid_constant__ CUtensorMap tmap_c, const Params p) {
@@ -390,7 +402,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
-  const int total_kb = (p.K + BK - 1) / BK;
+  constexpr int BKE = 128 / ELEM;                  // k elements per block (one 128-byte swizzle row)
+  constexpr int MNB = BKE;                         // MN-major box: MNB mn-elements x BKE k-rows
+  constexpr int MNB_BYTES = MNB * 128;             // 8 KB (16-bit) / 4 KB (TF32)
+  constexpr int MN_KSTEP = (ELEM == 2 ? 16 : 8) * 128;   // bytes per MMA K step in an MN-major panel
+  constexpr int MN_SBO = ELEM == 2 ? 1024 : 512;
+  constexpr int MN_LAYOUT = ELEM == 2 ? 2 : 1;
+  const int total_kb = (p.K + BKE - 1) / BKE;
   const int total_work = p.tiles_m * p.tiles_n * p.splits;   // tiles_m counts 256-row pair tiles here
 
   if (threadIdx.x == 0) {
@@ -437,21 +455,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
         if (leader) {
           uint8_t* sa = smem + s * P_STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
-          const int k0 = (kb0 + i) * BK;
+          const int k0 = (kb0 + i) * BKE;
           if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * P_STAGE_BYTES);   // both CTAs' bytes land on this barrier
           if (!A_MN) {
-            tma_load_2d_pair(sa, &tmap_a, &full_bar[s], k0, mr);            // box {64 k, 128 rows}
+            tma_load_2d_pair(sa, &tmap_a, &full_bar[s], k0, mr);            // box {BKE k, 128 rows}
           } else {
 #pragma unroll
-            for (int j = 0; j < BM / 64; j++)                                // box {64 m, 64 k} x2
-              tma_load_2d_pair(sa + j * 8192, &tmap_a, &full_bar[s], mr + 64 * j, k0);
+            for (int j = 0; j < BM / MNB; j++)                               // boxes {MNB m, BKE k}
+              tma_load_2d_pair(sa + j * MNB_BYTES, &tmap_a, &full_bar[s], mr + MNB * j, k0);
           }
           if (!B_MN) {
-            tma_load_2d_pair(sb, &tmap_b, &full_bar[s], k0, nr);            // box {64 k, 128 rows}
+            tma_load_2d_pair(sb, &tmap_b, &full_bar[s], k0, nr);            // box {BKE k, 128 rows}
           } else {
 #pragma unroll
-            for (int j = 0; j < BN / 128; j++)                               // box {64 n, 64 k} x2
-              tma_load_2d_pair(sb + j * 8192, &tmap_b, &full_bar[s], nr + 64 * j, k0);
+            for (int j = 0; j < (BN / 2) / MNB; j++)                         // boxes {MNB n, BKE k}
+              tma_load_2d_pair(sb + j * MNB_BYTES, &tmap_b, &full_bar[s], nr + MNB * j, k0);
           }
         }
         __syncwarp();
@@ -479,9 +497,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
           if (leader) {
 #pragma unroll
             for (int k = 0; k < BK / UK; k++) {
-              const uint64_t ad = A_MN ? make_smem_desc(sa + k * 2048, 8192, 1024, 2) : make_smem_desc(sa + k * 32, 16, 1024, 2);
-              const uint64_t bd = B_MN ? make_smem_desc(sb + k * 2048, 8192, 1024, 2) : make_smem_desc(sb + k * 32, 16, 1024, 2);
-              umma_16_pair(tb + acc * BN, ad, bd, p.idesc, (i > 0 || k > 0) ? 1u : 0u);
+              const uint64_t ad = A_MN ? make_smem_desc(sa + k * MN_KSTEP, MNB_BYTES, MN_SBO, MN_LAYOUT)
+                                       : make_smem_desc(sa + k * 32, 16, 1024, 2);
+              const uint64_t bd = B_MN ? make_smem_desc(sb + k * MN_KSTEP, MNB_BYTES, MN_SBO, MN_LAYOUT)
+                                       : make_smem_desc(sb + k * 32, 16, 1024, 2);
+              umma_pair<ELEM>(tb + acc * BN, ad, bd, p.idesc, (i > 0 || k > 0) ? 1u : 0u);
             }
             umma_commit_pair(&empty_bar[s]);
             if (i == nkb - 1) umma_commit_pair(&tmem_full[acc]);
@@ -718,12 +738,12 @@ int gemm_h16(const void* A, long long lda, int transA, int a_bf, const void* B, 
   do {                                                                                                               \
     static bool attr = false;                                                                                        \
     if (!attr) {                                                                                                     \
-      cudaError_t e = cudaFuncSetAttribute(gemm_h16_pair_kernel<AM, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+      cudaError_t e = cudaFuncSetAttribute(gemm_h16_pair_kernel<2, AM, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                            P_SMEM_BYTES);                                                            \
       if (e != cudaSuccess) return cuda_status(e, "gemm_h16 pair smem attribute");                                   \
       attr = true;                                                                                                   \
     }                                                                                                                \
-    DEER_LAUNCH((gemm_h16_pair_kernel<AM, BMN>), 2 * clusters, NUM_THREADS, P_SMEM_BYTES, stream, ma, mb, mc, p);    \
+    DEER_LAUNCH((gemm_h16_pair_kernel<2, AM, BMN>), 2 * clusters, NUM_THREADS, P_SMEM_BYTES, stream, ma, mb, mc, p);    \
   } while (0)
     if (!transA && transB) DEER_H16_PAIR_GO(false, false);
     else if (!transA && !transB) DEER_H16_PAIR_GO(false, true);
@@ -749,6 +769,75 @@ int gemm_h16(const void* A, long long lda, int transA, int a_bf, const void* B, 
   else if (transA && transB) DEER_H16_GO(true, false);
   else DEER_H16_GO(true, true);
 #undef DEER_H16_GO
+  return DEER_OK;
+}
+
+// ------------------------------------------------------------------------------------------------- TF32 on CTA pairs
+// Same kernel with fp32 operands read as TF32 (ELEM = 4): the 128x128-tile TF32 engine (gemm_tcgen05.cu) is bound by
+// shared-memory / L2 operand traffic; 256x256 pair tiles move a quarter of the operand bytes per FLOP and CTA.
+int g_tf32_pair = 1;   // deer_set_option(DEER_OPT_TF32_PAIR)
+bool gemm_tf32_pair_supported(int transA, int transB, int M, int N, int K, long long ldc, const float* bias, int act,
+                              float beta) {
+  (void)transA; (void)transB;
+  if (!g_tf32_pair) return false;
+  if (M <= 256 || N < 128 || K < 64) return false;                    // too small to feed 74 CTA pairs
+  if ((N & 3) || (ldc & 3)) return false;
+  if (bias && (reinterpret_cast<uintptr_t>(bias) & 15)) return false;
+  if (beta != 0.f && act != DEER_ACT_NONE) return false;
+  return true;
+}
+int gemm_tf32_pair(const float* A, long long lda, int transA, const float* B, long long ldb, int transB, float* C,
+                   long long ldc, int M, int N, int K, const float* bias, int act, float beta, cudaStream_t stream) {
+  using namespace h16;
+  constexpr int BKE = 32;
+  CUtensorMap ma, mb, mc;
+  bool ok = make_map_c(&mc, C, M, N, ldc);
+  if (!transA) ok = ok && tc::make_map(&ma, A, M, K, lda, BKE, BM, false);          // stored [M,K]: K-major
+  else ok = ok && tc::make_map(&ma, A, K, M, lda, 32, BKE, true);                    // stored [K,M]: MN-major
+  if (transB) ok = ok && tc::make_map(&mb, B, N, K, ldb, BKE, BN / 2, false);       // stored [N,K]: K-major, half tile
+  else ok = ok && tc::make_map(&mb, B, K, N, ldb, 32, BKE, true);                    // stored [K,N]: MN-major
+  if (!ok) {
+    set_error("gemm_tf32_pair: cuTensorMapEncodeTiled failed (M=%d N=%d K=%d lda=%lld ldb=%lld)", M, N, K, lda, ldb);
+    return DEER_ERR_UNSUPPORTED;
+  }
+  const int tiles_m = (M + 2 * BM - 1) / (2 * BM), tiles_n = (N + BN - 1) / BN;
+  const int total_kb = (K + BKE - 1) / BKE;
+  int splits = 1;
+  if (beta == 1.f && act == DEER_ACT_NONE) {
+    const int tiles = tiles_m * tiles_n;
+    const int units = kNumSMs / 2;
+    if (tiles < units && total_kb >= 64) {
+      splits = (2 * units + tiles - 1) / tiles;
+      const int max_splits = total_kb / 16;
+      if (splits > max_splits) splits = max_splits;
+      if (splits < 1) splits = 1;
+    }
+  }
+  int per = (total_kb + splits - 1) / splits;
+  splits = (total_kb + per - 1) / per;
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(transA ? 1 : 0) << 15) |
+                         ((uint32_t)(transB ? 0 : 1) << 16) | ((uint32_t)(BN >> 3) << 17) |
+                         ((uint32_t)((2 * BM) >> 4) << 24);
+  Params p{C, ldc, nullptr, 0, 0, bias, M, N, K, act, beta, splits, per, tiles_m, tiles_n, idesc, nullptr,
+           getenv("DEER_H16_DEBUG") ? atoi(getenv("DEER_H16_DEBUG")) : 0};
+  const int work = tiles_m * tiles_n * splits;
+  const int clusters = work < kNumSMs / 2 ? work : kNumSMs / 2;
+#define DEER_TF32_PAIR_GO(AM, BMN)                                                                                  \
+  do {                                                                                                              \
+    static bool attr = false;                                                                                       \
+    if (!attr) {                                                                                                    \
+      cudaError_t e = cudaFuncSetAttribute(gemm_h16_pair_kernel<4, AM, BMN>,                                        \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES);              \
+      if (e != cudaSuccess) return cuda_status(e, "gemm_tf32_pair smem attribute");                                 \
+      attr = true;                                                                                                  \
+    }                                                                                                               \
+    DEER_LAUNCH((gemm_h16_pair_kernel<4, AM, BMN>), 2 * clusters, NUM_THREADS, P_SMEM_BYTES, stream, ma, mb, mc, p); \
+  } while (0)
+  if (!transA && transB) DEER_TF32_PAIR_GO(false, false);
+  else if (!transA && !transB) DEER_TF32_PAIR_GO(false, true);
+  else if (transA && transB) DEER_TF32_PAIR_GO(true, false);
+  else DEER_TF32_PAIR_GO(true, true);
+#undef DEER_TF32_PAIR_GO
   return DEER_OK;
 }
 
