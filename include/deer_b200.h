@@ -102,6 +102,10 @@ int deer_layernorm_bwd(const float* dy, const float* x, const float* gamma, cons
  *      CUDA graph draws a fresh mask on every replay. */
 int deer_dropout(const float* x, float* y, long long n, float p, unsigned long long seed, unsigned long long offset,
                  const unsigned long long* step_ptr, void* stream);
+/*      the same mask (same seed / offset / step) applied while casting to the 16-bit GEMM operands of the next LSTM layer
+ *      (nn.LSTM inter-layer dropout, encoders.py:82-89): y_fp16 and/or y_bf16 [n], n % 4 == 0; p == 0 is a plain cast */
+int deer_dropout_cast16(const float* x, void* y_fp16, void* y_bf16, long long n, float p, unsigned long long seed,
+                        unsigned long long offset, const unsigned long long* step_ptr, void* stream);
 
 /* ---- attention pooling over time (encoders.py:93-98,383-384; :462-467,543-544; :597-602,738-746).
  *      rowdot: s[m] = sum_j h[m,j]*w[j] + b[0]   (the Linear(D/2 -> 1) scorer head) */

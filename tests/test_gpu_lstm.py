@@ -109,3 +109,36 @@ def test_persistent_full_length_vs_oracle():
     r = O.lstm_direction(x.double(), *wd[4:], True)
     ref = torch.cat([f, r], dim=-1).permute(1, 0, 2)
     assert_close(h, ref, 1e-3, "h vs oracle")
+
+
+@pytest.mark.gpu
+def test_fused_interlayer_dropout_matches_separate_kernel():
+    """nn.LSTM inter-layer dropout fused into the layer-1 operand casts (and into dx) draws the same Philox mask as the
+    stand-alone dropout kernel: identical outputs and gradients."""
+    import deer_b200
+    from deer_b200 import ops
+    torch.manual_seed(0)
+    enc = deer_b200.EnhancedAudioEncoder({"dropout": 0.3}).cuda().train()
+    x = torch.randn(32, 24, 84, device="cuda")
+    res = []
+    for fused in (True, False):
+        ops.set_fuse_lstm_dropout(fused)
+        try:
+            ops.manual_seed(123)
+            ops.begin_step()
+            for p in enc.parameters():
+                p.grad = None
+            xi = x.clone().requires_grad_(True)
+            h = enc.lstm_forward(xi)
+            (h * torch.linspace(-1, 1, h.numel(), device="cuda").view_as(h)).sum().backward()
+            res.append((h.detach().clone(), xi.grad.clone(), enc.lstm.weight_ih_l1.grad.clone(),
+                        enc.lstm.weight_hh_l0.grad.clone()))
+        finally:
+            ops.set_fuse_lstm_dropout(True)
+    for a, b in zip(*res):
+        assert torch.equal(a, b) or float((a - b).abs().max()) <= 1e-6 * float(b.abs().max())
+    # and dropout is really applied: eval-mode output differs
+    enc.eval()
+    with torch.no_grad():
+        h_eval = enc.lstm_forward(x)
+    assert float((h_eval - res[0][0]).abs().max()) > 1e-3

@@ -32,6 +32,7 @@ _PROTOS = {
     "deer_layernorm_fwd": [P, P, P, P, P, P, I, I, F, P],
     "deer_layernorm_bwd": [P, P, P, P, P, P, P, P, I, I, P],
     "deer_dropout": [P, P, L, F, U, U, P, P],
+    "deer_dropout_cast16": [P, P, P, L, F, U, U, P, P],
     "deer_rowdot_fwd": [P, P, P, P, L, I, P],
     "deer_rowdot_bwd": [P, P, P, P, P, P, L, I, P],
     "deer_attn_pool_fwd": [P, L, L, P, L, L, P, P, P, I, I, I, P],

@@ -1,6 +1,9 @@
 // Memory-bound helpers: activation backward + bias gradient, dropout, scorer dot, layout moves, small combiners.
 // All are streaming kernels: coalesced along the innermost dimension, float4 where the shape allows,
 // grids sized from the data (>= 2 waves of 148 SMs at the benchmark shapes).
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace deer {
@@ -53,19 +56,69 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
 __global__ void __launch_bounds__(256) dropout_kernel(const float* __restrict__ x, float* __restrict__ y, long long n,
                                                       float p, float scale, unsigned long long seed,
                                                       unsigned long long offset,
-                                                      const unsigned long long* __restrict__ step_ptr) {
-  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // group of 4 elements
-  const long long i = q * 4;
-  if (i >= n) return;
-  const unsigned long long c = (unsigned long long)q + offset;
+                                                      const unsigned long long* __restrict__ step_ptr, int vec) {
   const unsigned long long st = step_ptr ? *step_ptr : 0ull;  // device-side step counter: new mask per graph replay
-  const uint4 r = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)st, (uint32_t)(st >> 32)),
-                                make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-  const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
   const uint32_t thr = (uint32_t)fminf(p * 4294967296.f, 4294967040.f);
+  const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+  const long long groups = (n + 3) >> 2;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < groups;
+       q += (long long)gridDim.x * blockDim.x) {  // group of 4 elements = one Philox block
+    const long long i = q * 4;
+    const unsigned long long c = (unsigned long long)q + offset;
+    const uint4 r = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)st, (uint32_t)(st >> 32)), key);
+    if (vec && i + 3 < n) {  // 16-byte aligned buffers: one 128-bit load and store per Philox block
+      const float4 v = __ldcs(reinterpret_cast<const float4*>(x + i));
+      float4 o;
+      o.x = r.x >= thr ? v.x * scale : 0.f;
+      o.y = r.y >= thr ? v.y * scale : 0.f;
+      o.z = r.z >= thr ? v.z * scale : 0.f;
+      o.w = r.w >= thr ? v.w * scale : 0.f;
+      __stcs(reinterpret_cast<float4*>(y + i), o);
+    } else {
+      const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
-  for (int j = 0; j < 4; j++)
-    if (i + j < n) y[i + j] = rr[j] >= thr ? x[i + j] * scale : 0.f;
+      for (int j = 0; j < 4; j++)
+        if (i + j < n) y[i + j] = rr[j] >= thr ? x[i + j] * scale : 0.f;
+    }
+  }
+}
+
+// dropout of a row-major fp32 matrix fused with its 16-bit casts: the LSTM layer-1 input is consumed only as FP16
+// (input projection) and BF16 (dW_ih) GEMM operands, so the dropped fp32 tensor is never materialised.
+// Same Philox stream as dropout_kernel over the flattened [rows, cols] index (cols % 4 == 0).
+__global__ void __launch_bounds__(256) dropout_cast16_kernel(const float* __restrict__ x, uint16_t* __restrict__ y_h,
+                                                             uint16_t* __restrict__ y_b, long long n, float p,
+                                                             float scale, unsigned long long seed,
+                                                             unsigned long long offset,
+                                                             const unsigned long long* __restrict__ step_ptr) {
+  const unsigned long long st = step_ptr ? *step_ptr : 0ull;
+  const uint32_t thr = (uint32_t)fminf(p * 4294967296.f, 4294967040.f);
+  const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+  const long long groups = n >> 2;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < groups;
+       q += (long long)gridDim.x * blockDim.x) {
+    const long long i = q * 4;
+    float4 v = __ldcs(reinterpret_cast<const float4*>(x + i));
+    if (p > 0.f) {
+      const unsigned long long c = (unsigned long long)q + offset;
+      const uint4 r =
+          philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)st, (uint32_t)(st >> 32)), key);
+      v.x = r.x >= thr ? v.x * scale : 0.f;
+      v.y = r.y >= thr ? v.y * scale : 0.f;
+      v.z = r.z >= thr ? v.z * scale : 0.f;
+      v.w = r.w >= thr ? v.w * scale : 0.f;
+    }
+    if (y_h) {
+      __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+      uint2 o = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+      *reinterpret_cast<uint2*>(y_h + i) = o;
+    }
+    if (y_b) {
+      __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+      uint2 o = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+      *reinterpret_cast<uint2*>(y_b + i) = o;
+    }
+  }
 }
 
 // ------------------------------------------------------------------ scorer head: s[m] = h[m,:].w + b
@@ -382,12 +435,31 @@ int deer_bias_act_bwd(const float* dy, long long ld_dy, const float* y, long lon
   return DEER_OK;
 }
 
+static int dropout_grid(long long groups) {
+  long long g = cdiv(groups, 256);
+  const long long cap = (long long)kNumSMs * 16;
+  if (g > cap) g = cap;
+  return (int)(g < 1 ? 1 : g);
+}
+
 int deer_dropout(const float* x, float* y, long long n, float p, unsigned long long seed, unsigned long long offset,
                  const unsigned long long* step_ptr, void* stream) {
   DEER_CHECK_ARG(x && y && n > 0 && p >= 0.f && p < 1.f, "dropout: bad args");
   const long long groups = cdiv(n, 4);
-  DEER_LAUNCH(dropout_kernel, (unsigned)cdiv(groups, 256), 256, 0, stream, x, y, n, p, 1.f / (1.f - p), seed, offset,
-              step_ptr);
+  const int vec = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+  DEER_LAUNCH(dropout_kernel, dropout_grid(groups), 256, 0, stream, x, y, n, p, 1.f / (1.f - p), seed, offset, step_ptr,
+              vec);
+  return DEER_OK;
+}
+
+int deer_dropout_cast16(const float* x, void* y_fp16, void* y_bf16, long long n, float p, unsigned long long seed,
+                        unsigned long long offset, const unsigned long long* step_ptr, void* stream) {
+  DEER_CHECK_ARG(x && (y_fp16 || y_bf16) && n > 0 && (n & 3) == 0 && p >= 0.f && p < 1.f, "dropout_cast16: bad args");
+  DEER_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y_fp16) & 7) == 0 &&
+                     (reinterpret_cast<uintptr_t>(y_bf16) & 7) == 0,
+                 "dropout_cast16: alignment");
+  DEER_LAUNCH(dropout_cast16_kernel, dropout_grid(n >> 2), 256, 0, stream, x, reinterpret_cast<uint16_t*>(y_fp16),
+              reinterpret_cast<uint16_t*>(y_bf16), n, p, 1.f / (1.f - p), seed, offset, step_ptr);
   return DEER_OK;
 }
 

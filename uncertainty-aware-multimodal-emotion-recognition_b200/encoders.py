@@ -71,9 +71,9 @@ class EnhancedAudioEncoder(nn.Module):
         """[B,T,84] -> time-major LSTM output [T,B,hidden_dim]."""
         h = ops.to_time_major(features)
         for l in range(self.num_layers):
-            h = ops.bilstm_layer(h, *self._layer_weights(l))
-            if l < self.num_layers - 1:
-                h = ops.dropout(h, self.dropout, self.training)
+            # nn.LSTM(dropout=p): dropout on the OUTPUT of every layer but the last == on the input of layers >= 1
+            h = ops.bilstm_layer(h, *self._layer_weights(l), input_dropout=self.dropout if l > 0 else 0.0,
+                                 training=self.training)
         return h
 
     def forward(self, audio_input: torch.Tensor) -> torch.Tensor:

@@ -24,7 +24,12 @@ ENGINE_AUTO, ENGINE_SIMT, ENGINE_TF32 = 0, 1, 2
 # prone) outputs feed the bias / scorer gradients whose per-tensor cosine otherwise sits at 0.9992, too close to the
 # 0.999 gate (tools/precision_probe.py).
 _state = {"engine": ENGINE_AUTO, "lstm_engine": ENGINE_AUTO, "exact_small_fwd": True, "exact_small_bwd": True,
-          "small_rows": 8192, "direct_grad": False, "lstm_gemm16": True}
+          "small_rows": 8192, "direct_grad": False, "lstm_gemm16": True, "fuse_lstm_dropout": True}
+
+
+def set_fuse_lstm_dropout(on: bool):
+    """Inter-layer LSTM dropout fused into the next layer's 16-bit operand casts (default) or run as its own kernel."""
+    _state["fuse_lstm_dropout"] = bool(on)
 
 
 def set_lstm_gemm16(on: bool):
@@ -499,10 +504,13 @@ class _BiLSTMLayerCluster(torch.autograd.Function):
     The five time-batched contractions of the layer (input projection, dx, dW_ih, dW_hh x2 directions) run on the
     16-bit tcgen05 engine (deer_gemm_h16): forward operands FP16 (same 11 significant bits as TF32 for these value
     ranges), backward operands BF16.  The LSTM kernels write the 16-bit shadows of h and dpre themselves; x and the
-    weights are cast once per call."""
+    weights are cast once per call.
+
+    `drop` = (p, seed, offset) or None: nn.LSTM's inter-layer dropout on this layer's INPUT, fused into the 16-bit
+    casts (the dropped fp32 tensor is never materialised) and into dx in backward."""
 
     @staticmethod
-    def forward(ctx, x, wif, whf, bif, bhf, wir, whr, bir, bhr):
+    def forward(ctx, x, wif, whf, bif, bhf, wir, whr, bir, bhr, drop=None):
         x = _req(x, "x").contiguous()
         T, B, In = x.shape
         H = whf.shape[1]
@@ -520,8 +528,17 @@ class _BiLSTMLayerCluster(torch.autograd.Function):
         pre = torch.empty((T, B, 2, G), device=dev, dtype=torch.float32)
         M = T * B
         x16 = None
+        if drop is not None and not (use16 and In % 8 == 0):
+            raise _lib.DeerError("deer_b200: fused input dropout needs the 16-bit GEMM path and In % 8 == 0")
+        ctx.drop = drop
+        ctx.drop_step = _dropout_state["step"]
         if use16:
-            x16 = cast16(x)                                   # [M, Kp] fp16
+            if drop is not None:                              # dropout + fp16 cast in one pass over x
+                x16 = torch.empty((M, In), device=dev, dtype=torch.float16)
+                call("deer_dropout_cast16", ptr(x), x16.data_ptr(), None, M * In, float(drop[0]), drop[1], drop[2],
+                     ptr(ctx.drop_step))
+            else:
+                x16 = cast16(x)                               # [M, Kp] fp16
             Kp = x16.shape[1]
             w16 = cast16(wi_il.view(2 * G, In))               # [2G, Kp] fp16
             # both directions in ONE contraction: pre[M, 2G] = x16 [M, Kp] . w16[2G, Kp]^T (full 8 KB output rows)
@@ -565,14 +582,23 @@ class _BiLSTMLayerCluster(torch.autograd.Function):
         call("deer_lstm_cluster_bwd", ptr(gact), ptr(c_blk), ptr(dh), ptr(whf), ptr(whr), ptr(dpre), ptr(db_il),
              None if dpre16 is None else dpre16.data_ptr(), T, B, H)
         dx = None
+        drop = ctx.drop
         if use16:
-            xb16 = cast16(x, bf16=True)                        # [M, Kp] bf16: B operand of dW_ih (MN-major)
+            if drop is not None:                               # the same mask, regenerated while casting to bf16
+                xb16 = torch.empty((M, In), device=dev, dtype=torch.bfloat16)
+                call("deer_dropout_cast16", ptr(x), None, xb16.data_ptr(), M * In, float(drop[0]), drop[1], drop[2],
+                     ptr(ctx.drop_step))
+            else:
+                xb16 = cast16(x, bf16=True)                    # [M, Kp] bf16: B operand of dW_ih (MN-major)
             Kp = xb16.shape[1]
             if ctx.needs_input_grad[0]:
                 wb16 = cast16(wi_il.view(2 * G, In), bf16=True)   # [2G, Kp] bf16: B operand of dx (MN-major [K=G, N=In])
                 dx = torch.empty((T, B, In), device=dev, dtype=torch.float32)
                 # dx = dpre16 [M, 2G] . wb16 [2G, In]: the sum over the two directions is the K = 2G contraction itself
                 gemm_h16(dpre16, 2 * G, 0, wb16, Kp, 0, dx, In, M, In, 2 * G, a_bf16=True, b_bf16=True, beta=0.0)
+                if drop is not None:                           # d/dx of the input dropout, in place
+                    call("deer_dropout", ptr(dx), ptr(dx), dx.numel(), float(drop[0]), drop[1], drop[2],
+                         ptr(ctx.drop_step))
         elif ctx.needs_input_grad[0]:
             dx = torch.empty((T, B, In), device=dev, dtype=torch.float32)
             for d in range(2):
@@ -617,13 +643,26 @@ class _BiLSTMLayerCluster(torch.autograd.Function):
                 dbs.append(None if direct else tgt)
             out.append((None if dwi_direct else dwi, None if dwh_direct else dwh, dbs[0], dbs[1]))
         (dwif, dwhf, dbif, dbhf), (dwir, dwhr, dbir, dbhr) = out
-        return dx, dwif, dwhf, dbif, dbhf, dwir, dwhr, dbir, dbhr
+        return dx, dwif, dwhf, dbif, dbhf, dwir, dwhr, dbir, dbhr, None
 
 
-def bilstm_layer(x_tm, wif, whf, bif, bhf, wir, whr, bir, bhr):
-    """engine AUTO/TF32: persistent cluster kernels when H == 256; SIMT: exact-fp32 stepwise; others: see lstm.cu."""
-    if _state["lstm_engine"] in (ENGINE_AUTO, ENGINE_TF32) and whf.shape[1] == 256:
-        return _BiLSTMLayerCluster.apply(x_tm, wif, whf, bif, bhf, wir, whr, bir, bhr)
+def bilstm_layer(x_tm, wif, whf, bif, bhf, wir, whr, bir, bhr, input_dropout: float = 0.0, training: bool = False):
+    """engine AUTO/TF32: persistent cluster kernels when H == 256; SIMT: exact-fp32 stepwise; others: see lstm.cu.
+    `input_dropout` (with `training`) applies nn.LSTM's inter-layer dropout to x_tm: fused into the layer's 16-bit
+    operand casts on the cluster path, a separate kernel otherwise."""
+    cluster = _state["lstm_engine"] in (ENGINE_AUTO, ENGINE_TF32) and whf.shape[1] == 256
+    drop = None
+    if training and input_dropout > 0.0:
+        fusable = (cluster and _state["fuse_lstm_dropout"] and _state["lstm_gemm16"] and
+                   _state["engine"] == ENGINE_AUTO and x_tm.shape[-1] % 8 == 0)
+        if fusable:
+            off = _dropout_state["offset"]
+            _dropout_state["offset"] = off + (x_tm.numel() + 3) // 4
+            drop = (float(input_dropout), _dropout_state["seed"], off)
+        else:
+            x_tm = dropout(x_tm, input_dropout, True)
+    if cluster:
+        return _BiLSTMLayerCluster.apply(x_tm, wif, whf, bif, bhf, wir, whr, bir, bhr, drop)
     return _BiLSTMLayer.apply(x_tm, wif, whf, bif, bhf, wir, whr, bir, bhr)
 
 
