@@ -6,6 +6,8 @@
 namespace deer {
 
 std::atomic<long long> g_launches{0};
+int g_pdl = 0;   // measured: PDL made the B=1024 inference 10 % slower and the train step 2 % slower (early-resident
+                 // dependents compete for SM slots); kept as an ablation switch
 static thread_local char g_err[512] = "";
 
 void set_error(const char* fmt, ...) {
@@ -61,6 +63,9 @@ int deer_set_option(int option, int value) {
       return DEER_OK;
     case DEER_OPT_LSTM_TILE:
       lstm_cluster_set_option(-1, value);
+      return DEER_OK;
+    case DEER_OPT_PDL:
+      g_pdl = value ? 1 : 0;
       return DEER_OK;
     case DEER_OPT_TF32_PAIR:
       g_tf32_pair = value ? 1 : 0;

@@ -26,13 +26,43 @@ inline int cuda_status(cudaError_t e, const char* what) {
     }                                               \
   } while (0)
 
+// Programmatic dependent launch: every kernel of the library starts with DEER_PDL_ENTRY() -- it lets the NEXT kernel in
+// the stream be scheduled as soon as all CTAs of this one are resident (launch latency, block scheduling, barrier /
+// TMEM / tensormap prologues overlap this kernel's tail) and then waits until every kernel it depends on has completed
+// and flushed its memory.  Nothing may touch global memory before the wait.  A step is ~300 dependent launches, most
+// of them a few microseconds long, so the kernel-to-kernel gap is a first-order cost.
+#define DEER_PDL_ENTRY()                                         \
+  do {                                                           \
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); \
+    asm volatile("griddepcontrol.wait;" ::: "memory");           \
+  } while (0)
+
+extern int g_pdl;  // deer_set_option(DEER_OPT_PDL): 1 = launch with programmatic stream serialization (default 0)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                 Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // Count + launch + report (no synchronisation: errors here are launch-configuration errors).
-#define DEER_LAUNCH(kernel, grid, block, smem, stream, ...)                  \
-  do {                                                                       \
-    kernel<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__); \
-    deer::g_launches.fetch_add(1, std::memory_order_relaxed);                \
-    cudaError_t _e = cudaGetLastError();                                     \
-    if (_e != cudaSuccess) return deer::cuda_status(_e, #kernel);            \
+#define DEER_LAUNCH(kernel, grid, block, smem, stream, ...)                                              \
+  do {                                                                                                   \
+    cudaError_t _e = deer::launch_kernel(kernel, dim3(grid), dim3(block), (size_t)(smem),                \
+                                         (cudaStream_t)(stream), __VA_ARGS__);                           \
+    deer::g_launches.fetch_add(1, std::memory_order_relaxed);                                            \
+    if (_e == cudaSuccess) _e = cudaGetLastError();                                                      \
+    if (_e != cudaSuccess) return deer::cuda_status(_e, #kernel);                                        \
   } while (0)
 
 constexpr int kNumSMs = 148;  // B200

@@ -14,6 +14,7 @@ __global__ void __launch_bounds__(256) bias_act_bwd_kernel(const float* __restri
                                                            float* __restrict__ dz, long long ld_dz,
                                                            float* __restrict__ dbias, int M, int N, int act,
                                                            int rows_per_block) {
+  DEER_PDL_ENTRY();
   __shared__ float red[8][33];
   const int n = blockIdx.x * 32 + threadIdx.x;
   const int r0 = blockIdx.y * rows_per_block;
@@ -57,6 +58,7 @@ __global__ void __launch_bounds__(256) dropout_kernel(const float* __restrict__ 
                                                       float p, float scale, unsigned long long seed,
                                                       unsigned long long offset,
                                                       const unsigned long long* __restrict__ step_ptr, int vec) {
+  DEER_PDL_ENTRY();
   const unsigned long long st = step_ptr ? *step_ptr : 0ull;  // device-side step counter: new mask per graph replay
   const uint32_t thr = (uint32_t)fminf(p * 4294967296.f, 4294967040.f);
   const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
@@ -91,6 +93,7 @@ __global__ void __launch_bounds__(256) dropout_cast16_kernel(const float* __rest
                                                              float scale, unsigned long long seed,
                                                              unsigned long long offset,
                                                              const unsigned long long* __restrict__ step_ptr) {
+  DEER_PDL_ENTRY();
   const unsigned long long st = step_ptr ? *step_ptr : 0ull;
   const uint32_t thr = (uint32_t)fminf(p * 4294967296.f, 4294967040.f);
   const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
@@ -125,6 +128,7 @@ __global__ void __launch_bounds__(256) dropout_cast16_kernel(const float* __rest
 __global__ void __launch_bounds__(256) rowdot_fwd_kernel(const float* __restrict__ h, const float* __restrict__ w,
                                                          const float* __restrict__ b, float* __restrict__ s,
                                                          long long M, int N) {
+  DEER_PDL_ENTRY();
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
@@ -140,6 +144,7 @@ __global__ void __launch_bounds__(256) rowdot_bwd_kernel(const float* __restrict
                                                          const float* __restrict__ w, float* __restrict__ dh,
                                                          float* __restrict__ dw, float* __restrict__ db, long long M,
                                                          int N, int rows_per_block) {
+  DEER_PDL_ENTRY();
   __shared__ float red[8][33];
   const int n = blockIdx.x * 32 + threadIdx.x;
   const long long r0 = (long long)blockIdx.y * rows_per_block;
@@ -179,6 +184,7 @@ __global__ void __launch_bounds__(256) rowdot_bwd_kernel(const float* __restrict
 // y[t,b,:] = x[b,t,:]
 __global__ void __launch_bounds__(256) permute_bt_kernel(const float* __restrict__ x, float* __restrict__ y, int B,
                                                          int T, int D) {
+  DEER_PDL_ENTRY();
   const long long total = (long long)B * T * D;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -192,6 +198,7 @@ __global__ void __launch_bounds__(256) permute_bt_kernel(const float* __restrict
 
 __global__ void __launch_bounds__(256) rowscale_kernel(const float* __restrict__ x, const float* __restrict__ mask,
                                                        float* __restrict__ y, long long M, int D) {
+  DEER_PDL_ENTRY();
   const long long total = M * D;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x)
@@ -201,6 +208,7 @@ __global__ void __launch_bounds__(256) rowscale_kernel(const float* __restrict__
 // col[(b,t), k*C + c] = x[b, t+k-1, c]
 __global__ void __launch_bounds__(256) im2col3_kernel(const float* __restrict__ x, float* __restrict__ col, int B, int T,
                                                       int C) {
+  DEER_PDL_ENTRY();
   const long long total = (long long)B * T * 3 * C;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -217,6 +225,7 @@ __global__ void __launch_bounds__(256) im2col3_kernel(const float* __restrict__ 
 // dx[b,t,c] = sum_k dcol[(b,t-k+1), k*C + c]
 __global__ void __launch_bounds__(256) col2im3_kernel(const float* __restrict__ dcol, float* __restrict__ dx, int B,
                                                       int T, int C) {
+  DEER_PDL_ENTRY();
   const long long total = (long long)B * T * C;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -236,6 +245,7 @@ __global__ void __launch_bounds__(256) col2im3_kernel(const float* __restrict__ 
 // dir 0: wk[o,k,i] = w[o,i,k];  dir 1: w[o,i,k] += wk[o,k,i]
 __global__ void __launch_bounds__(256) conv3_pack_kernel(const float* __restrict__ src, float* __restrict__ dst,
                                                          int Cout, int Cin, int dir) {
+  DEER_PDL_ENTRY();
   const long long total = (long long)Cout * Cin * 3;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -256,6 +266,7 @@ __global__ void __launch_bounds__(256) conv3_pack_kernel(const float* __restrict
 // ------------------------------------------------------------------ small combiners (pooled model)
 __global__ void __launch_bounds__(256) axpby_kernel(const float* __restrict__ x1, const float* __restrict__ x2,
                                                     float* __restrict__ y, long long n, float a, float b) {
+  DEER_PDL_ENTRY();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     y[i] = a * x1[i] + (x2 ? b * x2[i] : 0.f);
 }
@@ -264,6 +275,7 @@ __global__ void __launch_bounds__(256) mix_fwd_kernel(const float* __restrict__ 
                                                       const float* __restrict__ u, long long ldu,
                                                       const float* __restrict__ s, const float* __restrict__ c,
                                                       float* __restrict__ out, long long M, int N) {
+  DEER_PDL_ENTRY();
   const long long total = M * N;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -278,6 +290,7 @@ __global__ void __launch_bounds__(256) mix_bwd_kernel(const float* __restrict__ 
                                                       float* __restrict__ dw, long long lddw, float* __restrict__ du,
                                                       long long lddu, float* __restrict__ ds, float* __restrict__ dc,
                                                       long long M, int N) {
+  DEER_PDL_ENTRY();
   const long long m = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (m >= M) return;
@@ -302,6 +315,7 @@ __global__ void __launch_bounds__(256) mix_bwd_kernel(const float* __restrict__ 
 __global__ void __launch_bounds__(256) gate_fwd_kernel(const float* __restrict__ g, const float* __restrict__ a,
                                                        const float* __restrict__ b, float* __restrict__ out,
                                                        long long n) {
+  DEER_PDL_ENTRY();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     out[i] = g[i] * a[i] + (1.f - g[i]) * b[i];
 }
@@ -309,6 +323,7 @@ __global__ void __launch_bounds__(256) gate_bwd_kernel(const float* __restrict__
                                                        const float* __restrict__ a, const float* __restrict__ b,
                                                        float* __restrict__ dg, float* __restrict__ da,
                                                        float* __restrict__ db, long long n) {
+  DEER_PDL_ENTRY();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     const float d = dout[i], gi = g[i];
@@ -320,6 +335,7 @@ __global__ void __launch_bounds__(256) gate_bwd_kernel(const float* __restrict__
 
 __global__ void __launch_bounds__(256) softmax_rows_fwd_kernel(const float* __restrict__ x, float* __restrict__ y,
                                                                long long M, int N) {
+  DEER_PDL_ENTRY();
   const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= M) return;
   float mx = -INFINITY;
@@ -332,6 +348,7 @@ __global__ void __launch_bounds__(256) softmax_rows_fwd_kernel(const float* __re
 __global__ void __launch_bounds__(256) softmax_rows_bwd_kernel(const float* __restrict__ dy,
                                                                const float* __restrict__ y, float* __restrict__ dx,
                                                                long long M, int N) {
+  DEER_PDL_ENTRY();
   const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= M) return;
   float dot = 0.f;
@@ -349,6 +366,7 @@ static inline int grid_for(long long n, int per_block = 256, int max_blocks = kN
 // y[m,n] = x[m,n] / t[n]   (temperature scaling, complete_project.py:449) and its backward
 __global__ void __launch_bounds__(256) coldiv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ t,
                                                          float* __restrict__ y, long long M, int N) {
+  DEER_PDL_ENTRY();
   const long long total = M * N;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x)
@@ -358,6 +376,7 @@ __global__ void __launch_bounds__(256) coldiv_fwd_kernel(const float* __restrict
 __global__ void __launch_bounds__(256) coldiv_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                                          const float* __restrict__ t, float* __restrict__ dx,
                                                          float* __restrict__ dt, long long M, int N) {
+  DEER_PDL_ENTRY();
   __shared__ float red[32];
   const int n = blockIdx.x;
   const float tn = t[n];
@@ -375,6 +394,7 @@ __global__ void __launch_bounds__(256) coldiv_bwd_kernel(const float* __restrict
 // kernels; inverse=1 maps interleaved -> natural; accumulate adds into dst (gradient un-permutation into .grad)
 __global__ void __launch_bounds__(256) gate_rows_interleave_kernel(const float* __restrict__ src, float* __restrict__ dst,
                                                                    int H, int K, int inverse, int accumulate) {
+  DEER_PDL_ENTRY();
   const long long total = 4LL * H * K;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {

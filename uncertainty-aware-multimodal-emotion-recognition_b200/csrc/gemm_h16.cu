@@ -97,6 +97,7 @@ template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
     gemm_h16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_c, const Params p) {
+  DEER_PDL_ENTRY();
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128B swizzle atoms, applied as an OFFSET on the __shared__ array: going through
   // uintptr_t would make every later access a generic LD/ST instead of LDS/STS
@@ -390,6 +391,7 @@ template <int ELEM, bool A_MN, bool B_MN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
     gemm_h16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const __grid_constant__ CUtensorMap tmap_c, const Params p) {
+  DEER_PDL_ENTRY();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   float* staging = reinterpret_cast<float*>(smem + P_STAGES * P_STAGE_BYTES);
@@ -845,6 +847,7 @@ int gemm_tf32_pair(const float* A, long long lda, int transA, const float* B, lo
 __global__ void __launch_bounds__(256) cast16_kernel(const float* __restrict__ src, long long ld_src,
                                                      uint16_t* __restrict__ dst, long long ld_dst, long long rows,
                                                      int cols, int cols_pad, int bf) {
+  DEER_PDL_ENTRY();
   const long long per_row = cols_pad / 2;
   const long long total = rows * per_row;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;

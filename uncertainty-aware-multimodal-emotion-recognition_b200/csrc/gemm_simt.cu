@@ -17,6 +17,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const float* __restrict_
                                                         const float* __restrict__ bias, int act, float beta,
                                                         int splitk, long long sA, long long sB, long long sC,
                                                         long long sBias) {
+  DEER_PDL_ENTRY();
   __shared__ float As[BK][BM + 4];
   __shared__ float Bs[BK][BN + 4];
   const int z = blockIdx.z;
@@ -127,6 +128,7 @@ __global__ void __launch_bounds__(256) gemm_small_kernel(const float* __restrict
                                                          float* __restrict__ C, long long ldc, int M, int N, int K,
                                                          const float* __restrict__ bias, int act, float beta,
                                                          long long sA, long long sB, long long sC, long long sBias) {
+  DEER_PDL_ENTRY();
   __shared__ __align__(16) float sm[2 * SM_G * SM_K * SM_LD];  // operand tiles, later the 3 x 1024 partial sums
   float(*As)[SM_K][SM_LD] = reinterpret_cast<float(*)[SM_K][SM_LD]>(sm);
   float(*Bs)[SM_K][SM_LD] = reinterpret_cast<float(*)[SM_K][SM_LD]>(sm + SM_G * SM_K * SM_LD);
@@ -261,6 +263,7 @@ __global__ void __launch_bounds__(256, 2) gemm_small2_kernel(const float* __rest
                                                               const float* __restrict__ bias, int act, float beta,
                                                               long long sA, long long sB, long long sC,
                                                               long long sBias) {
+  DEER_PDL_ENTRY();
   extern __shared__ __align__(16) float s2[];
   const int batch = blockIdx.z;
   A += batch * sA;

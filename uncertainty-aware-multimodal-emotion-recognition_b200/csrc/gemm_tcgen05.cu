@@ -51,6 +51,7 @@ template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(NUM_THREADS, 2)
     gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                      const Params p) {
+  DEER_PDL_ENTRY();
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment required by the 128B swizzle atoms
   // 1024-byte alignment for the 128B swizzle atoms, applied as an OFFSET on the __shared__ array: going through

@@ -45,6 +45,7 @@ static int step_gemm(bool tf32, const float* A, long long lda, const float* B, l
 __global__ void __launch_bounds__(256) lstm_cell_fwd_kernel(float* __restrict__ gates, float* __restrict__ h_out,
                                                             float* __restrict__ c_all, float* __restrict__ c_work,
                                                             int step, int T, int B, int H) {
+  DEER_PDL_ENTRY();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)B * 2 * H) return;
   const int j = (int)(idx % H);
@@ -82,6 +83,7 @@ __global__ void __launch_bounds__(256) lstm_cell_bwd_kernel(float* __restrict__ 
                                                             const float* __restrict__ dh_work,
                                                             float* __restrict__ dc_work, int step, int first, int T,
                                                             int B, int H) {
+  DEER_PDL_ENTRY();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)B * 2 * H) return;
   const int j = (int)(idx % H);

@@ -185,6 +185,7 @@ constexpr int Q_PROF_S0 = 64, Q_PROF_STEPS = 4, Q_PROF_SLOTS = 8;
 template <int N, bool TS>
 __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
     lstm_fwd_cluster_kernel(const LstmClusterParams p) {
+  DEER_PDL_ENTRY();
   using L = QLayout<N>;
   constexpr int NQ = L::NQ, ROWF = L::ROWF;
   extern __shared__ uint8_t smem_raw[];
@@ -440,6 +441,7 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
 template <int N, bool TS>
 __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
     lstm_bwd_cluster_kernel(const LstmClusterParams p) {
+  DEER_PDL_ENTRY();
   using L = QLayout<N>;
   constexpr int NQ = L::NQ, ROWF = L::ROWF;
   extern __shared__ uint8_t smem_raw[];

@@ -40,6 +40,7 @@ __global__ void __cluster_dims__(LC, 1, 1) __launch_bounds__(LTHREADS, 1)
     lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmap_w_fwd,
                                const __grid_constant__ CUtensorMap tmap_w_rev,
                                const __grid_constant__ CUtensorMap tmap_h, const LstmParams p) {
+  DEER_PDL_ENTRY();
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128B swizzle atoms, applied as an OFFSET on the __shared__ array: going through
   // uintptr_t would make every later access a generic LD/ST instead of LDS/STS

@@ -21,6 +21,7 @@ __global__ void __launch_bounds__(LING_WARPS * 32) linguistic_features_kernel(co
                                                                               const long long* __restrict__ mask,
                                                                               float* __restrict__ out, int B, int T,
                                                                               int max_length) {
+  DEER_PDL_ENTRY();
   extern __shared__ long long tok[];  // [LING_WARPS][T]
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int b = blockIdx.x * LING_WARPS + w;
@@ -85,6 +86,7 @@ constexpr int NMOM = DEER_METRICS_NMOM;
 __global__ void __launch_bounds__(MOM_THREADS) metrics_moments_kernel(const float* __restrict__ pred,
                                                                       const float* __restrict__ target, long long total,
                                                                       int D, double* __restrict__ out) {
+  DEER_PDL_ENTRY();
   __shared__ double red[NMOM][MOM_THREADS];
   const int tid = threadIdx.x;
   double m[NMOM];
@@ -135,6 +137,7 @@ __global__ void __launch_bounds__(256) uce_prepare_kernel(const float* __restric
                                                           const float* __restrict__ uncert, long long N, int D,
                                                           float* __restrict__ err_m, unsigned* __restrict__ keys,
                                                           unsigned long long* __restrict__ n_valid) {
+  DEER_PDL_ENTRY();
   unsigned long long cnt = 0;
   for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < N; b += (long long)gridDim.x * blockDim.x) {
     float se = 0.f, su = 0.f;
@@ -166,6 +169,7 @@ struct SelState {
 __global__ void __launch_bounds__(256) uce_select_hist_kernel(const unsigned* __restrict__ keys, long long N, int pass,
                                                               int R, const SelState* __restrict__ st,
                                                               unsigned long long* __restrict__ hist) {
+  DEER_PDL_ENTRY();
   __shared__ unsigned h[UCE_MAX_RANKS][256];
   __shared__ unsigned pre[UCE_MAX_RANKS];
   for (int i = threadIdx.x; i < R * 256; i += blockDim.x) (&h[0][0])[i] = 0u;
@@ -192,6 +196,7 @@ __global__ void __launch_bounds__(256) uce_select_hist_kernel(const unsigned* __
 }
 
 __global__ void uce_select_init_kernel(SelState init, SelState* __restrict__ st) {
+  DEER_PDL_ENTRY();
   if (threadIdx.x == 0) *st = init;
 }
 
@@ -199,6 +204,7 @@ __global__ void uce_select_init_kernel(SelState init, SelState* __restrict__ st)
 __global__ void __launch_bounds__(32) uce_select_scan_kernel(int pass, int R, SelState* __restrict__ st,
                                                              unsigned long long* __restrict__ hist,
                                                              float* __restrict__ values) {
+  DEER_PDL_ENTRY();
   const int r = threadIdx.x;
   if (r < R) {
     const unsigned long long* h = hist + (pass == 0 ? 0 : r * 256);
@@ -222,6 +228,7 @@ __global__ void __launch_bounds__(32) uce_select_scan_kernel(int pass, int R, Se
 __global__ void __launch_bounds__(256) uce_bins_kernel(const unsigned* __restrict__ keys,
                                                        const float* __restrict__ err_m, long long N, int n_bins,
                                                        const double* __restrict__ edges, double* __restrict__ out) {
+  DEER_PDL_ENTRY();
   __shared__ double sedge[DEER_UCE_MAX_BINS + 1];
   __shared__ double acc[3][DEER_UCE_MAX_BINS];
   if (threadIdx.x <= n_bins) sedge[threadIdx.x] = edges[threadIdx.x];

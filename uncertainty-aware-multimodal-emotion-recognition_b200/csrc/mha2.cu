@@ -8,6 +8,7 @@ namespace deer {
 // qkv [B,2,3E]; ctx [B,2,E]; attw [B,2,2]; probs [B,heads,2,2]
 __global__ void mha2_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ ctx, float* __restrict__ ctx_mean,
                                 float* __restrict__ attw, float* __restrict__ probs, int B, int E, int heads) {
+  DEER_PDL_ENTRY();
   __shared__ float pw[32][4];
   const int b = blockIdx.x, h = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int d = E / heads;
@@ -67,6 +68,7 @@ __global__ void mha2_bwd_kernel(const float* __restrict__ dctx, const float* __r
                                 const float* __restrict__ dattw,
                                 const float* __restrict__ qkv, const float* __restrict__ probs,
                                 float* __restrict__ dqkv, int B, int E, int heads) {
+  DEER_PDL_ENTRY();
   const int b = blockIdx.x, h = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int d = E / heads;
   const float scale = rsqrtf((float)d);

@@ -197,6 +197,7 @@ __global__ void __launch_bounds__(LOSS_THREADS, 6) nig_loss_stats_kernel(
     const float* __restrict__ alpha, const float* __restrict__ beta, const float* __restrict__ targets,
     const float* __restrict__ bin_edges, float* __restrict__ stats, const NigPlanes planes, int nig_out, int total, int D,
     int from_evidence, float eps) {
+  DEER_PDL_ENTRY();
   __shared__ float bins[3 * NBINS][LOSS_THREADS];  // private column per thread: conflict-free, no atomics
   __shared__ float sedges[NBINS + 1];
   __shared__ float red[5][LOSS_THREADS];
@@ -295,6 +296,7 @@ __global__ void __launch_bounds__(LOSS_THREADS, 6) nig_loss_finish_kernel(
     const float* __restrict__ bin_edges, const float* __restrict__ stats, const float* __restrict__ task_weights,
     float reg_w, float kl_w, float ece_w, float cross_w, float eps, int total_local, long long B_global, int D,
     int from_evidence, float grad_scale, float* __restrict__ losses, float* __restrict__ d_out) {
+  DEER_PDL_ENTRY();
   __shared__ DimCoef coef[8];
   __shared__ float sedges[NBINS + 1];
   __shared__ float ubar[8];
@@ -440,6 +442,7 @@ __global__ void __launch_bounds__(256) nig_head_fwd_kernel(const float* __restri
                                                            float* __restrict__ beta, float* __restrict__ alea,
                                                            float* __restrict__ epis, float* __restrict__ tot,
                                                            long long N) {
+  DEER_PDL_ENTRY();
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < N; e += (long long)gridDim.x * blockDim.x) {
     const float4 r = reinterpret_cast<const float4*>(evidence)[e];
     const float n = softplus_f(r.y) + 1e-6f, a = softplus_f(r.z) + 1.0f, b = softplus_f(r.w) + 1e-6f;
@@ -462,6 +465,7 @@ __global__ void __launch_bounds__(256) nig_head_bwd_kernel(const float* __restri
                                                            const float* __restrict__ depis,
                                                            const float* __restrict__ dtot, float* __restrict__ dev,
                                                            long long N) {
+  DEER_PDL_ENTRY();
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < N; e += (long long)gridDim.x * blockDim.x) {
     const float4 r = reinterpret_cast<const float4*>(evidence)[e];
     const float n = softplus_f(r.y) + 1e-6f, a = softplus_f(r.z) + 1.0f, b = softplus_f(r.w) + 1e-6f;
@@ -488,6 +492,7 @@ __global__ void __launch_bounds__(256) amini_loss_kernel(const float* __restrict
                                                          const float* __restrict__ targets, float ew, float kw,
                                                          long long N, float* __restrict__ dparams,
                                                          float* __restrict__ scratch) {
+  DEER_PDL_ENTRY();
   __shared__ float red[32];
   float s_nll = 0.f, s_reg = 0.f, s_kl = 0.f, s_mse = 0.f;
   const float invN = 1.f / (float)N;
@@ -535,6 +540,7 @@ __global__ void __launch_bounds__(256) amini_loss_kernel(const float* __restrict
   }
 }
 __global__ void amini_finish_kernel(const float* scratch, float ew, float kw, long long N, float* losses) {
+  DEER_PDL_ENTRY();
   const float invN = 1.f / (float)N;
   const float nll = scratch[0] * invN, reg = scratch[1] * invN, kl = scratch[2] * invN, mse = scratch[3] * invN;
   losses[0] = nll + ew * reg + kw * kl;

@@ -11,6 +11,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
                                                             const float* __restrict__ beta, float* __restrict__ y,
                                                             float* __restrict__ mean, float* __restrict__ rstd, int M,
                                                             int N, float eps) {
+  DEER_PDL_ENTRY();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
@@ -52,6 +53,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
                                                             const float* __restrict__ rstd, float* __restrict__ dx,
                                                             float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                             int M, int N, int rows_per_block) {
+  DEER_PDL_ENTRY();
   extern __shared__ float sm[];  // [8][N] dgamma partials, [8][N] dbeta partials
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r0 = blockIdx.x * rows_per_block;
@@ -118,6 +120,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
 __global__ void __launch_bounds__(256) bn_colreduce_kernel(const float* __restrict__ x, const float* __restrict__ sum,
                                                            float* __restrict__ out, long long M, int C, int mode,
                                                            int rows_per_block) {
+  DEER_PDL_ENTRY();
   __shared__ float red[8][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   const long long r0 = (long long)blockIdx.y * rows_per_block;
@@ -140,6 +143,7 @@ __global__ void __launch_bounds__(256) bn_colreduce_kernel(const float* __restri
   }
 }
 __global__ void bn_finalize_kernel(float* stats, long long M, int C) {
+  DEER_PDL_ENTRY();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < C) {
     stats[c] /= (float)M;
@@ -148,6 +152,7 @@ __global__ void bn_finalize_kernel(float* stats, long long M, int C) {
 }
 __global__ void bn_running_kernel(const float* __restrict__ stats, float* __restrict__ rm, float* __restrict__ rv,
                                   long long* __restrict__ nbt, long long M, int C, float momentum) {
+  DEER_PDL_ENTRY();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < C) {
     const float unb = M > 1 ? stats[C + c] * ((float)M / (float)(M - 1)) : stats[C + c];
@@ -162,6 +167,7 @@ __global__ void __launch_bounds__(256) bn_relu_fwd_kernel(const float* __restric
                                                           const float* __restrict__ gamma,
                                                           const float* __restrict__ beta, float* __restrict__ y,
                                                           long long M, int C, float eps) {
+  DEER_PDL_ENTRY();
   const long long total = M * C;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -177,6 +183,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restr
                                                             const float* __restrict__ mean,
                                                             const float* __restrict__ var, float* __restrict__ scratch,
                                                             long long M, int C, float eps, int rows_per_block) {
+  DEER_PDL_ENTRY();
   __shared__ float r1s[8][33], r2s[8][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   const long long r0 = (long long)blockIdx.y * rows_per_block;
@@ -212,6 +219,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
                                                            const float* __restrict__ scratch, float* __restrict__ dx,
                                                            float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                            long long M, int C, float eps, int batch_stats) {
+  DEER_PDL_ENTRY();
   const long long total = M * C;
   const float invM = 1.f / (float)M;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;

@@ -7,6 +7,7 @@
 namespace deer {
 
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ x, long long n, float* __restrict__ out) {
+  DEER_PDL_ENTRY();
   __shared__ float red[32];
   float s = 0.f;
   const long long n4 = n >> 2;
@@ -28,6 +29,7 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
                                                     float bc2_sqrt, const float* __restrict__ sumsq, float max_norm,
                                                     float grad_scale, const long long* __restrict__ step_dev,
                                                     const float* __restrict__ lr_dev) {
+  DEER_PDL_ENTRY();
   // CUDA-graph replays: the step count (bias corrections) and the learning rate come from device memory, so one
   // captured training step stays valid across steps and LR-schedule changes
   if (step_dev) {

@@ -59,6 +59,7 @@ __global__ void __launch_bounds__(256) attn_pool_fwd_kernel(const float* __restr
                                                             long long ss_b, long long ss_t,
                                                             const float* __restrict__ mask, float* __restrict__ out,
                                                             float* __restrict__ wts, int B, int T, int D) {
+  DEER_PDL_ENTRY();
   __shared__ float p[POOL_MAX_T];
   __shared__ float red[32];
   __shared__ float4 part[8][32];
@@ -116,6 +117,7 @@ __global__ void __launch_bounds__(256) attn_pool_bwd_kernel(const float* __restr
                                                             const float* __restrict__ wts, float* __restrict__ dx,
                                                             float* __restrict__ ds, int B, int T, int D,
                                                             int accumulate) {
+  DEER_PDL_ENTRY();
   __shared__ float dw[POOL_MAX_T];
   __shared__ float p[POOL_MAX_T];
   __shared__ float red[32];
