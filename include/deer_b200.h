@@ -68,6 +68,10 @@ int deer_lstm_set_profile_buffer(long long* device_buf);
  *      opA(A) is M x K: transA=0 -> A stored [M,K] (lda>=K); transA=1 -> A stored [K,M] (lda>=M).
  *      opB(B) is K x N: transB=0 -> B stored [K,N] (ldb>=N); transB=1 -> B stored [N,K] (ldb>=K)  (nn.Linear weight).
  *      batch>=1 with element strides sA/sB/sC/sBias (may be negative or zero). bias may be NULL. */
+/*      Sliding-window operands: a leading dimension SMALLER than the row length describes overlapping rows (row i starts
+ *      ld elements after row i-1).  Accepted on the TMA engines only (CTA-pair kernels): A with transA = 0, B with
+ *      transB = 0, and C with beta = 1 (overlapping output rows are accumulated with TMA reduce-add).  Other shapes
+ *      return DEER_ERR_UNSUPPORTED. */
 int deer_gemm(const float* A, long long lda, int transA, const float* B, long long ldb, int transB,
               float* C, long long ldc, int M, int N, int K, const float* bias, int act, float beta,
               int batch, long long sA, long long sB, long long sC, long long sBias, int engine, void* stream);
@@ -131,6 +135,12 @@ int deer_rowscale(const float* x, const float* mask, float* y, long long M, int 
 /* Conv1d(k=3,pad=1) lowering on channels-last x [B,T,C]: col [B*T, 3C], tap k holds x[b,t+k-1,:] (zero outside) */
 int deer_im2col3(const float* x, float* col, int B, int T, int C, void* stream);
 int deer_col2im3(const float* dcol, float* dx, int B, int T, int C, void* stream);
+/*      sliding-window form of the same convolution (no im2col matrix): padded copy
+ *        xp = [lead zero rows][sample 0: T rows][zero row][sample 1: T rows][zero row]...[tail zero rows]   ([.,C], C % 4 == 0)
+ *      with lead = 1 the rows of the k=3 im2col matrix are the OVERLAPPING windows xp[q .. q+3) (3C contiguous floats,
+ *      row pitch C): deer_gemm accepts lda < K / ldb < N / ldc < N (with beta = 1: atomic accumulation) for such views.
+ *      dir 0: x [B,T,C] -> xp;  dir 1: xp -> x (drops the pad rows). */
+int deer_rows_pad(const float* src, float* dst, int B, int T, int C, int lead, int tail, int dir, void* stream);
 /* w [Cout,Cin,3] (nn.Conv1d layout) <-> wk [Cout,3,Cin]; dir=0 pack, dir=1 unpack with accumulate into w */
 int deer_conv3_weight_pack(const float* w, float* wk, int Cout, int Cin, int dir, void* stream);
 

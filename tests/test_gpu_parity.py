@@ -562,3 +562,37 @@ def test_gemm_tf32_engines(M, N, K, ta, tb, pair):
             assert_close(C[:, :N], r, 1e-3, f"tf32 pair={pair} act={act} beta={beta}")
     finally:
         _lib.set_option(6, 1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,T,Cin,Cout", [(32, 12, 64, 512), (300, 50, 512, 512), (7, 50, 128, 260)])
+def test_conv1d_sliding_window_matches_im2col_and_torch(B, T, Cin, Cout):
+    """Conv1d(k=3, padding=1) through overlapping-row TMA windows of a zero-row-padded copy (no im2col matrix): same
+    result as the im2col + GEMM path and as torch's fp64 conv1d (encoders.py:450-459), forward and all gradients."""
+    from deer_b200 import _lib
+    g = torch.Generator().manual_seed(B * T + Cin)
+    x = torch.randn(B, T, Cin, generator=g)
+    w = torch.randn(Cout, Cin, 3, generator=g) * (3 * Cin) ** -0.5
+    b = torch.randn(Cout, generator=g) * 0.1
+    pr = torch.randn(B, T, Cout, generator=g)
+    xr, wr, br = (t.double().requires_grad_(True) for t in (x, w, b))
+    yr = torch.nn.functional.conv1d(xr.transpose(1, 2), wr, br, padding=1).transpose(1, 2)
+    (yr * pr.double()).sum().backward()
+    outs = []
+    for window in (True, False):
+        ops.set_conv_window(window)
+        try:
+            xc, wc, bc = (cu(t).requires_grad_(True) for t in (x, w, b))
+            before = _lib.launch_count()
+            y = ops.conv1d_k3(xc, wc, bc)
+            (y * cu(pr)).sum().backward()
+            outs.append((y.detach(), xc.grad, wc.grad, bc.grad, _lib.launch_count() - before))
+        finally:
+            ops.set_conv_window(True)
+    for got in outs:
+        assert_close(got[0], yr, 1e-3, "conv y")
+        assert_close(got[1], xr.grad, 1e-3, "conv dx")
+        assert_close(got[2], wr.grad, 1e-3, "conv dw")
+        assert_close(got[3], br.grad, 1e-3, "conv db")
+    for a, c in zip(outs[0][:4], outs[1][:4]):
+        assert_close(a, c, 1e-3, "window vs im2col")

@@ -41,6 +41,7 @@ _PROTOS = {
     "deer_rowscale": [P, P, P, L, I, P],
     "deer_im2col3": [P, P, I, I, I, P],
     "deer_col2im3": [P, P, I, I, I, P],
+    "deer_rows_pad": [P, P, I, I, I, I, I, I, P],
     "deer_conv3_weight_pack": [P, P, I, I, I, P],
     "deer_bn_stats": [P, P, L, I, P],
     "deer_bn_update_running": [P, P, P, P, L, I, F, P],

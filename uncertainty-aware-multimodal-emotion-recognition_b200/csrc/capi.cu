@@ -87,7 +87,22 @@ int deer_gemm(const float* A, long long lda, int transA, const float* B, long lo
               long long sB, long long sC, long long sBias, int engine, void* stream) {
   DEER_CHECK_ARG(A && B && C, "gemm: null pointer");
   DEER_CHECK_ARG(M > 0 && N > 0 && K > 0 && batch > 0, "gemm: empty shape");
-  DEER_CHECK_ARG(lda >= (transA ? M : K) && ldb >= (transB ? K : N) && ldc >= N, "gemm: leading dimension too small");
+  // a leading dimension smaller than the row length = overlapping rows (sliding-window operand); only the CTA-pair TMA
+  // kernels implement it (TMA reads any 16-byte-multiple pitch; overlapping C rows need the reduce-add epilogue)
+  const bool overlapA = !transA && lda < K, overlapB = !transB && ldb < N, overlapC = ldc < N;
+  DEER_CHECK_ARG((lda >= (transA ? M : K) || overlapA) && (ldb >= (transB ? K : N) || overlapB) && lda > 0 && ldb > 0 &&
+                     ldc > 0,
+                 "gemm: leading dimension too small");
+  if (overlapA || overlapB || overlapC) {
+    if (engine == DEER_GEMM_SIMT || batch != 1 || (overlapC && beta != 1.f) ||
+        !gemm_tcgen05_supported(A, lda, transA, B, ldb, transB, C, ldc, M, N, K, batch, sA, sB, sC) ||
+        !gemm_tf32_pair_supported(transA, transB, M, N, K, ldc, bias, act, beta)) {
+      set_error("gemm: overlapping-row operands need the CTA-pair TF32 engine (M=%d N=%d K=%d lda=%lld ldb=%lld ldc=%lld)",
+                M, N, K, lda, ldb, ldc);
+      return DEER_ERR_UNSUPPORTED;
+    }
+    return gemm_tf32_pair(A, lda, transA, B, ldb, transB, C, ldc, M, N, K, bias, act, beta, (cudaStream_t)stream);
+  }
   DEER_CHECK_ARG(act >= 0 && act <= 3, "gemm: bad activation");
   DEER_CHECK_ARG(beta == 0.f || beta == 1.f, "gemm: beta must be 0 or 1");
   cudaStream_t st = (cudaStream_t)stream;

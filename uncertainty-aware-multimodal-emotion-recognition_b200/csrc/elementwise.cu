@@ -222,6 +222,41 @@ __global__ void __launch_bounds__(256) im2col3_kernel(const float* __restrict__ 
     col[i] = (ts >= 0 && ts < T) ? x[((long long)b * T + ts) * C + c] : 0.f;
   }
 }
+// ------------------------------------------------------------------ zero-row padding for the sliding-window Conv1d
+// padded layout: [lead zero rows][sample 0: T rows][1 zero row][sample 1: T rows][1 zero row] ...  (one shared pad row
+// between samples; with lead = 1 a row view of 3*C contiguous floats starting at padded row q is exactly the k=3
+// im2col row centred on padded row q+1).  dir 0: x [B,T,C] -> xp (pad rows written as zeros); dir 1: xp -> x.
+__global__ void __launch_bounds__(256) rows_pad_kernel(const float* __restrict__ src, float* __restrict__ dst, int B,
+                                                       int T, int C4, int lead, int dir, long long pad_rows_total) {
+  DEER_PDL_ENTRY();
+  const long long per_sample = (long long)(T + 1) * C4;
+  const long long total = (dir == 0) ? pad_rows_total * C4 : (long long)B * T * C4;   // in float4 units
+  const float4* s4 = reinterpret_cast<const float4*>(src);
+  float4* d4 = reinterpret_cast<float4*>(dst);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    if (dir == 0) {   // iterate over PADDED elements: copy or zero
+      const long long r = i / C4;
+      const int c = (int)(i % C4);
+      const long long q = r - lead;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (q >= 0) {
+        const long long b = q / (T + 1);
+        const int t = (int)(q % (T + 1));
+        if (b < B && t < T) v = __ldcs(s4 + (b * T + t) * C4 + c);
+      }
+      d4[i] = v;
+    } else {          // iterate over compact elements
+      const long long r = i / C4;
+      const int c = (int)(i % C4);
+      const long long b = r / T;
+      const int t = (int)(r % T);
+      __stcs(d4 + i, s4[(lead + b * (T + 1) + t) * C4 + c]);
+    }
+  }
+  (void)per_sample;
+}
+
 // dx[b,t,c] = sum_k dcol[(b,t-k+1), k*C + c]
 __global__ void __launch_bounds__(256) col2im3_kernel(const float* __restrict__ dcol, float* __restrict__ dx, int B,
                                                       int T, int C) {
@@ -513,6 +548,16 @@ int deer_rowscale(const float* x, const float* mask, float* y, long long M, int 
 int deer_im2col3(const float* x, float* col, int B, int T, int C, void* stream) {
   DEER_CHECK_ARG(x && col && B > 0 && T > 0 && C > 0, "im2col3: bad args");
   DEER_LAUNCH(im2col3_kernel, grid_for((long long)B * T * 3 * C), 256, 0, stream, x, col, B, T, C);
+  return DEER_OK;
+}
+
+int deer_rows_pad(const float* src, float* dst, int B, int T, int C, int lead, int tail, int dir, void* stream) {
+  DEER_CHECK_ARG(src && dst && B > 0 && T > 0 && C > 0 && (C & 3) == 0 && lead >= 0 && tail >= 0 && (dir == 0 || dir == 1),
+                 "rows_pad: bad args");
+  DEER_CHECK_ARG(((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0, "rows_pad: alignment");
+  const long long pad_rows = (long long)lead + (long long)B * (T + 1) + tail;
+  const long long n4 = (dir == 0 ? pad_rows : (long long)B * T) * (C / 4);
+  DEER_LAUNCH(rows_pad_kernel, grid_for(n4), 256, 0, stream, src, dst, B, T, C / 4, lead, dir, pad_rows);
   return DEER_OK;
 }
 

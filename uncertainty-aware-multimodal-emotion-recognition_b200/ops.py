@@ -707,7 +707,71 @@ class _Conv1dK3(torch.autograd.Function):
         return dx, None if dw_direct else dw, None if db_direct else db
 
 
+class _Conv1dK3Window(torch.autograd.Function):
+    """The same convolution without an im2col matrix: x is copied once into a zero-row-padded layout xp
+    ([1 zero row][sample: T rows][zero row]...), whose OVERLAPPING row windows xp[q:q+3] (3*Cin contiguous floats, row
+    pitch Cin) are exactly the im2col rows.  The TMA engine reads those windows straight from xp (a tensor map whose row
+    pitch is smaller than its row length): forward y_big = windows . wk^T, backward dwk = dy_big^T . windows and
+    dx_p += dy_big . wk accumulated into overlapping rows by the TMA reduce-add epilogue (no dcol, no col2im).
+    Rows centred on a pad row are garbage in y_big and are dropped by the un-padding copy; dy_big has zeros there."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        x = _req(x, "x").contiguous()
+        B, T, Cin = x.shape
+        Cout = w.shape[0]
+        dev = x.device
+        Mp = B * (T + 1)                                        # window rows (one per padded row centre)
+        xp = torch.empty((Mp + 2, Cin), device=dev, dtype=torch.float32)
+        call("deer_rows_pad", ptr(x), ptr(xp), B, T, Cin, 1, 1, 0)
+        wk = torch.empty((Cout, 3 * Cin), device=dev, dtype=torch.float32)
+        call("deer_conv3_weight_pack", ptr(w.contiguous()), ptr(wk), Cout, Cin, 0)
+        y_big = torch.empty((Mp, Cout), device=dev, dtype=torch.float32)
+        gemm(xp, Cin, 0, wk, 3 * Cin, 1, y_big, Cout, Mp, Cout, 3 * Cin, bias=b)      # lda = Cin < K = 3 Cin
+        y = torch.empty((B, T, Cout), device=dev, dtype=torch.float32)
+        call("deer_rows_pad", ptr(y_big), ptr(y), B, T, Cout, 0, 0, 1)
+        ctx.save_for_backward(xp, wk)
+        ctx.dims = (B, T, Cin, Cout)
+        ctx.params = (w, b)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xp, wk = ctx.saved_tensors
+        B, T, Cin, Cout = ctx.dims
+        dev = dy.device
+        dy = dy.contiguous()
+        Mp = B * (T + 1)
+        dy_big = torch.empty((Mp, Cout), device=dev, dtype=torch.float32)
+        call("deer_rows_pad", ptr(dy), ptr(dy_big), B, T, Cout, 0, 0, 0)              # zero rows at the pad centres
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx_p = torch.zeros((Mp + 2, Cin), device=dev, dtype=torch.float32)
+            gemm(dy_big, Cout, 0, wk, 3 * Cin, 0, dx_p, Cin, Mp, 3 * Cin, Cout, beta=1.0)   # ldc = Cin < N: overlapped
+            dx = torch.empty((B, T, Cin), device=dev, dtype=torch.float32)
+            call("deer_rows_pad", ptr(dx_p), ptr(dx), B, T, Cin, 1, 1, 1)
+        dwk = torch.zeros_like(wk)
+        gemm(dy_big, Cout, 1, xp, Cin, 0, dwk, 3 * Cin, Cout, 3 * Cin, Mp, beta=1.0)         # ldb = Cin < N = 3 Cin
+        dw, dw_direct = _acc(ctx.params[0])
+        call("deer_conv3_weight_pack", ptr(dwk), ptr(dw), Cout, Cin, 1)
+        db, db_direct = _acc(ctx.params[1])
+        call("deer_bias_act_bwd", ptr(dy), Cout, None, 0, None, 0, ptr(db), B * T, Cout, 0)
+        return dx, None if dw_direct else dw, None if db_direct else db
+
+
+def set_conv_window(on: bool):
+    """Conv1d(k=3) through the sliding-window (overlapping-row TMA) path (default) or through an im2col matrix."""
+    _state["conv_window"] = bool(on)
+
+
 def conv1d_k3(x, w, b):
+    """Large batches on the TMA engine use the sliding-window path (no im2col matrix); small ones (the CTA-pair kernel
+    needs > 256 rows), forced engines and odd channel counts keep the im2col + GEMM path."""
+    B, T, Cin = x.shape
+    Cout = w.shape[0]
+    if (_state.get("conv_window", True) and _state["engine"] == ENGINE_AUTO and B * (T + 1) > 256 and Cin % 4 == 0 and
+            Cout % 4 == 0 and Cin >= 32 and Cout > 256):   # dW runs with M = Cout rows on the CTA-pair kernel
+        return _Conv1dK3Window.apply(x, w, b)
     return _Conv1dK3.apply(x, w, b)
 
 
