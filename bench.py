@@ -144,6 +144,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-pooled", action="store_true")
+    ap.add_argument("--no-branch-streams", action="store_true",
+                    help="ablation: video/text encoders on the main stream behind the audio encoder")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     if args.impl == "reference":
@@ -165,6 +167,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     K, W = args.steps, args.warmup
     pk = peaks()
+    ops.set_branch_streams(not args.no_branch_streams)
 
     def barrier():
         if world > 1:
@@ -331,7 +334,7 @@ def main():
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4},
-        "cuda_graph": use_graph,
+        "cuda_graph": use_graph, "branch_streams": ops.branch_streams_enabled(),
         "gpu_launches": int(launches_per_step * K),
         "launches_per_step": int(launches_per_step),
         "inference": {"value": infer_value, "unit": "samples/s", "batch_per_gpu": INFER_B, "ms_per_step": infer_ms,

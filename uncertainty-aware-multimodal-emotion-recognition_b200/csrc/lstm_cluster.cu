@@ -219,7 +219,16 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
     if (T > 1) mbar_expect_tx(&h_full[0], L::HB_BYTES);
     if (T > 2) mbar_expect_tx(&h_full[1], L::HB_BYTES);
   }
-  if (warp == 8) tmem_alloc(tmem_slot, TS ? 512 : 64);
+  // two allocations (accumulators 64 columns, resident operand 256) instead of one 512-column block: the 192 columns
+  // left over let a 128-column GEMM CTA of a concurrent stream share the SM instead of spinning in tcgen05.alloc
+  if (warp == 8) {
+    if constexpr (TS) {
+      tmem_alloc_more_follow(tmem_slot, 64);
+      tmem_alloc(tmem_slot + 1, 256);
+    } else {
+      tmem_alloc(tmem_slot, 64);
+    }
+  }
   if constexpr (!TS) {
     // W_hh rows of this CTA -> fp16, K-major SWIZZLE_128B: [acc a][k-block 4][128 rows x 128 B]; row m = 4*unit + gate
     for (int idx = threadIdx.x; idx < 2 * 128 * 32; idx += QTHREADS) {
@@ -237,6 +246,7 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_w = TS ? tmem_slot[1] : 0u;   // resident A operand (TS mode)
   if constexpr (TS) {
     if (warp < 8) {
       // resident A operand in TMEM: lane = row m of accumulator a, 128 columns = 256 fp16 (2 per column, low half first)
@@ -252,7 +262,7 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
           reinterpret_cast<uint32_t*>(v)[2 * i] = pack_h2(x.x, x.y);
           reinterpret_cast<uint32_t*>(v)[2 * i + 1] = pack_h2(x.z, x.w);
         }
-        tmem_st32(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(Q_WCOL + a * 128 + ch * 32), v);
+        tmem_st32(tmem_w + ((uint32_t)(sub * 32) << 16) + (uint32_t)(a * 128 + ch * 32), v);
       }
       tmem_st_wait();
     }
@@ -267,6 +277,7 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
     {
       constexpr uint32_t idesc = make_idesc_f16(0, 128, N);
       const uint32_t tb = warp_uniform(tmem_base);
+      const uint32_t tw = warp_uniform(tmem_w);
       const bool leader = elect_one();
       for (int s = 0; s < T; s++) {
         if (s == 0) {
@@ -286,7 +297,7 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
             // B operand, K-major no-swizzle: [32 k-chunks][N rows][16 B]; 8x16B core matrices, SBO 128 B, LBO N*16 B
             const uint64_t bd = make_smem_desc(hb + (2 * k) * (N * 16), N * 16, 128, 0);
             if constexpr (TS) {
-              umma_f16_ts(tb + a * N, tb + Q_WCOL + a * 128 + k * 8, bd, idesc, k > 0 ? 1u : 0u);
+              umma_f16_ts(tb + a * N, tw + a * 128 + k * 8, bd, idesc, k > 0 ? 1u : 0u);
             } else {
               const uint64_t ad =
                   make_smem_desc(smem_u32(wsm) + a * 65536 + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024, 2);
@@ -433,7 +444,8 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
   cluster_sync_all();  // no CTA retires while a peer may still address its shared memory
   if (warp == 8) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TS ? 512 : 64);
+    tmem_dealloc(tmem_base, 64);
+    if constexpr (TS) tmem_dealloc(tmem_w, 256);
   }
 }
 
@@ -476,7 +488,16 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
     if (T > 1) mbar_expect_tx(&part_full[0], L::PART_BYTES);
     if (T > 2) mbar_expect_tx(&part_full[1], L::PART_BYTES);
   }
-  if (warp == 8) tmem_alloc(tmem_slot, TS ? 512 : 64);
+  // two allocations (accumulators 64 columns, resident operand 256) instead of one 512-column block: the 192 columns
+  // left over let a 128-column GEMM CTA of a concurrent stream share the SM instead of spinning in tcgen05.alloc
+  if (warp == 8) {
+    if constexpr (TS) {
+      tmem_alloc_more_follow(tmem_slot, 64);
+      tmem_alloc(tmem_slot + 1, 256);
+    } else {
+      tmem_alloc(tmem_slot, 64);
+    }
+  }
   if constexpr (!TS) {
     // A[m = hidden unit (2 x 128)][k = 4*unit_local + gate] = W_hh[gate*256 + 64r + unit_local][m], bf16, K-major SW128
     for (int idx = threadIdx.x; idx < 2 * 32 * 128; idx += QTHREADS) {
@@ -497,6 +518,7 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_w = TS ? tmem_slot[1] : 0u;   // resident A operand (TS mode)
   if constexpr (TS) {
     if (warp < 8) {
       const int a = warp >> 2, sub = warp & 3, m = a * 128 + sub * 32 + lane;
@@ -510,7 +532,7 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
           const float f1 = __ldg(W + (size_t)(((k0 + 1) & 3) * QH + (int)r * QU + ((k0 + 1) >> 2)) * QH + m);
           reinterpret_cast<uint32_t*>(v)[i] = pack_bf2(f0, f1);
         }
-        tmem_st32(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(Q_WCOL + a * 128 + ch * 32), v);
+        tmem_st32(tmem_w + ((uint32_t)(sub * 32) << 16) + (uint32_t)(a * 128 + ch * 32), v);
       }
       tmem_st_wait();
     }
@@ -525,6 +547,7 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
     {
       constexpr uint32_t idesc = make_idesc_f16(1, 128, N);
       const uint32_t tb = warp_uniform(tmem_base);
+      const uint32_t tw = warp_uniform(tmem_w);
       const bool leader = elect_one();
       for (int s = 0; s + 1 < T; s++) {
         mbar_wait(b_ready, (uint32_t)(s & 1));
@@ -540,7 +563,7 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
           for (int k = 0; k < 16; k++) {
             const uint64_t bd = make_smem_desc(bb + (k >> 2) * (N * 128) + (k & 3) * 32, 16, 1024, 2);
             if constexpr (TS) {
-              umma_f16_ts(tb + a * N, tb + Q_WCOL + a * 128 + k * 8, bd, idesc, k > 0 ? 1u : 0u);
+              umma_f16_ts(tb + a * N, tw + a * 128 + k * 8, bd, idesc, k > 0 ? 1u : 0u);
             } else {
               const uint64_t ad =
                   make_smem_desc(smem_u32(wsm) + a * 65536 + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024, 2);
@@ -703,14 +726,16 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
   cluster_sync_all();
   if (warp == 8) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TS ? 512 : 64);
+    tmem_dealloc(tmem_base, 64);
+    if constexpr (TS) tmem_dealloc(tmem_w, 256);
   }
 }
 
 template <int N, bool TS>
 constexpr int fwd_smem_bytes() {
   using L = QLayout<N>;
-  // >= 120 KB even in TS mode: one CTA per SM, so a 512-column TMEM allocation can never wait on a co-resident CTA
+  // >= 120 KB even in TS mode: one LSTM CTA per SM (two would not fit their 2 x 320 TMEM columns and the second would
+  // spin in tcgen05.alloc); a TF32 GEMM CTA (100 KB, 128 columns) of another stream still fits beside it
   constexpr int need = (TS ? 0 : QW_BYTES) + 2 * L::HB_BYTES + L::ACT_BYTES + L::SH_BYTES + 64 + 1024;
   return need > 120 * 1024 ? need : 120 * 1024;
 }

@@ -24,7 +24,17 @@ ENGINE_AUTO, ENGINE_SIMT, ENGINE_TF32 = 0, 1, 2
 # prone) outputs feed the bias / scorer gradients whose per-tensor cosine otherwise sits at 0.9992, too close to the
 # 0.999 gate (tools/precision_probe.py).
 _state = {"engine": ENGINE_AUTO, "lstm_engine": ENGINE_AUTO, "exact_small_fwd": True, "exact_small_bwd": True,
-          "small_rows": 8192, "direct_grad": False, "lstm_gemm16": True, "fuse_lstm_dropout": True}
+          "small_rows": 8192, "direct_grad": False, "lstm_gemm16": True, "fuse_lstm_dropout": True,
+          "branch_streams": True}
+
+
+def set_branch_streams(on: bool):
+    """Run the video and text encoders of the sequence model on a second CUDA stream beside the audio LSTM (default)."""
+    _state["branch_streams"] = bool(on)
+
+
+def branch_streams_enabled() -> bool:
+    return _state["branch_streams"]
 
 
 def set_fuse_lstm_dropout(on: bool):

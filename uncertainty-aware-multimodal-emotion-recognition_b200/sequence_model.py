@@ -41,15 +41,40 @@ class SequenceDEERModel(nn.Module):
             attention_mask = d.get("attention_mask", attention_mask)
             linguistic_features = d.get("linguistic_features", linguistic_features)
         ops.begin_step()
-        a = self.audio_encoder(audio)
-        v = self.video_encoder(video)
-        t = self.text_encoder(text, attention_mask, linguistic_features)
+        if ops.branch_streams_enabled() and audio.is_cuda:
+            # The three encoders are independent until the fusion.  The audio LSTM recurrence is a latency-bound
+            # persistent kernel (128 of 148 SMs, one CTA each, mostly waiting on the cluster exchange), so it runs on
+            # its own HIGH-PRIORITY stream (its CTAs and the second wave of a large batch are placed first) while the
+            # video and text encoders fill the rest of the machine from the calling stream: forked here, joined
+            # before the fusion; autograd replays each node's backward on the stream its forward ran on, which
+            # overlaps BPTT the same way.  Fork / join are event edges, so the pattern is captured unchanged into
+            # the CUDA graph of a step.
+            main = torch.cuda.current_stream()
+            side = self._branch_stream()
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                a = self.audio_encoder(audio)
+            v = self.video_encoder(video)
+            t = self.text_encoder(text, attention_mask, linguistic_features)
+            main.wait_stream(side)
+            a.record_stream(main)
+        else:
+            a = self.audio_encoder(audio)
+            v = self.video_encoder(video)
+            t = self.text_encoder(text, attention_mask, linguistic_features)
         fus = self.fusion(a, v, t)
         out = self.deer(fus["fused_features"])
         out["fused_features"] = fus["fused_features"]
         out["audio_encoded"], out["video_encoded"], out["text_encoded"] = a, v, t
         out["attention_weights"] = fus["trimodal_attention_weights"]
         return out
+
+    def _branch_stream(self):
+        dev = torch.cuda.current_device()
+        st = self.__dict__.setdefault("_side_streams", {})
+        if dev not in st:
+            st[dev] = torch.cuda.Stream(device=dev, priority=-1)
+        return st[dev]
 
     def compute_loss(self, predictions: Dict[str, torch.Tensor], targets: torch.Tensor) -> Dict[str, torch.Tensor]:
         return self.loss_fn(predictions, targets)
