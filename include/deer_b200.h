@@ -78,8 +78,10 @@ int deer_gemm(const float* A, long long lda, int transA, const float* B, long lo
 
 /* ---- 16-bit-operand engine for the time-batched LSTM contractions (csrc/gemm_h16.cu): same contract as deer_gemm
  *      (batch = 1) but A and B are both FP16 (a_bf16 = b_bf16 = 0) or both BF16 (= 1) matrices; accumulation and C
- *      are fp32.  C16 (optional, may be NULL) receives a 16-bit copy of C (row pitch ldc16 elements) for the next GEMM.
- *      All pointers 16-byte aligned; lda/ldb multiples of 8 elements, ldc/ldc16 multiples of 4. */
+ *      are fp32.  16-bit OUTPUT: pass C = NULL and C16 (FP16, or BF16 with c16_bf16 = 1; row pitch ldc16 elements, a
+ *      multiple of 8): the result is rounded once, after bias/activation, and only 2 bytes per element are written
+ *      (CTA-pair kernel only: M > 128, beta = 0).  Passing both C and C16 returns DEER_ERR_UNSUPPORTED.
+ *      All pointers 16-byte aligned; lda/ldb multiples of 8 elements, ldc a multiple of 4. */
 int deer_gemm_h16(const void* A, long long lda, int transA, int a_bf16, const void* B, long long ldb, int transB,
                   int b_bf16, float* C, long long ldc, void* C16, long long ldc16, int c16_bf16, int M, int N, int K,
                   const float* bias, int act, float beta, void* stream);
@@ -192,6 +194,11 @@ int deer_lstm_cluster_tile(int B);  /* batch columns per 4-CTA cluster the kerne
  *      [T,B,2,H,4] written by the same kernels as operands for deer_gemm_h16 (NULL to skip). */
 int deer_lstm_cluster_fwd(const float* pre_il, const float* w_hh_fwd, const float* w_hh_rev, float* h_out, float* gact,
                           float* c_blk, void* h_f16, void* h_bf16, int T, int B, int H, void* stream);
+/*      the same forward reading FP16 pre-activations [T,B,2,H,4] (deer_gemm_h16 with a 16-bit output) */
+int deer_lstm_cluster_fwd_pre16(const void* pre_il_f16, const float* w_hh_fwd, const float* w_hh_rev, float* h_out,
+                                float* gact, float* c_blk, void* h_f16, void* h_bf16, int T, int B, int H,
+                                void* stream);
+/*      dpre_il (fp32) may be NULL when dpre_bf16 is given: only the 16-bit gradient is written */
 int deer_lstm_cluster_bwd(const float* gact, const float* c_blk, const float* dh_out, const float* w_hh_fwd,
                           const float* w_hh_rev, float* dpre_il, float* db_il, void* dpre_bf16, int T, int B, int H,
                           void* stream);

@@ -142,3 +142,31 @@ def test_fused_interlayer_dropout_matches_separate_kernel():
     with torch.no_grad():
         h_eval = enc.lstm_forward(x)
     assert float((h_eval - res[0][0]).abs().max()) > 1e-3
+
+
+@pytest.mark.parametrize("B,T,In", [(64, 20, 84), (130, 33, 512), (256, 40, 512)])
+def test_fp16_preactivations_match_fp32_preactivations(B, T, In):
+    """Input projection written as FP16 by the GEMM epilogue and read as FP16 by the recurrence kernel (default) vs the
+    fp32 pre-activation buffer: same h within the FP16-operand noise, same gradients; BPTT writes only the BF16 dpre."""
+    H = 256
+    ws = make_layer(In, H, B + T + 1)
+    x = torch.randn(B, T, In, generator=torch.Generator().manual_seed(B + 3))
+    res = []
+    for on in (True, False):
+        ops.set_lstm_pre16(on)
+        try:
+            res.append(run(x, ws, ops.ENGINE_AUTO, True))
+        finally:
+            ops.set_lstm_pre16(True)
+    (h16, g16), (h32, g32) = res
+    assert_close(h16, h32, 3e-4, "h (fp16 pre vs fp32 pre)")
+    assert float((h16 - h32).abs().max()) < 2e-3
+    for a, b_ in zip(g16, g32):
+        assert cosine(a, b_) > 0.99999
+    # against the exact engine as well
+    ops.set_gemm_engine(ops.ENGINE_SIMT)
+    h_ref, g_ref = run(x, ws, ops.ENGINE_SIMT, True)
+    ops.set_gemm_engine(ops.ENGINE_AUTO)
+    assert_close(h16, h_ref, 1e-3, "h (fp16 pre vs exact fp32)")
+    for a, b_ in zip(g16, g_ref):
+        assert cosine(a, b_) > 0.9999

@@ -452,6 +452,25 @@ def test_gemm_h16(M, N, K, ta, tb, a_bf, b_bf):
         r = {0: r, 1: torch.relu(r), 2: torch.tanh(r)}[act]
         assert_close(C[:, :N], r, 2e-5, f"gemm_h16 act={act} beta={beta}")
         assert float(C[:, N:].abs().max() if ldc > N else 0.0) == 0.0      # TMA clips the N tail
+    # 16-bit output (C = NULL, C16): rounded once after bias / activation; CTA-pair kernel only
+    if M > 128 and N % 2 == 0:
+        ld16 = (N + 7) // 8 * 8
+        for act, c16_bf in ((0, False), (2, True)):
+            dt = torch.bfloat16 if c16_bf else torch.float16
+            C16 = torch.zeros(M, ld16, device=DEV, dtype=dt)
+            use_bias = bias if N % 4 == 0 else None
+            ops.gemm_h16(Ad, lda, ta, Bd, ldb, tb, None, 0, M, N, K, a_bf16=bool(a_bf), b_bf16=bool(b_bf),
+                         bias=None if use_bias is None else cu(use_bias), act=act, C16=C16, ldc16=ld16, c16_bf16=c16_bf)
+            r = ref + (0 if use_bias is None else use_bias.double())
+            r = {0: r, 2: torch.tanh(r)}[act]
+            want = r.float().to(dt)                      # one rounding of the exact result
+            got = C16[:, :N].cpu()
+            ulp = 2.0 ** (-7 if c16_bf else -10)
+            # within one 16-bit ulp of the exact value (+ the fp32 accumulation error, relative to the largest entry)
+            assert float(((got.double() - r).abs() - ulp * r.abs()).max()) < 2e-5 * float(ref.abs().max())
+            if act == 0:
+                assert float((got != want).float().mean()) < 0.02   # and almost always the correctly rounded value
+            assert float(C16[:, N:].abs().max() if ld16 > N else 0.0) == 0.0
     # cast helper
     x = torch.randn(37, 84, generator=g)
     x16 = ops.cast16(cu(x))

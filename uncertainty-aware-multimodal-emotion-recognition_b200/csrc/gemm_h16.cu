@@ -380,6 +380,14 @@ __device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, float* v) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ uint32_t pack_bf2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
 __device__ __forceinline__ void red_add_v2(float* p, float a, float b) {
   asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
 }
@@ -569,6 +577,59 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
             }
           }
         }
+      } else if (p.C16 != nullptr) {
+        // ---- 16-bit output (tmap_c describes C16): 64 columns per store -- the same 4 KB, 128-byte-row staging tile
+        // carries twice the columns, so the kernel writes half the bytes (the fp32 store stream is what bounds the
+        // small-K projections)
+#pragma unroll 1
+        for (int c = half; c < BN / 64; c += 2) {
+          const int gn0 = n0 + c * 64;
+          if (gn0 >= p.N || row_base >= p.M) break;
+          float v[64];
+          const uint32_t ta = tmem_base + ((uint32_t)(gq * 32) << 16) + (uint32_t)(acc * BN + c * 64);
+          tmem_ld32(ta, v);
+          tmem_ld32(ta + 32, v + 32);
+          tmem_ld_wait();
+          if (add_bias) {
+#pragma unroll
+            for (int j = 0; j < 64; j += 4) {
+              if (gn0 + j < p.N) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + gn0 + j));
+                v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+              }
+            }
+          }
+          if (act != DEER_ACT_NONE) {
+#pragma unroll
+            for (int j = 0; j < 64; j += 4) {
+              const float4 o = act_apply4(make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]), act);
+              v[j] = o.x; v[j + 1] = o.y; v[j + 2] = o.z; v[j + 3] = o.w;
+            }
+          }
+          if (p.debug & 2) continue;
+          uint8_t* tile = tile0 + (nstore & 1) * 4096;
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            uint4 o;
+            if (p.c16_bf) {
+              o.x = pack_bf2(v[8 * j], v[8 * j + 1]); o.y = pack_bf2(v[8 * j + 2], v[8 * j + 3]);
+              o.z = pack_bf2(v[8 * j + 4], v[8 * j + 5]); o.w = pack_bf2(v[8 * j + 6], v[8 * j + 7]);
+            } else {
+              o.x = pack_h2(v[8 * j], v[8 * j + 1]); o.y = pack_h2(v[8 * j + 2], v[8 * j + 3]);
+              o.z = pack_h2(v[8 * j + 4], v[8 * j + 5]); o.w = pack_h2(v[8 * j + 6], v[8 * j + 7]);
+            }
+            *reinterpret_cast<uint4*>(tile + lane * 128 + ((j ^ (lane & 7)) << 4)) = o;
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0 && !(p.debug & 1)) {
+            tma_store_2d(&tmap_c, tile, gn0, row_base);
+            tma_store_commit();
+          }
+          nstore++;
+        }
       } else
 #pragma unroll 1
       for (int c = half; c < BN / 32; c += 2) {
@@ -682,17 +743,22 @@ int gemm_h16(const void* A, long long lda, int transA, int a_bf, const void* B, 
              int act, float beta, cudaStream_t stream) {
   using namespace h16;
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
-  if (!al16(A) || !al16(B) || !al16(C) || (lda & 7) || (ldb & 7) || (ldc & 3) || (bias && !al16(bias)) ||
-      (C16 && (!al16(C16) || (ldc16 & 3)))) {
+  // output: fp32 C, or (C == NULL) a 16-bit C16 alone -- the CTA-pair kernel's 64-column store tiles
+  const bool out16 = C == nullptr && C16 != nullptr;
+  if (out16) ldc = ldc16;
+  if (!al16(A) || !al16(B) || !al16(C) || (lda & 7) || (ldb & 7) || (!out16 && (ldc & 3)) || (bias && !al16(bias)) ||
+      (C16 && (!al16(C16) || (ldc16 & 7)))) {
     set_error("gemm_h16: operands must be 16-byte aligned with leading dimensions that are multiples of 16 bytes");
     return DEER_ERR_UNSUPPORTED;
   }
-  if (C16 != nullptr || (beta != 0.f && act != DEER_ACT_NONE) || (bias && (N & 3))) {
-    set_error("gemm_h16: unsupported epilogue (16-bit copy of C, activation on an accumulating GEMM, or bias with N % 4)");
+  if ((C16 != nullptr && !out16) || (C == nullptr && !out16) || (beta != 0.f && act != DEER_ACT_NONE) ||
+      (bias && (N & 3)) || (out16 && (beta != 0.f || !(g_h16_pair && M > BM && (N & 1) == 0)))) {
+    set_error("gemm_h16: unsupported epilogue (fp32 AND 16-bit output, activation on an accumulating GEMM, bias with "
+              "N % 4, or a 16-bit output outside the CTA-pair kernel / with beta != 0)");
     return DEER_ERR_UNSUPPORTED;
   }
   CUtensorMap ma, mb, mc;
-  bool ok = make_map_c(&mc, C, M, N, ldc);
+  bool ok = out16 ? make_map16(&mc, C16, c16_bf, M, N, ldc16, 64, 32) : make_map_c(&mc, C, M, N, ldc);
   if (!ok) {
     set_error("gemm_h16: cuTensorMapEncodeTiled failed for C (M=%d N=%d ldc=%lld)", M, N, ldc);
     return DEER_ERR_UNSUPPORTED;
@@ -877,9 +943,10 @@ extern "C" {
 int deer_gemm_h16(const void* A, long long lda, int transA, int a_bf16, const void* B, long long ldb, int transB,
                   int b_bf16, float* C, long long ldc, void* C16, long long ldc16, int c16_bf16, int M, int N, int K,
                   const float* bias, int act, float beta, void* stream) {
-  DEER_CHECK_ARG(A && B && C, "gemm_h16: null pointer");
+  DEER_CHECK_ARG(A && B && (C || C16), "gemm_h16: null pointer");
   DEER_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm_h16: empty shape");
-  DEER_CHECK_ARG(lda >= (transA ? M : K) && ldb >= (transB ? K : N) && ldc >= N, "gemm_h16: leading dimension too small");
+  DEER_CHECK_ARG(lda >= (transA ? M : K) && ldb >= (transB ? K : N) && (C ? ldc >= N : ldc16 >= N),
+                 "gemm_h16: leading dimension too small");
   DEER_CHECK_ARG(act >= 0 && act <= 3, "gemm_h16: bad activation");
   DEER_CHECK_ARG(beta == 0.f || beta == 1.f, "gemm_h16: beta must be 0 or 1");
   // tcgen05.mma kind::f16 takes ONE 16-bit format for both operands (a mixed descriptor traps as an illegal instruction)

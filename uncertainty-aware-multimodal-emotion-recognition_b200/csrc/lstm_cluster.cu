@@ -171,6 +171,7 @@ struct LstmClusterParams {
   __half* h16;
   __nv_bfloat16* hb16;
   __nv_bfloat16* dpre16;
+  const __half* pre16;  // fwd: FP16 pre-activations [T,B,2,H,4] (read instead of `gates` when non-null)
   int T, B, ntiles, keep;
   long long* prof;     // optional clock64 trace of block 0 (tools/lstm_probe.py --prof), else null
 };
@@ -325,13 +326,25 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
     float cst[NQ];
 #pragma unroll
     for (int i = 0; i < NQ; i++) cst[i] = 0.f;
-    float pre[N];
+    // pre-activations of the NEXT step, as loaded (fp32 bits, or an FP16 value in the low half): converting at load time
+    // would make the convert instruction wait for the DRAM round trip inside the current step
+    uint32_t pre[N];
+    const bool pre_is16 = p.pre16 != nullptr;
     const int il0 = 4 * ((int)r * QU + a * 32 + sub * 8);  // first interleaved gate column of this warp
     auto load_pre = [&](int s) {
       const int t = dir ? T - 1 - s : s;
-      const float* src = p.gates + (((long long)t * B + b0) * 2 + dir) * (4 * QH) + il0 + lane;
+      const long long off = (((long long)t * B + b0) * 2 + dir) * (4 * QH) + il0 + lane;
+      if (pre_is16) {   // FP16 pre-activations (the projection GEMM's 16-bit epilogue): half the bytes of the only
+                        // stream this kernel reads; one 64-byte request per warp and sample
+        const unsigned short* src = reinterpret_cast<const unsigned short*>(p.pre16) + off;
 #pragma unroll
-      for (int n = 0; n < N; n++) pre[n] = (b0 + n < B) ? __ldcs(src + (long long)n * (8 * QH)) : 0.f;
+        for (int n = 0; n < N; n++) pre[n] = (b0 + n < B) ? (uint32_t)__ldcs(src + (long long)n * (8 * QH)) : 0u;
+      } else {
+        const float* src = p.gates + off;
+#pragma unroll
+        for (int n = 0; n < N; n++)
+          pre[n] = (b0 + n < B) ? __float_as_uint(__ldcs(src + (long long)n * (8 * QH))) : 0u;
+      }
     };
     // blocked save area of this warp: ((((t*2+dir)*ntiles+tile)*4+r)*8+warp) blocks of 4*NQ*32 (gates) / NQ*32 (c)
     const long long blk_w = ((long long)dir * p.ntiles + tile) * 32 + (int)r * 8 + warp;
@@ -352,9 +365,16 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
         for (int n = 0; n < N; n++) x[n] = 0.f;
       }
       tc_fence_before();
+      if (pre_is16) {
+#pragma unroll
+        for (int n = 0; n < N; n++) x[n] += __half2float(__ushort_as_half((unsigned short)pre[n]));
+      } else {
+#pragma unroll
+        for (int n = 0; n < N; n++) x[n] += __uint_as_float(pre[n]);
+      }
 #pragma unroll
       for (int n = 0; n < N; n++) {
-        const float z = (x[n] + pre[n]) * sc;
+        const float z = x[n] * sc;
         x[n] = fmaf(sc, __fdividef(1.f, 1.f + __expf(-z)), 1.f - sc);
       }
 #pragma unroll
@@ -673,7 +693,7 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
 #pragma unroll
       for (int i = 0; i < NQ; i++) {
         if (b0 + q * NQ + i < B) {
-          __stcs(reinterpret_cast<float4*>(gout + (long long)i * (8 * QH)), dp[i]);
+          if (p.gates) __stcs(reinterpret_cast<float4*>(gout + (long long)i * (8 * QH)), dp[i]);
           if (p.dpre16)
             *reinterpret_cast<uint2*>(p.dpre16 + (((long long)t * B + b0 + q * NQ + i) * 2 + dir) * (4 * QH) + 4 * ug) = dp16[i];
           sdb[0] += dp[i].x; sdb[1] += dp[i].y; sdb[2] += dp[i].z; sdb[3] += dp[i].w;
@@ -795,13 +815,13 @@ static int launch_bwd(const tc::LstmClusterParams& p, cudaStream_t stream) {
 
 int lstm_cluster_tile(int B) { return pick_tile(B); }
 
-int lstm_fwd_cluster(const float* pre_il, const float* w_fwd, const float* w_rev, float* h_out, float* gact,
-                     float* c_blk, void* h16, void* hb16, int T, int B, cudaStream_t stream) {
+int lstm_fwd_cluster(const float* pre_il, const void* pre_f16, const float* w_fwd, const float* w_rev, float* h_out,
+                     float* gact, float* c_blk, void* h16, void* hb16, int T, int B, cudaStream_t stream) {
   const int N = pick_tile(B);
   const int keep = (gact != nullptr && c_blk != nullptr) ? 1 : 0;
   tc::LstmClusterParams p{const_cast<float*>(pre_il), w_fwd, w_rev, h_out, gact, c_blk, nullptr, nullptr,
-                          reinterpret_cast<__half*>(h16), reinterpret_cast<__nv_bfloat16*>(hb16), nullptr, T, B,
-                          (B + N - 1) / N, keep, g_lstm_prof};
+                          reinterpret_cast<__half*>(h16), reinterpret_cast<__nv_bfloat16*>(hb16), nullptr,
+                          reinterpret_cast<const __half*>(pre_f16), T, B, (B + N - 1) / N, keep, g_lstm_prof};
   if (N == 16) return g_lstm_ts ? launch_fwd<16, true>(p, stream) : launch_fwd<16, false>(p, stream);
   return g_lstm_ts ? launch_fwd<32, true>(p, stream) : launch_fwd<32, false>(p, stream);
 }
@@ -810,8 +830,8 @@ int lstm_bwd_cluster(const float* gact, const float* c_blk, const float* dh_out,
                      float* dpre_il, float* db_il, void* dpre16, int T, int B, cudaStream_t stream) {
   const int N = pick_tile(B);
   tc::LstmClusterParams p{dpre_il, w_fwd, w_rev, nullptr, const_cast<float*>(gact), const_cast<float*>(c_blk), dh_out,
-                          db_il, nullptr, nullptr, reinterpret_cast<__nv_bfloat16*>(dpre16), T, B, (B + N - 1) / N, 1,
-                          g_lstm_prof};
+                          db_il, nullptr, nullptr, reinterpret_cast<__nv_bfloat16*>(dpre16), nullptr, T, B,
+                          (B + N - 1) / N, 1, g_lstm_prof};
   if (N == 16) return g_lstm_ts ? launch_bwd<16, true>(p, stream) : launch_bwd<16, false>(p, stream);
   return launch_bwd<32, true>(p, stream);  // the N=32 tiles + 128 KB of smem-resident weights exceed 227 KB
 }
@@ -834,13 +854,31 @@ int deer_lstm_cluster_fwd(const float* pre_il, const float* w_hh_fwd, const floa
   }
   DEER_CHECK_ARG(((reinterpret_cast<uintptr_t>(h_f16) | reinterpret_cast<uintptr_t>(h_bf16)) & 15) == 0,
                  "lstm_cluster_fwd: 16-bit shadows must be 16-byte aligned");
-  return lstm_fwd_cluster(pre_il, w_hh_fwd, w_hh_rev, h_out, gact, c_blk, h_f16, h_bf16, T, B, (cudaStream_t)stream);
+  return lstm_fwd_cluster(pre_il, nullptr, w_hh_fwd, w_hh_rev, h_out, gact, c_blk, h_f16, h_bf16, T, B,
+                          (cudaStream_t)stream);
+}
+
+int deer_lstm_cluster_fwd_pre16(const void* pre_il_f16, const float* w_hh_fwd, const float* w_hh_rev, float* h_out,
+                                float* gact, float* c_blk, void* h_f16, void* h_bf16, int T, int B, int H,
+                                void* stream) {
+  DEER_CHECK_ARG(pre_il_f16 && w_hh_fwd && w_hh_rev && h_out && T > 0 && B > 0, "lstm_cluster_fwd_pre16: bad args");
+  DEER_CHECK_ARG((gact == nullptr) == (c_blk == nullptr), "lstm_cluster_fwd_pre16: gact and c_blk go together");
+  if (!lstm_cluster_supported(h_out, w_hh_fwd, w_hh_rev, H)) {
+    set_error("lstm_cluster_fwd_pre16: needs H == 256 and 16-byte aligned pointers");
+    return DEER_ERR_UNSUPPORTED;
+  }
+  DEER_CHECK_ARG(((reinterpret_cast<uintptr_t>(h_f16) | reinterpret_cast<uintptr_t>(h_bf16) |
+                   reinterpret_cast<uintptr_t>(pre_il_f16)) & 15) == 0,
+                 "lstm_cluster_fwd_pre16: 16-bit buffers must be 16-byte aligned");
+  return lstm_fwd_cluster(nullptr, pre_il_f16, w_hh_fwd, w_hh_rev, h_out, gact, c_blk, h_f16, h_bf16, T, B,
+                          (cudaStream_t)stream);
 }
 
 int deer_lstm_cluster_bwd(const float* gact, const float* c_blk, const float* dh_out, const float* w_hh_fwd,
                           const float* w_hh_rev, float* dpre_il, float* db_il, void* dpre_bf16, int T, int B, int H,
                           void* stream) {
-  DEER_CHECK_ARG(gact && c_blk && dh_out && w_hh_fwd && w_hh_rev && dpre_il && T > 0 && B > 0, "lstm_cluster_bwd: bad args");
+  DEER_CHECK_ARG(gact && c_blk && dh_out && w_hh_fwd && w_hh_rev && (dpre_il || dpre_bf16) && T > 0 && B > 0,
+                 "lstm_cluster_bwd: bad args");
   if (!lstm_cluster_supported(dpre_il, w_hh_fwd, w_hh_rev, H)) {
     set_error("lstm_cluster_bwd: needs H == 256 and 16-byte aligned pointers");
     return DEER_ERR_UNSUPPORTED;

@@ -25,7 +25,12 @@ ENGINE_AUTO, ENGINE_SIMT, ENGINE_TF32 = 0, 1, 2
 # 0.999 gate (tools/precision_probe.py).
 _state = {"engine": ENGINE_AUTO, "lstm_engine": ENGINE_AUTO, "exact_small_fwd": True, "exact_small_bwd": True,
           "small_rows": 8192, "direct_grad": False, "lstm_gemm16": True, "fuse_lstm_dropout": True,
-          "branch_streams": True}
+          "branch_streams": True, "lstm_pre16": True}
+
+
+def set_lstm_pre16(on: bool):
+    """FP16 (default) or fp32 pre-activations between the LSTM input projection and the recurrence kernel."""
+    _state["lstm_pre16"] = bool(on)
 
 
 def set_branch_streams(on: bool):
@@ -136,9 +141,10 @@ def _p16(t):
 
 def gemm_h16(A, lda, transA, B, ldb, transB, C, ldc, M, N, K, *, a_bf16=False, b_bf16=False, bias=None, act=0,
              beta=0.0, C16=None, ldc16=0, c16_bf16=False):
-    """deer_gemm_h16: 16-bit operands (pointers or tensors), fp32 accumulate/output, optional 16-bit copy of C."""
+    """deer_gemm_h16: 16-bit operands (pointers or tensors), fp32 accumulate; fp32 output C, or (C=None) 16-bit C16."""
     call("deer_gemm_h16", _p16(A), lda, int(transA), int(a_bf16), _p16(B), ldb, int(transB), int(b_bf16),
-         _p16(C), ldc, None if C16 is None else _p16(C16), ldc16, int(c16_bf16), M, N, K, ptr(bias), act, float(beta))
+         None if C is None else _p16(C), ldc, None if C16 is None else _p16(C16), ldc16, int(c16_bf16), M, N, K,
+         ptr(bias), act, float(beta))
 
 
 def _colw(w: torch.Tensor, k0: int, k1: int):
@@ -535,8 +541,11 @@ class _BiLSTMLayerCluster(torch.autograd.Function):
             call("deer_gate_rows_interleave", ptr(wi.contiguous()), ptr(wi_il[d]), H, In, 0, 0)
             call("deer_axpby", ptr(bi), ptr(bh), ptr(bsum), G, 1.0, 1.0)
             call("deer_gate_rows_interleave", ptr(bsum), ptr(b_il[d]), H, 1, 0, 0)
-        pre = torch.empty((T, B, 2, G), device=dev, dtype=torch.float32)
         M = T * B
+        # FP16 pre-activations (16-bit GEMM epilogue -> LSTM kernel): the projection is bound by its output stream, and
+        # the rounding (2^-12 relative, once) is of the order of what the FP16 operands already contribute
+        pre16 = use16 and _state["lstm_pre16"] and M > 128
+        pre = torch.empty((T, B, 2, G), device=dev, dtype=torch.float16 if pre16 else torch.float32)
         x16 = None
         if drop is not None and not (use16 and In % 8 == 0):
             raise _lib.DeerError("deer_b200: fused input dropout needs the 16-bit GEMM path and In % 8 == 0")
@@ -552,24 +561,29 @@ class _BiLSTMLayerCluster(torch.autograd.Function):
             Kp = x16.shape[1]
             w16 = cast16(wi_il.view(2 * G, In))               # [2G, Kp] fp16
             # both directions in ONE contraction: pre[M, 2G] = x16 [M, Kp] . w16[2G, Kp]^T (full 8 KB output rows)
-            gemm_h16(x16, Kp, 0, w16, Kp, 1, pre, 2 * G, M, 2 * G, In, bias=b_il.view(-1))
+            if pre16:
+                gemm_h16(x16, Kp, 0, w16, Kp, 1, None, 0, M, 2 * G, In, bias=b_il.view(-1), C16=pre, ldc16=2 * G)
+            else:
+                gemm_h16(x16, Kp, 0, w16, Kp, 1, pre, 2 * G, M, 2 * G, In, bias=b_il.view(-1))
         else:
             for d in range(2):
                 gemm(x, In, 0, wi_il[d], In, 1, pre.data_ptr() + 4 * G * d, 2 * G, M, G, In, bias=b_il[d])
         h = torch.empty((T, B, 2 * H), device=dev, dtype=torch.float32)
         whf_c, whr_c = whf.contiguous(), whr.contiguous()
+        fwd_fn = "deer_lstm_cluster_fwd_pre16" if pre16 else "deer_lstm_cluster_fwd"
         if keep:
             Bp = (B + 31) // 32 * 32
             gact = torch.empty(T * 2 * Bp * G, device=dev, dtype=torch.float32)
             c_blk = torch.empty(T * 2 * Bp * H, device=dev, dtype=torch.float32)
             hb16 = torch.empty((T, B, 2 * H), device=dev, dtype=torch.bfloat16) if use16 else None
-            call("deer_lstm_cluster_fwd", ptr(pre), ptr(whf_c), ptr(whr_c), ptr(h), ptr(gact), ptr(c_blk), None,
+            call(fwd_fn, pre.data_ptr(), ptr(whf_c), ptr(whr_c), ptr(h), ptr(gact), ptr(c_blk), None,
                  None if hb16 is None else hb16.data_ptr(), T, B, H)
             ctx.save_for_backward(x, wi_il, whf_c, whr_c, gact, c_blk, h)
-            ctx.pre = pre   # reused as the dpre buffer
+            # the fp32 pre buffer doubles as the fp32 dpre buffer; on the 16-bit path BPTT only writes the BF16 dpre
+            ctx.pre = None if use16 else pre
             ctx.hb16 = hb16
         else:
-            call("deer_lstm_cluster_fwd", ptr(pre), ptr(whf_c), ptr(whr_c), ptr(h), None, None, None, None, T, B, H)
+            call(fwd_fn, pre.data_ptr(), ptr(whf_c), ptr(whr_c), ptr(h), None, None, None, None, T, B, H)
         ctx.dims = (T, B, In, H)
         ctx.use16 = use16
         ctx.params = (wif, whf, bif, bhf, wir, whr, bir, bhr)
@@ -589,8 +603,8 @@ class _BiLSTMLayerCluster(torch.autograd.Function):
         M = T * B
         db_il = torch.zeros((2, G), device=dev, dtype=torch.float32)
         dpre16 = torch.empty((T, B, 2, G), device=dev, dtype=torch.bfloat16) if use16 else None
-        call("deer_lstm_cluster_bwd", ptr(gact), ptr(c_blk), ptr(dh), ptr(whf), ptr(whr), ptr(dpre), ptr(db_il),
-             None if dpre16 is None else dpre16.data_ptr(), T, B, H)
+        call("deer_lstm_cluster_bwd", ptr(gact), ptr(c_blk), ptr(dh), ptr(whf), ptr(whr),
+             None if dpre is None else ptr(dpre), ptr(db_il), None if dpre16 is None else dpre16.data_ptr(), T, B, H)
         dx = None
         drop = ctx.drop
         if use16:
@@ -622,7 +636,7 @@ class _BiLSTMLayerCluster(torch.autograd.Function):
             dwi_il2 = torch.zeros((2, G, In), device=dev, dtype=torch.float32)
             gemm_h16(dpre16, 2 * G, 1, xb16, Kp, 0, dwi_il2, In, 2 * G, In, M, a_bf16=True, b_bf16=True, beta=1.0)
         for d in range(2):
-            gp = dpre.data_ptr() + 4 * G * d
+            gp = None if use16 else dpre.data_ptr() + 4 * G * d
             dwi_il = dwi_il2[d] if use16 else torch.zeros((G, In), device=dev, dtype=torch.float32)
             dwh_il = torch.zeros((G, H), device=dev, dtype=torch.float32)
             Mr = (T - 1) * B
