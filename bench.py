@@ -417,7 +417,11 @@ def _time_launches(torch, fn, n, warm=5):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/)
-NCU_TRAFFIC = {}
+NCU_TRAFFIC = {
+    # profiles/r1_ncu_full_roofline_v11_summary.txt (ncu --set full --clock-control none, per launch)
+    "gemm_h16_pair_out16": 80.8e6 + 255.9e6,                       # algorithmic 395 MB; part of C16 still in L2 at kernel end
+    "nig_stats_plus_finish": 251.7e6 + 302.1e6 + 251.7e6 + 160.9e6,  # two passes: the 252 MB of operands are read twice
+}
 
 
 def roofline_probe(torch, ops, dev, pk):
@@ -429,39 +433,49 @@ def roofline_probe(torch, ops, dev, pk):
     of HBM peak) and the persistent LSTM recurrence (latency-bound: us per step)."""
     B, T, H = TRAIN_B, TA, 256
     M, N, K = B * T, 8 * H, 2 * H     # both directions in one contraction: pre[T*B, 2*4H] = h0[T*B, 512] W_ih^T
-    nbuf = 3   # 3 x (79 MB A + 629 MB C) > 126 MB L2
+    nbuf = 3   # 3 x (79 MB A + 315 MB C16 [+ 629 MB fp32 C]) > 126 MB L2
     A = [(torch.randn(M, K, device=dev) * 0.5).half() for _ in range(nbuf)]
     W = (torch.randn(N, K, device=dev) * 0.05).half()
     bias = torch.randn(N, device=dev)
-    C = [torch.empty(M, N, device=dev) for _ in range(nbuf)]
+    C16 = [torch.empty(M, N, device=dev, dtype=torch.float16) for _ in range(nbuf)]
 
-    def gemm_launch(i):
+    def gemm_launch(i):   # exactly the call ops._BiLSTMLayerCluster.forward makes for layer 1
         j = i % nbuf
-        ops.gemm_h16(A[j], K, 0, W, K, 1, C[j], N, M, N, K, bias=bias)
+        ops.gemm_h16(A[j], K, 0, W, K, 1, None, 0, M, N, K, bias=bias, C16=C16[j], ldc16=N)
 
     us = _time_launches(torch, gemm_launch, 12)
     flop = 2.0 * M * N * K
     achieved = flop / (us * 1e-6) / 1e12
-    alg_bytes = float(M * K * 2 + N * K * 2 + M * N * 4)
-    # With an fp32 output this contraction sits on the ridge of the roofline: its algorithmic traffic (A + W read once,
-    # C written once) needs slightly LONGER at the measured HBM peak than its FLOPs need at the measured bf16 peak, so
-    # the binding roof is HBM; the tensor-pipe fraction is reported next to it.
+    alg_bytes = float(M * K * 2 + N * K * 2 + M * N * 2)
+    # With the FP16 output the algorithmic traffic (A + W read once, C16 written once: 395 MB) needs 60 us at the
+    # measured HBM peak, the FLOPs need 99 us at the measured bf16 peak: the binding roof is the tensor pipe (with an
+    # fp32 output the same contraction was HBM-bound: 710 MB, 108 us; that variant is reported next to it).
     hbm_floor_us = alg_bytes / (pk["hbm_gbs"] * 1e3)
     tensor_floor_us = flop / (pk["bf16_tflops"] * 1e6)
     gbs = alg_bytes / (us * 1e-6) / 1e9
     hbm_bound = hbm_floor_us >= tensor_floor_us
-    roof = {"kernel": "h16::gemm_h16_pair_kernel<0,0> (layer-1 LSTM input projection of both directions, "
-                      "[76800,512]x[2048,512]^T, FP16 operands, fp32 accumulate/output, bias epilogue; cta_group::2)",
+    roof = {"kernel": "h16::gemm_h16_pair_kernel<2,0,0> (layer-1 LSTM input projection of both directions, "
+                      "[76800,512]x[2048,512]^T, FP16 operands, fp32 accumulate, bias epilogue, FP16 output through "
+                      "64-column TMA-store tiles; cta_group::2)",
             "bound": "hbm" if hbm_bound else "tensor",
             "achieved": gbs if hbm_bound else achieved, "peak": pk["hbm_gbs"] if hbm_bound else pk["bf16_tflops"],
             "unit": "GB/s" if hbm_bound else "TFLOP/s",
             "frac": (gbs / pk["hbm_gbs"]) if hbm_bound else (achieved / pk["bf16_tflops"]),
-            "traffic": NCU_TRAFFIC.get("gemm_h16_pair"), "us_per_launch": us,
+            "traffic": NCU_TRAFFIC.get("gemm_h16_pair_out16"), "us_per_launch": us,
             "flop_per_launch": flop, "algorithmic_bytes_per_launch": alg_bytes,
             "hbm_floor_us": hbm_floor_us, "tensor_floor_us": tensor_floor_us,
+            "hbm": {"achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"]},
             "tensor": {"achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
                        "frac": achieved / pk["bf16_tflops"]},
             "peak_source": f"{pk['source']} HBM copy bandwidth / cuBLAS bf16 burst (MEASURED_PEAKS.json)"}
+    del C16
+    C = [torch.empty(M, N, device=dev) for _ in range(nbuf)]
+    us32o = _time_launches(torch, lambda i: ops.gemm_h16(A[i % nbuf], K, 0, W, K, 1, C[i % nbuf], N, M, N, K, bias=bias), 8)
+    b32 = float(M * K * 2 + N * K * 2 + M * N * 4)
+    roof["fp32_output_same_shape"] = {"us_per_launch": us32o, "bound": "hbm", "algorithmic_bytes_per_launch": b32,
+                                      "achieved": b32 / (us32o * 1e-6) / 1e9, "unit": "GB/s",
+                                      "frac": b32 / (us32o * 1e-6) / 1e9 / pk["hbm_gbs"],
+                                      "tflops": flop / (us32o * 1e-6) / 1e12}
     # the other instances of the same engine in the step (small outputs: tensor-bound)
     others = {}
     G2, In = 8 * H, 2 * H
@@ -503,25 +517,27 @@ def roofline_probe(torch, ops, dev, pk):
     roof["nig_head_loss"] = {"kernel": "deer::nig_loss_stats_kernel + nig_loss_finish_kernel (B=2^22, 3 dims, train)",
                              "bound": "hbm", "achieved": nbytes / (us_n * 1e-6) / 1e9, "peak": pk["hbm_gbs"],
                              "unit": "GB/s", "frac": nbytes / (us_n * 1e-6) / 1e9 / pk["hbm_gbs"],
-                             "us_per_call": us_n, "algorithmic_bytes": nbytes}
+                             "us_per_call": us_n, "algorithmic_bytes": nbytes,
+                             "traffic": NCU_TRAFFIC.get("nig_stats_plus_finish")}
     del ev, tg
     torch.cuda.empty_cache()
 
     # ---- persistent LSTM recurrence (one layer, both directions), latency-bound
     from deer_b200._lib import call, ptr
     Bp = (B + 31) // 32 * 32
-    pre = torch.randn(T, B, 2, 4 * H, device=dev)
+    pre = torch.randn(T, B, 2, 4 * H, device=dev).half()          # FP16 pre-activations, as in the step
     w = [torch.randn(4 * H, H, device=dev) * 0.05 for _ in range(2)]
     h = torch.empty(T, B, 2 * H, device=dev)
+    hb16 = torch.empty(T, B, 2 * H, device=dev, dtype=torch.bfloat16)
     gact = torch.empty(T * 2 * Bp * 4 * H, device=dev)
     c = torch.empty(T * 2 * Bp * H, device=dev)
     dh = torch.randn(T, B, 2 * H, device=dev) * 1e-3
-    dpre = torch.empty(T, B, 2, 4 * H, device=dev)
+    dpre16 = torch.empty(T, B, 2, 4 * H, device=dev, dtype=torch.bfloat16)
     db = torch.zeros(2, 4 * H, device=dev)
-    us_f = _time_launches(torch, lambda i: call("deer_lstm_cluster_fwd", ptr(pre), ptr(w[0]), ptr(w[1]), ptr(h), ptr(gact),
-                                                ptr(c), None, None, T, B, H), 5, warm=2)
+    us_f = _time_launches(torch, lambda i: call("deer_lstm_cluster_fwd_pre16", pre.data_ptr(), ptr(w[0]), ptr(w[1]),
+                                                ptr(h), ptr(gact), ptr(c), None, hb16.data_ptr(), T, B, H), 5, warm=2)
     us_b = _time_launches(torch, lambda i: call("deer_lstm_cluster_bwd", ptr(gact), ptr(c), ptr(dh), ptr(w[0]), ptr(w[1]),
-                                                ptr(dpre), ptr(db), None, T, B, H), 5, warm=2)
+                                                None, ptr(db), dpre16.data_ptr(), T, B, H), 5, warm=2)
     rflop = 2.0 * B * 2 * 4 * H * H * T
     roof["lstm_recurrence"] = {"kernel": "tc::lstm_fwd_cluster_kernel / lstm_bwd_cluster_kernel (B=256, T=300, H=256, 2 dirs)",
                                "bound": "latency (serial over T)", "fwd_us_per_step": us_f / T, "bwd_us_per_step": us_b / T,
