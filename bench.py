@@ -146,6 +146,8 @@ def main():
     ap.add_argument("--no-pooled", action="store_true")
     ap.add_argument("--no-branch-streams", action="store_true",
                     help="ablation: video/text encoders on the main stream behind the audio encoder")
+    ap.add_argument("--no-defer-wgrad", action="store_true",
+                    help="ablation: small-layer weight gradients on the main stream")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     if args.impl == "reference":
@@ -168,6 +170,7 @@ def main():
     K, W = args.steps, args.warmup
     pk = peaks()
     ops.set_branch_streams(not args.no_branch_streams)
+    ops.set_defer_wgrad(not args.no_defer_wgrad)
 
     def barrier():
         if world > 1:

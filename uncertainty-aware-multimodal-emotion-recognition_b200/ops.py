@@ -25,7 +25,31 @@ ENGINE_AUTO, ENGINE_SIMT, ENGINE_TF32 = 0, 1, 2
 # 0.999 gate (tools/precision_probe.py).
 _state = {"engine": ENGINE_AUTO, "lstm_engine": ENGINE_AUTO, "exact_small_fwd": True, "exact_small_bwd": True,
           "small_rows": 8192, "direct_grad": False, "lstm_gemm16": True, "fuse_lstm_dropout": True,
-          "branch_streams": True, "lstm_pre16": True}
+          "branch_streams": True, "lstm_pre16": True, "defer_wgrad": True}
+
+
+def set_defer_wgrad(on: bool):
+    """Trainer mode: weight gradients of the small (M = batch rows) Linear layers on a second stream (default on)."""
+    _state["defer_wgrad"] = bool(on)
+
+
+_wgrad = {"streams": {}, "pending": False}
+
+
+def _wgrad_stream():
+    dev = torch.cuda.current_device()
+    st = _wgrad["streams"]
+    if dev not in st:
+        st[dev] = torch.cuda.Stream(device=dev)
+    return st[dev]
+
+
+def join_wgrad_stream():
+    """Make the current stream wait for the deferred weight-gradient GEMMs (call after backward, before the grads are
+    read).  A no-op when nothing was deferred."""
+    if _wgrad["pending"]:
+        torch.cuda.current_stream().wait_stream(_wgrad_stream())
+        _wgrad["pending"] = False
 
 
 def set_lstm_pre16(on: bool):
@@ -197,6 +221,11 @@ class _Linear(torch.autograd.Function):
             if db is not None:
                 call("deer_bias_act_bwd", ptr(dy2), ld_dy, None, 0, None, 0, ptr(db), M, N, 0)
         dw, dw_direct = _acc(pw) if ctx.needs_input_grad[0] else (None, False)
+        # Trainer mode, small layers (the serial fusion / head chain, M = batch rows): dW is not needed before the
+        # optimizer, so it leaves the dz -> dx critical path and runs on the weight-gradient stream, beside the
+        # next layers' dx GEMMs (each of these kernels fills a fraction of the machine); the trainer joins the
+        # stream before the gradient exchange (join_wgrad_stream).
+        defer = (dw is not None and dw_direct and _state["defer_wgrad"] and M < _state["small_rows"] and dz.is_cuda)
         dxs = []
         for i, x2 in enumerate(xs):
             ld, k0, K = ctx.meta[i]
@@ -206,8 +235,19 @@ class _Linear(torch.autograd.Function):
                 dxs.append(dx.view(ctx.in_shapes[i]))
             else:
                 dxs.append(None)
-            if dw is not None:
+            if dw is not None and not defer:
                 gemm(dz, N, 1, x2, ld, 0, dw.data_ptr() + 4 * k0, Ktot, N, K, M, beta=1.0, engine=_bwd_engine(M))
+        if defer:
+            cur = torch.cuda.current_stream()
+            aux = _wgrad_stream()
+            aux.wait_stream(cur)
+            with torch.cuda.stream(aux):
+                for i, x2 in enumerate(xs):
+                    ld, k0, K = ctx.meta[i]
+                    gemm(dz, N, 1, x2, ld, 0, dw.data_ptr() + 4 * k0, Ktot, N, K, M, beta=1.0, engine=_bwd_engine(M))
+                    x2.record_stream(aux)
+            dz.record_stream(aux)
+            _wgrad["pending"] = True
         return (None if dw_direct else dw, None if db_direct else db, None, None, *dxs)
 
 

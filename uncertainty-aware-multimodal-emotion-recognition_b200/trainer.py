@@ -152,6 +152,7 @@ class DEERDataParallelTrainer:
         losses, dE, _, _ = ops.nig_loss_raw(ev.detach(), None, targets, weights=self.loss_weights, want_grad=True,
                                             grad_scale=scale, stats_hook=hook, global_batch=gb)
         ev.backward(dE)
+        ops.join_wgrad_stream()   # deferred weight-gradient GEMMs of the small layers (ops._Linear.backward)
         self.last_losses = losses
         return losses
 
