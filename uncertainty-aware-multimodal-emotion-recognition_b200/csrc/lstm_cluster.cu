@@ -134,6 +134,35 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   return BF ? pack_bf2(a, b) : pack_h2(a, b);
 }
 
+// The gate epilogue is MUFU-bound (16 MUFU lanes per SM and clock; one ex2 + one rcp per sigmoid).  Two sigmoids share
+// ONE reciprocal: 1/a = b * rcp(a b), 1/b = a * rcp(a b); with the exponent clamped at 2^60 the product stays finite
+// (sigmoid < 1e-18 there).  Flush-to-zero MUFU forms: no denormal pre/post-scaling instructions around them.
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_ftz(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// (1 / (1 + 2^t0), 1 / (1 + 2^t1))
+__device__ __forceinline__ void sigmoid_pair_ex2(float t0, float t1, float& s0, float& s1) {
+  const float a0 = 1.f + ex2_ftz(fminf(t0, 60.f));
+  const float a1 = 1.f + ex2_ftz(fminf(t1, 60.f));
+  const float R = rcp_ftz(a0 * a1);
+  s0 = a1 * R;
+  s1 = a0 * R;
+}
+// (tanh x0, tanh x1) = 1 - 2 / (1 + e^{2x})
+__device__ __forceinline__ void tanh_pair(float x0, float x1, float& t0, float& t1) {
+  float s0, s1;
+  sigmoid_pair_ex2(x0 * 2.8853900817779268f, x1 * 2.8853900817779268f, s0, s1);
+  t0 = fmaf(-2.f, s0, 1.f);
+  t1 = fmaf(-2.f, s1, 1.f);
+}
+
 // byte offset of 16-byte chunk `c` (0..7) of row `row` inside a K-major SWIZZLE_128B tile whose 8-row groups are 1024 B apart
 __device__ __forceinline__ uint32_t sw128(int row, int c) {
   return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((c ^ (row & 7)) << 4));
@@ -372,10 +401,15 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
 #pragma unroll
         for (int n = 0; n < N; n++) x[n] += __uint_as_float(pre[n]);
       }
+      {
+        const float nsl = -1.4426950408889634f * sc;   // sigmoid(sc x) = 1 / (1 + 2^(nsl x))
 #pragma unroll
-      for (int n = 0; n < N; n++) {
-        const float z = x[n] * sc;
-        x[n] = fmaf(sc, __fdividef(1.f, 1.f + __expf(-z)), 1.f - sc);
+        for (int n = 0; n < N; n += 2) {
+          float s0, s1;
+          sigmoid_pair_ex2(x[n] * nsl, x[n + 1] * nsl, s0, s1);
+          x[n] = fmaf(sc, s0, 1.f - sc);
+          x[n + 1] = fmaf(sc, s1, 1.f - sc);
+        }
       }
 #pragma unroll
       for (int n = 0; n < N; n += 4)
@@ -397,11 +431,17 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
       }
       float hv[NQ];
 #pragma unroll
-      for (int i = 0; i < NQ; i++) {
-        const float cn = fmaf(gf[i], cst[i], gi[i] * gg[i]);
-        cst[i] = cn;
-        hv[i] = go[i] * tanh_f(cn);
+      for (int i = 0; i < NQ; i += 2) {
+        const float c0 = fmaf(gf[i], cst[i], gi[i] * gg[i]);
+        const float c1 = fmaf(gf[i + 1], cst[i + 1], gi[i + 1] * gg[i + 1]);
+        cst[i] = c0;
+        cst[i + 1] = c1;
+        float t0, t1;
+        tanh_pair(c0, c1, t0, t1);
+        hv[i] = go[i] * t0;
+        hv[i + 1] = go[i + 1] * t1;
         sh[(q * NQ + i) * 8 + j] = __float2half_rn(hv[i]);
+        sh[(q * NQ + i + 1) * 8 + j] = __float2half_rn(hv[i + 1]);
       }
       if (warp == 0 && lane == 0) Q_PROF(4);
       if (s + 1 < T) {
@@ -665,9 +705,12 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
       const int kb = ul >> 4, ch = (ul & 15) >> 1;
       float4 dp[NQ];
       uint2 dp16[NQ];
+      float tcv[NQ];
+#pragma unroll
+      for (int i = 0; i < NQ; i += 2) tanh_pair(vc[i], vc[i + 1], tcv[i], tcv[i + 1]);
 #pragma unroll
       for (int i = 0; i < NQ; i++) {
-        const float tc_ = tanh_f(vc[i]);
+        const float tc_ = tcv[i];
         const float d_o = dh[i] * tc_;
         const float dcc = fmaf(dh[i] * vo[i], 1.f - tc_ * tc_, dc[i]);
         dc[i] = dcc * vf[i];

@@ -20,18 +20,51 @@ namespace deer {
 
 constexpr int NSTAT = DEER_LOSS_NSTAT;  // 0 nll,1 reg,2 kl_alpha,3 kl_beta,4 sum u, 5..14 cnt, 15..24 conf, 25..34 err
 constexpr int LOSS_THREADS = 192;       // multiple of every supported D (1,2,3,4,6,8)
+constexpr int LOSS_MIN_BLOCKS = 5;      // 64 registers: two P2 pairs in flight per thread without spills
 constexpr int NBINS = 10;
 constexpr long long DEER_NIG_MAX_ELEMENTS = (1ll << 31) - (1ll << 24);  // 32-bit element indices + unroll slack
 constexpr long long DEER_NIG_L2_KEEP_BYTES = 72ll << 20;  // operand footprint up to which pass 1 pins its loads in L2
 
-struct Nig {
-  float gamma, nu, alpha, beta;
-  float sn, sa, sb;  // softplus'(raw) of nu / alpha / beta (chain rule back to the evidence)
+// ------------------------------------------------------------------------------------------------------------------
+// Value types.  The loss passes are instruction-ISSUE bound (ncu: 60-73 % issue-active, DRAM at 45-55 %), and two thirds
+// of what they issue is fp32 add / mul / fma.  Blackwell's packed fp32 instructions (add/mul/fma.f32x2 -> FADD2 /
+// FMUL2 / FFMA2) do two lanes' worth of that arithmetic per issue slot, so every thread processes its elements in
+// PAIRS: P2 holds the same quantity of two independent (sample, dim) elements, arithmetic goes through the packed
+// instructions, and the per-component work (MUFU, selects, compares, bin updates) stays scalar.  The math below is
+// written once, templated on the value type V = float (tail elements) or P2 (pairs): identical numerics.
+struct P2 {
+  float x, y;
+  __device__ __forceinline__ P2() {}
+  __device__ __forceinline__ P2(float a) : x(a), y(a) {}
+  __device__ __forceinline__ P2(float a, float b) : x(a), y(b) {}
 };
-
-// The loss kernels are instruction-issue bound (ncu: 70 % issue-active at 47 % occupancy), so the transcendentals are
-// single MUFU instructions with flush-to-zero semantics (no denormal pre/post-scaling around ex2/lg2/rcp) and every
-// data-dependent branch is a select; relative error ~1e-6, far inside the 1e-3 gate.
+#define DEER_P2_BIN(NAME, PTX)                                                                                          \
+  __device__ __forceinline__ P2 NAME(P2 a, P2 b) {                                                                      \
+    P2 o;                                                                                                               \
+    asm("{\n\t.reg .b64 ra, rb, ro;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t" PTX                          \
+        " ro, ra, rb;\n\tmov.b64 {%0, %1}, ro;\n\t}"                                                                    \
+        : "=f"(o.x), "=f"(o.y)                                                                                          \
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));                                                                      \
+    return o;                                                                                                           \
+  }
+DEER_P2_BIN(operator+, "add.f32x2")
+DEER_P2_BIN(operator-, "sub.f32x2")
+DEER_P2_BIN(operator*, "mul.f32x2")
+#undef DEER_P2_BIN
+__device__ __forceinline__ P2 vfma(P2 a, P2 b, P2 c) {
+  P2 o;
+  asm("{\n\t.reg .b64 ra, rb, rc, ro;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 ro, ra, rb, rc;\n\tmov.b64 {%0, %1}, ro;\n\t}"
+      : "=f"(o.x), "=f"(o.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return o;
+}
+__device__ __forceinline__ float vfma(float a, float b, float c) { return fmaf(a, b, c); }
+struct M2 {
+  bool x, y;
+};
+// single MUFU instructions with flush-to-zero semantics (no denormal pre/post-scaling around ex2/lg2/rcp); relative
+// error ~1e-6, far inside the 1e-3 gate
 __device__ __forceinline__ float fex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -47,44 +80,87 @@ __device__ __forceinline__ float frcp(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ float fexp(float x) { return fex2(x * 1.4426950408889634f); }
-__device__ __forceinline__ float flog(float x) { return flg2(x) * 0.6931471805599453f; }
+__device__ __forceinline__ float vrcp(float x) { return frcp(x); }
+__device__ __forceinline__ P2 vrcp(P2 a) { return P2(frcp(a.x), frcp(a.y)); }
+__device__ __forceinline__ float vlog(float x) { return flg2(x) * 0.6931471805599453f; }
+__device__ __forceinline__ P2 vlog(P2 a) { return P2(flg2(a.x), flg2(a.y)) * P2(0.6931471805599453f); }
+// exp(-|x|): the -|.| is an operand modifier of the MUFU instruction
+__device__ __forceinline__ float vexp_negabs(float x) { return fex2(-fabsf(x * 1.4426950408889634f)); }
+__device__ __forceinline__ P2 vexp_negabs(P2 a) {
+  const P2 t = a * P2(1.4426950408889634f);
+  return P2(fex2(-fabsf(t.x)), fex2(-fabsf(t.y)));
+}
+__device__ __forceinline__ float vmax0(float x) { return fmaxf(x, 0.f); }
+__device__ __forceinline__ P2 vmax0(P2 a) { return P2(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f)); }
+__device__ __forceinline__ float vmin(float x, float c) { return fminf(x, c); }
+__device__ __forceinline__ P2 vmin(P2 a, float c) { return P2(fminf(a.x, c), fminf(a.y, c)); }
+__device__ __forceinline__ float vabs(float x) { return fabsf(x); }
+__device__ __forceinline__ P2 vabs(P2 a) { return P2(fabsf(a.x), fabsf(a.y)); }
+__device__ __forceinline__ bool vgt(float a, float c) { return a > c; }
+__device__ __forceinline__ M2 vgt(P2 a, float c) { return M2{a.x > c, a.y > c}; }
+__device__ __forceinline__ bool vlt(float a, float c) { return a < c; }
+__device__ __forceinline__ M2 vlt(P2 a, float c) { return M2{a.x < c, a.y < c}; }
+__device__ __forceinline__ bool vge(float a, float c) { return a >= c; }
+__device__ __forceinline__ M2 vge(P2 a, float c) { return M2{a.x >= c, a.y >= c}; }
+__device__ __forceinline__ float vsel(bool m, float a, float b) { return m ? a : b; }
+__device__ __forceinline__ P2 vsel(M2 m, P2 a, P2 b) { return P2(m.x ? a.x : b.x, m.y ? a.y : b.y); }
+// sign(err) * s  (0 at err == 0)
+__device__ __forceinline__ float vsignmul(float err, float s) { return err > 0.f ? s : (err < 0.f ? -s : 0.f); }
+__device__ __forceinline__ P2 vsignmul(P2 err, P2 s) { return P2(vsignmul(err.x, s.x), vsignmul(err.y, s.y)); }
+__device__ __forceinline__ float hsum(float a) { return a; }
+__device__ __forceinline__ float hsum(P2 a) { return a.x + a.y; }
+
+template <class V>
+struct NigT {
+  V gamma, nu, alpha, beta;
+  V sn, sa, sb;  // softplus'(raw) of nu / alpha / beta (chain rule back to the evidence)
+};
+
 // softplus(x) (torch: beta=1, threshold=20) and its derivative sigmoid(x) from ONE exponential e = exp(-|x|):
 //   softplus = max(x,0) + log1p(e),  log1p(e) = log(u) + (e - (u - 1)) / u with u = fl(1 + e): the first-order
 //   correction of the rounding of 1 + e (both differences are exact in fp32), reusing the reciprocal sigmoid needs
-__device__ __forceinline__ void softplus_fast(float x, float& sp, float& sg) {
-  const float e = fexp(-fabsf(x));
-  const float u = 1.f + e;
-  const float r = frcp(u);
-  const float l = fmaf(e - (u - 1.f), r, flog(u));
-  const bool lin = x > 20.f;
-  sp = lin ? x : fmaxf(x, 0.f) + l;
-  sg = lin ? 1.f : (x >= 0.f ? r : e * r);
+template <class V>
+__device__ __forceinline__ void softplus_fast(V x, V& sp, V& sg) {
+  const V e = vexp_negabs(x);
+  const V u = V(1.f) + e;
+  const V r = vrcp(u);
+  const V l = vfma(e - (u - V(1.f)), r, vlog(u));
+  // torch's linear branch (x > 20 -> x, derivative 1) needs no select in fp32: there log1p(e) < 2.1e-9 is below half an
+  // ulp of x (>= 9.5e-7), so x + l == x, and r = 1 / (1 + e) rounds to exactly 1
+  sp = vmax0(x) + l;
+  sg = vsel(vge(x, 0.f), r, e * r);
 }
 // lgamma(a), a >= 1: shift a < 5 by 4 with one product, then Stirling through a^-7 (truncation < 5e-10 at a = 5;
 // fp32 rounding of (a-1/2) ln a dominates: < 1e-6 absolute for a in [1, 1e5])
-__device__ __forceinline__ float lgamma_ge1_fast(float a) {
-  const bool sh = a < 5.f;
-  const float as = sh ? a : 1.f;
-  const float lp = sh ? flog(as * (as + 1.f) * ((as + 2.f) * (as + 3.f))) : 0.f;
-  a = sh ? a + 4.f : a;
-  const float r = frcp(a), r2 = r * r;
-  const float s = r * (0.0833333333f - r2 * (0.00277777778f - r2 * (0.000793650794f - r2 * 0.000595238095f)));
-  return (a - 0.5f) * flog(a) - a + 0.918938533f + s - lp;
+template <class V>
+__device__ __forceinline__ V lgamma_ge1_fast(V a) {
+  const auto sh = vlt(a, 5.f);
+  const V as = vsel(sh, a, V(1.f));
+  const V lp = vsel(sh, vlog((as * (as + V(1.f))) * ((as + V(2.f)) * (as + V(3.f)))), V(0.f));
+  a = vsel(sh, a + V(4.f), a);
+  const V r = vrcp(a), r2 = r * r;
+  // r * (1/12 - r2 (1/360 - r2 (1/1260 - r2/1680))), Horner with signed coefficients
+  const V s = r * vfma(r2, vfma(r2, vfma(r2, V(-0.000595238095f), V(0.000793650794f)), V(-0.00277777778f)),
+                       V(0.0833333333f));
+  return vfma(a - V(0.5f), vlog(a), V(0.918938533f) - a) + (s - lp);
 }
-// digamma(x), x >= 1: psi(x) = psi(x+4) - sum_{i<4} 1/(x+i), the sum as ONE quotient p'(x)/p(x); series through x^-8
-__device__ __forceinline__ float digamma_ge1_fast(float x) {
-  const bool sh = x < 5.f;
-  const float t0 = sh ? x : 1.f, t1 = t0 + 1.f, t2 = t0 + 2.f, t3 = t0 + 3.f;
-  const float p01 = t0 * t1, p23 = t2 * t3;
+// digamma(x), x >= 1: psi(x) = psi(x+4) - sum_{i<4} 1/(x+i), the sum as ONE quotient p'(x)/p(x); series through (x+4)^-8
+template <class V>
+__device__ __forceinline__ V digamma_ge1_fast(V x) {
+  // the shift is applied for every x (it is exact); the shift terms use min(x, 1e6) so that p * x cannot overflow:
+  // beyond 1e6 that changes psi by < 4e-6 absolute (psi > 13.8 there)
+  const V t0 = vmin(x, 1e6f), t1 = t0 + V(1.f), t2 = t0 + V(2.f), t3 = t0 + V(3.f);
+  const V p01 = t0 * t1, p23 = t2 * t3;
   // d/dx [t0 t1 t2 t3] = (t0 + t1) p23 + (t2 + t3) p01
-  const float p = p01 * p23;
-  x = sh ? x + 4.f : x;
-  const float R = frcp(p * x);  // one MUFU for both 1/p and 1/x (p <= 1680, x < 1e5 on this path)
-  const float corr = sh ? ((t0 + t1) * p23 + (t2 + t3) * p01) * (x * R) : 0.f;
-  const float r = p * R, r2 = r * r;
-  return flog(x) - 0.5f * r -
-         r2 * (0.0833333333f - r2 * (0.00833333333f - r2 * (0.00396825397f - r2 * 0.00416666667f))) - corr;
+  const V p = p01 * p23;
+  x = x + V(4.f);
+  const V R = vrcp(p * x);  // one MUFU for both 1/p and 1/x
+  const V corr = vfma(t0 + t1, p23, (t2 + t3) * p01) * (x * R);
+  const V r = p * R, r2 = r * r;
+  // r2 (1/12 - r2 (1/120 - r2 (1/252 - r2/240))), Horner with signed coefficients
+  const V ser = r2 * vfma(r2, vfma(r2, vfma(r2, V(-0.00416666667f), V(0.00396825397f)), V(-0.00833333333f)),
+                          V(0.0833333333f));
+  return vfma(r, V(-0.5f), vlog(x)) - ser - corr;
 }
 
 // raw operands of one (sample, dim) element; fetched for several elements before any of them is processed so that
@@ -113,11 +189,11 @@ __device__ __forceinline__ float ld_keep_f(const float* p, unsigned long long po
   asm volatile("ld.global.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
   return v;
 }
-template <bool KEEP>
+template <bool KEEP, bool from_evidence>
 __device__ __forceinline__ RawNig fetch_nig(const float* __restrict__ evidence, const float* __restrict__ gamma,
                                             const float* __restrict__ nu, const float* __restrict__ alpha,
                                             const float* __restrict__ beta, const float* __restrict__ targets,
-                                            int e, int from_evidence, unsigned long long pol) {
+                                            int e, unsigned long long pol) {
   RawNig r;
   if (KEEP) {
     if (from_evidence) r.v = ld_keep_f4(reinterpret_cast<const float4*>(evidence) + e, pol);
@@ -131,52 +207,28 @@ __device__ __forceinline__ RawNig fetch_nig(const float* __restrict__ evidence, 
   }
   return r;
 }
-__device__ __forceinline__ Nig derive_nig(const RawNig& r, int from_evidence) {
-  Nig p;
-  p.sn = p.sa = p.sb = 1.f;
+// (e0, e1, e2, e3) of one element (V = float) or of two elements side by side (V = P2)
+template <bool from_evidence, class V>
+__device__ __forceinline__ NigT<V> derive_nig(V e0, V e1, V e2, V e3) {
+  NigT<V> p;
+  p.sn = p.sa = p.sb = V(1.f);
+  p.gamma = e0;
   if (from_evidence) {
-    float sp;
-    p.gamma = r.v.x;
-    softplus_fast(r.v.y, sp, p.sn);
-    p.nu = sp + 1e-6f;
-    softplus_fast(r.v.z, sp, p.sa);
-    p.alpha = sp + 1.0f;
-    softplus_fast(r.v.w, sp, p.sb);
-    p.beta = sp + 1e-6f;
+    V sp;
+    softplus_fast(e1, sp, p.sn);
+    p.nu = sp + V(1e-6f);
+    softplus_fast(e2, sp, p.sa);
+    p.alpha = sp + V(1.0f);
+    softplus_fast(e3, sp, p.sb);
+    p.beta = sp + V(1e-6f);
   } else {
-    p.gamma = r.v.x;
-    p.nu = r.v.y;
-    p.alpha = r.v.z;
-    p.beta = r.v.w;
+    p.nu = e1;
+    p.alpha = e2;
+    p.beta = e3;
   }
   return p;
 }
-constexpr int LOSS_UNROLL = 4;
-
-__device__ __forceinline__ Nig load_nig(const float* __restrict__ evidence, const float* __restrict__ gamma,
-                                        const float* __restrict__ nu, const float* __restrict__ alpha,
-                                        const float* __restrict__ beta, long long e, int from_evidence, float4& raw) {
-  Nig p;
-  p.sn = p.sa = p.sb = 1.f;
-  if (from_evidence) {
-    raw = __ldcs(reinterpret_cast<const float4*>(evidence) + e);
-    float sp;
-    p.gamma = raw.x;
-    softplus_fast(raw.y, sp, p.sn);
-    p.nu = sp + 1e-6f;
-    softplus_fast(raw.z, sp, p.sa);
-    p.alpha = sp + 1.0f;
-    softplus_fast(raw.w, sp, p.sb);
-    p.beta = sp + 1e-6f;
-  } else {
-    raw = make_float4(0.f, 0.f, 0.f, 0.f);
-    p.gamma = gamma[e];
-    p.nu = nu[e];
-    p.alpha = alpha[e];
-    p.beta = beta[e];
-  }
-  return p;
-}
+constexpr int LOSS_UNROLL = 4;   // elements in flight per thread = two P2 pairs
 
 __device__ __forceinline__ int ece_bin(float conf, const float* __restrict__ edges) {
   // (edges[k], edges[k+1]]  (losses.py:207-215); -1 when outside every bin (NaN / conf <= 0 / conf > 1)
@@ -190,13 +242,52 @@ struct NigPlanes {
   float* p[7];  // gamma, nu, alpha, beta, aleatoric, epistemic, total: [B*D] each
 };
 
+// ---- phase 1, per-value math (everything that is plain arithmetic); the bin update / stores stay per component
+template <class V>
+struct StatsOut {
+  V nll, reg, kla, klb, u, conf, aerr;   // contributions to the five sums; confidence and |err| for the ECE bins
+  V alea, epis;                          // head outputs (when requested)
+};
+template <class V>
+__device__ __forceinline__ StatsOut<V> stats_math(const NigT<V>& p, V y, float eps, float inv_two_pi_eps, float log1eps,
+                                                  bool eps_is_1e8, int nig_out) {
+  StatsOut<V> o;
+  const V err = y - p.gamma;
+  const V e2 = err * err;
+  const V S = vfma(p.nu * V(0.5f), e2, p.beta + V(eps));
+  const V lb = vlog(p.beta + V(eps));
+  const V lp = vfma(vlog(p.nu * V(inv_two_pi_eps)), V(0.5f), p.alpha * lb) - lgamma_ge1_fast(p.alpha + V(eps)) -
+               (p.alpha + V(0.5f)) * vlog(S);
+  o.nll = V(0.f) - lp;
+  o.reg = e2 * vfma(p.nu, e2, p.beta + p.beta);
+  const V am1 = p.alpha - V(1.f);
+  o.kla = am1 * am1;
+  const V dl = lb - V(log1eps);
+  o.klb = dl * dl;
+  const V den = am1 + V(eps);
+  const V dpb = den + p.beta;
+  const V rdc = vrcp(den * dpb);  // 1/den and conf = 1/(1+u) = den/(den+beta) from one reciprocal
+  const V u = p.beta * (dpb * rdc);
+  o.u = eps_is_1e8 ? u : p.beta * vrcp(am1 + V(1e-8f));
+  o.conf = den * (den * rdc);
+  o.aerr = vabs(err);
+  if (nig_out) {
+    const V ran = vrcp(am1 * p.nu);
+    o.alea = p.beta * (p.nu * ran);
+    o.epis = p.beta * ran;
+  }
+  return o;
+}
+
 // element indices are 32-bit inside the kernels (the entry points reject B*D >= 2^31 - grid slack)
-template <bool KEEP>
-__global__ void __launch_bounds__(LOSS_THREADS, 6) nig_loss_stats_kernel(
+// from_evidence is a template parameter: as a runtime flag both load variants were emitted predicated, and the
+// predicated-off half still took ~10 issue slots per element
+template <bool KEEP, bool from_evidence>
+__global__ void __launch_bounds__(LOSS_THREADS, LOSS_MIN_BLOCKS) nig_loss_stats_kernel(
     const float* __restrict__ evidence, const float* __restrict__ gamma, const float* __restrict__ nu,
     const float* __restrict__ alpha, const float* __restrict__ beta, const float* __restrict__ targets,
     const float* __restrict__ bin_edges, float* __restrict__ stats, const NigPlanes planes, int nig_out, int total, int D,
-    int from_evidence, float eps) {
+    float eps) {
   DEER_PDL_ENTRY();
   __shared__ float bins[3 * NBINS][LOSS_THREADS];  // private column per thread: conflict-free, no atomics
   __shared__ float sedges[NBINS + 1];
@@ -208,41 +299,18 @@ __global__ void __launch_bounds__(LOSS_THREADS, 6) nig_loss_stats_kernel(
   __syncthreads();
   const float inv_two_pi_eps = (float)(1.0 / (6.283185307179586 + (double)eps));
   const float log1eps = logf(1.f + eps);
-  float a_nll = 0.f, a_reg = 0.f, a_kla = 0.f, a_klb = 0.f, a_u = 0.f;
+  const bool eps_is_1e8 = eps == 1e-8f;
+  P2 a_nll(0.f), a_reg(0.f), a_kla(0.f), a_klb(0.f), a_u(0.f);   // per-component partial sums, folded at the end
   const unsigned long long pol = KEEP ? l2_evict_last_policy() : 0ull;
   const int stride = (int)gridDim.x * LOSS_THREADS;  // multiple of D -> dimension fixed per thread
-  // one element: everything except the shared-memory bin update order is independent across elements, so the
-  // unrolled main loop (no bounds checks, no early exit) lets the compiler interleave LOSS_UNROLL dependency chains
-  auto element = [&](const RawNig& raw, int e) {
-    const Nig p = derive_nig(raw, from_evidence);
-    const float y = raw.y;
-    const float err = y - p.gamma;
-    const float e2 = err * err;
-    const float S = p.beta + 0.5f * p.nu * e2 + eps;
-    const float lb = flog(p.beta + eps);
-    const float lp = 0.5f * flog(p.nu * inv_two_pi_eps) + p.alpha * lb - lgamma_ge1_fast(p.alpha + eps) -
-                     (p.alpha + 0.5f) * flog(S);
-    a_nll -= lp;
-    a_reg += e2 * (2.f * p.beta + p.nu * e2);
-    const float am1 = p.alpha - 1.f;
-    a_kla += am1 * am1;
-    const float dl = lb - log1eps;
-    a_klb += dl * dl;
-    const float den = am1 + eps;
-    const float rdc = frcp(den * (den + p.beta));  // 1/den and conf = 1/(1+u) = den/(den+beta) from one reciprocal
-    const float u = p.beta * ((den + p.beta) * rdc);
-    a_u += eps == 1e-8f ? u : p.beta * frcp(am1 + 1e-8f);
-    const float conf = den * (den * rdc);
+  auto tail = [&](float conf, float aerr, const NigT<float>& p, float alea, float epis, int e) {
     const int k = ece_bin(conf, sedges);
     if (k >= 0) {
       bins[k][tid] += 1.f;
       bins[NBINS + k][tid] += conf;
-      bins[2 * NBINS + k][tid] += fabsf(err);
+      bins[2 * NBINS + k][tid] += aerr;
     }
     if (nig_out) {
-      const float ran = frcp(am1 * p.nu);
-      const float alea = p.beta * (p.nu * ran);
-      const float epis = p.beta * ran;
       // plane bases live in the constant bank: one IMAD.WIDE per store address
       __stcs(planes.p[0] + e, p.gamma);
       __stcs(planes.p[1] + e, p.nu);
@@ -253,22 +321,47 @@ __global__ void __launch_bounds__(LOSS_THREADS, 6) nig_loss_stats_kernel(
       __stcs(planes.p[6] + e, alea + epis);
     }
   };
+  auto pair = [&](const RawNig& r0, const RawNig& r1, int e0, int e1) {
+    const NigT<P2> p = derive_nig<from_evidence>(P2(r0.v.x, r1.v.x), P2(r0.v.y, r1.v.y), P2(r0.v.z, r1.v.z),
+                                                 P2(r0.v.w, r1.v.w));
+    const StatsOut<P2> o = stats_math(p, P2(r0.y, r1.y), eps, inv_two_pi_eps, log1eps, eps_is_1e8, nig_out);
+    a_nll = a_nll + o.nll;
+    a_reg = a_reg + o.reg;
+    a_kla = a_kla + o.kla;
+    a_klb = a_klb + o.klb;
+    a_u = a_u + o.u;
+    NigT<float> q0, q1;
+    q0.gamma = p.gamma.x; q0.nu = p.nu.x; q0.alpha = p.alpha.x; q0.beta = p.beta.x;
+    q1.gamma = p.gamma.y; q1.nu = p.nu.y; q1.alpha = p.alpha.y; q1.beta = p.beta.y;
+    tail(o.conf.x, o.aerr.x, q0, o.alea.x, o.epis.x, e0);
+    tail(o.conf.y, o.aerr.y, q1, o.alea.y, o.epis.y, e1);
+  };
+  auto single = [&](const RawNig& r, int e) {
+    const NigT<float> p = derive_nig<from_evidence>(r.v.x, r.v.y, r.v.z, r.v.w);
+    const StatsOut<float> o = stats_math(p, r.y, eps, inv_two_pi_eps, log1eps, eps_is_1e8, nig_out);
+    a_nll.x += o.nll;
+    a_reg.x += o.reg;
+    a_kla.x += o.kla;
+    a_klb.x += o.klb;
+    a_u.x += o.u;
+    tail(o.conf, o.aerr, p, o.alea, o.epis, e);
+  };
   int eb = (int)blockIdx.x * LOSS_THREADS + tid;
   for (; eb + (LOSS_UNROLL - 1) * stride < total; eb += LOSS_UNROLL * stride) {
     RawNig rr[LOSS_UNROLL];
 #pragma unroll
     for (int q = 0; q < LOSS_UNROLL; q++)
-      rr[q] = fetch_nig<KEEP>(evidence, gamma, nu, alpha, beta, targets, eb + q * stride, from_evidence, pol);
+      rr[q] = fetch_nig<KEEP, from_evidence>(evidence, gamma, nu, alpha, beta, targets, eb + q * stride, pol);
 #pragma unroll
-    for (int q = 0; q < LOSS_UNROLL; q++) element(rr[q], eb + q * stride);
+    for (int q = 0; q < LOSS_UNROLL; q += 2) pair(rr[q], rr[q + 1], eb + q * stride, eb + (q + 1) * stride);
   }
   for (; eb < total; eb += stride)
-    element(fetch_nig<KEEP>(evidence, gamma, nu, alpha, beta, targets, eb, from_evidence, pol), eb);
-  red[0][tid] = a_nll;
-  red[1][tid] = a_reg;
-  red[2][tid] = a_kla;
-  red[3][tid] = a_klb;
-  red[4][tid] = a_u;
+    single(fetch_nig<KEEP, from_evidence>(evidence, gamma, nu, alpha, beta, targets, eb, pol), eb);
+  red[0][tid] = hsum(a_nll);
+  red[1][tid] = hsum(a_reg);
+  red[2][tid] = hsum(a_kla);
+  red[3][tid] = hsum(a_klb);
+  red[4][tid] = hsum(a_u);
   __syncthreads();
   // thread (d, s) for s < 35 sums the columns of threads whose dimension is d (tid % D == d)
   const int first_e_dim = ((int)blockIdx.x * LOSS_THREADS) % D;
@@ -290,12 +383,51 @@ struct DimCoef {
   float w;            // task weight
 };
 
-__global__ void __launch_bounds__(LOSS_THREADS, 6) nig_loss_finish_kernel(
+// ---- phase 2, per-value math: d total / d (gamma, nu, alpha, beta) up to the ECE term (which needs the element's bin)
+template <class V>
+struct GradOut {
+  V dg, dn, da, db;
+  V conf, u, rden, err;   // for the ECE / cross-dimension terms
+};
+template <class V>
+__device__ __forceinline__ GradOut<V> grad_math(const NigT<V>& p, V y, float eps, float log1eps, float reg_w, float kl_w) {
+  GradOut<V> o;
+  const V err = y - p.gamma, e2 = err * err;
+  const V S = vfma(p.nu * V(0.5f), e2, p.beta + V(eps));
+  const V ah = p.alpha + V(0.5f);
+  const V be = p.beta + V(eps);
+  // reciprocals in pairs: 1/a = b * rcp(ab), 1/b = a * rcp(ab) (the MUFU pipe is the busiest one in this kernel)
+  const V rSb = vrcp(S * be);
+  const V rS = be * rSb, rbe = S * rSb, lbe = vlog(be);
+  const V am1 = p.alpha - V(1.f);
+  const V den = am1 + V(eps);
+  const V rnd = vrcp(p.nu * den);
+  const V rnu = den * rnd, rden = p.nu * rnd;
+  const V ahrS = ah * rS;
+  // nll + reg + kl
+  //   dg = -ah nu err / S            - reg_w (4 beta err + 4 nu e2 err)
+  //   dn = -1/(2 nu) + ah e2 / (2 S) + reg_w e2^2
+  //   da = -log(be) + psi(alpha+eps) + log S + kl_w 2 (alpha - 1)
+  //   db = -alpha / be + ah / S      + reg_w 2 e2 + kl_w 0.2 (log be - log(1+eps)) / be
+  const V nue2 = p.nu * e2;
+  o.dg = V(0.f) - err * vfma(V(4.f * reg_w), p.beta + nue2, ahrS * p.nu);
+  o.dn = vfma(e2, vfma(V(reg_w), e2, ahrS * V(0.5f)), rnu * V(-0.5f));
+  o.da = vfma(V(2.f * kl_w), am1, digamma_ge1_fast(p.alpha + V(eps)) + (vlog(S) - lbe));
+  o.db = vfma(V(2.f * reg_w), e2, ahrS) + rbe * vfma(V(0.2f * kl_w), lbe - V(log1eps), V(0.f) - p.alpha);
+  o.u = p.beta * rden;
+  o.conf = vrcp(V(1.f) + o.u);
+  o.rden = rden;
+  o.err = err;
+  return o;
+}
+
+template <bool from_evidence>
+__global__ void __launch_bounds__(LOSS_THREADS, LOSS_MIN_BLOCKS) nig_loss_finish_kernel(
     const float* __restrict__ evidence, const float* __restrict__ gamma, const float* __restrict__ nu,
     const float* __restrict__ alpha, const float* __restrict__ beta, const float* __restrict__ targets,
     const float* __restrict__ bin_edges, const float* __restrict__ stats, const float* __restrict__ task_weights,
     float reg_w, float kl_w, float ece_w, float cross_w, float eps, int total_local, long long B_global, int D,
-    int from_evidence, float grad_scale, float* __restrict__ losses, float* __restrict__ d_out) {
+    float grad_scale, float* __restrict__ losses, float* __restrict__ d_out) {
   DEER_PDL_ENTRY();
   __shared__ DimCoef coef[8];
   __shared__ float sedges[NBINS + 1];
@@ -358,82 +490,75 @@ __global__ void __launch_bounds__(LOSS_THREADS, 6) nig_loss_finish_kernel(
   }
   if (d_out == nullptr) return;
   const float invD = 1.f / (float)D;
-  const float base = grad_scale * invD * invN;
   const float log1eps = logf(1.f + eps);
   const int stride = (int)gridDim.x * LOSS_THREADS;  // multiple of D: the dimension is fixed per thread
   const int d = ((int)blockIdx.x * LOSS_THREADS + tid) % D;
   const float w = coef[d].w;
+  const float base_w = grad_scale * invD * invN * w;   // task weight folded into the output scale
   const bool eps_is_1e8 = eps == 1e-8f;
+  // cross-dimension term enters UNWEIGHTED by the task weight: pre-divide by w where w != 0 (w == 0: term dropped,
+  // handled by the separate scale below)
   const float cross_c = (cross_w > 0.f && D > 1) ? cross_w * coef[d].cross : 0.f;
-  auto element = [&](const RawNig& raw, int e) {
-    const Nig p = derive_nig(raw, from_evidence);
-    const float y = raw.y;
-    const float err = y - p.gamma, e2 = err * err;
-    const float S = p.beta + 0.5f * p.nu * e2 + eps;
-    const float ah = p.alpha + 0.5f;
-    const float be = p.beta + eps;
-    // reciprocals in pairs: 1/a = b * rcp(ab), 1/b = a * rcp(ab) (the MUFU pipe is the busiest one in this kernel)
-    const float rSb = frcp(S * be);
-    const float rS = be * rSb, rbe = S * rSb, lbe = flog(be);
-    const float am1 = p.alpha - 1.f;
-    const float den = am1 + eps;
-    const float rnd = frcp(p.nu * den);
-    const float rnu = den * rnd, rden = p.nu * rnd;
-    // nll
-    float dg = -ah * p.nu * err * rS;
-    float dn = -0.5f * rnu + ah * e2 * 0.5f * rS;
-    float da = -lbe + digamma_ge1_fast(p.alpha + eps) + flog(S);
-    float db = -p.alpha * rbe + ah * rS;
-    // reg
-    dg += reg_w * (-(4.f * p.beta * err + 4.f * p.nu * e2 * err));
-    dn += reg_w * e2 * e2;
-    db += reg_w * 2.f * e2;
-    // kl
-    da += kl_w * 2.f * am1;
-    db += kl_w * 0.2f * (lbe - log1eps) * rbe;
-    // ece
-    const float u = p.beta * rden;
-    const float conf = frcp(1.f + u);
-    if (ece_w > 0.f) {  // uniform
-      const int k = ece_bin(conf, sedges);
-      const float sg = k >= 0 ? coef[d].sign[max(k, 0)] * ece_w : 0.f;
-      const float t = -sg * conf * conf * rden;  // sg * dconf/du * 1/den
-      db += t;
-      da -= t * u;
-      dg += err > 0.f ? -sg : (err < 0.f ? sg : 0.f);
+  const float base = grad_scale * invD * invN;
+  const float ece_on = ece_w > 0.f ? ece_w : 0.f;
+  const float* __restrict__ sgn = coef[d].sign;
+  // ECE bin sign of one element (scalar: a bin search and a shared-memory lookup), pre-multiplied by the ECE weight
+  auto bin_sign = [&](float conf) -> float {
+    const int k = ece_bin(conf, sedges);
+    return k >= 0 ? sgn[max(k, 0)] * ece_on : 0.f;
+  };
+  // ECE and cross-dimension corrections, task weight, chain rule back to the evidence: value-typed like the rest
+  auto finish = [&](auto g, const auto& p, auto sg) {
+    using V = decltype(g.dg);
+    if (ece_on > 0.f) {  // uniform
+      const V t = V(0.f) - sg * (g.conf * g.conf) * g.rden;  // sg * dconf/du * 1/den
+      g.db = g.db + t;
+      g.da = g.da - t * g.u;
+      g.dg = g.dg - vsignmul(g.err, sg);
     }
-    dg *= w;
-    dn *= w;
-    da *= w;
-    db *= w;
-    // cross-dimension consistency: d/d ubar_d * (1/N) * du/d(alpha,beta), u = beta/(alpha-1+1e-8)
-    if (cross_w > 0.f && D > 1) {  // uniform
-      const float r8 = eps_is_1e8 ? rden : frcp(am1 + 1e-8f);  // same denominator under the default epsilon
-      db += cross_c * r8;
-      da += cross_c * (-p.beta * r8 * r8);
+    V ox = g.dg * V(base_w), oy = g.dn * V(base_w), oz = g.da * V(base_w), ow = g.db * V(base_w);
+    // cross-dimension consistency: d/d ubar_d * (1/N) * du/d(alpha,beta), u = beta/(alpha-1+1e-8); not task-weighted
+    if (cross_c != 0.f) {  // uniform
+      const V r8 = eps_is_1e8 ? g.rden : vrcp((p.alpha - V(1.f)) + V(1e-8f));  // same denominator under the default epsilon
+      const V cb = r8 * V(base * cross_c);
+      ow = ow + cb;
+      oz = oz - cb * (p.beta * r8);
     }
-    float4 o;
     if (from_evidence) {
-      o.x = base * dg;
-      o.y = base * dn * p.sn;
-      o.z = base * da * p.sa;
-      o.w = base * db * p.sb;
-    } else {
-      o = make_float4(base * dg, base * dn, base * da, base * db);
+      oy = oy * p.sn;
+      oz = oz * p.sa;
+      ow = ow * p.sb;
     }
-    __stcs(reinterpret_cast<float4*>(d_out) + e, o);
+    g.dg = ox; g.dn = oy; g.da = oz; g.db = ow;
+    return g;
+  };
+  auto pair = [&](const RawNig& r0, const RawNig& r1, int e0, int e1) {
+    const NigT<P2> p = derive_nig<from_evidence>(P2(r0.v.x, r1.v.x), P2(r0.v.y, r1.v.y), P2(r0.v.z, r1.v.z),
+                                                 P2(r0.v.w, r1.v.w));
+    GradOut<P2> g = grad_math(p, P2(r0.y, r1.y), eps, log1eps, reg_w, kl_w);
+    const P2 sg = ece_on > 0.f ? P2(bin_sign(g.conf.x), bin_sign(g.conf.y)) : P2(0.f);
+    g = finish(g, p, sg);
+    __stcs(reinterpret_cast<float4*>(d_out) + e0, make_float4(g.dg.x, g.dn.x, g.da.x, g.db.x));
+    __stcs(reinterpret_cast<float4*>(d_out) + e1, make_float4(g.dg.y, g.dn.y, g.da.y, g.db.y));
+  };
+  auto single = [&](const RawNig& r, int e) {
+    const NigT<float> p = derive_nig<from_evidence>(r.v.x, r.v.y, r.v.z, r.v.w);
+    GradOut<float> g = grad_math(p, r.y, eps, log1eps, reg_w, kl_w);
+    const float sg = ece_on > 0.f ? bin_sign(g.conf) : 0.f;
+    g = finish(g, p, sg);
+    __stcs(reinterpret_cast<float4*>(d_out) + e, make_float4(g.dg, g.dn, g.da, g.db));
   };
   int eb = (int)blockIdx.x * LOSS_THREADS + tid;
   for (; eb + (LOSS_UNROLL - 1) * stride < total_local; eb += LOSS_UNROLL * stride) {
     RawNig rr[LOSS_UNROLL];
 #pragma unroll
     for (int q = 0; q < LOSS_UNROLL; q++)
-      rr[q] = fetch_nig<false>(evidence, gamma, nu, alpha, beta, targets, eb + q * stride, from_evidence, 0ull);
+      rr[q] = fetch_nig<false, from_evidence>(evidence, gamma, nu, alpha, beta, targets, eb + q * stride, 0ull);
 #pragma unroll
-    for (int q = 0; q < LOSS_UNROLL; q++) element(rr[q], eb + q * stride);
+    for (int q = 0; q < LOSS_UNROLL; q += 2) pair(rr[q], rr[q + 1], eb + q * stride, eb + (q + 1) * stride);
   }
   for (; eb < total_local; eb += stride)
-    element(fetch_nig<false>(evidence, gamma, nu, alpha, beta, targets, eb, from_evidence, 0ull), eb);
+    single(fetch_nig<false, from_evidence>(evidence, gamma, nu, alpha, beta, targets, eb, 0ull), eb);
 }
 
 // ------------------------------------------------------------------ stand-alone head
@@ -616,15 +741,18 @@ int deer_nig_loss_stats(const float* evidence, const float* gamma, const float* 
   const int has_out = nig_out != nullptr;
   // operands (20 B per element) small enough to stay in the 126 MB L2 between the two passes?
   const bool keep = total * 20 <= (long long)DEER_NIG_L2_KEEP_BYTES;
+#define DEER_NIG_STATS_GO(K, FE)                                                                                      \
+  DEER_LAUNCH((nig_loss_stats_kernel<K, FE>), resident_grid(nig_loss_stats_kernel<K, FE>, total, LOSS_THREADS),       \
+              LOSS_THREADS, 0, stream, evidence, gamma, nu, alpha, beta, targets, bin_edges, stats, planes, has_out,  \
+              (int)total, D, eps)
   if (keep) {
-    DEER_LAUNCH(nig_loss_stats_kernel<true>, resident_grid(nig_loss_stats_kernel<true>, total, LOSS_THREADS),
-                LOSS_THREADS, 0, stream, evidence, gamma, nu, alpha, beta, targets, bin_edges, stats, planes, has_out,
-                (int)total, D, from_evidence, eps);
+    if (from_evidence) DEER_NIG_STATS_GO(true, true);
+    else DEER_NIG_STATS_GO(true, false);
   } else {
-    DEER_LAUNCH(nig_loss_stats_kernel<false>, resident_grid(nig_loss_stats_kernel<false>, total, LOSS_THREADS),
-                LOSS_THREADS, 0, stream, evidence, gamma, nu, alpha, beta, targets, bin_edges, stats, planes, has_out,
-                (int)total, D, from_evidence, eps);
+    if (from_evidence) DEER_NIG_STATS_GO(false, true);
+    else DEER_NIG_STATS_GO(false, false);
   }
+#undef DEER_NIG_STATS_GO
   return DEER_OK;
 }
 
@@ -645,10 +773,13 @@ int deer_nig_loss_finish(const float* evidence, const float* gamma, const float*
     set_error("nig_loss_finish: B*D=%lld exceeds %lld", total, (long long)DEER_NIG_MAX_ELEMENTS);
     return DEER_ERR_UNSUPPORTED;
   }
-  DEER_LAUNCH(nig_loss_finish_kernel, resident_grid(nig_loss_finish_kernel, total, LOSS_THREADS), LOSS_THREADS, 0,
-              stream, evidence, gamma, nu, alpha, beta,
-              targets, bin_edges, stats, task_weights, reg_w, kl_w, ece_w, cross_w, eps, (int)total, B_global, D,
-              from_evidence, grad_scale, losses, d_out);
+#define DEER_NIG_FINISH_GO(FE)                                                                                        \
+  DEER_LAUNCH((nig_loss_finish_kernel<FE>), resident_grid(nig_loss_finish_kernel<FE>, total, LOSS_THREADS),           \
+              LOSS_THREADS, 0, stream, evidence, gamma, nu, alpha, beta, targets, bin_edges, stats, task_weights,     \
+              reg_w, kl_w, ece_w, cross_w, eps, (int)total, B_global, D, grad_scale, losses, d_out)
+  if (from_evidence) DEER_NIG_FINISH_GO(true);
+  else DEER_NIG_FINISH_GO(false);
+#undef DEER_NIG_FINISH_GO
   return DEER_OK;
 }
 
