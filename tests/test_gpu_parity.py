@@ -615,3 +615,67 @@ def test_conv1d_sliding_window_matches_im2col_and_torch(B, T, Cin, Cout):
         assert_close(got[3], br.grad, 1e-3, "conv db")
     for a, c in zip(outs[0][:4], outs[1][:4]):
         assert_close(a, c, 1e-3, "window vs im2col")
+
+
+def test_stream_concurrency_switches_do_not_change_results():
+    """The audio encoder on its own high-priority stream, the deferred small-layer weight gradients on a third stream
+    and the FP16 hand-off between LSTM layers only reorder / overlap launches: gradients and losses are identical to
+    the single-stream schedule (same kernels, same operands, disjoint accumulation targets)."""
+    from deer_b200.trainer import DEERDataParallelTrainer
+    from gen_common import seq_inputs
+
+    res = []
+    for branch, defer in ((True, True), (False, False), (True, False), (False, True)):
+        ops.set_branch_streams(branch)
+        ops.set_defer_wgrad(defer)
+        try:
+            torch.manual_seed(3)
+            model = deer_b200.SequenceDEERModel(dropout=0.0).to(DEV).train()
+            tr = DEERDataParallelTrainer(model)
+            b = [t.float().to(DEV) for t in seq_inputs(6, 9, 5, 7, seed=11)]
+            batch = {"audio_features": b[0], "video_features": b[1], "text_features": b[2], "attention_mask": b[3],
+                     "linguistic_features": b[4], "targets": b[5]}
+            for _ in range(2):          # twice: stream reuse across steps
+                tr.flat.grads.zero_()
+                losses = tr.forward_backward(batch)
+            torch.cuda.synchronize()
+            res.append((tr.flat.grads.clone(), losses.clone()))
+        finally:
+            ops.set_branch_streams(True)
+            ops.set_defer_wgrad(True)
+    assert float(res[0][0].norm()) > 0
+    for g, l in res[1:]:      # not bit-wise: several gradients are accumulated with floating-point atomics
+        assert_close(g, res[0][0], 1e-5, "flat gradients")
+        assert_close(l, res[0][1], 1e-6, "losses")
+
+
+def test_lstm_fp16_handoff_between_layers_is_exact():
+    """Inference / no-dropout: layer 0's recurrence kernel writes the FP16 copy of h that layer 1's input projection
+    consumes (no cast pass).  Same rounding (RN to FP16 of the same fp32 h) -> bit-identical encoder output."""
+    torch.manual_seed(1)
+    enc = deer_b200.EnhancedAudioEncoder({"dropout": 0.3}).to(DEV).eval()
+    x = torch.randn(40, 30, 84, device=DEV)
+    with torch.no_grad():
+        h_fast = enc.lstm_forward(x)
+        h = ops.to_time_major(x)
+        for l in range(enc.num_layers):           # the same two layers, each casting its own input
+            h = ops.bilstm_layer(h, *enc._layer_weights(l))
+    assert torch.equal(h_fast, h)
+    # training without dropout takes the hand-off too and must give the same gradients as the cast path
+    enc.train()
+    enc.dropout = 0.0
+    grads = []
+    for handoff in (True, False):
+        for p in enc.parameters():
+            p.grad = None
+        xi = x.clone().requires_grad_(True)
+        if handoff:
+            h = enc.lstm_forward(xi)
+        else:
+            h = ops.to_time_major(xi)
+            for l in range(enc.num_layers):
+                h = ops.bilstm_layer(h, *enc._layer_weights(l))
+        (h * torch.linspace(-1, 1, h.numel(), device=DEV).view_as(h)).sum().backward()
+        grads.append([xi.grad.clone()] + [p.grad.clone() for p in enc.lstm.parameters()])
+    for a, b in zip(*grads):      # atomically accumulated bias gradients: equal up to summation order
+        assert_close(a, b, 1e-5, "lstm gradients")

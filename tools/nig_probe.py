@@ -58,11 +58,14 @@ def main():
             j = i % nbuf
             ops.nig_loss_raw(ev[j], None, tg[j], want_nig=True, want_grad=True)
 
-        t1, t2, tb, ta = events(p1, 20), events(p2, 20), events(both, 20), events(api, 20)
-        alg = n * D * 64.0
-        print(f"B=2^{lg} ({nbuf} bufs): stats {t1:8.1f} us ({n*D*48/t1/1e3:7.0f} GB/s)  finish {t2:8.1f} us "
-              f"({n*D*36/t2/1e3:7.0f} GB/s)  both {tb:8.1f} us  api {ta:8.1f} us -> algorithmic "
-              f"{alg/tb/1e3:7.0f} GB/s = {alg/tb/1e3/PEAK*100:5.1f}% (api {alg/ta/1e3/PEAK*100:5.1f}%)", flush=True)
+        for pipe in (1, 0):   # DEER_OPT_NIG_PIPELINE
+            deer_b200._lib.set_option(8, pipe)
+            t1, t2, tb, ta = events(p1, 20), events(p2, 20), events(both, 20), events(api, 20)
+            alg = n * D * 64.0
+            print(f"B=2^{lg} ({nbuf} bufs, pipe={pipe}): stats {t1:8.1f} us ({n*D*48/t1/1e3:7.0f} GB/s)  finish {t2:8.1f} us "
+                  f"({n*D*36/t2/1e3:7.0f} GB/s)  both {tb:8.1f} us  api {ta:8.1f} us -> algorithmic "
+                  f"{alg/tb/1e3:7.0f} GB/s = {alg/tb/1e3/PEAK*100:5.1f}% (api {alg/ta/1e3/PEAK*100:5.1f}%)", flush=True)
+        deer_b200._lib.set_option(8, 1)
         del ev, tg, nig, grad
         torch.cuda.empty_cache()
 

@@ -21,6 +21,7 @@ namespace deer {
 constexpr int NSTAT = DEER_LOSS_NSTAT;  // 0 nll,1 reg,2 kl_alpha,3 kl_beta,4 sum u, 5..14 cnt, 15..24 conf, 25..34 err
 constexpr int LOSS_THREADS = 192;       // multiple of every supported D (1,2,3,4,6,8)
 constexpr int LOSS_MIN_BLOCKS = 5;      // 64 registers: two P2 pairs in flight per thread without spills
+constexpr int LOSS_MIN_BLOCKS_PIPE = 4; // 80 registers: + the next trip's operands (software-pipelined loads)
 constexpr int NBINS = 10;
 constexpr long long DEER_NIG_MAX_ELEMENTS = (1ll << 31) - (1ll << 24);  // 32-bit element indices + unroll slack
 constexpr long long DEER_NIG_L2_KEEP_BYTES = 72ll << 20;  // operand footprint up to which pass 1 pins its loads in L2
@@ -282,8 +283,8 @@ __device__ __forceinline__ StatsOut<V> stats_math(const NigT<V>& p, V y, float e
 // element indices are 32-bit inside the kernels (the entry points reject B*D >= 2^31 - grid slack)
 // from_evidence is a template parameter: as a runtime flag both load variants were emitted predicated, and the
 // predicated-off half still took ~10 issue slots per element
-template <bool KEEP, bool from_evidence>
-__global__ void __launch_bounds__(LOSS_THREADS, LOSS_MIN_BLOCKS) nig_loss_stats_kernel(
+template <bool KEEP, bool from_evidence, bool PIPE>
+__global__ void __launch_bounds__(LOSS_THREADS, PIPE ? LOSS_MIN_BLOCKS_PIPE : LOSS_MIN_BLOCKS) nig_loss_stats_kernel(
     const float* __restrict__ evidence, const float* __restrict__ gamma, const float* __restrict__ nu,
     const float* __restrict__ alpha, const float* __restrict__ beta, const float* __restrict__ targets,
     const float* __restrict__ bin_edges, float* __restrict__ stats, const NigPlanes planes, int nig_out, int total, int D,
@@ -347,13 +348,43 @@ __global__ void __launch_bounds__(LOSS_THREADS, LOSS_MIN_BLOCKS) nig_loss_stats_
     tail(o.conf, o.aerr, p, o.alea, o.epis, e);
   };
   int eb = (int)blockIdx.x * LOSS_THREADS + tid;
-  for (; eb + (LOSS_UNROLL - 1) * stride < total; eb += LOSS_UNROLL * stride) {
+  if constexpr (PIPE) {
+    // software pipeline: the loads of trip i+1 are issued before trip i is computed, so every warp keeps 80 bytes per
+    // thread in flight WHILE it computes (with load -> compute -> load the memory system idles during the math)
+    bool have = eb + (LOSS_UNROLL - 1) * stride < total;
     RawNig rr[LOSS_UNROLL];
+    if (have) {
 #pragma unroll
-    for (int q = 0; q < LOSS_UNROLL; q++)
-      rr[q] = fetch_nig<KEEP, from_evidence>(evidence, gamma, nu, alpha, beta, targets, eb + q * stride, pol);
+      for (int q = 0; q < LOSS_UNROLL; q++)
+        rr[q] = fetch_nig<KEEP, from_evidence>(evidence, gamma, nu, alpha, beta, targets, eb + q * stride, pol);
+    }
+    while (have) {
+      const int en = eb + LOSS_UNROLL * stride;
+      const bool more = en + (LOSS_UNROLL - 1) * stride < total;
+      RawNig nx[LOSS_UNROLL];
+      if (more) {
 #pragma unroll
-    for (int q = 0; q < LOSS_UNROLL; q += 2) pair(rr[q], rr[q + 1], eb + q * stride, eb + (q + 1) * stride);
+        for (int q = 0; q < LOSS_UNROLL; q++)
+          nx[q] = fetch_nig<KEEP, from_evidence>(evidence, gamma, nu, alpha, beta, targets, en + q * stride, pol);
+      }
+#pragma unroll
+      for (int q = 0; q < LOSS_UNROLL; q += 2) pair(rr[q], rr[q + 1], eb + q * stride, eb + (q + 1) * stride);
+      if (more) {
+#pragma unroll
+        for (int q = 0; q < LOSS_UNROLL; q++) rr[q] = nx[q];
+      }
+      eb = en;
+      have = more;
+    }
+  } else {
+    for (; eb + (LOSS_UNROLL - 1) * stride < total; eb += LOSS_UNROLL * stride) {
+      RawNig rr[LOSS_UNROLL];
+#pragma unroll
+      for (int q = 0; q < LOSS_UNROLL; q++)
+        rr[q] = fetch_nig<KEEP, from_evidence>(evidence, gamma, nu, alpha, beta, targets, eb + q * stride, pol);
+#pragma unroll
+      for (int q = 0; q < LOSS_UNROLL; q += 2) pair(rr[q], rr[q + 1], eb + q * stride, eb + (q + 1) * stride);
+    }
   }
   for (; eb < total; eb += stride)
     single(fetch_nig<KEEP, from_evidence>(evidence, gamma, nu, alpha, beta, targets, eb, pol), eb);
@@ -421,8 +452,8 @@ __device__ __forceinline__ GradOut<V> grad_math(const NigT<V>& p, V y, float eps
   return o;
 }
 
-template <bool from_evidence>
-__global__ void __launch_bounds__(LOSS_THREADS, LOSS_MIN_BLOCKS) nig_loss_finish_kernel(
+template <bool from_evidence, bool PIPE>
+__global__ void __launch_bounds__(LOSS_THREADS, PIPE ? LOSS_MIN_BLOCKS_PIPE : LOSS_MIN_BLOCKS) nig_loss_finish_kernel(
     const float* __restrict__ evidence, const float* __restrict__ gamma, const float* __restrict__ nu,
     const float* __restrict__ alpha, const float* __restrict__ beta, const float* __restrict__ targets,
     const float* __restrict__ bin_edges, const float* __restrict__ stats, const float* __restrict__ task_weights,
@@ -549,13 +580,41 @@ __global__ void __launch_bounds__(LOSS_THREADS, LOSS_MIN_BLOCKS) nig_loss_finish
     __stcs(reinterpret_cast<float4*>(d_out) + e, make_float4(g.dg, g.dn, g.da, g.db));
   };
   int eb = (int)blockIdx.x * LOSS_THREADS + tid;
-  for (; eb + (LOSS_UNROLL - 1) * stride < total_local; eb += LOSS_UNROLL * stride) {
+  if constexpr (PIPE) {   // software-pipelined like phase 1
+    bool have = eb + (LOSS_UNROLL - 1) * stride < total_local;
     RawNig rr[LOSS_UNROLL];
+    if (have) {
 #pragma unroll
-    for (int q = 0; q < LOSS_UNROLL; q++)
-      rr[q] = fetch_nig<false, from_evidence>(evidence, gamma, nu, alpha, beta, targets, eb + q * stride, 0ull);
+      for (int q = 0; q < LOSS_UNROLL; q++)
+        rr[q] = fetch_nig<false, from_evidence>(evidence, gamma, nu, alpha, beta, targets, eb + q * stride, 0ull);
+    }
+    while (have) {
+      const int en = eb + LOSS_UNROLL * stride;
+      const bool more = en + (LOSS_UNROLL - 1) * stride < total_local;
+      RawNig nx[LOSS_UNROLL];
+      if (more) {
 #pragma unroll
-    for (int q = 0; q < LOSS_UNROLL; q += 2) pair(rr[q], rr[q + 1], eb + q * stride, eb + (q + 1) * stride);
+        for (int q = 0; q < LOSS_UNROLL; q++)
+          nx[q] = fetch_nig<false, from_evidence>(evidence, gamma, nu, alpha, beta, targets, en + q * stride, 0ull);
+      }
+#pragma unroll
+      for (int q = 0; q < LOSS_UNROLL; q += 2) pair(rr[q], rr[q + 1], eb + q * stride, eb + (q + 1) * stride);
+      if (more) {
+#pragma unroll
+        for (int q = 0; q < LOSS_UNROLL; q++) rr[q] = nx[q];
+      }
+      eb = en;
+      have = more;
+    }
+  } else {
+    for (; eb + (LOSS_UNROLL - 1) * stride < total_local; eb += LOSS_UNROLL * stride) {
+      RawNig rr[LOSS_UNROLL];
+#pragma unroll
+      for (int q = 0; q < LOSS_UNROLL; q++)
+        rr[q] = fetch_nig<false, from_evidence>(evidence, gamma, nu, alpha, beta, targets, eb + q * stride, 0ull);
+#pragma unroll
+      for (int q = 0; q < LOSS_UNROLL; q += 2) pair(rr[q], rr[q + 1], eb + q * stride, eb + (q + 1) * stride);
+    }
   }
   for (; eb < total_local; eb += stride)
     single(fetch_nig<false, from_evidence>(evidence, gamma, nu, alpha, beta, targets, eb, 0ull), eb);
@@ -698,6 +757,8 @@ static int stream_grid(long long n, int threads) {
   return (int)(g < 1 ? 1 : g);
 }
 
+int g_nig_pipe = 1;   // DEER_OPT_NIG_PIPELINE
+
 }  // namespace deer
 
 using namespace deer;
@@ -741,17 +802,23 @@ int deer_nig_loss_stats(const float* evidence, const float* gamma, const float* 
   const int has_out = nig_out != nullptr;
   // operands (20 B per element) small enough to stay in the 126 MB L2 between the two passes?
   const bool keep = total * 20 <= (long long)DEER_NIG_L2_KEEP_BYTES;
-#define DEER_NIG_STATS_GO(K, FE)                                                                                      \
-  DEER_LAUNCH((nig_loss_stats_kernel<K, FE>), resident_grid(nig_loss_stats_kernel<K, FE>, total, LOSS_THREADS),       \
+#define DEER_NIG_STATS_GO(K, FE, PP)                                                                                  \
+  DEER_LAUNCH((nig_loss_stats_kernel<K, FE, PP>), resident_grid(nig_loss_stats_kernel<K, FE, PP>, total, LOSS_THREADS), \
               LOSS_THREADS, 0, stream, evidence, gamma, nu, alpha, beta, targets, bin_edges, stats, planes, has_out,  \
               (int)total, D, eps)
+#define DEER_NIG_STATS_GO2(K, FE)            \
+  do {                                       \
+    if (g_nig_pipe) DEER_NIG_STATS_GO(K, FE, true); \
+    else DEER_NIG_STATS_GO(K, FE, false);    \
+  } while (0)
   if (keep) {
-    if (from_evidence) DEER_NIG_STATS_GO(true, true);
-    else DEER_NIG_STATS_GO(true, false);
+    if (from_evidence) DEER_NIG_STATS_GO2(true, true);
+    else DEER_NIG_STATS_GO2(true, false);
   } else {
-    if (from_evidence) DEER_NIG_STATS_GO(false, true);
-    else DEER_NIG_STATS_GO(false, false);
+    if (from_evidence) DEER_NIG_STATS_GO2(false, true);
+    else DEER_NIG_STATS_GO2(false, false);
   }
+#undef DEER_NIG_STATS_GO2
 #undef DEER_NIG_STATS_GO
   return DEER_OK;
 }
@@ -773,12 +840,17 @@ int deer_nig_loss_finish(const float* evidence, const float* gamma, const float*
     set_error("nig_loss_finish: B*D=%lld exceeds %lld", total, (long long)DEER_NIG_MAX_ELEMENTS);
     return DEER_ERR_UNSUPPORTED;
   }
-#define DEER_NIG_FINISH_GO(FE)                                                                                        \
-  DEER_LAUNCH((nig_loss_finish_kernel<FE>), resident_grid(nig_loss_finish_kernel<FE>, total, LOSS_THREADS),           \
+#define DEER_NIG_FINISH_GO(FE, PP)                                                                                    \
+  DEER_LAUNCH((nig_loss_finish_kernel<FE, PP>), resident_grid(nig_loss_finish_kernel<FE, PP>, total, LOSS_THREADS),   \
               LOSS_THREADS, 0, stream, evidence, gamma, nu, alpha, beta, targets, bin_edges, stats, task_weights,     \
               reg_w, kl_w, ece_w, cross_w, eps, (int)total, B_global, D, grad_scale, losses, d_out)
-  if (from_evidence) DEER_NIG_FINISH_GO(true);
-  else DEER_NIG_FINISH_GO(false);
+  if (from_evidence) {
+    if (g_nig_pipe) DEER_NIG_FINISH_GO(true, true);
+    else DEER_NIG_FINISH_GO(true, false);
+  } else {
+    if (g_nig_pipe) DEER_NIG_FINISH_GO(false, true);
+    else DEER_NIG_FINISH_GO(false, false);
+  }
 #undef DEER_NIG_FINISH_GO
   return DEER_OK;
 }

@@ -70,10 +70,15 @@ class EnhancedAudioEncoder(nn.Module):
     def lstm_forward(self, features: torch.Tensor) -> torch.Tensor:
         """[B,T,84] -> time-major LSTM output [T,B,hidden_dim]."""
         h = ops.to_time_major(features)
+        h16 = None
+        nodrop = not (self.training and self.dropout > 0.0)
         for l in range(self.num_layers):
-            # nn.LSTM(dropout=p): dropout on the OUTPUT of every layer but the last == on the input of layers >= 1
-            h = ops.bilstm_layer(h, *self._layer_weights(l), input_dropout=self.dropout if l > 0 else 0.0,
-                                 training=self.training)
+            # nn.LSTM(dropout=p): dropout on the OUTPUT of every layer but the last == on the input of layers >= 1.
+            # Without dropout (inference) the recurrence kernel also writes the FP16 copy of h that the next layer's
+            # input projection consumes, so the [T*B, 512] cast pass disappears.
+            h, h16 = ops.bilstm_layer(h, *self._layer_weights(l), input_dropout=self.dropout if l > 0 else 0.0,
+                                      training=self.training, x_f16=h16,
+                                      emit_f16=nodrop and l + 1 < self.num_layers, return_f16=True)
         return h
 
     def forward(self, audio_input: torch.Tensor) -> torch.Tensor:

@@ -566,7 +566,9 @@ class _BiLSTMLayerCluster(torch.autograd.Function):
     casts (the dropped fp32 tensor is never materialised) and into dx in backward."""
 
     @staticmethod
-    def forward(ctx, x, wif, whf, bif, bhf, wir, whr, bir, bhr, drop=None):
+    def forward(ctx, x, wif, whf, bif, bhf, wir, whr, bir, bhr, drop=None, x16_in=None, emit_f16=False):
+        """x16_in: FP16 copy of x written by the previous layer's recurrence kernel (skips the cast pass); emit_f16: make
+        this layer's kernel write such a copy of h.  Returns (h, h_f16 or an empty tensor)."""
         x = _req(x, "x").contiguous()
         T, B, In = x.shape
         H = whf.shape[1]
@@ -596,6 +598,9 @@ class _BiLSTMLayerCluster(torch.autograd.Function):
                 x16 = torch.empty((M, In), device=dev, dtype=torch.float16)
                 call("deer_dropout_cast16", ptr(x), x16.data_ptr(), None, M * In, float(drop[0]), drop[1], drop[2],
                      ptr(ctx.drop_step))
+            elif (x16_in is not None and x16_in.dtype == torch.float16 and x16_in.numel() == M * In and In % 8 == 0
+                  and x16_in.is_contiguous()):
+                x16 = x16_in.view(M, In)                      # the producer kernel's FP16 shadow: no cast pass
             else:
                 x16 = cast16(x)                               # [M, Kp] fp16
             Kp = x16.shape[1]
@@ -609,6 +614,8 @@ class _BiLSTMLayerCluster(torch.autograd.Function):
             for d in range(2):
                 gemm(x, In, 0, wi_il[d], In, 1, pre.data_ptr() + 4 * G * d, 2 * G, M, G, In, bias=b_il[d])
         h = torch.empty((T, B, 2 * H), device=dev, dtype=torch.float32)
+        h16 = torch.empty((T, B, 2 * H), device=dev, dtype=torch.float16) if emit_f16 else None
+        h16p = None if h16 is None else h16.data_ptr()
         whf_c, whr_c = whf.contiguous(), whr.contiguous()
         fwd_fn = "deer_lstm_cluster_fwd_pre16" if pre16 else "deer_lstm_cluster_fwd"
         if keep:
@@ -616,21 +623,24 @@ class _BiLSTMLayerCluster(torch.autograd.Function):
             gact = torch.empty(T * 2 * Bp * G, device=dev, dtype=torch.float32)
             c_blk = torch.empty(T * 2 * Bp * H, device=dev, dtype=torch.float32)
             hb16 = torch.empty((T, B, 2 * H), device=dev, dtype=torch.bfloat16) if use16 else None
-            call(fwd_fn, pre.data_ptr(), ptr(whf_c), ptr(whr_c), ptr(h), ptr(gact), ptr(c_blk), None,
+            call(fwd_fn, pre.data_ptr(), ptr(whf_c), ptr(whr_c), ptr(h), ptr(gact), ptr(c_blk), h16p,
                  None if hb16 is None else hb16.data_ptr(), T, B, H)
             ctx.save_for_backward(x, wi_il, whf_c, whr_c, gact, c_blk, h)
             # the fp32 pre buffer doubles as the fp32 dpre buffer; on the 16-bit path BPTT only writes the BF16 dpre
             ctx.pre = None if use16 else pre
             ctx.hb16 = hb16
         else:
-            call(fwd_fn, pre.data_ptr(), ptr(whf_c), ptr(whr_c), ptr(h), None, None, None, None, T, B, H)
+            call(fwd_fn, pre.data_ptr(), ptr(whf_c), ptr(whr_c), ptr(h), None, None, h16p, None, T, B, H)
         ctx.dims = (T, B, In, H)
         ctx.use16 = use16
         ctx.params = (wif, whf, bif, bhf, wir, whr, bir, bhr)
-        return h
+        if h16 is None:
+            h16 = torch.empty(0, device=dev, dtype=torch.float16)
+        ctx.mark_non_differentiable(h16)
+        return h, h16
 
     @staticmethod
-    def backward(ctx, dh):
+    def backward(ctx, dh, _dh16=None):
         x, wi_il, whf, whr, gact, c_blk, h = ctx.saved_tensors
         T, B, In, H = ctx.dims
         G = 4 * H
@@ -707,13 +717,17 @@ class _BiLSTMLayerCluster(torch.autograd.Function):
                 dbs.append(None if direct else tgt)
             out.append((None if dwi_direct else dwi, None if dwh_direct else dwh, dbs[0], dbs[1]))
         (dwif, dwhf, dbif, dbhf), (dwir, dwhr, dbir, dbhr) = out
-        return dx, dwif, dwhf, dbif, dbhf, dwir, dwhr, dbir, dbhr, None
+        return dx, dwif, dwhf, dbif, dbhf, dwir, dwhr, dbir, dbhr, None, None, None
 
 
-def bilstm_layer(x_tm, wif, whf, bif, bhf, wir, whr, bir, bhr, input_dropout: float = 0.0, training: bool = False):
+def bilstm_layer(x_tm, wif, whf, bif, bhf, wir, whr, bir, bhr, input_dropout: float = 0.0, training: bool = False,
+                 x_f16=None, emit_f16: bool = False, return_f16: bool = False):
     """engine AUTO/TF32: persistent cluster kernels when H == 256; SIMT: exact-fp32 stepwise; others: see lstm.cu.
     `input_dropout` (with `training`) applies nn.LSTM's inter-layer dropout to x_tm: fused into the layer's 16-bit
-    operand casts on the cluster path, a separate kernel otherwise."""
+    operand casts on the cluster path, a separate kernel otherwise.
+    `return_f16`: return (h, h_f16); with `emit_f16` h_f16 is the FP16 copy of h the recurrence kernel writes beside it
+    (None when the path has none); pass it as `x_f16` to the next layer to skip that layer's operand cast (no-dropout
+    case)."""
     cluster = _state["lstm_engine"] in (ENGINE_AUTO, ENGINE_TF32) and whf.shape[1] == 256
     drop = None
     if training and input_dropout > 0.0:
@@ -726,8 +740,12 @@ def bilstm_layer(x_tm, wif, whf, bif, bhf, wir, whr, bir, bhr, input_dropout: fl
         else:
             x_tm = dropout(x_tm, input_dropout, True)
     if cluster:
-        return _BiLSTMLayerCluster.apply(x_tm, wif, whf, bif, bhf, wir, whr, bir, bhr, drop)
-    return _BiLSTMLayer.apply(x_tm, wif, whf, bif, bhf, wir, whr, bir, bhr)
+        want = bool(emit_f16 and _state["lstm_gemm16"] and _state["engine"] == ENGINE_AUTO)
+        h, h16 = _BiLSTMLayerCluster.apply(x_tm, wif, whf, bif, bhf, wir, whr, bir, bhr, drop,
+                                           x_f16 if drop is None else None, want)
+        return (h, h16 if h16.numel() else None) if return_f16 else h
+    h = _BiLSTMLayer.apply(x_tm, wif, whf, bif, bhf, wir, whr, bir, bhr)
+    return (h, None) if return_f16 else h
 
 
 # ----------------------------------------------------------------------------------------------- Conv1d(k=3) + BN
