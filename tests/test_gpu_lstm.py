@@ -170,3 +170,27 @@ def test_fp16_preactivations_match_fp32_preactivations(B, T, In):
     assert_close(h16, h_ref, 1e-3, "h (fp16 pre vs exact fp32)")
     for a, b_ in zip(g16, g_ref):
         assert cosine(a, b_) > 0.9999
+
+
+@pytest.mark.parametrize("B,T,In", [(70, 9, 512), (130, 33, 84), (1024, 12, 84)])
+def test_dual_subtile_forward_matches_monolithic_tile(B, T, In):
+    """Inference forward at 32 batch columns per CTA: two interleaved 16-column sub-tiles (DEER_OPT_LSTM_DUAL, default)
+    against the monolithic 32-column tile and the exact-fp32 stepwise engine; ragged batches leave a sub-tile partly or
+    completely empty."""
+    H = 256
+    ws = make_layer(In, H, B + T + 7)
+    x = torch.randn(B, T, In, generator=torch.Generator().manual_seed(B + 1))
+    _lib.set_option(3, 32)          # force 32 columns per CTA also for small batches
+    try:
+        _lib.set_option(9, 1)
+        h_dual, _ = run(x, ws, ops.ENGINE_AUTO, False)
+        _lib.set_option(9, 0)
+        h_mono, _ = run(x, ws, ops.ENGINE_AUTO, False)
+    finally:
+        _lib.set_option(9, 1)
+        _lib.set_option(3, 0)
+    assert torch.equal(h_dual, h_mono) or float((h_dual - h_mono).abs().max()) < 1e-6
+    if B <= 130:
+        ops.set_gemm_engine(ops.ENGINE_SIMT)
+        h_ref, _ = run(x, ws, ops.ENGINE_SIMT, False)
+        assert_close(h_dual, h_ref, 1e-3, "h vs exact fp32")

@@ -37,7 +37,9 @@ def main():
     ap.add_argument("--engine", type=int, default=AUTO)
     ap.add_argument("--skip-bwd", action="store_true")
     ap.add_argument("--prof", action="store_true")
+    ap.add_argument("--dual", type=int, default=1)
     a = ap.parse_args()
+    _lib.set_option(9, a.dual)
     _lib.set_option(2, a.ts)
     _lib.set_option(3, a.tile)
     dev = "cuda"

@@ -212,46 +212,66 @@ constexpr int Q_PROF_S0 = 64, Q_PROF_STEPS = 4, Q_PROF_SLOTS = 8;
   } while (0)
 
 // ================================================================================================ forward
-template <int N, bool TS>
-__global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
+// G = 1: one batch tile of N columns per CTA (8 compute warps + the MMA warp).
+// G = 2 (inference, large batches): TWO independent batch sub-tiles of N columns per CTA, each with its own 8 compute
+// warps, accumulators, h tiles and barriers, sharing the resident W_hh and the MMA warp.  A step of one tile is a serial
+// chain (MMA -> gate epilogue -> cell update -> exchange); with two tiles in flight one tile's MUFU-bound epilogue runs
+// while the other's MMAs and DSMEM exchange are in flight, instead of every unit idling in turn (a monolithic 32-column
+// tile took 2.75 us per step; two waves of CTAs were needed at B = 1024).
+template <int N, bool TS, int G>
+__global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(G * 256 + 32, 1)
     lstm_fwd_cluster_kernel(const LstmClusterParams p) {
   DEER_PDL_ENTRY();
   using L = QLayout<N>;
   constexpr int NQ = L::NQ, ROWF = L::ROWF;
+  constexpr int MMAW = 8 * G;            // index of the MMA-issuing warp
+  constexpr int NTHREADS = G * 256 + 32;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128B swizzle atoms, applied as an OFFSET on the __shared__ array: going through
   // uintptr_t would make every later access a generic LD/ST instead of LDS/STS
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* wsm = smem;                                   // SS: 128 KB resident W (unused in TS mode)
-  uint8_t* hbuf = smem + (TS ? 0 : QW_BYTES);            // 2 x HB_BYTES
-  float* stage_act = reinterpret_cast<float*>(hbuf + 2 * L::HB_BYTES);
-  __half* stage_h = reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(stage_act) + L::ACT_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stage_h) + L::SH_BYTES);
-  uint64_t* h_full = bars;        // [2]
-  uint64_t* mma_done = bars + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+  uint8_t* hbuf_all = smem + (TS ? 0 : QW_BYTES);        // per group: 2 x HB_BYTES
+  float* stage_act_all = reinterpret_cast<float*>(hbuf_all + G * 2 * L::HB_BYTES);
+  __half* stage_h_all = reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(stage_act_all) + G * L::ACT_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stage_h_all) + G * L::SH_BYTES);
+  uint64_t* h_full_all = bars;            // [G][2]
+  uint64_t* mma_done_all = bars + 2 * G;  // [G]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * G);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp_id = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grp = (G == 2 && warp_id >= 8 && warp_id < 16) ? 1 : 0;   // batch sub-tile of this compute warp
+  const int warp = warp_id == MMAW ? 8 : (warp_id & 7);              // role index: 0..7 compute, 8 = MMA issuer
+  uint8_t* hbuf = hbuf_all + grp * 2 * L::HB_BYTES;
+  float* stage_act = stage_act_all + grp * (L::ACT_BYTES / 4);
+  __half* stage_h = stage_h_all + grp * (L::SH_BYTES / 2);
+  uint64_t* h_full = h_full_all + 2 * grp;
+  uint64_t* mma_done = mma_done_all + grp;
   const uint32_t r = cluster_ctarank();
   const int cid = blockIdx.x / QC;
-  const int tile = cid % p.ntiles, dir = cid / p.ntiles;
+  const int ctile = cid % p.ntiles, dir = cid / p.ntiles;   // p.ntiles counts CTA tiles of G*N batch columns
+  const int tile = ctile * G + grp;
   const int b0 = tile * N;
   const int T = p.T, B = p.B;
   const float* __restrict__ W = dir ? p.w_rev : p.w_fwd;
 
   // ---- one-time setup
   if (threadIdx.x == 0) {
-    mbar_init(&h_full[0], 1);
-    mbar_init(&h_full[1], 1);
-    mbar_init(mma_done, 1);
+    for (int g = 0; g < G; g++) {
+      mbar_init(&h_full_all[2 * g + 0], 1);
+      mbar_init(&h_full_all[2 * g + 1], 1);
+      mbar_init(&mma_done_all[g], 1);
+    }
     fence_barrier_init();
     // each phase of h_full[b] = one arming arrival + N x 256 fp16 of h landing from the 4 CTAs (async proxy)
-    if (T > 1) mbar_expect_tx(&h_full[0], L::HB_BYTES);
-    if (T > 2) mbar_expect_tx(&h_full[1], L::HB_BYTES);
+    for (int g = 0; g < G; g++) {
+      if (T > 1) mbar_expect_tx(&h_full_all[2 * g + 0], L::HB_BYTES);
+      if (T > 2) mbar_expect_tx(&h_full_all[2 * g + 1], L::HB_BYTES);
+    }
   }
   // two allocations (accumulators 64 columns, resident operand 256) instead of one 512-column block: the 192 columns
   // left over let a 128-column GEMM CTA of a concurrent stream share the SM instead of spinning in tcgen05.alloc
-  if (warp == 8) {
+  if (warp_id == MMAW) {
     if constexpr (TS) {
       tmem_alloc_more_follow(tmem_slot, 64);
       tmem_alloc(tmem_slot + 1, 256);
@@ -261,7 +281,7 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
   }
   if constexpr (!TS) {
     // W_hh rows of this CTA -> fp16, K-major SWIZZLE_128B: [acc a][k-block 4][128 rows x 128 B]; row m = 4*unit + gate
-    for (int idx = threadIdx.x; idx < 2 * 128 * 32; idx += QTHREADS) {
+    for (int idx = threadIdx.x; idx < 2 * 128 * 32; idx += NTHREADS) {
       const int kc = idx & 31, m = (idx >> 5) & 127, a = idx >> 12;
       const int g = m & 3, u = a * 32 + (m >> 2);
       const float4* src = reinterpret_cast<const float4*>(W + (size_t)(g * QH + (int)r * QU + u) * QH + kc * 8);
@@ -278,7 +298,7 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_w = TS ? tmem_slot[1] : 0u;   // resident A operand (TS mode)
   if constexpr (TS) {
-    if (warp < 8) {
+    if (warp_id < 8) {
       // resident A operand in TMEM: lane = row m of accumulator a, 128 columns = 256 fp16 (2 per column, low half first)
       const int a = warp >> 2, sub = warp & 3, m = sub * 32 + lane;
       const int g = m & 3, u = a * 32 + (m >> 2);
@@ -310,35 +330,41 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
       const uint32_t tw = warp_uniform(tmem_w);
       const bool leader = elect_one();
       for (int s = 0; s < T; s++) {
-        if (s == 0) {
-          if (leader) mbar_arrive(mma_done);  // h_{-1} = 0: the gates of step 0 are the input projection alone
-          continue;
-        }
-        mbar_wait(&h_full[(s - 1) & 1], (uint32_t)(((s - 1) >> 1) & 1));
-        if (leader) Q_PROF(0);
-        if (leader && s + 2 < T) mbar_expect_tx(&h_full[(s - 1) & 1], L::HB_BYTES);  // re-arm for h_{s+1}
-        tc_fence_after();
-        const uint32_t hb = smem_u32(hbuf) + ((s - 1) & 1) * L::HB_BYTES;
-        if (leader) {
 #pragma unroll
-        for (int a = 0; a < 2; a++) {
-#pragma unroll
-          for (int k = 0; k < 16; k++) {
-            // B operand, K-major no-swizzle: [32 k-chunks][N rows][16 B]; 8x16B core matrices, SBO 128 B, LBO N*16 B
-            const uint64_t bd = make_smem_desc(hb + (2 * k) * (N * 16), N * 16, 128, 0);
-            if constexpr (TS) {
-              umma_f16_ts(tb + a * N, tw + a * 128 + k * 8, bd, idesc, k > 0 ? 1u : 0u);
-            } else {
-              const uint64_t ad =
-                  make_smem_desc(smem_u32(wsm) + a * 65536 + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024, 2);
-              umma_f16_ss(tb + a * N, ad, bd, idesc, k > 0 ? 1u : 0u);
-            }
+        for (int g = 0; g < G; g++) {   // the batch sub-tiles take turns on the tensor core
+          uint64_t* hf = h_full_all + 2 * g;
+          uint64_t* md = mma_done_all + g;
+          if (s == 0) {
+            if (leader) mbar_arrive(md);  // h_{-1} = 0: the gates of step 0 are the input projection alone
+            continue;
           }
+          mbar_wait(&hf[(s - 1) & 1], (uint32_t)(((s - 1) >> 1) & 1));
+          if (leader && g == 0) Q_PROF(0);
+          if (leader && s + 2 < T) mbar_expect_tx(&hf[(s - 1) & 1], L::HB_BYTES);  // re-arm for h_{s+1}
+          tc_fence_after();
+          const uint32_t hb = smem_u32(hbuf_all) + (2 * g + ((s - 1) & 1)) * L::HB_BYTES;
+          const uint32_t tg = tb + (uint32_t)(g * 2 * N);
+          if (leader) {
+#pragma unroll
+            for (int a = 0; a < 2; a++) {
+#pragma unroll
+              for (int k = 0; k < 16; k++) {
+                // B operand, K-major no-swizzle: [32 k-chunks][N rows][16 B]; 8x16B core matrices, SBO 128 B, LBO N*16 B
+                const uint64_t bd = make_smem_desc(hb + (2 * k) * (N * 16), N * 16, 128, 0);
+                if constexpr (TS) {
+                  umma_f16_ts(tg + a * N, tw + a * 128 + k * 8, bd, idesc, k > 0 ? 1u : 0u);
+                } else {
+                  const uint64_t ad =
+                      make_smem_desc(smem_u32(wsm) + a * 65536 + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024, 2);
+                  umma_f16_ss(tg + a * N, ad, bd, idesc, k > 0 ? 1u : 0u);
+                }
+              }
+            }
+            umma_commit(md);
+            if (g == 0) Q_PROF(1);
+          }
+          __syncwarp();
         }
-        umma_commit(mma_done);
-        Q_PROF(1);
-        }
-        __syncwarp();
       }
     }
   } else {
@@ -347,7 +373,7 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
     const int j = lane >> 2, g = lane & 3;        // gate-row role: unit j of this warp, gate g
     const int ul = a * 32 + sub * 8 + j;          // unit inside the CTA
     const int ug = (int)r * QU + ul;              // unit inside the direction
-    const uint32_t tacc = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(a * N);
+    const uint32_t tacc = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(grp * 2 * N + a * N);
     float* sa = stage_act + warp * (32 * ROWF);
     __half* sh_base = stage_h + warp * (2 * N * 8);
     const float sc = (g == 2) ? 2.f : 1.f;        // tanh(x) = 2*sigmoid(2x) - 1 keeps the warp convergent
@@ -376,14 +402,14 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
       }
     };
     // blocked save area of this warp: ((((t*2+dir)*ntiles+tile)*4+r)*8+warp) blocks of 4*NQ*32 (gates) / NQ*32 (c)
-    const long long blk_w = ((long long)dir * p.ntiles + tile) * 32 + (int)r * 8 + warp;
-    const long long blk_t = 2LL * p.ntiles * 32;
+    const long long blk_w = ((long long)dir * (p.ntiles * G) + tile) * 32 + (int)r * 8 + warp;
+    const long long blk_t = 2LL * (p.ntiles * G) * 32;
     load_pre(0);
     for (int s = 0; s < T; s++) {
       const int t = dir ? T - 1 - s : s;
       __half* sh = sh_base + (s & 1) * (N * 8);
       mbar_wait(mma_done, (uint32_t)(s & 1));
-      if (warp == 0 && lane == 0) Q_PROF(2);
+      if (warp_id == 0 && lane == 0) Q_PROF(2);
       tc_fence_after();
       float x[N];
       if (s > 0) {
@@ -416,7 +442,7 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
         *reinterpret_cast<float4*>(sa + lane * ROWF + n) = make_float4(x[n], x[n + 1], x[n + 2], x[n + 3]);
       if (s + 1 < T) load_pre(s + 1);  // a full step ahead of its use: DRAM latency never lands on the critical path
       __syncwarp();
-      if (warp == 0 && lane == 0) Q_PROF(3);
+      if (warp_id == 0 && lane == 0) Q_PROF(3);
       float gi[NQ], gf[NQ], gg[NQ], go[NQ];
 #pragma unroll
       for (int i = 0; i < NQ; i += 4) {
@@ -443,7 +469,7 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
         sh[(q * NQ + i) * 8 + j] = __float2half_rn(hv[i]);
         sh[(q * NQ + i + 1) * 8 + j] = __float2half_rn(hv[i + 1]);
       }
-      if (warp == 0 && lane == 0) Q_PROF(4);
+      if (warp_id == 0 && lane == 0) Q_PROF(4);
       if (s + 1 < T) {
         // all-gather FIRST (it is the only thing the next step waits for): this warp's [N cols x 8 units] fp16 block is
         // k-chunk 8r+4a+sub of every CTA's B operand; one async-proxy bulk copy per destination, completion counted on
@@ -455,7 +481,7 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
           bulk_copy_to_peer(mapa_u32(dst, (uint32_t)lane), smem_u32(sh), N * 16,
                             mapa_u32(smem_u32(&h_full[s & 1]), (uint32_t)lane));
         }
-        if (warp == 0 && lane == 0) Q_PROF(5);
+        if (warp_id == 0 && lane == 0) Q_PROF(5);
       } else {
         __syncwarp();
       }
@@ -794,12 +820,12 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
   }
 }
 
-template <int N, bool TS>
+template <int N, bool TS, int G = 1>
 constexpr int fwd_smem_bytes() {
   using L = QLayout<N>;
   // >= 120 KB even in TS mode: one LSTM CTA per SM (two would not fit their 2 x 320 TMEM columns and the second would
   // spin in tcgen05.alloc); a TF32 GEMM CTA (100 KB, 128 columns) of another stream still fits beside it
-  constexpr int need = (TS ? 0 : QW_BYTES) + 2 * L::HB_BYTES + L::ACT_BYTES + L::SH_BYTES + 64 + 1024;
+  constexpr int need = (TS ? 0 : QW_BYTES) + G * (2 * L::HB_BYTES + L::ACT_BYTES + L::SH_BYTES) + 64 + 1024;
   return need > 120 * 1024 ? need : 120 * 1024;
 }
 template <int N, bool TS>
@@ -813,6 +839,7 @@ constexpr int bwd_smem_bytes() {
 
 static int g_lstm_ts = 1;      // resident operand in TMEM (1) or in shared memory (0)
 static int g_lstm_tile = 0;    // 0 auto, else forced N (16 or 32)
+int g_lstm_dual = 1;           // DEER_OPT_LSTM_DUAL: two interleaved 16-column sub-tiles per CTA for no-keep 32-column tiles
 static long long* g_lstm_prof = nullptr;
 void lstm_cluster_set_profile(long long* buf) { g_lstm_prof = buf; }
 void lstm_cluster_set_option(int ts, int tile) {
@@ -831,16 +858,17 @@ static int pick_tile(int B) {
   return (2 * ((B + 15) / 16) <= 32) ? 16 : 32;
 }
 
-template <int N, bool TS>
+template <int N, bool TS, int G = 1>
 static int launch_fwd(const tc::LstmClusterParams& p, cudaStream_t stream) {
-  constexpr int smem = tc::fwd_smem_bytes<N, TS>();
+  constexpr int smem = tc::fwd_smem_bytes<N, TS, G>();
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(tc::lstm_fwd_cluster_kernel<N, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(tc::lstm_fwd_cluster_kernel<N, TS, G>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return cuda_status(e, "lstm_fwd_cluster smem attribute");
     attr = true;
   }
-  DEER_LAUNCH((tc::lstm_fwd_cluster_kernel<N, TS>), tc::QC * p.ntiles * 2, tc::QTHREADS, smem, stream, p);
+  DEER_LAUNCH((tc::lstm_fwd_cluster_kernel<N, TS, G>), tc::QC * p.ntiles * 2, G * 256 + 32, smem, stream, p);
   return DEER_OK;
 }
 template <int N, bool TS>
@@ -866,6 +894,9 @@ int lstm_fwd_cluster(const float* pre_il, const void* pre_f16, const float* w_fw
                           reinterpret_cast<__half*>(h16), reinterpret_cast<__nv_bfloat16*>(hb16), nullptr,
                           reinterpret_cast<const __half*>(pre_f16), T, B, (B + N - 1) / N, keep, g_lstm_prof};
   if (N == 16) return g_lstm_ts ? launch_fwd<16, true>(p, stream) : launch_fwd<16, false>(p, stream);
+  // inference (nothing kept for BPTT): the 32 batch columns of a CTA run as two interleaved 16-column sub-tiles.  The
+  // kept gate / cell layouts are those of the 32-column backward kernel, so training keeps the monolithic tile.
+  if (!keep && g_lstm_ts && g_lstm_dual) return launch_fwd<16, true, 2>(p, stream);
   return g_lstm_ts ? launch_fwd<32, true>(p, stream) : launch_fwd<32, false>(p, stream);
 }
 
