@@ -474,12 +474,12 @@ class _BiLSTMLayer(torch.autograd.Function):
     """One bidirectional nn.LSTM layer on a time-major input x [T,B,I] -> h [T,B,2H]."""
 
     @staticmethod
-    def forward(ctx, x, wif, whf, bif, bhf, wir, whr, bir, bhr):
+    def forward(ctx, x, wif, whf, bif, bhf, wir, whr, bir, bhr, grad_mode=True):
         x = _req(x, "x").contiguous()
         T, B, In = x.shape
         H = whf.shape[1]
         dev = x.device
-        keep = any(ctx.needs_input_grad)
+        keep = grad_mode and any(ctx.needs_input_grad)   # needs_input_grad ignores no_grad(): the caller's mode
         gates = torch.empty((T, B, 2, 4 * H), device=dev, dtype=torch.float32)
         bsum = torch.empty((2, 4 * H), device=dev, dtype=torch.float32)
         call("deer_axpby", ptr(bif), ptr(bhf), bsum.data_ptr(), 4 * H, 1.0, 1.0)
@@ -547,7 +547,7 @@ class _BiLSTMLayer(torch.autograd.Function):
                     dbs.append(db)
             grads.append((None if dwi_direct else dwi, None if dwh_direct else dwh, dbs[0], dbs[1]))
         (dwif, dwhf, dbif, dbhf), (dwir, dwhr, dbir, dbhr) = grads
-        return dx, dwif, dwhf, dbif, dbhf, dwir, dwhr, dbir, dbhr
+        return dx, dwif, dwhf, dbif, dbhf, dwir, dwhr, dbir, dbhr, None
 
 
 class _BiLSTMLayerCluster(torch.autograd.Function):
@@ -566,7 +566,8 @@ class _BiLSTMLayerCluster(torch.autograd.Function):
     casts (the dropped fp32 tensor is never materialised) and into dx in backward."""
 
     @staticmethod
-    def forward(ctx, x, wif, whf, bif, bhf, wir, whr, bir, bhr, drop=None, x16_in=None, emit_f16=False):
+    def forward(ctx, x, wif, whf, bif, bhf, wir, whr, bir, bhr, drop=None, x16_in=None, emit_f16=False,
+                grad_mode=True):
         """x16_in: FP16 copy of x written by the previous layer's recurrence kernel (skips the cast pass); emit_f16: make
         this layer's kernel write such a copy of h.  Returns (h, h_f16 or an empty tensor)."""
         x = _req(x, "x").contiguous()
@@ -574,7 +575,7 @@ class _BiLSTMLayerCluster(torch.autograd.Function):
         H = whf.shape[1]
         G = 4 * H
         dev = x.device
-        keep = any(ctx.needs_input_grad)
+        keep = grad_mode and any(ctx.needs_input_grad)   # needs_input_grad ignores no_grad(): the caller's mode
         use16 = _state["lstm_gemm16"] and _state["engine"] == ENGINE_AUTO   # a forced engine (tests) is respected
         wi_il = torch.empty((2, G, In), device=dev, dtype=torch.float32)
         b_il = torch.empty((2, G), device=dev, dtype=torch.float32)
@@ -717,7 +718,7 @@ class _BiLSTMLayerCluster(torch.autograd.Function):
                 dbs.append(None if direct else tgt)
             out.append((None if dwi_direct else dwi, None if dwh_direct else dwh, dbs[0], dbs[1]))
         (dwif, dwhf, dbif, dbhf), (dwir, dwhr, dbir, dbhr) = out
-        return dx, dwif, dwhf, dbif, dbhf, dwir, dwhr, dbir, dbhr, None, None, None
+        return dx, dwif, dwhf, dbif, dbhf, dwir, dwhr, dbir, dbhr, None, None, None, None
 
 
 def bilstm_layer(x_tm, wif, whf, bif, bhf, wir, whr, bir, bhr, input_dropout: float = 0.0, training: bool = False,
@@ -741,10 +742,12 @@ def bilstm_layer(x_tm, wif, whf, bif, bhf, wir, whr, bir, bhr, input_dropout: fl
             x_tm = dropout(x_tm, input_dropout, True)
     if cluster:
         want = bool(emit_f16 and _state["lstm_gemm16"] and _state["engine"] == ENGINE_AUTO)
+        # (a custom Function's forward always runs with grad mode off: the caller's mode is passed in, so that an
+        # inference forward keeps nothing for BPTT and can use the no-keep kernels)
         h, h16 = _BiLSTMLayerCluster.apply(x_tm, wif, whf, bif, bhf, wir, whr, bir, bhr, drop,
-                                           x_f16 if drop is None else None, want)
+                                           x_f16 if drop is None else None, want, torch.is_grad_enabled())
         return (h, h16 if h16.numel() else None) if return_f16 else h
-    h = _BiLSTMLayer.apply(x_tm, wif, whf, bif, bhf, wir, whr, bir, bhr)
+    h = _BiLSTMLayer.apply(x_tm, wif, whf, bif, bhf, wir, whr, bir, bhr, torch.is_grad_enabled())
     return (h, None) if return_f16 else h
 
 
