@@ -146,6 +146,7 @@ def main():
     ap.add_argument("--no-pooled", action="store_true")
     ap.add_argument("--no-branch-streams", action="store_true",
                     help="ablation: video/text encoders on the main stream behind the audio encoder")
+    ap.add_argument("--branch-max-batch", type=int, default=None)
     ap.add_argument("--no-defer-wgrad", action="store_true",
                     help="ablation: small-layer weight gradients on the main stream")
     args = ap.parse_args()
@@ -171,6 +172,8 @@ def main():
     pk = peaks()
     ops.set_branch_streams(not args.no_branch_streams)
     ops.set_defer_wgrad(not args.no_defer_wgrad)
+    if args.branch_max_batch is not None:
+        ops.set_branch_max_batch(args.branch_max_batch)
 
     def barrier():
         if world > 1:

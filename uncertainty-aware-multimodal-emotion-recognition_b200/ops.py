@@ -25,7 +25,8 @@ ENGINE_AUTO, ENGINE_SIMT, ENGINE_TF32 = 0, 1, 2
 # 0.999 gate (tools/precision_probe.py).
 _state = {"engine": ENGINE_AUTO, "lstm_engine": ENGINE_AUTO, "exact_small_fwd": True, "exact_small_bwd": True,
           "small_rows": 8192, "direct_grad": False, "lstm_gemm16": True, "fuse_lstm_dropout": True,
-          "branch_streams": True, "lstm_pre16": True, "defer_wgrad": True}
+          "branch_streams": True, "lstm_pre16": True, "defer_wgrad": True,
+          "branch_max_batch": 512}
 
 
 def set_defer_wgrad(on: bool):
@@ -64,6 +65,15 @@ def set_branch_streams(on: bool):
 
 def branch_streams_enabled() -> bool:
     return _state["branch_streams"]
+
+
+def branch_max_batch() -> int:
+    return _state["branch_max_batch"]
+
+
+def set_branch_max_batch(n: int):
+    """Largest batch for which the sequence model forks its encoders onto two streams (default 512)."""
+    _state["branch_max_batch"] = int(n)
 
 
 def set_fuse_lstm_dropout(on: bool):

@@ -41,9 +41,11 @@ class SequenceDEERModel(nn.Module):
             attention_mask = d.get("attention_mask", attention_mask)
             linguistic_features = d.get("linguistic_features", linguistic_features)
         ops.begin_step()
-        # up to 512 samples the recurrence is ONE wave of clusters; beyond that the second wave competes with the side
-        # work for SMs and the overlap costs more than it hides (measured at B = 1024: 6.46 -> 6.72 ms)
-        if ops.branch_streams_enabled() and audio.is_cuda and audio.shape[0] <= 512:
+        # training: up to 512 samples the recurrence is ONE wave of clusters; beyond that the second wave of the
+        # (gate / cell storing) kernels competes with the side work for SMs.  Inference forwards (no stores for BPTT,
+        # dual sub-tile kernel) gain at every size (B = 1024: 5.28 -> 5.11 ms).
+        if ops.branch_streams_enabled() and audio.is_cuda and (
+                audio.shape[0] <= ops.branch_max_batch() or not torch.is_grad_enabled()):
             # The three encoders are independent until the fusion.  The audio LSTM recurrence is a latency-bound
             # persistent kernel (128 of 148 SMs, one CTA each, mostly waiting on the cluster exchange), so it runs on
             # its own HIGH-PRIORITY stream (its CTAs and the second wave of a large batch are placed first) while the
