@@ -147,6 +147,7 @@ def main():
     ap.add_argument("--no-branch-streams", action="store_true",
                     help="ablation: video/text encoders on the main stream behind the audio encoder")
     ap.add_argument("--branch-max-batch", type=int, default=None)
+    ap.add_argument("--tf32-pair", type=int, default=None, help="DEER_OPT_TF32_PAIR override (ablation)")
     ap.add_argument("--no-defer-wgrad", action="store_true",
                     help="ablation: small-layer weight gradients on the main stream")
     args = ap.parse_args()
@@ -174,6 +175,10 @@ def main():
     ops.set_defer_wgrad(not args.no_defer_wgrad)
     if args.branch_max_batch is not None:
         ops.set_branch_max_batch(args.branch_max_batch)
+    if args.tf32_pair is not None:
+        _lib.set_option(6, args.tf32_pair)
+        if not args.tf32_pair:
+            ops.set_conv_window(False)   # the sliding-window Conv1d needs the pair kernel's TMA reduce epilogue
 
     def barrier():
         if world > 1:
@@ -424,9 +429,9 @@ def _time_launches(torch, fn, n, warm=5):
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/)
 NCU_TRAFFIC = {
-    # profiles/r1_ncu_full_roofline_v11_summary.txt (ncu --set full --clock-control none, per launch)
-    "gemm_h16_pair_out16": 80.8e6 + 255.9e6,                       # algorithmic 395 MB; part of C16 still in L2 at kernel end
-    "nig_stats_plus_finish": 251.7e6 + 302.1e6 + 251.7e6 + 160.9e6,  # two passes: the 252 MB of operands are read twice
+    # profiles/r1_ncu_full_roofline_v12_summary.txt (ncu --set full --clock-control none, per launch)
+    "gemm_h16_pair_out16": 80.8e6 + 255.4e6,                       # algorithmic 395 MB; part of C16 still in L2 at kernel end
+    "nig_stats_plus_finish": 251.7e6 + 296.4e6 + 251.7e6 + 156.9e6,  # two passes: the 252 MB of operands are read twice
 }
 
 
