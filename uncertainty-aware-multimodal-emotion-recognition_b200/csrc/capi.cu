@@ -76,7 +76,7 @@ int deer_set_option(int option, int value) {
       g_h16_pair = value ? 1 : 0;
       return DEER_OK;
     case DEER_OPT_LSTM_DUAL:
-      g_lstm_dual = value ? 1 : 0;
+      g_lstm_dual = value;
       return DEER_OK;
     case DEER_OPT_NIG_PIPELINE:
       g_nig_pipe = value ? 1 : 0;

@@ -888,15 +888,19 @@ int lstm_cluster_tile(int B) { return pick_tile(B); }
 
 int lstm_fwd_cluster(const float* pre_il, const void* pre_f16, const float* w_fwd, const float* w_rev, float* h_out,
                      float* gact, float* c_blk, void* h16, void* hb16, int T, int B, cudaStream_t stream) {
-  const int N = pick_tile(B);
+  int N = pick_tile(B);
   const int keep = (gact != nullptr && c_blk != nullptr) ? 1 : 0;
+  // experiment (DEER_OPT_LSTM_DUAL = 2): training forward of a one-wave batch on HALF the SMs, as dual sub-tiles of 32
+  // columns per CTA; the kept layouts are the 16-column kernel's when ceil(B/16) == 2 ceil(B/32)
+  const bool dual_keep = g_lstm_dual == 2 && keep && N == 16 && g_lstm_ts && (B + 15) / 16 == 2 * ((B + 31) / 32);
+  if (dual_keep) N = 32;
   tc::LstmClusterParams p{const_cast<float*>(pre_il), w_fwd, w_rev, h_out, gact, c_blk, nullptr, nullptr,
                           reinterpret_cast<__half*>(h16), reinterpret_cast<__nv_bfloat16*>(hb16), nullptr,
                           reinterpret_cast<const __half*>(pre_f16), T, B, (B + N - 1) / N, keep, g_lstm_prof};
   if (N == 16) return g_lstm_ts ? launch_fwd<16, true>(p, stream) : launch_fwd<16, false>(p, stream);
   // inference (nothing kept for BPTT): the 32 batch columns of a CTA run as two interleaved 16-column sub-tiles.  The
   // kept gate / cell layouts are those of the 32-column backward kernel, so training keeps the monolithic tile.
-  if (!keep && g_lstm_ts && g_lstm_dual) return launch_fwd<16, true, 2>(p, stream);
+  if ((!keep || dual_keep) && g_lstm_ts && g_lstm_dual) return launch_fwd<16, true, 2>(p, stream);
   return g_lstm_ts ? launch_fwd<32, true>(p, stream) : launch_fwd<32, false>(p, stream);
 }
 
