@@ -56,6 +56,7 @@ long long deer_launch_count(void);
 #define DEER_OPT_TF32_PAIR 6       /* 1 (default): large TF32 GEMMs on the CTA-pair kernel (256x256 tiles); 0: 128x128-tile kernel */
 #define DEER_OPT_NIG_PIPELINE 8    /* 1 (default): software-pipelined operand loads in the two NIG loss passes (80 registers, 4 blocks/SM); 0: load -> compute trips (64 registers, 5 blocks/SM) */
 #define DEER_OPT_LSTM_DUAL 9       /* 1 (default): inference LSTM at 32 batch columns per CTA = two interleaved 16-column sub-tiles (own warps, shared resident weights); 0: one monolithic 32-column tile; 2: experiment - also the TRAINING forward of a one-wave batch as dual sub-tiles on half the SMs (measured slower: 4.66 -> 5.39 ms, the audio stream is the critical path) */
+#define DEER_OPT_LSTM_COLSPLIT 10  /* 1: forward LSTM on 16-column tiles with 16 compute warps (two column halves per tile; same results, measured no faster: the step is instruction-issue bound); 0 (default): 8 compute warps */
 #define DEER_OPT_PDL 7             /* 1: launch kernels with programmatic stream serialization (PDL); 0 (default, faster as measured) */
 int deer_set_option(int option, int value);
 /* debugging aid: device buffer of >= 32 int64 that receives a clock64() trace of four steps of the persistent LSTM

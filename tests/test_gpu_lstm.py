@@ -194,3 +194,28 @@ def test_dual_subtile_forward_matches_monolithic_tile(B, T, In):
         ops.set_gemm_engine(ops.ENGINE_SIMT)
         h_ref, _ = run(x, ws, ops.ENGINE_SIMT, False)
         assert_close(h_dual, h_ref, 1e-3, "h vs exact fp32")
+
+
+@pytest.mark.parametrize("B,T,In", [(4, 6, 84), (70, 9, 512), (130, 33, 84), (256, 40, 512)])
+@pytest.mark.parametrize("grad", [False, True])
+def test_column_split_forward_matches_eight_warp_kernel(B, T, In, grad):
+    """Forward on 16-column tiles with 16 compute warps (two column halves, DEER_OPT_LSTM_COLSPLIT, default) against the
+    8-warp kernel: same h, and -- through the unchanged BPTT kernel reading the kept gates / cell states -- the same
+    gradients (the kept layouts must be identical)."""
+    H = 256
+    ws = make_layer(In, H, B + T + 11)
+    x = torch.randn(B, T, In, generator=torch.Generator().manual_seed(B + 5))
+    _lib.set_option(3, 16)
+    res = []
+    try:
+        for cs in (1, 0):
+            _lib.set_option(10, cs)
+            res.append(run(x, ws, ops.ENGINE_AUTO, grad))
+    finally:
+        _lib.set_option(10, 1)
+        _lib.set_option(3, 0)
+    (h1, g1), (h0, g0) = res
+    assert torch.equal(h1, h0) or float((h1 - h0).abs().max()) < 1e-6
+    if grad:
+        for a, b_ in zip(g1, g0):
+            assert_close(a, b_, 1e-5, "gradients")

@@ -28,6 +28,7 @@ extern int g_small_engine;
 extern int g_h16_pair;
 extern int g_nig_pipe;
 extern int g_lstm_dual;
+extern int g_lstm_colsplit;
 extern int g_tf32_pair;
 bool gemm_tf32_pair_supported(int transA, int transB, int M, int N, int K, long long ldc, const float* bias, int act,
                               float beta);
@@ -74,6 +75,9 @@ int deer_set_option(int option, int value) {
       return DEER_OK;
     case DEER_OPT_H16_PAIR:
       g_h16_pair = value ? 1 : 0;
+      return DEER_OK;
+    case DEER_OPT_LSTM_COLSPLIT:
+      g_lstm_colsplit = value ? 1 : 0;
       return DEER_OK;
     case DEER_OPT_LSTM_DUAL:
       g_lstm_dual = value;

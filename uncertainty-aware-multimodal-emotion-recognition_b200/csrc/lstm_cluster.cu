@@ -111,7 +111,9 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 }
 template <int N>
 __device__ __forceinline__ void tmem_ld_row(uint32_t taddr, float* v) {
-  if constexpr (N == 16) {
+  if constexpr (N == 8) {
+    tmem_ld8(taddr, v);
+  } else if constexpr (N == 16) {
     tmem_ld16(taddr, v);
   } else {
     tmem_ld32(taddr, v);
@@ -218,14 +220,24 @@ constexpr int Q_PROF_S0 = 64, Q_PROF_STEPS = 4, Q_PROF_SLOTS = 8;
 // chain (MMA -> gate epilogue -> cell update -> exchange); with two tiles in flight one tile's MUFU-bound epilogue runs
 // while the other's MMAs and DSMEM exchange are in flight, instead of every unit idling in turn (a monolithic 32-column
 // tile took 2.75 us per step; two waves of CTAs were needed at B = 1024).
-template <int N, bool TS, int G>
-__global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(G * 256 + 32, 1)
+// CS = 2 (training, N = 16): the SAME tile and MMAs, but two sets of 8 compute warps that each take one half of the
+// tile's batch columns (a warp may read its TMEM lane quadrant at any column): the gate epilogue / cell update /
+// exchange of a step -- a latency-bound chain with only two warps per scheduler -- runs at half the length per warp.
+// The kept gate / cell layouts stay those of the 8-warp kernel, so the BPTT kernel is unchanged.
+template <int N, bool TS, int G, int CS = 1>
+__global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(G * CS * 256 + 32, 1)
     lstm_fwd_cluster_kernel(const LstmClusterParams p) {
   DEER_PDL_ENTRY();
+  static_assert(CS == 1 || (CS == 2 && G == 1 && N == 16), "column split: one 16-column tile, two warp sets");
   using L = QLayout<N>;
-  constexpr int NQ = L::NQ, ROWF = L::ROWF;
-  constexpr int MMAW = 8 * G;            // index of the MMA-issuing warp
-  constexpr int NTHREADS = G * 256 + 32;
+  constexpr int NW = N / CS;             // batch columns per compute warp
+  constexpr int NQ = NW / 4;             // batch columns per cell thread
+  constexpr int ROWF = NW + 4;           // padded fp32 row of the per-warp transpose tile
+  constexpr int NCW = 8 * G * CS;        // compute warps
+  constexpr int MMAW = NCW;              // index of the MMA-issuing warp
+  constexpr int NTHREADS = NCW * 32 + 32;
+  constexpr int ACT_TOTAL = NCW * 32 * ROWF * 4;   // per-warp activation transpose tiles
+  constexpr int SH_TOTAL = NCW * 2 * NW * 16;      // double-buffered per-warp fp16 h blocks [NW cols][8 units]
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128B swizzle atoms, applied as an OFFSET on the __shared__ array: going through
   // uintptr_t would make every later access a generic LD/ST instead of LDS/STS
@@ -233,18 +245,18 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(G * 256 + 32, 1)
   uint8_t* wsm = smem;                                   // SS: 128 KB resident W (unused in TS mode)
   uint8_t* hbuf_all = smem + (TS ? 0 : QW_BYTES);        // per group: 2 x HB_BYTES
   float* stage_act_all = reinterpret_cast<float*>(hbuf_all + G * 2 * L::HB_BYTES);
-  __half* stage_h_all = reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(stage_act_all) + G * L::ACT_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stage_h_all) + G * L::SH_BYTES);
+  __half* stage_h_all = reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(stage_act_all) + ACT_TOTAL);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stage_h_all) + SH_TOTAL);
   uint64_t* h_full_all = bars;            // [G][2]
   uint64_t* mma_done_all = bars + 2 * G;  // [G]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * G);
 
   const int warp_id = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int grp = (G == 2 && warp_id >= 8 && warp_id < 16) ? 1 : 0;   // batch sub-tile of this compute warp
+  const int chalf = (CS == 2 && warp_id >= 8 && warp_id < 16) ? 1 : 0;  // column half of this compute warp
   const int warp = warp_id == MMAW ? 8 : (warp_id & 7);              // role index: 0..7 compute, 8 = MMA issuer
+  const int wslot = warp_id < NCW ? warp_id : 0;                     // private staging slot of a compute warp
   uint8_t* hbuf = hbuf_all + grp * 2 * L::HB_BYTES;
-  float* stage_act = stage_act_all + grp * (L::ACT_BYTES / 4);
-  __half* stage_h = stage_h_all + grp * (L::SH_BYTES / 2);
   uint64_t* h_full = h_full_all + 2 * grp;
   uint64_t* mma_done = mma_done_all + grp;
   const uint32_t r = cluster_ctarank();
@@ -373,9 +385,10 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(G * 256 + 32, 1)
     const int j = lane >> 2, g = lane & 3;        // gate-row role: unit j of this warp, gate g
     const int ul = a * 32 + sub * 8 + j;          // unit inside the CTA
     const int ug = (int)r * QU + ul;              // unit inside the direction
-    const uint32_t tacc = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(grp * 2 * N + a * N);
-    float* sa = stage_act + warp * (32 * ROWF);
-    __half* sh_base = stage_h + warp * (2 * N * 8);
+    const uint32_t tacc = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(grp * 2 * N + a * N + chalf * NW);
+    float* sa = stage_act_all + wslot * (32 * ROWF);
+    __half* sh_base = stage_h_all + wslot * (2 * NW * 8);
+    const int bw0 = b0 + chalf * NW;              // first batch column of this warp
     const float sc = (g == 2) ? 2.f : 1.f;        // tanh(x) = 2*sigmoid(2x) - 1 keeps the warp convergent
     const int q = g;                              // cell role: columns [q*NQ, q*NQ+NQ) of unit j
     float cst[NQ];
@@ -383,22 +396,22 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(G * 256 + 32, 1)
     for (int i = 0; i < NQ; i++) cst[i] = 0.f;
     // pre-activations of the NEXT step, as loaded (fp32 bits, or an FP16 value in the low half): converting at load time
     // would make the convert instruction wait for the DRAM round trip inside the current step
-    uint32_t pre[N];
+    uint32_t pre[NW];
     const bool pre_is16 = p.pre16 != nullptr;
     const int il0 = 4 * ((int)r * QU + a * 32 + sub * 8);  // first interleaved gate column of this warp
     auto load_pre = [&](int s) {
       const int t = dir ? T - 1 - s : s;
-      const long long off = (((long long)t * B + b0) * 2 + dir) * (4 * QH) + il0 + lane;
+      const long long off = (((long long)t * B + bw0) * 2 + dir) * (4 * QH) + il0 + lane;
       if (pre_is16) {   // FP16 pre-activations (the projection GEMM's 16-bit epilogue): half the bytes of the only
                         // stream this kernel reads; one 64-byte request per warp and sample
         const unsigned short* src = reinterpret_cast<const unsigned short*>(p.pre16) + off;
 #pragma unroll
-        for (int n = 0; n < N; n++) pre[n] = (b0 + n < B) ? (uint32_t)__ldcs(src + (long long)n * (8 * QH)) : 0u;
+        for (int n = 0; n < NW; n++) pre[n] = (bw0 + n < B) ? (uint32_t)__ldcs(src + (long long)n * (8 * QH)) : 0u;
       } else {
         const float* src = p.gates + off;
 #pragma unroll
-        for (int n = 0; n < N; n++)
-          pre[n] = (b0 + n < B) ? __float_as_uint(__ldcs(src + (long long)n * (8 * QH))) : 0u;
+        for (int n = 0; n < NW; n++)
+          pre[n] = (bw0 + n < B) ? __float_as_uint(__ldcs(src + (long long)n * (8 * QH))) : 0u;
       }
     };
     // blocked save area of this warp: ((((t*2+dir)*ntiles+tile)*4+r)*8+warp) blocks of 4*NQ*32 (gates) / NQ*32 (c)
@@ -407,30 +420,30 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(G * 256 + 32, 1)
     load_pre(0);
     for (int s = 0; s < T; s++) {
       const int t = dir ? T - 1 - s : s;
-      __half* sh = sh_base + (s & 1) * (N * 8);
+      __half* sh = sh_base + (s & 1) * (NW * 8);
       mbar_wait(mma_done, (uint32_t)(s & 1));
       if (warp_id == 0 && lane == 0) Q_PROF(2);
       tc_fence_after();
-      float x[N];
+      float x[NW];
       if (s > 0) {
-        tmem_ld_row<N>(tacc, x);
+        tmem_ld_row<NW>(tacc, x);
         tmem_ld_wait();
       } else {
 #pragma unroll
-        for (int n = 0; n < N; n++) x[n] = 0.f;
+        for (int n = 0; n < NW; n++) x[n] = 0.f;
       }
       tc_fence_before();
       if (pre_is16) {
 #pragma unroll
-        for (int n = 0; n < N; n++) x[n] += __half2float(__ushort_as_half((unsigned short)pre[n]));
+        for (int n = 0; n < NW; n++) x[n] += __half2float(__ushort_as_half((unsigned short)pre[n]));
       } else {
 #pragma unroll
-        for (int n = 0; n < N; n++) x[n] += __uint_as_float(pre[n]);
+        for (int n = 0; n < NW; n++) x[n] += __uint_as_float(pre[n]);
       }
       {
         const float nsl = -1.4426950408889634f * sc;   // sigmoid(sc x) = 1 / (1 + 2^(nsl x))
 #pragma unroll
-        for (int n = 0; n < N; n += 2) {
+        for (int n = 0; n < NW; n += 2) {
           float s0, s1;
           sigmoid_pair_ex2(x[n] * nsl, x[n + 1] * nsl, s0, s1);
           x[n] = fmaf(sc, s0, 1.f - sc);
@@ -438,12 +451,20 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(G * 256 + 32, 1)
         }
       }
 #pragma unroll
-      for (int n = 0; n < N; n += 4)
+      for (int n = 0; n < NW; n += 4)
         *reinterpret_cast<float4*>(sa + lane * ROWF + n) = make_float4(x[n], x[n + 1], x[n + 2], x[n + 3]);
       if (s + 1 < T) load_pre(s + 1);  // a full step ahead of its use: DRAM latency never lands on the critical path
       __syncwarp();
       if (warp_id == 0 && lane == 0) Q_PROF(3);
       float gi[NQ], gf[NQ], gg[NQ], go[NQ];
+      if constexpr (NQ == 2) {
+        const float2 vi = *reinterpret_cast<const float2*>(sa + (4 * j + 0) * ROWF + q * NQ);
+        const float2 vf = *reinterpret_cast<const float2*>(sa + (4 * j + 1) * ROWF + q * NQ);
+        const float2 vg = *reinterpret_cast<const float2*>(sa + (4 * j + 2) * ROWF + q * NQ);
+        const float2 vo = *reinterpret_cast<const float2*>(sa + (4 * j + 3) * ROWF + q * NQ);
+        gi[0] = vi.x; gi[1] = vi.y; gf[0] = vf.x; gf[1] = vf.y;
+        gg[0] = vg.x; gg[1] = vg.y; go[0] = vo.x; go[1] = vo.y;
+      } else
 #pragma unroll
       for (int i = 0; i < NQ; i += 4) {
         const float4 vi = *reinterpret_cast<const float4*>(sa + (4 * j + 0) * ROWF + q * NQ + i);
@@ -477,8 +498,9 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(G * 256 + 32, 1)
         fence_proxy_async_smem();
         __syncwarp();
         if (lane < QC) {
-          const uint32_t dst = smem_u32(hbuf) + (s & 1) * L::HB_BYTES + ((int)r * 8 + 4 * a + sub) * (N * 16);
-          bulk_copy_to_peer(mapa_u32(dst, (uint32_t)lane), smem_u32(sh), N * 16,
+          const uint32_t dst = smem_u32(hbuf) + (s & 1) * L::HB_BYTES + ((int)r * 8 + 4 * a + sub) * (N * 16) +
+                               chalf * (NW * 16);
+          bulk_copy_to_peer(mapa_u32(dst, (uint32_t)lane), smem_u32(sh), NW * 16,
                             mapa_u32(smem_u32(&h_full[s & 1]), (uint32_t)lane));
         }
         if (warp_id == 0 && lane == 0) Q_PROF(5);
@@ -486,11 +508,26 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(G * 256 + 32, 1)
         __syncwarp();
       }
       // ---- everything below is off the recurrence's critical path: global stores of this step's results
-      const long long row0 = (long long)t * B + b0 + q * NQ;
+      const long long row0 = (long long)t * B + bw0 + q * NQ;
       const long long blk = (long long)t * blk_t + blk_w;
 #pragma unroll
       for (int i = 0; i < NQ; i++)
-        if (b0 + q * NQ + i < B) p.h_out[(row0 + i) * (2 * QH) + dir * QH + ug] = hv[i];
+        if (bw0 + q * NQ + i < B) p.h_out[(row0 + i) * (2 * QH) + dir * QH + ug] = hv[i];
+      if constexpr (CS == 2) {
+        if (p.keep) {
+          // the 8-warp kernel's blocked layout ([gate][32 lanes][4 columns] per warp block): this thread's two columns
+          // are one half of the float4 that lane (j, chalf*2 + q/2) of the 8-warp kernel would store
+          const int lane8 = j * 4 + chalf * 2 + (q >> 1);
+          const int eo = (q & 1) * 2;
+          float* gs = p.gact + blk * 512 + lane8 * 4 + eo;
+          float* cs = p.c_all + blk * 128 + lane8 * 4 + eo;
+          __stcs(reinterpret_cast<float2*>(gs + 0 * 128), make_float2(gi[0], gi[1]));
+          __stcs(reinterpret_cast<float2*>(gs + 1 * 128), make_float2(gf[0], gf[1]));
+          __stcs(reinterpret_cast<float2*>(gs + 2 * 128), make_float2(gg[0], gg[1]));
+          __stcs(reinterpret_cast<float2*>(gs + 3 * 128), make_float2(go[0], go[1]));
+          __stcs(reinterpret_cast<float2*>(cs), make_float2(cst[0], cst[1]));
+        }
+      } else
       if (p.keep) {
         float4* gs = reinterpret_cast<float4*>(p.gact + blk * (4 * NQ * 32)) + lane;
         float4* cs = reinterpret_cast<float4*>(p.c_all + blk * (NQ * 32)) + lane;
@@ -506,9 +543,9 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(G * 256 + 32, 1)
       if (p.h16 || p.hb16) {
         // the warp's [N cols x 8 units] fp16 block doubles as the source of the 16-bit shadows of h: one 16-byte
         // store per sample row (the tile is double-buffered and only READ by the bulk copies in flight)
-        if (lane < N && b0 + lane < B) {
+        if (lane < NW && bw0 + lane < B) {
           const uint4 hv8 = *reinterpret_cast<const uint4*>(sh + lane * 8);
-          const long long o = ((long long)t * B + b0 + lane) * (2 * QH) + dir * QH + (int)r * QU + a * 32 + sub * 8;
+          const long long o = ((long long)t * B + bw0 + lane) * (2 * QH) + dir * QH + (int)r * QU + a * 32 + sub * 8;
           if (p.h16) *reinterpret_cast<uint4*>(p.h16 + o) = hv8;
           if (p.hb16) {
             const __half2* hp = reinterpret_cast<const __half2*>(&hv8);
@@ -820,12 +857,13 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
   }
 }
 
-template <int N, bool TS, int G = 1>
+template <int N, bool TS, int G = 1, int CS = 1>
 constexpr int fwd_smem_bytes() {
   using L = QLayout<N>;
+  constexpr int NW = N / CS, NCW = 8 * G * CS;
   // >= 120 KB even in TS mode: one LSTM CTA per SM (two would not fit their 2 x 320 TMEM columns and the second would
   // spin in tcgen05.alloc); a TF32 GEMM CTA (100 KB, 128 columns) of another stream still fits beside it
-  constexpr int need = (TS ? 0 : QW_BYTES) + G * (2 * L::HB_BYTES + L::ACT_BYTES + L::SH_BYTES) + 64 + 1024;
+  constexpr int need = (TS ? 0 : QW_BYTES) + G * 2 * L::HB_BYTES + NCW * 32 * (NW + 4) * 4 + NCW * 2 * NW * 16 + 64 + 1024;
   return need > 120 * 1024 ? need : 120 * 1024;
 }
 template <int N, bool TS>
@@ -839,6 +877,7 @@ constexpr int bwd_smem_bytes() {
 
 static int g_lstm_ts = 1;      // resident operand in TMEM (1) or in shared memory (0)
 static int g_lstm_tile = 0;    // 0 auto, else forced N (16 or 32)
+int g_lstm_colsplit = 0;       // DEER_OPT_LSTM_COLSPLIT: 16 compute warps (two column halves) on 16-column tiles; measured: no gain (1.444 vs 1.438 us/step: the step is issue-bound, not latency-bound), so off
 int g_lstm_dual = 1;           // DEER_OPT_LSTM_DUAL: two interleaved 16-column sub-tiles per CTA for no-keep 32-column tiles
 static long long* g_lstm_prof = nullptr;
 void lstm_cluster_set_profile(long long* buf) { g_lstm_prof = buf; }
@@ -858,17 +897,17 @@ static int pick_tile(int B) {
   return (2 * ((B + 15) / 16) <= 32) ? 16 : 32;
 }
 
-template <int N, bool TS, int G = 1>
+template <int N, bool TS, int G = 1, int CS = 1>
 static int launch_fwd(const tc::LstmClusterParams& p, cudaStream_t stream) {
-  constexpr int smem = tc::fwd_smem_bytes<N, TS, G>();
+  constexpr int smem = tc::fwd_smem_bytes<N, TS, G, CS>();
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(tc::lstm_fwd_cluster_kernel<N, TS, G>,
+    cudaError_t e = cudaFuncSetAttribute(tc::lstm_fwd_cluster_kernel<N, TS, G, CS>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return cuda_status(e, "lstm_fwd_cluster smem attribute");
     attr = true;
   }
-  DEER_LAUNCH((tc::lstm_fwd_cluster_kernel<N, TS, G>), tc::QC * p.ntiles * 2, G * 256 + 32, smem, stream, p);
+  DEER_LAUNCH((tc::lstm_fwd_cluster_kernel<N, TS, G, CS>), tc::QC * p.ntiles * 2, G * CS * 256 + 32, smem, stream, p);
   return DEER_OK;
 }
 template <int N, bool TS>
@@ -897,7 +936,10 @@ int lstm_fwd_cluster(const float* pre_il, const void* pre_f16, const float* w_fw
   tc::LstmClusterParams p{const_cast<float*>(pre_il), w_fwd, w_rev, h_out, gact, c_blk, nullptr, nullptr,
                           reinterpret_cast<__half*>(h16), reinterpret_cast<__nv_bfloat16*>(hb16), nullptr,
                           reinterpret_cast<const __half*>(pre_f16), T, B, (B + N - 1) / N, keep, g_lstm_prof};
-  if (N == 16) return g_lstm_ts ? launch_fwd<16, true>(p, stream) : launch_fwd<16, false>(p, stream);
+  if (N == 16) {
+    if (g_lstm_ts && g_lstm_colsplit) return launch_fwd<16, true, 1, 2>(p, stream);
+    return g_lstm_ts ? launch_fwd<16, true>(p, stream) : launch_fwd<16, false>(p, stream);
+  }
   // inference (nothing kept for BPTT): the 32 batch columns of a CTA run as two interleaved 16-column sub-tiles.  The
   // kept gate / cell layouts are those of the 32-column backward kernel, so training keeps the monolithic tile.
   if ((!keep || dual_keep) && g_lstm_ts && g_lstm_dual) return launch_fwd<16, true, 2>(p, stream);
