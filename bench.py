@@ -146,6 +146,8 @@ def main():
     ap.add_argument("--no-pooled", action="store_true")
     ap.add_argument("--no-branch-streams", action="store_true",
                     help="ablation: video/text encoders on the main stream behind the audio encoder")
+    ap.add_argument("--overlap-exchange", action="store_true",
+                    help="ablation: all-reduce the non-audio gradients beside the audio backward (measured: no gain)")
     ap.add_argument("--branch-max-batch", type=int, default=None)
     ap.add_argument("--tf32-pair", type=int, default=None, help="DEER_OPT_TF32_PAIR override (ablation)")
     ap.add_argument("--lstm-dual", type=int, default=None, help="DEER_OPT_LSTM_DUAL override (ablation)")
@@ -214,6 +216,24 @@ def main():
     batches = [synth_batch(TRAIN_B, dev, gen) for _ in range(NB)]
 
     use_graph = not args.no_graph
+    overlap_check = None
+    if world > 1:
+        # the early (overlapped) gradient exchange must give the same reduced gradients as one all-reduce at the end,
+        # up to the run-to-run noise of the atomically accumulated / split-K gradients (measured on the spot)
+        g = []
+        for ov in (True, False, False):
+            trainer.overlap_exchange = ov
+            trainer.forward_backward(batches[0])
+            if not trainer._grads_reduced:
+                trainer._allreduce(trainer.flat.grads)
+            trainer._grads_reduced = False
+            torch.cuda.synchronize()
+            g.append(trainer.flat.grads.clone())
+        trainer.overlap_exchange = args.overlap_exchange
+        noise = float((g[1] - g[2]).norm() / g[2].norm())
+        overlap_check = float((g[0] - g[2]).norm() / g[2].norm())
+        assert overlap_check < 3 * noise + 1e-5, f"overlapped gradient exchange differs: {overlap_check} (noise {noise})"
+        del g
     # launches of one step, counted on an eager step (a graph replay issues the same kernels with one host call)
     trainer.train_step(batches[0])
     l0 = _lib.launch_count()
@@ -349,6 +369,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4},
         "cuda_graph": use_graph, "branch_streams": ops.branch_streams_enabled(),
+        "exchange_overlap": bool(world > 1 and trainer.overlap_exchange), "exchange_overlap_check": overlap_check,
         "gpu_launches": int(launches_per_step * K),
         "launches_per_step": int(launches_per_step),
         "inference": {"value": infer_value, "unit": "samples/s", "batch_per_gpu": INFER_B, "ms_per_step": infer_ms,

@@ -127,6 +127,9 @@ class EnhancedVideoEncoder(nn.Module):
                                       "per-frame features [B,F,frame_feature_dim]")
         sp, cnn = self.spatial_projection, self.temporal_cnn
         p = ops.linear(video_input, sp[0].weight, sp[0].bias, "relu")
+        # the autograd node that runs LAST in this encoder's backward: the data-parallel trainer hangs its early
+        # gradient exchange on it (trainer._forward_backward)
+        self.__dict__["_first_bwd_node"] = p.grad_fn
         p = ops.dropout(p, self.dropout, self.training)
         if video_input.shape[1] > 1:
             h = ops.conv1d_k3(p, cnn[0].weight, cnn[0].bias)
