@@ -47,6 +47,9 @@ int deer_version(void);
 const char* deer_last_error(void);
 /* number of kernels launched by this library since process start (bench.py `gpu_launches`) */
 long long deer_launch_count(void);
+/* timeline probe: a one-thread kernel that writes %globaltimer (ns) to slots[index] when the stream reaches it; capturable
+ * into CUDA graphs, so the phases of a replayed step can be timed on every stream (tools/step_timeline.py) */
+int deer_timestamp(unsigned long long* slots, int index, void* stream);
 /* process-wide tuning switches (testing / ablation) */
 #define DEER_OPT_TMA_TF32_ROUND 1 /* 1 (default): TMA loads fp32 operands as TFLOAT32 (rounded); 0: raw fp32 bits */
 #define DEER_OPT_LSTM_TS 2        /* 1 (default): resident recurrent weights in TMEM (tcgen05.mma A from TMEM); 0: in smem */

@@ -22,6 +22,7 @@ _PROTOS = {
     "deer_version": [],
     "deer_last_error": [],
     "deer_launch_count": [],
+    "deer_timestamp": [P, I, P],
     "deer_set_option": [I, I],
     "deer_lstm_set_profile_buffer": [P],
     "deer_gemm": [P, L, I, P, L, I, P, L, I, I, I, P, I, F, I, L, L, L, L, I, P],

@@ -45,11 +45,25 @@ bool gemm_tcgen05_supported(const float* A, long long lda, int transA, const flo
 
 using namespace deer;
 
+namespace deer {
+__global__ void timestamp_kernel(unsigned long long* slots, int index) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  slots[index] = t;
+}
+}  // namespace deer
+
 extern "C" {
 
 int deer_version(void) { return 100; }
 const char* deer_last_error(void) { return g_err; }
 long long deer_launch_count(void) { return g_launches.load(); }
+
+int deer_timestamp(unsigned long long* slots, int index, void* stream) {
+  DEER_CHECK_ARG(slots && index >= 0, "timestamp: bad args");
+  DEER_LAUNCH(timestamp_kernel, 1, 1, 0, stream, slots, index);
+  return DEER_OK;
+}
 
 int deer_lstm_set_profile_buffer(long long* device_buf) {
   lstm_cluster_set_profile(device_buf);

@@ -53,6 +53,64 @@ def join_wgrad_stream():
         _wgrad["pending"] = False
 
 
+_timeline = {"buf": None, "names": []}
+
+
+def timeline_begin(device) -> None:
+    """Debug aid (tools/step_timeline.py): from now on `mark(name)` launches a timestamp kernel on the current stream."""
+    _timeline["buf"] = torch.zeros(256, dtype=torch.int64, device=device)
+    _timeline["names"] = []
+
+
+def timeline_end():
+    """-> [(name, ns)] of the marks reached by the last run (after a synchronize), and stop marking."""
+    buf, names = _timeline["buf"], _timeline["names"]
+    _timeline["buf"] = None
+    if buf is None:
+        return []
+    vals = buf.cpu().tolist()
+    return [(n, vals[i]) for i, n in enumerate(names)]
+
+
+def timeline_read():
+    buf, names = _timeline["buf"], _timeline["names"]
+    vals = buf.cpu().tolist()
+    return [(n, vals[i]) for i, n in enumerate(names)]
+
+
+def mark(name: str) -> None:
+    """No-op unless a timeline is being recorded."""
+    buf = _timeline["buf"]
+    if buf is None:
+        return
+    names = _timeline["names"]
+    if name in names:
+        idx = names.index(name)
+    else:
+        idx = len(names)
+        names.append(name)
+    call("deer_timestamp", buf.data_ptr(), idx)
+
+
+class _Mark(torch.autograd.Function):
+    """Identity whose forward and backward each drop a timeline mark on their stream."""
+
+    @staticmethod
+    def forward(ctx, x, name):
+        ctx.name = name
+        mark(name + ":fwd")
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        mark(ctx.name + ":bwd")
+        return g, None
+
+
+def mark_tensor(x, name: str):
+    return _Mark.apply(x, name) if _timeline["buf"] is not None else x
+
+
 def set_lstm_pre16(on: bool):
     """FP16 (default) or fp32 pre-activations between the LSTM input projection and the recurrence kernel."""
     _state["lstm_pre16"] = bool(on)

@@ -56,12 +56,15 @@ class SequenceDEERModel(nn.Module):
             main = torch.cuda.current_stream()
             side = self._branch_stream()
             side.wait_stream(main)
+            ops.mark("step_start")
             with torch.cuda.stream(side):
-                a = self.audio_encoder(audio)
-            v = self.video_encoder(video)
-            t = self.text_encoder(text, attention_mask, linguistic_features)
+                a = ops.mark_tensor(self.audio_encoder(ops.mark_tensor(audio, "audio_in")), "audio_out")
+            v = ops.mark_tensor(self.video_encoder(ops.mark_tensor(video, "video_in")), "video_out")
+            t = ops.mark_tensor(self.text_encoder(ops.mark_tensor(text, "text_in"), attention_mask,
+                                                  linguistic_features), "text_out")
             main.wait_stream(side)
             a.record_stream(main)
+            ops.mark("joined")
         else:
             a = self.audio_encoder(audio)
             v = self.video_encoder(video)
