@@ -151,6 +151,7 @@ def main():
     ap.add_argument("--branch-max-batch", type=int, default=None)
     ap.add_argument("--tf32-pair", type=int, default=None, help="DEER_OPT_TF32_PAIR override (ablation)")
     ap.add_argument("--lstm-dual", type=int, default=None, help="DEER_OPT_LSTM_DUAL override (ablation)")
+    ap.add_argument("--lstm-tile", type=int, default=None, help="DEER_OPT_LSTM_TILE override (ablation)")
     ap.add_argument("--no-defer-wgrad", action="store_true",
                     help="ablation: small-layer weight gradients on the main stream")
     args = ap.parse_args()
@@ -180,6 +181,8 @@ def main():
         ops.set_branch_max_batch(args.branch_max_batch)
     if args.lstm_dual is not None:
         _lib.set_option(9, args.lstm_dual)
+    if args.lstm_tile is not None:
+        _lib.set_option(3, args.lstm_tile)
     if args.tf32_pair is not None:
         _lib.set_option(6, args.tf32_pair)
         if not args.tf32_pair:

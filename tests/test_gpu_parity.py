@@ -679,3 +679,34 @@ def test_lstm_fp16_handoff_between_layers_is_exact():
         grads.append([xi.grad.clone()] + [p.grad.clone() for p in enc.lstm.parameters()])
     for a, b in zip(*grads):      # atomically accumulated bias gradients: equal up to summation order
         assert_close(a, b, 1e-5, "lstm gradients")
+
+
+@pytest.mark.parametrize("B,D", [(300001, 3), (70001, 1), (1000, 2)])
+def test_fused_loss_pipelined_and_plain_trips_agree(B, D):
+    """Several grid-stride trips per thread (software-pipelined loads, DEER_OPT_NIG_PIPELINE, default) against the plain
+    load -> compute trips and against the fp64 oracle on the loss value: element pairs, odd tails, D = 1 / 2 / 3."""
+    from deer_b200 import _lib
+    g = torch.Generator().manual_seed(B + D)
+    e = torch.randn(B, D, 4, generator=g, dtype=torch.float64) * 2.0
+    e[:, :, 2] = e[:, :, 2].clamp(min=-5.0)
+    y = torch.tanh(torch.randn(B, D, generator=g, dtype=torch.float64))
+    res = []
+    try:
+        for pipe in (1, 0):
+            _lib.set_option(8, pipe)
+            losses, dE, nig, _ = ops.nig_loss_raw(cu(e), None, cu(y), want_nig=True, want_grad=True)
+            torch.cuda.synchronize()
+            res.append((losses.clone(), dE.clone(), nig.clone()))
+    finally:
+        _lib.set_option(8, 1)
+    (l1, d1, n1), (l0, d0, n0) = res
+    assert_close(l1, l0, 1e-5, "losses")          # statistics are accumulated with atomics: equal up to summation order
+    assert_close(d1, d0, 1e-5, "gradient")
+    assert torch.equal(n1, n0)                    # the head outputs are per-element: bit-identical
+    if D == 3:
+        pred = {}
+        for i, dname in enumerate(("valence", "arousal", "dominance")):
+            for k, v in O.nig_from_evidence(e[:, i:i + 1, :]).items():
+                pred[f"{dname}_{k}"] = v
+        ref = float(O.multitask_deer_loss(pred, y)["total_loss"])
+        assert abs(float(l1[-1]) - ref) <= TOL * abs(ref)
