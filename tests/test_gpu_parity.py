@@ -710,3 +710,45 @@ def test_fused_loss_pipelined_and_plain_trips_agree(B, D):
                 pred[f"{dname}_{k}"] = v
         ref = float(O.multitask_deer_loss(pred, y)["total_loss"])
         assert abs(float(l1[-1]) - ref) <= TOL * abs(ref)
+
+
+@pytest.mark.parametrize("time_major,masked", [(True, False), (False, False), (False, True)])
+def test_fused_scorer_pool_matches_separate_nodes(time_major, masked):
+    """ops.scorer_pool (one autograd node; the scorer's dx GEMM accumulates onto the pooling kernel's dx) against the
+    separate Linear-tanh / rowdot / attn_pool nodes whose input gradients autograd adds: same output and gradients."""
+    g = torch.Generator().manual_seed(5)
+    B, T, D, Hd = 37, 21, 64, 32
+    x0 = torch.randn((T, B, D) if time_major else (B, T, D), generator=g)
+    w1, b1 = torch.randn(Hd, D, generator=g) * 0.2, torch.randn(Hd, generator=g) * 0.1
+    w2, b2 = torch.randn(1, Hd, generator=g) * 0.3, torch.randn(1, generator=g)
+    mask = (torch.rand(B, T, generator=g) > 0.3).float() if masked else None
+    if masked:
+        mask[:, 0] = 1.0
+    pr = torch.randn(B, D, generator=g)
+    res = []
+    for fused in (True, False):
+        xs = cu(x0).requires_grad_(True)
+        ps = [cu(t).requires_grad_(True) for t in (w1, b1, w2, b2)]
+        m = None if mask is None else cu(mask)
+        if fused:
+            out, wts = ops.scorer_pool(xs, *ps, m, time_major)
+        else:
+            hidden = ops.linear(xs, ps[0], ps[1], "tanh")
+            s = ops.rowdot(hidden, ps[2].view(-1), ps[3])
+            out, wts = ops.attn_pool(xs.permute(1, 0, 2), s.permute(1, 0), m) if time_major else ops.attn_pool(xs, s, m)
+        (out * cu(pr)).sum().backward()
+        res.append([out.detach(), wts.detach(), xs.grad] + [p.grad for p in ps])
+    for a, b in zip(*res):
+        assert_close(a, b, 1e-5, "fused vs separate")
+    # and against torch fp64
+    xd = x0.double().requires_grad_(True)
+    xb = xd.permute(1, 0, 2) if time_major else xd
+    sc = torch.tanh(xb @ w1.double().t() + b1.double()) @ w2.double().view(-1) + b2.double()
+    p = torch.softmax(sc, dim=1)
+    if masked:
+        p = p * mask.double()
+        p = p / (p.sum(dim=1, keepdim=True) + 1e-10)
+    ref = (p.unsqueeze(-1) * xb).sum(dim=1)
+    (ref * pr.double()).sum().backward()
+    assert_close(res[0][0], ref, 1e-4, "pooled vs fp64")
+    assert_close(res[0][2], xd.grad, 1e-3, "dx vs fp64")

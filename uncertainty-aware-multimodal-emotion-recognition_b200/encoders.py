@@ -40,6 +40,17 @@ def _scorer_pool(x_bt, x_rows, att: nn.Sequential, mask=None):
     return hidden, s
 
 
+def _scorer_and_pool(x, att: nn.Sequential, mask=None, time_major=False):
+    """Scorer + softmax-over-time pooling of x ([T,B,D] when time_major, else [B,T,D]) as one autograd node
+    (ops.scorer_pool), or as the separate scorer / pooling ops when fusion is switched off."""
+    if ops.scorer_pool_fused():
+        return ops.scorer_pool(x, att[0].weight, att[0].bias, att[2].weight, att[2].bias, mask, time_major)
+    _, s = _scorer_pool(None, x, att)
+    if time_major:
+        return ops.attn_pool(x.permute(1, 0, 2), s.permute(1, 0), mask)
+    return ops.attn_pool(x, s, mask)
+
+
 class EnhancedAudioEncoder(nn.Module):
     def __init__(self, config: Optional[Dict] = None):
         super().__init__()
@@ -88,8 +99,7 @@ class EnhancedAudioEncoder(nn.Module):
         if audio_input.dim() == 2:
             audio_input = audio_input.unsqueeze(1)
         h_tm = self.lstm_forward(audio_input)                      # [T,B,D]
-        _, s_tm = _scorer_pool(None, h_tm, self.attention)         # [T,B]
-        pooled, _ = ops.attn_pool(h_tm.permute(1, 0, 2), s_tm.permute(1, 0))
+        pooled, _ = _scorer_and_pool(h_tm, self.attention, time_major=True)
         op = self.output_projection
         y = ops.linear(pooled, op[0].weight, op[0].bias, "relu")
         y = ops.dropout(y, self.dropout, self.training)
@@ -137,8 +147,7 @@ class EnhancedVideoEncoder(nn.Module):
             h = ops.dropout(h, self.dropout, self.training)
             h = ops.conv1d_k3(h, cnn[4].weight, cnn[4].bias)
             h = self._bn_relu(h, cnn[5])
-            _, s = _scorer_pool(None, h, self.temporal_attention)
-            pooled, _ = ops.attn_pool(h, s)
+            pooled, _ = _scorer_and_pool(h, self.temporal_attention)
         else:
             pooled = p[:, 0]
         op = self.output_projection
@@ -188,8 +197,7 @@ class EnhancedTextEncoder(nn.Module):
         if linguistic_features is None:
             linguistic_features = torch.zeros((B, 10), device=dev, dtype=torch.float32)
         x = ops.rowscale(token_embeddings, m)
-        _, s = _scorer_pool(None, x, self.token_attention)
-        agg, _ = ops.attn_pool(x, s, m)
+        agg, _ = _scorer_and_pool(x, self.token_attention, mask=m)
         bp, lp, op = self.bert_projection, self.linguistic_projection, self.output_projection
         pb = ops.dropout(ops.linear(agg, bp[0].weight, bp[0].bias, "relu"), self.dropout, self.training)
         pl = ops.dropout(ops.linear(linguistic_features, lp[0].weight, lp[0].bias, "relu"), self.dropout, self.training)

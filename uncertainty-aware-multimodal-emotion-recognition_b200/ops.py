@@ -26,7 +26,7 @@ ENGINE_AUTO, ENGINE_SIMT, ENGINE_TF32 = 0, 1, 2
 _state = {"engine": ENGINE_AUTO, "lstm_engine": ENGINE_AUTO, "exact_small_fwd": True, "exact_small_bwd": True,
           "small_rows": 8192, "direct_grad": False, "lstm_gemm16": True, "fuse_lstm_dropout": True,
           "branch_streams": True, "lstm_pre16": True, "defer_wgrad": True,
-          "branch_max_batch": 512}
+          "branch_max_batch": 512, "scorer_pool_fused": True}
 
 
 def set_defer_wgrad(on: bool):
@@ -466,6 +466,78 @@ class _AttnPool(torch.autograd.Function):
 
 def attn_pool(x, s, mask=None):
     return _AttnPool.apply(x, s, mask)
+
+
+class _ScorerPool(torch.autograd.Function):
+    """Attention pooling with its Linear-Tanh-Linear scorer as ONE autograd node (encoders.py:93-98,383-384; :462-467,
+    543-544; :597-602,738-746):  s = w2 . tanh(x W1^T + b1) + b2;  p = softmax_t(s) [masked, renormalised];
+    out[b] = sum_t p[b,t] x[b,t].  x [R0,R1,D] contiguous enumerates (t,b) (time_major) or (b,t).
+    x feeds both the scorer and the weighted sum; as two nodes autograd materialised both input gradients and added
+    them with a separate kernel (157 MB at the audio encoder).  Here the pooling backward writes dx and the scorer's
+    input-gradient GEMM accumulates onto it (beta = 1)."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, mask, time_major):
+        x = _req(x, "x").contiguous()
+        R0, R1, D = x.shape
+        M = R0 * R1
+        Hd = w1.shape[0]
+        dev = x.device
+        B, T = (R1, R0) if time_major else (R0, R1)
+        xs_b, xs_t = (D, B * D) if time_major else (T * D, D)
+        ss_b, ss_t = (1, B) if time_major else (T, 1)
+        hidden = torch.empty((M, Hd), device=dev, dtype=torch.float32)
+        gemm(x, D, 0, w1, w1.stride(0), 1, hidden, Hd, M, Hd, D, bias=b1, act=ACT["tanh"], engine=_fwd_engine(M))
+        sc = torch.empty(M, device=dev, dtype=torch.float32)
+        w2v = w2.reshape(-1)
+        call("deer_rowdot_fwd", ptr(hidden), ptr(w2v), ptr(b2), ptr(sc), M, Hd)
+        m = None if mask is None else _req(mask, "mask").contiguous()
+        out = torch.empty((B, D), device=dev, dtype=torch.float32)
+        wts = torch.empty((B, T), device=dev, dtype=torch.float32)
+        call("deer_attn_pool_fwd", ptr(x), xs_b, xs_t, ptr(sc), ss_b, ss_t, ptr(m), ptr(out), ptr(wts), B, T, D)
+        ctx.save_for_backward(x, hidden, sc, m, wts, w1, w2v)
+        ctx.geom = (B, T, D, M, Hd, xs_b, xs_t, ss_b, ss_t)
+        ctx.params = (w1, b1, w2, b2)
+        ctx.mark_non_differentiable(wts)
+        return out, wts
+
+    @staticmethod
+    def backward(ctx, dout, _dw):
+        x, hidden, sc, m, wts, w1, w2v = ctx.saved_tensors
+        B, T, D, M, Hd, xs_b, xs_t, ss_b, ss_t = ctx.geom
+        dev = x.device
+        pw1, pb1, pw2, pb2 = ctx.params
+        need_dx = ctx.needs_input_grad[0]
+        dx = torch.empty_like(x)               # the pooling kernel always writes it; dropped when x needs no gradient
+        ds = torch.empty(M, device=dev, dtype=torch.float32)
+        call("deer_attn_pool_bwd", ptr(dout.contiguous()), ptr(x), xs_b, xs_t, ptr(sc), ss_b, ss_t, ptr(m), ptr(wts),
+             ptr(dx), ptr(ds), B, T, D, 0)
+        dh = torch.empty_like(hidden)
+        dw2, dw2_direct = _acc(pw2, like=w2v)
+        db2, db2_direct = _acc(pb2)
+        call("deer_rowdot_bwd", ptr(ds), ptr(hidden), ptr(w2v), ptr(dh), ptr(dw2), ptr(db2), M, Hd)
+        db1, db1_direct = _acc(pb1)
+        call("deer_bias_act_bwd", ptr(dh), Hd, ptr(hidden), Hd, ptr(dh), Hd, ptr(db1), M, Hd, ACT["tanh"])   # in place
+        if need_dx:
+            gemm(dh, Hd, 0, w1, w1.stride(0), 0, dx, D, M, D, Hd, beta=1.0, engine=_bwd_engine(M))
+        dw1, dw1_direct = _acc(pw1)
+        gemm(dh, Hd, 1, x, D, 0, dw1, D, Hd, D, M, beta=1.0, engine=_bwd_engine(M))
+        return (dx if need_dx else None, None if dw1_direct else dw1, None if db1_direct else db1,
+                None if dw2_direct else dw2.view_as(pw2), None if db2_direct else db2, None, None)
+
+
+def set_scorer_pool_fused(on: bool):
+    """Scorer + attention pooling as one autograd node (default) or as separate Linear / rowdot / pooling nodes."""
+    _state["scorer_pool_fused"] = bool(on)
+
+
+def scorer_pool_fused() -> bool:
+    return _state["scorer_pool_fused"]
+
+
+def scorer_pool(x, w1, b1, w2, b2, mask=None, time_major=False):
+    """(pooled [B,D], attention weights [B,T]) of x [T,B,D] (time_major) or [B,T,D]; see _ScorerPool."""
+    return _ScorerPool.apply(x, w1, b1, w2, b2, mask, bool(time_major))
 
 
 class _RowScale(torch.autograd.Function):
