@@ -208,6 +208,16 @@ int deer_lstm_cluster_fwd_pre16(const void* pre_il_f16, const float* w_hh_fwd, c
 int deer_lstm_cluster_bwd(const float* gact, const float* c_blk, const float* dh_out, const float* w_hh_fwd,
                           const float* w_hh_rev, float* dpre_il, float* db_il, void* dpre_bf16, int T, int B, int H,
                           void* stream);
+/*      one-pass operand preparation of an LSTM layer for the cluster kernels + 16-bit GEMM: W_ih of both directions
+ *      (nn.LSTM order, fp32 [4H,In]) -> gate-interleaved FP16/BF16 [2*4H, Kp] (Kp >= In even, zero-padded), and (b_il may
+ *      be NULL) b_ih + b_hh -> gate-interleaved fp32 [2*4H];  and the reverse for the gradients: gate-interleaved
+ *      dW_ih [2,4H,In], dW_hh [2,4H,H], db [2,4H] accumulated (+=) into the eight natural-order targets. */
+int deer_lstm_prep(const float* w_ih_fwd, const float* w_ih_rev, const float* b_ih_fwd, const float* b_hh_fwd,
+                   const float* b_ih_rev, const float* b_hh_rev, void* w16, float* b_il, int H, int In, int Kp, int bf16,
+                   void* stream);
+int deer_lstm_unprep(const float* dwi_il, const float* dwh_il, const float* db_il, float* dw_ih_fwd, float* dw_ih_rev,
+                     float* dw_hh_fwd, float* dw_hh_rev, float* db_ih_fwd, float* db_hh_fwd, float* db_ih_rev,
+                     float* db_hh_rev, int H, int In, void* stream);
 /*      rows g*H+u of src [4H,K] -> rows 4u+g of dst (inverse=0) or back (inverse=1); accumulate!=0 adds into dst */
 int deer_gate_rows_interleave(const float* src, float* dst, int H, int K, int inverse, int accumulate, void* stream);
 

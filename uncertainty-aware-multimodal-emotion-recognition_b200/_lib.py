@@ -54,6 +54,8 @@ _PROTOS = {
     "deer_lstm_bwd": [P, P, P, P, P, P, P, I, I, I, I, P],
     "deer_lstm_cluster_tile": [I],
     "deer_lstm_cluster_fwd": [P, P, P, P, P, P, P, P, I, I, I, P],
+    "deer_lstm_prep": [P, P, P, P, P, P, P, P, I, I, I, I, P],
+    "deer_lstm_unprep": [P, P, P, P, P, P, P, P, P, P, P, I, I, P],
     "deer_lstm_cluster_fwd_pre16": [P, P, P, P, P, P, P, P, I, I, I, P],
     "deer_lstm_cluster_bwd": [P, P, P, P, P, P, P, P, I, I, I, P],
     "deer_gate_rows_interleave": [P, P, I, I, I, I, P],

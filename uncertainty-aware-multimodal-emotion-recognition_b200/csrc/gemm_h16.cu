@@ -938,6 +938,80 @@ __global__ void __launch_bounds__(256) cast16_kernel(const float* __restrict__ s
 
 using namespace deer;
 
+namespace deer {
+// LSTM layer operands in one pass: W_ih of both directions (nn.LSTM row order g*H+u, fp32 [4H,In]) -> gate-interleaved
+// (row 4u+g) 16-bit [2*4H, Kp] (columns >= In zero-filled), and b_ih + b_hh -> gate-interleaved fp32 [2*4H].
+// Replaces 2 row permutations + 2 bias sums + 2 bias permutations + 1 cast (7 launches at the head of every layer).
+__global__ void __launch_bounds__(256) lstm_prep_kernel(const float* __restrict__ w_f, const float* __restrict__ w_r,
+                                                        const float* __restrict__ bi_f, const float* __restrict__ bh_f,
+                                                        const float* __restrict__ bi_r, const float* __restrict__ bh_r,
+                                                        uint16_t* __restrict__ w16, float* __restrict__ b_il, int H, int In,
+                                                        int Kp, int bf) {
+  DEER_PDL_ENTRY();
+  const int G = 4 * H;
+  const long long per_row = Kp / 2;
+  const long long total = 2LL * G * per_row;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int ro = (int)(i / per_row);            // output row: d*G + 4u + g
+    const int c = (int)(i % per_row) * 2;
+    const int d = ro / G, rr = ro % G;
+    const int srow = (rr & 3) * H + (rr >> 2);    // g*H + u
+    const float* w = d ? w_r : w_f;
+    const float a = c < In ? w[(long long)srow * In + c] : 0.f;
+    const float b = c + 1 < In ? w[(long long)srow * In + c + 1] : 0.f;
+    uint32_t v;
+    if (bf) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+      v = *reinterpret_cast<uint32_t*>(&h);
+    } else {
+      __half2 h = __floats2half2_rn(a, b);
+      v = *reinterpret_cast<uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint32_t*>(w16 + (long long)ro * Kp + c) = v;
+    if (b_il != nullptr && c == 0) b_il[ro] = (d ? bi_r : bi_f)[srow] + (d ? bh_r : bh_f)[srow];
+  }
+}
+// The reverse for the gradients: gate-interleaved dW_ih [2,4H,In], dW_hh [2,4H,H], db [2,4H] ACCUMULATED into the
+// natural-order targets of both directions (8 launches at the tail of every layer's backward -> 1).
+struct LstmGradTargets {
+  float* dwi[2];
+  float* dwh[2];
+  float* dbi[2];
+  float* dbh[2];
+};
+__global__ void __launch_bounds__(256) lstm_unprep_kernel(const float* __restrict__ dwi_il, const float* __restrict__ dwh_il,
+                                                          const float* __restrict__ db_il, const LstmGradTargets tg, int H,
+                                                          int In) {
+  DEER_PDL_ENTRY();
+  const int G = 4 * H;
+  const long long n_wi = 2LL * G * In, n_wh = 2LL * G * H, n_b = 2LL * G;
+  const long long total = n_wi + n_wh + n_b;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    if (i < n_wi) {
+      const int k = (int)(i % In);
+      const int ro = (int)(i / In);
+      const int d = ro / G, rr = ro % G;
+      tg.dwi[d][(long long)((rr & 3) * H + (rr >> 2)) * In + k] += dwi_il[i];
+    } else if (i < n_wi + n_wh) {
+      const long long j = i - n_wi;
+      const int k = (int)(j % H);
+      const int ro = (int)(j / H);
+      const int d = ro / G, rr = ro % G;
+      tg.dwh[d][(long long)((rr & 3) * H + (rr >> 2)) * H + k] += dwh_il[j];
+    } else {
+      const int ro = (int)(i - n_wi - n_wh);
+      const int d = ro / G, rr = ro % G;
+      const int srow = (rr & 3) * H + (rr >> 2);
+      const float v = db_il[ro];
+      tg.dbi[d][srow] += v;     // b_ih and b_hh receive the same gradient
+      tg.dbh[d][srow] += v;
+    }
+  }
+}
+}  // namespace deer
+
 extern "C" {
 
 int deer_gemm_h16(const void* A, long long lda, int transA, int a_bf16, const void* B, long long ldb, int transB,
@@ -969,6 +1043,32 @@ int deer_cast16(const float* src, long long ld_src, void* dst, long long ld_dst,
   if (g > kNumSMs * 16) g = kNumSMs * 16;
   DEER_LAUNCH(cast16_kernel, (unsigned)g, 256, 0, stream, src, ld_src, reinterpret_cast<uint16_t*>(dst), ld_dst, rows, cols,
               cols_pad, bf16);
+  return DEER_OK;
+}
+
+int deer_lstm_prep(const float* w_ih_fwd, const float* w_ih_rev, const float* b_ih_fwd, const float* b_hh_fwd,
+                   const float* b_ih_rev, const float* b_hh_rev, void* w16, float* b_il, int H, int In, int Kp, int bf16,
+                   void* stream) {
+  DEER_CHECK_ARG(w_ih_fwd && w_ih_rev && w16 && H > 0 && In > 0 && Kp >= In && (Kp & 1) == 0, "lstm_prep: bad args");
+  DEER_CHECK_ARG(b_il == nullptr || (b_ih_fwd && b_hh_fwd && b_ih_rev && b_hh_rev), "lstm_prep: biases");
+  long long g = cdiv(2LL * 4 * H * (Kp / 2), 256);
+  if (g > kNumSMs * 8) g = kNumSMs * 8;
+  DEER_LAUNCH(lstm_prep_kernel, (unsigned)g, 256, 0, stream, w_ih_fwd, w_ih_rev, b_ih_fwd, b_hh_fwd, b_ih_rev, b_hh_rev,
+              reinterpret_cast<uint16_t*>(w16), b_il, H, In, Kp, bf16);
+  return DEER_OK;
+}
+
+int deer_lstm_unprep(const float* dwi_il, const float* dwh_il, const float* db_il, float* dw_ih_fwd, float* dw_ih_rev,
+                     float* dw_hh_fwd, float* dw_hh_rev, float* db_ih_fwd, float* db_hh_fwd, float* db_ih_rev,
+                     float* db_hh_rev, int H, int In, void* stream) {
+  DEER_CHECK_ARG(dwi_il && dwh_il && db_il && dw_ih_fwd && dw_ih_rev && dw_hh_fwd && dw_hh_rev && db_ih_fwd &&
+                     db_hh_fwd && db_ih_rev && db_hh_rev && H > 0 && In > 0,
+                 "lstm_unprep: bad args");
+  DEER_CHECK_ARG(db_ih_fwd != db_hh_fwd && db_ih_rev != db_hh_rev, "lstm_unprep: b_ih and b_hh targets must differ");
+  LstmGradTargets tg{{dw_ih_fwd, dw_ih_rev}, {dw_hh_fwd, dw_hh_rev}, {db_ih_fwd, db_ih_rev}, {db_hh_fwd, db_hh_rev}};
+  long long g = cdiv(2LL * 4 * H * (In + H + 1), 256);
+  if (g > kNumSMs * 8) g = kNumSMs * 8;
+  DEER_LAUNCH(lstm_unprep_kernel, (unsigned)g, 256, 0, stream, dwi_il, dwh_il, db_il, tg, H, In);
   return DEER_OK;
 }
 

@@ -717,13 +717,22 @@ class _BiLSTMLayerCluster(torch.autograd.Function):
         dev = x.device
         keep = grad_mode and any(ctx.needs_input_grad)   # needs_input_grad ignores no_grad(): the caller's mode
         use16 = _state["lstm_gemm16"] and _state["engine"] == ENGINE_AUTO   # a forced engine (tests) is respected
-        wi_il = torch.empty((2, G, In), device=dev, dtype=torch.float32)
         b_il = torch.empty((2, G), device=dev, dtype=torch.float32)
-        bsum = torch.empty(G, device=dev, dtype=torch.float32)
-        for d, (wi, bi, bh) in enumerate(((wif, bif, bhf), (wir, bir, bhr))):
-            call("deer_gate_rows_interleave", ptr(wi.contiguous()), ptr(wi_il[d]), H, In, 0, 0)
-            call("deer_axpby", ptr(bi), ptr(bh), ptr(bsum), G, 1.0, 1.0)
-            call("deer_gate_rows_interleave", ptr(bsum), ptr(b_il[d]), H, 1, 0, 0)
+        w16 = None
+        if use16:
+            # one pass: both directions' W_ih -> gate-interleaved FP16 [2G, Kp], b_ih + b_hh -> gate-interleaved [2G]
+            Kp = (In + 7) // 8 * 8
+            w16 = torch.empty((2 * G, Kp), device=dev, dtype=torch.float16)
+            call("deer_lstm_prep", ptr(wif.contiguous()), ptr(wir.contiguous()), ptr(bif), ptr(bhf), ptr(bir), ptr(bhr),
+                 w16.data_ptr(), ptr(b_il), H, In, Kp, 0)
+            wi_il = torch.empty(0, device=dev, dtype=torch.float32)
+        else:
+            wi_il = torch.empty((2, G, In), device=dev, dtype=torch.float32)
+            bsum = torch.empty(G, device=dev, dtype=torch.float32)
+            for d, (wi, bi, bh) in enumerate(((wif, bif, bhf), (wir, bir, bhr))):
+                call("deer_gate_rows_interleave", ptr(wi.contiguous()), ptr(wi_il[d]), H, In, 0, 0)
+                call("deer_axpby", ptr(bi), ptr(bh), ptr(bsum), G, 1.0, 1.0)
+                call("deer_gate_rows_interleave", ptr(bsum), ptr(b_il[d]), H, 1, 0, 0)
         M = T * B
         # FP16 pre-activations (16-bit GEMM epilogue -> LSTM kernel): the projection is bound by its output stream, and
         # the rounding (2^-12 relative, once) is of the order of what the FP16 operands already contribute
@@ -744,8 +753,7 @@ class _BiLSTMLayerCluster(torch.autograd.Function):
                 x16 = x16_in.view(M, In)                      # the producer kernel's FP16 shadow: no cast pass
             else:
                 x16 = cast16(x)                               # [M, Kp] fp16
-            Kp = x16.shape[1]
-            w16 = cast16(wi_il.view(2 * G, In))               # [2G, Kp] fp16
+            assert x16.shape[1] == Kp
             # both directions in ONE contraction: pre[M, 2G] = x16 [M, Kp] . w16[2G, Kp]^T (full 8 KB output rows)
             if pre16:
                 gemm_h16(x16, Kp, 0, w16, Kp, 1, None, 0, M, 2 * G, In, bias=b_il.view(-1), C16=pre, ldc16=2 * G)
@@ -807,7 +815,10 @@ class _BiLSTMLayerCluster(torch.autograd.Function):
                 xb16 = cast16(x, bf16=True)                    # [M, Kp] bf16: B operand of dW_ih (MN-major)
             Kp = xb16.shape[1]
             if ctx.needs_input_grad[0]:
-                wb16 = cast16(wi_il.view(2 * G, In), bf16=True)   # [2G, Kp] bf16: B operand of dx (MN-major [K=G, N=In])
+                # [2G, Kp] bf16 gate-interleaved W_ih of both directions: B operand of dx (MN-major [K=G, N=In])
+                wb16 = torch.empty((2 * G, Kp), device=dev, dtype=torch.bfloat16)
+                call("deer_lstm_prep", ptr(ctx.params[0].contiguous()), ptr(ctx.params[4].contiguous()), None, None, None,
+                     None, wb16.data_ptr(), None, H, In, Kp, 1)
                 dx = torch.empty((T, B, In), device=dev, dtype=torch.float32)
                 # dx = dpre16 [M, 2G] . wb16 [2G, In]: the sum over the two directions is the K = 2G contraction itself
                 gemm_h16(dpre16, 2 * G, 0, wb16, Kp, 0, dx, In, M, In, 2 * G, a_bf16=True, b_bf16=True, beta=0.0)
@@ -826,27 +837,31 @@ class _BiLSTMLayerCluster(torch.autograd.Function):
             # dW_ih of both directions at once: [2G, In] = dpre16 [M, 2G]^T . xb16 [M, In]
             dwi_il2 = torch.zeros((2, G, In), device=dev, dtype=torch.float32)
             gemm_h16(dpre16, 2 * G, 1, xb16, Kp, 0, dwi_il2, In, 2 * G, In, M, a_bf16=True, b_bf16=True, beta=1.0)
+        if use16:
+            dwh_il2 = torch.zeros((2, G, H), device=dev, dtype=torch.float32)
+            Mr = (T - 1) * B
+            if T > 1:
+                # rows t=1.. of the forward direction pair with h[t-1]; rows ..T-2 of the reverse one with h[t+1]
+                gemm_h16(dpre16.data_ptr() + 2 * B * 2 * G, 2 * G, 1, hb16.data_ptr(), 2 * H, 0, dwh_il2[0], H, G, H, Mr,
+                         a_bf16=True, b_bf16=True, beta=1.0)
+                gemm_h16(dpre16.data_ptr() + 2 * G, 2 * G, 1, hb16.data_ptr() + 2 * (B * 2 * H + H), 2 * H, 0,
+                         dwh_il2[1], H, G, H, Mr, a_bf16=True, b_bf16=True, beta=1.0)
+            tg = [_acc(P[i]) for i in (0, 4, 1, 5, 2, 3, 6, 7)]   # dW_ih f/r, dW_hh f/r, db_ih f, db_hh f, db_ih r, db_hh r
+            # one pass: every gate-interleaved gradient of the layer accumulated into its nn.LSTM-order target
+            call("deer_lstm_unprep", ptr(dwi_il2), ptr(dwh_il2), ptr(db_il), *[ptr(t[0]) for t in tg], H, In)
+            r = [None if direct else buf for buf, direct in tg]
+            return dx, r[0], r[2], r[4], r[5], r[1], r[3], r[6], r[7], None, None, None, None
         for d in range(2):
-            gp = None if use16 else dpre.data_ptr() + 4 * G * d
-            dwi_il = dwi_il2[d] if use16 else torch.zeros((G, In), device=dev, dtype=torch.float32)
+            gp = dpre.data_ptr() + 4 * G * d
+            dwi_il = torch.zeros((G, In), device=dev, dtype=torch.float32)
             dwh_il = torch.zeros((G, H), device=dev, dtype=torch.float32)
             Mr = (T - 1) * B
-            if use16:
-                gp16 = dpre16.data_ptr() + 2 * G * d
-                if T > 1:
-                    if d == 0:   # rows t=1.. pair with h[t-1]
-                        gemm_h16(gp16 + 2 * B * 2 * G, 2 * G, 1, hb16.data_ptr(), 2 * H, 0, dwh_il, H, G, H, Mr,
-                                 a_bf16=True, b_bf16=True, beta=1.0)
-                    else:        # rows t=..T-2 pair with h[t+1]
-                        gemm_h16(gp16, 2 * G, 1, hb16.data_ptr() + 2 * (B * 2 * H + H), 2 * H, 0, dwh_il, H, G, H, Mr,
-                                 a_bf16=True, b_bf16=True, beta=1.0)
-            else:
-                gemm(gp, 2 * G, 1, x, In, 0, dwi_il, In, G, In, M, beta=1.0)
-                if T > 1:
-                    if d == 0:
-                        gemm(gp + 4 * B * 2 * G, 2 * G, 1, h.data_ptr(), 2 * H, 0, dwh_il, H, G, H, Mr, beta=1.0)
-                    else:
-                        gemm(gp, 2 * G, 1, h.data_ptr() + 4 * (B * 2 * H + H), 2 * H, 0, dwh_il, H, G, H, Mr, beta=1.0)
+            gemm(gp, 2 * G, 1, x, In, 0, dwi_il, In, G, In, M, beta=1.0)
+            if T > 1:
+                if d == 0:   # rows t=1.. pair with h[t-1]
+                    gemm(gp + 4 * B * 2 * G, 2 * G, 1, h.data_ptr(), 2 * H, 0, dwh_il, H, G, H, Mr, beta=1.0)
+                else:        # rows t=..T-2 pair with h[t+1]
+                    gemm(gp, 2 * G, 1, h.data_ptr() + 4 * (B * 2 * H + H), 2 * H, 0, dwh_il, H, G, H, Mr, beta=1.0)
             dwi, dwi_direct = _acc(P[4 * d])
             call("deer_gate_rows_interleave", ptr(dwi_il), ptr(dwi), H, In, 1, 1)
             dwh, dwh_direct = _acc(P[4 * d + 1])
