@@ -800,7 +800,13 @@ class _BiLSTMLayerCluster(torch.autograd.Function):
         ctx.pre = ctx.hb16 = None
         use16 = ctx.use16
         M = T * B
-        db_il = torch.zeros((2, G), device=dev, dtype=torch.float32)
+        if use16:   # the three gate-interleaved gradient accumulators of the layer in one zero-filled allocation
+            zbuf = torch.zeros(2 * G * (In + H + 1), device=dev, dtype=torch.float32)
+            dwi_il2 = zbuf[:2 * G * In].view(2, G, In)
+            dwh_il2 = zbuf[2 * G * In:2 * G * (In + H)].view(2, G, H)
+            db_il = zbuf[2 * G * (In + H):].view(2, G)
+        else:
+            db_il = torch.zeros((2, G), device=dev, dtype=torch.float32)
         dpre16 = torch.empty((T, B, 2, G), device=dev, dtype=torch.bfloat16) if use16 else None
         call("deer_lstm_cluster_bwd", ptr(gact), ptr(c_blk), ptr(dh), ptr(whf), ptr(whr),
              None if dpre is None else ptr(dpre), ptr(db_il), None if dpre16 is None else dpre16.data_ptr(), T, B, H)
@@ -832,13 +838,10 @@ class _BiLSTMLayerCluster(torch.autograd.Function):
                      beta=0.0 if d == 0 else 1.0)
         P = ctx.params
         out = []
-        dwi_il2 = None
         if use16:
             # dW_ih of both directions at once: [2G, In] = dpre16 [M, 2G]^T . xb16 [M, In]
-            dwi_il2 = torch.zeros((2, G, In), device=dev, dtype=torch.float32)
             gemm_h16(dpre16, 2 * G, 1, xb16, Kp, 0, dwi_il2, In, 2 * G, In, M, a_bf16=True, b_bf16=True, beta=1.0)
         if use16:
-            dwh_il2 = torch.zeros((2, G, H), device=dev, dtype=torch.float32)
             Mr = (T - 1) * B
             if T > 1:
                 # rows t=1.. of the forward direction pair with h[t-1]; rows ..T-2 of the reverse one with h[t+1]
