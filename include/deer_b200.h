@@ -125,6 +125,10 @@ int deer_dropout_cast16(const float* x, void* y_fp16, void* y_bf16, long long n,
 int deer_rowdot_fwd(const float* h, const float* w, const float* b, float* s, long long M, int N, void* stream);
 int deer_rowdot_bwd(const float* ds, const float* h, const float* w, float* dh, float* dw, float* db,
                     long long M, int N, void* stream);
+/*      backward of the whole scorer head s = w2 . tanh(z) + b2 in one pass over hidden = tanh(z) [M,N]:
+ *      dz = ds w2 (1 - hidden^2) (may alias hidden), dw2 += sum_m ds hidden, db1 += sum_m dz, db2 += sum_m ds */
+int deer_scorer_bwd(const float* ds, const float* hidden, const float* w2, float* dz, float* dw2, float* db1, float* db2,
+                    long long M, int N, void* stream);
 /*      pool: p = softmax_t(s[b,:]); if mask: p = p*mask / (sum_t p*mask + 1e-10); out[b,:] = sum_t p[b,t] * x[b,t,:]
  *      x element (b,t,d) at x[b*xs_b + t*xs_t + d]; s element (b,t) at s[b*ss_b + t*ss_t]; mask [B,T] contiguous or NULL;
  *      if premask, x is multiplied by mask before use (text path, encoders.py:734-735). wts [B,T] out. */

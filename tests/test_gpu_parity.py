@@ -738,7 +738,12 @@ def test_fused_scorer_pool_matches_separate_nodes(time_major, masked):
             out, wts = ops.attn_pool(xs.permute(1, 0, 2), s.permute(1, 0), m) if time_major else ops.attn_pool(xs, s, m)
         (out * cu(pr)).sum().backward()
         res.append([out.detach(), wts.detach(), xs.grad] + [p.grad for p in ps])
-    for a, b in zip(*res):      # bias gradients are atomically accumulated: equal up to the summation order
+    for i, (a, b) in enumerate(zip(*res)):
+        if i == len(res[0]) - 1:
+            # d/d b2 is sum_t ds = 0 in exact arithmetic (softmax is shift invariant): pure rounding noise in both
+            assert float(a.abs().max()) < 1e-4 and float(b.abs().max()) < 1e-4
+            continue
+        # bias gradients are atomically accumulated: equal up to the summation order
         assert_close(a, b, 1e-4, "fused vs separate")
     # and against torch fp64
     xd = x0.double().requires_grad_(True)

@@ -39,6 +39,7 @@ _PROTOS = {
     "deer_attn_pool_fwd": [P, L, L, P, L, L, P, P, P, I, I, I, P],
     "deer_attn_pool_bwd": [P, P, L, L, P, L, L, P, P, P, P, I, I, I, I, P],
     "deer_permute_bt": [P, P, I, I, I, P],
+    "deer_scorer_bwd": [P, P, P, P, P, P, P, L, I, P],
     "deer_rowscale": [P, P, P, L, I, P],
     "deer_im2col3": [P, P, I, I, I, P],
     "deer_col2im3": [P, P, I, I, I, P],

@@ -40,6 +40,49 @@ __global__ void __launch_bounds__(256) bias_act_bwd_kernel(const float* __restri
   }
 }
 
+// ------------------------------------------------------------------ attention-scorer backward (Linear-Tanh-Linear(1))
+// s[m] = w2 . hidden[m,:] + b2 with hidden = tanh(.): from ds [M] in ONE pass over hidden
+//   dz[m,j] = ds[m] w2[j] (1 - hidden[m,j]^2)   (gradient at the first Linear's output; may overwrite `hidden`)
+//   dw2[j] += sum_m ds[m] hidden[m,j],  db1[j] += sum_m dz[m,j],  db2 += sum_m ds[m]
+// (as rowdot_bwd followed by bias_act_bwd the [M,Hd] intermediate was written and read once more).
+__global__ void __launch_bounds__(256) scorer_bwd_kernel(const float* __restrict__ ds, const float* __restrict__ hidden,
+                                                         const float* __restrict__ w2, float* __restrict__ dz,
+                                                         float* __restrict__ dw2, float* __restrict__ db1,
+                                                         float* __restrict__ db2, int M, int N, int rows_per_block) {
+  DEER_PDL_ENTRY();
+  __shared__ float red[2][8][33];
+  const int n = blockIdx.x * 32 + threadIdx.x;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(M, r0 + rows_per_block);
+  float sw = 0.f, sb = 0.f, sd = 0.f;
+  if (n < N) {
+    const float w = w2[n];
+    for (int m = r0 + threadIdx.y; m < r1; m += 8) {
+      const float d = ds[m];
+      const float h = hidden[(long long)m * N + n];
+      const float g = d * w * (1.f - h * h);
+      dz[(long long)m * N + n] = g;
+      sw = fmaf(d, h, sw);
+      sb += g;
+      if (blockIdx.x == 0 && threadIdx.x == 0) sd += d;
+    }
+  }
+  red[0][threadIdx.y][threadIdx.x] = sw;
+  red[1][threadIdx.y][threadIdx.x] = sb;
+  __syncthreads();
+  if (threadIdx.y == 0 && n < N) {
+    float tw = 0.f, tb = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      tw += red[0][i][threadIdx.x];
+      tb += red[1][i][threadIdx.x];
+    }
+    atomicAdd(dw2 + n, tw);
+    atomicAdd(db1 + n, tb);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(db2, sd);   // one column of blocks sums ds
+}
+
 // ------------------------------------------------------------------ Philox-4x32-10
 __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
   const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
@@ -515,6 +558,20 @@ int deer_dropout_cast16(const float* x, void* y_fp16, void* y_bf16, long long n,
                  "dropout_cast16: alignment");
   DEER_LAUNCH(dropout_cast16_kernel, dropout_grid(n >> 2), 256, 0, stream, x, reinterpret_cast<uint16_t*>(y_fp16),
               reinterpret_cast<uint16_t*>(y_bf16), n, p, 1.f / (1.f - p), seed, offset, step_ptr);
+  return DEER_OK;
+}
+
+int deer_scorer_bwd(const float* ds, const float* hidden, const float* w2, float* dz, float* dw2, float* db1, float* db2,
+                    long long M, int N, void* stream) {
+  DEER_CHECK_ARG(ds && hidden && w2 && dz && dw2 && db1 && db2 && M > 0 && M < (1ll << 31) && N > 0,
+                 "scorer_bwd: bad args");
+  const long long gx = cdiv(N, 32);
+  long long want_gy = cdiv(6 * kNumSMs, gx);
+  int rpb = (int)cdiv(M, want_gy);
+  rpb = ((rpb + 7) / 8) * 8;
+  if (rpb < 8) rpb = 8;
+  dim3 grid((unsigned)gx, (unsigned)cdiv(M, rpb));
+  DEER_LAUNCH(scorer_bwd_kernel, grid, dim3(32, 8), 0, stream, ds, hidden, w2, dz, dw2, db1, db2, (int)M, N, rpb);
   return DEER_OK;
 }
 

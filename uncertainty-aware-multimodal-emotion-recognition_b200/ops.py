@@ -512,12 +512,12 @@ class _ScorerPool(torch.autograd.Function):
         ds = torch.empty(M, device=dev, dtype=torch.float32)
         call("deer_attn_pool_bwd", ptr(dout.contiguous()), ptr(x), xs_b, xs_t, ptr(sc), ss_b, ss_t, ptr(m), ptr(wts),
              ptr(dx), ptr(ds), B, T, D, 0)
-        dh = torch.empty_like(hidden)
         dw2, dw2_direct = _acc(pw2, like=w2v)
         db2, db2_direct = _acc(pb2)
-        call("deer_rowdot_bwd", ptr(ds), ptr(hidden), ptr(w2v), ptr(dh), ptr(dw2), ptr(db2), M, Hd)
         db1, db1_direct = _acc(pb1)
-        call("deer_bias_act_bwd", ptr(dh), Hd, ptr(hidden), Hd, ptr(dh), Hd, ptr(db1), M, Hd, ACT["tanh"])   # in place
+        # the whole scorer head backward in one pass over the saved tanh output
+        dh = torch.empty_like(hidden)
+        call("deer_scorer_bwd", ptr(ds), ptr(hidden), ptr(w2v), ptr(dh), ptr(dw2), ptr(db1), ptr(db2), M, Hd)
         if need_dx:
             gemm(dh, Hd, 0, w1, w1.stride(0), 0, dx, D, M, D, Hd, beta=1.0, engine=_bwd_engine(M))
         dw1, dw1_direct = _acc(pw1)
