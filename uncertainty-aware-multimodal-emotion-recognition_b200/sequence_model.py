@@ -70,7 +70,7 @@ class SequenceDEERModel(nn.Module):
             v = self.video_encoder(video)
             t = self.text_encoder(text, attention_mask, linguistic_features)
         fus = self.fusion(a, v, t)
-        out = self.deer(fus["fused_features"])
+        out = self.deer(ops.mark_tensor(fus["fused_features"], "fused"))
         out["fused_features"] = fus["fused_features"]
         out["audio_encoded"], out["video_encoded"], out["text_encoded"] = a, v, t
         out["attention_weights"] = fus["trimodal_attention_weights"]

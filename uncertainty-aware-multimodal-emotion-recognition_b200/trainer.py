@@ -167,8 +167,10 @@ class DEERDataParallelTrainer:
         gb = B * self.world if self.exact_global_loss else B
         # with exact global semantics local gradients are SUMMED across ranks; otherwise they are averaged
         scale = 1.0 if self.exact_global_loss else 1.0 / self.world
+        ops.mark("head_out")
         losses, dE, _, _ = ops.nig_loss_raw(ev.detach(), None, targets, weights=self.loss_weights, want_grad=True,
                                             grad_scale=scale, stats_hook=hook, global_batch=gb)
+        ops.mark("loss_done")
         state = {}
         handle = None
         fence = getattr(getattr(model, "video_encoder", None), "_first_bwd_node", None)
