@@ -757,3 +757,31 @@ def test_fused_scorer_pool_matches_separate_nodes(time_major, masked):
     (ref * pr.double()).sum().backward()
     assert_close(res[0][0], ref, 1e-4, "pooled vs fp64")
     assert_close(res[0][2], xd.grad, 1e-3, "dx vs fp64")
+
+
+@pytest.mark.parametrize("shared_input", [True, False])
+@pytest.mark.parametrize("act", ["relu", "none"])
+def test_grouped_linear_batched_matches_per_group_launches(shared_input, act):
+    """Per-head grouped Linear as ONE batched GEMM launch (evenly spaced operands) against one launch per group:
+    outputs, input gradients and weight / bias gradients."""
+    g = torch.Generator().manual_seed(9)
+    G, M, K, N = 3, 50, 48, 32
+    wbuf = torch.randn(G, N * K + N + 16, generator=g) * 0.2          # [W | b | pad] per head, evenly spaced
+    xin = torch.randn(M, K, generator=g) if shared_input else torch.randn(M, G, K, generator=g)
+    pr = torch.randn(M, G, N, generator=g)
+    res = []
+    for batched in (True, False):
+        ops.set_grouped_batched(batched)
+        try:
+            wb = cu(wbuf).requires_grad_(True)
+            ws = [wb[i, :N * K].view(N, K) for i in range(G)]
+            bs = [wb[i, N * K:N * K + N] for i in range(G)]
+            x = cu(xin).requires_grad_(True)
+            xs = [x] * G if shared_input else [x[:, i] for i in range(G)]
+            out = ops.grouped_linear(xs, ws, bs, act)
+            (out * cu(pr)).sum().backward()
+            res.append((out.detach(), x.grad, wb.grad))
+        finally:
+            ops.set_grouped_batched(True)
+    for a, b in zip(*res):
+        assert_close(a, b, 1e-5, "batched vs per-group")

@@ -26,7 +26,12 @@ ENGINE_AUTO, ENGINE_SIMT, ENGINE_TF32 = 0, 1, 2
 _state = {"engine": ENGINE_AUTO, "lstm_engine": ENGINE_AUTO, "exact_small_fwd": True, "exact_small_bwd": True,
           "small_rows": 8192, "direct_grad": False, "lstm_gemm16": True, "fuse_lstm_dropout": True,
           "branch_streams": True, "lstm_pre16": True, "defer_wgrad": True,
-          "branch_max_batch": 512, "scorer_pool_fused": True}
+          "branch_max_batch": 512, "scorer_pool_fused": True, "grouped_batched": True}
+
+
+def set_grouped_batched(on: bool):
+    """Per-head grouped Linear layers as one batched GEMM launch when their operands are evenly spaced (default)."""
+    _state["grouped_batched"] = bool(on)
 
 
 def set_defer_wgrad(on: bool):
@@ -1092,6 +1097,16 @@ def mha2_core(qkv, heads):
 
 
 # ----------------------------------------------------------------------------------------------- grouped Linear
+def _uniform_stride(ptrs):
+    """Element stride between consecutive fp32 pointers if it is the same for all of them (None otherwise)."""
+    if len(ptrs) < 2:
+        return None
+    d = ptrs[1] - ptrs[0]
+    if d % 16 != 0 or any(ptrs[i + 1] - ptrs[i] != d for i in range(len(ptrs) - 1)):
+        return None
+    return d // 4
+
+
 class _GroupedLinear(torch.autograd.Function):
     """out[:, g, :] = act(x_g W_g^T + b_g) for g in range(G); out [M,G,N].  Inputs may be strided row views
     (e.g. slices out[:, g, :] of a previous grouped output), so chains of per-head layers need no copies."""
@@ -1103,10 +1118,29 @@ class _GroupedLinear(torch.autograd.Function):
         rows = [_rows2d(_req(x, "input")) for x in xs]
         M = rows[0][1]
         out = torch.empty((M, G, N), device=ws[0].device, dtype=torch.float32)
-        for g in range(G):
-            x2, _, K, ld = rows[g]
-            gemm(x2, ld, 0, ws[g], ws[g].stride(0), 1, out.data_ptr() + 4 * g * N, G * N, M, N, K, bias=bs[g], act=act,
-                 engine=_fwd_engine(M))
+        # One batched launch when the groups' operands are evenly spaced in memory (the per-head layers of the NIG head:
+        # equal-sized heads laid out back to back in the trainer's flat parameter buffer; inputs either one shared
+        # tensor or slices of a previous grouped output)
+        same = (all(r[2] == rows[0][2] and r[3] == rows[0][3] for r in rows) and
+                all(w.shape == ws[0].shape and w.stride(0) == ws[0].stride(0) for w in ws) and
+                all(b is not None for b in bs))
+        sx = sw = sb = None
+        if same and G > 1 and _state["grouped_batched"] and M < _state["small_rows"]:   # (large M: tcgen05, unbatched)
+            xp = [r[0].data_ptr() for r in rows]
+            sx = 0 if all(q == xp[0] for q in xp) else _uniform_stride(xp)
+            sw = _uniform_stride([w.data_ptr() for w in ws])
+            sb = _uniform_stride([b.data_ptr() for b in bs])
+        batched = sx is not None and sw is not None and sb is not None
+        if batched:
+            x2, _, K, ld = rows[0]
+            gemm(x2, ld, 0, ws[0], ws[0].stride(0), 1, out, G * N, M, N, K, bias=bs[0], act=act, batch=G, sA=sx, sB=sw,
+                 sC=N, sBias=sb, engine=_fwd_engine(M))
+        else:
+            for g in range(G):
+                x2, _, K, ld = rows[g]
+                gemm(x2, ld, 0, ws[g], ws[g].stride(0), 1, out.data_ptr() + 4 * g * N, G * N, M, N, K, bias=bs[g],
+                     act=act, engine=_fwd_engine(M))
+        ctx.batched = (sx, sw) if batched else None
         ctx.act, ctx.G = act, G
         ctx.params = (ws, bs)
         ctx.meta = [(r[3], r[2]) for r in rows]
@@ -1134,6 +1168,28 @@ class _GroupedLinear(torch.autograd.Function):
             elif dbs[g] is not None:
                 call("deer_bias_act_bwd", dout.data_ptr() + off, G * N, None, 0, None, 0, ptr(dbs[g]), M, N, 0)
         dws, dxs = [], []
+        if ctx.batched is not None and all(ctx.needs_input_grad[2 + g] for g in range(G)):
+            # batched weight gradients (and input gradients when the groups have distinct inputs): one launch each
+            sx, sw = ctx.batched
+            ld, K = ctx.meta[0]
+            dw_acc = [_acc(pws[g]) for g in range(G)]
+            sdw = _uniform_stride([a[0].data_ptr() for a in dw_acc])
+            need_dx = [ctx.needs_input_grad[2 + 2 * G + g] for g in range(G)]
+            # (sdw == 0: one weight shared by the groups, e.g. the packed in_proj of the two-token attention -- its
+            # gradient contributions must be accumulated one after the other, not by concurrent batch entries)
+            if sdw and (sx != 0 or not any(need_dx)) and (all(need_dx) or not any(need_dx)):
+                gemm(dz, G * N, 1, xs[0], ld, 0, dw_acc[0][0], K, N, K, M, beta=1.0, batch=G, sA=N, sB=sx, sC=sdw,
+                     engine=_bwd_engine(M))
+                dws = [None if direct else buf for buf, direct in dw_acc]
+                if all(need_dx):
+                    dxa = torch.empty((G, M, K), device=dev, dtype=torch.float32)
+                    gemm(dz, G * N, 0, ws[0], ws[0].stride(0), 0, dxa, K, M, K, N, batch=G, sA=N, sB=sw, sC=M * K,
+                         engine=_bwd_engine(M))
+                    dxs = [dxa[g].view(ctx.in_shapes[g]) for g in range(G)]
+                else:
+                    dxs = [None] * G
+                dbs = [None if a[1] else a[0] for a in db_acc]
+                return (None, None, *dws, *dbs, *dxs)
         for g in range(G):
             ld, K = ctx.meta[g]
             zp = dz.data_ptr() + 4 * g * N
