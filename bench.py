@@ -119,17 +119,19 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import torch_baseline as TB
-    sample_b = 32
+    sample_b = args.ref_batch       # default: the SAME batch as the GPU arm (B=256, ~3 s per step on 16 host threads)
     sps, dt, threads = TB.time_cpu_baseline("train", sample_b, iters=max(1, args.steps), warmup=max(1, args.warmup))
     line = {
         "impl": "reference", "metric": "deer_train_step_samples_per_s", "value": sps, "unit": "samples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"sequence DEER train step (fwd+loss+bwd+clip+AdamW) on host CPU, bounded sample "
-                               f"B={sample_b} of the B={TRAIN_B} config; audio {TA}x84, video {TV}x256, text {TT}x768",
+        "same_config": sample_b == TRAIN_B,
+        "config": {"workload": f"sequence DEER train step (fwd+loss+bwd+clip+AdamW) on host CPU, B={sample_b} per step "
+                               f"(GPU arm: B={TRAIN_B}/GPU); audio {TA}x84, video {TV}x256, text {TT}x768, dropout 0.3",
                    "batch_per_step": sample_b},
         "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": threads, "kind": "port",
-                         "sample": f"B={sample_b} train steps x{args.steps} (oracle/torch_baseline.py)"},
+                         "sample": f"B={sample_b} train steps x{args.steps} (oracle/torch_baseline.py: stock torch.nn "
+                                   "layers wired as the reference wires them; /root/reference cannot travel)"},
         "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -154,6 +156,12 @@ def main():
     ap.add_argument("--lstm-tile", type=int, default=None, help="DEER_OPT_LSTM_TILE override (ablation)")
     ap.add_argument("--no-defer-wgrad", action="store_true",
                     help="ablation: small-layer weight gradients on the main stream")
+    ap.add_argument("--ref-batch", type=int, default=TRAIN_B, help="batch of the CPU reference arm (default: same as GPU)")
+    ap.add_argument("--global-batch", type=int, default=0,
+                    help="STRONG scaling: fixed global batch split over the ranks (BASELINE configs[3]: 2048); the "
+                         "headline then reports scaling=strong.  Default 0: weak scaling, B=256 per GPU")
+    ap.add_argument("--no-strong", action="store_true", help="skip the extra strong-scaling block (global batch 2048)")
+    ap.add_argument("--no-loss-check", action="store_true", help="skip the step-0 loss check against the CPU port")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     if args.impl == "reference":
@@ -211,22 +219,57 @@ def main():
         return max_over_ranks(e0.elapsed_time(e1))
 
     # ------------------------------------------------------------------ model + trainer
+    strong = args.global_batch > 0
+    if strong and args.global_batch % world:
+        raise SystemExit(f"--global-batch {args.global_batch} is not divisible by {world} ranks")
+    B = args.global_batch // world if strong else TRAIN_B
     torch.manual_seed(42)
     model = deer_b200.SequenceDEERModel(dropout=0.3).to(dev).train()
     trainer = DEERDataParallelTrainer(model, learning_rate=1e-4, weight_decay=1e-5, gradient_clip=1.0)
     gen = torch.Generator().manual_seed(1234 + rank)
-    NB = 4  # rotating resident batches: 4 x 89 MB > 126 MB L2
-    batches = [synth_batch(TRAIN_B, dev, gen) for _ in range(NB)]
-
     use_graph = not args.no_graph
+
+    # step-0 check of the path being timed against the CPU port (same weights, same inputs; eval mode so that neither
+    # side draws dropout masks): the loss the bench optimises is the reference's loss
+    loss_check = None
+    if rank == 0 and not args.no_loss_check:
+        loss_check = check_loss_against_port(torch, model, dev, gen)
+
+    def measure_train(Bt, steps, warm):
+        """(ms per step, launches per step, final loss) of the trainer step at Bt samples per GPU, inputs resident."""
+        nb = max(2, min(4, (256 * 4) // Bt))    # rotating resident batches: >= 2, 4 x 89 MB at B=256 (> 126 MB L2)
+        batches = [synth_batch(Bt, dev, gen) for _ in range(nb)]
+        trainer.train_step(batches[0])
+        l0 = _lib.launch_count()
+        trainer.train_step(batches[0])
+        launches = _lib.launch_count() - l0
+        # the whole step (fwd + loss + bwd + all-reduce + clip + AdamW) captured once per resident batch and replayed
+        replays = [trainer.capture(b) for b in batches] if use_graph else None
+
+        def fn(i):
+            if use_graph:
+                replays[i % nb]()
+            else:
+                trainer.train_step(batches[i % nb])
+
+        for i in range(warm):
+            fn(i)
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        ms = timed(fn, steps)
+        clk = sampler.stop() if rank == 0 else None
+        return ms / steps, launches, float(trainer.last_losses[-1]), clk, nb
+
     overlap_check = None
     if world > 1:
         # the early (overlapped) gradient exchange must give the same reduced gradients as one all-reduce at the end,
         # up to the run-to-run noise of the atomically accumulated / split-K gradients (measured on the spot)
+        b0 = synth_batch(B, dev, gen)
         g = []
         for ov in (True, False, False):
             trainer.overlap_exchange = ov
-            trainer.forward_backward(batches[0])
+            trainer.forward_backward(b0)
             if not trainer._grads_reduced:
                 trainer._allreduce(trainer.flat.grads)
             trainer._grads_reduced = False
@@ -236,63 +279,34 @@ def main():
         noise = float((g[1] - g[2]).norm() / g[2].norm())
         overlap_check = float((g[0] - g[2]).norm() / g[2].norm())
         assert overlap_check < 3 * noise + 1e-5, f"overlapped gradient exchange differs: {overlap_check} (noise {noise})"
-        del g
-    # launches of one step, counted on an eager step (a graph replay issues the same kernels with one host call)
-    trainer.train_step(batches[0])
-    l0 = _lib.launch_count()
-    trainer.train_step(batches[0])
-    launches_per_step = _lib.launch_count() - l0
-    # the whole step (fwd + loss + bwd + all-reduce + clip + AdamW) captured once per resident batch and replayed
-    replays = [trainer.capture(b) for b in batches] if use_graph else None
+        del g, b0
 
-    def train_fn(i):
-        if use_graph:
-            replays[i % NB]()
-        else:
-            trainer.train_step(batches[i % NB])
-
-    for i in range(W):
-        train_fn(i)
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    ms = timed(train_fn, K)
-    clocks = sampler.stop() if rank == 0 else None
-    ms_per_step = ms / K
-    value = TRAIN_B * world / (ms_per_step / 1e3)
-    final_loss = float(trainer.last_losses[-1])
+    ms_per_step, launches_per_step, final_loss, clocks, NB = measure_train(B, K, W)
+    value = B * world / (ms_per_step / 1e3)
 
     # ------------------------------------------------------------------ e2e: pinned host -> device every step
-    # Public API path: pinned host batch -> H2D copy -> trainer.train_step -> D2H read of the loss, every step inside
-    # the timed region.  The copy of step i+1 is issued on a side stream while step i computes (double-buffered
-    # device batches), which is how a real input pipeline feeds the trainer; every byte still crosses PCIe per step.
-    host = [synth_batch(TRAIN_B, None, gen, pinned=True) for _ in range(2)]
-    h2d = sum(v.numel() * v.element_size() for v in host[0].values())
-    copy_stream = torch.cuda.Stream(device=dev)
-    dev_bufs = [{k: torch.empty_like(v, device=dev) for k, v in host[0].items()} for _ in range(2)]
-    ready = [torch.cuda.Event() for _ in range(2)]
-    consumed = [torch.cuda.Event() for _ in range(2)]
-
-    def stage(i):
-        j = i % 2
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(consumed[j])          # the step that last read this buffer has finished
-            for k, v in host[j].items():
-                dev_bufs[j][k].copy_(v, non_blocking=True)
-            ready[j].record(copy_stream)
-
+    # Public API path: pinned host batch -> deer_b200.data.DevicePrefetcher (H2D on a copy stream into rotating static
+    # device buffers) -> trainer step (graph replay on that buffer set) -> D2H read of the loss, every step inside the
+    # timed region.  The copy of step i+1 runs while step i computes; every byte still crosses PCIe per step.
+    from deer_b200.data import DevicePrefetcher
+    host = [synth_batch(B, None, gen, pinned=True) for _ in range(2)]
+    stager = DevicePrefetcher([], dev, depth=2)
     loss_host = [torch.zeros(1).pin_memory() for _ in range(2)]     # pinned landing buffers for the per-step loss
     loss_done = [torch.cuda.Event() for _ in range(2)]
     loss_log = []
+    state = {"next": stager.stage(host[0]), "i": 0}
 
-    e2e_replays = [trainer.capture(b) for b in dev_bufs] if use_graph else None
-
-    def e2e_fn(i):
+    def e2e_fn(_):
+        i = state["i"]
+        state["i"] = i + 1
         j = i % 2
-        stage(i + 1)                                     # prefetch the next step's batch
-        torch.cuda.current_stream().wait_event(ready[j])
-        losses = e2e_replays[j]() if use_graph else trainer.train_step(dev_bufs[j])
-        consumed[j].record()
+        cur = state["next"]
+        state["next"] = stager.stage(host[(i + 1) % 2])      # prefetch the next step's batch
+        stager.wait(cur)
+        tens = stager.tensors(cur)
+        losses = (trainer.train_step_auto(tens, eager_steps=1, static_inputs=True) if use_graph
+                  else trainer.train_step(tens))
+        stager.release(cur)
         # D2H read of the step's loss: asynchronous copy into pinned memory every step; the host consumes the value
         # one step later (after its event), so kernel launches of step i+1 are never held back by a device sync
         loss_host[j].copy_(losses[-1:], non_blocking=True)
@@ -301,55 +315,97 @@ def main():
             loss_done[1 - j].synchronize()
             loss_log.append(float(loss_host[1 - j]))
 
-    for j in range(2):
-        consumed[j].record()
-    stage(0)
-    for i in range(2):
+    for i in range(6):        # per buffer set: one eager step, then the capture; afterwards replays only
         e2e_fn(i)
     torch.cuda.synchronize()
-    stage_base = 2
-
-    def e2e_timed(i):
-        e2e_fn(stage_base + i)
-
-    e2e_ms = timed(e2e_timed, K) / K
-    e2e_value = TRAIN_B * world / (e2e_ms / 1e3)
+    h2d = stager.bytes_per_batch
+    e2e_ms = timed(e2e_fn, K) / K
+    e2e_value = B * world / (e2e_ms / 1e3)
     torch.cuda.synchronize()
     assert len(loss_log) >= K and all(v == v for v in loss_log[-K:]), "e2e loop must deliver a finite loss every step"
+    del host
+
+    # ------------------------------------------------------------------ strong scaling (BASELINE configs[3]): global 2048
+    strong_block = None
+    if not strong and not args.no_strong and STRONG_GLOBAL % world == 0:
+        Bs = STRONG_GLOBAL // world
+        if Bs == B:
+            strong_block = {"global_batch": STRONG_GLOBAL, "batch_per_gpu": Bs, "value": value,
+                            "ms_per_step": ms_per_step, "unit": "samples/s", "note": "same run as the headline"}
+        else:
+            sk = max(5, K // 4)
+            sms, _, _, _, _ = measure_train(Bs, sk, 3)
+            strong_block = {"global_batch": STRONG_GLOBAL, "batch_per_gpu": Bs, "value": STRONG_GLOBAL / (sms / 1e3),
+                            "ms_per_step": sms, "unit": "samples/s", "steps": sk}
+        trainer._graphs.clear()
+        torch.cuda.empty_cache()
 
     # ------------------------------------------------------------------ inference B=1024
     model.eval()
     ibatches = [synth_batch(INFER_B, dev, gen) for _ in range(2)]
+    ikeys = ("audio_features", "video_features", "text_features", "attention_mask", "linguistic_features")
 
-    def infer_eager(i):
-        b = ibatches[i % 2]
+    def infer_eager(b):
         with torch.no_grad():
-            model(b["audio_features"], b["video_features"], b["text_features"], b["attention_mask"],
-                  b["linguistic_features"])
+            return model(*[b[k] for k in ikeys])
 
     for i in range(2):
-        infer_eager(i)
+        infer_eager(ibatches[i])
     l0 = _lib.launch_count()
-    infer_eager(0)
+    infer_eager(ibatches[0])
     infer_launches = _lib.launch_count() - l0
+    from deer_b200.trainer import capture_forward
     if use_graph:
-        from deer_b200.trainer import capture_forward
-        ireplays = [capture_forward(model, b["audio_features"], b["video_features"], b["text_features"],
-                                    b["attention_mask"], b["linguistic_features"])[0] for b in ibatches]
+        ireplays = [capture_forward(model, *[b[k] for k in ikeys])[0] for b in ibatches]
 
     def infer_fn(i):
         if use_graph:
             ireplays[i % 2]()
         else:
-            infer_eager(i)
+            infer_eager(ibatches[i % 2])
 
-    infer_ms = timed(infer_fn, max(3, K // 2)) / max(3, K // 2)
+    KI = max(3, K // 2)
+    infer_ms = timed(infer_fn, KI) / KI
     infer_value = INFER_B * world / (infer_ms / 1e3)
-    model.train()
     del ibatches
+    # inference end to end: pinned host batch (357 MB at B=1024) -> H2D -> forward -> D2H of the NIG parameters
+    ihost = [{k: v for k, v in synth_batch(INFER_B, None, gen, pinned=True).items() if k in ikeys} for _ in range(2)]
+    istager = DevicePrefetcher([], dev, depth=2)
+    nig_host = [torch.zeros(4, INFER_B, 3).pin_memory() for _ in range(2)]
+    istate = {"next": istager.stage(ihost[0]), "i": 0, "replays": {}}
+
+    def infer_e2e(_):
+        i = istate["i"]
+        istate["i"] = i + 1
+        cur = istate["next"]
+        istate["next"] = istager.stage(ihost[(i + 1) % 2])
+        istager.wait(cur)
+        tens = istager.tensors(cur)
+        key = tens["audio_features"].data_ptr()
+        if use_graph and key not in istate["replays"]:
+            istate["replays"][key] = capture_forward(model, *[tens[k] for k in ikeys])
+        if use_graph:
+            rep, out = istate["replays"][key]
+            rep()
+        else:
+            out = infer_eager(tens)
+        istager.release(cur)
+        dst = nig_host[i % 2]
+        for q, k in enumerate(("gamma", "nu", "alpha", "beta")):
+            dst[q].copy_(out[k], non_blocking=True)
+
+    for i in range(3):
+        infer_e2e(i)
+    torch.cuda.synchronize()
+    infer_e2e_ms = timed(infer_e2e, KI) / KI
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(nig_host[0]).all())
+    infer_h2d = istager.bytes_per_batch
+    model.train()
+    del ihost, istate, istager
     torch.cuda.empty_cache()
 
-    # ------------------------------------------------------------------ roofline of the dominant kernel
+    # ------------------------------------------------------------------ roofline of the dominant kernels
     roof = roofline_probe(torch, ops, dev, pk)
 
     # ------------------------------------------------------------------ BASELINE configs[4]: pooled CompleteDEERModel on
@@ -357,62 +413,122 @@ def main():
     pooled = (pooled_sweep(torch, deer_b200, DEERDataParallelTrainer, dev, use_graph)
               if (world == 1 and not args.no_pooled) else None)
 
+    inference = {"value": infer_value, "unit": "samples/s", "batch_per_gpu": INFER_B, "ms_per_step": infer_ms,
+                 "launches_per_step": int(infer_launches),
+                 "tensor_frac_of_sustained_bf16": infer_value / world * FWD_FLOP_PER_SAMPLE / 1e12 /
+                 pk["bf16_tflops_sustained"],
+                 "e2e": {"value": INFER_B * world / (infer_e2e_ms / 1e3), "unit": "samples/s",
+                         "ms_per_step": infer_e2e_ms, "h2d_bytes_per_step": infer_h2d,
+                         "d2h_bytes_per_step": 4 * INFER_B * 3 * 4,
+                         "note": "PCIe-bound: 357 MB of fp32 features per forward"}}
     line = {
         "metric": "deer_train_step_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": world,
-        "steps": K, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "steps": K, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "strong" if strong else "weak",
+        "vs_baseline": None,
+        "dtype": "mixed: fp16/bf16 (LSTM GEMMs + recurrence) and tf32 (scorers, conv, projections) tensor-core operands, "
+                 "fp32 accumulate; 3xTF32 (fp32-grade) fusion/head chain; fp32 transcendentals and loss",
+        "data": "synthetic",
         "config": {"workload": f"sequence DEER training step: fwd + DEER multitask NIG loss + bwd + grad all-reduce + "
-                               f"clip + AdamW; B={TRAIN_B}/GPU (global {TRAIN_B * world}), audio {TA}x84, video "
+                               f"clip + AdamW; B={B}/GPU (global {B * world}), audio {TA}x84, video "
                                f"{TV}x256, text {TT}x768, dropout 0.3, 9,262,642 params",
-                   "batch_per_gpu": TRAIN_B, "global_batch": TRAIN_B * world, "parallelism": f"dp{world}",
-                   "l2_policy": f"{NB} rotating resident input batches ({NB * TRAIN_B * INPUT_BYTES_PER_SAMPLE / 1e6:.0f} "
+                   "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
+                   "l2_policy": f"{NB} rotating resident input batches ({NB * B * INPUT_BYTES_PER_SAMPLE / 1e6:.0f} "
                                 "MB) + >1 GB of activations per step, larger than the 126 MB L2",
-                   "loss_semantics": "exact global batch (loss statistics all-reduced)", "final_loss": final_loss},
+                   "loss_semantics": "exact global batch (loss statistics all-reduced)", "final_loss": final_loss,
+                   "loss_check_vs_cpu_port": loss_check},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": 4},
+                "d2h_bytes_per_step": 4, "api": "deer_b200.data.DevicePrefetcher -> DEERDataParallelTrainer.train_step_auto"},
         "cuda_graph": use_graph, "branch_streams": ops.branch_streams_enabled(),
         "exchange_overlap": bool(world > 1 and trainer.overlap_exchange), "exchange_overlap_check": overlap_check,
         "gpu_launches": int(launches_per_step * K),
         "launches_per_step": int(launches_per_step),
-        "inference": {"value": infer_value, "unit": "samples/s", "batch_per_gpu": INFER_B, "ms_per_step": infer_ms,
-                      "launches_per_step": int(infer_launches),
-                      "tensor_frac_of_sustained_bf16": infer_value / world * FWD_FLOP_PER_SAMPLE / 1e12 /
-                      pk["bf16_tflops_sustained"]},
+        "inference": inference,
+        "strong_scaling": strong_block,
         "train_tensor_frac_of_sustained_bf16": value / world * TRAIN_FLOP_PER_SAMPLE / 1e12 / pk["bf16_tflops_sustained"],
         "roofline": roof,
         "peaks": pk,
     }
+    # (the driver's parser keeps nested keys of `config` / `e2e` / `roofline`: the inference and strong-scaling numbers are
+    # mirrored there so they survive into BENCH_rNN.json / SCALE_rNN.json)
+    line["config"]["inference"] = {k: inference[k] for k in ("value", "ms_per_step", "batch_per_gpu")}
+    line["config"]["inference"]["e2e_value"] = inference["e2e"]["value"]
+    line["config"]["strong_scaling"] = strong_block
+    roof["inference"] = inference
     if pooled is not None:
         line["pooled_model_sweep"] = pooled
+        line["config"]["pooled_model_sweep"] = pooled
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import torch_baseline as TB
-        sb = 32
-        sps, dt, threads = TB.time_cpu_baseline("train", sb, iters=8, warmup=1)
-        isps, idt, _ = TB.time_cpu_baseline("infer", 64, iters=4, warmup=1)
+        sb = TRAIN_B
+        sps, dt, threads = TB.time_cpu_baseline("train", sb, iters=3, warmup=1)
+        sps32, dt32, _ = TB.time_cpu_baseline("train", 32, iters=4, warmup=1)
+        isps, idt, _ = TB.time_cpu_baseline("infer", 256, iters=3, warmup=1)
         line["cpu_baseline"] = {"value": sps, "unit": "samples/s", "cores": threads, "kind": "port",
-                                "sample": f"B={sb} train steps x8 ({dt:.2f} s/step) of the B={TRAIN_B} workload, "
-                                          "oracle/torch_baseline.py (stock torch.nn, oneDNN LSTM)",
-                                "inference_value": isps, "inference_sample": f"B=64 x4 ({idt:.2f} s/step)"}
+                                "sample": f"B={sb} train steps x3 ({dt:.2f} s/step): the same per-step workload as the GPU "
+                                          "arm; oracle/torch_baseline.py (stock torch.nn, oneDNN LSTM)",
+                                "value_b32": sps32, "sample_b32": f"B=32 x4 ({dt32:.2f} s/step)",
+                                "inference_value": isps, "inference_sample": f"B=256 x3 ({idt:.2f} s/step)"}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
-        # captured graphs hold NCCL work: drop them, drain the device, meet the other ranks, then leave without the
-        # process-group teardown (destroy_process_group after graph-captured collectives hung at exit on NCCL 2.28)
-        replays = e2e_replays = None
-        trainer._graphs.clear()
-        trainer._auto.clear()
-        import gc
-        gc.collect()
-        torch.cuda.synchronize()
-        dist.barrier()
-        torch.cuda.synchronize()
-        sys.stdout.flush()
-        sys.stderr.flush()
-        os._exit(0)
+        teardown_distributed(torch, dist, trainer)
 
 
-def pooled_sweep(torch, deer_b200, Trainer, dev, use_graph=True, batches=(64, 1024, 16384, 65536)):
+STRONG_GLOBAL = 2048
+
+
+def teardown_distributed(torch, dist, trainer):
+    """Leave a multi-rank run: drop the captured graphs (they hold NCCL work), drain, meet the other ranks, destroy the
+    process group.  destroy_process_group after graph-captured collectives hung at exit on NCCL 2.28 in round 1, so it
+    runs under a watchdog: if it has not returned after 20 s the rank leaves with os._exit(0) (all results are already
+    printed and flushed)."""
+    import gc
+    trainer._graphs.clear()
+    trainer._auto.clear()
+    gc.collect()
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    done = threading.Event()
+
+    def watchdog():
+        if not done.wait(20.0):
+            os._exit(0)
+
+    threading.Thread(target=watchdog, daemon=True).start()
+    dist.destroy_process_group()
+    done.set()
+
+
+def check_loss_against_port(torch, model, dev, gen, Bc=16):
+    """The GPU path's DEER multitask loss on a small batch vs the stock-torch.nn CPU port with the SAME weights
+    (eval mode: no dropout masks on either side).  Asserts 1e-3 relative agreement; returns the two numbers."""
+    from oracle import torch_baseline as TB
+    was = model.training
+    model.eval()
+    b = synth_batch(Bc, "cpu", gen)
+    port = TB.SequenceBaseline(dropout=0.0).eval()
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    missing, unexpected = port.load_state_dict(sd, strict=False)
+    assert not missing, f"CPU port is missing weights: {missing[:4]}"
+    with torch.no_grad():
+        pred = port(b["audio_features"], b["video_features"], b["text_features"], b["attention_mask"],
+                    b["linguistic_features"])
+        ref = float(TB.multitask_loss(pred, b["targets"]))
+        db = {k: v.to(dev) for k, v in b.items()}
+        out = model(db)
+        got = float(model.compute_loss(out, db["targets"])["total_loss"])
+    model.train(was)
+    rel = abs(got - ref) / max(abs(ref), 1e-12)
+    assert rel <= 1e-3, f"bench loss check failed: GPU {got} vs CPU port {ref} (rel {rel:.2e})"
+    return {"gpu": got, "cpu_port": ref, "rel_err": rel, "batch": Bc}
+
+
+def pooled_sweep(torch, deer_b200, Trainer, dev, use_graph=True, batches=(64, 256, 1024, 4096, 16384, 65536)):
     """Pooled-feature model (complete_project.py:462, 3,918,324 parameters): samples/s of the trainer step and of the
     eval forward per batch size (inputs resident; 5 timed steps each)."""
     torch.manual_seed(7)
@@ -454,7 +570,12 @@ def _time_launches(torch, fn, n, warm=5):
     return e0.elapsed_time(e1) * 1e3 / n   # us per launch
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/)
+# bytes of kept BPTT state per (sample, step, direction, hidden unit): 4 activated gates + the cell state
+LSTM_KEEP_BYTES_PER_UNIT = 4 * 4 + 4
+# dram__bytes_read.sum + dram__bytes_write.sum per launch: OFFLINE constants transcribed from the committed
+# `ncu --set full` captures under profiles/ (a bench run cannot measure DRAM traffic itself; a number taken under the
+# profiler is never a bench value) -- reported as `traffic` with `traffic_source`
+NCU_TRAFFIC_SOURCE = "offline: profiles/r1_ncu_full_roofline_v12_summary.txt, profiles/r1_ncu_full_lstm_v12_summary.txt"
 NCU_TRAFFIC = {
     # profiles/r1_ncu_full_roofline_v12_summary.txt (ncu --set full --clock-control none, per launch)
     "gemm_h16_pair_out16": 80.8e6 + 255.4e6,                       # algorithmic 395 MB; part of C16 still in L2 at kernel end
@@ -499,7 +620,7 @@ def roofline_probe(torch, ops, dev, pk):
             "achieved": gbs if hbm_bound else achieved, "peak": pk["hbm_gbs"] if hbm_bound else pk["bf16_tflops"],
             "unit": "GB/s" if hbm_bound else "TFLOP/s",
             "frac": (gbs / pk["hbm_gbs"]) if hbm_bound else (achieved / pk["bf16_tflops"]),
-            "traffic": NCU_TRAFFIC.get("gemm_h16_pair_out16"), "us_per_launch": us,
+            "traffic": NCU_TRAFFIC.get("gemm_h16_pair_out16"), "traffic_source": NCU_TRAFFIC_SOURCE, "us_per_launch": us,
             "flop_per_launch": flop, "algorithmic_bytes_per_launch": alg_bytes,
             "hbm_floor_us": hbm_floor_us, "tensor_floor_us": tensor_floor_us,
             "hbm": {"achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"]},
@@ -556,7 +677,7 @@ def roofline_probe(torch, ops, dev, pk):
                              "bound": "hbm", "achieved": nbytes / (us_n * 1e-6) / 1e9, "peak": pk["hbm_gbs"],
                              "unit": "GB/s", "frac": nbytes / (us_n * 1e-6) / 1e9 / pk["hbm_gbs"],
                              "us_per_call": us_n, "algorithmic_bytes": nbytes,
-                             "traffic": NCU_TRAFFIC.get("nig_stats_plus_finish")}
+                             "traffic": NCU_TRAFFIC.get("nig_stats_plus_finish"), "traffic_source": NCU_TRAFFIC_SOURCE}
     del ev, tg
     torch.cuda.empty_cache()
 
@@ -577,9 +698,39 @@ def roofline_probe(torch, ops, dev, pk):
     us_b = _time_launches(torch, lambda i: call("deer_lstm_cluster_bwd", ptr(gact), ptr(c), ptr(dh), ptr(w[0]), ptr(w[1]),
                                                 None, ptr(db), dpre16.data_ptr(), T, B, H), 5, warm=2)
     rflop = 2.0 * B * 2 * 4 * H * H * T
+    # algorithmic HBM bytes per (sample, step, direction) [SURVEY 8d / DESIGN 4]: forward reads the FP16 pre-activations
+    # (4H x 2 B) and writes h fp32 (H x 4) + its BF16 shadow (H x 2) + the kept gates / cell state (keep_bytes); BPTT
+    # reads the kept gates / cell states (c_t and c_{t-1} are one stream) + dh (H x 4) and writes the BF16 dpre (4H x 2)
+    keep_b = LSTM_KEEP_BYTES_PER_UNIT * H
+    fwd_bytes = (4 * H * 2 + H * 4 + H * 2 + keep_b) * float(B * T * 2)
+    bwd_bytes = (keep_b + H * 4 + 4 * H * 2) * float(B * T * 2)
     roof["lstm_recurrence"] = {"kernel": "tc::lstm_fwd_cluster_kernel / lstm_bwd_cluster_kernel (B=256, T=300, H=256, 2 dirs)",
                                "bound": "latency (serial over T)", "fwd_us_per_step": us_f / T, "bwd_us_per_step": us_b / T,
-                               "fwd_tflops": rflop / (us_f * 1e-6) / 1e12, "bwd_tflops": rflop / (us_b * 1e-6) / 1e12}
+                               "fwd_tflops": rflop / (us_f * 1e-6) / 1e12, "bwd_tflops": rflop / (us_b * 1e-6) / 1e12,
+                               "fwd_algorithmic_bytes": fwd_bytes, "bwd_algorithmic_bytes": bwd_bytes,
+                               "fwd_hbm": {"achieved": fwd_bytes / (us_f * 1e-6) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                                           "frac": fwd_bytes / (us_f * 1e-6) / 1e9 / pk["hbm_gbs"]},
+                               "bwd_hbm": {"achieved": bwd_bytes / (us_b * 1e-6) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                                           "frac": bwd_bytes / (us_b * 1e-6) / 1e9 / pk["hbm_gbs"]},
+                               "traffic": NCU_TRAFFIC.get("lstm_fwd_keep"), "traffic_source": NCU_TRAFFIC_SOURCE}
+    del pre, h, hb16, gact, c, dh, dpre16
+    torch.cuda.empty_cache()
+
+    # ---- attention pooling (audio encoder shape): the HBM-measurable op of SURVEY 8d -- one pass over [B,T,512] fp32
+    Bp_, D = INFER_B, 2 * H
+    xs = [torch.randn(T, Bp_, D, device=dev) for _ in range(2)]        # time-major, as the LSTM writes it (2 x 629 MB)
+    sc = torch.randn(T * Bp_, device=dev)
+    outp = torch.empty(Bp_, D, device=dev)
+    wts = torch.empty(Bp_, T, device=dev)
+    us_p = _time_launches(torch, lambda i: call("deer_attn_pool_fwd", ptr(xs[i % 2]), D, Bp_ * D, ptr(sc), 1, Bp_, None,
+                                                ptr(outp), ptr(wts), Bp_, T, D), 8, warm=2)
+    pbytes = float(Bp_ * T * D * 4 + 2 * Bp_ * T * 4 + Bp_ * D * 4)
+    roof["attn_pool"] = {"kernel": "deer::attn_pool_fwd_kernel (B=1024, T=300, D=512: online softmax + weighted sum, one pass)",
+                         "bound": "hbm", "achieved": pbytes / (us_p * 1e-6) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                         "frac": pbytes / (us_p * 1e-6) / 1e9 / pk["hbm_gbs"], "us_per_launch": us_p,
+                         "algorithmic_bytes": pbytes, "traffic": None}
+    del xs, sc, outp, wts
+    torch.cuda.empty_cache()
     return roof
 
 

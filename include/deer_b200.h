@@ -44,6 +44,14 @@ extern "C" {
 #define DEER_LSTM_PERSISTENT_V1 4
 
 int deer_version(void);
+/* which engine the dispatchers picked, counted per call since process start (the parity tests assert that the
+ * benchmarked dispatch -- tcgen05 for the time-batched contractions -- is the one they exercised) */
+#define DEER_ENGINE_SIMT 1       /* exact-fp32 CUDA-core tiles */
+#define DEER_ENGINE_TF32 2       /* tcgen05 kind::tf32, 128x128 tiles */
+#define DEER_ENGINE_TF32_PAIR 3  /* tcgen05 kind::tf32, cta_group::2 256x256 tiles */
+#define DEER_ENGINE_H16 4        /* tcgen05 kind::f16 (deer_gemm_h16) */
+#define DEER_ENGINE_TF32X3 5     /* error-compensated 3xTF32 tensor-core tiles (fp32-grade accuracy) */
+long long deer_gemm_engine_count(int engine);
 const char* deer_last_error(void);
 /* number of kernels launched by this library since process start (bench.py `gpu_launches`) */
 long long deer_launch_count(void);
@@ -259,6 +267,11 @@ int deer_sumsq(const float* x, long long n, float* out /* accumulates */, void* 
 /*      step_dev (device int64, may be NULL): when given the update uses step = *step_dev + 1 and `step` is ignored;
  *      lr_dev (device float, may be NULL): when given the learning rate is lr * *lr_dev.  Both exist so that a
  *      CUDA-graph capture of the training step stays valid across steps and LR-schedule changes. */
+/* x[0..n) = 0 and (y non-NULL) y[0..ny) = 0: the once-per-step clear of the flat gradient buffer and of the
+ * gradient-norm accumulator (replaces optimizer.zero_grad(), training.py:215); step_increment: *step += 1 on the device
+ * (graph-replayable step counter read by deer_adamw and the dropout kernels) */
+int deer_fill_zero(float* x, long long n, float* y, long long ny, void* stream);
+int deer_step_increment(long long* step, void* stream);
 int deer_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                float eps, float weight_decay, int step, const float* sumsq, float max_norm, float grad_scale,
                const long long* step_dev, const float* lr_dev, void* stream);

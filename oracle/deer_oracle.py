@@ -66,11 +66,13 @@ def lstm_direction(x, w_ih, w_hh, b_ih, b_hh, reverse):
     H = w_hh.shape[1]
     h = x.new_zeros(B, H)
     c = x.new_zeros(B, H)
-    pre = linear(x, w_ih, b_ih + b_hh)  # [B,T,4H]
+    # (unbind, not pre[:, t]: the backward of T selects would materialise T zero-filled [B,T,4H] tensors)
+    pre = linear(x, w_ih, b_ih + b_hh).unbind(1)  # T x [B,4H]
     outs = [None] * T
     order = range(T - 1, -1, -1) if reverse else range(T)
+    w_hh_t = w_hh.t()
     for t in order:
-        g = pre[:, t] + h @ w_hh.t()
+        g = pre[t] + h @ w_hh_t
         i_, f_, g_, o_ = g.split(H, dim=1)
         i_, f_, o_ = torch.sigmoid(i_), torch.sigmoid(f_), torch.sigmoid(o_)
         g_ = torch.tanh(g_)

@@ -22,6 +22,7 @@ _PROTOS = {
     "deer_version": [],
     "deer_last_error": [],
     "deer_launch_count": [],
+    "deer_gemm_engine_count": [I],
     "deer_timestamp": [P, I, P],
     "deer_set_option": [I, I],
     "deer_lstm_set_profile_buffer": [P],
@@ -66,6 +67,8 @@ _PROTOS = {
     "deer_nig_loss_finish": [P, P, P, P, P, P, P, P, P, F, F, F, F, F, L, L, I, I, F, P, P, P],
     "deer_amini_loss": [P, P, P, P, P, F, F, L, P, P, P, P],
     "deer_sumsq": [P, L, P, P],
+    "deer_fill_zero": [P, L, P, L, P],
+    "deer_step_increment": [P, P],
     "deer_adamw": [P, P, P, P, L, F, F, F, F, F, I, P, F, F, P, P, P],
     "deer_axpby": [P, P, P, L, F, F, P],
     "deer_mix_fwd": [P, L, P, L, P, P, P, L, I, P],
@@ -82,7 +85,7 @@ _PROTOS = {
     "deer_uce_select": [P, L, P, I, P, P, L, P],
     "deer_uce_bins": [P, P, L, I, P, P, P],
 }
-_RESTYPES = {"deer_last_error": ctypes.c_char_p, "deer_launch_count": L}
+_RESTYPES = {"deer_last_error": ctypes.c_char_p, "deer_launch_count": L, "deer_gemm_engine_count": L}
 
 EXPORTS = tuple(_PROTOS)
 
@@ -118,6 +121,15 @@ def check(rc: int, what: str = ""):
 
 def launch_count() -> int:
     return int(load().deer_launch_count())
+
+
+ENGINE_NAMES = {1: "simt", 2: "tf32", 3: "tf32_pair", 4: "h16", 5: "tf32x3"}
+
+
+def engine_counts() -> dict:
+    """{engine name: GEMM dispatches since process start} (deer_gemm_engine_count)."""
+    lib = load()
+    return {n: int(lib.deer_gemm_engine_count(e)) for e, n in ENGINE_NAMES.items()}
 
 
 def stream() -> int:

@@ -6,6 +6,7 @@
 namespace deer {
 
 std::atomic<long long> g_launches{0};
+std::atomic<long long> g_engine_calls[8];   // per-engine dispatch counters (deer_gemm_engine_count)
 int g_pdl = 0;   // measured: PDL made the B=1024 inference 10 % slower and the train step 2 % slower (early-resident
                  // dependents compete for SM slots); kept as an ablation switch
 static thread_local char g_err[512] = "";
@@ -55,7 +56,10 @@ __global__ void timestamp_kernel(unsigned long long* slots, int index) {
 
 extern "C" {
 
-int deer_version(void) { return 100; }
+int deer_version(void) { return 200; }
+long long deer_gemm_engine_count(int engine) {
+  return (engine >= 0 && engine < 8) ? g_engine_calls[engine].load() : -1;
+}
 const char* deer_last_error(void) { return g_err; }
 long long deer_launch_count(void) { return g_launches.load(); }
 
@@ -127,23 +131,31 @@ int deer_gemm(const float* A, long long lda, int transA, const float* B, long lo
                 M, N, K, lda, ldb, ldc);
       return DEER_ERR_UNSUPPORTED;
     }
+    g_engine_calls[DEER_ENGINE_TF32_PAIR]++;
     return gemm_tf32_pair(A, lda, transA, B, ldb, transB, C, ldc, M, N, K, bias, act, beta, (cudaStream_t)stream);
   }
   DEER_CHECK_ARG(act >= 0 && act <= 3, "gemm: bad activation");
   DEER_CHECK_ARG(beta == 0.f || beta == 1.f, "gemm: beta must be 0 or 1");
   cudaStream_t st = (cudaStream_t)stream;
-  if (engine == DEER_GEMM_SIMT)
+  if (engine == DEER_GEMM_SIMT) {
+    g_engine_calls[DEER_ENGINE_SIMT]++;
     return gemm_simt(A, lda, transA, B, ldb, transB, C, ldc, M, N, K, bias, act, beta, batch, sA, sB, sC, sBias, st);
+  }
   const bool ok = gemm_tcgen05_supported(A, lda, transA, B, ldb, transB, C, ldc, M, N, K, batch, sA, sB, sC);
   if (engine == DEER_GEMM_TF32 && !ok) {
     set_error("gemm: shape/alignment not supported by the tcgen05 engine (M=%d N=%d K=%d lda=%lld ldb=%lld)", M, N, K,
               lda, ldb);
     return DEER_ERR_UNSUPPORTED;
   }
-  if (ok && gemm_tf32_pair_supported(transA, transB, M, N, K, ldc, bias, act, beta))
+  if (ok && gemm_tf32_pair_supported(transA, transB, M, N, K, ldc, bias, act, beta)) {
+    g_engine_calls[DEER_ENGINE_TF32_PAIR]++;
     return gemm_tf32_pair(A, lda, transA, B, ldb, transB, C, ldc, M, N, K, bias, act, beta, st);
-  if (ok)
+  }
+  if (ok) {
+    g_engine_calls[DEER_ENGINE_TF32]++;
     return gemm_tcgen05(A, lda, transA, B, ldb, transB, C, ldc, M, N, K, bias, act, beta, batch, sA, sB, sC, sBias, st);
+  }
+  g_engine_calls[DEER_ENGINE_SIMT]++;
   return gemm_simt(A, lda, transA, B, ldb, transB, C, ldc, M, N, K, bias, act, beta, batch, sA, sB, sC, sBias, st);
 }
 

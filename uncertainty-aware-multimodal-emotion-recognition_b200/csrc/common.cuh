@@ -10,6 +10,7 @@
 namespace deer {
 
 extern std::atomic<long long> g_launches;
+extern std::atomic<long long> g_engine_calls[8];
 void set_error(const char* fmt, ...);
 
 inline int cuda_status(cudaError_t e, const char* what) {

@@ -1025,6 +1025,7 @@ int deer_gemm_h16(const void* A, long long lda, int transA, int a_bf16, const vo
   DEER_CHECK_ARG(beta == 0.f || beta == 1.f, "gemm_h16: beta must be 0 or 1");
   // tcgen05.mma kind::f16 takes ONE 16-bit format for both operands (a mixed descriptor traps as an illegal instruction)
   DEER_CHECK_ARG((a_bf16 != 0) == (b_bf16 != 0), "gemm_h16: A and B must both be FP16 or both be BF16");
+  g_engine_calls[DEER_ENGINE_H16]++;
   return gemm_h16(A, lda, transA, a_bf16, B, ldb, transB, b_bf16, C, ldc, C16, ldc16, c16_bf16, M, N, K, bias, act, beta,
                   (cudaStream_t)stream);
 }

@@ -57,6 +57,24 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
     v[i] = vi;
   }
 }
+// zero-fill of the trainer's flat gradient buffer (+ an optional second small buffer: the gradient-norm accumulator)
+__global__ void __launch_bounds__(256) fill_zero_kernel(float* __restrict__ x, long long n, float* __restrict__ y,
+                                                        long long ny) {
+  DEER_PDL_ENTRY();
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+  const bool al = (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+  const long long n4 = al ? (n >> 2) : 0;
+  float4* x4 = reinterpret_cast<float4*>(x);
+  for (long long i = tid; i < n4; i += nth) x4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long i = (n4 << 2) + tid; i < n; i += nth) x[i] = 0.f;
+  if (y)
+    for (long long i = tid; i < ny; i += nth) y[i] = 0.f;
+}
+
+__global__ void step_increment_kernel(long long* step) {
+  DEER_PDL_ENTRY();
+  *step += 1;
+}
 
 }  // namespace deer
 
@@ -71,6 +89,21 @@ int deer_sumsq(const float* x, long long n, float* out, void* stream) {
   if (g > kNumSMs * 8) g = kNumSMs * 8;
   if (g < 1) g = 1;
   DEER_LAUNCH(sumsq_kernel, (unsigned)g, 256, 0, stream, x, n, out);
+  return DEER_OK;
+}
+
+int deer_fill_zero(float* x, long long n, float* y, long long ny, void* stream) {
+  DEER_CHECK_ARG(x && n > 0 && (y == nullptr || ny > 0), "fill_zero: bad args");
+  long long g = cdiv(n, 256 * 8);
+  if (g > kNumSMs * 8) g = kNumSMs * 8;
+  if (g < 1) g = 1;
+  DEER_LAUNCH(fill_zero_kernel, (unsigned)g, 256, 0, stream, x, n, y, ny);
+  return DEER_OK;
+}
+
+int deer_step_increment(long long* step, void* stream) {
+  DEER_CHECK_ARG(step, "step_increment: null pointer");
+  DEER_LAUNCH(step_increment_kernel, 1, 1, 0, stream, step);
   return DEER_OK;
 }
 

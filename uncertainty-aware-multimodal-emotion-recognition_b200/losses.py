@@ -37,7 +37,10 @@ def _gather(cols: List[torch.Tensor]) -> torch.Tensor:
     if all(c.dim() == 2 and c.shape[1] == 1 and c.stride(0) == D and c.data_ptr() == base.data_ptr() + 4 * i
            for i, c in enumerate(cols)) and base._base is not None and all(c._base is base._base for c in cols):
         b = base._base
-        if b.dim() >= 2 and b.shape[-1] == D and b.is_contiguous():
+        # (only when the gathered view stays on the autograd tape: a base allocated inside a custom Function's forward
+        # -- the [7,B*D] buffer of ops.nig_head -- has no grad_fn, and a view of it would silently detach the head)
+        on_tape = (not any(c.requires_grad for c in cols)) or b.requires_grad
+        if on_tape and b.dim() >= 2 and b.shape[-1] == D and b.is_contiguous():
             flat = b.reshape(-1, D)
             off = (base.data_ptr() - b.data_ptr()) // (4 * D)
             return flat[off:off + base.shape[0]]

@@ -183,15 +183,19 @@ def set_exact_small_forward(on: bool, small_rows: int = 8192, backward: Optional
     _state["small_rows"] = int(small_rows)
 
 
-def _bwd_engine(M: int):
-    if _state["engine"] == ENGINE_AUTO and _state["exact_small_bwd"] and M < _state["small_rows"]:
+def _bwd_engine(M: int, chain: bool = False):
+    """Engine for a backward GEMM of an nn.Linear with M rows; `chain`: see _fwd_engine."""
+    if _state["engine"] == ENGINE_AUTO and _state["exact_small_bwd"] and (chain or M < _state["small_rows"]):
         return ENGINE_SIMT
     return None
 
 
-def _fwd_engine(M: int):
-    """Engine for a FORWARD nn.Linear with M rows under the precision policy."""
-    if _state["engine"] == ENGINE_AUTO and _state["exact_small_fwd"] and M < _state["small_rows"]:
+def _fwd_engine(M: int, chain: bool = False):
+    """Engine for a FORWARD nn.Linear with M rows under the precision policy.  `chain` = a post-pooling layer (one row
+    per sample: fusion, NIG head, pooled model): exact at EVERY batch size -- the policy is keyed on the layer's role, not
+    on the row count, so outputs do not change discontinuously with the batch.  Time-batched contractions (M = B*T
+    rows: scorers, Conv1d taps, projections) use the TF32 tensor-core engine once M reaches `small_rows`."""
+    if _state["engine"] == ENGINE_AUTO and _state["exact_small_fwd"] and (chain or M < _state["small_rows"]):
         return ENGINE_SIMT
     return None
 
@@ -261,17 +265,20 @@ class _Linear(torch.autograd.Function):
         k0 = 0
         y = None
         lead = xs[0].shape[:-1]
+        chain = len(lead) == 1          # one row per sample: a post-pooling (fusion / head) layer, exact at every M
         for i, x in enumerate(xs):
             x2, M, K, ld = _rows2d(_req(x, "input"))
             if y is None:
                 y = torch.empty((M, N), device=w.device, dtype=torch.float32)
             last = i == len(xs) - 1
             gemm(x2, ld, 0, w.data_ptr() + 4 * k0, w.stride(0), 1, y, N, M, N, K,
-                 bias=b if last else None, act=act if last else 0, beta=0.0 if i == 0 else 1.0, engine=_fwd_engine(M))
+                 bias=b if last else None, act=act if last else 0, beta=0.0 if i == 0 else 1.0,
+                 engine=_fwd_engine(M, chain))
             rows.append((x2, ld, k0, K))
             k0 += K
         assert k0 == Ktot, f"input widths {k0} != weight in-features {Ktot}"
         ctx.act = act
+        ctx.chain = chain
         ctx.has_bias = b is not None
         ctx.params = (w, b)
         ctx.meta = [(ld, k, K) for (_, ld, k, K) in rows]
@@ -299,17 +306,19 @@ class _Linear(torch.autograd.Function):
         # next layers' dx GEMMs (each of these kernels fills a fraction of the machine); the trainer joins the
         # stream before the gradient exchange (join_wgrad_stream).
         defer = (dw is not None and dw_direct and _state["defer_wgrad"] and M < _state["small_rows"] and dz.is_cuda)
+        chain = ctx.chain
         dxs = []
         for i, x2 in enumerate(xs):
             ld, k0, K = ctx.meta[i]
             if ctx.needs_input_grad[4 + i]:
                 dx = torch.empty((M, K), device=w.device, dtype=torch.float32)
-                gemm(dz, N, 0, w.data_ptr() + 4 * k0, w.stride(0), 0, dx, K, M, K, N, engine=_bwd_engine(M))
+                gemm(dz, N, 0, w.data_ptr() + 4 * k0, w.stride(0), 0, dx, K, M, K, N, engine=_bwd_engine(M, chain))
                 dxs.append(dx.view(ctx.in_shapes[i]))
             else:
                 dxs.append(None)
             if dw is not None and not defer:
-                gemm(dz, N, 1, x2, ld, 0, dw.data_ptr() + 4 * k0, Ktot, N, K, M, beta=1.0, engine=_bwd_engine(M))
+                gemm(dz, N, 1, x2, ld, 0, dw.data_ptr() + 4 * k0, Ktot, N, K, M, beta=1.0,
+                     engine=_bwd_engine(M, chain))
         if defer:
             cur = torch.cuda.current_stream()
             aux = _wgrad_stream()
@@ -317,7 +326,8 @@ class _Linear(torch.autograd.Function):
             with torch.cuda.stream(aux):
                 for i, x2 in enumerate(xs):
                     ld, k0, K = ctx.meta[i]
-                    gemm(dz, N, 1, x2, ld, 0, dw.data_ptr() + 4 * k0, Ktot, N, K, M, beta=1.0, engine=_bwd_engine(M))
+                    gemm(dz, N, 1, x2, ld, 0, dw.data_ptr() + 4 * k0, Ktot, N, K, M, beta=1.0,
+                         engine=_bwd_engine(M, chain))
                     x2.record_stream(aux)
             dz.record_stream(aux)
             _wgrad["pending"] = True
@@ -364,23 +374,39 @@ def layer_norm(x, g, b, eps=1e-5):
 
 
 # ----------------------------------------------------------------------------------------------- Dropout
-_dropout_state = {"seed": 0x5EED, "offset": 0, "step": None}
+_dropout_state = {"seed": 0x5EED, "offset": 0, "step": None, "host_step": 0}
+_SEED_MIX = 0x9E3779B97F4A7C15
 
 
 def manual_seed(seed: int):
     _dropout_state["seed"] = int(seed)
     _dropout_state["offset"] = 0
+    _dropout_state["host_step"] = 0
 
 
 def set_dropout_step_tensor(t: Optional[torch.Tensor]):
-    """int64 CUDA scalar the trainer increments once per step; mixed into the Philox counter so CUDA-graph replays
-    draw fresh masks.  None disables it."""
+    """int64 CUDA scalar a trainer increments once per step; mixed into the Philox counter so CUDA-graph replays
+    draw fresh masks.  None disables it (the host-side step counter of begin_step() is used instead).  Returns the
+    previous binding: a trainer binds its own tensor around its step and restores the caller's afterwards, so two
+    trainers in one process never share masks."""
+    prev = _dropout_state["step"]
     _dropout_state["step"] = t
+    return prev
 
 
 def begin_step():
-    """Restart the per-step element offsets (call once per forward so graph capture and eager agree)."""
+    """Once per model forward: restart the per-step element offsets (graph capture and eager agree) and advance the
+    host-side step counter that keys the masks when no device step tensor is bound -- a plain torch.optim loop around
+    the drop-in modules draws fresh dropout masks every forward."""
     _dropout_state["offset"] = 0
+    _dropout_state["host_step"] += 1
+
+
+def _dropout_seed() -> int:
+    """Seed of the masks drawn now: the base seed, mixed with the host step unless a device step tensor is bound."""
+    if _dropout_state["step"] is not None:
+        return _dropout_state["seed"]
+    return (_dropout_state["seed"] ^ (_dropout_state["host_step"] * _SEED_MIX)) & 0xFFFFFFFFFFFFFFFF
 
 
 class _Dropout(torch.autograd.Function):
@@ -406,7 +432,7 @@ def dropout(x, p: float, training: bool):
         return x
     off = _dropout_state["offset"]
     _dropout_state["offset"] = off + (x.numel() + 3) // 4
-    return _Dropout.apply(x, p, _dropout_state["seed"], off)
+    return _Dropout.apply(x, p, _dropout_seed(), off)
 
 
 # ----------------------------------------------------------------------------------------------- attention pooling
@@ -900,7 +926,7 @@ def bilstm_layer(x_tm, wif, whf, bif, bhf, wir, whr, bir, bhr, input_dropout: fl
         if fusable:
             off = _dropout_state["offset"]
             _dropout_state["offset"] = off + (x_tm.numel() + 3) // 4
-            drop = (float(input_dropout), _dropout_state["seed"], off)
+            drop = (float(input_dropout), _dropout_seed(), off)
         else:
             x_tm = dropout(x_tm, input_dropout, True)
     if cluster:
@@ -1125,7 +1151,7 @@ class _GroupedLinear(torch.autograd.Function):
                 all(w.shape == ws[0].shape and w.stride(0) == ws[0].stride(0) for w in ws) and
                 all(b is not None for b in bs))
         sx = sw = sb = None
-        if same and G > 1 and _state["grouped_batched"] and M < _state["small_rows"]:   # (large M: tcgen05, unbatched)
+        if same and G > 1 and _state["grouped_batched"]:
             xp = [r[0].data_ptr() for r in rows]
             sx = 0 if all(q == xp[0] for q in xp) else _uniform_stride(xp)
             sw = _uniform_stride([w.data_ptr() for w in ws])
@@ -1134,12 +1160,12 @@ class _GroupedLinear(torch.autograd.Function):
         if batched:
             x2, _, K, ld = rows[0]
             gemm(x2, ld, 0, ws[0], ws[0].stride(0), 1, out, G * N, M, N, K, bias=bs[0], act=act, batch=G, sA=sx, sB=sw,
-                 sC=N, sBias=sb, engine=_fwd_engine(M))
+                 sC=N, sBias=sb, engine=_fwd_engine(M, True))
         else:
             for g in range(G):
                 x2, _, K, ld = rows[g]
                 gemm(x2, ld, 0, ws[g], ws[g].stride(0), 1, out.data_ptr() + 4 * g * N, G * N, M, N, K, bias=bs[g],
-                     act=act, engine=_fwd_engine(M))
+                     act=act, engine=_fwd_engine(M, True))
         ctx.batched = (sx, sw) if batched else None
         ctx.act, ctx.G = act, G
         ctx.params = (ws, bs)
@@ -1179,12 +1205,12 @@ class _GroupedLinear(torch.autograd.Function):
             # gradient contributions must be accumulated one after the other, not by concurrent batch entries)
             if sdw and (sx != 0 or not any(need_dx)) and (all(need_dx) or not any(need_dx)):
                 gemm(dz, G * N, 1, xs[0], ld, 0, dw_acc[0][0], K, N, K, M, beta=1.0, batch=G, sA=N, sB=sx, sC=sdw,
-                     engine=_bwd_engine(M))
+                     engine=_bwd_engine(M, True))
                 dws = [None if direct else buf for buf, direct in dw_acc]
                 if all(need_dx):
                     dxa = torch.empty((G, M, K), device=dev, dtype=torch.float32)
                     gemm(dz, G * N, 0, ws[0], ws[0].stride(0), 0, dxa, K, M, K, N, batch=G, sA=N, sB=sw, sC=M * K,
-                         engine=_bwd_engine(M))
+                         engine=_bwd_engine(M, True))
                     dxs = [dxa[g].view(ctx.in_shapes[g]) for g in range(G)]
                 else:
                     dxs = [None] * G
@@ -1195,13 +1221,13 @@ class _GroupedLinear(torch.autograd.Function):
             zp = dz.data_ptr() + 4 * g * N
             if ctx.needs_input_grad[2 + g]:
                 dw, direct = _acc(pws[g])
-                gemm(zp, G * N, 1, xs[g], ld, 0, dw, K, N, K, M, beta=1.0, engine=_bwd_engine(M))
+                gemm(zp, G * N, 1, xs[g], ld, 0, dw, K, N, K, M, beta=1.0, engine=_bwd_engine(M, True))
                 dws.append(None if direct else dw)
             else:
                 dws.append(None)
             if ctx.needs_input_grad[2 + 2 * G + g]:
                 dx = torch.empty((M, K), device=dev, dtype=torch.float32)
-                gemm(zp, G * N, 0, ws[g], ws[g].stride(0), 0, dx, K, M, K, N, engine=_bwd_engine(M))
+                gemm(zp, G * N, 0, ws[g], ws[g].stride(0), 0, dx, K, M, K, N, engine=_bwd_engine(M, True))
                 dxs.append(dx.view(ctx.in_shapes[g]))
             else:
                 dxs.append(None)

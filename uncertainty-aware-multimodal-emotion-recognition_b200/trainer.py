@@ -78,9 +78,21 @@ def shard_batch(batch: Dict[str, torch.Tensor], rank: int, world: int) -> Dict[s
     return out
 
 
+# Parameters that never receive a gradient in the REFERENCE (`p.grad is None`, so torch.optim.AdamW skips them
+# entirely: no weight decay, no moment update): the never-executed uncertainty gate of HierarchicalMultimodalFusion
+# (fusion.py:147-159) and the pooled model's calibration layer, whose output does not feed the loss
+# (complete_project.py:449).  Parameters with an exactly-zero gradient (Q/K rows of a single-key attention) DO take
+# weight decay in the reference and stay in the optimised groups.
+REFERENCE_NO_GRAD_PREFIXES = ("fusion.uncertainty_gate.", "calibration_layer.")
+GROUP_ENCODER, GROUP_DEFAULT, GROUP_FROZEN = 0, 1, 2
+
+
 def reference_lr_group(name: str) -> int:
-    """training.py:128-142: names containing 'encoder' train at 0.5 x lr (group 0); everything else at lr (group 1)."""
-    return 0 if "encoder" in name else 1
+    """training.py:128-142: names containing 'encoder' train at 0.5 x lr (group 0); everything else at lr (group 1);
+    group 2 = parameters the reference optimizer never touches (grad is None), placed last and skipped."""
+    if name.startswith(REFERENCE_NO_GRAD_PREFIXES):
+        return GROUP_FROZEN
+    return GROUP_ENCODER if "encoder" in name else GROUP_DEFAULT
 
 
 def capture_forward(model: nn.Module, *inputs, warmup: int = 2, **kw_inputs):
@@ -108,14 +120,26 @@ def capture_forward(model: nn.Module, *inputs, warmup: int = 2, **kw_inputs):
 class DEERDataParallelTrainer:
     def __init__(self, model: nn.Module, learning_rate: float = 1e-4, weight_decay: float = 1e-5,
                  gradient_clip: float = 1.0, betas=(0.9, 0.999), eps: float = 1e-8,
-                 process_group=None, exact_global_loss: bool = True, loss_weights=(0.1, 0.01, 0.05, 0.05)):
+                 process_group=None, exact_global_loss: bool = True, loss_weights=None, task_weights=None,
+                 loss_eps: Optional[float] = None):
         self.model = model
         self._lr = float(learning_rate)
         self.wd, self.clip, self.betas, self.eps = weight_decay, gradient_clip, betas, eps
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
         self.exact_global_loss = exact_global_loss
-        self.loss_weights = loss_weights
+        # the optimised objective is the model's own loss (what compute_loss reports): reg / kl / ece / cross-dimension
+        # weights, task weights and epsilon are read from model.loss_fn (losses.MultiTaskDEERLoss) unless given
+        lf = getattr(model, "loss_fn", None)
+        if loss_weights is None:
+            loss_weights = lf._weights()[0] if hasattr(lf, "_weights") else (0.1, 0.01, 0.05, 0.05)
+        if task_weights is None and hasattr(lf, "_task_weight_list"):
+            task_weights = lf._task_weight_list()
+        if loss_eps is None:
+            loss_eps = lf._weights()[1] if hasattr(lf, "_weights") else 1e-8
+        self.loss_weights = tuple(float(w) for w in loss_weights)
+        self.task_weights = task_weights
+        self.loss_eps = float(loss_eps)
         self.flat = FlatBuffers(model, reference_lr_group)
         dev = self.flat.params.device
         self.m = torch.zeros_like(self.flat.params)
@@ -125,11 +149,14 @@ class DEERDataParallelTrainer:
         # device-side step counter and learning rate: a captured CUDA graph of the step replays unchanged while
         # both advance (dropout masks, AdamW bias corrections, LR schedule)
         self.step_tensor = torch.zeros(1, device=dev, dtype=torch.int64)
-        self.lr_tensor = torch.full((1,), float(learning_rate), device=dev, dtype=torch.float32)
+        # one learning rate PER GROUP on the device (training.py:138-142: encoder group at 0.5 x lr, and
+        # CosineAnnealingLR anneals every group from ITS base value to the same eta_min, :155-159)
+        self.group_scale = {GROUP_ENCODER: 0.5, GROUP_DEFAULT: 1.0}
+        self.lr_tensor = torch.tensor([self.group_scale[GROUP_ENCODER] * float(learning_rate), float(learning_rate)],
+                                      device=dev, dtype=torch.float32)
         self._graphs: Dict[int, tuple] = {}
         self._auto: Dict[tuple, dict] = {}
         self._graph_pool = None
-        ops.set_dropout_step_tensor(self.step_tensor)
         self.direct_grad = True   # backward kernels accumulate straight into the flat gradient buffer
         # Gradient exchange overlapped with BPTT: the audio encoder's parameters lead the flat buffer and its backward
         # (the LSTM recurrence, on its own stream) is the tail of the step, so everything behind them is all-reduced
@@ -139,7 +166,6 @@ class DEERDataParallelTrainer:
         self.overlap_exchange = False
         self._audio_end = self.flat.leading_prefix_end("audio_encoder.")
         self._grads_reduced = False
-        self.group_lr = {0: 0.5, 1: 1.0}
         self.last_losses: Optional[torch.Tensor] = None
 
     # ------------------------------------------------------------------ pieces
@@ -147,18 +173,24 @@ class DEERDataParallelTrainer:
         if self.world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.pg)
 
-    def forward_backward(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
-        """fwd + fused head/loss + bwd; gradients are accumulated into the flat buffer.  Returns losses [5D+2]."""
-        model = self.model
-        self.flat.grads.zero_()
+    def forward_backward(self, batch: Dict[str, torch.Tensor], loss_weight: float = 1.0) -> torch.Tensor:
+        """fwd + fused head/loss + bwd; gradients are accumulated into the flat buffer.  Returns losses [5D+2].
+        `loss_weight`: the per-batch dataset weight of training.py:211-212 (`weighted_loss = total_loss * w`): it scales
+        the back-propagated gradient; the returned loss components stay unweighted (as the reference logs them)."""
+        # one launch clears the flat gradient buffer and the gradient-norm accumulator
+        call("deer_fill_zero", ptr(self.flat.grads), self.flat.numel, ptr(self.sumsq), 1)
         ops.set_direct_grad_accumulation(self.direct_grad)
+        # this trainer's device step counter keys the dropout masks of ITS step only (restored afterwards)
+        prev = ops.set_dropout_step_tensor(self.step_tensor)
         try:
-            return self._forward_backward(batch)
+            return self._forward_backward(batch, float(loss_weight))
         finally:
+            ops.set_dropout_step_tensor(prev)
             ops.set_direct_grad_accumulation(False)
 
-    def _forward_backward(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
+    def _forward_backward(self, batch: Dict[str, torch.Tensor], loss_weight: float = 1.0) -> torch.Tensor:
         model = self.model
+        batch = {k: v for k, v in batch.items() if k != "dataset_id"}
         out = model(batch)   # both models accept the reference's batch dict (preprocessing.py:461-491)
         ev = out[EVIDENCE_KEY]
         targets = batch["targets"]
@@ -166,9 +198,10 @@ class DEERDataParallelTrainer:
         hook = self._allreduce if (self.exact_global_loss and self.world > 1) else None
         gb = B * self.world if self.exact_global_loss else B
         # with exact global semantics local gradients are SUMMED across ranks; otherwise they are averaged
-        scale = 1.0 if self.exact_global_loss else 1.0 / self.world
+        scale = (1.0 if self.exact_global_loss else 1.0 / self.world) * loss_weight
         ops.mark("head_out")
-        losses, dE, _, _ = ops.nig_loss_raw(ev.detach(), None, targets, weights=self.loss_weights, want_grad=True,
+        losses, dE, _, _ = ops.nig_loss_raw(ev.detach(), None, targets, weights=self.loss_weights, eps=self.loss_eps,
+                                            task_weights=self.task_weights, want_grad=True,
                                             grad_scale=scale, stats_hook=hook, global_batch=gb)
         ops.mark("loss_done")
         state = {}
@@ -204,10 +237,21 @@ class DEERDataParallelTrainer:
 
     @lr.setter
     def lr(self, value: float):
-        """Learning-rate schedule hook: updates the device scalar the (possibly graph-captured) AdamW launches read."""
+        """Learning-rate schedule hook: updates the device scalars the (possibly graph-captured) AdamW launches read
+        (every group at its multiple of `value`)."""
+        self.set_group_lrs({g: sc * float(value) for g, sc in self.group_scale.items()})
         self._lr = float(value)
-        if hasattr(self, "lr_tensor"):
-            self.lr_tensor.fill_(self._lr)
+
+    def set_group_lrs(self, lrs: Dict[int, float]):
+        """Per-group learning rates (group 0 = names containing 'encoder', group 1 = the rest), e.g. from a scheduler
+        that anneals each group from its own base value (CosineAnnealingLR, training.py:155-159)."""
+        vals = [float(lrs[GROUP_ENCODER]), float(lrs[GROUP_DEFAULT])]
+        self.lr_tensor.copy_(torch.tensor(vals, dtype=torch.float32), non_blocking=False)
+        self._lr = vals[1]
+
+    def group_lrs(self) -> Dict[int, float]:
+        v = self.lr_tensor.tolist()
+        return {GROUP_ENCODER: v[0], GROUP_DEFAULT: v[1]}
 
     def optimizer_step(self):
         self.step_count += 1
@@ -215,32 +259,32 @@ class DEERDataParallelTrainer:
         if not self._grads_reduced:
             self._allreduce(f.grads)
         self._grads_reduced = False
-        self.sumsq.zero_()
         call("deer_sumsq", ptr(f.grads), f.numel, ptr(self.sumsq))
         for g, lo, hi in f.group_bounds:
             n = hi - lo
-            if n <= 0:
+            if n <= 0 or g == GROUP_FROZEN:   # the reference optimizer never sees these (grad is None): no decay either
                 continue
-            # lr = group multiplier x *lr_tensor, step = *step_tensor + 1: both read on the device
+            # lr = lr_tensor[group], step = *step_tensor + 1: both read on the device
             call("deer_adamw", f.params.data_ptr() + 4 * lo, f.grads.data_ptr() + 4 * lo, self.m.data_ptr() + 4 * lo,
-                 self.v.data_ptr() + 4 * lo, n, float(self.group_lr[g]), float(self.betas[0]),
+                 self.v.data_ptr() + 4 * lo, n, 1.0, float(self.betas[0]),
                  float(self.betas[1]), float(self.eps), float(self.wd), 0, ptr(self.sumsq),
-                 float(self.clip), 1.0, self.step_tensor.data_ptr(), ptr(self.lr_tensor))
-        self.step_tensor.add_(1)
+                 float(self.clip), 1.0, self.step_tensor.data_ptr(), self.lr_tensor.data_ptr() + 4 * g)
+        call("deer_step_increment", self.step_tensor.data_ptr())
 
-    def train_step(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
-        losses = self.forward_backward(batch)
+    def train_step(self, batch: Dict[str, torch.Tensor], loss_weight: float = 1.0) -> torch.Tensor:
+        losses = self.forward_backward(batch, loss_weight)
         self.optimizer_step()
         return losses
 
     # ------------------------------------------------------------------ CUDA-graph replay of the whole step
-    def capture(self, batch: Dict[str, torch.Tensor], warmup: int = 2):
+    def capture(self, batch: Dict[str, torch.Tensor], warmup: int = 2, loss_weight: float = 1.0):
         """Capture fwd + loss + bwd + exchange + clip + AdamW on the tensors of `batch` (which become the static
         input buffers: refill them in place, e.g. with `copy_` from pinned host memory) into one CUDA graph.
         The ~300 kernel launches of a step then cost one `cudaGraphLaunch`; the step counter, dropout masks and the
         learning rate keep advancing because the kernels read them from device memory.  Returns a callable that
         replays the step and returns the (static) losses tensor."""
         key = tuple(sorted((k, v.data_ptr(), tuple(v.shape)) for k, v in batch.items() if torch.is_tensor(v)))
+        key = key + (("loss_weight", float(loss_weight)),)   # a kernel argument of the captured launches
         hit = self._graphs.get(hash(key))
         if hit is not None:
             return hit[2]
@@ -248,14 +292,14 @@ class DEERDataParallelTrainer:
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(warmup):       # lazily created state (TMA descriptors, smem opt-ins, NCCL buffers)
-                self.train_step(batch)
+                self.train_step(batch, loss_weight)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
         if self._graph_pool is None:
             self._graph_pool = torch.cuda.graph_pool_handle()
         with torch.cuda.graph(graph, pool=self._graph_pool):
-            losses = self.train_step(batch)
+            losses = self.train_step(batch, loss_weight)
         self.step_count -= 1   # the capture pass itself launched nothing
 
         def replay() -> torch.Tensor:
@@ -267,20 +311,32 @@ class DEERDataParallelTrainer:
         self._graphs[hash(key)] = (graph, losses, replay)
         return replay
 
-    def train_step_auto(self, batch: Dict[str, torch.Tensor], eager_steps: int = 2) -> torch.Tensor:
+    def train_step_auto(self, batch: Dict[str, torch.Tensor], eager_steps: int = 2,
+                        loss_weight: float = 1.0, static_inputs: bool = False) -> torch.Tensor:
         """train_step for a stream of freshly allocated batches (a DataLoader): the first `eager_steps` batches of a
         given shape run eagerly (they double as the warm-up), then the step is captured once on static input buffers
         and every later batch of that shape is copied into them and replayed.  Batches of another shape (the last,
         short one of an epoch) get their own entry."""
-        tens = {k: v for k, v in batch.items() if torch.is_tensor(v)}
-        sig = tuple(sorted((k, tuple(v.shape), v.dtype) for k, v in tens.items()))
+        tens = {k: v for k, v in batch.items() if torch.is_tensor(v) and k != "dataset_id"}
+        if static_inputs:
+            # the batch already lives in static device buffers (data.DevicePrefetcher rotates a few sets): capture the
+            # step on those addresses directly -- one graph per buffer set, no device-to-device copy per step
+            sig = tuple(sorted((k, v.data_ptr(), tuple(v.shape)) for k, v in tens.items())) + (float(loss_weight),)
+            ent = self._auto.setdefault(sig, {"seen": 0, "replay": None})
+            if ent["replay"] is None:
+                ent["seen"] += 1
+                if ent["seen"] <= eager_steps or not all(v.is_cuda for v in tens.values()):
+                    return self.train_step(tens, loss_weight)
+                ent["replay"] = self.capture(tens, warmup=0, loss_weight=loss_weight)
+            return ent["replay"]()
+        sig = tuple(sorted((k, tuple(v.shape), v.dtype) for k, v in tens.items())) + (float(loss_weight),)
         ent = self._auto.setdefault(sig, {"seen": 0, "static": None, "replay": None})
         if ent["replay"] is None:
             ent["seen"] += 1
             if ent["seen"] <= eager_steps or not all(v.is_cuda for v in tens.values()):
-                return self.train_step(batch)
+                return self.train_step(batch, loss_weight)
             ent["static"] = {k: v.clone() for k, v in tens.items()}
-            ent["replay"] = self.capture(ent["static"], warmup=0)
+            ent["replay"] = self.capture(ent["static"], warmup=0, loss_weight=loss_weight)
             # the capture pass launched nothing: fall through and replay this batch
         for k, v in tens.items():
             ent["static"][k].copy_(v, non_blocking=True)
