@@ -36,6 +36,8 @@ extern "C" {
 #define DEER_GEMM_AUTO 0   /* tcgen05 when the shape/alignment allows it, SIMT otherwise */
 #define DEER_GEMM_SIMT 1   /* fp32 CUDA-core tiles (exact fp32; small or unaligned shapes) */
 #define DEER_GEMM_TF32 2   /* tcgen05.mma kind::tf32, fp32 accumulate in TMEM, TMA-fed */
+#define DEER_GEMM_TF32X3 5 /* error-compensated 3xTF32 tensor-core tiles (fp32-grade accuracy at every M): the engine of
+                              the post-pooling fusion / head chain, see deer_gemm_x3 */
 /* LSTM recurrence engines (deer_lstm_fwd/bwd `engine`): DEER_GEMM_SIMT = exact-fp32 stepwise; DEER_GEMM_AUTO/TF32 =
  * round-1 8-CTA TF32 persistent forward kernel when H == 256 (stepwise otherwise; backward always stepwise);
  * 3 = stepwise with TF32 step GEMMs; 4 = same as AUTO.  These natural-layout entry points are the on-device reference;
@@ -275,6 +277,32 @@ int deer_step_increment(long long* step, void* stream);
 int deer_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                float eps, float weight_decay, int step, const float* sumsq, float max_norm, float grad_scale,
                const long long* step_dev, const float* lr_dev, void* stream);
+
+/* ---- fused 3xTF32 GEMM of the post-pooling chain: replaces the addmm + relu + dropout (+ their backward:
+ * threshold_backward, dropout mask multiply, bias-gradient sum) ATen calls of nn.Linear / nn.ReLU / nn.Dropout stacks in
+ * fusion.py:188-343 (AudioVisualFusion / TrimodalFusion / output_projection), deer.py:30-108,198-266 (DEERLayer,
+ * MultiDimensionalDEER), encoders.py:101-107,470-475,608-625 (output projections) and complete_project.py:61-588.
+ *   C[b] = dropout( act( opA(A_eff[b]) opB(B[b]) + bias[b] + beta*C[b] ) ),   A_eff = A (.) gatefn(gate)
+ * gate (optional, same layout as A with leading dimension ldgate): gate_mode 1 = (gate > 0 ? gate_scale : 0) -- the
+ * backward of ReLU (+ inverted dropout, gate_scale = 1/(1-p)) from the layer's saved output; 2 = (1-gate^2)*gate_scale
+ * (tanh'); 3 = gate(1-gate)*gate_scale (sigmoid').  colsum (optional, transA only): colsum[b][m] += sum_k A_eff[k,m],
+ * the bias gradient of dW = dz^T x.  Dropout: inverted, Philox stream of deer_dropout keyed by (seed, *drop_step) over the
+ * flat index row*drop_ld + b*drop_batch_stride + drop_col0 + col (drop_ld = 0 means ldc).  batch > 1: operand b at pointer + b*stride. */
+typedef struct {
+  const float* A; const float* B; float* C; const float* bias; const float* gate; float* colsum;
+  const unsigned long long* drop_step;
+  long long lda, ldb, ldc, ldgate;
+  long long sA, sB, sC, sBias, sGate, sColsum;
+  unsigned long long drop_seed, drop_offset;
+  long long drop_ld, drop_batch_stride;
+  int drop_col0;
+  int M, N, K, batch;
+  int transA, transB, act;
+  float beta, drop_p;
+  int gate_mode;
+  float gate_scale;
+} deer_gemm_x3_args;
+int deer_gemm_x3(const deer_gemm_x3_args* args, void* stream);
 
 /* ---- generic elementwise helpers used by the pooled model (complete_project.py:282-293,364,439-459) */
 /* y = a*x1 + b*x2 (x2 may be NULL) */

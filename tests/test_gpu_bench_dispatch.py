@@ -111,7 +111,7 @@ def test_train_step_b256_benchmark_dispatch_vs_fp64_oracle():
     used = {k: after[k] - before[k] for k in after}
     # the benchmarked dispatch: TF32 tcgen05 for scorers / conv taps / projections, 16-bit tcgen05 for the LSTM GEMMs
     assert used["tf32_pair"] + used["tf32"] >= 12, used
-    assert used["h16"] >= 10, used
+    assert used["h16"] >= 8, used
     assert ops.branch_streams_enabled() and B <= ops.branch_max_batch()
 
     sdg = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd64.items()}

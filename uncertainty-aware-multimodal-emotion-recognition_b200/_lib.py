@@ -17,6 +17,16 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libdeer_b200.so")
 
+class GemmX3Args(ctypes.Structure):
+    """deer_gemm_x3_args (include/deer_b200.h)."""
+    _fields_ = [("A", P), ("B", P), ("C", P), ("bias", P), ("gate", P), ("colsum", P), ("drop_step", P),
+                ("lda", L), ("ldb", L), ("ldc", L), ("ldgate", L),
+                ("sA", L), ("sB", L), ("sC", L), ("sBias", L), ("sGate", L), ("sColsum", L),
+                ("drop_seed", U), ("drop_offset", U), ("drop_ld", L), ("drop_batch_stride", L), ("drop_col0", I),
+                ("M", I), ("N", I), ("K", I), ("batch", I), ("transA", I), ("transB", I), ("act", I),
+                ("beta", F), ("drop_p", F), ("gate_mode", I), ("gate_scale", F)]
+
+
 # name -> argtypes (every function returns int unless listed in _RESTYPES)
 _PROTOS = {
     "deer_version": [],
@@ -27,6 +37,7 @@ _PROTOS = {
     "deer_set_option": [I, I],
     "deer_lstm_set_profile_buffer": [P],
     "deer_gemm": [P, L, I, P, L, I, P, L, I, I, I, P, I, F, I, L, L, L, L, I, P],
+    "deer_gemm_x3": [ctypes.POINTER(GemmX3Args), P],
     "deer_gemm_h16": [P, L, I, I, P, L, I, I, P, L, P, L, I, I, I, I, P, I, F, P],
     "deer_cast16": [P, L, P, L, L, I, I, I, P],
     "deer_gemm_h16_set_profile_buffer": [P],

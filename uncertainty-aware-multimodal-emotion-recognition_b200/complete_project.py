@@ -45,8 +45,9 @@ class ModelConfig:
     gradient_clip: float = 1.0
 
 
-def _lin(x, m: nn.Linear, act="none"):
-    return ops.linear(x, m.weight, m.bias, act)
+def _lin(x, m: nn.Linear, act="none", dropout: float = 0.0, training: bool = False):
+    """nn.Linear (+ activation) (+ nn.Dropout, fused into the GEMM epilogue on the chain engine)."""
+    return ops.linear(x, m.weight, m.bias, act, dropout=dropout, training=training)
 
 
 def _ln(x, m: nn.LayerNorm):
@@ -60,7 +61,7 @@ class ResidualBlock(nn.Module):
         self.layers = nn.Sequential(nn.Linear(dim, dim), nn.ReLU(inplace=True), nn.Dropout(dropout), nn.LayerNorm(dim))
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        h = ops.dropout(_lin(x, self.layers[0], "relu"), self.dropout, self.training)
+        h = _lin(x, self.layers[0], "relu", self.dropout, self.training)
         return ops.add(x, _ln(h, self.layers[3]))
 
 
@@ -120,7 +121,7 @@ class UncertaintyEstimator(nn.Module):
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         e = self.estimator
-        h = ops.dropout(_lin(x, e[0], "relu"), e[2].p, self.training)
+        h = _lin(x, e[0], "relu", e[2].p, self.training)
         return _lin(_lin(h, e[3], "relu"), e[5], "sigmoid")
 
 
@@ -141,7 +142,7 @@ class UncertaintyAwareAttention(nn.Module):
         ca, cv, ct = (self.cross_attention(text, z, z) for z in (audio, video, text))
         unc = torch.cat([ua, uv, ut], dim=1)
         wn = self.weight_network
-        w = ops.dropout(ops.linear([sa, sv, st, unc], wn[0].weight, wn[0].bias, "relu"), self.dropout, self.training)
+        w = ops.linear([sa, sv, st, unc], wn[0].weight, wn[0].bias, "relu", dropout=self.dropout, training=self.training)
         w = ops.softmax_rows(_lin(w, wn[3]))
         return {"audio": ops.mix(w[:, 0], unc[:, 0], sa, ca), "video": ops.mix(w[:, 1], unc[:, 1], sv, cv),
                 "text": ops.mix(w[:, 2], unc[:, 2], st, ct), "attention_weights": w, "modality_uncertainties": unc}
@@ -160,7 +161,7 @@ class HierarchicalFusionModule(nn.Module):
         self.fusion_gate = nn.Sequential(nn.Linear(fusion_dim + feature_dim, fusion_dim), nn.Sigmoid())
 
     def _stage(self, seq, xs):
-        h = ops.dropout(ops.linear(xs, seq[0].weight, seq[0].bias, "relu"), self.dropout, self.training)
+        h = ops.linear(xs, seq[0].weight, seq[0].bias, "relu", dropout=self.dropout, training=self.training)
         return _lin(_ln(h, seq[3]), seq[4], "relu")
 
     def forward(self, audio: torch.Tensor, video: torch.Tensor, text: torch.Tensor) -> torch.Tensor:
@@ -180,8 +181,8 @@ class DEERPredictionHead(nn.Module):
 
     def evidence(self, x):
         n = self.evidence_network
-        h = ops.dropout(_lin(x, n[0], "relu"), self.dropout, self.training)
-        h = ops.dropout(_lin(h, n[3], "relu"), self.dropout, self.training)
+        h = _lin(x, n[0], "relu", self.dropout, self.training)
+        h = _lin(h, n[3], "relu", self.dropout, self.training)
         return _lin(h, n[6])
 
     def forward(self, x: torch.Tensor) -> Dict[str, torch.Tensor]:
@@ -250,11 +251,10 @@ class CompleteDEERModel(nn.Module):
         nets = [self.prediction_heads[d].evidence_network for d in self.DIMS]
         p = self.config.dropout
         D = len(nets)
-        h = ops.grouped_linear([fused] * D, [n[0].weight for n in nets], [n[0].bias for n in nets], "relu")
-        h = ops.dropout(h, p, self.training)
-        h = ops.grouped_linear([h[:, g] for g in range(D)], [n[3].weight for n in nets], [n[3].bias for n in nets], "relu")
-        h = ops.dropout(h, p, self.training)
-        ev = ops.grouped_linear([h[:, g] for g in range(D)], [n[6].weight for n in nets], [n[6].bias for n in nets])
+        dr = dict(dropout=p, training=self.training)
+        h = ops.grouped_linear([fused] * D, [n[0].weight for n in nets], [n[0].bias for n in nets], "relu", **dr)
+        h = ops.grouped_linear(h, [n[3].weight for n in nets], [n[3].bias for n in nets], "relu", **dr)
+        ev = ops.grouped_linear(h, [n[6].weight for n in nets], [n[6].bias for n in nets])
         out = nig_dict(ev, ops.nig_head(ev), self.DIMS, trailing_dim=False)
         out["calibrated_uncertainty"] = self.calibration_layer(out["uncertainty_all"])
         out["attention_weights"] = att["attention_weights"]

@@ -25,6 +25,9 @@ int gemm_simt(const float* A, long long lda, int transA, const float* B, long lo
 int gemm_tcgen05(const float* A, long long lda, int transA, const float* B, long long ldb, int transB, float* C,
                  long long ldc, int M, int N, int K, const float* bias, int act, float beta, int batch, long long sA,
                  long long sB, long long sC, long long sBias, cudaStream_t stream);
+int gemm_x3_plain(const float* A, long long lda, int transA, const float* B, long long ldb, int transB, float* C,
+                  long long ldc, int M, int N, int K, const float* bias, int act, float beta, int batch, long long sA,
+                  long long sB, long long sC, long long sBias, cudaStream_t stream);
 extern int g_small_engine;
 extern int g_h16_pair;
 extern int g_nig_pipe;
@@ -137,6 +140,8 @@ int deer_gemm(const float* A, long long lda, int transA, const float* B, long lo
   DEER_CHECK_ARG(act >= 0 && act <= 3, "gemm: bad activation");
   DEER_CHECK_ARG(beta == 0.f || beta == 1.f, "gemm: beta must be 0 or 1");
   cudaStream_t st = (cudaStream_t)stream;
+  if (engine == DEER_GEMM_TF32X3)
+    return gemm_x3_plain(A, lda, transA, B, ldb, transB, C, ldc, M, N, K, bias, act, beta, batch, sA, sB, sC, sBias, st);
   if (engine == DEER_GEMM_SIMT) {
     g_engine_calls[DEER_ENGINE_SIMT]++;
     return gemm_simt(A, lda, transA, B, ldb, transB, C, ldc, M, N, K, bias, act, beta, batch, sA, sB, sC, sBias, st);

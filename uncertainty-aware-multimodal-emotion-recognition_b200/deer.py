@@ -32,8 +32,8 @@ class DEERLayer(nn.Module):
 
     def evidence(self, x):
         n = self.evidence_net
-        h = ops.dropout(ops.linear(x, n[0].weight, n[0].bias, "relu"), self.dropout, self.training)
-        h = ops.dropout(ops.linear(h, n[3].weight, n[3].bias, "relu"), self.dropout, self.training)
+        h = ops.linear(x, n[0].weight, n[0].bias, "relu", dropout=self.dropout, training=self.training)
+        h = ops.linear(h, n[3].weight, n[3].bias, "relu", dropout=self.dropout, training=self.training)
         return ops.linear(h, n[6].weight, n[6].bias).view(x.shape[0], self.output_dim, 4)
 
     def forward(self, x: torch.Tensor) -> Dict[str, torch.Tensor]:
@@ -69,16 +69,15 @@ class MultiDimensionalDEER(nn.Module):
     def evidence(self, x: torch.Tensor) -> torch.Tensor:
         """[B,input_dim] -> raw evidence [B,D,4]; the D heads run as grouped GEMMs into one buffer."""
         fp = self.feature_processor
-        f = ops.dropout(ops.linear(x, fp[0].weight, fp[0].bias, "relu"), self.dropout, self.training)
-        f = ops.dropout(ops.linear(f, fp[3].weight, fp[3].bias, "relu"), self.dropout, self.training)
+        dr = dict(dropout=self.dropout, training=self.training)    # fused into the GEMM epilogues
+        f = ops.linear(x, fp[0].weight, fp[0].bias, "relu", **dr)
+        f = ops.linear(f, fp[3].weight, fp[3].bias, "relu", **dr)
         D = self.emotion_dims
         nets = [h.evidence_net for h in self.deer_heads]
-        h1 = ops.grouped_linear([f] * D, [n[0].weight for n in nets], [n[0].bias for n in nets], "relu")
-        h1 = ops.dropout(h1, self.dropout, self.training)
-        h2 = ops.grouped_linear([h1[:, g] for g in range(D)], [n[3].weight for n in nets], [n[3].bias for n in nets],
-                                "relu")
-        h2 = ops.dropout(h2, self.dropout, self.training)
-        return ops.grouped_linear([h2[:, g] for g in range(D)], [n[6].weight for n in nets], [n[6].bias for n in nets])
+        h1 = ops.grouped_linear([f] * D, [n[0].weight for n in nets], [n[0].bias for n in nets], "relu", **dr)
+        # (a [B,D,K] tensor as input: head g reads h[:, g]; its gradient comes back as one tensor)
+        h2 = ops.grouped_linear(h1, [n[3].weight for n in nets], [n[3].bias for n in nets], "relu", **dr)
+        return ops.grouped_linear(h2, [n[6].weight for n in nets], [n[6].bias for n in nets])
 
     def forward(self, x: torch.Tensor) -> Dict[str, torch.Tensor]:
         e = self.evidence(x)

@@ -101,8 +101,7 @@ class EnhancedAudioEncoder(nn.Module):
         h_tm = self.lstm_forward(audio_input)                      # [T,B,D]
         pooled, _ = _scorer_and_pool(h_tm, self.attention, time_major=True)
         op = self.output_projection
-        y = ops.linear(pooled, op[0].weight, op[0].bias, "relu")
-        y = ops.dropout(y, self.dropout, self.training)
+        y = ops.linear(pooled, op[0].weight, op[0].bias, "relu", dropout=self.dropout, training=self.training)
         y = ops.linear(y, op[3].weight, op[3].bias)
         return ops.layer_norm(y, op[4].weight, op[4].bias, op[4].eps)
 
@@ -151,8 +150,7 @@ class EnhancedVideoEncoder(nn.Module):
         else:
             pooled = p[:, 0]
         op = self.output_projection
-        y = ops.linear(pooled, op[0].weight, op[0].bias, "relu")
-        y = ops.dropout(y, self.dropout, self.training)
+        y = ops.linear(pooled, op[0].weight, op[0].bias, "relu", dropout=self.dropout, training=self.training)
         return ops.layer_norm(y, op[3].weight, op[3].bias, op[3].eps)
 
 
@@ -199,10 +197,10 @@ class EnhancedTextEncoder(nn.Module):
         x = ops.rowscale(token_embeddings, m)
         agg, _ = _scorer_and_pool(x, self.token_attention, mask=m)
         bp, lp, op = self.bert_projection, self.linguistic_projection, self.output_projection
-        pb = ops.dropout(ops.linear(agg, bp[0].weight, bp[0].bias, "relu"), self.dropout, self.training)
-        pl = ops.dropout(ops.linear(linguistic_features, lp[0].weight, lp[0].bias, "relu"), self.dropout, self.training)
-        y = ops.linear([pb, pl], op[0].weight, op[0].bias, "relu")
-        y = ops.dropout(y, self.dropout, self.training)
+        dr = dict(dropout=self.dropout, training=self.training)
+        pb = ops.linear(agg, bp[0].weight, bp[0].bias, "relu", **dr)
+        pl = ops.linear(linguistic_features, lp[0].weight, lp[0].bias, "relu", **dr)
+        y = ops.linear([pb, pl], op[0].weight, op[0].bias, "relu", **dr)
         return ops.layer_norm(y, op[3].weight, op[3].bias, op[3].eps)
 
 

@@ -40,8 +40,7 @@ class AudioVisualFusion(nn.Module):
         a_att = ops.linear(ops.linear(vp, wv, bv), ca.out_proj.weight, ca.out_proj.bias)
         v_att = ops.linear(ops.linear(ap, wv, bv), ca.out_proj.weight, ca.out_proj.bias)
         fl = self.fusion_layers
-        y = ops.linear([a_att, v_att], fl[0].weight, fl[0].bias, "relu")
-        y = ops.dropout(y, self.dropout, self.training)
+        y = ops.linear([a_att, v_att], fl[0].weight, fl[0].bias, "relu", dropout=self.dropout, training=self.training)
         y = ops.layer_norm(y, fl[3].weight, fl[3].bias, fl[3].eps)
         ones = torch.ones((audio_features.shape[0], 1), device=audio_features.device, dtype=torch.float32)
         return {"fused_features": y, "attention_weights": {"audio_to_video": ones, "video_to_audio": ones.clone()}}
@@ -70,8 +69,7 @@ class TrimodalFusion(nn.Module):
         ctx_mean, attw = ops.mha2_core(qkv, self.num_heads)
         pooled = ops.linear(ctx_mean, ma.out_proj.weight, ma.out_proj.bias)
         ff = self.final_fusion
-        y = ops.linear(pooled, ff[0].weight, ff[0].bias, "relu")
-        y = ops.dropout(y, self.dropout, self.training)
+        y = ops.linear(pooled, ff[0].weight, ff[0].bias, "relu", dropout=self.dropout, training=self.training)
         y = ops.layer_norm(y, ff[3].weight, ff[3].bias, ff[3].eps)
         return {"fused_features": y, "attention_weights": attw}
 
@@ -131,8 +129,8 @@ class HierarchicalMultimodalFusion(nn.Module):
         av = self.audio_visual_fusion(audio_features, video_features)
         tri = self.trimodal_fusion(av["fused_features"], text_features)
         op = self.output_projection
-        y = ops.linear(tri["fused_features"], op[0].weight, op[0].bias, "relu")
-        y = ops.dropout(y, self.dropout, self.training)
+        y = ops.linear(tri["fused_features"], op[0].weight, op[0].bias, "relu", dropout=self.dropout,
+                       training=self.training)
         y = ops.layer_norm(y, op[3].weight, op[3].bias, op[3].eps)
         return {"fused_features": y, "audiovisual_features": av["fused_features"],
                 "trimodal_features": tri["fused_features"], "av_attention_weights": av["attention_weights"],

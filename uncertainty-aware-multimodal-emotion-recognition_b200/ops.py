@@ -14,7 +14,7 @@ from . import _lib
 from ._lib import call, ptr
 
 ACT = {"none": 0, None: 0, "relu": 1, "tanh": 2, "sigmoid": 3}
-ENGINE_AUTO, ENGINE_SIMT, ENGINE_TF32 = 0, 1, 2
+ENGINE_AUTO, ENGINE_SIMT, ENGINE_TF32, ENGINE_X3 = 0, 1, 2, 5
 
 # Precision policy (DESIGN.md "numerics"): the time-batched contractions (M = B*T rows: LSTM input projections,
 # pooling scorers, Conv1d taps) and every backward GEMM run on the tcgen05 TF32 engine; the FORWARD of the small
@@ -26,7 +26,7 @@ ENGINE_AUTO, ENGINE_SIMT, ENGINE_TF32 = 0, 1, 2
 _state = {"engine": ENGINE_AUTO, "lstm_engine": ENGINE_AUTO, "exact_small_fwd": True, "exact_small_bwd": True,
           "small_rows": 8192, "direct_grad": False, "lstm_gemm16": True, "fuse_lstm_dropout": True,
           "branch_streams": True, "lstm_pre16": True, "defer_wgrad": True,
-          "branch_max_batch": 512, "scorer_pool_fused": True, "grouped_batched": True}
+          "branch_max_batch": 512, "scorer_pool_fused": True, "grouped_batched": True, "exact_engine": ENGINE_X3}
 
 
 def set_grouped_batched(on: bool):
@@ -186,7 +186,7 @@ def set_exact_small_forward(on: bool, small_rows: int = 8192, backward: Optional
 def _bwd_engine(M: int, chain: bool = False):
     """Engine for a backward GEMM of an nn.Linear with M rows; `chain`: see _fwd_engine."""
     if _state["engine"] == ENGINE_AUTO and _state["exact_small_bwd"] and (chain or M < _state["small_rows"]):
-        return ENGINE_SIMT
+        return _state["exact_engine"]
     return None
 
 
@@ -196,8 +196,21 @@ def _fwd_engine(M: int, chain: bool = False):
     on the row count, so outputs do not change discontinuously with the batch.  Time-batched contractions (M = B*T
     rows: scorers, Conv1d taps, projections) use the TF32 tensor-core engine once M reaches `small_rows`."""
     if _state["engine"] == ENGINE_AUTO and _state["exact_small_fwd"] and (chain or M < _state["small_rows"]):
-        return ENGINE_SIMT
+        return _state["exact_engine"]
     return None
+
+
+def set_exact_engine(engine: int):
+    """Engine of the fp32-grade contractions: ENGINE_X3 (default: error-compensated 3xTF32 tensor-core tiles with fused
+    bias / activation / dropout / backward-gate / bias-gradient) or ENGINE_SIMT (fp32 FFMA tiles, separate elementwise
+    kernels: the round-1 path, kept as the on-device reference)."""
+    _state["exact_engine"] = int(engine)
+
+
+def _fused_chain() -> bool:
+    """The fused 3xTF32 Linear nodes are in use (default policy, no forced engine)."""
+    return (_state["engine"] == ENGINE_AUTO and _state["exact_small_fwd"] and _state["exact_small_bwd"] and
+            _state["exact_engine"] == ENGINE_X3)
 
 
 def _req(t: torch.Tensor, name: str):
@@ -246,6 +259,40 @@ def gemm_h16(A, lda, transA, B, ldb, transB, C, ldc, M, N, K, *, a_bf16=False, b
     call("deer_gemm_h16", _p16(A), lda, int(transA), int(a_bf16), _p16(B), ldb, int(transB), int(b_bf16),
          None if C is None else _p16(C), ldc, None if C16 is None else _p16(C16), ldc16, int(c16_bf16), M, N, K,
          ptr(bias), act, float(beta))
+
+
+def gemm_x3(A, lda, transA, B, ldb, transB, C, ldc, M, N, K, *, bias=None, act=0, beta=0.0, batch=1, sA=0, sB=0, sC=0,
+            sBias=0, gate=None, ldgate=0, gate_mode=0, gate_scale=1.0, sGate=0, colsum=None, sColsum=0, drop=None,
+            drop_ld=0, drop_col0=0, drop_batch_stride=0):
+    """deer_gemm_x3: fused 3xTF32 GEMM (include/deer_b200.h).  Pointers or fp32 CUDA tensors; `drop` = (p, seed, offset,
+    step tensor or None)."""
+    def P(t):
+        return None if t is None else (ptr(t) if isinstance(t, torch.Tensor) else int(t))
+    a = _lib.GemmX3Args()
+    a.A, a.B, a.C, a.bias, a.gate, a.colsum = P(A), P(B), P(C), P(bias), P(gate), P(colsum)
+    a.lda, a.ldb, a.ldc, a.ldgate = int(lda), int(ldb), int(ldc), int(ldgate)
+    a.sA, a.sB, a.sC, a.sBias, a.sGate, a.sColsum = int(sA), int(sB), int(sC), int(sBias), int(sGate), int(sColsum)
+    if drop is not None and drop[0] > 0.0:
+        a.drop_p, a.drop_seed, a.drop_offset = float(drop[0]), int(drop[1]), int(drop[2])
+        a.drop_step = P(drop[3])
+    a.drop_ld, a.drop_col0, a.drop_batch_stride = int(drop_ld), int(drop_col0), int(drop_batch_stride)
+    a.M, a.N, a.K, a.batch = int(M), int(N), int(K), int(batch)
+    a.transA, a.transB, a.act = int(transA), int(transB), int(act)
+    a.beta = float(beta)
+    a.gate_mode, a.gate_scale = int(gate_mode), float(gate_scale)
+    _lib.check(_lib.load().deer_gemm_x3(a, _lib.stream()), "deer_gemm_x3")
+
+
+_GATE_MODE = {1: 1, 2: 2, 3: 3}   # activation code -> gate mode (derivative from the saved output)
+
+
+def _take_dropout(numel: int, p: float, training: bool):
+    """Reserve the Philox block range of one dropout application: (p, seed, offset, step tensor) or None."""
+    if not training or p <= 0.0:
+        return None
+    off = _dropout_state["offset"]
+    _dropout_state["offset"] = off + (numel + 3) // 4
+    return (float(p), _dropout_seed(), off, _dropout_state["step"])
 
 
 def _colw(w: torch.Tensor, k0: int, k1: int):
@@ -334,9 +381,106 @@ class _Linear(torch.autograd.Function):
         return (None if dw_direct else dw, None if db_direct else db, None, None, *dxs)
 
 
-def linear(x, w, b=None, act="none"):
+class _LinearX3(torch.autograd.Function):
+    """y = dropout(act(sum_i x_i W[:, blk_i]^T + b)) as ONE launch per input block, backward as two launches per block:
+    the fused 3xTF32 engine (csrc/gemm_x3.cu) applies bias / activation / inverted dropout in the epilogue, the
+    ReLU-and-dropout (or tanh / sigmoid) derivative while it reads dy ("gate" from the saved output: d > 0 <=> the unit
+    was active AND kept), and the bias gradient as the column sums of the gated dy inside the dW GEMM."""
+
+    @staticmethod
+    def forward(ctx, w, b, act, drop, n_in, *xs):
+        _req(w, "weight")
+        N, Ktot = w.shape
+        rows = []
+        k0 = 0
+        y = None
+        lead = xs[0].shape[:-1]
+        for i, x in enumerate(xs):
+            x2, M, K, ld = _rows2d(_req(x, "input"))
+            if y is None:
+                y = torch.empty((M, N), device=w.device, dtype=torch.float32)
+            last = i == len(xs) - 1
+            gemm_x3(x2, ld, 0, w.data_ptr() + 4 * k0, w.stride(0), 1, y, N, M, N, K, bias=b if last else None,
+                    act=act if last else 0, beta=0.0 if i == 0 else 1.0, drop=drop if last else None)
+            rows.append((x2, ld, k0, K))
+            k0 += K
+        assert k0 == Ktot, f"input widths {k0} != weight in-features {Ktot}"
+        ctx.act = act
+        ctx.drop_p = drop[0] if drop is not None else 0.0
+        ctx.has_bias = b is not None
+        ctx.params = (w, b)
+        ctx.meta = [(ld, k, K) for (_, ld, k, K) in rows]
+        ctx.in_shapes = [x.shape for x in xs]
+        ctx.save_for_backward(w, y if (act != 0 or ctx.drop_p > 0.0) else None, *[r[0] for r in rows])
+        return y.view(*lead, N)
+
+    @staticmethod
+    def backward(ctx, dy):
+        w, y, *xs = ctx.saved_tensors
+        N, Ktot = w.shape
+        dy2, M, _, ld_dy = _rows2d(dy if dy.is_contiguous() else dy.contiguous())
+        pw, pb = ctx.params
+        gate, gmode, gscale = None, 0, 1.0
+        if y is not None:
+            gate, gmode = y, _GATE_MODE[ctx.act]
+            gscale = 1.0 / (1.0 - ctx.drop_p) if ctx.drop_p > 0.0 else 1.0
+        need_db = ctx.has_bias and ctx.needs_input_grad[1]
+        need_dw = ctx.needs_input_grad[0]
+        db, db_direct = _acc(pb) if need_db else (None, False)
+        dw, dw_direct = _acc(pw) if need_dw else (None, False)
+        if need_db and not need_dw:        # (not on the model's path: the bias gradient rides on the dW GEMM)
+            dz = torch.empty_like(dy2)
+            call("deer_bias_act_bwd", ptr(dy2), ld_dy, ptr(y), N, ptr(dz), N, ptr(db), M, N, ctx.act)
+        defer = (dw is not None and dw_direct and (db is None or db_direct) and _state["defer_wgrad"] and
+                 M < _state["small_rows"])
+        dxs = []
+        for i, x2 in enumerate(xs):
+            ld, k0, K = ctx.meta[i]
+            if ctx.needs_input_grad[5 + i]:
+                dx = torch.empty((M, K), device=w.device, dtype=torch.float32)
+                gemm_x3(dy2, ld_dy, 0, w.data_ptr() + 4 * k0, w.stride(0), 0, dx, K, M, K, N, gate=gate, ldgate=N,
+                        gate_mode=gmode, gate_scale=gscale)
+                dxs.append(dx.view(ctx.in_shapes[i]))
+            else:
+                dxs.append(None)
+
+        def wgrads():
+            for i, x2 in enumerate(xs):
+                ld, k0, K = ctx.meta[i]
+                gemm_x3(dy2, ld_dy, 1, x2, ld, 0, dw.data_ptr() + 4 * k0, Ktot, N, K, M, beta=1.0, gate=gate, ldgate=N,
+                        gate_mode=gmode, gate_scale=gscale, colsum=db if (i == 0 and need_db) else None)
+
+        if dw is not None:
+            if defer:
+                # trainer mode: dW (+ db) is not needed before the optimizer, so it leaves the dy -> dx critical path and
+                # runs on the weight-gradient stream beside the next layers' dx GEMMs (joined before the exchange)
+                cur = torch.cuda.current_stream()
+                aux = _wgrad_stream()
+                aux.wait_stream(cur)
+                with torch.cuda.stream(aux):
+                    wgrads()
+                    for x2 in xs:
+                        x2.record_stream(aux)
+                dy2.record_stream(aux)
+                if gate is not None:
+                    gate.record_stream(aux)
+                _wgrad["pending"] = True
+            else:
+                wgrads()
+        return (None if dw_direct else dw, None if db_direct else db, None, None, None, *dxs)
+
+
+def linear(x, w, b=None, act="none", dropout: float = 0.0, training: bool = False):
+    """nn.Linear (+ activation) (+ nn.Dropout) on x, or on the virtual concatenation of a list of inputs.  Post-pooling
+    layers (2-D inputs: one row per sample) run as one fused 3xTF32 launch (`_LinearX3`) under the default policy;
+    time-batched layers and forced engines take the generic node with separate elementwise kernels."""
     xs = x if isinstance(x, (list, tuple)) else [x]
-    return _Linear.apply(w, b, ACT[act], len(xs), *xs)
+    a = ACT[act]
+    if xs[0].dim() == 2 and _fused_chain() and (dropout <= 0.0 or not training or a == 1):
+        drop = _take_dropout(xs[0].shape[0] * w.shape[0], dropout, training)
+        return _LinearX3.apply(w, b, a, drop, len(xs), *xs)
+    y = _Linear.apply(w, b, a, len(xs), *xs)
+    return _apply_dropout(y, dropout, training)
 
 
 # ----------------------------------------------------------------------------------------------- LayerNorm
@@ -433,6 +577,9 @@ def dropout(x, p: float, training: bool):
     off = _dropout_state["offset"]
     _dropout_state["offset"] = off + (x.numel() + 3) // 4
     return _Dropout.apply(x, p, _dropout_seed(), off)
+
+
+_apply_dropout = dropout
 
 
 # ----------------------------------------------------------------------------------------------- attention pooling
@@ -1235,9 +1382,174 @@ class _GroupedLinear(torch.autograd.Function):
         return (None, None, *dws, *dbs, *dxs)
 
 
-def grouped_linear(xs: Sequence[torch.Tensor], ws: Sequence[torch.Tensor], bs: Sequence[torch.Tensor], act="none"):
+class _GroupedLinearX3(torch.autograd.Function):
+    """out[:, g, :] = dropout(act(x_g W_g^T + b_g)), out [M,G,N], on the fused 3xTF32 engine: one batched launch when the
+    groups' operands are evenly spaced (per-head layers laid out back to back in the trainer's flat buffers), one launch
+    per group otherwise.  Backward: gate (activation / dropout derivative from the saved output) and bias gradients
+    inside the GEMMs; groups that share one input accumulate ONE input gradient (no per-group temporaries + adds)."""
+
+    @staticmethod
+    def forward(ctx, act, drop, G, sliced, *args):
+        ws, bs, xs = args[:G], args[G:2 * G], args[2 * G:]
+        N = ws[0].shape[0]
+        if sliced:      # ONE input [M,G,K]: group g reads x[:, g] (its gradient comes back as one [M,G,K] tensor)
+            x3 = _req(xs[0], "input").contiguous()
+            ctx.sliced_shape = x3.shape
+            xs = [x3[:, g] for g in range(G)]
+        ctx.sliced = bool(sliced)
+        rows = [_rows2d(_req(x, "input")) for x in xs]
+        M = rows[0][1]
+        out = torch.empty((M, G, N), device=ws[0].device, dtype=torch.float32)
+        same = (all(r[2] == rows[0][2] and r[3] == rows[0][3] for r in rows) and
+                all(w.shape == ws[0].shape and w.stride(0) == ws[0].stride(0) for w in ws) and
+                all(b is not None for b in bs))
+        sx = sw = sb = None
+        if same and G > 1 and _state["grouped_batched"]:
+            xp = [r[0].data_ptr() for r in rows]
+            sx = 0 if all(q == xp[0] for q in xp) else _uniform_stride(xp)
+            wp = [w.data_ptr() for w in ws]
+            sw = 0 if all(q == wp[0] for q in wp) else _uniform_stride(wp)
+            bp = [b.data_ptr() for b in bs]
+            sb = 0 if all(q == bp[0] for q in bp) else _uniform_stride(bp)
+        batched = sx is not None and sw is not None and sb is not None
+        if batched:
+            x2, _, K, ld = rows[0]
+            gemm_x3(x2, ld, 0, ws[0], ws[0].stride(0), 1, out, G * N, M, N, K, bias=bs[0], act=act, batch=G, sA=sx, sB=sw,
+                    sC=N, sBias=sb, drop=drop, drop_ld=G * N, drop_batch_stride=N)
+        else:
+            for g in range(G):
+                x2, _, K, ld = rows[g]
+                gemm_x3(x2, ld, 0, ws[g], ws[g].stride(0), 1, out.data_ptr() + 4 * g * N, G * N, M, N, K, bias=bs[g],
+                        act=act, drop=drop, drop_ld=G * N, drop_col0=g * N)
+        ctx.batched = (sx, sw) if batched else None
+        ctx.act, ctx.G = act, G
+        ctx.drop_p = drop[0] if drop is not None else 0.0
+        ctx.params = (ws, bs)
+        ctx.meta = [(r[3], r[2]) for r in rows]
+        ctx.in_shapes = [x.shape for x in xs]
+        ctx.save_for_backward(out if (act != 0 or ctx.drop_p > 0.0) else None, *ws, *[r[0] for r in rows])
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        G, act = ctx.G, ctx.act
+        saved = ctx.saved_tensors
+        out, ws, xs = saved[0], saved[1:1 + G], saved[1 + G:]
+        dout = dout.contiguous()
+        M, _, N = dout.shape
+        dev = dout.device
+        pws, pbs = ctx.params
+        gmode = _GATE_MODE[act] if out is not None else 0
+        gscale = 1.0 / (1.0 - ctx.drop_p) if ctx.drop_p > 0.0 else 1.0
+        LD = G * N
+        need_w = [ctx.needs_input_grad[4 + g] for g in range(G)]
+        need_b = [ctx.needs_input_grad[4 + G + g] for g in range(G)]
+        need_x = [ctx.needs_input_grad[4 + 2 * G + (0 if ctx.sliced else g)] for g in range(G)]
+        # ---- weight (+ bias) gradients
+        dws, dbs = [None] * G, [None] * G
+        w_acc = [_acc(pws[g]) if need_w[g] else (None, False) for g in range(G)]
+        b_acc = [_acc(pbs[g]) if need_b[g] else (None, False) for g in range(G)]
+        shared_w = all(w.data_ptr() == ws[0].data_ptr() for w in ws)   # one weight used by every group (packed in_proj)
+        if shared_w and G > 1:
+            # the contributions of the groups accumulate into ONE gradient buffer, one after the other
+            w_acc = [w_acc[0]] * G
+            b_acc = [b_acc[0]] * G
+        done_batched = False
+        if ctx.batched is not None and all(need_w) and all(need_b) and not shared_w:
+            sx, sw = ctx.batched
+            ld, K = ctx.meta[0]
+            sdw = _uniform_stride([a[0].data_ptr() for a in w_acc])
+            sdb = _uniform_stride([a[0].data_ptr() for a in b_acc])
+            if sdw and sdb:
+                gemm_x3(dout, LD, 1, xs[0], ld, 0, w_acc[0][0], K, N, K, M, beta=1.0, batch=G, sA=N, sB=sx, sC=sdw,
+                        gate=out, ldgate=LD, gate_mode=gmode, gate_scale=gscale, sGate=N, colsum=b_acc[0][0],
+                        sColsum=sdb)
+                done_batched = True
+        if not done_batched:
+            for g in range(G):
+                if not need_w[g]:
+                    continue
+                ld, K = ctx.meta[g]
+                off = 4 * g * N
+                gemm_x3(dout.data_ptr() + off, LD, 1, xs[g], ld, 0, w_acc[g][0], K, N, K, M, beta=1.0,
+                        gate=None if out is None else out.data_ptr() + off, ldgate=LD, gate_mode=gmode,
+                        gate_scale=gscale, colsum=b_acc[g][0] if need_b[g] else None)
+        for g in range(G):
+            if shared_w and g > 0:
+                continue
+            dws[g] = None if (w_acc[g][0] is None or w_acc[g][1]) else w_acc[g][0]
+            dbs[g] = None if (b_acc[g][0] is None or b_acc[g][1]) else b_acc[g][0]
+        # ---- input gradients
+        dxs = [None] * G
+        shared_x = G > 1 and all(x.data_ptr() == xs[0].data_ptr() for x in xs) and all(m == ctx.meta[0] for m in ctx.meta)
+        if ctx.sliced:
+            dx_full = None
+            if need_x[0]:
+                K = ctx.meta[0][1]
+                dx_full = torch.empty((M, G, K), device=dev, dtype=torch.float32)
+                swp = _uniform_stride([w.data_ptr() for w in ws]) if not shared_w else 0
+                if swp is not None and all(w.stride(0) == ws[0].stride(0) for w in ws):
+                    gemm_x3(dout, LD, 0, ws[0], ws[0].stride(0), 0, dx_full, G * K, M, K, N, batch=G, sA=N, sB=swp, sC=K,
+                            gate=out, ldgate=LD, gate_mode=gmode, gate_scale=gscale, sGate=N)
+                else:
+                    for g in range(G):
+                        off = 4 * g * N
+                        gemm_x3(dout.data_ptr() + off, LD, 0, ws[g], ws[g].stride(0), 0, dx_full.data_ptr() + 4 * g * K,
+                                G * K, M, K, N, gate=None if out is None else out.data_ptr() + off, ldgate=LD,
+                                gate_mode=gmode, gate_scale=gscale)
+            return (None, None, None, None, *dws, *dbs, dx_full)
+        if any(need_x):
+            if shared_x:
+                # one input feeds every group: dx = sum_g dz_g W_g -- a single contraction over K = G*N when the weights
+                # are stacked back to back, otherwise accumulated group by group into the same buffer
+                ld, K = ctx.meta[0]
+                dx = torch.empty((M, K), device=dev, dtype=torch.float32)
+                swp = _uniform_stride([w.data_ptr() for w in ws])
+                if swp == N * ws[0].stride(0) and all(w.stride(0) == ws[0].stride(0) for w in ws):
+                    gemm_x3(dout, LD, 0, ws[0], ws[0].stride(0), 0, dx, K, M, K, G * N, gate=out, ldgate=LD,
+                            gate_mode=gmode, gate_scale=gscale)
+                else:
+                    for g in range(G):
+                        off = 4 * g * N
+                        gemm_x3(dout.data_ptr() + off, LD, 0, ws[g], ws[g].stride(0), 0, dx, K, M, K, N,
+                                beta=0.0 if g == 0 else 1.0, gate=None if out is None else out.data_ptr() + off,
+                                ldgate=LD, gate_mode=gmode, gate_scale=gscale)
+                dxs[0] = dx.view(ctx.in_shapes[0])
+            elif ctx.batched is not None and all(need_x):
+                sx, sw = ctx.batched
+                ld, K = ctx.meta[0]
+                dxa = torch.empty((G, M, K), device=dev, dtype=torch.float32)
+                gemm_x3(dout, LD, 0, ws[0], ws[0].stride(0), 0, dxa, K, M, K, N, batch=G, sA=N, sB=sw, sC=M * K, gate=out,
+                        ldgate=LD, gate_mode=gmode, gate_scale=gscale, sGate=N)
+                dxs = [dxa[g].view(ctx.in_shapes[g]) for g in range(G)]
+            else:
+                for g in range(G):
+                    if not need_x[g]:
+                        continue
+                    ld, K = ctx.meta[g]
+                    off = 4 * g * N
+                    dx = torch.empty((M, K), device=dev, dtype=torch.float32)
+                    gemm_x3(dout.data_ptr() + off, LD, 0, ws[g], ws[g].stride(0), 0, dx, K, M, K, N,
+                            gate=None if out is None else out.data_ptr() + off, ldgate=LD, gate_mode=gmode,
+                            gate_scale=gscale)
+                    dxs[g] = dx.view(ctx.in_shapes[g])
+        return (None, None, None, None, *dws, *dbs, *dxs)
+
+
+def grouped_linear(xs: Sequence[torch.Tensor], ws: Sequence[torch.Tensor], bs: Sequence[torch.Tensor], act="none",
+                   dropout: float = 0.0, training: bool = False):
+    """Per-group nn.Linear (+ activation) (+ nn.Dropout) into one [M,G,N] buffer (the D heads of the NIG head; the packed
+    q|k|v projection of the two fusion tokens)."""
     G = len(ws)
-    return _GroupedLinear.apply(ACT[act], G, *ws, *bs, *xs)
+    a = ACT[act]
+    sliced = isinstance(xs, torch.Tensor)      # one [M,G,K] tensor: group g reads xs[:, g]
+    if _fused_chain() and all(b is not None for b in bs) and (dropout <= 0.0 or not training or a == 1):
+        M = xs.shape[0] if sliced else xs[0].numel() // xs[0].shape[-1]
+        drop = _take_dropout(M * G * ws[0].shape[0], dropout, training)
+        return _GroupedLinearX3.apply(a, drop, G, sliced, *ws, *bs, *([xs] if sliced else xs))
+    if sliced:
+        xs = [xs[:, g] for g in range(G)]
+    return _apply_dropout(_GroupedLinear.apply(a, G, *ws, *bs, *xs), dropout, training)
 
 
 # ----------------------------------------------------------------------------------------------- NIG head + losses
