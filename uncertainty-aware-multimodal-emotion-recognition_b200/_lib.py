@@ -38,6 +38,8 @@ _PROTOS = {
     "deer_lstm_set_profile_buffer": [P],
     "deer_gemm": [P, L, I, P, L, I, P, L, I, I, I, P, I, F, I, L, L, L, L, I, P],
     "deer_gemm_x3": [ctypes.POINTER(GemmX3Args), P],
+    "deer_gemm_h16_split": [P, P, L, I, P, P, L, I, P, L, I, I, I, P, I, P],
+    "deer_cast_split16": [P, L, P, P, L, L, I, I, P],
     "deer_gemm_h16": [P, L, I, I, P, L, I, I, P, L, P, L, I, I, I, I, P, I, F, P],
     "deer_cast16": [P, L, P, L, L, I, I, I, P],
     "deer_gemm_h16_set_profile_buffer": [P],
@@ -134,7 +136,7 @@ def launch_count() -> int:
     return int(load().deer_launch_count())
 
 
-ENGINE_NAMES = {1: "simt", 2: "tf32", 3: "tf32_pair", 4: "h16", 5: "tf32x3"}
+ENGINE_NAMES = {1: "simt", 2: "tf32", 3: "tf32_pair", 4: "h16", 5: "tf32x3", 6: "h16_split"}
 
 
 def engine_counts() -> dict:

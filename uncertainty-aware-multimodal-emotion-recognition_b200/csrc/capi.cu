@@ -32,6 +32,7 @@ extern int g_small_engine;
 extern int g_h16_pair;
 extern int g_nig_pipe;
 extern int g_lstm_dual;
+extern int g_lstm_keep16;
 extern int g_lstm_colsplit;
 extern int g_tf32_pair;
 bool gemm_tf32_pair_supported(int transA, int transB, int M, int N, int K, long long ldc, const float* bias, int act,
@@ -102,6 +103,9 @@ int deer_set_option(int option, int value) {
       return DEER_OK;
     case DEER_OPT_LSTM_DUAL:
       g_lstm_dual = value;
+      return DEER_OK;
+    case DEER_OPT_LSTM_KEEP16:
+      g_lstm_keep16 = value ? 1 : 0;
       return DEER_OK;
     case DEER_OPT_NIG_PIPELINE:
       g_nig_pipe = value ? 1 : 0;

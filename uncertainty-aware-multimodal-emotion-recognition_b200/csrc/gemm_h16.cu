@@ -49,6 +49,8 @@ struct Params {
   uint32_t idesc;
   long long* prof;      // optional per-role wait/busy cycle counters of block 0 (debug), else null
   int debug;            // bit 0: skip the fp32 stores (timing experiments only)
+  int kb_phase;         // split-precision mode (pair kernel): k-blocks of ONE pass over K; the k loop makes three passes
+                        // (A_hi,B_hi), (A_lo,B_hi), (A_hi,B_lo) over the hi / lo operand maps.  0: plain GEMM
 };
 #define H16_T0() const long long _t0 = p.prof ? clock64() : 0
 #define H16_ACC(slot)                                                   \
@@ -398,7 +400,8 @@ __device__ __forceinline__ void red_add_v2(float* p, float a, float b) {
 template <int ELEM, bool A_MN, bool B_MN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
     gemm_h16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                         const __grid_constant__ CUtensorMap tmap_c, const Params p) {
+                         const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_a2,
+                         const __grid_constant__ CUtensorMap tmap_b2, const Params p) {
   DEER_PDL_ENTRY();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -418,13 +421,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
   constexpr int MN_KSTEP = (ELEM == 2 ? 16 : 8) * 128;   // bytes per MMA K step in an MN-major panel
   constexpr int MN_SBO = ELEM == 2 ? 1024 : 512;
   constexpr int MN_LAYOUT = ELEM == 2 ? 2 : 1;
-  const int total_kb = (p.K + BKE - 1) / BKE;
+  // split precision (p.kb_phase > 0): every operand is a pair of FP16 matrices x = hi + lo (hi = fp16(x), lo =
+  // fp16(x - hi): 22 significant bits); the k loop runs three passes over K accumulating A_hi B_hi + A_lo B_hi +
+  // A_hi B_lo in the fp32 TMEM accumulator -- fp32-grade products at 3 MMAs on the 16-bit tensor rate
+  const int total_kb = p.kb_phase > 0 ? 3 * p.kb_phase : (p.K + BKE - 1) / BKE;
   const int total_work = p.tiles_m * p.tiles_n * p.splits;   // tiles_m counts 256-row pair tiles here
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
     prefetch_tmap(&tmap_c);
+    if (p.kb_phase > 0) {
+      prefetch_tmap(&tmap_a2);
+      prefetch_tmap(&tmap_b2);
+    }
     for (int s = 0; s < P_STAGES; s++) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -465,21 +475,30 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
         if (leader) {
           uint8_t* sa = smem + s * P_STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
-          const int k0 = (kb0 + i) * BKE;
+          int kbi = kb0 + i;
+          const CUtensorMap* ta = &tmap_a;
+          const CUtensorMap* tb = &tmap_b;
+          if (p.kb_phase > 0) {                     // pass 0: (hi, hi), pass 1: (lo, hi), pass 2: (hi, lo)
+            const int pass = kbi / p.kb_phase;
+            kbi -= pass * p.kb_phase;
+            if (pass == 1) ta = &tmap_a2;
+            if (pass == 2) tb = &tmap_b2;
+          }
+          const int k0 = kbi * BKE;
           if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * P_STAGE_BYTES);   // both CTAs' bytes land on this barrier
           if (!A_MN) {
-            tma_load_2d_pair(sa, &tmap_a, &full_bar[s], k0, mr);            // box {BKE k, 128 rows}
+            tma_load_2d_pair(sa, ta, &full_bar[s], k0, mr);                 // box {BKE k, 128 rows}
           } else {
 #pragma unroll
             for (int j = 0; j < BM / MNB; j++)                               // boxes {MNB m, BKE k}
-              tma_load_2d_pair(sa + j * MNB_BYTES, &tmap_a, &full_bar[s], mr + MNB * j, k0);
+              tma_load_2d_pair(sa + j * MNB_BYTES, ta, &full_bar[s], mr + MNB * j, k0);
           }
           if (!B_MN) {
-            tma_load_2d_pair(sb, &tmap_b, &full_bar[s], k0, nr);            // box {BKE k, 128 rows}
+            tma_load_2d_pair(sb, tb, &full_bar[s], k0, nr);                 // box {BKE k, 128 rows}
           } else {
 #pragma unroll
             for (int j = 0; j < (BN / 2) / MNB; j++)                         // boxes {MNB n, BKE k}
-              tma_load_2d_pair(sb + j * MNB_BYTES, &tmap_b, &full_bar[s], nr + MNB * j, k0);
+              tma_load_2d_pair(sb + j * MNB_BYTES, tb, &full_bar[s], nr + MNB * j, k0);
           }
         }
         __syncwarp();
@@ -738,14 +757,33 @@ static long long* g_h16_prof = nullptr;
 int g_h16_pair = 1;   // 1 (default): cta_group::2 CTA-pair kernel when M > 128; 0: single-CTA kernel (DEER_OPT_H16_PAIR)
 void gemm_h16_set_profile(long long* buf) { g_h16_prof = buf; }
 
+int gemm_h16_ex(const void* A, const void* A_lo, long long lda, int transA, int a_bf, const void* B, const void* B_lo,
+                long long ldb, int transB, int b_bf, float* C, long long ldc, void* C16, long long ldc16, int c16_bf, int M,
+                int N, int K, const float* bias, int act, float beta, cudaStream_t stream);
 int gemm_h16(const void* A, long long lda, int transA, int a_bf, const void* B, long long ldb, int transB, int b_bf,
              float* C, long long ldc, void* C16, long long ldc16, int c16_bf, int M, int N, int K, const float* bias,
              int act, float beta, cudaStream_t stream) {
+  return gemm_h16_ex(A, nullptr, lda, transA, a_bf, B, nullptr, ldb, transB, b_bf, C, ldc, C16, ldc16, c16_bf, M, N, K,
+                     bias, act, beta, stream);
+}
+
+// A_lo / B_lo non-NULL: split-precision product (A + A_lo)(B + B_lo) ~ A B + A_lo B + A B_lo on FP16 hi / lo operand
+// pairs (CTA-pair kernel only; beta = 0)
+int gemm_h16_ex(const void* A, const void* A_lo, long long lda, int transA, int a_bf, const void* B, const void* B_lo,
+                long long ldb, int transB, int b_bf, float* C, long long ldc, void* C16, long long ldc16, int c16_bf, int M,
+                int N, int K, const float* bias, int act, float beta, cudaStream_t stream) {
   using namespace h16;
+  const bool split = A_lo != nullptr;
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   // output: fp32 C, or (C == NULL) a 16-bit C16 alone -- the CTA-pair kernel's 64-column store tiles
   const bool out16 = C == nullptr && C16 != nullptr;
   if (out16) ldc = ldc16;
+  if (split && (B_lo == nullptr || a_bf || b_bf || beta != 0.f || !al16(A_lo) || !al16(B_lo) ||
+                !(g_h16_pair && M > BM && (N & 1) == 0 && (ldc & 1) == 0))) {
+    set_error("gemm_h16: the split-precision product needs FP16 hi/lo pairs for both operands, beta = 0 and the CTA-pair "
+              "kernel (M > 128, even N)");
+    return DEER_ERR_UNSUPPORTED;
+  }
   if (!al16(A) || !al16(B) || !al16(C) || (lda & 7) || (ldb & 7) || (!out16 && (ldc & 3)) || (bias && !al16(bias)) ||
       (C16 && (!al16(C16) || (ldc16 & 7)))) {
     set_error("gemm_h16: operands must be 16-byte aligned with leading dimensions that are multiples of 16 bytes");
@@ -778,9 +816,19 @@ int gemm_h16(const void* A, long long lda, int transA, int a_bf, const void* B, 
       return DEER_ERR_UNSUPPORTED;
     }
   }
+  CUtensorMap ma2 = ma, mb2 = mb;
+  if (split) {   // the lo operands: same geometry as their hi partners
+    bool ok2 = transA ? make_map16(&ma2, A_lo, 0, K, M, lda, 64, BK) : make_map16(&ma2, A_lo, 0, M, K, lda, BK, BM);
+    ok2 = ok2 && (transB ? make_map16(&mb2, B_lo, 0, N, K, ldb, BK, BN / 2) : make_map16(&mb2, B_lo, 0, K, N, ldb, 64, BK));
+    if (!ok2) {
+      set_error("gemm_h16: cuTensorMapEncodeTiled failed for the lo operands");
+      return DEER_ERR_UNSUPPORTED;
+    }
+  }
   const int tile_rows = pair ? 2 * BM : BM;
   const int tiles_m = (M + tile_rows - 1) / tile_rows, tiles_n = (N + BN - 1) / BN;
-  const int total_kb = (K + BK - 1) / BK;
+  const int kb_phase = (K + BK - 1) / BK;
+  const int total_kb = split ? 3 * kb_phase : kb_phase;
   int splits = 1;
   if (beta == 1.f && act == DEER_ACT_NONE && C16 == nullptr) {
     const int tiles = tiles_m * tiles_n;
@@ -798,7 +846,8 @@ int gemm_h16(const void* A, long long lda, int transA, int a_bf, const void* B, 
   const uint32_t idesc = (1u << 4) | ((uint32_t)(a_bf ? 1 : 0) << 7) | ((uint32_t)(b_bf ? 1 : 0) << 10) |
                          ((uint32_t)(transA ? 1 : 0) << 15) | ((uint32_t)(transB ? 0 : 1) << 16) |
                          ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(tile_rows >> 4) << 24);
-  Params p{C, ldc, C16, ldc16, c16_bf, bias, M, N, K, act, beta, splits, per, tiles_m, tiles_n, idesc, g_h16_prof, getenv("DEER_H16_DEBUG") ? atoi(getenv("DEER_H16_DEBUG")) : 0};
+  Params p{C, ldc, C16, ldc16, c16_bf, bias, M, N, K, act, beta, splits, per, tiles_m, tiles_n, idesc, g_h16_prof,
+           getenv("DEER_H16_DEBUG") ? atoi(getenv("DEER_H16_DEBUG")) : 0, split ? kb_phase : 0};
   const int work = tiles_m * tiles_n * splits;
   if (pair) {
     const int clusters = work < kNumSMs / 2 ? work : kNumSMs / 2;
@@ -811,7 +860,7 @@ int gemm_h16(const void* A, long long lda, int transA, int a_bf, const void* B, 
       if (e != cudaSuccess) return cuda_status(e, "gemm_h16 pair smem attribute");                                   \
       attr = true;                                                                                                   \
     }                                                                                                                \
-    DEER_LAUNCH((gemm_h16_pair_kernel<2, AM, BMN>), 2 * clusters, NUM_THREADS, P_SMEM_BYTES, stream, ma, mb, mc, p);    \
+    DEER_LAUNCH((gemm_h16_pair_kernel<2, AM, BMN>), 2 * clusters, NUM_THREADS, P_SMEM_BYTES, stream, ma, mb, mc, ma2, mb2, p);     \
   } while (0)
     if (!transA && transB) DEER_H16_PAIR_GO(false, false);
     else if (!transA && !transB) DEER_H16_PAIR_GO(false, true);
@@ -887,7 +936,7 @@ int gemm_tf32_pair(const float* A, long long lda, int transA, const float* B, lo
                          ((uint32_t)(transB ? 0 : 1) << 16) | ((uint32_t)(BN >> 3) << 17) |
                          ((uint32_t)((2 * BM) >> 4) << 24);
   Params p{C, ldc, nullptr, 0, 0, bias, M, N, K, act, beta, splits, per, tiles_m, tiles_n, idesc, nullptr,
-           getenv("DEER_H16_DEBUG") ? atoi(getenv("DEER_H16_DEBUG")) : 0};
+           getenv("DEER_H16_DEBUG") ? atoi(getenv("DEER_H16_DEBUG")) : 0, 0};
   const int work = tiles_m * tiles_n * splits;
   const int clusters = work < kNumSMs / 2 ? work : kNumSMs / 2;
 #define DEER_TF32_PAIR_GO(AM, BMN)                                                                                  \
@@ -899,7 +948,7 @@ int gemm_tf32_pair(const float* A, long long lda, int transA, const float* B, lo
       if (e != cudaSuccess) return cuda_status(e, "gemm_tf32_pair smem attribute");                                 \
       attr = true;                                                                                                  \
     }                                                                                                               \
-    DEER_LAUNCH((gemm_h16_pair_kernel<4, AM, BMN>), 2 * clusters, NUM_THREADS, P_SMEM_BYTES, stream, ma, mb, mc, p); \
+    DEER_LAUNCH((gemm_h16_pair_kernel<4, AM, BMN>), 2 * clusters, NUM_THREADS, P_SMEM_BYTES, stream, ma, mb, mc, ma, mb, p); \
   } while (0)
   if (!transA && transB) DEER_TF32_PAIR_GO(false, false);
   else if (!transA && !transB) DEER_TF32_PAIR_GO(false, true);
@@ -907,6 +956,37 @@ int gemm_tf32_pair(const float* A, long long lda, int transA, const float* B, lo
   else DEER_TF32_PAIR_GO(true, true);
 #undef DEER_TF32_PAIR_GO
   return DEER_OK;
+}
+
+// fp32 -> FP16 hi / lo pair of a row-major matrix: hi = fp16(x), lo = fp16(x - hi) (22 significant bits together);
+// same geometry as cast16 (columns cols..cols_pad-1 zero-filled)
+__global__ void __launch_bounds__(256) cast_split16_kernel(const float* __restrict__ src, long long ld_src,
+                                                           uint16_t* __restrict__ hi, uint16_t* __restrict__ lo,
+                                                           long long ld_dst, long long rows, int cols, int cols_pad) {
+  DEER_PDL_ENTRY();
+  const int quads = cols_pad >> 2;                     // cols_pad % 4 == 0
+  const long long total = rows * quads;
+  const bool vec = (ld_src & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / quads;
+    const int c = (int)(i % quads) * 4;
+    float v[4];
+    if (vec && c + 3 < cols) {
+      const float4 x = __ldcs(reinterpret_cast<const float4*>(src + r * ld_src + c));
+      v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; j++) v[j] = (c + j < cols) ? src[r * ld_src + c + j] : 0.f;
+    }
+    __half h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      h[j] = __float2half_rn(v[j]);
+      l[j] = __float2half_rn(v[j] - __half2float(h[j]));
+    }
+    *reinterpret_cast<uint2*>(hi + r * ld_dst + c) = *reinterpret_cast<const uint2*>(h);
+    *reinterpret_cast<uint2*>(lo + r * ld_dst + c) = *reinterpret_cast<const uint2*>(l);
+  }
 }
 
 // fp32 -> 16-bit cast of a row-major matrix; dst row pitch ld_dst >= cols (columns cols..cols_pad-1 are zero-filled)
@@ -1028,6 +1108,34 @@ int deer_gemm_h16(const void* A, long long lda, int transA, int a_bf16, const vo
   g_engine_calls[DEER_ENGINE_H16]++;
   return gemm_h16(A, lda, transA, a_bf16, B, ldb, transB, b_bf16, C, ldc, C16, ldc16, c16_bf16, M, N, K, bias, act, beta,
                   (cudaStream_t)stream);
+}
+
+int deer_gemm_h16_split(const void* A_hi, const void* A_lo, long long lda, int transA, const void* B_hi, const void* B_lo,
+                        long long ldb, int transB, float* C, long long ldc, int M, int N, int K, const float* bias, int act,
+                        void* stream) {
+  DEER_CHECK_ARG(A_hi && A_lo && B_hi && B_lo && C, "gemm_h16_split: null pointer");
+  DEER_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm_h16_split: empty shape");
+  // lda < K with !transA = overlapping rows (sliding-window operand of the Conv1d taps): any 16-byte-multiple pitch
+  DEER_CHECK_ARG(lda > 0 && (transA ? lda >= M : true) && ldb >= (transB ? K : N) && ldc >= N,
+                 "gemm_h16_split: leading dimension too small");
+  DEER_CHECK_ARG(act >= 0 && act <= 3, "gemm_h16_split: bad activation");
+  g_engine_calls[DEER_ENGINE_H16_SPLIT]++;
+  return gemm_h16_ex(A_hi, A_lo, lda, transA, 0, B_hi, B_lo, ldb, transB, 0, C, ldc, nullptr, 0, 0, M, N, K, bias, act,
+                     0.f, (cudaStream_t)stream);
+}
+
+int deer_cast_split16(const float* src, long long ld_src, void* hi, void* lo, long long ld_dst, long long rows, int cols,
+                      int cols_pad, void* stream) {
+  DEER_CHECK_ARG(src && hi && lo && rows > 0 && cols > 0 && cols_pad >= cols && (cols_pad & 3) == 0 && ld_dst >= cols_pad &&
+                     (ld_dst & 3) == 0,
+                 "cast_split16: bad args");
+  DEER_CHECK_ARG(((reinterpret_cast<uintptr_t>(hi) | reinterpret_cast<uintptr_t>(lo)) & 7) == 0,
+                 "cast_split16: outputs must be 8-byte aligned");
+  long long g = cdiv(rows * (cols_pad / 4), 256);
+  if (g > kNumSMs * 16) g = kNumSMs * 16;
+  DEER_LAUNCH(cast_split16_kernel, (unsigned)g, 256, 0, stream, src, ld_src, reinterpret_cast<uint16_t*>(hi),
+              reinterpret_cast<uint16_t*>(lo), ld_dst, rows, cols, cols_pad);
+  return DEER_OK;
 }
 
 int deer_gemm_h16_set_profile_buffer(long long* device_buf) {

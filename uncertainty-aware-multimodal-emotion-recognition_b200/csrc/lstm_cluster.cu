@@ -205,6 +205,7 @@ struct LstmClusterParams {
   const __half* pre16;  // fwd: FP16 pre-activations [T,B,2,H,4] (read instead of `gates` when non-null)
   int T, B, ntiles, keep;
   long long* prof;     // optional clock64 trace of block 0 (tools/lstm_probe.py --prof), else null
+  int keep16;          // 1: the kept gates / cell states are FP16 (same blocked order, half the bytes), 0: fp32
 };
 constexpr int Q_PROF_S0 = 64, Q_PROF_STEPS = 4, Q_PROF_SLOTS = 8;
 #define Q_PROF(slot)                                                                               \
@@ -529,6 +530,24 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(G * CS * 256 + 32, 
         }
       } else
       if (p.keep) {
+        if (p.keep16) {
+          // FP16 kept state (gates in (0,1) / (-1,1), cell state: 11 significant bits, far inside what the BF16 operands
+          // of BPTT carry): per 4-column chunk one 16-byte store of (i,f) and one of (g,o) per thread -- 512 contiguous
+          // bytes per warp -- and one 8-byte store of c; 2.5 KB per (sample, step, direction) instead of 5 KB
+          uint4* gs = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.gact) + blk * (4 * NQ * 32)) + lane;
+          uint2* cs = reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.c_all) + blk * (NQ * 32)) + lane;
+#pragma unroll
+          for (int i = 0; i < NQ; i += 4) {
+            uint4 a, b;
+            a.x = pack_h2(gi[i], gi[i + 1]); a.y = pack_h2(gi[i + 2], gi[i + 3]);
+            a.z = pack_h2(gf[i], gf[i + 1]); a.w = pack_h2(gf[i + 2], gf[i + 3]);
+            b.x = pack_h2(gg[i], gg[i + 1]); b.y = pack_h2(gg[i + 2], gg[i + 3]);
+            b.z = pack_h2(go[i], go[i + 1]); b.w = pack_h2(go[i + 2], go[i + 3]);
+            __stcs(gs + (i / 4 * 2 + 0) * 32, a);
+            __stcs(gs + (i / 4 * 2 + 1) * 32, b);
+            __stcs(cs + (i / 4) * 32, make_uint2(pack_h2(cst[i], cst[i + 1]), pack_h2(cst[i + 2], cst[i + 3])));
+          }
+        } else {
         float4* gs = reinterpret_cast<float4*>(p.gact + blk * (4 * NQ * 32)) + lane;
         float4* cs = reinterpret_cast<float4*>(p.c_all + blk * (NQ * 32)) + lane;
 #pragma unroll
@@ -538,6 +557,7 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(G * CS * 256 + 32, 
           __stcs(gs + (2 * NQ + i) * 8, make_float4(gg[i], gg[i + 1], gg[i + 2], gg[i + 3]));
           __stcs(gs + (3 * NQ + i) * 8, make_float4(go[i], go[i + 1], go[i + 2], go[i + 3]));
           __stcs(cs + i * 8, make_float4(cst[i], cst[i + 1], cst[i + 2], cst[i + 3]));
+        }
         }
       }
       if (p.h16 || p.hb16) {
@@ -721,6 +741,26 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
       const int tp = dir ? t + 1 : t - 1;           // forward-previous time step (c_{prev})
       const bool first = dir ? (t == T - 1) : (t == 0);
       const long long blk = (long long)t * blk_t + blk_w;
+      if (p.keep16) {
+        const uint4* gs = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(p.gact) + blk * (4 * NQ * 32)) + lane;
+        const uint2* cs = reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(p.c_all) + blk * (NQ * 32)) + lane;
+        const uint2* cps = reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(p.c_all) +
+                                                          ((long long)tp * blk_t + blk_w) * (NQ * 32)) + lane;
+        auto h2f = [](uint32_t v) { return __half22float2(*reinterpret_cast<const __half2*>(&v)); };
+#pragma unroll
+        for (int i = 0; i < NQ; i += 4) {
+          const uint4 a = __ldcs(gs + (i / 4 * 2 + 0) * 32), b = __ldcs(gs + (i / 4 * 2 + 1) * 32);
+          const uint2 c = __ldcs(cs + (i / 4) * 32);
+          const uint2 cp = first ? make_uint2(0u, 0u) : __ldcs(cps + (i / 4) * 32);
+          float2 f;
+          f = h2f(a.x); vi[i] = f.x; vi[i + 1] = f.y; f = h2f(a.y); vi[i + 2] = f.x; vi[i + 3] = f.y;
+          f = h2f(a.z); vf[i] = f.x; vf[i + 1] = f.y; f = h2f(a.w); vf[i + 2] = f.x; vf[i + 3] = f.y;
+          f = h2f(b.x); vg[i] = f.x; vg[i + 1] = f.y; f = h2f(b.y); vg[i + 2] = f.x; vg[i + 3] = f.y;
+          f = h2f(b.z); vo[i] = f.x; vo[i + 1] = f.y; f = h2f(b.w); vo[i + 2] = f.x; vo[i + 3] = f.y;
+          f = h2f(c.x); vc[i] = f.x; vc[i + 1] = f.y; f = h2f(c.y); vc[i + 2] = f.x; vc[i + 3] = f.y;
+          f = h2f(cp.x); vcp[i] = f.x; vcp[i + 1] = f.y; f = h2f(cp.y); vcp[i + 2] = f.x; vcp[i + 3] = f.y;
+        }
+      } else {
       const float4* gs = reinterpret_cast<const float4*>(p.gact + blk * (4 * NQ * 32)) + lane;
       const float4* cs = reinterpret_cast<const float4*>(p.c_all + blk * (NQ * 32)) + lane;
       const float4* cps = reinterpret_cast<const float4*>(p.c_all + ((long long)tp * blk_t + blk_w) * (NQ * 32)) + lane;
@@ -736,6 +776,7 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
         vo[i] = a3.x; vo[i + 1] = a3.y; vo[i + 2] = a3.z; vo[i + 3] = a3.w;
         vc[i] = a4.x; vc[i + 1] = a4.y; vc[i + 2] = a4.z; vc[i + 3] = a4.w;
         vcp[i] = a5.x; vcp[i + 1] = a5.y; vcp[i + 2] = a5.z; vcp[i + 3] = a5.w;
+      }
       }
 #pragma unroll
       for (int i = 0; i < NQ; i++) {
@@ -879,6 +920,7 @@ static int g_lstm_ts = 1;      // resident operand in TMEM (1) or in shared memo
 static int g_lstm_tile = 0;    // 0 auto, else forced N (16 or 32)
 int g_lstm_colsplit = 0;       // DEER_OPT_LSTM_COLSPLIT: 16 compute warps (two column halves) on 16-column tiles; measured: no gain (1.444 vs 1.438 us/step: the step is issue-bound, not latency-bound), so off
 int g_lstm_dual = 1;           // DEER_OPT_LSTM_DUAL: two interleaved 16-column sub-tiles per CTA for no-keep 32-column tiles
+int g_lstm_keep16 = 1;         // DEER_OPT_LSTM_KEEP16: FP16 (1, default) or fp32 (0) kept gates / cell states
 static long long* g_lstm_prof = nullptr;
 void lstm_cluster_set_profile(long long* buf) { g_lstm_prof = buf; }
 void lstm_cluster_set_option(int ts, int tile) {
@@ -935,9 +977,10 @@ int lstm_fwd_cluster(const float* pre_il, const void* pre_f16, const float* w_fw
   if (dual_keep) N = 32;
   tc::LstmClusterParams p{const_cast<float*>(pre_il), w_fwd, w_rev, h_out, gact, c_blk, nullptr, nullptr,
                           reinterpret_cast<__half*>(h16), reinterpret_cast<__nv_bfloat16*>(hb16), nullptr,
-                          reinterpret_cast<const __half*>(pre_f16), T, B, (B + N - 1) / N, keep, g_lstm_prof};
+                          reinterpret_cast<const __half*>(pre_f16), T, B, (B + N - 1) / N, keep, g_lstm_prof,
+                          g_lstm_keep16};
   if (N == 16) {
-    if (g_lstm_ts && g_lstm_colsplit) return launch_fwd<16, true, 1, 2>(p, stream);
+    if (g_lstm_ts && g_lstm_colsplit && !g_lstm_keep16) return launch_fwd<16, true, 1, 2>(p, stream);
     return g_lstm_ts ? launch_fwd<16, true>(p, stream) : launch_fwd<16, false>(p, stream);
   }
   // inference (nothing kept for BPTT): the 32 batch columns of a CTA run as two interleaved 16-column sub-tiles.  The
@@ -951,7 +994,7 @@ int lstm_bwd_cluster(const float* gact, const float* c_blk, const float* dh_out,
   const int N = pick_tile(B);
   tc::LstmClusterParams p{dpre_il, w_fwd, w_rev, nullptr, const_cast<float*>(gact), const_cast<float*>(c_blk), dh_out,
                           db_il, nullptr, nullptr, reinterpret_cast<__nv_bfloat16*>(dpre16), nullptr, T, B,
-                          (B + N - 1) / N, 1, g_lstm_prof};
+                          (B + N - 1) / N, 1, g_lstm_prof, g_lstm_keep16};
   if (N == 16) return g_lstm_ts ? launch_bwd<16, true>(p, stream) : launch_bwd<16, false>(p, stream);
   return launch_bwd<32, true>(p, stream);  // the N=32 tiles + 128 KB of smem-resident weights exceed 227 KB
 }
@@ -964,22 +1007,24 @@ extern "C" {
 
 int deer_lstm_cluster_tile(int B) { return B > 0 ? lstm_cluster_tile(B) : DEER_ERR_INVALID; }
 
-int deer_lstm_cluster_fwd(const float* pre_il, const float* w_hh_fwd, const float* w_hh_rev, float* h_out, float* gact,
-                          float* c_blk, void* h_f16, void* h_bf16, int T, int B, int H, void* stream) {
+int deer_lstm_cluster_fwd(const float* pre_il, const float* w_hh_fwd, const float* w_hh_rev, float* h_out, void* gact,
+                          void* c_blk, void* h_f16, void* h_bf16, int T, int B, int H, void* stream) {
   DEER_CHECK_ARG(pre_il && w_hh_fwd && w_hh_rev && h_out && T > 0 && B > 0, "lstm_cluster_fwd: bad args");
   DEER_CHECK_ARG((gact == nullptr) == (c_blk == nullptr), "lstm_cluster_fwd: gact and c_blk go together");
+  DEER_CHECK_ARG(((reinterpret_cast<uintptr_t>(gact) | reinterpret_cast<uintptr_t>(c_blk)) & 15) == 0,
+                 "lstm_cluster_fwd: gact / c_blk must be 16-byte aligned");
   if (!lstm_cluster_supported(pre_il, w_hh_fwd, w_hh_rev, H)) {
     set_error("lstm_cluster_fwd: needs H == 256 and 16-byte aligned pointers");
     return DEER_ERR_UNSUPPORTED;
   }
   DEER_CHECK_ARG(((reinterpret_cast<uintptr_t>(h_f16) | reinterpret_cast<uintptr_t>(h_bf16)) & 15) == 0,
                  "lstm_cluster_fwd: 16-bit shadows must be 16-byte aligned");
-  return lstm_fwd_cluster(pre_il, nullptr, w_hh_fwd, w_hh_rev, h_out, gact, c_blk, h_f16, h_bf16, T, B,
-                          (cudaStream_t)stream);
+  return lstm_fwd_cluster(pre_il, nullptr, w_hh_fwd, w_hh_rev, h_out, reinterpret_cast<float*>(gact),
+                          reinterpret_cast<float*>(c_blk), h_f16, h_bf16, T, B, (cudaStream_t)stream);
 }
 
 int deer_lstm_cluster_fwd_pre16(const void* pre_il_f16, const float* w_hh_fwd, const float* w_hh_rev, float* h_out,
-                                float* gact, float* c_blk, void* h_f16, void* h_bf16, int T, int B, int H,
+                                void* gact, void* c_blk, void* h_f16, void* h_bf16, int T, int B, int H,
                                 void* stream) {
   DEER_CHECK_ARG(pre_il_f16 && w_hh_fwd && w_hh_rev && h_out && T > 0 && B > 0, "lstm_cluster_fwd_pre16: bad args");
   DEER_CHECK_ARG((gact == nullptr) == (c_blk == nullptr), "lstm_cluster_fwd_pre16: gact and c_blk go together");
@@ -990,11 +1035,11 @@ int deer_lstm_cluster_fwd_pre16(const void* pre_il_f16, const float* w_hh_fwd, c
   DEER_CHECK_ARG(((reinterpret_cast<uintptr_t>(h_f16) | reinterpret_cast<uintptr_t>(h_bf16) |
                    reinterpret_cast<uintptr_t>(pre_il_f16)) & 15) == 0,
                  "lstm_cluster_fwd_pre16: 16-bit buffers must be 16-byte aligned");
-  return lstm_fwd_cluster(nullptr, pre_il_f16, w_hh_fwd, w_hh_rev, h_out, gact, c_blk, h_f16, h_bf16, T, B,
-                          (cudaStream_t)stream);
+  return lstm_fwd_cluster(nullptr, pre_il_f16, w_hh_fwd, w_hh_rev, h_out, reinterpret_cast<float*>(gact),
+                          reinterpret_cast<float*>(c_blk), h_f16, h_bf16, T, B, (cudaStream_t)stream);
 }
 
-int deer_lstm_cluster_bwd(const float* gact, const float* c_blk, const float* dh_out, const float* w_hh_fwd,
+int deer_lstm_cluster_bwd(const void* gact, const void* c_blk, const float* dh_out, const float* w_hh_fwd,
                           const float* w_hh_rev, float* dpre_il, float* db_il, void* dpre_bf16, int T, int B, int H,
                           void* stream) {
   DEER_CHECK_ARG(gact && c_blk && dh_out && w_hh_fwd && w_hh_rev && (dpre_il || dpre_bf16) && T > 0 && B > 0,
@@ -1004,7 +1049,8 @@ int deer_lstm_cluster_bwd(const float* gact, const float* c_blk, const float* dh
     return DEER_ERR_UNSUPPORTED;
   }
   DEER_CHECK_ARG((reinterpret_cast<uintptr_t>(dpre_bf16) & 15) == 0, "lstm_cluster_bwd: dpre_bf16 must be 16-byte aligned");
-  return lstm_bwd_cluster(gact, c_blk, dh_out, w_hh_fwd, w_hh_rev, dpre_il, db_il, dpre_bf16, T, B, (cudaStream_t)stream);
+  return lstm_bwd_cluster(reinterpret_cast<const float*>(gact), reinterpret_cast<const float*>(c_blk), dh_out, w_hh_fwd,
+                          w_hh_rev, dpre_il, db_il, dpre_bf16, T, B, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -40,11 +40,11 @@ def _scorer_pool(x_bt, x_rows, att: nn.Sequential, mask=None):
     return hidden, s
 
 
-def _scorer_and_pool(x, att: nn.Sequential, mask=None, time_major=False):
+def _scorer_and_pool(x, att: nn.Sequential, mask=None, time_major=False, precise=True):
     """Scorer + softmax-over-time pooling of x ([T,B,D] when time_major, else [B,T,D]) as one autograd node
     (ops.scorer_pool), or as the separate scorer / pooling ops when fusion is switched off."""
     if ops.scorer_pool_fused():
-        return ops.scorer_pool(x, att[0].weight, att[0].bias, att[2].weight, att[2].bias, mask, time_major)
+        return ops.scorer_pool(x, att[0].weight, att[0].bias, att[2].weight, att[2].bias, mask, time_major, precise)
     _, s = _scorer_pool(None, x, att)
     if time_major:
         return ops.attn_pool(x.permute(1, 0, 2), s.permute(1, 0), mask)
@@ -99,7 +99,7 @@ class EnhancedAudioEncoder(nn.Module):
         if audio_input.dim() == 2:
             audio_input = audio_input.unsqueeze(1)
         h_tm = self.lstm_forward(audio_input)                      # [T,B,D]
-        pooled, _ = _scorer_and_pool(h_tm, self.attention, time_major=True)
+        pooled, _ = _scorer_and_pool(h_tm, self.attention, time_major=True, precise=False)
         op = self.output_projection
         y = ops.linear(pooled, op[0].weight, op[0].bias, "relu", dropout=self.dropout, training=self.training)
         y = ops.linear(y, op[3].weight, op[3].bias)
@@ -188,12 +188,12 @@ class EnhancedTextEncoder(nn.Module):
         B, T, _ = token_embeddings.shape
         dev = token_embeddings.device
         if attention_mask is None:
-            attention_mask = torch.ones((B, T), device=dev, dtype=torch.float32)
+            attention_mask = ops.constant(1.0, (B, T), dev)
         m = attention_mask.to(torch.float32)
         if linguistic_features is None and input_ids is not None:
             linguistic_features = self.extract_linguistic_features(input_ids, attention_mask)
         if linguistic_features is None:
-            linguistic_features = torch.zeros((B, 10), device=dev, dtype=torch.float32)
+            linguistic_features = ops.constant(0.0, (B, 10), dev)
         x = ops.rowscale(token_embeddings, m)
         agg, _ = _scorer_and_pool(x, self.token_attention, mask=m)
         bp, lp, op = self.bert_projection, self.linguistic_projection, self.output_projection

@@ -42,8 +42,9 @@ class AudioVisualFusion(nn.Module):
         fl = self.fusion_layers
         y = ops.linear([a_att, v_att], fl[0].weight, fl[0].bias, "relu", dropout=self.dropout, training=self.training)
         y = ops.layer_norm(y, fl[3].weight, fl[3].bias, fl[3].eps)
-        ones = torch.ones((audio_features.shape[0], 1), device=audio_features.device, dtype=torch.float32)
-        return {"fused_features": y, "attention_weights": {"audio_to_video": ones, "video_to_audio": ones.clone()}}
+        # softmax over ONE key: the attention weights are identically 1 (fusion.py:244-255); a cached constant
+        ones = ops.constant(1.0, (audio_features.shape[0], 1), audio_features.device)
+        return {"fused_features": y, "attention_weights": {"audio_to_video": ones, "video_to_audio": ones}}
 
 
 class TrimodalFusion(nn.Module):

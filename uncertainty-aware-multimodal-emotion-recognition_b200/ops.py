@@ -26,7 +26,16 @@ ENGINE_AUTO, ENGINE_SIMT, ENGINE_TF32, ENGINE_X3 = 0, 1, 2, 5
 _state = {"engine": ENGINE_AUTO, "lstm_engine": ENGINE_AUTO, "exact_small_fwd": True, "exact_small_bwd": True,
           "small_rows": 8192, "direct_grad": False, "lstm_gemm16": True, "fuse_lstm_dropout": True,
           "branch_streams": True, "lstm_pre16": True, "defer_wgrad": True,
-          "branch_max_batch": 512, "scorer_pool_fused": True, "grouped_batched": True, "exact_engine": ENGINE_X3}
+          "branch_max_batch": 512, "scorer_pool_fused": True, "grouped_batched": True, "exact_engine": ENGINE_X3,
+          "small_rows_bwd": 8192, "conv_exact": 0, "lstm_keep16": True,
+          "split_fwd": True, "split_rows": 1024}
+
+
+def set_lstm_keep16(on: bool):
+    """FP16 (default) or fp32 kept gates / cell states of the persistent LSTM kernels (DEER_OPT_LSTM_KEEP16).  Must not
+    change between a forward and its backward."""
+    _state["lstm_keep16"] = bool(on)
+    _lib.set_option(11, 1 if on else 0)
 
 
 def set_grouped_batched(on: bool):
@@ -160,10 +169,77 @@ def _acc(param, like=None):
     """(buffer the kernels accumulate d/dparam into, whether it is param.grad itself)."""
     if param is None:
         return None, False
-    g = param.grad if (_state["direct_grad"] and param.is_leaf) else None
-    if _state["direct_grad"] and g is not None and g.is_contiguous() and g.dtype == torch.float32 and g.is_cuda:
-        return g, True
+    if _state["direct_grad"]:
+        if param.is_leaf:
+            g = param.grad
+            if g is not None and g.is_contiguous() and g.dtype == torch.float32 and g.is_cuda:
+                return g, True
+        else:
+            # a view of a leaf parameter (the V rows of a packed in_proj_weight): accumulate into the same view of the
+            # leaf's gradient -- no temporary, no zero fill, no slice-backward copy + add
+            base = param._base
+            if (base is not None and base.is_leaf and base.grad is not None and base.grad.is_contiguous() and
+                    base.is_contiguous() and base.grad.dtype == torch.float32 and param.is_contiguous()):
+                gv = base.grad.as_strided(param.shape, param.stride(),
+                                          base.grad.storage_offset() + param.storage_offset() - base.storage_offset())
+                return gv, True
     return torch.zeros_like(param if like is None else like), False
+
+
+# ------------------------------------------------------------------------------------------------ zeroed scratch arena
+# Transient zero-initialised scratch of the backward kernels (split-K / atomically accumulated gradient staging, the loss
+# statistics): sub-allocated from one buffer that is cleared ONCE per step by one deer_fill_zero launch (begin_step)
+# instead of one at::fill kernel per request.  Invariant: [cursor, zeroed) is clean.  Buffers are never freed while the
+# process lives: captured CUDA graphs hold their addresses.
+_arena = {}
+
+
+def _arena_state(device):
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    st = _arena.get(key)
+    if st is None:
+        st = _arena[key] = {"buf": None, "cursor": 0, "high": 0, "zeroed": 0, "old": []}
+    return st
+
+
+def _arena_begin_step():
+    for st in _arena.values():
+        if st["buf"] is not None and st["high"] > 0 and st["buf"].device.index == torch.cuda.current_device():
+            call("deer_fill_zero", ptr(st["buf"]), st["high"], None, 0)
+            st["zeroed"] = st["high"]
+        st["cursor"] = 0
+
+
+def zeros_scratch(shape, device) -> torch.Tensor:
+    """Zero-filled fp32 scratch valid until the end of the calling autograd function (see _arena above)."""
+    if isinstance(shape, int):
+        shape = (shape,)
+    n = 1
+    for d in shape:
+        n *= int(d)
+    npad = (n + 63) // 64 * 64            # 256-byte slots
+    st = _arena_state(torch.device(device))
+    if st["cursor"] > (1 << 26) and not torch.cuda.is_current_stream_capturing():
+        # 256 MB handed out without a begin_step(): ops driven directly in a loop (not through a model forward).  Every
+        # earlier request was transient, so drain the device and start over.
+        torch.cuda.synchronize()
+        st["cursor"], st["zeroed"] = 0, 0
+    if st["buf"] is None or st["cursor"] + npad > st["buf"].numel():
+        if st["buf"] is not None:
+            st["old"].append(st["buf"])
+        size = max(npad * 2, 2 * (st["buf"].numel() if st["buf"] is not None else 0), 1 << 20)
+        st["buf"] = torch.empty(size, device=device, dtype=torch.float32)
+        st["cursor"], st["zeroed"] = 0, 0
+        st["high"] = max(st["high"], 0)
+    lo = st["cursor"]
+    if lo + npad > st["zeroed"]:          # first step (or a new high-water mark): clear just this piece
+        start = max(lo, st["zeroed"])
+        call("deer_fill_zero", st["buf"].data_ptr() + 4 * start, lo + npad - start, None, 0)
+        if start <= st["zeroed"]:
+            st["zeroed"] = lo + npad
+    st["cursor"] = lo + npad
+    st["high"] = max(st["high"], st["cursor"])
+    return st["buf"][lo:lo + n].view(*shape)
 
 
 def set_gemm_engine(engine: int):
@@ -177,15 +253,24 @@ def set_lstm_engine(engine: int):
     _state["lstm_engine"] = int(engine)
 
 
-def set_exact_small_forward(on: bool, small_rows: int = 8192, backward: Optional[bool] = None):
+def set_exact_small_forward(on: bool, small_rows: int = 8192, backward: Optional[bool] = None,
+                            small_rows_bwd: Optional[int] = None):
+    """Precision policy of the time-batched contractions: below `small_rows` (forward) / `small_rows_bwd` (backward) rows
+    they run on the fp32-grade engine, from there on the TF32 tcgen05 engine."""
     _state["exact_small_fwd"] = bool(on)
     _state["exact_small_bwd"] = bool(on if backward is None else backward)
     _state["small_rows"] = int(small_rows)
+    _state["small_rows_bwd"] = int(small_rows if small_rows_bwd is None else small_rows_bwd)
+
+
+def set_conv_exact(fwd: bool = False, bwd: bool = False):
+    """Diagnostics: Conv1d taps (forward / backward GEMMs) on the fp32-grade engine through the im2col path."""
+    _state["conv_exact"] = (1 if fwd else 0) | (2 if bwd else 0)
 
 
 def _bwd_engine(M: int, chain: bool = False):
     """Engine for a backward GEMM of an nn.Linear with M rows; `chain`: see _fwd_engine."""
-    if _state["engine"] == ENGINE_AUTO and _state["exact_small_bwd"] and (chain or M < _state["small_rows"]):
+    if _state["engine"] == ENGINE_AUTO and _state["exact_small_bwd"] and (chain or M < _state["small_rows_bwd"]):
         return _state["exact_engine"]
     return None
 
@@ -261,6 +346,40 @@ def gemm_h16(A, lda, transA, B, ldb, transB, C, ldc, M, N, K, *, a_bf16=False, b
          ptr(bias), act, float(beta))
 
 
+def cast_split16(x: torch.Tensor, rows=None, cols=None, ld=None):
+    """fp32 rows -> (hi, lo) FP16 [rows, Kp] with x = hi + lo to 22 significant bits (Kp = cols rounded up to 8).
+    `x` may be a tensor (viewed as rows of its last dimension) or a raw (pointer, rows, cols, ld) description."""
+    if isinstance(x, torch.Tensor):
+        x2, rows, cols, ld = _rows2d(_req(x, "x"))
+        src, dev = ptr(x2), x.device
+    else:
+        src, dev = int(x[0]), x[1]
+    Kp = (cols + 7) // 8 * 8
+    hi = torch.empty((rows, Kp), device=dev, dtype=torch.float16)
+    lo = torch.empty((rows, Kp), device=dev, dtype=torch.float16)
+    call("deer_cast_split16", src, ld, hi.data_ptr(), lo.data_ptr(), Kp, rows, cols, Kp)
+    return hi, lo, Kp
+
+
+def gemm_split(a_hi, a_lo, lda, b_hi, b_lo, ldb, C, ldc, M, N, K, bias=None, act=0):
+    """C = act(A B^T + bias) on FP16 hi/lo operand pairs (deer_gemm_h16_split): A [M,K] rows (pitch lda, may be < K:
+    overlapping windows), B [N,K] rows."""
+    call("deer_gemm_h16_split", a_hi.data_ptr(), a_lo.data_ptr(), int(lda), 0, b_hi.data_ptr(), b_lo.data_ptr(),
+         int(ldb), 1, ptr(C), int(ldc), int(M), int(N), int(K), ptr(bias), int(act))
+
+
+def set_split_forward(on: bool, rows: int = 1024):
+    """Time-batched FORWARD contractions with at least `rows` rows on the split-precision 16-bit engine (default on);
+    off: TF32 tcgen05 from `small_rows` rows on (the round-1 policy; ~3e-4 forward error)."""
+    _state["split_fwd"] = bool(on)
+    _state["split_rows"] = int(rows)
+
+
+def _split_fwd_ok(M: int, N: int, K: int, bias=None) -> bool:
+    return (_state["split_fwd"] and _state["engine"] == ENGINE_AUTO and M >= _state["split_rows"] and M > 128 and
+            N % 4 == 0 and N >= 64 and K >= 32)
+
+
 def gemm_x3(A, lda, transA, B, ldb, transB, C, ldc, M, N, K, *, bias=None, act=0, beta=0.0, batch=1, sA=0, sB=0, sC=0,
             sBias=0, gate=None, ldgate=0, gate_mode=0, gate_scale=1.0, sGate=0, colsum=None, sColsum=0, drop=None,
             drop_ld=0, drop_col0=0, drop_batch_stride=0):
@@ -318,9 +437,15 @@ class _Linear(torch.autograd.Function):
             if y is None:
                 y = torch.empty((M, N), device=w.device, dtype=torch.float32)
             last = i == len(xs) - 1
-            gemm(x2, ld, 0, w.data_ptr() + 4 * k0, w.stride(0), 1, y, N, M, N, K,
-                 bias=b if last else None, act=act if last else 0, beta=0.0 if i == 0 else 1.0,
-                 engine=_fwd_engine(M, chain))
+            if not chain and len(xs) == 1 and _split_fwd_ok(M, N, K):
+                # time-batched forward projection: fp32-grade products on FP16 hi/lo operand pairs (see gemm_split)
+                xh, xl, Kp = cast_split16(x2)
+                wh, wl, _ = cast_split16(w)
+                gemm_split(xh, xl, Kp, wh, wl, Kp, y, N, M, N, K, bias=b, act=act)
+            else:
+                gemm(x2, ld, 0, w.data_ptr() + 4 * k0, w.stride(0), 1, y, N, M, N, K,
+                     bias=b if last else None, act=act if last else 0, beta=0.0 if i == 0 else 1.0,
+                     engine=_fwd_engine(M, chain))
             rows.append((x2, ld, k0, K))
             k0 += K
         assert k0 == Ktot, f"input widths {k0} != weight in-features {Ktot}"
@@ -544,6 +669,7 @@ def begin_step():
     the drop-in modules draws fresh dropout masks every forward."""
     _dropout_state["offset"] = 0
     _dropout_state["host_step"] += 1
+    _arena_begin_step()
 
 
 def _dropout_seed() -> int:
@@ -655,7 +781,7 @@ class _ScorerPool(torch.autograd.Function):
     input-gradient GEMM accumulates onto it (beta = 1)."""
 
     @staticmethod
-    def forward(ctx, x, w1, b1, w2, b2, mask, time_major):
+    def forward(ctx, x, w1, b1, w2, b2, mask, time_major, precise=True):
         x = _req(x, "x").contiguous()
         R0, R1, D = x.shape
         M = R0 * R1
@@ -665,7 +791,12 @@ class _ScorerPool(torch.autograd.Function):
         xs_b, xs_t = (D, B * D) if time_major else (T * D, D)
         ss_b, ss_t = (1, B) if time_major else (T, 1)
         hidden = torch.empty((M, Hd), device=dev, dtype=torch.float32)
-        gemm(x, D, 0, w1, w1.stride(0), 1, hidden, Hd, M, Hd, D, bias=b1, act=ACT["tanh"], engine=_fwd_engine(M))
+        if precise and _split_fwd_ok(M, Hd, D):
+            xh, xl, Kp = cast_split16(x.view(M, D))
+            wh, wl, _ = cast_split16(w1)
+            gemm_split(xh, xl, Kp, wh, wl, Kp, hidden, Hd, M, Hd, D, bias=b1, act=ACT["tanh"])
+        else:
+            gemm(x, D, 0, w1, w1.stride(0), 1, hidden, Hd, M, Hd, D, bias=b1, act=ACT["tanh"], engine=_fwd_engine(M))
         sc = torch.empty(M, device=dev, dtype=torch.float32)
         w2v = w2.reshape(-1)
         call("deer_rowdot_fwd", ptr(hidden), ptr(w2v), ptr(b2), ptr(sc), M, Hd)
@@ -701,7 +832,7 @@ class _ScorerPool(torch.autograd.Function):
         dw1, dw1_direct = _acc(pw1)
         gemm(dh, Hd, 1, x, D, 0, dw1, D, Hd, D, M, beta=1.0, engine=_bwd_engine(M))
         return (dx if need_dx else None, None if dw1_direct else dw1, None if db1_direct else db1,
-                None if dw2_direct else dw2.view_as(pw2), None if db2_direct else db2, None, None)
+                None if dw2_direct else dw2.view_as(pw2), None if db2_direct else db2, None, None, None)
 
 
 def set_scorer_pool_fused(on: bool):
@@ -713,9 +844,11 @@ def scorer_pool_fused() -> bool:
     return _state["scorer_pool_fused"]
 
 
-def scorer_pool(x, w1, b1, w2, b2, mask=None, time_major=False):
-    """(pooled [B,D], attention weights [B,T]) of x [T,B,D] (time_major) or [B,T,D]; see _ScorerPool."""
-    return _ScorerPool.apply(x, w1, b1, w2, b2, mask, bool(time_major))
+def scorer_pool(x, w1, b1, w2, b2, mask=None, time_major=False, precise=True):
+    """(pooled [B,D], attention weights [B,T]) of x [T,B,D] (time_major) or [B,T,D]; see _ScorerPool.  `precise`: the
+    scorer's forward GEMM on the split-precision engine (default); False = TF32 (the audio encoder: its pooled output
+    averages 300 highly correlated steps and is dominated by the FP16 recurrence's own 4e-5, measured)."""
+    return _ScorerPool.apply(x, w1, b1, w2, b2, mask, bool(time_major), bool(precise))
 
 
 class _RowScale(torch.autograd.Function):
@@ -947,8 +1080,9 @@ class _BiLSTMLayerCluster(torch.autograd.Function):
         fwd_fn = "deer_lstm_cluster_fwd_pre16" if pre16 else "deer_lstm_cluster_fwd"
         if keep:
             Bp = (B + 31) // 32 * 32
-            gact = torch.empty(T * 2 * Bp * G, device=dev, dtype=torch.float32)
-            c_blk = torch.empty(T * 2 * Bp * H, device=dev, dtype=torch.float32)
+            kdt = torch.float16 if _state["lstm_keep16"] else torch.float32     # DEER_OPT_LSTM_KEEP16
+            gact = torch.empty(T * 2 * Bp * G, device=dev, dtype=kdt)
+            c_blk = torch.empty(T * 2 * Bp * H, device=dev, dtype=kdt)
             hb16 = torch.empty((T, B, 2 * H), device=dev, dtype=torch.bfloat16) if use16 else None
             call(fwd_fn, pre.data_ptr(), ptr(whf_c), ptr(whr_c), ptr(h), ptr(gact), ptr(c_blk), h16p,
                  None if hb16 is None else hb16.data_ptr(), T, B, H)
@@ -979,12 +1113,12 @@ class _BiLSTMLayerCluster(torch.autograd.Function):
         use16 = ctx.use16
         M = T * B
         if use16:   # the three gate-interleaved gradient accumulators of the layer in one zero-filled allocation
-            zbuf = torch.zeros(2 * G * (In + H + 1), device=dev, dtype=torch.float32)
+            zbuf = zeros_scratch(2 * G * (In + H + 1), dev)
             dwi_il2 = zbuf[:2 * G * In].view(2, G, In)
             dwh_il2 = zbuf[2 * G * In:2 * G * (In + H)].view(2, G, H)
             db_il = zbuf[2 * G * (In + H):].view(2, G)
         else:
-            db_il = torch.zeros((2, G), device=dev, dtype=torch.float32)
+            db_il = zeros_scratch((2, G), dev)
         dpre16 = torch.empty((T, B, 2, G), device=dev, dtype=torch.bfloat16) if use16 else None
         call("deer_lstm_cluster_bwd", ptr(gact), ptr(c_blk), ptr(dh), ptr(whf), ptr(whr),
              None if dpre is None else ptr(dpre), ptr(db_il), None if dpre16 is None else dpre16.data_ptr(), T, B, H)
@@ -1101,7 +1235,11 @@ class _Conv1dK3(torch.autograd.Function):
         wk = torch.empty((Cout, 3 * Cin), device=x.device, dtype=torch.float32)
         call("deer_conv3_weight_pack", ptr(w.contiguous()), ptr(wk), Cout, Cin, 0)
         y = torch.empty((B, T, Cout), device=x.device, dtype=torch.float32)
-        gemm(col, 3 * Cin, 0, wk, 3 * Cin, 1, y, Cout, B * T, Cout, 3 * Cin, bias=b)
+        ce = _state["conv_exact"]
+        # small problems (the im2col path): forward taps on the fp32-grade engine, like every other forward contraction
+        exact_fwd = (ce & 1) or (_state["split_fwd"] and _state["engine"] == ENGINE_AUTO)
+        gemm(col, 3 * Cin, 0, wk, 3 * Cin, 1, y, Cout, B * T, Cout, 3 * Cin, bias=b,
+             engine=_state["exact_engine"] if exact_fwd else None)
         ctx.save_for_backward(col, wk)
         ctx.dims = (B, T, Cin, Cout)
         ctx.params = (w, b)
@@ -1116,11 +1254,13 @@ class _Conv1dK3(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dcol = torch.empty_like(col)
-            gemm(dy, Cout, 0, wk, 3 * Cin, 0, dcol, 3 * Cin, M, 3 * Cin, Cout)
+            gemm(dy, Cout, 0, wk, 3 * Cin, 0, dcol, 3 * Cin, M, 3 * Cin, Cout,
+                 engine=_state["exact_engine"] if (_state["conv_exact"] & 2) else None)
             dx = torch.empty((B, T, Cin), device=dy.device, dtype=torch.float32)
             call("deer_col2im3", ptr(dcol), ptr(dx), B, T, Cin)
-        dwk = torch.zeros_like(wk)
-        gemm(dy, Cout, 1, col, 3 * Cin, 0, dwk, 3 * Cin, Cout, 3 * Cin, M, beta=1.0)
+        dwk = zeros_scratch(tuple(wk.shape), dy.device)
+        gemm(dy, Cout, 1, col, 3 * Cin, 0, dwk, 3 * Cin, Cout, 3 * Cin, M, beta=1.0,
+             engine=_state["exact_engine"] if (_state["conv_exact"] & 2) else None)
         dw, dw_direct = _acc(ctx.params[0])
         call("deer_conv3_weight_pack", ptr(dwk), ptr(dw), Cout, Cin, 1)
         db, db_direct = _acc(ctx.params[1])
@@ -1148,7 +1288,13 @@ class _Conv1dK3Window(torch.autograd.Function):
         wk = torch.empty((Cout, 3 * Cin), device=dev, dtype=torch.float32)
         call("deer_conv3_weight_pack", ptr(w.contiguous()), ptr(wk), Cout, Cin, 0)
         y_big = torch.empty((Mp, Cout), device=dev, dtype=torch.float32)
-        gemm(xp, Cin, 0, wk, 3 * Cin, 1, y_big, Cout, Mp, Cout, 3 * Cin, bias=b)      # lda = Cin < K = 3 Cin
+        if _split_fwd_ok(Mp, Cout, 3 * Cin) and Cin % 8 == 0:
+            # split-precision taps: the hi / lo FP16 copies of the padded rows keep the overlapping-window geometry
+            xh, xl, _ = cast_split16(xp)
+            wh, wl, _ = cast_split16(wk)
+            gemm_split(xh, xl, Cin, wh, wl, 3 * Cin, y_big, Cout, Mp, Cout, 3 * Cin, bias=b)   # lda = Cin < K = 3 Cin
+        else:
+            gemm(xp, Cin, 0, wk, 3 * Cin, 1, y_big, Cout, Mp, Cout, 3 * Cin, bias=b)      # lda = Cin < K = 3 Cin
         y = torch.empty((B, T, Cout), device=dev, dtype=torch.float32)
         call("deer_rows_pad", ptr(y_big), ptr(y), B, T, Cout, 0, 0, 1)
         ctx.save_for_backward(xp, wk)
@@ -1167,11 +1313,11 @@ class _Conv1dK3Window(torch.autograd.Function):
         call("deer_rows_pad", ptr(dy), ptr(dy_big), B, T, Cout, 0, 0, 0)              # zero rows at the pad centres
         dx = None
         if ctx.needs_input_grad[0]:
-            dx_p = torch.zeros((Mp + 2, Cin), device=dev, dtype=torch.float32)
+            dx_p = zeros_scratch((Mp + 2, Cin), dev)
             gemm(dy_big, Cout, 0, wk, 3 * Cin, 0, dx_p, Cin, Mp, 3 * Cin, Cout, beta=1.0)   # ldc = Cin < N: overlapped
             dx = torch.empty((B, T, Cin), device=dev, dtype=torch.float32)
             call("deer_rows_pad", ptr(dx_p), ptr(dx), B, T, Cin, 1, 1, 1)
-        dwk = torch.zeros_like(wk)
+        dwk = zeros_scratch(tuple(wk.shape), dev)
         gemm(dy_big, Cout, 1, xp, Cin, 0, dwk, 3 * Cin, Cout, 3 * Cin, Mp, beta=1.0)         # ldb = Cin < N = 3 Cin
         dw, dw_direct = _acc(ctx.params[0])
         call("deer_conv3_weight_pack", ptr(dwk), ptr(dw), Cout, Cin, 1)
@@ -1190,7 +1336,8 @@ def conv1d_k3(x, w, b):
     needs > 256 rows), forced engines and odd channel counts keep the im2col + GEMM path."""
     B, T, Cin = x.shape
     Cout = w.shape[0]
-    if (_state.get("conv_window", True) and _state["engine"] == ENGINE_AUTO and B * (T + 1) > 256 and Cin % 4 == 0 and
+    if (_state.get("conv_window", True) and not _state["conv_exact"] and _state["engine"] == ENGINE_AUTO and
+            B * (T + 1) > 256 and Cin % 4 == 0 and
             Cout % 4 == 0 and Cin >= 32 and Cout > 256):   # dW runs with M = Cout rows on the CTA-pair kernel
         return _Conv1dK3Window.apply(x, w, b)
     return _Conv1dK3.apply(x, w, b)
@@ -1583,6 +1730,19 @@ def nig_head(evidence):
 _edges_cache = {}
 
 
+_const_cache = {}
+
+
+def constant(value: float, shape, device) -> torch.Tensor:
+    """A cached read-only constant tensor (attention weights that are identically 1, default masks / zero features): one
+    fill when first requested instead of one at::fill kernel per forward.  Callers must not write to it."""
+    key = (float(value), tuple(int(d) for d in shape), str(device))
+    t = _const_cache.get(key)
+    if t is None:
+        t = _const_cache[key] = torch.full(key[1], float(value), device=device, dtype=torch.float32)
+    return t
+
+
 def ece_edges(device):
     """torch.linspace(0,1,11) exactly as losses.py:207 builds it (computed once on the host)."""
     key = str(device)
@@ -1607,7 +1767,7 @@ def nig_loss_raw(evidence, params, targets, *, weights=(0.1, 0.01, 0.05, 0.05), 
     else:
         e = None
         g, n, a, b = [_req(p, "nig param").contiguous() for p in params]
-    stats = torch.zeros((D, 40), device=dev, dtype=torch.float32)
+    stats = zeros_scratch((D, 40), dev)
     nig_out = torch.empty((7, B, D), device=dev, dtype=torch.float32) if want_nig else None
     edges = ece_edges(dev)
     call("deer_nig_loss_stats", ptr(e), ptr(g), ptr(n), ptr(a), ptr(b), ptr(t), ptr(edges), ptr(stats), ptr(nig_out),
