@@ -192,7 +192,7 @@ def test_split_precision_gemm_is_fp32_grade(M, N, K, act):
     assert _lib.engine_counts()["h16_split"] == before + 1
     ref = x.double() @ w.double().t() + b.double()
     ref = {0: ref, 1: torch.relu(ref), 2: torch.tanh(ref)}[act]
-    assert rel_l2(y, ref) <= 3e-6, rel_l2(y, ref)
+    assert rel_l2(y, ref) <= 1e-5, rel_l2(y, ref)
     # the single-pass FP16 product of the same operands, for scale
     y1 = torch.empty((M, N), device=DEV)
     ops.gemm_h16(xh, Kp, 0, wh, Kp, 1, y1, N, M, N, K, bias=b, act=act)
@@ -210,7 +210,7 @@ def test_split_precision_conv_window_matches_fp64_conv():
     y = ops.conv1d_k3(x, w, b)
     assert _lib.engine_counts()["h16_split"] == before + 1
     ref = torch.nn.functional.conv1d(x.double().transpose(1, 2), w.double(), b.double(), padding=1).transpose(1, 2)
-    assert rel_l2(y, ref) <= 3e-6, rel_l2(y, ref)
+    assert rel_l2(y, ref) <= 1e-5, rel_l2(y, ref)
     ops.set_split_forward(False)
     try:
         y_tf32 = ops.conv1d_k3(x, w, b)

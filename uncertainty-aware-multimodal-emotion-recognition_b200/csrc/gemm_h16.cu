@@ -1099,7 +1099,10 @@ int deer_gemm_h16(const void* A, long long lda, int transA, int a_bf16, const vo
                   const float* bias, int act, float beta, void* stream) {
   DEER_CHECK_ARG(A && B && (C || C16), "gemm_h16: null pointer");
   DEER_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm_h16: empty shape");
-  DEER_CHECK_ARG(lda >= (transA ? M : K) && ldb >= (transB ? K : N) && (C ? ldc >= N : ldc16 >= N),
+  // a leading dimension smaller than the row length = overlapping rows (the sliding-window Conv1d operands): K-major A
+  // (lda < K), MN-major B (ldb < N) and an accumulating fp32 C (ldc < N with beta = 1: TMA reduce-add) are supported
+  DEER_CHECK_ARG(lda > 0 && ldb > 0 && (transA ? lda >= M : true) && (transB ? ldb >= K : true) &&
+                     (C ? (ldc >= N || (ldc > 0 && beta == 1.f)) : ldc16 >= N),
                  "gemm_h16: leading dimension too small");
   DEER_CHECK_ARG(act >= 0 && act <= 3, "gemm_h16: bad activation");
   DEER_CHECK_ARG(beta == 0.f || beta == 1.f, "gemm_h16: beta must be 0 or 1");

@@ -593,7 +593,10 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(G * CS * 256 + 32, 
 }
 
 // ================================================================================================ backward
-template <int N, bool TS>
+// K16: the kept gates / cell states are FP16 (DEER_OPT_LSTM_KEEP16): they are loaded a step ahead as RAW bits and
+// converted only when the step that uses them starts (a convert at the load would wait for the DRAM round trip inside
+// the current step -- measured 1.48 -> 1.93 us per step)
+template <int N, bool TS, bool K16 = false>
 __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
     lstm_bwd_cluster_kernel(const LstmClusterParams p) {
   DEER_PDL_ENTRY();
@@ -736,29 +739,24 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
     const long long blk_t = 2LL * p.ntiles * 32;
     float sdb[4] = {0.f, 0.f, 0.f, 0.f};          // bias gradient of (unit, 4 gates) over this thread's columns, all t
     float vi[NQ], vf[NQ], vg[NQ], vo[NQ], vc[NQ], vcp[NQ], vdh[NQ];
+    uint4 ra[NQ / 4], rb[NQ / 4];                 // K16: raw FP16 bits of the next step's (i,f) / (g,o) gates
+    uint2 rc[NQ / 4], rcp[NQ / 4];                //      ... and of c_t / c_{t-1}
     auto load_step = [&](int s) {
       const int t = dir ? s : T - 1 - s;            // reverse of the forward order
       const int tp = dir ? t + 1 : t - 1;           // forward-previous time step (c_{prev})
       const bool first = dir ? (t == T - 1) : (t == 0);
       const long long blk = (long long)t * blk_t + blk_w;
-      if (p.keep16) {
+      if constexpr (K16) {
         const uint4* gs = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(p.gact) + blk * (4 * NQ * 32)) + lane;
         const uint2* cs = reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(p.c_all) + blk * (NQ * 32)) + lane;
         const uint2* cps = reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(p.c_all) +
                                                           ((long long)tp * blk_t + blk_w) * (NQ * 32)) + lane;
-        auto h2f = [](uint32_t v) { return __half22float2(*reinterpret_cast<const __half2*>(&v)); };
 #pragma unroll
         for (int i = 0; i < NQ; i += 4) {
-          const uint4 a = __ldcs(gs + (i / 4 * 2 + 0) * 32), b = __ldcs(gs + (i / 4 * 2 + 1) * 32);
-          const uint2 c = __ldcs(cs + (i / 4) * 32);
-          const uint2 cp = first ? make_uint2(0u, 0u) : __ldcs(cps + (i / 4) * 32);
-          float2 f;
-          f = h2f(a.x); vi[i] = f.x; vi[i + 1] = f.y; f = h2f(a.y); vi[i + 2] = f.x; vi[i + 3] = f.y;
-          f = h2f(a.z); vf[i] = f.x; vf[i + 1] = f.y; f = h2f(a.w); vf[i + 2] = f.x; vf[i + 3] = f.y;
-          f = h2f(b.x); vg[i] = f.x; vg[i + 1] = f.y; f = h2f(b.y); vg[i + 2] = f.x; vg[i + 3] = f.y;
-          f = h2f(b.z); vo[i] = f.x; vo[i + 1] = f.y; f = h2f(b.w); vo[i + 2] = f.x; vo[i + 3] = f.y;
-          f = h2f(c.x); vc[i] = f.x; vc[i + 1] = f.y; f = h2f(c.y); vc[i + 2] = f.x; vc[i + 3] = f.y;
-          f = h2f(cp.x); vcp[i] = f.x; vcp[i + 1] = f.y; f = h2f(cp.y); vcp[i + 2] = f.x; vcp[i + 3] = f.y;
+          ra[i / 4] = __ldcs(gs + (i / 4 * 2 + 0) * 32);
+          rb[i / 4] = __ldcs(gs + (i / 4 * 2 + 1) * 32);
+          rc[i / 4] = __ldcs(cs + (i / 4) * 32);
+          rcp[i / 4] = first ? make_uint2(0u, 0u) : __ldcs(cps + (i / 4) * 32);
         }
       } else {
       const float4* gs = reinterpret_cast<const float4*>(p.gact + blk * (4 * NQ * 32)) + lane;
@@ -790,6 +788,21 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
       float dh[NQ];
 #pragma unroll
       for (int i = 0; i < NQ; i++) dh[i] = vdh[i];
+      if constexpr (K16) {
+        auto h2f = [](uint32_t v) { return __half22float2(*reinterpret_cast<const __half2*>(&v)); };
+#pragma unroll
+        for (int i = 0; i < NQ; i += 4) {
+          const uint4 a = ra[i / 4], b = rb[i / 4];
+          const uint2 c = rc[i / 4], cp = rcp[i / 4];
+          float2 f;
+          f = h2f(a.x); vi[i] = f.x; vi[i + 1] = f.y; f = h2f(a.y); vi[i + 2] = f.x; vi[i + 3] = f.y;
+          f = h2f(a.z); vf[i] = f.x; vf[i + 1] = f.y; f = h2f(a.w); vf[i + 2] = f.x; vf[i + 3] = f.y;
+          f = h2f(b.x); vg[i] = f.x; vg[i + 1] = f.y; f = h2f(b.y); vg[i + 2] = f.x; vg[i + 3] = f.y;
+          f = h2f(b.z); vo[i] = f.x; vo[i + 1] = f.y; f = h2f(b.w); vo[i + 2] = f.x; vo[i + 3] = f.y;
+          f = h2f(c.x); vc[i] = f.x; vc[i + 1] = f.y; f = h2f(c.y); vc[i + 2] = f.x; vc[i + 3] = f.y;
+          f = h2f(cp.x); vcp[i] = f.x; vcp[i + 1] = f.y; f = h2f(cp.y); vcp[i + 2] = f.x; vcp[i + 3] = f.y;
+        }
+      }
       if (s > 0) {
         mbar_wait(&part_full[(s - 1) & 1], (uint32_t)(((s - 1) >> 1) & 1));
         if (warp == 0 && lane == 0) Q_PROF(2);
@@ -952,16 +965,16 @@ static int launch_fwd(const tc::LstmClusterParams& p, cudaStream_t stream) {
   DEER_LAUNCH((tc::lstm_fwd_cluster_kernel<N, TS, G, CS>), tc::QC * p.ntiles * 2, G * CS * 256 + 32, smem, stream, p);
   return DEER_OK;
 }
-template <int N, bool TS>
+template <int N, bool TS, bool K16>
 static int launch_bwd(const tc::LstmClusterParams& p, cudaStream_t stream) {
   constexpr int smem = tc::bwd_smem_bytes<N, TS>();
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(tc::lstm_bwd_cluster_kernel<N, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(tc::lstm_bwd_cluster_kernel<N, TS, K16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return cuda_status(e, "lstm_bwd_cluster smem attribute");
     attr = true;
   }
-  DEER_LAUNCH((tc::lstm_bwd_cluster_kernel<N, TS>), tc::QC * p.ntiles * 2, tc::QTHREADS, smem, stream, p);
+  DEER_LAUNCH((tc::lstm_bwd_cluster_kernel<N, TS, K16>), tc::QC * p.ntiles * 2, tc::QTHREADS, smem, stream, p);
   return DEER_OK;
 }
 
@@ -995,8 +1008,12 @@ int lstm_bwd_cluster(const float* gact, const float* c_blk, const float* dh_out,
   tc::LstmClusterParams p{dpre_il, w_fwd, w_rev, nullptr, const_cast<float*>(gact), const_cast<float*>(c_blk), dh_out,
                           db_il, nullptr, nullptr, reinterpret_cast<__nv_bfloat16*>(dpre16), nullptr, T, B,
                           (B + N - 1) / N, 1, g_lstm_prof, g_lstm_keep16};
-  if (N == 16) return g_lstm_ts ? launch_bwd<16, true>(p, stream) : launch_bwd<16, false>(p, stream);
-  return launch_bwd<32, true>(p, stream);  // the N=32 tiles + 128 KB of smem-resident weights exceed 227 KB
+  if (g_lstm_keep16) {
+    if (N == 16) return g_lstm_ts ? launch_bwd<16, true, true>(p, stream) : launch_bwd<16, false, true>(p, stream);
+    return launch_bwd<32, true, true>(p, stream);
+  }
+  if (N == 16) return g_lstm_ts ? launch_bwd<16, true, false>(p, stream) : launch_bwd<16, false, false>(p, stream);
+  return launch_bwd<32, true, false>(p, stream);  // the N=32 tiles + 128 KB of smem-resident weights exceed 227 KB
 }
 
 }  // namespace deer

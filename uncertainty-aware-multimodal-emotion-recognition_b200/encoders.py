@@ -40,11 +40,12 @@ def _scorer_pool(x_bt, x_rows, att: nn.Sequential, mask=None):
     return hidden, s
 
 
-def _scorer_and_pool(x, att: nn.Sequential, mask=None, time_major=False, precise=True):
+def _scorer_and_pool(x, att: nn.Sequential, mask=None, time_major=False, precise=True, x_bf16=None):
     """Scorer + softmax-over-time pooling of x ([T,B,D] when time_major, else [B,T,D]) as one autograd node
     (ops.scorer_pool), or as the separate scorer / pooling ops when fusion is switched off."""
     if ops.scorer_pool_fused():
-        return ops.scorer_pool(x, att[0].weight, att[0].bias, att[2].weight, att[2].bias, mask, time_major, precise)
+        return ops.scorer_pool(x, att[0].weight, att[0].bias, att[2].weight, att[2].bias, mask, time_major, precise,
+                               x_bf16)
     _, s = _scorer_pool(None, x, att)
     if time_major:
         return ops.attn_pool(x.permute(1, 0, 2), s.permute(1, 0), mask)
@@ -78,19 +79,20 @@ class EnhancedAudioEncoder(nn.Module):
                 g(f"weight_ih_l{l}_reverse"), g(f"weight_hh_l{l}_reverse"), g(f"bias_ih_l{l}_reverse"),
                 g(f"bias_hh_l{l}_reverse"))
 
-    def lstm_forward(self, features: torch.Tensor) -> torch.Tensor:
-        """[B,T,84] -> time-major LSTM output [T,B,hidden_dim]."""
+    def lstm_forward(self, features: torch.Tensor, return_bf16: bool = False):
+        """[B,T,84] -> time-major LSTM output [T,B,hidden_dim] (and, on request, the BF16 copy of it that the last
+        layer's recurrence kernel wrote for BPTT: the pooling scorer's weight-gradient GEMM reads it as well)."""
         h = ops.to_time_major(features)
-        h16 = None
+        h16 = hb16 = None
         nodrop = not (self.training and self.dropout > 0.0)
         for l in range(self.num_layers):
             # nn.LSTM(dropout=p): dropout on the OUTPUT of every layer but the last == on the input of layers >= 1.
             # Without dropout (inference) the recurrence kernel also writes the FP16 copy of h that the next layer's
             # input projection consumes, so the [T*B, 512] cast pass disappears.
-            h, h16 = ops.bilstm_layer(h, *self._layer_weights(l), input_dropout=self.dropout if l > 0 else 0.0,
-                                      training=self.training, x_f16=h16,
-                                      emit_f16=nodrop and l + 1 < self.num_layers, return_f16=True)
-        return h
+            h, h16, hb16 = ops.bilstm_layer(h, *self._layer_weights(l), input_dropout=self.dropout if l > 0 else 0.0,
+                                            training=self.training, x_f16=h16,
+                                            emit_f16=nodrop and l + 1 < self.num_layers, return_bf16=True)
+        return (h, hb16) if return_bf16 else h
 
     def forward(self, audio_input: torch.Tensor) -> torch.Tensor:
         if audio_input.shape[-1] != self.enhanced_features_dim:
@@ -98,8 +100,8 @@ class EnhancedAudioEncoder(nn.Module):
                                       "path; pass pre-extracted 84-D frames [B,T,84]")
         if audio_input.dim() == 2:
             audio_input = audio_input.unsqueeze(1)
-        h_tm = self.lstm_forward(audio_input)                      # [T,B,D]
-        pooled, _ = _scorer_and_pool(h_tm, self.attention, time_major=True, precise=False)
+        h_tm, hb16 = self.lstm_forward(audio_input, return_bf16=True)   # [T,B,D]
+        pooled, _ = _scorer_and_pool(h_tm, self.attention, time_major=True, precise=False, x_bf16=hb16)
         op = self.output_projection
         y = ops.linear(pooled, op[0].weight, op[0].bias, "relu", dropout=self.dropout, training=self.training)
         y = ops.linear(y, op[3].weight, op[3].bias)

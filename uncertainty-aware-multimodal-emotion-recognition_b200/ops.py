@@ -28,7 +28,19 @@ _state = {"engine": ENGINE_AUTO, "lstm_engine": ENGINE_AUTO, "exact_small_fwd": 
           "branch_streams": True, "lstm_pre16": True, "defer_wgrad": True,
           "branch_max_batch": 512, "scorer_pool_fused": True, "grouped_batched": True, "exact_engine": ENGINE_X3,
           "small_rows_bwd": 8192, "conv_exact": 0, "lstm_keep16": True,
-          "split_fwd": True, "split_rows": 1024}
+          "split_fwd": True, "split_rows": 1024, "bwd16": True}
+
+
+def set_backward_bf16(on: bool):
+    """Time-batched BACKWARD contractions (>= small_rows_bwd rows) on the 16-bit tcgen05 engine with BF16 operands
+    (default; gradients are insensitive to the operand precision -- measured cosine >= 0.99999 -- and the engine runs at
+    2.5x the TF32 one) or on the TF32 engine."""
+    _state["bwd16"] = bool(on)
+
+
+def _bwd16_ok(M: int) -> bool:
+    return (_state["bwd16"] and _state["engine"] == ENGINE_AUTO and _state["lstm_gemm16"] and
+            M >= _state["small_rows_bwd"] and M > 128)
 
 
 def set_lstm_keep16(on: bool):
@@ -479,6 +491,20 @@ class _Linear(torch.autograd.Function):
         # stream before the gradient exchange (join_wgrad_stream).
         defer = (dw is not None and dw_direct and _state["defer_wgrad"] and M < _state["small_rows"] and dz.is_cuda)
         chain = ctx.chain
+        if not chain and len(xs) == 1 and _bwd16_ok(M) and N % 8 == 0:
+            # time-batched layer: BF16 operands on the 16-bit tcgen05 engine (dz cast once, shared by dW and dx)
+            ld, k0, K = ctx.meta[0]
+            dzb = cast16(dz, bf16=True)
+            dxs = [None]
+            if ctx.needs_input_grad[4]:
+                wb = cast16(w, bf16=True)
+                dx = torch.empty((M, K), device=w.device, dtype=torch.float32)
+                gemm_h16(dzb, N, 0, wb, wb.shape[1], 0, dx, K, M, K, N, a_bf16=True, b_bf16=True)
+                dxs = [dx.view(ctx.in_shapes[0])]
+            if dw is not None:
+                xb = cast16(xs[0], bf16=True)
+                gemm_h16(dzb, N, 1, xb, xb.shape[1], 0, dw, Ktot, N, K, M, a_bf16=True, b_bf16=True, beta=1.0)
+            return (None if dw_direct else dw, None if db_direct else db, None, None, *dxs)
         dxs = []
         for i, x2 in enumerate(xs):
             ld, k0, K = ctx.meta[i]
@@ -781,8 +807,12 @@ class _ScorerPool(torch.autograd.Function):
     input-gradient GEMM accumulates onto it (beta = 1)."""
 
     @staticmethod
-    def forward(ctx, x, w1, b1, w2, b2, mask, time_major, precise=True):
+    def forward(ctx, x, w1, b1, w2, b2, mask, time_major, precise=True, x_bf16=None):
+        """x_bf16: optional BF16 copy of x written by its producer (the LSTM recurrence kernel's shadow of h): the B
+        operand of dW1 in backward without a cast pass."""
         x = _req(x, "x").contiguous()
+        ctx.x_bf16 = (x_bf16 if (x_bf16 is not None and x_bf16.dtype == torch.bfloat16 and x_bf16.is_contiguous() and
+                                 x_bf16.numel() == x.numel()) else None)
         R0, R1, D = x.shape
         M = R0 * R1
         Hd = w1.shape[0]
@@ -827,12 +857,22 @@ class _ScorerPool(torch.autograd.Function):
         # the whole scorer head backward in one pass over the saved tanh output
         dh = torch.empty_like(hidden)
         call("deer_scorer_bwd", ptr(ds), ptr(hidden), ptr(w2v), ptr(dh), ptr(dw2), ptr(db1), ptr(db2), M, Hd)
-        if need_dx:
-            gemm(dh, Hd, 0, w1, w1.stride(0), 0, dx, D, M, D, Hd, beta=1.0, engine=_bwd_engine(M))
         dw1, dw1_direct = _acc(pw1)
-        gemm(dh, Hd, 1, x, D, 0, dw1, D, Hd, D, M, beta=1.0, engine=_bwd_engine(M))
+        if _bwd16_ok(M) and Hd % 8 == 0 and D % 8 == 0:
+            # BF16 operands on the 16-bit tcgen05 engine: dx += dh W1 (onto the pooling gradient), dW1 += dh^T x
+            dhb = cast16(dh, bf16=True)
+            if need_dx:
+                wb = cast16(w1, bf16=True)
+                gemm_h16(dhb, Hd, 0, wb, D, 0, dx, D, M, D, Hd, a_bf16=True, b_bf16=True, beta=1.0)
+            xb = ctx.x_bf16 if ctx.x_bf16 is not None else cast16(x.view(M, D), bf16=True)
+            gemm_h16(dhb, Hd, 1, xb, D, 0, dw1, D, Hd, D, M, a_bf16=True, b_bf16=True, beta=1.0)
+        else:
+            if need_dx:
+                gemm(dh, Hd, 0, w1, w1.stride(0), 0, dx, D, M, D, Hd, beta=1.0, engine=_bwd_engine(M))
+            gemm(dh, Hd, 1, x, D, 0, dw1, D, Hd, D, M, beta=1.0, engine=_bwd_engine(M))
+        ctx.x_bf16 = None
         return (dx if need_dx else None, None if dw1_direct else dw1, None if db1_direct else db1,
-                None if dw2_direct else dw2.view_as(pw2), None if db2_direct else db2, None, None, None)
+                None if dw2_direct else dw2.view_as(pw2), None if db2_direct else db2, None, None, None, None)
 
 
 def set_scorer_pool_fused(on: bool):
@@ -844,11 +884,11 @@ def scorer_pool_fused() -> bool:
     return _state["scorer_pool_fused"]
 
 
-def scorer_pool(x, w1, b1, w2, b2, mask=None, time_major=False, precise=True):
+def scorer_pool(x, w1, b1, w2, b2, mask=None, time_major=False, precise=True, x_bf16=None):
     """(pooled [B,D], attention weights [B,T]) of x [T,B,D] (time_major) or [B,T,D]; see _ScorerPool.  `precise`: the
     scorer's forward GEMM on the split-precision engine (default); False = TF32 (the audio encoder: its pooled output
     averages 300 highly correlated steps and is dominated by the FP16 recurrence's own 4e-5, measured)."""
-    return _ScorerPool.apply(x, w1, b1, w2, b2, mask, bool(time_major), bool(precise))
+    return _ScorerPool.apply(x, w1, b1, w2, b2, mask, bool(time_major), bool(precise), x_bf16)
 
 
 class _RowScale(torch.autograd.Function):
@@ -1097,11 +1137,12 @@ class _BiLSTMLayerCluster(torch.autograd.Function):
         ctx.params = (wif, whf, bif, bhf, wir, whr, bir, bhr)
         if h16 is None:
             h16 = torch.empty(0, device=dev, dtype=torch.float16)
-        ctx.mark_non_differentiable(h16)
-        return h, h16
+        hb_out = ctx.hb16 if (keep and ctx.hb16 is not None) else torch.empty(0, device=dev, dtype=torch.bfloat16)
+        ctx.mark_non_differentiable(h16, hb_out)
+        return h, h16, hb_out
 
     @staticmethod
-    def backward(ctx, dh, _dh16=None):
+    def backward(ctx, dh, _dh16=None, _dhb16=None):
         x, wi_il, whf, whr, gact, c_blk, h = ctx.saved_tensors
         T, B, In, H = ctx.dims
         G = 4 * H
@@ -1192,7 +1233,7 @@ class _BiLSTMLayerCluster(torch.autograd.Function):
 
 
 def bilstm_layer(x_tm, wif, whf, bif, bhf, wir, whr, bir, bhr, input_dropout: float = 0.0, training: bool = False,
-                 x_f16=None, emit_f16: bool = False, return_f16: bool = False):
+                 x_f16=None, emit_f16: bool = False, return_f16: bool = False, return_bf16: bool = False):
     """engine AUTO/TF32: persistent cluster kernels when H == 256; SIMT: exact-fp32 stepwise; others: see lstm.cu.
     `input_dropout` (with `training`) applies nn.LSTM's inter-layer dropout to x_tm: fused into the layer's 16-bit
     operand casts on the cluster path, a separate kernel otherwise.
@@ -1214,10 +1255,14 @@ def bilstm_layer(x_tm, wif, whf, bif, bhf, wir, whr, bir, bhr, input_dropout: fl
         want = bool(emit_f16 and _state["lstm_gemm16"] and _state["engine"] == ENGINE_AUTO)
         # (a custom Function's forward always runs with grad mode off: the caller's mode is passed in, so that an
         # inference forward keeps nothing for BPTT and can use the no-keep kernels)
-        h, h16 = _BiLSTMLayerCluster.apply(x_tm, wif, whf, bif, bhf, wir, whr, bir, bhr, drop,
-                                           x_f16 if drop is None else None, want, torch.is_grad_enabled())
+        h, h16, hb16 = _BiLSTMLayerCluster.apply(x_tm, wif, whf, bif, bhf, wir, whr, bir, bhr, drop,
+                                                 x_f16 if drop is None else None, want, torch.is_grad_enabled())
+        if return_bf16:     # (h, FP16 copy or None, BF16 copy or None): the 16-bit shadows the recurrence kernel wrote
+            return h, (h16 if h16.numel() else None), (hb16 if hb16.numel() else None)
         return (h, h16 if h16.numel() else None) if return_f16 else h
     h = _BiLSTMLayer.apply(x_tm, wif, whf, bif, bhf, wir, whr, bir, bhr, torch.is_grad_enabled())
+    if return_bf16:
+        return h, None, None
     return (h, None) if return_f16 else h
 
 
@@ -1312,13 +1357,24 @@ class _Conv1dK3Window(torch.autograd.Function):
         dy_big = torch.empty((Mp, Cout), device=dev, dtype=torch.float32)
         call("deer_rows_pad", ptr(dy), ptr(dy_big), B, T, Cout, 0, 0, 0)              # zero rows at the pad centres
         dx = None
+        bf = _bwd16_ok(Mp) and Cin % 8 == 0 and Cout % 8 == 0
+        if bf:   # BF16 operands on the 16-bit tcgen05 engine (same overlapping-row geometry)
+            dyb = cast16(dy_big, bf16=True)
+            xpb = cast16(xp, bf16=True)
         if ctx.needs_input_grad[0]:
             dx_p = zeros_scratch((Mp + 2, Cin), dev)
-            gemm(dy_big, Cout, 0, wk, 3 * Cin, 0, dx_p, Cin, Mp, 3 * Cin, Cout, beta=1.0)   # ldc = Cin < N: overlapped
+            if bf:
+                wkb = cast16(wk, bf16=True)
+                gemm_h16(dyb, Cout, 0, wkb, 3 * Cin, 0, dx_p, Cin, Mp, 3 * Cin, Cout, a_bf16=True, b_bf16=True, beta=1.0)
+            else:
+                gemm(dy_big, Cout, 0, wk, 3 * Cin, 0, dx_p, Cin, Mp, 3 * Cin, Cout, beta=1.0)   # ldc = Cin < N: overlapped
             dx = torch.empty((B, T, Cin), device=dev, dtype=torch.float32)
             call("deer_rows_pad", ptr(dx_p), ptr(dx), B, T, Cin, 1, 1, 1)
         dwk = zeros_scratch(tuple(wk.shape), dev)
-        gemm(dy_big, Cout, 1, xp, Cin, 0, dwk, 3 * Cin, Cout, 3 * Cin, Mp, beta=1.0)         # ldb = Cin < N = 3 Cin
+        if bf:
+            gemm_h16(dyb, Cout, 1, xpb, Cin, 0, dwk, 3 * Cin, Cout, 3 * Cin, Mp, a_bf16=True, b_bf16=True, beta=1.0)
+        else:
+            gemm(dy_big, Cout, 1, xp, Cin, 0, dwk, 3 * Cin, Cout, 3 * Cin, Mp, beta=1.0)         # ldb = Cin < N = 3 Cin
         dw, dw_direct = _acc(ctx.params[0])
         call("deer_conv3_weight_pack", ptr(dwk), ptr(dw), Cout, Cin, 1)
         db, db_direct = _acc(ctx.params[1])
