@@ -28,13 +28,15 @@ _state = {"engine": ENGINE_AUTO, "lstm_engine": ENGINE_AUTO, "exact_small_fwd": 
           "branch_streams": True, "lstm_pre16": True, "defer_wgrad": True,
           "branch_max_batch": 512, "scorer_pool_fused": True, "grouped_batched": True, "exact_engine": ENGINE_X3,
           "small_rows_bwd": 8192, "conv_exact": 0, "lstm_keep16": True,
-          "split_fwd": True, "split_rows": 1024, "bwd16": True}
+          "split_fwd": True, "split_rows": 1024, "bwd16": False}
 
 
 def set_backward_bf16(on: bool):
-    """Time-batched BACKWARD contractions (>= small_rows_bwd rows) on the 16-bit tcgen05 engine with BF16 operands
-    (default; gradients are insensitive to the operand precision -- measured cosine >= 0.99999 -- and the engine runs at
-    2.5x the TF32 one) or on the TF32 engine."""
+    """Ablation switch (default OFF): time-batched BACKWARD contractions (>= small_rows_bwd rows) on the 16-bit tcgen05
+    engine with BF16 operands instead of the TF32 engine.  Gradients tolerate the operand precision (all parity gates
+    hold) and the GEMMs themselves run ~2.5x faster, but the fp32 -> BF16 cast passes of dy / x / W that feed them cost
+    more than that saves: measured 4.28 ms vs 4.20 ms per B=256 step.  It would need the casts fused into the producing
+    kernels (BatchNorm / scorer backward) to pay."""
     _state["bwd16"] = bool(on)
 
 
