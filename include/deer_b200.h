@@ -318,8 +318,37 @@ typedef struct {
   float beta, drop_p;
   int gate_mode;
   float gate_scale;
+  int splitk;   /* internal (cross-CTA split-K factor chosen by the dispatcher); ignored on input */
 } deer_gemm_x3_args;
 int deer_gemm_x3(const deer_gemm_x3_args* args, void* stream);
+
+/* ---- persistent chain kernel: the whole post-pooling part of a step (HierarchicalMultimodalFusion.forward
+ * fusion.py:119-171 with AudioVisualFusion :188-271 and TrimodalFusion :274-343, then MultiDimensionalDEER.forward
+ * deer.py:233-266; and their autograd) as ONE launch per direction.  The caller passes a PROGRAM: ops grouped into
+ * dependency levels; one CTA per SM deals the tiles of a level round-robin and a grid-wide barrier separates levels.
+ * Op kinds: 0 GEMM (`g` = deer_gemm_x3 arguments, 32x32 tiles: tiles = ceil(M/32)*ceil(N/32)*batch; operands 16-byte
+ * aligned, pitches multiples of 4); 1 LayerNorm forward (g.A = x, g.B = gamma, g.bias = beta, g.C = y, g.gate = mean out,
+ * g.colsum = rstd out, g.beta = eps; tiles = ceil(M/8)); 2 LayerNorm backward (g.A = dy, g.B = x, g.bias = gamma,
+ * g.gate = mean, g.colsum = rstd, g.C = dx (g.beta = 1: +=), dgamma / dbeta accumulators as pointers in g.drop_seed /
+ * g.drop_offset; tiles = ceil(M/32)); 3 / 4 two-token attention core forward / backward (see csrc/chain.cu; g.N = E,
+ * g.K = heads; tiles = M); 5 y (+)= x (g.A, g.C, g.beta; tiles = ceil(M/32)).  `barrier`: a zero-initialised device
+ * counter; `error` (optional): set to 1 by the device-side watchdog if a barrier times out. */
+#define DEER_CHAIN_MAX_OPS 72
+#define DEER_CHAIN_MAX_LEVELS 48
+typedef struct {
+  int kind, tiles, tiles_n, pad_;
+  deer_gemm_x3_args g;
+} deer_chain_op;
+typedef struct {
+  int nops, nlevels;
+  unsigned int* barrier;
+  int* error;
+  int level_begin[DEER_CHAIN_MAX_LEVELS + 1];
+  deer_chain_op ops[DEER_CHAIN_MAX_OPS];
+} deer_chain_program;
+int deer_chain_run(const deer_chain_program* program, void* stream);
+int deer_chain_max_ops(void);
+int deer_chain_max_levels(void);
 
 /* ---- generic elementwise helpers used by the pooled model (complete_project.py:282-293,364,439-459) */
 /* y = a*x1 + b*x2 (x2 may be NULL) */

@@ -24,7 +24,7 @@ class GemmX3Args(ctypes.Structure):
                 ("sA", L), ("sB", L), ("sC", L), ("sBias", L), ("sGate", L), ("sColsum", L),
                 ("drop_seed", U), ("drop_offset", U), ("drop_ld", L), ("drop_batch_stride", L), ("drop_col0", I),
                 ("M", I), ("N", I), ("K", I), ("batch", I), ("transA", I), ("transB", I), ("act", I),
-                ("beta", F), ("drop_p", F), ("gate_mode", I), ("gate_scale", F)]
+                ("beta", F), ("drop_p", F), ("gate_mode", I), ("gate_scale", F), ("splitk", I)]
 
 
 # name -> argtypes (every function returns int unless listed in _RESTYPES)
@@ -38,6 +38,9 @@ _PROTOS = {
     "deer_lstm_set_profile_buffer": [P],
     "deer_gemm": [P, L, I, P, L, I, P, L, I, I, I, P, I, F, I, L, L, L, L, I, P],
     "deer_gemm_x3": [ctypes.POINTER(GemmX3Args), P],
+    "deer_chain_run": [P, P],
+    "deer_chain_max_ops": None,
+    "deer_chain_max_levels": None,
     "deer_gemm_h16_split": [P, P, L, I, P, P, L, I, P, L, I, I, I, P, I, P],
     "deer_cast_split16": [P, L, P, P, L, L, I, I, P],
     "deer_gemm_h16": [P, L, I, I, P, L, I, I, P, L, P, L, I, I, I, I, P, I, F, P],
@@ -116,7 +119,7 @@ def load():
         lib = ctypes.CDLL(LIB_PATH)
         for name, args in _PROTOS.items():
             fn = getattr(lib, name)
-            fn.argtypes = args
+            fn.argtypes = args if args is not None else []
             fn.restype = _RESTYPES.get(name, I)
         _lib = lib
     return _lib

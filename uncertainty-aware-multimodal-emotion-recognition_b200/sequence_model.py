@@ -10,8 +10,8 @@ from typing import Dict, Optional
 import torch
 import torch.nn as nn
 
-from . import ops
-from .deer import MultiDimensionalDEER
+from . import chain, ops
+from .deer import MultiDimensionalDEER, nig_dict
 from .encoders import EnhancedAudioEncoder, EnhancedTextEncoder, EnhancedVideoEncoder
 from .fusion import HierarchicalMultimodalFusion
 from .losses import MultiTaskDEERLoss
@@ -69,6 +69,16 @@ class SequenceDEERModel(nn.Module):
             a = self.audio_encoder(audio)
             v = self.video_encoder(video)
             t = self.text_encoder(text, attention_mask, linguistic_features)
+        if chain.enabled() and a.is_cuda and chain.supported(self.fusion, self.deer, a, v, t):
+            # fusion + NIG head as ONE persistent-kernel launch (and one in backward): csrc/chain.cu
+            fused, _av, _tri, attw, ev = chain.fusion_head_chain(self.fusion, self.deer, a, v, t)
+            ops.mark_tensor(fused, "fused")
+            ops.mark("head_out_chain")
+            out = nig_dict(ev, ops.nig_head(ev), self.deer.dimension_names)
+            out["fused_features"] = fused
+            out["audio_encoded"], out["video_encoded"], out["text_encoded"] = a, v, t
+            out["attention_weights"] = attw
+            return out
         fus = self.fusion(a, v, t)
         out = self.deer(ops.mark_tensor(fus["fused_features"], "fused"))
         out["fused_features"] = fus["fused_features"]
