@@ -114,7 +114,10 @@ def test_train_step_b256_benchmark_dispatch_vs_fp64_oracle():
     assert used["h16_split"] >= 5, used
     assert used["tf32_pair"] + used["tf32"] >= 8, used
     assert used["h16"] >= 8, used
-    assert used["tf32x3"] >= 40 and used["simt"] == 0, used
+    # (>= 40 separate fused 3xTF32 nodes module by module; with the persistent chain kernel the whole fusion + head is
+    # one dispatch per direction, the encoders' small layers remain separate)
+    from deer_b200 import chain
+    assert used["tf32x3"] >= (10 if chain.enabled() else 40) and used["simt"] == 0, used
     assert ops.branch_streams_enabled() and B <= ops.branch_max_batch()
 
     sdg = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd64.items()}
