@@ -125,7 +125,15 @@ class Program:
         _lib.check(_lib.load().deer_chain_run(ctypes.byref(c), _lib.stream()), "deer_chain_run")
 
 
-_state = {"enabled": True}
+_state = {"enabled": True, "max_batch": 512}
+
+
+def set_max_batch(n: int):
+    """Largest batch that takes the chain kernel (default 512).  Measured (tools/chain_time.py, graph replay): the kernel
+    replaces ~120 launches of 5-8 us but keeps one grid barrier + one cold operand pipeline per level, so it only pays
+    while the layers are launch/latency-bound; from B = 1024 on the module-by-module path is faster (373 vs 510 us
+    forward at B = 1024, 651 vs 957 us at B = 2048)."""
+    _state["max_batch"] = int(n)
 
 
 def set_enabled(on: bool):
@@ -164,7 +172,8 @@ def supported(fusion, deer, a, v, t) -> bool:
     dims = [a.shape[1], v.shape[1], t.shape[1], E1, E, ps[28].shape[0], ps[32].shape[0], ps[34].shape[0]]
     drops = {float(fusion.dropout), float(fusion.audio_visual_fusion.dropout), float(fusion.trimodal_fusion.dropout),
              float(deer.dropout)} | {float(h.dropout) for h in deer.deer_heads}
-    return (a.dim() == 2 and len(drops) == 1 and all(d % 4 == 0 for d in dims) and E <= 512 and E1 <= 512 and
+    return (a.dim() == 2 and a.shape[0] <= _state["max_batch"] and len(drops) == 1 and
+            all(d % 4 == 0 for d in dims) and E <= 512 and E1 <= 512 and
             fusion.training == deer.training and
             tri_heads(fusion) <= 8 and E % tri_heads(fusion) == 0 and ps[36].shape[0] == 4 and
             all(p.is_cuda and p.dtype == torch.float32 and p.is_contiguous() for p in ps) and
