@@ -85,6 +85,7 @@ class EnhancedAudioEncoder(nn.Module):
         h = ops.to_time_major(features)
         h16 = hb16 = None
         nodrop = not (self.training and self.dropout > 0.0)
+        nodes = []
         for l in range(self.num_layers):
             # nn.LSTM(dropout=p): dropout on the OUTPUT of every layer but the last == on the input of layers >= 1.
             # Without dropout (inference) the recurrence kernel also writes the FP16 copy of h that the next layer's
@@ -92,6 +93,10 @@ class EnhancedAudioEncoder(nn.Module):
             h, h16, hb16 = ops.bilstm_layer(h, *self._layer_weights(l), input_dropout=self.dropout if l > 0 else 0.0,
                                             training=self.training, x_f16=h16,
                                             emit_f16=nodrop and l + 1 < self.num_layers, return_bf16=True)
+            nodes.append(h.grad_fn)
+        # autograd nodes of the layers, first layer first: layer l's weight gradients are complete when node l has run (the
+        # data-parallel trainer exchanges the gradients of layers >= 1 beside the BPTT of layer 0)
+        self.__dict__["_lstm_bwd_nodes"] = nodes
         return (h, hb16) if return_bf16 else h
 
     def forward(self, audio_input: torch.Tensor) -> torch.Tensor:

@@ -840,6 +840,7 @@ class _ScorerPool(torch.autograd.Function):
         ctx.geom = (B, T, D, M, Hd, xs_b, xs_t, ss_b, ss_t)
         ctx.params = (w1, b1, w2, b2)
         ctx.mark_non_differentiable(wts)
+        ctx.set_materialize_grads(False)
         return out, wts
 
     @staticmethod
@@ -849,6 +850,8 @@ class _ScorerPool(torch.autograd.Function):
         dev = x.device
         pw1, pb1, pw2, pb2 = ctx.params
         need_dx = ctx.needs_input_grad[0]
+        if dout is None:
+            dout = torch.zeros((B, D), device=dev, dtype=torch.float32)
         dx = torch.empty_like(x)               # the pooling kernel always writes it; dropped when x needs no gradient
         ds = torch.empty(M, device=dev, dtype=torch.float32)
         call("deer_attn_pool_bwd", ptr(dout.contiguous()), ptr(x), xs_b, xs_t, ptr(sc), ss_b, ss_t, ptr(m), ptr(wts),
@@ -871,7 +874,19 @@ class _ScorerPool(torch.autograd.Function):
         else:
             if need_dx:
                 gemm(dh, Hd, 0, w1, w1.stride(0), 0, dx, D, M, D, Hd, beta=1.0, engine=_bwd_engine(M))
-            gemm(dh, Hd, 1, x, D, 0, dw1, D, Hd, D, M, beta=1.0, engine=_bwd_engine(M))
+            if dw1_direct and _state["defer_wgrad"] and _state["direct_grad"]:
+                # trainer mode: dW1 is not needed before the optimizer -- it leaves the path to the LSTM's BPTT and runs
+                # on the weight-gradient stream (a split-K TF32 GEMM of 100 KB CTAs: it shares SMs with the recurrence)
+                cur = torch.cuda.current_stream()
+                aux = _wgrad_stream()
+                aux.wait_stream(cur)
+                with torch.cuda.stream(aux):
+                    gemm(dh, Hd, 1, x, D, 0, dw1, D, Hd, D, M, beta=1.0, engine=_bwd_engine(M))
+                dh.record_stream(aux)
+                x.record_stream(aux)
+                _wgrad["pending"] = True
+            else:
+                gemm(dh, Hd, 1, x, D, 0, dw1, D, Hd, D, M, beta=1.0, engine=_bwd_engine(M))
         ctx.x_bf16 = None
         return (dx if need_dx else None, None if dw1_direct else dw1, None if db1_direct else db1,
                 None if dw2_direct else dw2.view_as(pw2), None if db2_direct else db2, None, None, None, None)
@@ -1096,11 +1111,19 @@ class _BiLSTMLayerCluster(torch.autograd.Function):
             raise _lib.DeerError("deer_b200: fused input dropout needs the 16-bit GEMM path and In % 8 == 0")
         ctx.drop = drop
         ctx.drop_step = _dropout_state["step"]
+        ctx.xdrop_b16 = None
+        # the 16-bit shadow outputs are non-differentiable: without this autograd hands backward a zero-filled tensor
+        # for each of them (a 79 MB BF16 fill per layer and step)
+        ctx.set_materialize_grads(False)
         if use16:
             if drop is not None:                              # dropout + fp16 cast in one pass over x
                 x16 = torch.empty((M, In), device=dev, dtype=torch.float16)
-                call("deer_dropout_cast16", ptr(x), x16.data_ptr(), None, M * In, float(drop[0]), drop[1], drop[2],
-                     ptr(ctx.drop_step))
+                # training: the same pass also writes the BF16 copy the weight-gradient GEMM of backward reads (79 MB
+                # more to store here, instead of a second Philox pass over x in backward: 47 us -> ~10 us)
+                xdrop_b16 = torch.empty((M, In), device=dev, dtype=torch.bfloat16) if keep else None
+                call("deer_dropout_cast16", ptr(x), x16.data_ptr(), None if xdrop_b16 is None else xdrop_b16.data_ptr(),
+                     M * In, float(drop[0]), drop[1], drop[2], ptr(ctx.drop_step))
+                ctx.xdrop_b16 = xdrop_b16
             elif (x16_in is not None and x16_in.dtype == torch.float16 and x16_in.numel() == M * In and In % 8 == 0
                   and x16_in.is_contiguous()):
                 x16 = x16_in.view(M, In)                      # the producer kernel's FP16 shadow: no cast pass
@@ -1149,7 +1172,7 @@ class _BiLSTMLayerCluster(torch.autograd.Function):
         T, B, In, H = ctx.dims
         G = 4 * H
         dev = x.device
-        dh = dh.contiguous()
+        dh = torch.zeros((T, B, 2 * H), device=dev, dtype=torch.float32) if dh is None else dh.contiguous()
         dpre = ctx.pre
         hb16 = ctx.hb16
         ctx.pre = ctx.hb16 = None
@@ -1168,7 +1191,10 @@ class _BiLSTMLayerCluster(torch.autograd.Function):
         dx = None
         drop = ctx.drop
         if use16:
-            if drop is not None:                               # the same mask, regenerated while casting to bf16
+            if drop is not None and ctx.xdrop_b16 is not None:
+                xb16 = ctx.xdrop_b16                           # written by the forward's dropout + cast pass
+                ctx.xdrop_b16 = None
+            elif drop is not None:                             # the same mask, regenerated while casting to bf16
                 xb16 = torch.empty((M, In), device=dev, dtype=torch.bfloat16)
                 call("deer_dropout_cast16", ptr(x), None, xb16.data_ptr(), M * In, float(drop[0]), drop[1], drop[2],
                      ptr(ctx.drop_step))

@@ -161,14 +161,46 @@ class DEERDataParallelTrainer:
         # Gradient exchange overlapped with BPTT: the audio encoder's parameters lead the flat buffer and its backward
         # (the LSTM recurrence, on its own stream) is the tail of the step, so everything behind them is all-reduced
         # as soon as the video / text / fusion / head backward has been issued, beside the audio backward.
-        # Measured at N = 2 (B200, NVLink): 4.93 ms with the early exchange vs 4.90 ms without -- the 37 MB all-reduce
-        # is not what a step loses against one GPU -- so it is OFF by default.
+        # Measured (round 2, B200 NVLink, graph replay): N = 2: 4.38 ms per step with one all-reduce at the end vs 4.39 ms
+        # with the bucketed early exchange on a 32-CTA communicator, 4.53 ms on 8 CTAs, 5.12 ms on 2 CTAs (the collective
+        # no longer fits the window); N = 8: 4.48 vs 4.53 ms.  The 2-rank timeline (profiles/r2_step_timeline_n2.txt)
+        # shows what a step loses against one GPU: +43 us for the loss-statistics all-reduce between the two loss phases
+        # and 109 us for the gradient all-reduce -- hiding the latter costs as much as it saves, because any CTA that is
+        # resident beside the recurrence kernels pushes some of their 32 clusters into a second wave.  OFF by default.
         self.overlap_exchange = False
         self._audio_end = self.flat.leading_prefix_end("audio_encoder.")
+        # Bucketed exchange (overlap_exchange): [0, _layer0_end) = the first LSTM layer (its gradients are the LAST to
+        # complete), [_layer0_end, _audio_end) = rest of the audio encoder, [_audio_end, numel) = everything else.  The two
+        # later buckets are all-reduced from a side stream on a separate NCCL communicator limited to `exchange_ctas`
+        # CTAs, so that the collective fits beside the 128 CTAs of the recurrence kernels instead of pushing their
+        # clusters into a second wave; only the first layer's 0.7 M gradients remain for the end of the step.
+        self._layer0_end = self._leading_match_end(lambda n: n.startswith("audio_encoder.lstm.") and "_l0" in n)
+        self.exchange_ctas = 8
+        self._comm_group = None
+        self._comm_stream = None
         self._grads_reduced = False
         self.last_losses: Optional[torch.Tensor] = None
 
     # ------------------------------------------------------------------ pieces
+    def _leading_match_end(self, pred) -> int:
+        """End offset of the run of parameters at the START of the flat buffer whose names satisfy `pred`."""
+        f = self.flat
+        for n, o in zip(f.names, f.offsets):
+            if not pred(n):
+                return o
+        return f.numel
+
+    def _comm(self):
+        """(low-CTA NCCL communicator, launch stream) of the overlapped gradient buckets; created collectively on first use."""
+        if self._comm_group is None:
+            opts = dist.ProcessGroupNCCL.Options()
+            opts.config.max_ctas = int(self.exchange_ctas)
+            opts.config.min_ctas = 1
+            ranks = dist.get_process_group_ranks(self.pg) if self.pg is not None else None
+            self._comm_group = dist.new_group(ranks=ranks, backend="nccl", pg_options=opts)
+            self._comm_stream = torch.cuda.Stream()
+        return self._comm_group, self._comm_stream
+
     def _allreduce(self, t: torch.Tensor):
         if self.world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.pg)
@@ -204,29 +236,46 @@ class DEERDataParallelTrainer:
                                             task_weights=self.task_weights, want_grad=True,
                                             grad_scale=scale, stats_hook=hook, global_batch=gb)
         ops.mark("loss_done")
-        state = {}
-        handle = None
+        works = []
+        handles = []
         fence = getattr(getattr(model, "video_encoder", None), "_first_bwd_node", None)
+        lstm_nodes = getattr(getattr(model, "audio_encoder", None), "_lstm_bwd_nodes", None) or []
         if (self.world > 1 and self.overlap_exchange and fence is not None and ev.is_cuda and
                 0 < self._audio_end < self.flat.numel and ops.branch_streams_enabled()):
-            rest = self.flat.grads[self._audio_end:]
+            group, cs = self._comm()
+            grads = self.flat.grads
 
-            def _early_exchange(*_):
-                # runs on the autograd thread right after the LAST video/text/fusion/head backward node (the video
-                # encoder's first op has the lowest sequence number on the main stream): every gradient behind the
-                # audio block is complete once the main and weight-gradient streams drain; the audio backward has not
-                # been issued yet and runs beside this all-reduce
-                ops.join_wgrad_stream()
-                state["work"] = dist.all_reduce(rest, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+            def _bucket(lo, hi):
+                # issued from the autograd thread inside a node hook: the collective is launched on the communication
+                # stream once the stream of that node AND the weight-gradient stream have drained up to here; neither
+                # of them waits for it
+                def hook(*_):
+                    cs.wait_stream(torch.cuda.current_stream())
+                    cs.wait_stream(ops._wgrad_stream())
+                    with torch.cuda.stream(cs):
+                        works.append(dist.all_reduce(grads[lo:hi], op=dist.ReduceOp.SUM, group=group, async_op=True))
+                return hook
 
-            handle = fence.register_hook(_early_exchange)
+            # (1) right after the LAST video/text/fusion/head backward node (the video encoder's first op has the lowest
+            # sequence number on the main stream): every gradient behind the audio block is complete
+            handles.append(fence.register_hook(_bucket(self._audio_end, self.flat.numel)))
+            # (2) right after the BPTT + weight-gradient GEMMs of LSTM layer 1 (audio stream): the rest of the audio
+            # encoder; it travels beside the BPTT of layer 0
+            tail_lo = 0
+            if len(lstm_nodes) >= 2 and lstm_nodes[1] is not None and 0 < self._layer0_end < self._audio_end:
+                handles.append(lstm_nodes[1].register_hook(_bucket(self._layer0_end, self._audio_end)))
+                tail_lo = self._layer0_end
+            else:
+                tail_lo = self._audio_end
         ev.backward(dE)
-        if handle is not None:
-            handle.remove()
+        for h_ in handles:
+            h_.remove()
         ops.join_wgrad_stream()   # deferred weight-gradient GEMMs of the small layers (ops._Linear.backward)
-        if "work" in state:
-            dist.all_reduce(self.flat.grads[:self._audio_end], op=dist.ReduceOp.SUM, group=self.pg)
-            state["work"].wait()
+        if works:
+            # (3) what is left: the first LSTM layer (or the whole audio block), on the full-bandwidth communicator
+            dist.all_reduce(self.flat.grads[:tail_lo], op=dist.ReduceOp.SUM, group=self.pg)
+            for w in works:
+                w.wait()
             self._grads_reduced = True
         self.last_losses = losses
         return losses
@@ -259,6 +308,7 @@ class DEERDataParallelTrainer:
         if not self._grads_reduced:
             self._allreduce(f.grads)
         self._grads_reduced = False
+        ops.mark("grads_exchanged")
         call("deer_sumsq", ptr(f.grads), f.numel, ptr(self.sumsq))
         for g, lo, hi in f.group_bounds:
             n = hi - lo
