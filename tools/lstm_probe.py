@@ -38,8 +38,12 @@ def main():
     ap.add_argument("--skip-bwd", action="store_true")
     ap.add_argument("--prof", action="store_true")
     ap.add_argument("--dual", type=int, default=1)
+    ap.add_argument("--stasync", type=int, default=1)
+    ap.add_argument("--halfsplit", type=int, default=3)
     a = ap.parse_args()
     _lib.set_option(9, a.dual)
+    _lib.set_option(12, a.stasync)
+    _lib.set_option(13, a.halfsplit)
     _lib.set_option(2, a.ts)
     _lib.set_option(3, a.tile)
     dev = "cuda"

@@ -33,6 +33,8 @@ extern int g_h16_pair;
 extern int g_nig_pipe;
 extern int g_lstm_dual;
 extern int g_lstm_keep16;
+extern int g_lstm_stasync;
+extern int g_lstm_halfsplit;
 extern int g_lstm_colsplit;
 extern int g_tf32_pair;
 bool gemm_tf32_pair_supported(int transA, int transB, int M, int N, int K, long long ldc, const float* bias, int act,
@@ -103,6 +105,12 @@ int deer_set_option(int option, int value) {
       return DEER_OK;
     case DEER_OPT_LSTM_DUAL:
       g_lstm_dual = value;
+      return DEER_OK;
+    case DEER_OPT_LSTM_HALFSPLIT:
+      g_lstm_halfsplit = value & 3;
+      return DEER_OK;
+    case DEER_OPT_LSTM_STASYNC:
+      g_lstm_stasync = value ? 1 : 0;
       return DEER_OK;
     case DEER_OPT_LSTM_KEEP16:
       g_lstm_keep16 = value ? 1 : 0;

@@ -61,6 +61,14 @@ __device__ __forceinline__ void bulk_copy_to_peer(uint32_t dst_cluster, uint32_t
                "r"(src_cta), "r"(bytes), "r"(mbar_cluster)
                : "memory");
 }
+// asynchronous 16-byte store into the shared memory of a cluster peer; its completion (16 bytes) is counted on the
+// peer's mbarrier -- no staging fence, no bulk-copy descriptor through the TMA unit
+__device__ __forceinline__ void st_async_v4(uint32_t dst_cluster, uint4 v, uint32_t mbar_cluster) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(
+                   dst_cluster),
+               "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(mbar_cluster)
+               : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t raddr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
 }
@@ -206,6 +214,7 @@ struct LstmClusterParams {
   int T, B, ntiles, keep;
   long long* prof;     // optional clock64 trace of block 0 (tools/lstm_probe.py --prof), else null
   int keep16;          // 1: the kept gates / cell states are FP16 (same blocked order, half the bytes), 0: fp32
+  int stasync;         // forward h all-gather: 1 = per-lane st.async stores into the peers' B operand, 0 = bulk copies
 };
 constexpr int Q_PROF_S0 = 64, Q_PROF_STEPS = 4, Q_PROF_SLOTS = 8;
 #define Q_PROF(slot)                                                                               \
@@ -225,16 +234,24 @@ constexpr int Q_PROF_S0 = 64, Q_PROF_STEPS = 4, Q_PROF_SLOTS = 8;
 // tile's batch columns (a warp may read its TMEM lane quadrant at any column): the gate epilogue / cell update /
 // exchange of a step -- a latency-bound chain with only two warps per scheduler -- runs at half the length per warp.
 // The kept gate / cell layouts stay those of the 8-warp kernel, so the BPTT kernel is unchanged.
+// G = 2 with CS = 2 ("half split", HS; N = 16): the two column halves of ONE 16-column tile run as two INDEPENDENT
+// recurrences -- own 8 compute warps, accumulators, B-operand tiles (8 valid rows of a 16-row tile; the MMA stays N = 16,
+// the tensor pipe is 90 % idle anyway) and barriers, sharing the resident W_hh and the MMA warp.  A step of one half is a
+// serial chain MMA (420 cycles) -> gate epilogue -> cell update -> DSMEM all-gather (750-900 cycles from "h computed" to
+// "the peers' MMA warps see it", whichever transport is used); with two halves in flight one half's exchange flies while
+// the other half's gates are computed, on all 128 SMs of a B = 256 batch.  Same kept layouts as the 8-warp kernel.
 template <int N, bool TS, int G, int CS = 1>
-__global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(G * CS * 256 + 32, 1)
+__global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__((G == 2 && CS == 2 ? 512 : G * CS * 256) + 32, 1)
     lstm_fwd_cluster_kernel(const LstmClusterParams p) {
   DEER_PDL_ENTRY();
-  static_assert(CS == 1 || (CS == 2 && G == 1 && N == 16), "column split: one 16-column tile, two warp sets");
+  static_assert(CS == 1 || (CS == 2 && N == 16), "column split: one 16-column tile, two warp sets");
+  constexpr bool HS = (G == 2 && CS == 2);
   using L = QLayout<N>;
   constexpr int NW = N / CS;             // batch columns per compute warp
   constexpr int NQ = NW / 4;             // batch columns per cell thread
   constexpr int ROWF = NW + 4;           // padded fp32 row of the per-warp transpose tile
-  constexpr int NCW = 8 * G * CS;        // compute warps
+  constexpr int NCW = HS ? 16 : 8 * G * CS;   // compute warps
+  constexpr uint32_t XBYTES = HS ? L::HB_BYTES / 2 : L::HB_BYTES;   // bytes of h landing in one B-operand tile per step
   constexpr int MMAW = NCW;              // index of the MMA-issuing warp
   constexpr int NTHREADS = NCW * 32 + 32;
   constexpr int ACT_TOTAL = NCW * 32 * ROWF * 4;   // per-warp activation transpose tiles
@@ -262,8 +279,9 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(G * CS * 256 + 32, 
   uint64_t* mma_done = mma_done_all + grp;
   const uint32_t r = cluster_ctarank();
   const int cid = blockIdx.x / QC;
-  const int ctile = cid % p.ntiles, dir = cid / p.ntiles;   // p.ntiles counts CTA tiles of G*N batch columns
-  const int tile = ctile * G + grp;
+  const int ctile = cid % p.ntiles, dir = cid / p.ntiles;   // p.ntiles counts CTA tiles of G*N (HS: N) batch columns
+  const int tile = HS ? ctile : ctile * G + grp;
+  const int ntiles_all = HS ? p.ntiles : p.ntiles * G;      // N-column tiles per direction (the kept layouts' unit)
   const int b0 = tile * N;
   const int T = p.T, B = p.B;
   const float* __restrict__ W = dir ? p.w_rev : p.w_fwd;
@@ -278,8 +296,8 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(G * CS * 256 + 32, 
     fence_barrier_init();
     // each phase of h_full[b] = one arming arrival + N x 256 fp16 of h landing from the 4 CTAs (async proxy)
     for (int g = 0; g < G; g++) {
-      if (T > 1) mbar_expect_tx(&h_full_all[2 * g + 0], L::HB_BYTES);
-      if (T > 2) mbar_expect_tx(&h_full_all[2 * g + 1], L::HB_BYTES);
+      if (T > 1) mbar_expect_tx(&h_full_all[2 * g + 0], XBYTES);
+      if (T > 2) mbar_expect_tx(&h_full_all[2 * g + 1], XBYTES);
     }
   }
   // two allocations (accumulators 64 columns, resident operand 256) instead of one 512-column block: the 192 columns
@@ -351,9 +369,16 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(G * CS * 256 + 32, 
             if (leader) mbar_arrive(md);  // h_{-1} = 0: the gates of step 0 are the input projection alone
             continue;
           }
-          mbar_wait(&hf[(s - 1) & 1], (uint32_t)(((s - 1) >> 1) & 1));
+          if (p.stasync) {
+            // the tile was written by the peers' (generic-proxy) st.async stores: acquire at cluster scope, then order
+            // them before this warp's async-proxy reads (tcgen05.mma operand fetch)
+            mbar_wait_cluster(&hf[(s - 1) & 1], (uint32_t)(((s - 1) >> 1) & 1));
+            fence_proxy_async_smem();
+          } else {
+            mbar_wait(&hf[(s - 1) & 1], (uint32_t)(((s - 1) >> 1) & 1));
+          }
           if (leader && g == 0) Q_PROF(0);
-          if (leader && s + 2 < T) mbar_expect_tx(&hf[(s - 1) & 1], L::HB_BYTES);  // re-arm for h_{s+1}
+          if (leader && s + 2 < T) mbar_expect_tx(&hf[(s - 1) & 1], XBYTES);  // re-arm for h_{s+1}
           tc_fence_after();
           const uint32_t hb = smem_u32(hbuf_all) + (2 * g + ((s - 1) & 1)) * L::HB_BYTES;
           const uint32_t tg = tb + (uint32_t)(g * 2 * N);
@@ -386,7 +411,8 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(G * CS * 256 + 32, 
     const int j = lane >> 2, g = lane & 3;        // gate-row role: unit j of this warp, gate g
     const int ul = a * 32 + sub * 8 + j;          // unit inside the CTA
     const int ug = (int)r * QU + ul;              // unit inside the direction
-    const uint32_t tacc = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(grp * 2 * N + a * N + chalf * NW);
+    const uint32_t tacc = tmem_base + ((uint32_t)(sub * 32) << 16) +
+                          (uint32_t)(grp * 2 * N + a * N + (HS ? 0 : chalf * NW));
     float* sa = stage_act_all + wslot * (32 * ROWF);
     __half* sh_base = stage_h_all + wslot * (2 * NW * 8);
     const int bw0 = b0 + chalf * NW;              // first batch column of this warp
@@ -416,8 +442,8 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(G * CS * 256 + 32, 
       }
     };
     // blocked save area of this warp: ((((t*2+dir)*ntiles+tile)*4+r)*8+warp) blocks of 4*NQ*32 (gates) / NQ*32 (c)
-    const long long blk_w = ((long long)dir * (p.ntiles * G) + tile) * 32 + (int)r * 8 + warp;
-    const long long blk_t = 2LL * (p.ntiles * G) * 32;
+    const long long blk_w = ((long long)dir * ntiles_all + tile) * 32 + (int)r * 8 + warp;
+    const long long blk_t = 2LL * ntiles_all * 32;
     load_pre(0);
     for (int s = 0; s < T; s++) {
       const int t = dir ? T - 1 - s : s;
@@ -496,13 +522,25 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(G * CS * 256 + 32, 
         // all-gather FIRST (it is the only thing the next step waits for): this warp's [N cols x 8 units] fp16 block is
         // k-chunk 8r+4a+sub of every CTA's B operand; one async-proxy bulk copy per destination, completion counted on
         // the destination's h_full barrier
+        const uint32_t dst = smem_u32(hbuf) + (s & 1) * L::HB_BYTES + ((int)r * 8 + 4 * a + sub) * (N * 16) +
+                             (HS ? 0 : chalf * (NW * 16));   // HS: the half's own tile, rows 0 .. 7
+        if (p.stasync) {
+          // lane n sends column n of the block (8 units x fp16 = one 16-byte row of the B operand) straight to the four
+          // CTAs: posted stores, completion counted on each destination's h_full barrier
+          __syncwarp();
+          if (lane < NW) {
+            const uint4 hv8 = *reinterpret_cast<const uint4*>(sh + lane * 8);
+            const uint32_t bar = smem_u32(&h_full[s & 1]);
+#pragma unroll
+            for (uint32_t d = 0; d < QC; d++) st_async_v4(mapa_u32(dst + lane * 16, d), hv8, mapa_u32(bar, d));
+          }
+        } else {
         fence_proxy_async_smem();
         __syncwarp();
         if (lane < QC) {
-          const uint32_t dst = smem_u32(hbuf) + (s & 1) * L::HB_BYTES + ((int)r * 8 + 4 * a + sub) * (N * 16) +
-                               chalf * (NW * 16);
           bulk_copy_to_peer(mapa_u32(dst, (uint32_t)lane), smem_u32(sh), NW * 16,
                             mapa_u32(smem_u32(&h_full[s & 1]), (uint32_t)lane));
+        }
         }
         if (warp_id == 0 && lane == 0) Q_PROF(5);
       } else {
@@ -520,6 +558,18 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(G * CS * 256 + 32, 
           // are one half of the float4 that lane (j, chalf*2 + q/2) of the 8-warp kernel would store
           const int lane8 = j * 4 + chalf * 2 + (q >> 1);
           const int eo = (q & 1) * 2;
+          if (p.keep16) {
+            // FP16 kept state: this thread's two columns are one 32-bit word of each of the (i,f) / (g,o) 16-byte groups
+            // and of the 8-byte c group that lane8 of the 8-warp kernel stores
+            uint32_t* gw = reinterpret_cast<uint32_t*>(reinterpret_cast<__half*>(p.gact) + blk * 512);
+            uint32_t* cw = reinterpret_cast<uint32_t*>(reinterpret_cast<__half*>(p.c_all) + blk * 128);
+            const int h2 = eo >> 1;
+            __stcs(gw + lane8 * 4 + h2, pack_h2(gi[0], gi[1]));
+            __stcs(gw + lane8 * 4 + 2 + h2, pack_h2(gf[0], gf[1]));
+            __stcs(gw + (32 + lane8) * 4 + h2, pack_h2(gg[0], gg[1]));
+            __stcs(gw + (32 + lane8) * 4 + 2 + h2, pack_h2(go[0], go[1]));
+            __stcs(cw + lane8 * 2 + h2, pack_h2(cst[0], cst[1]));
+          } else {
           float* gs = p.gact + blk * 512 + lane8 * 4 + eo;
           float* cs = p.c_all + blk * 128 + lane8 * 4 + eo;
           __stcs(reinterpret_cast<float2*>(gs + 0 * 128), make_float2(gi[0], gi[1]));
@@ -527,6 +577,7 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(G * CS * 256 + 32, 
           __stcs(reinterpret_cast<float2*>(gs + 2 * 128), make_float2(gg[0], gg[1]));
           __stcs(reinterpret_cast<float2*>(gs + 3 * 128), make_float2(go[0], go[1]));
           __stcs(reinterpret_cast<float2*>(cs), make_float2(cst[0], cst[1]));
+          }
         }
       } else
       if (p.keep) {
@@ -738,10 +789,18 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
     const long long blk_w = ((long long)dir * p.ntiles + tile) * 32 + (int)r * 8 + warp;
     const long long blk_t = 2LL * p.ntiles * 32;
     float sdb[4] = {0.f, 0.f, 0.f, 0.f};          // bias gradient of (unit, 4 gates) over this thread's columns, all t
-    float vi[NQ], vf[NQ], vg[NQ], vo[NQ], vc[NQ], vcp[NQ], vdh[NQ];
-    uint4 ra[NQ / 4], rb[NQ / 4];                 // K16: raw FP16 bits of the next step's (i,f) / (g,o) gates
-    uint2 rc[NQ / 4], rcp[NQ / 4];                //      ... and of c_t / c_{t-1}
-    auto load_step = [&](int s) {
+    // Operands of a step -- the kept gates / cell states and dh_out -- are fetched TWO steps ahead into one of two
+    // register sets (the loop body is instantiated once per set, so no register is ever indexed dynamically): ncu put
+    // 22 % of all stall samples of the one-step-ahead version on the first FP16 -> FP32 convert of a step, i.e. on the
+    // DRAM round trip of loads issued only half a step (~0.7 us) earlier.
+    constexpr bool DEEP = K16 && N == 16;         // (32-column tiles / fp32 kept state: two sets would spill -- one step ahead)
+    struct Kept {
+      uint4 ra[NQ / 4], rb[NQ / 4];               // K16: raw FP16 bits of the (i,f) / (g,o) gates
+      uint2 rc[NQ / 4], rcp[NQ / 4];              //      ... and of c_t / c_{t-1}
+      float4 f[K16 ? 1 : 6 * (NQ / 4)];           // fp32 kept state: i, f, g, o, c, c_prev per 4-column chunk
+      float vdh[NQ];
+    };
+    auto load_step = [&](int s, Kept& k) {
       const int t = dir ? s : T - 1 - s;            // reverse of the forward order
       const int tp = dir ? t + 1 : t - 1;           // forward-previous time step (c_{prev})
       const bool first = dir ? (t == T - 1) : (t == 0);
@@ -753,47 +812,44 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
                                                           ((long long)tp * blk_t + blk_w) * (NQ * 32)) + lane;
 #pragma unroll
         for (int i = 0; i < NQ; i += 4) {
-          ra[i / 4] = __ldcs(gs + (i / 4 * 2 + 0) * 32);
-          rb[i / 4] = __ldcs(gs + (i / 4 * 2 + 1) * 32);
-          rc[i / 4] = __ldcs(cs + (i / 4) * 32);
-          rcp[i / 4] = first ? make_uint2(0u, 0u) : __ldcs(cps + (i / 4) * 32);
+          k.ra[i / 4] = __ldcs(gs + (i / 4 * 2 + 0) * 32);
+          k.rb[i / 4] = __ldcs(gs + (i / 4 * 2 + 1) * 32);
+          k.rc[i / 4] = __ldcs(cs + (i / 4) * 32);
+          k.rcp[i / 4] = first ? make_uint2(0u, 0u) : __ldcs(cps + (i / 4) * 32);
         }
       } else {
-      const float4* gs = reinterpret_cast<const float4*>(p.gact + blk * (4 * NQ * 32)) + lane;
-      const float4* cs = reinterpret_cast<const float4*>(p.c_all + blk * (NQ * 32)) + lane;
-      const float4* cps = reinterpret_cast<const float4*>(p.c_all + ((long long)tp * blk_t + blk_w) * (NQ * 32)) + lane;
+        const float4* gs = reinterpret_cast<const float4*>(p.gact + blk * (4 * NQ * 32)) + lane;
+        const float4* cs = reinterpret_cast<const float4*>(p.c_all + blk * (NQ * 32)) + lane;
+        const float4* cps = reinterpret_cast<const float4*>(p.c_all + ((long long)tp * blk_t + blk_w) * (NQ * 32)) + lane;
 #pragma unroll
-      for (int i = 0; i < NQ; i += 4) {
-        const float4 a0 = __ldcs(gs + (0 * NQ + i) * 8), a1 = __ldcs(gs + (1 * NQ + i) * 8);
-        const float4 a2 = __ldcs(gs + (2 * NQ + i) * 8), a3 = __ldcs(gs + (3 * NQ + i) * 8);
-        const float4 a4 = __ldcs(cs + i * 8);
-        const float4 a5 = first ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldcs(cps + i * 8);
-        vi[i] = a0.x; vi[i + 1] = a0.y; vi[i + 2] = a0.z; vi[i + 3] = a0.w;
-        vf[i] = a1.x; vf[i + 1] = a1.y; vf[i + 2] = a1.z; vf[i + 3] = a1.w;
-        vg[i] = a2.x; vg[i + 1] = a2.y; vg[i + 2] = a2.z; vg[i + 3] = a2.w;
-        vo[i] = a3.x; vo[i + 1] = a3.y; vo[i + 2] = a3.z; vo[i + 3] = a3.w;
-        vc[i] = a4.x; vc[i + 1] = a4.y; vc[i + 2] = a4.z; vc[i + 3] = a4.w;
-        vcp[i] = a5.x; vcp[i + 1] = a5.y; vcp[i + 2] = a5.z; vcp[i + 3] = a5.w;
-      }
+        for (int i = 0; i < NQ; i += 4) {
+          float4* f = k.f + 6 * (i / 4);
+          f[0] = __ldcs(gs + (0 * NQ + i) * 8);
+          f[1] = __ldcs(gs + (1 * NQ + i) * 8);
+          f[2] = __ldcs(gs + (2 * NQ + i) * 8);
+          f[3] = __ldcs(gs + (3 * NQ + i) * 8);
+          f[4] = __ldcs(cs + i * 8);
+          f[5] = first ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldcs(cps + i * 8);
+        }
       }
 #pragma unroll
       for (int i = 0; i < NQ; i++) {
         const int b = b0 + q * NQ + i;
-        vdh[i] = (b < B) ? __ldcs(p.dh_out + ((long long)t * B + b) * (2 * QH) + dir * QH + ug) : 0.f;
+        k.vdh[i] = (b < B) ? __ldcs(p.dh_out + ((long long)t * B + b) * (2 * QH) + dir * QH + ug) : 0.f;
       }
     };
-    load_step(0);
-    for (int s = 0; s < T; s++) {
+    auto body = [&](const int s, Kept& kept) {
       const int t = dir ? s : T - 1 - s;
+      float vi[NQ], vf[NQ], vg[NQ], vo[NQ], vc[NQ], vcp[NQ];
       float dh[NQ];
 #pragma unroll
-      for (int i = 0; i < NQ; i++) dh[i] = vdh[i];
+      for (int i = 0; i < NQ; i++) dh[i] = kept.vdh[i];
       if constexpr (K16) {
         auto h2f = [](uint32_t v) { return __half22float2(*reinterpret_cast<const __half2*>(&v)); };
 #pragma unroll
         for (int i = 0; i < NQ; i += 4) {
-          const uint4 a = ra[i / 4], b = rb[i / 4];
-          const uint2 c = rc[i / 4], cp = rcp[i / 4];
+          const uint4 a = kept.ra[i / 4], b = kept.rb[i / 4];
+          const uint2 c = kept.rc[i / 4], cp = kept.rcp[i / 4];
           float2 f;
           f = h2f(a.x); vi[i] = f.x; vi[i + 1] = f.y; f = h2f(a.y); vi[i + 2] = f.x; vi[i + 3] = f.y;
           f = h2f(a.z); vf[i] = f.x; vf[i + 1] = f.y; f = h2f(a.w); vf[i + 2] = f.x; vf[i + 3] = f.y;
@@ -802,6 +858,20 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
           f = h2f(c.x); vc[i] = f.x; vc[i + 1] = f.y; f = h2f(c.y); vc[i + 2] = f.x; vc[i + 3] = f.y;
           f = h2f(cp.x); vcp[i] = f.x; vcp[i + 1] = f.y; f = h2f(cp.y); vcp[i + 2] = f.x; vcp[i + 3] = f.y;
         }
+      } else {
+#pragma unroll
+        for (int i = 0; i < NQ; i += 4) {
+          const float4* f = kept.f + 6 * (i / 4);
+          vi[i] = f[0].x; vi[i + 1] = f[0].y; vi[i + 2] = f[0].z; vi[i + 3] = f[0].w;
+          vf[i] = f[1].x; vf[i + 1] = f[1].y; vf[i + 2] = f[1].z; vf[i + 3] = f[1].w;
+          vg[i] = f[2].x; vg[i + 1] = f[2].y; vg[i + 2] = f[2].z; vg[i + 3] = f[2].w;
+          vo[i] = f[3].x; vo[i + 1] = f[3].y; vo[i + 2] = f[3].z; vo[i + 3] = f[3].w;
+          vc[i] = f[4].x; vc[i + 1] = f[4].y; vc[i + 2] = f[4].z; vc[i + 3] = f[4].w;
+          vcp[i] = f[5].x; vcp[i + 1] = f[5].y; vcp[i + 2] = f[5].z; vcp[i + 3] = f[5].w;
+        }
+      }
+      if constexpr (DEEP) {
+        if (s + 2 < T) load_step(s + 2, kept);   // this set is free again: its next use is two steps away
       }
       if (s > 0) {
         mbar_wait(&part_full[(s - 1) & 1], (uint32_t)(((s - 1) >> 1) & 1));
@@ -860,7 +930,7 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
         }
       }
       if (s + 1 < T) {
-        load_step(s + 1);  // next step's operands stream in while the tensor core and the exchange run
+        if constexpr (!DEEP) load_step(s + 1, kept);   // one step ahead: streams in while the tensor core and the exchange run
         mbar_wait(mma_done, (uint32_t)(s & 1));
         if (warp == 0 && lane == 0) Q_PROF(4);
         tc_fence_after();
@@ -887,6 +957,19 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
         }
         if (warp == 0 && lane == 0) Q_PROF(5);
       }
+    };
+    if constexpr (DEEP) {
+      Kept set0, set1;
+      load_step(0, set0);
+      if (T > 1) load_step(1, set1);
+      for (int s = 0; s < T; s += 2) {
+        body(s, set0);
+        if (s + 1 < T) body(s + 1, set1);
+      }
+    } else {
+      Kept set0;
+      load_step(0, set0);
+      for (int s = 0; s < T; s++) body(s, set0);
     }
     if (p.db) {
       // db[dir, unit, gate] += sum over this cluster's samples and all T steps: fold the 4 column groups of a unit
@@ -911,10 +994,286 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
   }
 }
 
+// ================================================================================================ backward, half split
+// The BPTT counterpart of the forward kernel's half split (N = 16, resident operand in TMEM, FP16 kept state): the two
+// 8-column halves of a 16-column tile are two INDEPENDENT backward recurrences -- own 8 compute warps, dpre B-operand
+// tile (8 valid rows of 16; the MMA stays N = 16), accumulators, partial-dh slots and barriers; shared resident W_hh^T
+// slice and MMA warp.  One half's reduce-scatter flies while the other half's gate gradients are computed.  Layouts in
+// HBM (kept gates / cell states, dpre, dh) are exactly those of lstm_bwd_cluster_kernel.
+constexpr int HNV = 8;                                   // valid batch columns per half
+constexpr int HB_TILE = 16 * QH * 2;                     // B-operand tile of one half: 16 rows x 256 k bf16 (8 KB)
+constexpr int HPART = QC * QU * HNV * 2;                 // one partial-dh buffer of one half: [src][unit][8] bf16 (4 KB)
+constexpr int HPSTAGE = 8 * 2 * 32 * HNV * 2;            // per half: per-warp double-buffered [32 rows][8] bf16 (8 KB)
+constexpr int HTHREADS = 16 * 32 + 32;
+
+__global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(HTHREADS, 1)
+    lstm_bwd_half_kernel(const LstmClusterParams p) {
+  DEER_PDL_ENTRY();
+  constexpr int N = 16, NQ = HNV / 4;   // MMA N; batch columns per cell thread (2)
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* bsm_all = smem;                                                                   // [2 halves][HB_TILE]
+  __nv_bfloat16* part_all = reinterpret_cast<__nv_bfloat16*>(bsm_all + 2 * HB_TILE);         // [2][2 buffers][HPART]
+  __nv_bfloat16* pstage_all = part_all + 2 * 2 * (HPART / 2);                                // [2][HPSTAGE]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(pstage_all) + 2 * HPSTAGE);
+  // per half: part_full[2], b_ready, mma_done
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp_id = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grp = (warp_id >= 8 && warp_id < 16) ? 1 : 0;
+  const int warp = warp_id == 16 ? 8 : (warp_id & 7);
+  const uint32_t r = cluster_ctarank();
+  const int cid = blockIdx.x / QC;
+  const int tile = cid % p.ntiles, dir = cid / p.ntiles;
+  const int b0 = tile * N + grp * HNV;            // first batch column of this half
+  const int T = p.T, B = p.B;
+  const float* __restrict__ W = dir ? p.w_rev : p.w_fwd;
+  uint8_t* bsm = bsm_all + grp * HB_TILE;
+  __nv_bfloat16* part = part_all + grp * 2 * (HPART / 2);
+  __nv_bfloat16* pstage = pstage_all + grp * (HPSTAGE / 2);
+  uint64_t* part_full = bars + 4 * grp;
+  uint64_t* b_ready = bars + 4 * grp + 2;
+  uint64_t* mma_done = bars + 4 * grp + 3;
+
+  if (threadIdx.x == 0) {
+    for (int g = 0; g < 2; g++) {
+      mbar_init(&bars[4 * g + 0], 1);
+      mbar_init(&bars[4 * g + 1], 1);
+      mbar_init(&bars[4 * g + 2], 8);
+      mbar_init(&bars[4 * g + 3], 1);
+    }
+    fence_barrier_init();
+    for (int g = 0; g < 2; g++) {
+      if (T > 1) mbar_expect_tx(&bars[4 * g + 0], HPART);
+      if (T > 2) mbar_expect_tx(&bars[4 * g + 1], HPART);
+    }
+  }
+  if (warp_id == 16) {
+    tmem_alloc_more_follow(tmem_slot, 64);
+    tmem_alloc(tmem_slot + 1, 256);
+  }
+  // the unused rows 8..15 of both B-operand tiles: zero once (they only feed accumulator columns nobody reads, but
+  // uninitialised shared memory may hold NaN patterns that would be harmless yet needlessly exercise the special paths)
+  for (int i = threadIdx.x; i < 2 * HB_TILE / 16; i += HTHREADS) reinterpret_cast<uint4*>(bsm_all)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_w = tmem_slot[1];
+  if (warp_id < 8) {
+    // resident A operand: A[m = hidden unit (2 x 128)][k = 4*unit_local + gate] = W_hh[gate*256 + 64r + unit_local][m]
+    const int a = warp >> 2, sub = warp & 3, m = a * 128 + sub * 32 + lane;
+#pragma unroll 1
+    for (int ch = 0; ch < 4; ch++) {
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; i++) {
+        const int k0 = ch * 64 + 2 * i;
+        const float f0 = __ldg(W + (size_t)((k0 & 3) * QH + (int)r * QU + (k0 >> 2)) * QH + m);
+        const float f1 = __ldg(W + (size_t)(((k0 + 1) & 3) * QH + (int)r * QU + ((k0 + 1) >> 2)) * QH + m);
+        reinterpret_cast<uint32_t*>(v)[i] = pack_bf2(f0, f1);
+      }
+      tmem_st32(tmem_w + ((uint32_t)(sub * 32) << 16) + (uint32_t)(a * 128 + ch * 32), v);
+    }
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  cluster_sync_all();
+
+  if (warp == 8) {
+    // =================================================================== MMA issuer: the halves take turns
+    constexpr uint32_t idesc = make_idesc_f16(1, 128, N);
+    const uint32_t tb = warp_uniform(tmem_base);
+    const uint32_t tw = warp_uniform(tmem_w);
+    const bool leader = elect_one();
+    for (int s = 0; s + 1 < T; s++) {
+#pragma unroll
+      for (int g = 0; g < 2; g++) {
+        uint64_t* pf = bars + 4 * g;
+        mbar_wait(&bars[4 * g + 2], (uint32_t)(s & 1));
+        if (leader && g == 0) Q_PROF(0);
+        // every cell thread of the half has consumed the partials of step s-1: re-arm that buffer for step s+1
+        if (leader && s >= 1 && s + 2 < T) mbar_expect_tx(&pf[(s - 1) & 1], HPART);
+        tc_fence_after();
+        const uint32_t bb = smem_u32(bsm_all) + g * HB_TILE;
+        const uint32_t tg = tb + (uint32_t)(g * 2 * N);
+        if (leader) {
+#pragma unroll
+          for (int a = 0; a < 2; a++) {
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+              const uint64_t bd = make_smem_desc(bb + (k >> 2) * (N * 128) + (k & 3) * 32, 16, 1024, 2);
+              umma_f16_ts(tg + a * N, tw + a * 128 + k * 8, bd, idesc, k > 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(&bars[4 * g + 3]);
+          if (g == 0) Q_PROF(1);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    const int a = warp >> 2, sub = warp & 3;
+    const int j = lane >> 2, q = lane & 3;        // cell role: unit j of this warp, columns [q*2, q*2+2) of the half
+    const int ul = a * 32 + sub * 8 + j;
+    const int ug = (int)r * QU + ul;
+    const uint32_t tacc = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(grp * 2 * N + a * N);
+    const uint32_t dst_cta = (uint32_t)(2 * a + (sub >> 1));
+    float dc[NQ] = {0.f, 0.f};
+    // kept state: the 8-warp kernels' blocked layout; this thread's two columns are one 32-bit word of the (i,f) and
+    // (g,o) 16-byte groups / the 8-byte c group of lane8
+    const long long blk_w = ((long long)dir * p.ntiles + tile) * 32 + (int)r * 8 + warp;
+    const long long blk_t = 2LL * p.ntiles * 32;
+    const int lane8 = j * 4 + grp * 2 + (q >> 1), h2 = q & 1;
+    float sdb[4] = {0.f, 0.f, 0.f, 0.f};
+    struct Kept {                                 // operands of one step, fetched two steps ahead (see the 8-warp kernel)
+      uint32_t ri, rf, rg, ro, rc, rcp;           // raw FP16 pairs
+      float vdh[NQ];
+    };
+    auto load_step = [&](int s, Kept& k) {
+      const int t = dir ? s : T - 1 - s;
+      const int tp = dir ? t + 1 : t - 1;
+      const bool first = dir ? (t == T - 1) : (t == 0);
+      const long long blk = (long long)t * blk_t + blk_w;
+      const uint32_t* gw = reinterpret_cast<const uint32_t*>(reinterpret_cast<const __half*>(p.gact) + blk * 512);
+      const uint32_t* cw = reinterpret_cast<const uint32_t*>(reinterpret_cast<const __half*>(p.c_all) + blk * 128);
+      const uint32_t* cpw = reinterpret_cast<const uint32_t*>(reinterpret_cast<const __half*>(p.c_all) +
+                                                              ((long long)tp * blk_t + blk_w) * 128);
+      k.ri = __ldcs(gw + lane8 * 4 + h2);
+      k.rf = __ldcs(gw + lane8 * 4 + 2 + h2);
+      k.rg = __ldcs(gw + (32 + lane8) * 4 + h2);
+      k.ro = __ldcs(gw + (32 + lane8) * 4 + 2 + h2);
+      k.rc = __ldcs(cw + lane8 * 2 + h2);
+      k.rcp = first ? 0u : __ldcs(cpw + lane8 * 2 + h2);
+#pragma unroll
+      for (int i = 0; i < NQ; i++) {
+        const int b = b0 + q * NQ + i;
+        k.vdh[i] = (b < B) ? __ldcs(p.dh_out + ((long long)t * B + b) * (2 * QH) + dir * QH + ug) : 0.f;
+      }
+    };
+    auto h2f = [](uint32_t v) { return __half22float2(*reinterpret_cast<const __half2*>(&v)); };
+    auto body = [&](const int s, Kept& kept) {
+      const int t = dir ? s : T - 1 - s;
+      float dh[NQ] = {kept.vdh[0], kept.vdh[1]};
+      const float2 fi = h2f(kept.ri), ff = h2f(kept.rf), fg = h2f(kept.rg), fo = h2f(kept.ro), fc = h2f(kept.rc),
+                   fcp = h2f(kept.rcp);
+      const float vi[NQ] = {fi.x, fi.y}, vf[NQ] = {ff.x, ff.y}, vg[NQ] = {fg.x, fg.y}, vo[NQ] = {fo.x, fo.y};
+      const float vc[NQ] = {fc.x, fc.y}, vcp[NQ] = {fcp.x, fcp.y};
+      if (s + 2 < T) load_step(s + 2, kept);
+      if (s > 0) {
+        mbar_wait(&part_full[(s - 1) & 1], (uint32_t)(((s - 1) >> 1) & 1));
+        if (warp_id == 0 && lane == 0) Q_PROF(2);
+        const __nv_bfloat16* ps = part + ((s - 1) & 1) * (HPART / 2) + ul * HNV + q * NQ;
+#pragma unroll
+        for (int src = 0; src < QC; src++) {
+          const uint32_t v = *reinterpret_cast<const uint32_t*>(ps + src * (QU * HNV));
+          const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v));
+          dh[0] += f.x;
+          dh[1] += f.y;
+        }
+      }
+      const int kb = ul >> 4, ch = (ul & 15) >> 1;
+      float4 dp[NQ];
+      uint2 dp16[NQ];
+      float tcv[NQ];
+      tanh_pair(vc[0], vc[1], tcv[0], tcv[1]);
+#pragma unroll
+      for (int i = 0; i < NQ; i++) {
+        const float tc_ = tcv[i];
+        const float d_o = dh[i] * tc_;
+        const float dcc = fmaf(dh[i] * vo[i], 1.f - tc_ * tc_, dc[i]);
+        dc[i] = dcc * vf[i];
+        dp[i].x = dcc * vg[i] * vi[i] * (1.f - vi[i]);
+        dp[i].y = dcc * vcp[i] * vf[i] * (1.f - vf[i]);
+        dp[i].z = dcc * vi[i] * (1.f - vg[i] * vg[i]);
+        dp[i].w = d_o * vo[i] * (1.f - vo[i]);
+        dp16[i].x = pack_bf2(dp[i].x, dp[i].y);
+        dp16[i].y = pack_bf2(dp[i].z, dp[i].w);
+        if (s + 1 < T) {
+          const int n = q * NQ + i;           // row of the half's B-operand tile (0..7)
+          *reinterpret_cast<uint2*>(bsm + kb * (N * 128) + sw128(n, ch) + (ul & 1) * 8) = dp16[i];
+        }
+      }
+      if (s + 1 < T) {
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(b_ready);
+        if (warp_id == 0 && lane == 0) Q_PROF(3);
+      }
+#pragma unroll
+      for (int i = 0; i < NQ; i++) {
+        const int b = b0 + q * NQ + i;
+        if (b < B) {
+          const long long o = (((long long)t * B + b) * 2 + dir) * (4 * QH) + 4 * ug;
+          if (p.gates) __stcs(reinterpret_cast<float4*>(p.gates + o), dp[i]);
+          if (p.dpre16) *reinterpret_cast<uint2*>(p.dpre16 + o) = dp16[i];
+          sdb[0] += dp[i].x; sdb[1] += dp[i].y; sdb[2] += dp[i].z; sdb[3] += dp[i].w;
+        }
+      }
+      if (s + 1 < T) {
+        mbar_wait(mma_done, (uint32_t)(s & 1));
+        if (warp_id == 0 && lane == 0) Q_PROF(4);
+        tc_fence_after();
+        float x[HNV];
+        tmem_ld8(tacc, x);
+        tmem_ld_wait();
+        // reduce-scatter: this warp's 32 accumulator rows x 8 columns (hidden units of CTA dst_cta) -> that CTA's slot
+        __nv_bfloat16* st = pstage + (warp * 2 + (s & 1)) * (32 * HNV);
+        uint4 v;
+        v.x = pack_bf2(x[0], x[1]); v.y = pack_bf2(x[2], x[3]);
+        v.z = pack_bf2(x[4], x[5]); v.w = pack_bf2(x[6], x[7]);
+        *reinterpret_cast<uint4*>(st + lane * HNV) = v;
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          const uint32_t slot = smem_u32(part) + (uint32_t)(((s & 1) * QC + (int)r) * QU + (sub & 1) * 32) * (HNV * 2);
+          bulk_copy_to_peer(mapa_u32(slot, dst_cta), smem_u32(st), 32 * HNV * 2,
+                            mapa_u32(smem_u32(&part_full[s & 1]), dst_cta));
+        }
+        if (warp_id == 0 && lane == 0) Q_PROF(5);
+      }
+    };
+    Kept set0, set1;
+    load_step(0, set0);
+    if (T > 1) load_step(1, set1);
+    for (int s = 0; s < T; s += 2) {
+      body(s, set0);
+      if (s + 1 < T) body(s + 1, set1);
+    }
+    if (p.db) {
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        sdb[e] += __shfl_xor_sync(0xffffffffu, sdb[e], 1);
+        sdb[e] += __shfl_xor_sync(0xffffffffu, sdb[e], 2);
+      }
+      if (q == 0) {
+#pragma unroll
+        for (int e = 0; e < 4; e++) atomicAdd(p.db + dir * (4 * QH) + 4 * ug + e, sdb[e]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 64);
+    tmem_dealloc(tmem_w, 256);
+  }
+}
+constexpr int bwd_half_smem_bytes() {
+  constexpr int need = 2 * HB_TILE + 2 * 2 * HPART + 2 * HPSTAGE + 128 + 1024;
+  return need > 120 * 1024 ? need : 120 * 1024;   // one LSTM CTA per SM (see fwd_smem_bytes)
+}
+
 template <int N, bool TS, int G = 1, int CS = 1>
 constexpr int fwd_smem_bytes() {
   using L = QLayout<N>;
-  constexpr int NW = N / CS, NCW = 8 * G * CS;
+  constexpr int NW = N / CS, NCW = (G == 2 && CS == 2) ? 16 : 8 * G * CS;
   // >= 120 KB even in TS mode: one LSTM CTA per SM (two would not fit their 2 x 320 TMEM columns and the second would
   // spin in tcgen05.alloc); a TF32 GEMM CTA (100 KB, 128 columns) of another stream still fits beside it
   constexpr int need = (TS ? 0 : QW_BYTES) + G * 2 * L::HB_BYTES + NCW * 32 * (NW + 4) * 4 + NCW * 2 * NW * 16 + 64 + 1024;
@@ -934,6 +1293,8 @@ static int g_lstm_tile = 0;    // 0 auto, else forced N (16 or 32)
 int g_lstm_colsplit = 0;       // DEER_OPT_LSTM_COLSPLIT: 16 compute warps (two column halves) on 16-column tiles; measured: no gain (1.444 vs 1.438 us/step: the step is issue-bound, not latency-bound), so off
 int g_lstm_dual = 1;           // DEER_OPT_LSTM_DUAL: two interleaved 16-column sub-tiles per CTA for no-keep 32-column tiles
 int g_lstm_keep16 = 1;         // DEER_OPT_LSTM_KEEP16: FP16 (1, default) or fp32 (0) kept gates / cell states
+int g_lstm_halfsplit = 3;      // DEER_OPT_LSTM_HALFSPLIT: 16-column tiles as two independent 8-column halves (bit 0: forward, bit 1: BPTT)
+int g_lstm_stasync = 1;        // DEER_OPT_LSTM_STASYNC: forward h all-gather by st.async stores (1) or bulk copies (0)
 static long long* g_lstm_prof = nullptr;
 void lstm_cluster_set_profile(long long* buf) { g_lstm_prof = buf; }
 void lstm_cluster_set_option(int ts, int tile) {
@@ -962,7 +1323,8 @@ static int launch_fwd(const tc::LstmClusterParams& p, cudaStream_t stream) {
     if (e != cudaSuccess) return cuda_status(e, "lstm_fwd_cluster smem attribute");
     attr = true;
   }
-  DEER_LAUNCH((tc::lstm_fwd_cluster_kernel<N, TS, G, CS>), tc::QC * p.ntiles * 2, G * CS * 256 + 32, smem, stream, p);
+  DEER_LAUNCH((tc::lstm_fwd_cluster_kernel<N, TS, G, CS>), tc::QC * p.ntiles * 2,
+              ((G == 2 && CS == 2) ? 512 : G * CS * 256) + 32, smem, stream, p);
   return DEER_OK;
 }
 template <int N, bool TS, bool K16>
@@ -991,8 +1353,9 @@ int lstm_fwd_cluster(const float* pre_il, const void* pre_f16, const float* w_fw
   tc::LstmClusterParams p{const_cast<float*>(pre_il), w_fwd, w_rev, h_out, gact, c_blk, nullptr, nullptr,
                           reinterpret_cast<__half*>(h16), reinterpret_cast<__nv_bfloat16*>(hb16), nullptr,
                           reinterpret_cast<const __half*>(pre_f16), T, B, (B + N - 1) / N, keep, g_lstm_prof,
-                          g_lstm_keep16};
+                          g_lstm_keep16, g_lstm_stasync};
   if (N == 16) {
+    if (g_lstm_ts && (g_lstm_halfsplit & 1)) return launch_fwd<16, true, 2, 2>(p, stream);
     if (g_lstm_ts && g_lstm_colsplit && !g_lstm_keep16) return launch_fwd<16, true, 1, 2>(p, stream);
     return g_lstm_ts ? launch_fwd<16, true>(p, stream) : launch_fwd<16, false>(p, stream);
   }
@@ -1002,13 +1365,26 @@ int lstm_fwd_cluster(const float* pre_il, const void* pre_f16, const float* w_fw
   return g_lstm_ts ? launch_fwd<32, true>(p, stream) : launch_fwd<32, false>(p, stream);
 }
 
+static int launch_bwd_half(const tc::LstmClusterParams& p, cudaStream_t stream) {
+  constexpr int smem = tc::bwd_half_smem_bytes();
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(tc::lstm_bwd_half_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return cuda_status(e, "lstm_bwd_half smem attribute");
+    attr = true;
+  }
+  DEER_LAUNCH(tc::lstm_bwd_half_kernel, tc::QC * p.ntiles * 2, tc::HTHREADS, smem, stream, p);
+  return DEER_OK;
+}
+
 int lstm_bwd_cluster(const float* gact, const float* c_blk, const float* dh_out, const float* w_fwd, const float* w_rev,
                      float* dpre_il, float* db_il, void* dpre16, int T, int B, cudaStream_t stream) {
   const int N = pick_tile(B);
   tc::LstmClusterParams p{dpre_il, w_fwd, w_rev, nullptr, const_cast<float*>(gact), const_cast<float*>(c_blk), dh_out,
                           db_il, nullptr, nullptr, reinterpret_cast<__nv_bfloat16*>(dpre16), nullptr, T, B,
-                          (B + N - 1) / N, 1, g_lstm_prof, g_lstm_keep16};
+                          (B + N - 1) / N, 1, g_lstm_prof, g_lstm_keep16, 0};
   if (g_lstm_keep16) {
+    if (N == 16 && g_lstm_ts && (g_lstm_halfsplit & 2)) return launch_bwd_half(p, stream);
     if (N == 16) return g_lstm_ts ? launch_bwd<16, true, true>(p, stream) : launch_bwd<16, false, true>(p, stream);
     return launch_bwd<32, true, true>(p, stream);
   }
