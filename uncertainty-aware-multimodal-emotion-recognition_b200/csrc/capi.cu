@@ -107,7 +107,7 @@ int deer_set_option(int option, int value) {
       g_lstm_dual = value;
       return DEER_OK;
     case DEER_OPT_LSTM_HALFSPLIT:
-      g_lstm_halfsplit = value & 3;
+      g_lstm_halfsplit = value ? 1 : 0;
       return DEER_OK;
     case DEER_OPT_LSTM_STASYNC:
       g_lstm_stasync = value ? 1 : 0;

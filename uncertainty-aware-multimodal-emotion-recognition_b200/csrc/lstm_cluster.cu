@@ -994,282 +994,6 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
   }
 }
 
-// ================================================================================================ backward, half split
-// The BPTT counterpart of the forward kernel's half split (N = 16, resident operand in TMEM, FP16 kept state): the two
-// 8-column halves of a 16-column tile are two INDEPENDENT backward recurrences -- own 8 compute warps, dpre B-operand
-// tile (8 valid rows of 16; the MMA stays N = 16), accumulators, partial-dh slots and barriers; shared resident W_hh^T
-// slice and MMA warp.  One half's reduce-scatter flies while the other half's gate gradients are computed.  Layouts in
-// HBM (kept gates / cell states, dpre, dh) are exactly those of lstm_bwd_cluster_kernel.
-constexpr int HNV = 8;                                   // valid batch columns per half
-constexpr int HB_TILE = 16 * QH * 2;                     // B-operand tile of one half: 16 rows x 256 k bf16 (8 KB)
-constexpr int HPART = QC * QU * HNV * 2;                 // one partial-dh buffer of one half: [src][unit][8] bf16 (4 KB)
-constexpr int HPSTAGE = 8 * 2 * 32 * HNV * 2;            // per half: per-warp double-buffered [32 rows][8] bf16 (8 KB)
-constexpr int HTHREADS = 16 * 32 + 32;
-
-__global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(HTHREADS, 1)
-    lstm_bwd_half_kernel(const LstmClusterParams p) {
-  DEER_PDL_ENTRY();
-  constexpr int N = 16, NQ = HNV / 4;   // MMA N; batch columns per cell thread (2)
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* bsm_all = smem;                                                                   // [2 halves][HB_TILE]
-  __nv_bfloat16* part_all = reinterpret_cast<__nv_bfloat16*>(bsm_all + 2 * HB_TILE);         // [2][2 buffers][HPART]
-  __nv_bfloat16* pstage_all = part_all + 2 * 2 * (HPART / 2);                                // [2][HPSTAGE]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(pstage_all) + 2 * HPSTAGE);
-  // per half: part_full[2], b_ready, mma_done
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
-
-  const int warp_id = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int grp = (warp_id >= 8 && warp_id < 16) ? 1 : 0;
-  const int warp = warp_id == 16 ? 8 : (warp_id & 7);
-  const uint32_t r = cluster_ctarank();
-  const int cid = blockIdx.x / QC;
-  const int tile = cid % p.ntiles, dir = cid / p.ntiles;
-  const int b0 = tile * N + grp * HNV;            // first batch column of this half
-  const int T = p.T, B = p.B;
-  const float* __restrict__ W = dir ? p.w_rev : p.w_fwd;
-  uint8_t* bsm = bsm_all + grp * HB_TILE;
-  __nv_bfloat16* part = part_all + grp * 2 * (HPART / 2);
-  __nv_bfloat16* pstage = pstage_all + grp * (HPSTAGE / 2);
-  uint64_t* part_full = bars + 4 * grp;
-  uint64_t* b_ready = bars + 4 * grp + 2;
-  uint64_t* mma_done = bars + 4 * grp + 3;
-
-  if (threadIdx.x == 0) {
-    for (int g = 0; g < 2; g++) {
-      mbar_init(&bars[4 * g + 0], 1);
-      mbar_init(&bars[4 * g + 1], 1);
-      mbar_init(&bars[4 * g + 2], 8);
-      mbar_init(&bars[4 * g + 3], 1);
-    }
-    fence_barrier_init();
-    for (int g = 0; g < 2; g++) {
-      if (T > 1) mbar_expect_tx(&bars[4 * g + 0], HPART);
-      if (T > 2) mbar_expect_tx(&bars[4 * g + 1], HPART);
-    }
-  }
-  if (warp_id == 16) {
-    tmem_alloc_more_follow(tmem_slot, 64);
-    tmem_alloc(tmem_slot + 1, 256);
-  }
-  // the unused rows 8..15 of both B-operand tiles: zero once (they only feed accumulator columns nobody reads, but
-  // uninitialised shared memory may hold NaN patterns that would be harmless yet needlessly exercise the special paths)
-  for (int i = threadIdx.x; i < 2 * HB_TILE / 16; i += HTHREADS) reinterpret_cast<uint4*>(bsm_all)[i] = make_uint4(0, 0, 0, 0);
-  fence_proxy_async_smem();
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_w = tmem_slot[1];
-  if (warp_id < 8) {
-    // resident A operand: A[m = hidden unit (2 x 128)][k = 4*unit_local + gate] = W_hh[gate*256 + 64r + unit_local][m]
-    const int a = warp >> 2, sub = warp & 3, m = a * 128 + sub * 32 + lane;
-#pragma unroll 1
-    for (int ch = 0; ch < 4; ch++) {
-      float v[32];
-#pragma unroll
-      for (int i = 0; i < 32; i++) {
-        const int k0 = ch * 64 + 2 * i;
-        const float f0 = __ldg(W + (size_t)((k0 & 3) * QH + (int)r * QU + (k0 >> 2)) * QH + m);
-        const float f1 = __ldg(W + (size_t)(((k0 + 1) & 3) * QH + (int)r * QU + ((k0 + 1) >> 2)) * QH + m);
-        reinterpret_cast<uint32_t*>(v)[i] = pack_bf2(f0, f1);
-      }
-      tmem_st32(tmem_w + ((uint32_t)(sub * 32) << 16) + (uint32_t)(a * 128 + ch * 32), v);
-    }
-    tmem_st_wait();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  cluster_sync_all();
-
-  if (warp == 8) {
-    // =================================================================== MMA issuer: the halves take turns
-    constexpr uint32_t idesc = make_idesc_f16(1, 128, N);
-    const uint32_t tb = warp_uniform(tmem_base);
-    const uint32_t tw = warp_uniform(tmem_w);
-    const bool leader = elect_one();
-    for (int s = 0; s + 1 < T; s++) {
-#pragma unroll
-      for (int g = 0; g < 2; g++) {
-        uint64_t* pf = bars + 4 * g;
-        mbar_wait(&bars[4 * g + 2], (uint32_t)(s & 1));
-        if (leader && g == 0) Q_PROF(0);
-        // every cell thread of the half has consumed the partials of step s-1: re-arm that buffer for step s+1
-        if (leader && s >= 1 && s + 2 < T) mbar_expect_tx(&pf[(s - 1) & 1], HPART);
-        tc_fence_after();
-        const uint32_t bb = smem_u32(bsm_all) + g * HB_TILE;
-        const uint32_t tg = tb + (uint32_t)(g * 2 * N);
-        if (leader) {
-#pragma unroll
-          for (int a = 0; a < 2; a++) {
-#pragma unroll
-            for (int k = 0; k < 16; k++) {
-              const uint64_t bd = make_smem_desc(bb + (k >> 2) * (N * 128) + (k & 3) * 32, 16, 1024, 2);
-              umma_f16_ts(tg + a * N, tw + a * 128 + k * 8, bd, idesc, k > 0 ? 1u : 0u);
-            }
-          }
-          umma_commit(&bars[4 * g + 3]);
-          if (g == 0) Q_PROF(1);
-        }
-        __syncwarp();
-      }
-    }
-  } else {
-    const int a = warp >> 2, sub = warp & 3;
-    const int j = lane >> 2, q = lane & 3;        // cell role: unit j of this warp, columns [q*2, q*2+2) of the half
-    const int ul = a * 32 + sub * 8 + j;
-    const int ug = (int)r * QU + ul;
-    const uint32_t tacc = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(grp * 2 * N + a * N);
-    const uint32_t dst_cta = (uint32_t)(2 * a + (sub >> 1));
-    float dc[NQ] = {0.f, 0.f};
-    // kept state: the 8-warp kernels' blocked layout; this thread's two columns are one 32-bit word of the (i,f) and
-    // (g,o) 16-byte groups / the 8-byte c group of lane8
-    const long long blk_w = ((long long)dir * p.ntiles + tile) * 32 + (int)r * 8 + warp;
-    const long long blk_t = 2LL * p.ntiles * 32;
-    const int lane8 = j * 4 + grp * 2 + (q >> 1), h2 = q & 1;
-    float sdb[4] = {0.f, 0.f, 0.f, 0.f};
-    struct Kept {                                 // operands of one step, fetched two steps ahead (see the 8-warp kernel)
-      uint32_t ri, rf, rg, ro, rc, rcp;           // raw FP16 pairs
-      float vdh[NQ];
-    };
-    auto load_step = [&](int s, Kept& k) {
-      const int t = dir ? s : T - 1 - s;
-      const int tp = dir ? t + 1 : t - 1;
-      const bool first = dir ? (t == T - 1) : (t == 0);
-      const long long blk = (long long)t * blk_t + blk_w;
-      const uint32_t* gw = reinterpret_cast<const uint32_t*>(reinterpret_cast<const __half*>(p.gact) + blk * 512);
-      const uint32_t* cw = reinterpret_cast<const uint32_t*>(reinterpret_cast<const __half*>(p.c_all) + blk * 128);
-      const uint32_t* cpw = reinterpret_cast<const uint32_t*>(reinterpret_cast<const __half*>(p.c_all) +
-                                                              ((long long)tp * blk_t + blk_w) * 128);
-      k.ri = __ldcs(gw + lane8 * 4 + h2);
-      k.rf = __ldcs(gw + lane8 * 4 + 2 + h2);
-      k.rg = __ldcs(gw + (32 + lane8) * 4 + h2);
-      k.ro = __ldcs(gw + (32 + lane8) * 4 + 2 + h2);
-      k.rc = __ldcs(cw + lane8 * 2 + h2);
-      k.rcp = first ? 0u : __ldcs(cpw + lane8 * 2 + h2);
-#pragma unroll
-      for (int i = 0; i < NQ; i++) {
-        const int b = b0 + q * NQ + i;
-        k.vdh[i] = (b < B) ? __ldcs(p.dh_out + ((long long)t * B + b) * (2 * QH) + dir * QH + ug) : 0.f;
-      }
-    };
-    auto h2f = [](uint32_t v) { return __half22float2(*reinterpret_cast<const __half2*>(&v)); };
-    auto body = [&](const int s, Kept& kept) {
-      const int t = dir ? s : T - 1 - s;
-      float dh[NQ] = {kept.vdh[0], kept.vdh[1]};
-      const float2 fi = h2f(kept.ri), ff = h2f(kept.rf), fg = h2f(kept.rg), fo = h2f(kept.ro), fc = h2f(kept.rc),
-                   fcp = h2f(kept.rcp);
-      const float vi[NQ] = {fi.x, fi.y}, vf[NQ] = {ff.x, ff.y}, vg[NQ] = {fg.x, fg.y}, vo[NQ] = {fo.x, fo.y};
-      const float vc[NQ] = {fc.x, fc.y}, vcp[NQ] = {fcp.x, fcp.y};
-      if (s + 2 < T) load_step(s + 2, kept);
-      if (s > 0) {
-        mbar_wait(&part_full[(s - 1) & 1], (uint32_t)(((s - 1) >> 1) & 1));
-        if (warp_id == 0 && lane == 0) Q_PROF(2);
-        const __nv_bfloat16* ps = part + ((s - 1) & 1) * (HPART / 2) + ul * HNV + q * NQ;
-#pragma unroll
-        for (int src = 0; src < QC; src++) {
-          const uint32_t v = *reinterpret_cast<const uint32_t*>(ps + src * (QU * HNV));
-          const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v));
-          dh[0] += f.x;
-          dh[1] += f.y;
-        }
-      }
-      const int kb = ul >> 4, ch = (ul & 15) >> 1;
-      float4 dp[NQ];
-      uint2 dp16[NQ];
-      float tcv[NQ];
-      tanh_pair(vc[0], vc[1], tcv[0], tcv[1]);
-#pragma unroll
-      for (int i = 0; i < NQ; i++) {
-        const float tc_ = tcv[i];
-        const float d_o = dh[i] * tc_;
-        const float dcc = fmaf(dh[i] * vo[i], 1.f - tc_ * tc_, dc[i]);
-        dc[i] = dcc * vf[i];
-        dp[i].x = dcc * vg[i] * vi[i] * (1.f - vi[i]);
-        dp[i].y = dcc * vcp[i] * vf[i] * (1.f - vf[i]);
-        dp[i].z = dcc * vi[i] * (1.f - vg[i] * vg[i]);
-        dp[i].w = d_o * vo[i] * (1.f - vo[i]);
-        dp16[i].x = pack_bf2(dp[i].x, dp[i].y);
-        dp16[i].y = pack_bf2(dp[i].z, dp[i].w);
-        if (s + 1 < T) {
-          const int n = q * NQ + i;           // row of the half's B-operand tile (0..7)
-          *reinterpret_cast<uint2*>(bsm + kb * (N * 128) + sw128(n, ch) + (ul & 1) * 8) = dp16[i];
-        }
-      }
-      if (s + 1 < T) {
-        fence_proxy_async_smem();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(b_ready);
-        if (warp_id == 0 && lane == 0) Q_PROF(3);
-      }
-#pragma unroll
-      for (int i = 0; i < NQ; i++) {
-        const int b = b0 + q * NQ + i;
-        if (b < B) {
-          const long long o = (((long long)t * B + b) * 2 + dir) * (4 * QH) + 4 * ug;
-          if (p.gates) __stcs(reinterpret_cast<float4*>(p.gates + o), dp[i]);
-          if (p.dpre16) *reinterpret_cast<uint2*>(p.dpre16 + o) = dp16[i];
-          sdb[0] += dp[i].x; sdb[1] += dp[i].y; sdb[2] += dp[i].z; sdb[3] += dp[i].w;
-        }
-      }
-      if (s + 1 < T) {
-        mbar_wait(mma_done, (uint32_t)(s & 1));
-        if (warp_id == 0 && lane == 0) Q_PROF(4);
-        tc_fence_after();
-        float x[HNV];
-        tmem_ld8(tacc, x);
-        tmem_ld_wait();
-        // reduce-scatter: this warp's 32 accumulator rows x 8 columns (hidden units of CTA dst_cta) -> that CTA's slot
-        __nv_bfloat16* st = pstage + (warp * 2 + (s & 1)) * (32 * HNV);
-        uint4 v;
-        v.x = pack_bf2(x[0], x[1]); v.y = pack_bf2(x[2], x[3]);
-        v.z = pack_bf2(x[4], x[5]); v.w = pack_bf2(x[6], x[7]);
-        *reinterpret_cast<uint4*>(st + lane * HNV) = v;
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          const uint32_t slot = smem_u32(part) + (uint32_t)(((s & 1) * QC + (int)r) * QU + (sub & 1) * 32) * (HNV * 2);
-          bulk_copy_to_peer(mapa_u32(slot, dst_cta), smem_u32(st), 32 * HNV * 2,
-                            mapa_u32(smem_u32(&part_full[s & 1]), dst_cta));
-        }
-        if (warp_id == 0 && lane == 0) Q_PROF(5);
-      }
-    };
-    Kept set0, set1;
-    load_step(0, set0);
-    if (T > 1) load_step(1, set1);
-    for (int s = 0; s < T; s += 2) {
-      body(s, set0);
-      if (s + 1 < T) body(s + 1, set1);
-    }
-    if (p.db) {
-#pragma unroll
-      for (int e = 0; e < 4; e++) {
-        sdb[e] += __shfl_xor_sync(0xffffffffu, sdb[e], 1);
-        sdb[e] += __shfl_xor_sync(0xffffffffu, sdb[e], 2);
-      }
-      if (q == 0) {
-#pragma unroll
-        for (int e = 0; e < 4; e++) atomicAdd(p.db + dir * (4 * QH) + 4 * ug + e, sdb[e]);
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();
-  if (warp == 8) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 64);
-    tmem_dealloc(tmem_w, 256);
-  }
-}
-constexpr int bwd_half_smem_bytes() {
-  constexpr int need = 2 * HB_TILE + 2 * 2 * HPART + 2 * HPSTAGE + 128 + 1024;
-  return need > 120 * 1024 ? need : 120 * 1024;   // one LSTM CTA per SM (see fwd_smem_bytes)
-}
-
 template <int N, bool TS, int G = 1, int CS = 1>
 constexpr int fwd_smem_bytes() {
   using L = QLayout<N>;
@@ -1293,7 +1017,9 @@ static int g_lstm_tile = 0;    // 0 auto, else forced N (16 or 32)
 int g_lstm_colsplit = 0;       // DEER_OPT_LSTM_COLSPLIT: 16 compute warps (two column halves) on 16-column tiles; measured: no gain (1.444 vs 1.438 us/step: the step is issue-bound, not latency-bound), so off
 int g_lstm_dual = 1;           // DEER_OPT_LSTM_DUAL: two interleaved 16-column sub-tiles per CTA for no-keep 32-column tiles
 int g_lstm_keep16 = 1;         // DEER_OPT_LSTM_KEEP16: FP16 (1, default) or fp32 (0) kept gates / cell states
-int g_lstm_halfsplit = 3;      // DEER_OPT_LSTM_HALFSPLIT: 16-column tiles as two independent 8-column halves (bit 0: forward, bit 1: BPTT)
+int g_lstm_halfsplit = 1;      // DEER_OPT_LSTM_HALFSPLIT: forward recurrence on 16-column tiles as two independent 8-column halves
+                               // (the same split of the BPTT kernel was built and measured SLOWER: 0.498 vs 0.402 ms per layer at
+                               // B = 256 -- its kept-state reads become 4-byte accesses and 17 warps cap it at 96 registers)
 int g_lstm_stasync = 1;        // DEER_OPT_LSTM_STASYNC: forward h all-gather by st.async stores (1) or bulk copies (0)
 static long long* g_lstm_prof = nullptr;
 void lstm_cluster_set_profile(long long* buf) { g_lstm_prof = buf; }
@@ -1355,7 +1081,7 @@ int lstm_fwd_cluster(const float* pre_il, const void* pre_f16, const float* w_fw
                           reinterpret_cast<const __half*>(pre_f16), T, B, (B + N - 1) / N, keep, g_lstm_prof,
                           g_lstm_keep16, g_lstm_stasync};
   if (N == 16) {
-    if (g_lstm_ts && (g_lstm_halfsplit & 1)) return launch_fwd<16, true, 2, 2>(p, stream);
+    if (g_lstm_ts && g_lstm_halfsplit) return launch_fwd<16, true, 2, 2>(p, stream);
     if (g_lstm_ts && g_lstm_colsplit && !g_lstm_keep16) return launch_fwd<16, true, 1, 2>(p, stream);
     return g_lstm_ts ? launch_fwd<16, true>(p, stream) : launch_fwd<16, false>(p, stream);
   }
@@ -1365,18 +1091,6 @@ int lstm_fwd_cluster(const float* pre_il, const void* pre_f16, const float* w_fw
   return g_lstm_ts ? launch_fwd<32, true>(p, stream) : launch_fwd<32, false>(p, stream);
 }
 
-static int launch_bwd_half(const tc::LstmClusterParams& p, cudaStream_t stream) {
-  constexpr int smem = tc::bwd_half_smem_bytes();
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(tc::lstm_bwd_half_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return cuda_status(e, "lstm_bwd_half smem attribute");
-    attr = true;
-  }
-  DEER_LAUNCH(tc::lstm_bwd_half_kernel, tc::QC * p.ntiles * 2, tc::HTHREADS, smem, stream, p);
-  return DEER_OK;
-}
-
 int lstm_bwd_cluster(const float* gact, const float* c_blk, const float* dh_out, const float* w_fwd, const float* w_rev,
                      float* dpre_il, float* db_il, void* dpre16, int T, int B, cudaStream_t stream) {
   const int N = pick_tile(B);
@@ -1384,7 +1098,6 @@ int lstm_bwd_cluster(const float* gact, const float* c_blk, const float* dh_out,
                           db_il, nullptr, nullptr, reinterpret_cast<__nv_bfloat16*>(dpre16), nullptr, T, B,
                           (B + N - 1) / N, 1, g_lstm_prof, g_lstm_keep16, 0};
   if (g_lstm_keep16) {
-    if (N == 16 && g_lstm_ts && (g_lstm_halfsplit & 2)) return launch_bwd_half(p, stream);
     if (N == 16) return g_lstm_ts ? launch_bwd<16, true, true>(p, stream) : launch_bwd<16, false, true>(p, stream);
     return launch_bwd<32, true, true>(p, stream);
   }
