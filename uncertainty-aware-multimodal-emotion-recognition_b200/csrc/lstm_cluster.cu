@@ -217,10 +217,14 @@ struct LstmClusterParams {
   int stasync;         // forward h all-gather: 1 = per-lane st.async stores into the peers' B operand, 0 = bulk copies
 };
 constexpr int Q_PROF_S0 = 64, Q_PROF_STEPS = 4, Q_PROF_SLOTS = 8;
+// (only in the FAST = false instantiation -- the probe's: the clock read and its guards were 3 % of all instructions the
+//  production kernel issued)
 #define Q_PROF(slot)                                                                               \
   do {                                                                                             \
-    if (p.prof && blockIdx.x == 0 && s >= Q_PROF_S0 && s < Q_PROF_S0 + Q_PROF_STEPS)               \
-      p.prof[(s - Q_PROF_S0) * Q_PROF_SLOTS + (slot)] = clock64();                                 \
+    if constexpr (!FAST) {                                                                         \
+      if (p.prof && blockIdx.x == 0 && s >= Q_PROF_S0 && s < Q_PROF_S0 + Q_PROF_STEPS)             \
+        p.prof[(s - Q_PROF_S0) * Q_PROF_SLOTS + (slot)] = clock64();                               \
+    }                                                                                              \
   } while (0)
 
 // ================================================================================================ forward
@@ -240,7 +244,9 @@ constexpr int Q_PROF_S0 = 64, Q_PROF_STEPS = 4, Q_PROF_SLOTS = 8;
 // serial chain MMA (420 cycles) -> gate epilogue -> cell update -> DSMEM all-gather (750-900 cycles from "h computed" to
 // "the peers' MMA warps see it", whichever transport is used); with two halves in flight one half's exchange flies while
 // the other half's gates are computed, on all 128 SMs of a B = 256 batch.  Same kept layouts as the 8-warp kernel.
-template <int N, bool TS, int G, int CS = 1>
+// FAST: the batch is a whole number of tiles and no clock trace is requested -- the per-column bounds checks (a branch
+// around every global load / store of the inner loop) and the trace guards are compiled out.
+template <int N, bool TS, int G, int CS = 1, bool FAST = false>
 __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__((G == 2 && CS == 2 ? 512 : G * CS * 256) + 32, 1)
     lstm_fwd_cluster_kernel(const LstmClusterParams p) {
   DEER_PDL_ENTRY();
@@ -433,12 +439,13 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__((G == 2 && CS == 2 
                         // stream this kernel reads; one 64-byte request per warp and sample
         const unsigned short* src = reinterpret_cast<const unsigned short*>(p.pre16) + off;
 #pragma unroll
-        for (int n = 0; n < NW; n++) pre[n] = (bw0 + n < B) ? (uint32_t)__ldcs(src + (long long)n * (8 * QH)) : 0u;
+        for (int n = 0; n < NW; n++)
+          pre[n] = (FAST || bw0 + n < B) ? (uint32_t)__ldcs(src + (long long)n * (8 * QH)) : 0u;
       } else {
         const float* src = p.gates + off;
 #pragma unroll
         for (int n = 0; n < NW; n++)
-          pre[n] = (bw0 + n < B) ? __float_as_uint(__ldcs(src + (long long)n * (8 * QH))) : 0u;
+          pre[n] = (FAST || bw0 + n < B) ? __float_as_uint(__ldcs(src + (long long)n * (8 * QH))) : 0u;
       }
     };
     // blocked save area of this warp: ((((t*2+dir)*ntiles+tile)*4+r)*8+warp) blocks of 4*NQ*32 (gates) / NQ*32 (c)
@@ -551,7 +558,7 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__((G == 2 && CS == 2 
       const long long blk = (long long)t * blk_t + blk_w;
 #pragma unroll
       for (int i = 0; i < NQ; i++)
-        if (bw0 + q * NQ + i < B) p.h_out[(row0 + i) * (2 * QH) + dir * QH + ug] = hv[i];
+        if (FAST || bw0 + q * NQ + i < B) p.h_out[(row0 + i) * (2 * QH) + dir * QH + ug] = hv[i];
       if constexpr (CS == 2) {
         if (p.keep) {
           // the 8-warp kernel's blocked layout ([gate][32 lanes][4 columns] per warp block): this thread's two columns
@@ -614,7 +621,7 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__((G == 2 && CS == 2 
       if (p.h16 || p.hb16) {
         // the warp's [N cols x 8 units] fp16 block doubles as the source of the 16-bit shadows of h: one 16-byte
         // store per sample row (the tile is double-buffered and only READ by the bulk copies in flight)
-        if (lane < NW && bw0 + lane < B) {
+        if (lane < NW && (FAST || bw0 + lane < B)) {
           const uint4 hv8 = *reinterpret_cast<const uint4*>(sh + lane * 8);
           const long long o = ((long long)t * B + bw0 + lane) * (2 * QH) + dir * QH + (int)r * QU + a * 32 + sub * 8;
           if (p.h16) *reinterpret_cast<uint4*>(p.h16 + o) = hv8;
@@ -647,7 +654,7 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__((G == 2 && CS == 2 
 // K16: the kept gates / cell states are FP16 (DEER_OPT_LSTM_KEEP16): they are loaded a step ahead as RAW bits and
 // converted only when the step that uses them starts (a convert at the load would wait for the DRAM round trip inside
 // the current step -- measured 1.48 -> 1.93 us per step)
-template <int N, bool TS, bool K16 = false>
+template <int N, bool TS, bool K16 = false, bool FAST = false>
 __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
     lstm_bwd_cluster_kernel(const LstmClusterParams p) {
   DEER_PDL_ENTRY();
@@ -835,7 +842,7 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
 #pragma unroll
       for (int i = 0; i < NQ; i++) {
         const int b = b0 + q * NQ + i;
-        k.vdh[i] = (b < B) ? __ldcs(p.dh_out + ((long long)t * B + b) * (2 * QH) + dir * QH + ug) : 0.f;
+        k.vdh[i] = (FAST || b < B) ? __ldcs(p.dh_out + ((long long)t * B + b) * (2 * QH) + dir * QH + ug) : 0.f;
       }
     };
     auto body = [&](const int s, Kept& kept) {
@@ -922,7 +929,7 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
       }
 #pragma unroll
       for (int i = 0; i < NQ; i++) {
-        if (b0 + q * NQ + i < B) {
+        if (FAST || b0 + q * NQ + i < B) {
           if (p.gates) __stcs(reinterpret_cast<float4*>(gout + (long long)i * (8 * QH)), dp[i]);
           if (p.dpre16)
             *reinterpret_cast<uint2*>(p.dpre16 + (((long long)t * B + b0 + q * NQ + i) * 2 + dir) * (4 * QH) + 4 * ug) = dp16[i];
@@ -1039,31 +1046,44 @@ static int pick_tile(int B) {
   return (2 * ((B + 15) / 16) <= 32) ? 16 : 32;
 }
 
-template <int N, bool TS, int G = 1, int CS = 1>
-static int launch_fwd(const tc::LstmClusterParams& p, cudaStream_t stream) {
+template <int N, bool TS, int G, int CS, bool FAST>
+static int launch_fwd_f(const tc::LstmClusterParams& p, cudaStream_t stream) {
   constexpr int smem = tc::fwd_smem_bytes<N, TS, G, CS>();
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(tc::lstm_fwd_cluster_kernel<N, TS, G, CS>,
+    cudaError_t e = cudaFuncSetAttribute(tc::lstm_fwd_cluster_kernel<N, TS, G, CS, FAST>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return cuda_status(e, "lstm_fwd_cluster smem attribute");
     attr = true;
   }
-  DEER_LAUNCH((tc::lstm_fwd_cluster_kernel<N, TS, G, CS>), tc::QC * p.ntiles * 2,
+  DEER_LAUNCH((tc::lstm_fwd_cluster_kernel<N, TS, G, CS, FAST>), tc::QC * p.ntiles * 2,
               ((G == 2 && CS == 2) ? 512 : G * CS * 256) + 32, smem, stream, p);
+  return DEER_OK;
+}
+template <int N, bool TS, int G = 1, int CS = 1>
+static int launch_fwd(const tc::LstmClusterParams& p, cudaStream_t stream) {
+  // whole tiles (of the columns ONE CTA covers) and no clock trace: the check-free instantiation
+  constexpr int cols = (G == 2 && CS == 2) ? N : G * N;
+  if (p.B % cols == 0 && p.prof == nullptr) return launch_fwd_f<N, TS, G, CS, true>(p, stream);
+  return launch_fwd_f<N, TS, G, CS, false>(p, stream);
+}
+template <int N, bool TS, bool K16, bool FAST>
+static int launch_bwd_f(const tc::LstmClusterParams& p, cudaStream_t stream) {
+  constexpr int smem = tc::bwd_smem_bytes<N, TS>();
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(tc::lstm_bwd_cluster_kernel<N, TS, K16, FAST>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return cuda_status(e, "lstm_bwd_cluster smem attribute");
+    attr = true;
+  }
+  DEER_LAUNCH((tc::lstm_bwd_cluster_kernel<N, TS, K16, FAST>), tc::QC * p.ntiles * 2, tc::QTHREADS, smem, stream, p);
   return DEER_OK;
 }
 template <int N, bool TS, bool K16>
 static int launch_bwd(const tc::LstmClusterParams& p, cudaStream_t stream) {
-  constexpr int smem = tc::bwd_smem_bytes<N, TS>();
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(tc::lstm_bwd_cluster_kernel<N, TS, K16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return cuda_status(e, "lstm_bwd_cluster smem attribute");
-    attr = true;
-  }
-  DEER_LAUNCH((tc::lstm_bwd_cluster_kernel<N, TS, K16>), tc::QC * p.ntiles * 2, tc::QTHREADS, smem, stream, p);
-  return DEER_OK;
+  if (p.B % N == 0 && p.prof == nullptr) return launch_bwd_f<N, TS, K16, true>(p, stream);
+  return launch_bwd_f<N, TS, K16, false>(p, stream);
 }
 
 int lstm_cluster_tile(int B) { return pick_tile(B); }
