@@ -156,6 +156,11 @@ def main():
     ap.add_argument("--tf32-pair", type=int, default=None, help="DEER_OPT_TF32_PAIR override (ablation)")
     ap.add_argument("--lstm-dual", type=int, default=None, help="DEER_OPT_LSTM_DUAL override (ablation)")
     ap.add_argument("--lstm-tile", type=int, default=None, help="DEER_OPT_LSTM_TILE override (ablation)")
+    ap.add_argument("--lstm-halfsplit", type=int, default=None, help="DEER_OPT_LSTM_HALFSPLIT override (ablation)")
+    ap.add_argument("--lstm-stasync", type=int, default=None, help="DEER_OPT_LSTM_STASYNC override (ablation)")
+    ap.add_argument("--chain", action="store_true",
+                    help="ablation: fusion + head as the persistent chain kernel (one launch per direction; measured slower)")
+    ap.add_argument("--train-only", action="store_true", help="ablation runs: only the training-step line (no e2e / inference / roofline)")
     ap.add_argument("--no-defer-wgrad", action="store_true",
                     help="ablation: small-layer weight gradients on the main stream")
     ap.add_argument("--ref-batch", type=int, default=TRAIN_B, help="batch of the CPU reference arm (default: same as GPU)")
@@ -193,6 +198,13 @@ def main():
         _lib.set_option(9, args.lstm_dual)
     if args.lstm_tile is not None:
         _lib.set_option(3, args.lstm_tile)
+    if args.lstm_halfsplit is not None:
+        _lib.set_option(13, args.lstm_halfsplit)
+    if args.lstm_stasync is not None:
+        _lib.set_option(12, args.lstm_stasync)
+    if args.chain:
+        from deer_b200 import chain as _chain
+        _chain.set_enabled(True)
     if args.tf32_pair is not None:
         _lib.set_option(6, args.tf32_pair)
         if not args.tf32_pair:
@@ -287,6 +299,13 @@ def main():
 
     ms_per_step, launches_per_step, final_loss, clocks, NB = measure_train(B, K, W)
     value = B * world / (ms_per_step / 1e3)
+    if args.train_only:
+        if rank == 0:
+            print(json.dumps({"metric": "deer_train_step_samples_per_s", "value": value, "ms_per_step": ms_per_step,
+                              "launches_per_step": int(launches_per_step), "ablation": vars(args)}), flush=True)
+        if world > 1:
+            teardown_distributed(torch, dist, trainer)
+        return
 
     # ------------------------------------------------------------------ e2e: pinned host -> device every step
     # Public API path: pinned host batch -> deer_b200.data.DevicePrefetcher (H2D on a copy stream into rotating static

@@ -125,7 +125,11 @@ class Program:
         _lib.check(_lib.load().deer_chain_run(ctypes.byref(c), _lib.stream()), "deer_chain_run")
 
 
-_state = {"enabled": True, "max_batch": 512}
+# OFF by default: measured on one box, back to back (tools/gpu_r2_ab.sh, B = 256 training step, graph replay): 4.171 ms
+# with the chain kernel vs 4.112 ms module by module (the fused 3xTF32 nodes, weight gradients on their own stream).  The
+# kernel replaces ~66 launches per step, but inside a CUDA graph a launch costs ~2 us while every level of the chain pays
+# a grid-wide barrier plus a cold operand pipeline (~10 us; profiles/r2_chain_rowpartition_experiment.txt).
+_state = {"enabled": False, "max_batch": 512}
 
 
 def set_max_batch(n: int):
@@ -137,7 +141,7 @@ def set_max_batch(n: int):
 
 
 def set_enabled(on: bool):
-    """Fusion + NIG head as one persistent-kernel launch per direction (default) or module by module."""
+    """Fusion + NIG head as one persistent-kernel launch per direction, or module by module (default)."""
     _state["enabled"] = bool(on)
 
 

@@ -1024,9 +1024,12 @@ static int g_lstm_tile = 0;    // 0 auto, else forced N (16 or 32)
 int g_lstm_colsplit = 0;       // DEER_OPT_LSTM_COLSPLIT: 16 compute warps (two column halves) on 16-column tiles; measured: no gain (1.444 vs 1.438 us/step: the step is issue-bound, not latency-bound), so off
 int g_lstm_dual = 1;           // DEER_OPT_LSTM_DUAL: two interleaved 16-column sub-tiles per CTA for no-keep 32-column tiles
 int g_lstm_keep16 = 1;         // DEER_OPT_LSTM_KEEP16: FP16 (1, default) or fp32 (0) kept gates / cell states
-int g_lstm_halfsplit = 1;      // DEER_OPT_LSTM_HALFSPLIT: forward recurrence on 16-column tiles as two independent 8-column halves
-                               // (the same split of the BPTT kernel was built and measured SLOWER: 0.498 vs 0.402 ms per layer at
-                               // B = 256 -- its kept-state reads become 4-byte accesses and 17 warps cap it at 96 registers)
+int g_lstm_halfsplit = 0;      // DEER_OPT_LSTM_HALFSPLIT: forward recurrence on 16-column tiles as two independent 8-column halves.
+                               // The KERNEL is 9 % faster that way (1.46 -> 1.33 us/step at B = 256), but its 17 warps x 96
+                               // registers leave the video / text stream's kernels less room on the same SMs: the whole
+                               // training step measured 4.30 ms with it vs 4.26 ms without (same box, back to back), so it is
+                               // off by default.  (The same split of the BPTT kernel was built and measured slower by itself:
+                               // 0.498 vs 0.402 ms per layer -- its kept-state reads become 4-byte accesses.)
 int g_lstm_stasync = 1;        // DEER_OPT_LSTM_STASYNC: forward h all-gather by st.async stores (1) or bulk copies (0)
 static long long* g_lstm_prof = nullptr;
 void lstm_cluster_set_profile(long long* buf) { g_lstm_prof = buf; }
