@@ -598,11 +598,15 @@ LSTM_KEEP_BYTES_PER_UNIT = 4 * 2 + 2     # FP16 kept state (DEER_OPT_LSTM_KEEP16
 # dram__bytes_read.sum + dram__bytes_write.sum per launch: OFFLINE constants transcribed from the committed
 # `ncu --set full` captures under profiles/ (a bench run cannot measure DRAM traffic itself; a number taken under the
 # profiler is never a bench value) -- reported as `traffic` with `traffic_source`
-NCU_TRAFFIC_SOURCE = "offline: profiles/r1_ncu_full_roofline_v12_summary.txt, profiles/r1_ncu_full_lstm_v12_summary.txt"
+NCU_TRAFFIC_SOURCE = ("offline ncu --set full captures of this build (dram__bytes_read.sum + dram__bytes_write.sum per launch): "
+                      "profiles/r2_ncu_full_roofline_summary.txt, profiles/r2_ncu_full_lstm_summary.txt")
 NCU_TRAFFIC = {
-    # profiles/r1_ncu_full_roofline_v12_summary.txt (ncu --set full --clock-control none, per launch)
-    "gemm_h16_pair_out16": 80.8e6 + 255.4e6,                       # algorithmic 395 MB; part of C16 still in L2 at kernel end
-    "nig_stats_plus_finish": 251.7e6 + 296.4e6 + 251.7e6 + 156.9e6,  # two passes: the 252 MB of operands are read twice
+    # profiles/r2_ncu_full_roofline_summary.txt (ncu --set full --clock-control none, per launch)
+    "gemm_h16_pair_out16": 80.8e6 + 255.5e6,                       # algorithmic 395 MB; part of C16 still in L2 at kernel end
+    "nig_stats_plus_finish": 251.7e6 + 296.8e6 + 251.7e6 + 156.7e6,  # two passes: the 252 MB of operands are read twice
+    # profiles/r2_ncu_full_lstm_summary.txt: the kernels inside the real training step (B=256, layer 1)
+    "lstm_fwd_keep": 316.7e6 + 572.0e6,    # reads = the 315 MB of FP16 pre-activations; algorithmic 944 MB (tail of the stores in L2)
+    "lstm_bwd": 556.3e6 + 260.0e6,         # algorithmic 865 MB
 }
 
 
@@ -749,7 +753,8 @@ def roofline_probe(torch, ops, dev, pk):
                                            "frac": fwd_bytes / (us_f * 1e-6) / 1e9 / pk["hbm_gbs"]},
                                "bwd_hbm": {"achieved": bwd_bytes / (us_b * 1e-6) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
                                            "frac": bwd_bytes / (us_b * 1e-6) / 1e9 / pk["hbm_gbs"]},
-                               "traffic": NCU_TRAFFIC.get("lstm_fwd_keep"), "traffic_source": NCU_TRAFFIC_SOURCE}
+                               "traffic": NCU_TRAFFIC.get("lstm_fwd_keep"), "bwd_traffic": NCU_TRAFFIC.get("lstm_bwd"),
+                               "traffic_source": NCU_TRAFFIC_SOURCE}
     del pre, h, hb16, gact, c, dh, dpre16
     torch.cuda.empty_cache()
 

@@ -38,7 +38,7 @@ def main():
     ap.add_argument("--skip-bwd", action="store_true")
     ap.add_argument("--prof", action="store_true")
     ap.add_argument("--dual", type=int, default=1)
-    ap.add_argument("--stasync", type=int, default=1)
+    ap.add_argument("--stasync", type=int, default=0)
     ap.add_argument("--halfsplit", type=int, default=0)
     a = ap.parse_args()
     _lib.set_option(9, a.dual)

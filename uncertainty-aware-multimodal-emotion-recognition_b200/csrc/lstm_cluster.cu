@@ -1030,7 +1030,11 @@ int g_lstm_halfsplit = 0;      // DEER_OPT_LSTM_HALFSPLIT: forward recurrence on
                                // training step measured 4.30 ms with it vs 4.26 ms without (same box, back to back), so it is
                                // off by default.  (The same split of the BPTT kernel was built and measured slower by itself:
                                // 0.498 vs 0.402 ms per layer -- its kept-state reads become 4-byte accesses.)
-int g_lstm_stasync = 1;        // DEER_OPT_LSTM_STASYNC: forward h all-gather by st.async stores (1) or bulk copies (0)
+int g_lstm_stasync = 0;        // DEER_OPT_LSTM_STASYNC: forward h all-gather by st.async stores (1) or bulk copies (0, default).
+                               // Same-box A/B at the end of round 2: training step 4.02 ms (bulk) vs 4.06-4.12 ms (st.async);
+                               // kernel alone at B = 256: 1.41 vs 1.44 us/step; B = 1024 inference 0.977 vs 0.960 ms per layer;
+                               // B = 1024 training forward 1.39 vs 1.55 ms.  From issue to the peers' MMA warps seeing the tile
+                               // both transports take 750-900 cycles.
 static long long* g_lstm_prof = nullptr;
 void lstm_cluster_set_profile(long long* buf) { g_lstm_prof = buf; }
 void lstm_cluster_set_option(int ts, int tile) {
