@@ -74,6 +74,7 @@ int deer_timestamp(unsigned long long* slots, int index, void* stream);
 #define DEER_OPT_LSTM_KEEP16 11    /* 1 (default): the activated gates / cell states the LSTM forward keeps for BPTT (`gact`, `c_blk`) are FP16 (half the bytes of the recurrence's dominant store / load stream); 0: fp32.  Both kernels read the option, so it must not change between a forward and its backward */
 #define DEER_OPT_LSTM_STASYNC 12   /* 1: the forward recurrence all-gathers h with per-lane st.async stores (16 bytes, completion counted on the peer's mbarrier) straight into the peers' B-operand tiles; 0 (default; measured equal or faster in every configuration): one bulk copy (cp.async.bulk.shared::cluster) per warp and destination */
 #define DEER_OPT_LSTM_HALFSPLIT 13 /* 1: forward recurrence on 16-column tiles as TWO independent 8-column halves per CTA (own compute warps, accumulators, B-operand tiles and barriers; shared resident weights and MMA warp): one half's DSMEM exchange flies while the other half's gates are computed (the kernel alone: 1.46 -> 1.33 us/step; the whole step: slower, so off); 0 (default): one 16-column recurrence per CTA */
+#define DEER_OPT_LSTM_CARVEOUT 14  /* 1 (default): the persistent LSTM kernels request the maximum shared-memory carve-out, so that a <= 100 KB GEMM CTA of a concurrent stream can share the SM with a recurrence CTA (must be set before the first LSTM launch of the process: the attribute is applied once per kernel) */
 #define DEER_OPT_PDL 7             /* 1: launch kernels with programmatic stream serialization (PDL); 0 (default, faster as measured) */
 int deer_set_option(int option, int value);
 /* debugging aid: device buffer of >= 32 int64 that receives a clock64() trace of four steps of the persistent LSTM

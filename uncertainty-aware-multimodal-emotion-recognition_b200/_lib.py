@@ -15,7 +15,8 @@ from ctypes import c_void_p as P
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libdeer_b200.so")
+# DEER_B200_LIB: another build of the same library (same-box A/B of two kernel versions, tools/gpu_r2_*.sh); no fallback
+LIB_PATH = os.environ.get("DEER_B200_LIB") or os.path.join(_HERE, "csrc", "libdeer_b200.so")
 
 class GemmX3Args(ctypes.Structure):
     """deer_gemm_x3_args (include/deer_b200.h)."""

@@ -39,7 +39,7 @@ namespace tc {
 constexpr int QH = 256;        // hidden size
 constexpr int QC = 4;          // cluster size
 constexpr int QU = QH / QC;    // hidden units per CTA (64)
-constexpr int QTHREADS = 288;  // 8 compute warps + 1 control warp
+constexpr int QTHREADS = 256;  // BPTT kernel: 8 compute warps, warp 0 also issues the MMAs (no control warp, see there)
 constexpr int QW_BYTES = 2 * 128 * QH * 2;  // resident A operand: 2 accumulators x 128 rows x 256 k x 16 bit = 128 KB
 constexpr int Q_WCOL = 64;     // TMEM column where the resident A operand starts (TS mode)
 
@@ -655,7 +655,9 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__((G == 2 && CS == 2 
 // converted only when the step that uses them starts (a convert at the load would wait for the DRAM round trip inside
 // the current step -- measured 1.48 -> 1.93 us per step)
 template <int N, bool TS, bool K16 = false, bool FAST = false>
-__global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
+// 160 registers (not the 255 that 8 warps would allow): 2 warps x 5120 registers per sub-partition leave 6144 for the
+// warps of a GEMM CTA of the concurrent stream
+__global__ void __cluster_dims__(QC, 1, 1) __maxnreg__(160)
     lstm_bwd_cluster_kernel(const LstmClusterParams p) {
   DEER_PDL_ENTRY();
   using L = QLayout<N>;
@@ -694,7 +696,7 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
   }
   // two allocations (accumulators 64 columns, resident operand 256) instead of one 512-column block: the 192 columns
   // left over let a 128-column GEMM CTA of a concurrent stream share the SM instead of spinning in tcgen05.alloc
-  if (warp == 8) {
+  if (warp == 0) {
     if constexpr (TS) {
       tmem_alloc_more_follow(tmem_slot, 64);
       tmem_alloc(tmem_slot + 1, 256);
@@ -724,7 +726,7 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_w = TS ? tmem_slot[1] : 0u;   // resident A operand (TS mode)
   if constexpr (TS) {
-    if (warp < 8) {
+    {
       const int a = warp >> 2, sub = warp & 3, m = a * 128 + sub * 32 + lane;
 #pragma unroll 1
       for (int ch = 0; ch < 4; ch++) {  // 64 k = 16 units x 4 gates per chunk
@@ -746,42 +748,42 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
   }
   cluster_sync_all();
 
-  if (warp == 8) {
-    // =================================================================== MMA issuer (whole warp, one elected lane issues)
-    {
-      constexpr uint32_t idesc = make_idesc_f16(1, 128, N);
-      const uint32_t tb = warp_uniform(tmem_base);
-      const uint32_t tw = warp_uniform(tmem_w);
-      const bool leader = elect_one();
-      for (int s = 0; s + 1 < T; s++) {
-        mbar_wait(b_ready, (uint32_t)(s & 1));
-        if (leader) Q_PROF(0);
-        // every cell thread has consumed the partials of step s-1: re-arm that buffer for step s+1
-        if (leader && s >= 1 && s + 2 < T) mbar_expect_tx(&part_full[(s - 1) & 1], L::PART_BYTES);
-        tc_fence_after();
-        const uint32_t bb = smem_u32(bsm);
-        if (leader) {
+  // No dedicated control warp in this kernel: warp 0 issues the MMAs of a step between handing over its own part of the
+  // B operand and its global stores.  A 9th warp costs a whole register slot (156 registers x 32 lanes) in ONE of the SM's
+  // four sub-partitions (warps are dealt round-robin, registers are allocated per sub-partition): with 3 x 5120 of its
+  // 16384 registers taken no warp of another kernel fits there, so no CTA of a concurrent stream could ever share the SM
+  // with a recurrence CTA (tools/probes/coresidency_probe.cu).  With 8 warps every sub-partition keeps 6144 registers free.
+  constexpr uint32_t idesc = make_idesc_f16(1, 128, N);
+  const uint32_t tb = warp_uniform(tmem_base);
+  const uint32_t tw = warp_uniform(tmem_w);
+  const bool leader = elect_one();
+  auto issue_step = [&](const int s) {
+    mbar_wait(b_ready, (uint32_t)(s & 1));
+    if (leader) Q_PROF(0);
+    // every cell thread has consumed the partials of step s-1: re-arm that buffer for step s+1
+    if (leader && s >= 1 && s + 2 < T) mbar_expect_tx(&part_full[(s - 1) & 1], L::PART_BYTES);
+    tc_fence_after();
+    const uint32_t bb = smem_u32(bsm);
+    if (leader) {
 #pragma unroll
-        for (int a = 0; a < 2; a++) {
+      for (int a = 0; a < 2; a++) {
 #pragma unroll
-          for (int k = 0; k < 16; k++) {
-            const uint64_t bd = make_smem_desc(bb + (k >> 2) * (N * 128) + (k & 3) * 32, 16, 1024, 2);
-            if constexpr (TS) {
-              umma_f16_ts(tb + a * N, tw + a * 128 + k * 8, bd, idesc, k > 0 ? 1u : 0u);
-            } else {
-              const uint64_t ad =
-                  make_smem_desc(smem_u32(wsm) + a * 65536 + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024, 2);
-              umma_f16_ss(tb + a * N, ad, bd, idesc, k > 0 ? 1u : 0u);
-            }
+        for (int k = 0; k < 16; k++) {
+          const uint64_t bd = make_smem_desc(bb + (k >> 2) * (N * 128) + (k & 3) * 32, 16, 1024, 2);
+          if constexpr (TS) {
+            umma_f16_ts(tb + a * N, tw + a * 128 + k * 8, bd, idesc, k > 0 ? 1u : 0u);
+          } else {
+            const uint64_t ad = make_smem_desc(smem_u32(wsm) + a * 65536 + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024, 2);
+            umma_f16_ss(tb + a * N, ad, bd, idesc, k > 0 ? 1u : 0u);
           }
         }
-        umma_commit(mma_done);
-        Q_PROF(1);
-        }
-        __syncwarp();
       }
+      umma_commit(mma_done);
+      Q_PROF(1);
     }
-  } else {
+    __syncwarp();
+  };
+  {
     const int a = warp >> 2, sub = warp & 3;
     const int j = lane >> 2, q = lane & 3;        // cell role: unit j of this warp, columns [q*NQ, q*NQ+NQ)
     const int ul = a * 32 + sub * 8 + j;
@@ -926,16 +928,23 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
         __syncwarp();
         if (lane == 0) mbar_arrive(b_ready);
         if (warp == 0 && lane == 0) Q_PROF(3);
+        if (warp == 0) issue_step(s);   // waits for the other 7 warps' tiles, then launches the step's 32 MMAs
       }
+      auto store_step = [&]() {
 #pragma unroll
-      for (int i = 0; i < NQ; i++) {
-        if (FAST || b0 + q * NQ + i < B) {
-          if (p.gates) __stcs(reinterpret_cast<float4*>(gout + (long long)i * (8 * QH)), dp[i]);
-          if (p.dpre16)
-            *reinterpret_cast<uint2*>(p.dpre16 + (((long long)t * B + b0 + q * NQ + i) * 2 + dir) * (4 * QH) + 4 * ug) = dp16[i];
-          sdb[0] += dp[i].x; sdb[1] += dp[i].y; sdb[2] += dp[i].z; sdb[3] += dp[i].w;
+        for (int i = 0; i < NQ; i++) {
+          if (FAST || b0 + q * NQ + i < B) {
+            if (p.gates) __stcs(reinterpret_cast<float4*>(gout + (long long)i * (8 * QH)), dp[i]);
+            if (p.dpre16)
+              *reinterpret_cast<uint2*>(p.dpre16 + (((long long)t * B + b0 + q * NQ + i) * 2 + dir) * (4 * QH) + 4 * ug) = dp16[i];
+            sdb[0] += dp[i].x; sdb[1] += dp[i].y; sdb[2] += dp[i].z; sdb[3] += dp[i].w;
+          }
         }
-      }
+      };
+      // warps 1-7 store in the shadow of the MMAs; warp 0 has just spent that time issuing them, so its stores wait until
+      // its partial-dh rows are on their way to the peers (they would otherwise delay the next step of the whole cluster)
+      const bool store_late = (warp == 0) && (s + 1 < T);
+      if (!store_late) store_step();
       if (s + 1 < T) {
         if constexpr (!DEEP) load_step(s + 1, kept);   // one step ahead: streams in while the tensor core and the exchange run
         mbar_wait(mma_done, (uint32_t)(s & 1));
@@ -964,6 +973,7 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
         }
         if (warp == 0 && lane == 0) Q_PROF(5);
       }
+      if (store_late) store_step();
     };
     if constexpr (DEEP) {
       Kept set0, set1;
@@ -994,7 +1004,7 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__(QTHREADS, 1)
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
-  if (warp == 8) {
+  if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 64);
     if constexpr (TS) tmem_dealloc(tmem_w, 256);
@@ -1035,6 +1045,7 @@ int g_lstm_stasync = 0;        // DEER_OPT_LSTM_STASYNC: forward h all-gather by
                                // kernel alone at B = 256: 1.41 vs 1.44 us/step; B = 1024 inference 0.977 vs 0.960 ms per layer;
                                // B = 1024 training forward 1.39 vs 1.55 ms.  From issue to the peers' MMA warps seeing the tile
                                // both transports take 750-900 cycles.
+int g_lstm_carveout = 1;       // DEER_OPT_LSTM_CARVEOUT: ask for the maximum shared-memory carve-out while the recurrence runs
 static long long* g_lstm_prof = nullptr;
 void lstm_cluster_set_profile(long long* buf) { g_lstm_prof = buf; }
 void lstm_cluster_set_option(int ts, int tile) {
@@ -1061,6 +1072,12 @@ static int launch_fwd_f(const tc::LstmClusterParams& p, cudaStream_t stream) {
     cudaError_t e = cudaFuncSetAttribute(tc::lstm_fwd_cluster_kernel<N, TS, G, CS, FAST>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return cuda_status(e, "lstm_fwd_cluster smem attribute");
+    // The L1 / shared-memory split of an SM is fixed while CTAs are resident, and the driver picks the smallest carve-out
+    // that fits the kernel: ask for the maximum, so that a <= 100 KB GEMM CTA of the other stream can join the recurrence
+    // CTA (what decides whether it does is the register file, see lstm_bwd_cluster_kernel).
+    if (g_lstm_carveout)
+      cudaFuncSetAttribute(tc::lstm_fwd_cluster_kernel<N, TS, G, CS, FAST>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                           cudaSharedmemCarveoutMaxShared);
     attr = true;
   }
   DEER_LAUNCH((tc::lstm_fwd_cluster_kernel<N, TS, G, CS, FAST>), tc::QC * p.ntiles * 2,
@@ -1082,6 +1099,9 @@ static int launch_bwd_f(const tc::LstmClusterParams& p, cudaStream_t stream) {
     cudaError_t e = cudaFuncSetAttribute(tc::lstm_bwd_cluster_kernel<N, TS, K16, FAST>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return cuda_status(e, "lstm_bwd_cluster smem attribute");
+    if (g_lstm_carveout)   // see launch_fwd_f
+      cudaFuncSetAttribute(tc::lstm_bwd_cluster_kernel<N, TS, K16, FAST>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                           cudaSharedmemCarveoutMaxShared);
     attr = true;
   }
   DEER_LAUNCH((tc::lstm_bwd_cluster_kernel<N, TS, K16, FAST>), tc::QC * p.ntiles * 2, tc::QTHREADS, smem, stream, p);
