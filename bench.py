@@ -765,7 +765,7 @@ def roofline_probe(torch, ops, dev, pk):
     outp = torch.empty(Bp_, D, device=dev)
     wts = torch.empty(Bp_, T, device=dev)
     us_p = _time_launches(torch, lambda i: call("deer_attn_pool_fwd", ptr(xs[i % 2]), D, Bp_ * D, ptr(sc), 1, Bp_, None,
-                                                ptr(outp), ptr(wts), Bp_, T, D), 8, warm=2)
+                                                ptr(outp), ptr(wts), Bp_, T, D, 0), 8, warm=2)
     pbytes = float(Bp_ * T * D * 4 + 2 * Bp_ * T * 4 + Bp_ * D * 4)
     roof["attn_pool"] = {"kernel": "deer::attn_pool_fwd_kernel (B=1024, T=300, D=512: online softmax + weighted sum, one pass)",
                          "bound": "hbm", "achieved": pbytes / (us_p * 1e-6) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",

@@ -141,22 +141,29 @@ int deer_rowdot_fwd(const float* h, const float* w, const float* b, float* s, lo
 int deer_rowdot_bwd(const float* ds, const float* h, const float* w, float* dh, float* dw, float* db,
                     long long M, int N, void* stream);
 /*      backward of the whole scorer head s = w2 . tanh(z) + b2 in one pass over hidden = tanh(z) [M,N]:
- *      dz = ds w2 (1 - hidden^2) (may alias hidden), dw2 += sum_m ds hidden, db1 += sum_m dz, db2 += sum_m ds */
+ *      dz = ds w2 (1 - hidden^2) (may alias hidden), dw2 += sum_m ds hidden, db1 += sum_m dz, db2 += sum_m ds;
+ *      dz_row_scale (may be NULL): the STORED row m of dz is multiplied by dz_row_scale[m] (premasked scorer input) */
 int deer_scorer_bwd(const float* ds, const float* hidden, const float* w2, float* dz, float* dw2, float* db1, float* db2,
-                    long long M, int N, void* stream);
+                    const float* dz_row_scale, long long M, int N, void* stream);
 /*      pool: p = softmax_t(s[b,:]); if mask: p = p*mask / (sum_t p*mask + 1e-10); out[b,:] = sum_t p[b,t] * x[b,t,:]
  *      x element (b,t,d) at x[b*xs_b + t*xs_t + d]; s element (b,t) at s[b*ss_b + t*ss_t]; mask [B,T] contiguous or NULL;
- *      if premask, x is multiplied by mask before use (text path, encoders.py:734-735). wts [B,T] out. */
+ *      if premask, the pooled rows are mask[b,t] * x[b,t,:] (text path, encoders.py:733-735: the masked embeddings are
+ *      never materialised; the scorer sees them through deer_cast_split16's row_scale). wts [B,T] out. */
 int deer_attn_pool_fwd(const float* x, long long xs_b, long long xs_t, const float* s, long long ss_b, long long ss_t,
-                       const float* mask, float* out, float* wts, int B, int T, int D, void* stream);
-/*      dx (b,t,d) = wts*dout (same strides as x, overwritten or accumulated per `accumulate`), ds (same strides as s) */
+                       const float* mask, float* out, float* wts, int B, int T, int D, int premask, void* stream);
+/*      dx (b,t,d) = wts*dout (same strides as x, overwritten or accumulated per `accumulate`; NULL when x needs no
+ *      gradient: only ds is produced), ds (same strides as s) */
 int deer_attn_pool_bwd(const float* dout, const float* x, long long xs_b, long long xs_t, const float* s, long long ss_b,
                        long long ss_t, const float* mask, const float* wts, float* dx, float* ds, int B, int T, int D,
-                       int accumulate, void* stream);
+                       int accumulate, int premask, void* stream);
 
 /* ---- layout helpers */
 /* y[t,b,:] = x[b,t,:] (batch-first -> time-major) and the inverse */
 int deer_permute_bt(const float* x, float* y, int B, int T, int D, void* stream);
+/*      [B,T,D] fp32 -> time-major 16-bit rows [T*B, Dp] (Dp >= D even, columns D.. zero): FP16 (y_fp16) and / or BF16 (y_bf16)
+ *      copies in one pass -- the first nn.LSTM layer's projection operand and its weight-gradient operand
+ *      (encoders.py:82-89,380: `self.lstm(enhanced_features)` on a batch_first input) */
+int deer_permute_bt_cast16(const float* x, void* y_fp16, void* y_bf16, int B, int T, int D, int Dp, void* stream);
 /* y[m,:] = x[m,:] * mask[m]  (text mask, encoders.py:734-735); backward is the same call on dy */
 int deer_rowscale(const float* x, const float* mask, float* y, long long M, int D, void* stream);
 /* Conv1d(k=3,pad=1) lowering on channels-last x [B,T,C]: col [B*T, 3C], tap k holds x[b,t+k-1,:] (zero outside) */
@@ -168,6 +175,13 @@ int deer_col2im3(const float* dcol, float* dx, int B, int T, int C, void* stream
  *      row pitch C): deer_gemm accepts lda < K / ldb < N / ldc < N (with beta = 1: atomic accumulation) for such views.
  *      dir 0: x [B,T,C] -> xp;  dir 1: xp -> x (drops the pad rows). */
 int deer_rows_pad(const float* src, float* dst, int B, int T, int C, int lead, int tail, int dir, void* stream);
+/*      the same copy with the video encoder's neighbouring passes folded in (encoders.py:450-459, nn.Dropout -> nn.Conv1d):
+ *      dir 0: optional inverted dropout of x (the Philox stream of deer_dropout over the flat index of x: identical masks),
+ *      padded fp32 copy, and (hi / lo non-NULL, C % 8 == 0) its FP16 hi / lo split in the same geometry -- the A operand of
+ *      deer_gemm_h16_split; dir 1: un-pad dx_p and apply the same mask (the backward of dropout o pad). */
+int deer_rows_pad_fused(const float* src, float* dst, void* hi, void* lo, int B, int T, int C, int lead, int tail, int dir,
+                        float drop_p, unsigned long long seed, unsigned long long offset, const unsigned long long* step_ptr,
+                        void* stream);
 /* w [Cout,Cin,3] (nn.Conv1d layout) <-> wk [Cout,3,Cin]; dir=0 pack, dir=1 unpack with accumulate into w */
 int deer_conv3_weight_pack(const float* w, float* wk, int Cout, int Cin, int dir, void* stream);
 
@@ -295,8 +309,10 @@ int deer_adamw(float* p, const float* g, float* m, float* v, long long n, float 
 int deer_gemm_h16_split(const void* A_hi, const void* A_lo, long long lda, int transA, const void* B_hi, const void* B_lo,
                         long long ldb, int transB, float* C, long long ldc, int M, int N, int K, const float* bias, int act,
                         void* stream);
-int deer_cast_split16(const float* src, long long ld_src, void* hi, void* lo, long long ld_dst, long long rows, int cols,
-                      int cols_pad, void* stream);
+/*   row_scale (may be NULL): row r of src is multiplied by row_scale[r] before the split -- the text encoder's
+ *   `token_embeddings * attention_mask` (encoders.py:733-735) without materialising the masked copy */
+int deer_cast_split16(const float* src, long long ld_src, const float* row_scale, void* hi, void* lo, long long ld_dst,
+                      long long rows, int cols, int cols_pad, void* stream);
 
 /* ---- fused 3xTF32 GEMM of the post-pooling chain: replaces the addmm + relu + dropout (+ their backward:
  * threshold_backward, dropout mask multiply, bias-gradient sum) ATen calls of nn.Linear / nn.ReLU / nn.Dropout stacks in

@@ -43,7 +43,7 @@ _PROTOS = {
     "deer_chain_max_ops": None,
     "deer_chain_max_levels": None,
     "deer_gemm_h16_split": [P, P, L, I, P, P, L, I, P, L, I, I, I, P, I, P],
-    "deer_cast_split16": [P, L, P, P, L, L, I, I, P],
+    "deer_cast_split16": [P, L, P, P, P, L, L, I, I, P],
     "deer_gemm_h16": [P, L, I, I, P, L, I, I, P, L, P, L, I, I, I, I, P, I, F, P],
     "deer_cast16": [P, L, P, L, L, I, I, I, P],
     "deer_gemm_h16_set_profile_buffer": [P],
@@ -54,14 +54,16 @@ _PROTOS = {
     "deer_dropout_cast16": [P, P, P, L, F, U, U, P, P],
     "deer_rowdot_fwd": [P, P, P, P, L, I, P],
     "deer_rowdot_bwd": [P, P, P, P, P, P, L, I, P],
-    "deer_attn_pool_fwd": [P, L, L, P, L, L, P, P, P, I, I, I, P],
-    "deer_attn_pool_bwd": [P, P, L, L, P, L, L, P, P, P, P, I, I, I, I, P],
+    "deer_attn_pool_fwd": [P, L, L, P, L, L, P, P, P, I, I, I, I, P],
+    "deer_attn_pool_bwd": [P, P, L, L, P, L, L, P, P, P, P, I, I, I, I, I, P],
     "deer_permute_bt": [P, P, I, I, I, P],
-    "deer_scorer_bwd": [P, P, P, P, P, P, P, L, I, P],
+    "deer_permute_bt_cast16": [P, P, P, I, I, I, I, P],
+    "deer_scorer_bwd": [P, P, P, P, P, P, P, P, L, I, P],
     "deer_rowscale": [P, P, P, L, I, P],
     "deer_im2col3": [P, P, I, I, I, P],
     "deer_col2im3": [P, P, I, I, I, P],
     "deer_rows_pad": [P, P, I, I, I, I, I, I, P],
+    "deer_rows_pad_fused": [P, P, P, P, I, I, I, I, I, I, F, U, U, P, P],
     "deer_conv3_weight_pack": [P, P, I, I, I, P],
     "deer_bn_stats": [P, P, L, I, P],
     "deer_bn_update_running": [P, P, P, P, L, I, F, P],

@@ -48,7 +48,8 @@ __global__ void __launch_bounds__(256) bias_act_bwd_kernel(const float* __restri
 __global__ void __launch_bounds__(256) scorer_bwd_kernel(const float* __restrict__ ds, const float* __restrict__ hidden,
                                                          const float* __restrict__ w2, float* __restrict__ dz,
                                                          float* __restrict__ dw2, float* __restrict__ db1,
-                                                         float* __restrict__ db2, int M, int N, int rows_per_block) {
+                                                         float* __restrict__ db2, const float* __restrict__ dz_row_scale,
+                                                         int M, int N, int rows_per_block) {
   DEER_PDL_ENTRY();
   __shared__ float red[2][8][33];
   const int n = blockIdx.x * 32 + threadIdx.x;
@@ -61,7 +62,9 @@ __global__ void __launch_bounds__(256) scorer_bwd_kernel(const float* __restrict
       const float d = ds[m];
       const float h = hidden[(long long)m * N + n];
       const float g = d * w * (1.f - h * h);
-      dz[(long long)m * N + n] = g;
+      // dz_row_scale: the Linear's input was row_scale[m] * x[m] (masked text embeddings): dW1 = dz^T (scale x) is taken as
+      // (scale dz)^T x, so the stored rows carry the factor while db1 sums the unscaled gradient
+      dz[(long long)m * N + n] = dz_row_scale ? g * __ldg(dz_row_scale + m) : g;
       sw = fmaf(d, h, sw);
       sb += g;
       if (blockIdx.x == 0 && threadIdx.x == 0) sd += d;
@@ -225,6 +228,29 @@ __global__ void __launch_bounds__(256) permute_bt_kernel(const float* __restrict
   }
 }
 
+// [B,T,D] fp32 -> time-major 16-bit rows [T*B, Dp] (columns D..Dp-1 zero): the first LSTM layer's A operand (FP16) and,
+// for training, the BF16 copy its weight-gradient GEMM reads -- one pass over the input instead of permute_bt (fp32
+// time-major copy) + cast16 forward + cast16 backward
+__global__ void __launch_bounds__(256) permute_bt_cast16_kernel(const float* __restrict__ x, __half* __restrict__ y16,
+                                                                __nv_bfloat16* __restrict__ yb16, int B, int T, int D,
+                                                                int Dp) {
+  DEER_PDL_ENTRY();
+  const int pairs = Dp >> 1;
+  const long long total = (long long)B * T * pairs;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int d = (int)(i % pairs) * 2;
+    const long long r = i / pairs;  // output row = t*B + b
+    const int b = (int)(r % B);
+    const int t = (int)(r / B);
+    const float* src = x + ((long long)b * T + t) * D + d;
+    const float v0 = d < D ? __ldcs(src) : 0.f;
+    const float v1 = d + 1 < D ? __ldcs(src + 1) : 0.f;
+    if (y16) *reinterpret_cast<__half2*>(y16 + r * Dp + d) = __floats2half2_rn(v0, v1);
+    if (yb16) *reinterpret_cast<__nv_bfloat162*>(yb16 + r * Dp + d) = __floats2bfloat162_rn(v0, v1);
+  }
+}
+
 __global__ void __launch_bounds__(256) rowscale_kernel(const float* __restrict__ x, const float* __restrict__ mask,
                                                        float* __restrict__ y, long long M, int D) {
   DEER_PDL_ENTRY();
@@ -284,6 +310,79 @@ __global__ void __launch_bounds__(256) rows_pad_kernel(const float* __restrict__
     }
   }
   (void)per_sample;
+}
+
+// rows_pad with the neighbouring elementwise passes of the video encoder's Conv1d stack folded in (encoders.py:450-459:
+// Dropout -> Conv1d): dir 0 reads x [B,T,C] once, applies inverted dropout (the Philox stream of deer_dropout over the flat
+// index of x, so the fused and the separate path draw identical masks), writes the padded fp32 copy (kept for the weight
+// gradient) and, optionally, its FP16 hi / lo split in the same geometry (the A operand of the split-precision forward
+// GEMM); dir 1 (backward) drops the pad rows of dx_p and applies the same mask.  Replaces dropout + rows_pad +
+// cast_split16 (three passes over the tensor) forward and rows_pad + dropout backward.
+__global__ void __launch_bounds__(256) rows_pad_fused_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                             uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, int B,
+                                                             int T, int C4, int lead, int dir, long long pad_rows_total,
+                                                             float p, float scale, unsigned long long seed,
+                                                             unsigned long long offset,
+                                                             const unsigned long long* __restrict__ step_ptr) {
+  DEER_PDL_ENTRY();
+  const unsigned long long st = step_ptr ? *step_ptr : 0ull;
+  const uint32_t thr = (uint32_t)fminf(p * 4294967296.f, 4294967040.f);
+  const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+  const bool drop = p > 0.f;
+  const long long total = (dir == 0) ? pad_rows_total * C4 : (long long)B * T * C4;   // in float4 units
+  const float4* s4 = reinterpret_cast<const float4*>(src);
+  float4* d4 = reinterpret_cast<float4*>(dst);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / C4;
+    const int c = (int)(i % C4);
+    long long ci;          // float4 index into the compact [B,T,C] tensor, < 0: a pad row
+    if (dir == 0) {
+      const long long q = r - lead;
+      ci = -1;
+      if (q >= 0) {
+        const long long b = q / (T + 1);
+        const int t = (int)(q % (T + 1));
+        if (b < B && t < T) ci = (b * T + t) * C4 + c;
+      }
+    } else {
+      ci = i;
+    }
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ci >= 0) {
+      if (dir == 0) {
+        v = __ldcs(s4 + ci);
+      } else {
+        const long long b = r / T;
+        const int t = (int)(r % T);
+        v = __ldcs(s4 + (lead + b * (T + 1) + t) * C4 + c);
+      }
+      if (drop) {
+        const unsigned long long cnt = (unsigned long long)ci + offset;
+        const uint4 rr = philox4x32_10(make_uint4((uint32_t)cnt, (uint32_t)(cnt >> 32), (uint32_t)st, (uint32_t)(st >> 32)), key);
+        v.x = rr.x >= thr ? v.x * scale : 0.f;
+        v.y = rr.y >= thr ? v.y * scale : 0.f;
+        v.z = rr.z >= thr ? v.z * scale : 0.f;
+        v.w = rr.w >= thr ? v.w * scale : 0.f;
+      }
+    }
+    if (dir == 0) {
+      d4[i] = v;            // re-read by the GEMMs: default caching
+      if (hi) {
+        const float f[4] = {v.x, v.y, v.z, v.w};
+        __half h[4], l[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          h[j] = __float2half_rn(f[j]);
+          l[j] = __float2half_rn(f[j] - __half2float(h[j]));
+        }
+        *reinterpret_cast<uint2*>(hi + i * 4) = *reinterpret_cast<const uint2*>(h);
+        *reinterpret_cast<uint2*>(lo + i * 4) = *reinterpret_cast<const uint2*>(l);
+      }
+    } else {
+      __stcs(d4 + i, v);
+    }
+  }
 }
 
 // dx[b,t,c] = sum_k dcol[(b,t-k+1), k*C + c]
@@ -548,7 +647,7 @@ int deer_dropout_cast16(const float* x, void* y_fp16, void* y_bf16, long long n,
 }
 
 int deer_scorer_bwd(const float* ds, const float* hidden, const float* w2, float* dz, float* dw2, float* db1, float* db2,
-                    long long M, int N, void* stream) {
+                    const float* dz_row_scale, long long M, int N, void* stream) {
   DEER_CHECK_ARG(ds && hidden && w2 && dz && dw2 && db1 && db2 && M > 0 && M < (1ll << 31) && N > 0,
                  "scorer_bwd: bad args");
   const long long gx = cdiv(N, 32);
@@ -557,7 +656,7 @@ int deer_scorer_bwd(const float* ds, const float* hidden, const float* w2, float
   rpb = ((rpb + 7) / 8) * 8;
   if (rpb < 8) rpb = 8;
   dim3 grid((unsigned)gx, (unsigned)cdiv(M, rpb));
-  DEER_LAUNCH(scorer_bwd_kernel, grid, dim3(32, 8), 0, stream, ds, hidden, w2, dz, dw2, db1, db2, (int)M, N, rpb);
+  DEER_LAUNCH(scorer_bwd_kernel, grid, dim3(32, 8), 0, stream, ds, hidden, w2, dz, dw2, db1, db2, dz_row_scale, (int)M, N, rpb);
   return DEER_OK;
 }
 
@@ -582,6 +681,13 @@ int deer_permute_bt(const float* x, float* y, int B, int T, int D, void* stream)
   return DEER_OK;
 }
 
+int deer_permute_bt_cast16(const float* x, void* y_fp16, void* y_bf16, int B, int T, int D, int Dp, void* stream) {
+  DEER_CHECK_ARG(x && (y_fp16 || y_bf16) && B > 0 && T > 0 && D > 0 && Dp >= D && (Dp & 1) == 0, "permute_bt_cast16: bad args");
+  DEER_LAUNCH(permute_bt_cast16_kernel, grid_for((long long)B * T * (Dp / 2)), 256, 0, stream, x,
+              reinterpret_cast<__half*>(y_fp16), reinterpret_cast<__nv_bfloat16*>(y_bf16), B, T, D, Dp);
+  return DEER_OK;
+}
+
 int deer_rowscale(const float* x, const float* mask, float* y, long long M, int D, void* stream) {
   DEER_CHECK_ARG(x && mask && y && M > 0 && D > 0, "rowscale: bad args");
   DEER_LAUNCH(rowscale_kernel, grid_for(M * D), 256, 0, stream, x, mask, y, M, D);
@@ -601,6 +707,23 @@ int deer_rows_pad(const float* src, float* dst, int B, int T, int C, int lead, i
   const long long pad_rows = (long long)lead + (long long)B * (T + 1) + tail;
   const long long n4 = (dir == 0 ? pad_rows : (long long)B * T) * (C / 4);
   DEER_LAUNCH(rows_pad_kernel, grid_for(n4), 256, 0, stream, src, dst, B, T, C / 4, lead, dir, pad_rows);
+  return DEER_OK;
+}
+
+int deer_rows_pad_fused(const float* src, float* dst, void* hi, void* lo, int B, int T, int C, int lead, int tail, int dir,
+                        float drop_p, unsigned long long seed, unsigned long long offset, const unsigned long long* step_ptr,
+                        void* stream) {
+  DEER_CHECK_ARG(src && dst && B > 0 && T > 0 && C > 0 && (C & 3) == 0 && lead >= 0 && tail >= 0 && (dir == 0 || dir == 1) &&
+                     drop_p >= 0.f && drop_p < 1.f && ((hi == nullptr) == (lo == nullptr)) && (dir == 0 || hi == nullptr),
+                 "rows_pad_fused: bad args");
+  DEER_CHECK_ARG(((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0 &&
+                     ((reinterpret_cast<uintptr_t>(hi) | reinterpret_cast<uintptr_t>(lo)) & 7) == 0,
+                 "rows_pad_fused: alignment");
+  const long long pad_rows = (long long)lead + (long long)B * (T + 1) + tail;
+  const long long n4 = (dir == 0 ? pad_rows : (long long)B * T) * (C / 4);
+  DEER_LAUNCH(rows_pad_fused_kernel, grid_for(n4), 256, 0, stream, src, dst, reinterpret_cast<uint16_t*>(hi),
+              reinterpret_cast<uint16_t*>(lo), B, T, C / 4, lead, dir, pad_rows, drop_p, 1.f / (1.f - drop_p), seed, offset,
+              step_ptr);
   return DEER_OK;
 }
 

@@ -959,8 +959,10 @@ int gemm_tf32_pair(const float* A, long long lda, int transA, const float* B, lo
 }
 
 // fp32 -> FP16 hi / lo pair of a row-major matrix: hi = fp16(x), lo = fp16(x - hi) (22 significant bits together);
-// same geometry as cast16 (columns cols..cols_pad-1 zero-filled)
+// same geometry as cast16 (columns cols..cols_pad-1 zero-filled).  row_scale (optional): row r is multiplied by
+// row_scale[r] first (the text encoder's attention mask, encoders.py:733-735 -- the masked copy is never materialised)
 __global__ void __launch_bounds__(256) cast_split16_kernel(const float* __restrict__ src, long long ld_src,
+                                                           const float* __restrict__ row_scale,
                                                            uint16_t* __restrict__ hi, uint16_t* __restrict__ lo,
                                                            long long ld_dst, long long rows, int cols, int cols_pad) {
   DEER_PDL_ENTRY();
@@ -977,6 +979,11 @@ __global__ void __launch_bounds__(256) cast_split16_kernel(const float* __restri
     } else {
 #pragma unroll
       for (int j = 0; j < 4; j++) v[j] = (c + j < cols) ? src[r * ld_src + c + j] : 0.f;
+    }
+    if (row_scale) {
+      const float sc = __ldg(row_scale + r);
+#pragma unroll
+      for (int j = 0; j < 4; j++) v[j] *= sc;
     }
     __half h[4], l[4];
 #pragma unroll
@@ -1127,8 +1134,8 @@ int deer_gemm_h16_split(const void* A_hi, const void* A_lo, long long lda, int t
                      0.f, (cudaStream_t)stream);
 }
 
-int deer_cast_split16(const float* src, long long ld_src, void* hi, void* lo, long long ld_dst, long long rows, int cols,
-                      int cols_pad, void* stream) {
+int deer_cast_split16(const float* src, long long ld_src, const float* row_scale, void* hi, void* lo, long long ld_dst,
+                      long long rows, int cols, int cols_pad, void* stream) {
   DEER_CHECK_ARG(src && hi && lo && rows > 0 && cols > 0 && cols_pad >= cols && (cols_pad & 3) == 0 && ld_dst >= cols_pad &&
                      (ld_dst & 3) == 0,
                  "cast_split16: bad args");
@@ -1136,7 +1143,7 @@ int deer_cast_split16(const float* src, long long ld_src, void* hi, void* lo, lo
                  "cast_split16: outputs must be 8-byte aligned");
   long long g = cdiv(rows * (cols_pad / 4), 256);
   if (g > kNumSMs * 16) g = kNumSMs * 16;
-  DEER_LAUNCH(cast_split16_kernel, (unsigned)g, 256, 0, stream, src, ld_src, reinterpret_cast<uint16_t*>(hi),
+  DEER_LAUNCH(cast_split16_kernel, (unsigned)g, 256, 0, stream, src, ld_src, row_scale, reinterpret_cast<uint16_t*>(hi),
               reinterpret_cast<uint16_t*>(lo), ld_dst, rows, cols, cols_pad);
   return DEER_OK;
 }

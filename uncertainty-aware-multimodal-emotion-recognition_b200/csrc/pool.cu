@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(256) attn_pool_fwd_kernel(const float* __restr
                                                             long long xs_t, const float* __restrict__ s,
                                                             long long ss_b, long long ss_t,
                                                             const float* __restrict__ mask, float* __restrict__ out,
-                                                            float* __restrict__ wts, int B, int T, int D) {
+                                                            float* __restrict__ wts, int B, int T, int D, int premask) {
   DEER_PDL_ENTRY();
   __shared__ float p[POOL_MAX_T];
   __shared__ float red[32];
@@ -67,6 +67,13 @@ __global__ void __launch_bounds__(256) attn_pool_fwd_kernel(const float* __restr
   row_softmax_to_smem(s + b * ss_b, ss_t, mask ? mask + (long long)b * T : nullptr, T, p, red);
   if (blockIdx.y == 0 && wts)
     for (int t = threadIdx.x; t < T; t += blockDim.x) wts[(long long)b * T + t] = p[t];
+  if (premask) {
+    // the pooled rows are x~[b,t] = mask[b,t] x[b,t] (encoders.py:733-735): fold the factor into the weights of the sum
+    // instead of materialising x~ (a read + write of the whole [B,T,D] tensor)
+    __syncthreads();
+    for (int t = threadIdx.x; t < T; t += blockDim.x) p[t] *= mask[(long long)b * T + t];
+    __syncthreads();
+  }
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c4 = blockIdx.y * 32 + lane;  // float4 column
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -116,7 +123,7 @@ __global__ void __launch_bounds__(256) attn_pool_bwd_kernel(const float* __restr
                                                             long long ss_t, const float* __restrict__ mask,
                                                             const float* __restrict__ wts, float* __restrict__ dx,
                                                             float* __restrict__ ds, int B, int T, int D,
-                                                            int accumulate) {
+                                                            int accumulate, int premask) {
   DEER_PDL_ENTRY();
   __shared__ float dw[POOL_MAX_T];
   __shared__ float p[POOL_MAX_T];
@@ -128,12 +135,15 @@ __global__ void __launch_bounds__(256) attn_pool_bwd_kernel(const float* __restr
   float* dxb = dx + b * xs_b;
   const float* wb = wts + (long long)b * T;
   for (int t = w; t < T; t += 8) {
-    const float wt = wb[t];
+    // premask: the pooled rows are x~ = mask x, so dw_t = mask_t (x_t . dout) and dx_t = mask_t w_t dout
+    const float mt = premask ? mask[(long long)b * T + t] : 1.f;
+    const float wt = wb[t] * mt;
     float acc = 0.f;
     for (int c = lane * 4; c < D; c += 128) {
       const float4 g = *reinterpret_cast<const float4*>(dob + c);
       const float4 v = *reinterpret_cast<const float4*>(xb + (long long)t * xs_t + c);
       acc += g.x * v.x + g.y * v.y + g.z * v.z + g.w * v.w;
+      if (dx == nullptr) continue;           // x needs no gradient (an input tensor): only ds is produced
       float4* dp = reinterpret_cast<float4*>(dxb + (long long)t * xs_t + c);
       float4 o = make_float4(wt * g.x, wt * g.y, wt * g.z, wt * g.w);
       if (accumulate) {
@@ -145,7 +155,7 @@ __global__ void __launch_bounds__(256) attn_pool_bwd_kernel(const float* __restr
       }
       *dp = o;
     }
-    acc = warp_sum(acc);
+    acc = warp_sum(acc) * mt;
     if (lane == 0) dw[t] = acc;
   }
   __syncthreads();
@@ -184,27 +194,27 @@ using namespace deer;
 extern "C" {
 
 int deer_attn_pool_fwd(const float* x, long long xs_b, long long xs_t, const float* s, long long ss_b, long long ss_t,
-                       const float* mask, float* out, float* wts, int B, int T, int D, void* stream) {
-  DEER_CHECK_ARG(x && s && out && B > 0 && T > 0 && D > 0, "attn_pool_fwd: bad args");
+                       const float* mask, float* out, float* wts, int B, int T, int D, int premask, void* stream) {
+  DEER_CHECK_ARG(x && s && out && B > 0 && T > 0 && D > 0 && (!premask || mask), "attn_pool_fwd: bad args");
   if (T > POOL_MAX_T || (D & 3) || (xs_b & 3) || (xs_t & 3)) {
     set_error("attn_pool_fwd: need T<=%d and D, strides multiples of 4 (T=%d D=%d)", POOL_MAX_T, T, D);
     return DEER_ERR_UNSUPPORTED;
   }
   dim3 grid(B, (unsigned)cdiv(D, 128));
-  DEER_LAUNCH(attn_pool_fwd_kernel, grid, 256, 0, stream, x, xs_b, xs_t, s, ss_b, ss_t, mask, out, wts, B, T, D);
+  DEER_LAUNCH(attn_pool_fwd_kernel, grid, 256, 0, stream, x, xs_b, xs_t, s, ss_b, ss_t, mask, out, wts, B, T, D, premask);
   return DEER_OK;
 }
 
 int deer_attn_pool_bwd(const float* dout, const float* x, long long xs_b, long long xs_t, const float* s, long long ss_b,
                        long long ss_t, const float* mask, const float* wts, float* dx, float* ds, int B, int T, int D,
-                       int accumulate, void* stream) {
-  DEER_CHECK_ARG(dout && x && s && wts && dx && ds && B > 0 && T > 0 && D > 0, "attn_pool_bwd: bad args");
+                       int accumulate, int premask, void* stream) {
+  DEER_CHECK_ARG(dout && x && s && wts && ds && B > 0 && T > 0 && D > 0 && (!premask || mask), "attn_pool_bwd: bad args");
   if (T > POOL_MAX_T || (D & 3) || (xs_b & 3) || (xs_t & 3)) {
     set_error("attn_pool_bwd: need T<=%d and D, strides multiples of 4 (T=%d D=%d)", POOL_MAX_T, T, D);
     return DEER_ERR_UNSUPPORTED;
   }
   DEER_LAUNCH(attn_pool_bwd_kernel, B, 256, 0, stream, dout, x, xs_b, xs_t, s, ss_b, ss_t, mask, wts, dx, ds, B, T, D,
-              accumulate);
+              accumulate, premask);
   return DEER_OK;
 }
 

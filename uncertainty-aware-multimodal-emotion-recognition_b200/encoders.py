@@ -82,7 +82,7 @@ class EnhancedAudioEncoder(nn.Module):
     def lstm_forward(self, features: torch.Tensor, return_bf16: bool = False):
         """[B,T,84] -> time-major LSTM output [T,B,hidden_dim] (and, on request, the BF16 copy of it that the last
         layer's recurrence kernel wrote for BPTT: the pooling scorer's weight-gradient GEMM reads it as well)."""
-        h = ops.to_time_major(features)
+        h = features            # batch_first: layer 0 permutes while casting its operands (ops.bilstm_layer)
         h16 = hb16 = None
         nodrop = not (self.training and self.dropout > 0.0)
         nodes = []
@@ -92,7 +92,8 @@ class EnhancedAudioEncoder(nn.Module):
             # input projection consumes, so the [T*B, 512] cast pass disappears.
             h, h16, hb16 = ops.bilstm_layer(h, *self._layer_weights(l), input_dropout=self.dropout if l > 0 else 0.0,
                                             training=self.training, x_f16=h16,
-                                            emit_f16=nodrop and l + 1 < self.num_layers, return_bf16=True)
+                                            emit_f16=nodrop and l + 1 < self.num_layers, return_bf16=True,
+                                            x_batch_major=(l == 0))
             nodes.append(h.grad_fn)
         # autograd nodes of the layers, first layer first: layer l's weight gradients are complete when node l has run (the
         # data-parallel trainer exchanges the gradients of layers >= 1 beside the BPTT of layer 0)
@@ -146,16 +147,15 @@ class EnhancedVideoEncoder(nn.Module):
         # the autograd node that runs LAST in this encoder's backward: the data-parallel trainer hangs its early
         # gradient exchange on it (trainer._forward_backward)
         self.__dict__["_first_bwd_node"] = p.grad_fn
-        p = ops.dropout(p, self.dropout, self.training)
         if video_input.shape[1] > 1:
-            h = ops.conv1d_k3(p, cnn[0].weight, cnn[0].bias)
+            # the two nn.Dropout layers in front of the convolutions ride on the convolutions' padding passes
+            h = ops.conv1d_k3(p, cnn[0].weight, cnn[0].bias, self.dropout, self.training)
             h = self._bn_relu(h, cnn[1])
-            h = ops.dropout(h, self.dropout, self.training)
-            h = ops.conv1d_k3(h, cnn[4].weight, cnn[4].bias)
+            h = ops.conv1d_k3(h, cnn[4].weight, cnn[4].bias, self.dropout, self.training)
             h = self._bn_relu(h, cnn[5])
             pooled, _ = _scorer_and_pool(h, self.temporal_attention)
         else:
-            pooled = p[:, 0]
+            pooled = ops.dropout(p, self.dropout, self.training)[:, 0]
         op = self.output_projection
         y = ops.linear(pooled, op[0].weight, op[0].bias, "relu", dropout=self.dropout, training=self.training)
         return ops.layer_norm(y, op[3].weight, op[3].bias, op[3].eps)
@@ -201,8 +201,15 @@ class EnhancedTextEncoder(nn.Module):
             linguistic_features = self.extract_linguistic_features(input_ids, attention_mask)
         if linguistic_features is None:
             linguistic_features = ops.constant(0.0, (B, 10), dev)
-        x = ops.rowscale(token_embeddings, m)
-        agg, _ = _scorer_and_pool(x, self.token_attention, mask=m)
+        att = self.token_attention
+        if ops.scorer_pool_fused() and not (token_embeddings.requires_grad and torch.is_grad_enabled()):
+            # `token_embeddings * attention_mask` (encoders.py:733-735) inside the scorer's operand cast and the pooling
+            # kernels: the masked copy is never written
+            agg, _ = ops.scorer_pool(token_embeddings, att[0].weight, att[0].bias, att[2].weight, att[2].bias, m,
+                                     premask=True)
+        else:
+            x = ops.rowscale(token_embeddings, m)
+            agg, _ = _scorer_and_pool(x, att, mask=m)
         bp, lp, op = self.bert_projection, self.linguistic_projection, self.output_projection
         dr = dict(dropout=self.dropout, training=self.training)
         pb = ops.linear(agg, bp[0].weight, bp[0].bias, "relu", **dr)

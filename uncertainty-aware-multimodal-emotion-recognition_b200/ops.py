@@ -360,9 +360,10 @@ def gemm_h16(A, lda, transA, B, ldb, transB, C, ldc, M, N, K, *, a_bf16=False, b
          ptr(bias), act, float(beta))
 
 
-def cast_split16(x: torch.Tensor, rows=None, cols=None, ld=None):
+def cast_split16(x: torch.Tensor, rows=None, cols=None, ld=None, row_scale=None):
     """fp32 rows -> (hi, lo) FP16 [rows, Kp] with x = hi + lo to 22 significant bits (Kp = cols rounded up to 8).
-    `x` may be a tensor (viewed as rows of its last dimension) or a raw (pointer, rows, cols, ld) description."""
+    `x` may be a tensor (viewed as rows of its last dimension) or a raw (pointer, rows, cols, ld) description.
+    `row_scale` [rows] (optional): every row is multiplied by its factor first (the text encoder's attention mask)."""
     if isinstance(x, torch.Tensor):
         x2, rows, cols, ld = _rows2d(_req(x, "x"))
         src, dev = ptr(x2), x.device
@@ -371,7 +372,7 @@ def cast_split16(x: torch.Tensor, rows=None, cols=None, ld=None):
     Kp = (cols + 7) // 8 * 8
     hi = torch.empty((rows, Kp), device=dev, dtype=torch.float16)
     lo = torch.empty((rows, Kp), device=dev, dtype=torch.float16)
-    call("deer_cast_split16", src, ld, hi.data_ptr(), lo.data_ptr(), Kp, rows, cols, Kp)
+    call("deer_cast_split16", src, ld, ptr(row_scale), hi.data_ptr(), lo.data_ptr(), Kp, rows, cols, Kp)
     return hi, lo, Kp
 
 
@@ -780,7 +781,7 @@ class _AttnPool(torch.autograd.Function):
         out = torch.empty((B, D), device=x.device, dtype=torch.float32)
         wts = torch.empty((B, T), device=x.device, dtype=torch.float32)
         call("deer_attn_pool_fwd", ptr(x), x.stride(0), x.stride(1), ptr(s), s.stride(0), s.stride(1), ptr(m), ptr(out),
-             ptr(wts), B, T, D)
+             ptr(wts), B, T, D, 0)
         ctx.save_for_backward(x, s, m, wts)
         ctx.mark_non_differentiable(wts)
         return out, wts
@@ -792,7 +793,7 @@ class _AttnPool(torch.autograd.Function):
         dx = torch.empty_strided(x.shape, x.stride(), device=x.device, dtype=torch.float32)
         ds = torch.empty_strided(s.shape, s.stride(), device=x.device, dtype=torch.float32)
         call("deer_attn_pool_bwd", ptr(dout.contiguous()), ptr(x), x.stride(0), x.stride(1), ptr(s), s.stride(0),
-             s.stride(1), ptr(m), ptr(wts), ptr(dx), ptr(ds), B, T, D, 0)
+             s.stride(1), ptr(m), ptr(wts), ptr(dx), ptr(ds), B, T, D, 0, 0)
         return dx, ds, None
 
 
@@ -809,10 +810,18 @@ class _ScorerPool(torch.autograd.Function):
     input-gradient GEMM accumulates onto it (beta = 1)."""
 
     @staticmethod
-    def forward(ctx, x, w1, b1, w2, b2, mask, time_major, precise=True, x_bf16=None):
+    def forward(ctx, x, w1, b1, w2, b2, mask, time_major, precise=True, x_bf16=None, premask=False):
         """x_bf16: optional BF16 copy of x written by its producer (the LSTM recurrence kernel's shadow of h): the B
-        operand of dW1 in backward without a cast pass."""
+        operand of dW1 in backward without a cast pass.
+        premask: scorer and pooling see x~[b,t] = mask[b,t] x[b,t] (encoders.py:733-735: `token_embeddings *
+        attention_mask`) -- applied inside the operand cast and the pooling kernels, the masked copy (50 MB read + write at
+        B = 256) is never materialised.  Batch-major x only; the scorer then runs on the split-precision engine."""
         x = _req(x, "x").contiguous()
+        premask = bool(premask)
+        if premask and (mask is None or time_major or ctx.needs_input_grad[0] or not (precise and _split_fwd_ok(
+                x.shape[0] * x.shape[1], w1.shape[0], x.shape[2]))):
+            raise _lib.DeerError("deer_b200: scorer_pool(premask=True) needs a mask, batch-major x without gradient and a "
+                                 "shape the split-precision engine takes")
         ctx.x_bf16 = (x_bf16 if (x_bf16 is not None and x_bf16.dtype == torch.bfloat16 and x_bf16.is_contiguous() and
                                  x_bf16.numel() == x.numel()) else None)
         R0, R1, D = x.shape
@@ -823,8 +832,9 @@ class _ScorerPool(torch.autograd.Function):
         xs_b, xs_t = (D, B * D) if time_major else (T * D, D)
         ss_b, ss_t = (1, B) if time_major else (T, 1)
         hidden = torch.empty((M, Hd), device=dev, dtype=torch.float32)
+        m = None if mask is None else _req(mask, "mask").contiguous()
         if precise and _split_fwd_ok(M, Hd, D):
-            xh, xl, Kp = cast_split16(x.view(M, D))
+            xh, xl, Kp = cast_split16(x.view(M, D), row_scale=m if premask else None)
             wh, wl, _ = cast_split16(w1)
             gemm_split(xh, xl, Kp, wh, wl, Kp, hidden, Hd, M, Hd, D, bias=b1, act=ACT["tanh"])
         else:
@@ -832,11 +842,11 @@ class _ScorerPool(torch.autograd.Function):
         sc = torch.empty(M, device=dev, dtype=torch.float32)
         w2v = w2.reshape(-1)
         call("deer_rowdot_fwd", ptr(hidden), ptr(w2v), ptr(b2), ptr(sc), M, Hd)
-        m = None if mask is None else _req(mask, "mask").contiguous()
         out = torch.empty((B, D), device=dev, dtype=torch.float32)
         wts = torch.empty((B, T), device=dev, dtype=torch.float32)
-        call("deer_attn_pool_fwd", ptr(x), xs_b, xs_t, ptr(sc), ss_b, ss_t, ptr(m), ptr(out), ptr(wts), B, T, D)
+        call("deer_attn_pool_fwd", ptr(x), xs_b, xs_t, ptr(sc), ss_b, ss_t, ptr(m), ptr(out), ptr(wts), B, T, D, int(premask))
         ctx.save_for_backward(x, hidden, sc, m, wts, w1, w2v)
+        ctx.premask = premask
         ctx.geom = (B, T, D, M, Hd, xs_b, xs_t, ss_b, ss_t)
         ctx.params = (w1, b1, w2, b2)
         ctx.mark_non_differentiable(wts)
@@ -852,16 +862,17 @@ class _ScorerPool(torch.autograd.Function):
         need_dx = ctx.needs_input_grad[0]
         if dout is None:
             dout = torch.zeros((B, D), device=dev, dtype=torch.float32)
-        dx = torch.empty_like(x)               # the pooling kernel always writes it; dropped when x needs no gradient
+        dx = torch.empty_like(x) if need_dx else None    # an input tensor (text embeddings): only ds is produced
         ds = torch.empty(M, device=dev, dtype=torch.float32)
         call("deer_attn_pool_bwd", ptr(dout.contiguous()), ptr(x), xs_b, xs_t, ptr(sc), ss_b, ss_t, ptr(m), ptr(wts),
-             ptr(dx), ptr(ds), B, T, D, 0)
+             ptr(dx), ptr(ds), B, T, D, 0, int(ctx.premask))
         dw2, dw2_direct = _acc(pw2, like=w2v)
         db2, db2_direct = _acc(pb2)
         db1, db1_direct = _acc(pb1)
         # the whole scorer head backward in one pass over the saved tanh output
         dh = torch.empty_like(hidden)
-        call("deer_scorer_bwd", ptr(ds), ptr(hidden), ptr(w2v), ptr(dh), ptr(dw2), ptr(db1), ptr(db2), M, Hd)
+        call("deer_scorer_bwd", ptr(ds), ptr(hidden), ptr(w2v), ptr(dh), ptr(dw2), ptr(db1), ptr(db2),
+             ptr(m.view(-1)) if ctx.premask else None, M, Hd)
         dw1, dw1_direct = _acc(pw1)
         if _bwd16_ok(M) and Hd % 8 == 0 and D % 8 == 0:
             # BF16 operands on the 16-bit tcgen05 engine: dx += dh W1 (onto the pooling gradient), dW1 += dh^T x
@@ -889,7 +900,7 @@ class _ScorerPool(torch.autograd.Function):
                 gemm(dh, Hd, 1, x, D, 0, dw1, D, Hd, D, M, beta=1.0, engine=_bwd_engine(M))
         ctx.x_bf16 = None
         return (dx if need_dx else None, None if dw1_direct else dw1, None if db1_direct else db1,
-                None if dw2_direct else dw2.view_as(pw2), None if db2_direct else db2, None, None, None, None)
+                None if dw2_direct else dw2.view_as(pw2), None if db2_direct else db2, None, None, None, None, None)
 
 
 def set_scorer_pool_fused(on: bool):
@@ -901,11 +912,16 @@ def scorer_pool_fused() -> bool:
     return _state["scorer_pool_fused"]
 
 
-def scorer_pool(x, w1, b1, w2, b2, mask=None, time_major=False, precise=True, x_bf16=None):
+def scorer_pool(x, w1, b1, w2, b2, mask=None, time_major=False, precise=True, x_bf16=None, premask=False):
     """(pooled [B,D], attention weights [B,T]) of x [T,B,D] (time_major) or [B,T,D]; see _ScorerPool.  `precise`: the
     scorer's forward GEMM on the split-precision engine (default); False = TF32 (the audio encoder: its pooled output
     averages 300 highly correlated steps and is dominated by the FP16 recurrence's own 4e-5, measured)."""
-    return _ScorerPool.apply(x, w1, b1, w2, b2, mask, bool(time_major), bool(precise), x_bf16)
+    if premask:
+        M = x.shape[0] * x.shape[1]
+        if not (precise and _split_fwd_ok(M, w1.shape[0], x.shape[2])):
+            # no split-precision engine for this shape (small batches, forced engines): materialise the masked rows
+            x, premask = rowscale(x, mask), False
+    return _ScorerPool.apply(x, w1, b1, w2, b2, mask, bool(time_major), bool(precise), x_bf16, bool(premask))
 
 
 class _RowScale(torch.autograd.Function):
@@ -975,6 +991,12 @@ class _PermuteBT(torch.autograd.Function):
 
 def to_time_major(x):
     return _PermuteBT.apply(x)
+
+
+def set_lstm_batch_major_input(on: bool):
+    """First LSTM layer reads the batch_first input through one permute + 16-bit cast pass (default) or through a
+    materialised fp32 time-major copy (ablation / reference point of the equality test)."""
+    _state["lstm_bm_input"] = bool(on)
 
 
 # ----------------------------------------------------------------------------------------------- BiLSTM layer
@@ -1075,11 +1097,16 @@ class _BiLSTMLayerCluster(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, wif, whf, bif, bhf, wir, whr, bir, bhr, drop=None, x16_in=None, emit_f16=False,
-                grad_mode=True):
+                grad_mode=True, batch_major=False):
         """x16_in: FP16 copy of x written by the previous layer's recurrence kernel (skips the cast pass); emit_f16: make
-        this layer's kernel write such a copy of h.  Returns (h, h_f16 or an empty tensor)."""
+        this layer's kernel write such a copy of h.  Returns (h, h_f16 or an empty tensor).
+        batch_major: x is the batch_first input [B,T,In] of the first layer (no gradient): one pass writes its
+        time-major FP16 / BF16 operand copies (no fp32 time-major copy, no cast passes)."""
         x = _req(x, "x").contiguous()
-        T, B, In = x.shape
+        if batch_major:
+            B, T, In = x.shape
+        else:
+            T, B, In = x.shape
         H = whf.shape[1]
         G = 4 * H
         dev = x.device
@@ -1115,8 +1142,17 @@ class _BiLSTMLayerCluster(torch.autograd.Function):
         # the 16-bit shadow outputs are non-differentiable: without this autograd hands backward a zero-filled tensor
         # for each of them (a 79 MB BF16 fill per layer and step)
         ctx.set_materialize_grads(False)
+        if batch_major and not (use16 and drop is None and not ctx.needs_input_grad[0]):
+            raise _lib.DeerError("deer_b200: batch_major LSTM input needs the 16-bit GEMM path, no input dropout and an "
+                                 "input without gradient")
         if use16:
-            if drop is not None:                              # dropout + fp16 cast in one pass over x
+            if batch_major:                                   # permute + both 16-bit casts in one pass over x
+                x16 = torch.empty((M, Kp), device=dev, dtype=torch.float16)
+                xb16 = torch.empty((M, Kp), device=dev, dtype=torch.bfloat16) if keep else None
+                call("deer_permute_bt_cast16", ptr(x), x16.data_ptr(), None if xb16 is None else xb16.data_ptr(),
+                     B, T, In, Kp)
+                ctx.xdrop_b16 = xb16
+            elif drop is not None:                            # dropout + fp16 cast in one pass over x
                 x16 = torch.empty((M, In), device=dev, dtype=torch.float16)
                 # training: the same pass also writes the BF16 copy the weight-gradient GEMM of backward reads (79 MB
                 # more to store here, instead of a second Philox pass over x in backward: 47 us -> ~10 us)
@@ -1191,8 +1227,8 @@ class _BiLSTMLayerCluster(torch.autograd.Function):
         dx = None
         drop = ctx.drop
         if use16:
-            if drop is not None and ctx.xdrop_b16 is not None:
-                xb16 = ctx.xdrop_b16                           # written by the forward's dropout + cast pass
+            if ctx.xdrop_b16 is not None:
+                xb16 = ctx.xdrop_b16                           # written by the forward's (dropout / permute) + cast pass
                 ctx.xdrop_b16 = None
             elif drop is not None:                             # the same mask, regenerated while casting to bf16
                 xb16 = torch.empty((M, In), device=dev, dtype=torch.bfloat16)
@@ -1234,7 +1270,7 @@ class _BiLSTMLayerCluster(torch.autograd.Function):
             # one pass: every gate-interleaved gradient of the layer accumulated into its nn.LSTM-order target
             call("deer_lstm_unprep", ptr(dwi_il2), ptr(dwh_il2), ptr(db_il), *[ptr(t[0]) for t in tg], H, In)
             r = [None if direct else buf for buf, direct in tg]
-            return dx, r[0], r[2], r[4], r[5], r[1], r[3], r[6], r[7], None, None, None, None
+            return dx, r[0], r[2], r[4], r[5], r[1], r[3], r[6], r[7], None, None, None, None, None
         for d in range(2):
             gp = dpre.data_ptr() + 4 * G * d
             dwi_il = torch.zeros((G, In), device=dev, dtype=torch.float32)
@@ -1257,12 +1293,15 @@ class _BiLSTMLayerCluster(torch.autograd.Function):
                 dbs.append(None if direct else tgt)
             out.append((None if dwi_direct else dwi, None if dwh_direct else dwh, dbs[0], dbs[1]))
         (dwif, dwhf, dbif, dbhf), (dwir, dwhr, dbir, dbhr) = out
-        return dx, dwif, dwhf, dbif, dbhf, dwir, dwhr, dbir, dbhr, None, None, None, None
+        return dx, dwif, dwhf, dbif, dbhf, dwir, dwhr, dbir, dbhr, None, None, None, None, None
 
 
 def bilstm_layer(x_tm, wif, whf, bif, bhf, wir, whr, bir, bhr, input_dropout: float = 0.0, training: bool = False,
-                 x_f16=None, emit_f16: bool = False, return_f16: bool = False, return_bf16: bool = False):
+                 x_f16=None, emit_f16: bool = False, return_f16: bool = False, return_bf16: bool = False,
+                 x_batch_major: bool = False):
     """engine AUTO/TF32: persistent cluster kernels when H == 256; SIMT: exact-fp32 stepwise; others: see lstm.cu.
+    `x_batch_major`: x_tm is the batch_first [B,T,I] input of the first layer; on the cluster path its time-major 16-bit
+    operand copies are written in one pass, elsewhere it is permuted first (ops.to_time_major).
     `input_dropout` (with `training`) applies nn.LSTM's inter-layer dropout to x_tm: fused into the layer's 16-bit
     operand casts on the cluster path, a separate kernel otherwise.
     `return_f16`: return (h, h_f16); with `emit_f16` h_f16 is the FP16 copy of h the recurrence kernel writes beside it
@@ -1270,6 +1309,12 @@ def bilstm_layer(x_tm, wif, whf, bif, bhf, wir, whr, bir, bhr, input_dropout: fl
     case)."""
     cluster = _state["lstm_engine"] in (ENGINE_AUTO, ENGINE_TF32) and whf.shape[1] == 256
     drop = None
+    bm = False
+    if x_batch_major:
+        bm = (cluster and _state["lstm_gemm16"] and _state["engine"] == ENGINE_AUTO and _state.get("lstm_bm_input", True)
+              and not (training and input_dropout > 0.0) and not (x_tm.requires_grad and torch.is_grad_enabled()))
+        if not bm:
+            x_tm = to_time_major(x_tm)
     if training and input_dropout > 0.0:
         fusable = (cluster and _state["fuse_lstm_dropout"] and _state["lstm_gemm16"] and
                    _state["engine"] == ENGINE_AUTO and x_tm.shape[-1] % 8 == 0)
@@ -1284,7 +1329,7 @@ def bilstm_layer(x_tm, wif, whf, bif, bhf, wir, whr, bir, bhr, input_dropout: fl
         # (a custom Function's forward always runs with grad mode off: the caller's mode is passed in, so that an
         # inference forward keeps nothing for BPTT and can use the no-keep kernels)
         h, h16, hb16 = _BiLSTMLayerCluster.apply(x_tm, wif, whf, bif, bhf, wir, whr, bir, bhr, drop,
-                                                 x_f16 if drop is None else None, want, torch.is_grad_enabled())
+                                                 x_f16 if drop is None else None, want, torch.is_grad_enabled(), bm)
         if return_bf16:     # (h, FP16 copy or None, BF16 copy or None): the 16-bit shadows the recurrence kernel wrote
             return h, (h16 if h16.numel() else None), (hb16 if hb16.numel() else None)
         return (h, h16 if h16.numel() else None) if return_f16 else h
@@ -1350,20 +1395,28 @@ class _Conv1dK3Window(torch.autograd.Function):
     Rows centred on a pad row are garbage in y_big and are dropped by the un-padding copy; dy_big has zeros there."""
 
     @staticmethod
-    def forward(ctx, x, w, b):
+    def forward(ctx, x, w, b, drop=None):
+        """drop = (p, seed, offset, step tensor or None): the nn.Dropout in front of the convolution (encoders.py:453-454)
+        folded into the padding pass (forward) and the un-padding pass (backward): same Philox stream as ops.dropout."""
         x = _req(x, "x").contiguous()
         B, T, Cin = x.shape
         Cout = w.shape[0]
         dev = x.device
         Mp = B * (T + 1)                                        # window rows (one per padded row centre)
         xp = torch.empty((Mp + 2, Cin), device=dev, dtype=torch.float32)
-        call("deer_rows_pad", ptr(x), ptr(xp), B, T, Cin, 1, 1, 0)
+        split = _split_fwd_ok(Mp, Cout, 3 * Cin) and Cin % 8 == 0
+        dp, dseed, doff, dstep = drop if drop is not None else (0.0, 0, 0, None)
+        xh = xl = None
+        if split:   # the hi / lo FP16 copies of the padded rows keep the overlapping-window geometry (row pitch Cin)
+            xh = torch.empty((Mp + 2, Cin), device=dev, dtype=torch.float16)
+            xl = torch.empty((Mp + 2, Cin), device=dev, dtype=torch.float16)
+        # one pass: dropout, zero pad rows, fp32 copy (weight gradient) and the split-precision A operand
+        call("deer_rows_pad_fused", ptr(x), ptr(xp), None if xh is None else xh.data_ptr(),
+             None if xl is None else xl.data_ptr(), B, T, Cin, 1, 1, 0, float(dp), int(dseed), int(doff), ptr(dstep))
         wk = torch.empty((Cout, 3 * Cin), device=dev, dtype=torch.float32)
         call("deer_conv3_weight_pack", ptr(w.contiguous()), ptr(wk), Cout, Cin, 0)
         y_big = torch.empty((Mp, Cout), device=dev, dtype=torch.float32)
-        if _split_fwd_ok(Mp, Cout, 3 * Cin) and Cin % 8 == 0:
-            # split-precision taps: the hi / lo FP16 copies of the padded rows keep the overlapping-window geometry
-            xh, xl, _ = cast_split16(xp)
+        if split:
             wh, wl, _ = cast_split16(wk)
             gemm_split(xh, xl, Cin, wh, wl, 3 * Cin, y_big, Cout, Mp, Cout, 3 * Cin, bias=b)   # lda = Cin < K = 3 Cin
         else:
@@ -1373,6 +1426,7 @@ class _Conv1dK3Window(torch.autograd.Function):
         ctx.save_for_backward(xp, wk)
         ctx.dims = (B, T, Cin, Cout)
         ctx.params = (w, b)
+        ctx.drop = (float(dp), int(dseed), int(doff), dstep)
         return y
 
     @staticmethod
@@ -1397,7 +1451,8 @@ class _Conv1dK3Window(torch.autograd.Function):
             else:
                 gemm(dy_big, Cout, 0, wk, 3 * Cin, 0, dx_p, Cin, Mp, 3 * Cin, Cout, beta=1.0)   # ldc = Cin < N: overlapped
             dx = torch.empty((B, T, Cin), device=dev, dtype=torch.float32)
-            call("deer_rows_pad", ptr(dx_p), ptr(dx), B, T, Cin, 1, 1, 1)
+            dp, dseed, doff, dstep = ctx.drop
+            call("deer_rows_pad_fused", ptr(dx_p), ptr(dx), None, None, B, T, Cin, 1, 1, 1, dp, dseed, doff, ptr(dstep))
         dwk = zeros_scratch(tuple(wk.shape), dev)
         if bf:
             gemm_h16(dyb, Cout, 1, xpb, Cin, 0, dwk, 3 * Cin, Cout, 3 * Cin, Mp, a_bf16=True, b_bf16=True, beta=1.0)
@@ -1407,7 +1462,7 @@ class _Conv1dK3Window(torch.autograd.Function):
         call("deer_conv3_weight_pack", ptr(dwk), ptr(dw), Cout, Cin, 1)
         db, db_direct = _acc(ctx.params[1])
         call("deer_bias_act_bwd", ptr(dy), Cout, None, 0, None, 0, ptr(db), B * T, Cout, 0)
-        return dx, None if dw_direct else dw, None if db_direct else db
+        return dx, None if dw_direct else dw, None if db_direct else db, None
 
 
 def set_conv_window(on: bool):
@@ -1415,16 +1470,34 @@ def set_conv_window(on: bool):
     _state["conv_window"] = bool(on)
 
 
-def conv1d_k3(x, w, b):
-    """Large batches on the TMA engine use the sliding-window path (no im2col matrix); small ones (the CTA-pair kernel
-    needs > 256 rows), forced engines and odd channel counts keep the im2col + GEMM path."""
+def conv1d_k3(x, w, b, dropout_p: float = 0.0, training: bool = False):
+    """Conv1d(k=3, padding=1) of dropout(x) (dropout_p > 0 and training: the nn.Dropout in front of the convolution,
+    encoders.py:453-454).  Large batches on the TMA engine use the sliding-window path (no im2col matrix; the dropout
+    rides on its padding / un-padding passes); small ones (the CTA-pair kernel needs > 256 rows), forced engines and odd
+    channel counts keep the im2col + GEMM path behind a separate dropout node.  Both draw the same masks."""
     B, T, Cin = x.shape
     Cout = w.shape[0]
+    dropping = training and dropout_p > 0.0
     if (_state.get("conv_window", True) and not _state["conv_exact"] and _state["engine"] == ENGINE_AUTO and
             B * (T + 1) > 256 and Cin % 4 == 0 and
             Cout % 4 == 0 and Cin >= 32 and Cout > 256):   # dW runs with M = Cout rows on the CTA-pair kernel
-        return _Conv1dK3Window.apply(x, w, b)
+        drop = None
+        if dropping and _state.get("conv_drop_fused", True):
+            off = _dropout_state["offset"]
+            _dropout_state["offset"] = off + (x.numel() + 3) // 4
+            drop = (float(dropout_p), _dropout_seed(), off, _dropout_state["step"])
+        elif dropping:
+            x = dropout(x, dropout_p, training)
+        return _Conv1dK3Window.apply(x, w, b, drop)
+    if dropping:
+        x = dropout(x, dropout_p, training)
     return _Conv1dK3.apply(x, w, b)
+
+
+def set_conv_dropout_fused(on: bool):
+    """Dropout in front of a sliding-window Conv1d inside its padding passes (default) or as a separate node (ablation /
+    the reference point of the equality test)."""
+    _state["conv_drop_fused"] = bool(on)
 
 
 class _BNReLU(torch.autograd.Function):
