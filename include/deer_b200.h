@@ -132,8 +132,10 @@ int deer_dropout(const float* x, float* y, long long n, float p, unsigned long l
                  const unsigned long long* step_ptr, void* stream);
 /*      the same mask (same seed / offset / step) applied while casting to the 16-bit GEMM operands of the next LSTM layer
  *      (nn.LSTM inter-layer dropout, encoders.py:82-89): y_fp16 and/or y_bf16 [n], n % 4 == 0; p == 0 is a plain cast */
+/*      keep_mask (may be NULL; needs n % 128 == 0): uint32 [n/32], bit j of word w = element 32 w + j survived -- read
+ *      back by deer_gemm_h16_dropmask in backward instead of a Philox pass over the input gradient */
 int deer_dropout_cast16(const float* x, void* y_fp16, void* y_bf16, long long n, float p, unsigned long long seed,
-                        unsigned long long offset, const unsigned long long* step_ptr, void* stream);
+                        unsigned long long offset, const unsigned long long* step_ptr, void* keep_mask, void* stream);
 
 /* ---- attention pooling over time (encoders.py:93-98,383-384; :462-467,543-544; :597-602,738-746).
  *      rowdot: s[m] = sum_j h[m,j]*w[j] + b[0]   (the Linear(D/2 -> 1) scorer head) */
@@ -297,6 +299,14 @@ int deer_step_increment(long long* step, void* stream);
 int deer_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                float eps, float weight_decay, int step, const float* sumsq, float max_norm, float grad_scale,
                const long long* step_dev, const float* lr_dev, void* stream);
+
+/* ---- C = dropout'(A B): the 16-bit GEMM (CTA-pair kernel: M > 128, N % 32 == 0, fp32 C, beta = 0) whose epilogue applies
+ * the keep mask of an inverted dropout over C (deer_dropout_cast16's keep_mask, row pitch N/32 words) and its 1/(1-p)
+ * scale: nn.LSTM's inter-layer dropout in backward (encoders.py:82-89) -- dx of layer l+1 is masked while it is written,
+ * instead of a read-modify-write pass over [T*B, 2H] fp32. */
+int deer_gemm_h16_dropmask(const void* A, long long lda, int transA, int a_bf16, const void* B, long long ldb, int transB,
+                           int b_bf16, float* C, long long ldc, int M, int N, int K, const void* keep_mask, float scale,
+                           void* stream);
 
 /* ---- split-precision GEMM of the time-batched FORWARD contractions (scorers encoders.py:93-98,462-467,597-602, video
  * spatial_projection :443-447, Conv1d taps :450-459): every fp32 operand travels as a pair of FP16 matrices

@@ -138,3 +138,46 @@ def test_lstm_batch_first_input_cast_is_bitwise_the_permuted_copy():
     assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
     for a, b, (n, _) in zip(res[0][2], res[1][2], enc.lstm.named_parameters()):
         assert torch.equal(a, b), n
+
+
+def test_lstm_interlayer_dropout_mask_in_gemm_epilogue_matches_philox_pass():
+    """nn.LSTM inter-layer dropout (encoders.py:82-89) in backward: the keep bits written by the forward's dropout + cast
+    pass, applied by the epilogue of layer 1's input-gradient GEMM (deer_gemm_h16_dropmask) == the Philox pass over dx:
+    same forward, the same gradients (identical operands, same kernel: bitwise)."""
+    from deer_b200.encoders import EnhancedAudioEncoder
+    torch.manual_seed(5)
+    enc = EnhancedAudioEncoder({"dropout": 0.3}).cuda().train()
+    x = torch.randn(8, 40, 84, device="cuda")           # M = 320 rows: the CTA-pair kernel
+    pr = torch.randn(40, 8, 512, device="cuda")
+    res = []
+    for masked in (True, False):
+        ops.set_lstm_dropout_mask(masked)
+        try:
+            ops.manual_seed(11)
+            ops.begin_step()
+            for p in enc.parameters():
+                p.grad = None
+            h = enc.lstm_forward(x)
+            (h * pr).sum().backward()
+            res.append((h.detach(), {n: p.grad.clone() for n, p in enc.lstm.named_parameters()}))
+        finally:
+            ops.set_lstm_dropout_mask(True)
+    assert torch.equal(res[0][0], res[1][0])
+    for n in res[0][1]:
+        a, b = res[0][1][n], res[1][1][n]
+        if "_l1" in n:        # layer 1's own gradients do not pass through the masked dx
+            assert torch.equal(a, b), n
+        else:                 # layer 0 sees dx: x * scale vs x * (1/(1-p)) may differ in the last bit
+            assert_close(a, b, 1e-6, n)
+
+
+def test_dropout_keep_mask_bits_match_the_dropped_tensor():
+    from deer_b200._lib import call
+    n = 128 * 50
+    x = torch.randn(n, device="cuda").abs() + 0.1
+    y16 = torch.empty(n, device="cuda", dtype=torch.float16)
+    mask = torch.zeros(n // 32, device="cuda", dtype=torch.int32)
+    call("deer_dropout_cast16", x.data_ptr(), y16.data_ptr(), None, n, 0.4, 99, 7, None, mask.data_ptr())
+    bits = ((mask.view(-1, 1) >> torch.arange(32, device="cuda", dtype=torch.int32)) & 1).reshape(-1).bool()
+    assert torch.equal(bits, y16 != 0)
+    assert 0.5 < float(bits.float().mean()) < 0.7

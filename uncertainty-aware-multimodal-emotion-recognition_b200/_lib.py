@@ -51,7 +51,8 @@ _PROTOS = {
     "deer_layernorm_fwd": [P, P, P, P, P, P, I, I, F, P],
     "deer_layernorm_bwd": [P, P, P, P, P, P, P, P, I, I, P],
     "deer_dropout": [P, P, L, F, U, U, P, P],
-    "deer_dropout_cast16": [P, P, P, L, F, U, U, P, P],
+    "deer_dropout_cast16": [P, P, P, L, F, U, U, P, P, P],
+    "deer_gemm_h16_dropmask": [P, L, I, I, P, L, I, I, P, L, I, I, I, P, F, P],
     "deer_rowdot_fwd": [P, P, P, P, L, I, P],
     "deer_rowdot_bwd": [P, P, P, P, P, P, L, I, P],
     "deer_attn_pool_fwd": [P, L, L, P, L, L, P, P, P, I, I, I, I, P],

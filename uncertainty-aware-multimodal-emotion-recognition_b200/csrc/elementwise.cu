@@ -124,7 +124,8 @@ __global__ void __launch_bounds__(256) dropout_cast16_kernel(const float* __rest
                                                              uint16_t* __restrict__ y_b, long long n, float p,
                                                              float scale, unsigned long long seed,
                                                              unsigned long long offset,
-                                                             const unsigned long long* __restrict__ step_ptr) {
+                                                             const unsigned long long* __restrict__ step_ptr,
+                                                             uint32_t* __restrict__ mask_out) {
   DEER_PDL_ENTRY();
   const unsigned long long st = step_ptr ? *step_ptr : 0ull;
   const uint32_t thr = (uint32_t)fminf(p * 4294967296.f, 4294967040.f);
@@ -134,6 +135,7 @@ __global__ void __launch_bounds__(256) dropout_cast16_kernel(const float* __rest
        q += (long long)gridDim.x * blockDim.x) {
     const long long i = q * 4;
     float4 v = __ldcs(reinterpret_cast<const float4*>(x + i));
+    uint32_t keep = 0xFu;
     if (p > 0.f) {
       const unsigned long long c = (unsigned long long)q + offset;
       const uint4 r =
@@ -142,6 +144,17 @@ __global__ void __launch_bounds__(256) dropout_cast16_kernel(const float* __rest
       v.y = r.y >= thr ? v.y * scale : 0.f;
       v.z = r.z >= thr ? v.z * scale : 0.f;
       v.w = r.w >= thr ? v.w * scale : 0.f;
+      keep = (r.x >= thr ? 1u : 0u) | (r.y >= thr ? 2u : 0u) | (r.z >= thr ? 4u : 0u) | (r.w >= thr ? 8u : 0u);
+    }
+    if (mask_out) {
+      // keep bits of 32 consecutive elements as one word (bit j = element 32 w + j): 8 lanes x 4 bits; the host
+      // guarantees n % 128 == 0, so every warp is complete here.  Read back by the epilogue of the backward's
+      // input-gradient GEMM (deer_gemm_h16_dropmask) instead of a Philox pass over dx.
+      uint32_t w = keep << (4 * (threadIdx.x & 7));
+      w |= __shfl_xor_sync(0xffffffffu, w, 1);
+      w |= __shfl_xor_sync(0xffffffffu, w, 2);
+      w |= __shfl_xor_sync(0xffffffffu, w, 4);
+      if ((threadIdx.x & 7) == 0) mask_out[q >> 3] = w;
     }
     if (y_h) {
       __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
@@ -636,13 +649,15 @@ int deer_dropout(const float* x, float* y, long long n, float p, unsigned long l
 }
 
 int deer_dropout_cast16(const float* x, void* y_fp16, void* y_bf16, long long n, float p, unsigned long long seed,
-                        unsigned long long offset, const unsigned long long* step_ptr, void* stream) {
-  DEER_CHECK_ARG(x && (y_fp16 || y_bf16) && n > 0 && (n & 3) == 0 && p >= 0.f && p < 1.f, "dropout_cast16: bad args");
+                        unsigned long long offset, const unsigned long long* step_ptr, void* keep_mask, void* stream) {
+  DEER_CHECK_ARG(x && (y_fp16 || y_bf16) && n > 0 && (n & 3) == 0 && p >= 0.f && p < 1.f && (!keep_mask || (n & 127) == 0),
+                 "dropout_cast16: bad args");
   DEER_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y_fp16) & 7) == 0 &&
                      (reinterpret_cast<uintptr_t>(y_bf16) & 7) == 0,
                  "dropout_cast16: alignment");
   DEER_LAUNCH(dropout_cast16_kernel, dropout_grid(n >> 2), 256, 0, stream, x, reinterpret_cast<uint16_t*>(y_fp16),
-              reinterpret_cast<uint16_t*>(y_bf16), n, p, 1.f / (1.f - p), seed, offset, step_ptr);
+              reinterpret_cast<uint16_t*>(y_bf16), n, p, 1.f / (1.f - p), seed, offset, step_ptr,
+              reinterpret_cast<uint32_t*>(keep_mask));
   return DEER_OK;
 }
 

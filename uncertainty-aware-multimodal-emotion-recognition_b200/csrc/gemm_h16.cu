@@ -51,6 +51,8 @@ struct Params {
   int debug;            // bit 0: skip the fp32 stores (timing experiments only)
   int kb_phase;         // split-precision mode (pair kernel): k-blocks of ONE pass over K; the k loop makes three passes
                         // (A_hi,B_hi), (A_lo,B_hi), (A_hi,B_lo) over the hi / lo operand maps.  0: plain GEMM
+  const uint32_t* drop_mask;   // optional (pair kernel, fp32 output, beta = 0, N % 32 == 0): keep bits of an inverted dropout
+  float drop_scale;            // over C, one word per (row, 32 columns): C = keep ? C * drop_scale : 0 in the epilogue
 };
 #define H16_T0() const long long _t0 = p.prof ? clock64() : 0
 #define H16_ACC(slot)                                                   \
@@ -673,6 +675,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
             v[j] = o.x; v[j + 1] = o.y; v[j + 2] = o.z; v[j + 3] = o.w;
           }
         }
+        if (p.drop_mask) {
+          // the backward of an inverted dropout on this GEMM's output (nn.LSTM's inter-layer dropout applied to dx): this
+          // lane holds 32 consecutive columns of one row = one word of the keep mask the forward pass wrote
+          const int row = row_base + lane;
+          const uint32_t w = row < p.M ? __ldg(p.drop_mask + (long long)row * (p.N >> 5) + (gn0 >> 5)) : 0u;
+#pragma unroll
+          for (int j = 0; j < 32; j++) v[j] = ((w >> j) & 1u) ? v[j] * p.drop_scale : 0.f;
+        }
         if (p.debug & 2) continue;   // timing experiments: TMEM read only
         // double-buffered store tiles: before overwriting a tile only the store issued TWO chunks ago must have been
         // read out by the TMA unit; the previous chunk's store keeps draining while this one is staged (the wait
@@ -767,6 +777,10 @@ int gemm_h16(const void* A, long long lda, int transA, int a_bf, const void* B, 
                      bias, act, beta, stream);
 }
 
+// keep mask handed to the NEXT gemm_h16_ex call of this thread (set and cleared by gemm_h16_dropmask)
+static thread_local const uint32_t* t_drop_mask = nullptr;
+static thread_local float t_drop_scale = 1.f;
+
 // A_lo / B_lo non-NULL: split-precision product (A + A_lo)(B + B_lo) ~ A B + A_lo B + A B_lo on FP16 hi / lo operand
 // pairs (CTA-pair kernel only; beta = 0)
 int gemm_h16_ex(const void* A, const void* A_lo, long long lda, int transA, int a_bf, const void* B, const void* B_lo,
@@ -847,7 +861,11 @@ int gemm_h16_ex(const void* A, const void* A_lo, long long lda, int transA, int 
                          ((uint32_t)(transA ? 1 : 0) << 15) | ((uint32_t)(transB ? 0 : 1) << 16) |
                          ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(tile_rows >> 4) << 24);
   Params p{C, ldc, C16, ldc16, c16_bf, bias, M, N, K, act, beta, splits, per, tiles_m, tiles_n, idesc, g_h16_prof,
-           getenv("DEER_H16_DEBUG") ? atoi(getenv("DEER_H16_DEBUG")) : 0, split ? kb_phase : 0};
+           getenv("DEER_H16_DEBUG") ? atoi(getenv("DEER_H16_DEBUG")) : 0, split ? kb_phase : 0, t_drop_mask, t_drop_scale};
+  if (p.drop_mask && (!pair || out16 || beta != 0.f || (N & 31) || ldc < N || p.debug)) {
+    set_error("gemm_h16: the dropout-mask epilogue needs the CTA-pair kernel (M > 128), fp32 output, beta = 0 and N %% 32 == 0");
+    return DEER_ERR_UNSUPPORTED;
+  }
   const int work = tiles_m * tiles_n * splits;
   if (pair) {
     const int clusters = work < kNumSMs / 2 ? work : kNumSMs / 2;
@@ -1118,6 +1136,24 @@ int deer_gemm_h16(const void* A, long long lda, int transA, int a_bf16, const vo
   g_engine_calls[DEER_ENGINE_H16]++;
   return gemm_h16(A, lda, transA, a_bf16, B, ldb, transB, b_bf16, C, ldc, C16, ldc16, c16_bf16, M, N, K, bias, act, beta,
                   (cudaStream_t)stream);
+}
+
+int deer_gemm_h16_dropmask(const void* A, long long lda, int transA, int a_bf16, const void* B, long long ldb, int transB,
+                           int b_bf16, float* C, long long ldc, int M, int N, int K, const void* keep_mask, float scale,
+                           void* stream) {
+  DEER_CHECK_ARG(A && B && C && keep_mask && M > 0 && N > 0 && K > 0 && scale > 0.f, "gemm_h16_dropmask: bad args");
+  DEER_CHECK_ARG(lda > 0 && ldb > 0 && ldc >= N && (transA ? lda >= M : true) && (transB ? ldb >= K : true),
+                 "gemm_h16_dropmask: leading dimension too small");
+  DEER_CHECK_ARG((a_bf16 != 0) == (b_bf16 != 0), "gemm_h16_dropmask: A and B must both be FP16 or both be BF16");
+  DEER_CHECK_ARG((reinterpret_cast<uintptr_t>(keep_mask) & 3) == 0, "gemm_h16_dropmask: mask alignment");
+  g_engine_calls[DEER_ENGINE_H16]++;
+  t_drop_mask = reinterpret_cast<const uint32_t*>(keep_mask);
+  t_drop_scale = scale;
+  const int rc = gemm_h16(A, lda, transA, a_bf16, B, ldb, transB, b_bf16, C, ldc, nullptr, 0, 0, M, N, K, nullptr, DEER_ACT_NONE,
+                          0.f, (cudaStream_t)stream);
+  t_drop_mask = nullptr;
+  t_drop_scale = 1.f;
+  return rc;
 }
 
 int deer_gemm_h16_split(const void* A_hi, const void* A_lo, long long lda, int transA, const void* B_hi, const void* B_lo,

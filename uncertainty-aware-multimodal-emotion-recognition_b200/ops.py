@@ -993,6 +993,12 @@ def to_time_major(x):
     return _PermuteBT.apply(x)
 
 
+def set_lstm_dropout_mask(on: bool):
+    """nn.LSTM's inter-layer dropout in backward: keep bits written by the forward pass and applied by the epilogue of
+    the dx GEMM (default), or a Philox pass over dx (ablation / reference point of the equality test)."""
+    _state["lstm_drop_mask"] = bool(on)
+
+
 def set_lstm_batch_major_input(on: bool):
     """First LSTM layer reads the batch_first input through one permute + 16-bit cast pass (default) or through a
     materialised fp32 time-major copy (ablation / reference point of the equality test)."""
@@ -1139,6 +1145,7 @@ class _BiLSTMLayerCluster(torch.autograd.Function):
         ctx.drop = drop
         ctx.drop_step = _dropout_state["step"]
         ctx.xdrop_b16 = None
+        ctx.drop_mask = None
         # the 16-bit shadow outputs are non-differentiable: without this autograd hands backward a zero-filled tensor
         # for each of them (a 79 MB BF16 fill per layer and step)
         ctx.set_materialize_grads(False)
@@ -1157,9 +1164,17 @@ class _BiLSTMLayerCluster(torch.autograd.Function):
                 # training: the same pass also writes the BF16 copy the weight-gradient GEMM of backward reads (79 MB
                 # more to store here, instead of a second Philox pass over x in backward: 47 us -> ~10 us)
                 xdrop_b16 = torch.empty((M, In), device=dev, dtype=torch.bfloat16) if keep else None
+                # ... and the keep bits (1 bit per element): the epilogue of backward's dx GEMM applies them, instead of a
+                # Philox read-modify-write pass over dx (56 us at B = 256)
+                kmask = None
+                if (keep and ctx.needs_input_grad[0] and _state.get("lstm_drop_mask", True) and M > 128 and In % 32 == 0
+                        and (M * In) % 128 == 0):
+                    kmask = torch.empty(M * In // 32, device=dev, dtype=torch.int32)
                 call("deer_dropout_cast16", ptr(x), x16.data_ptr(), None if xdrop_b16 is None else xdrop_b16.data_ptr(),
-                     M * In, float(drop[0]), drop[1], drop[2], ptr(ctx.drop_step))
+                     M * In, float(drop[0]), drop[1], drop[2], ptr(ctx.drop_step),
+                     None if kmask is None else kmask.data_ptr())
                 ctx.xdrop_b16 = xdrop_b16
+                ctx.drop_mask = kmask
             elif (x16_in is not None and x16_in.dtype == torch.float16 and x16_in.numel() == M * In and In % 8 == 0
                   and x16_in.is_contiguous()):
                 x16 = x16_in.view(M, In)                      # the producer kernel's FP16 shadow: no cast pass
@@ -1244,10 +1259,17 @@ class _BiLSTMLayerCluster(torch.autograd.Function):
                      None, wb16.data_ptr(), None, H, In, Kp, 1)
                 dx = torch.empty((T, B, In), device=dev, dtype=torch.float32)
                 # dx = dpre16 [M, 2G] . wb16 [2G, In]: the sum over the two directions is the K = 2G contraction itself
-                gemm_h16(dpre16, 2 * G, 0, wb16, Kp, 0, dx, In, M, In, 2 * G, a_bf16=True, b_bf16=True, beta=0.0)
-                if drop is not None:                           # d/dx of the input dropout, in place
-                    call("deer_dropout", ptr(dx), ptr(dx), dx.numel(), float(drop[0]), drop[1], drop[2],
-                         ptr(ctx.drop_step))
+                kmask = ctx.drop_mask
+                ctx.drop_mask = None
+                if drop is not None and kmask is not None:
+                    # d/dx of the input dropout inside the GEMM's epilogue (keep bits written by the forward pass)
+                    call("deer_gemm_h16_dropmask", dpre16.data_ptr(), 2 * G, 0, 1, wb16.data_ptr(), Kp, 0, 1, ptr(dx), In,
+                         M, In, 2 * G, kmask.data_ptr(), 1.0 / (1.0 - float(drop[0])))
+                else:
+                    gemm_h16(dpre16, 2 * G, 0, wb16, Kp, 0, dx, In, M, In, 2 * G, a_bf16=True, b_bf16=True, beta=0.0)
+                    if drop is not None:                       # d/dx of the input dropout, in place
+                        call("deer_dropout", ptr(dx), ptr(dx), dx.numel(), float(drop[0]), drop[1], drop[2],
+                             ptr(ctx.drop_step))
         elif ctx.needs_input_grad[0]:
             dx = torch.empty((T, B, In), device=dev, dtype=torch.float32)
             for d in range(2):
