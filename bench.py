@@ -158,6 +158,7 @@ def main():
     ap.add_argument("--lstm-tile", type=int, default=None, help="DEER_OPT_LSTM_TILE override (ablation)")
     ap.add_argument("--lstm-halfsplit", type=int, default=None, help="DEER_OPT_LSTM_HALFSPLIT override (ablation)")
     ap.add_argument("--lstm-stasync", type=int, default=None, help="DEER_OPT_LSTM_STASYNC override (ablation)")
+    ap.add_argument("--lstm-xin", type=int, default=None, help="DEER_OPT_LSTM_XIN override (ablation): 0 = layer-0 input projection as a GEMM")
     ap.add_argument("--chain", action="store_true",
                     help="ablation: fusion + head as the persistent chain kernel (one launch per direction; measured slower)")
     ap.add_argument("--train-only", action="store_true", help="ablation runs: only the training-step line (no e2e / inference / roofline)")
@@ -202,6 +203,8 @@ def main():
         _lib.set_option(13, args.lstm_halfsplit)
     if args.lstm_stasync is not None:
         _lib.set_option(12, args.lstm_stasync)
+    if args.lstm_xin is not None:
+        _lib.set_option(15, args.lstm_xin)
     if args.chain:
         from deer_b200 import chain as _chain
         _chain.set_enabled(True)

@@ -7,7 +7,7 @@ import deer_b200  # noqa: F401
 from deer_b200 import ops
 from deer_b200.encoders import EnhancedTextEncoder, EnhancedVideoEncoder
 
-from helpers import assert_close
+from helpers import assert_close, cosine
 
 pytestmark = pytest.mark.gpu
 
@@ -181,3 +181,49 @@ def test_dropout_keep_mask_bits_match_the_dropped_tensor():
     bits = ((mask.view(-1, 1) >> torch.arange(32, device="cuda", dtype=torch.int32)) & 1).reshape(-1).bool()
     assert torch.equal(bits, y16 != 0)
     assert 0.5 < float(bits.float().mean()) < 0.7
+
+
+@pytest.mark.parametrize("B,T,train", [(6, 37, True), (32, 20, True), (256, 12, True), (300, 9, False), (320, 7, False),
+                                       (40, 1, True)])
+def test_lstm_input_projection_inside_the_recurrence_matches_the_gemm_path(B, T, train):
+    """First nn.LSTM layer (encoders.py:82-89,380; In = 84): W_ih x_t issued inside the forward recurrence kernel
+    (deer_lstm_cluster_fwd_xin: one-wave batches of 16-column tiles, whole-tile and ragged; larger batches keep the GEMM) == the projection GEMM + FP16 pre-activations path up to that path's own FP16
+    rounding of the pre-activations, and both agree with torch's fp64 nn.LSTM."""
+    from deer_b200 import _lib
+    from deer_b200.encoders import EnhancedAudioEncoder
+    torch.manual_seed(B + T)
+    enc = EnhancedAudioEncoder({"dropout": 0.0}).cuda()
+    enc.train(train)
+    x = torch.randn(B, T, 84, device="cuda")
+    pr = torch.randn(T, B, 512, device="cuda")
+    # (batches beyond one wave of 16-column tiles keep the projection GEMM: both runs then take the same path)
+    assert _lib.load().deer_lstm_cluster_xin_mode(B, int(train), 88) == (1 if B <= 256 else 0)
+    res = []
+    for fused in (True, False):
+        ops.set_lstm_input_projection_fused(fused)
+        try:
+            for p in enc.parameters():
+                p.grad = None
+            if train:
+                h = enc.lstm_forward(x)
+                (h * pr).sum().backward()
+                res.append((h.detach(), [p.grad.clone() for p in enc.lstm.parameters()]))
+            else:
+                with torch.no_grad():
+                    res.append((enc.lstm_forward(x), []))
+        finally:
+            ops.set_lstm_input_projection_fused(True)
+    assert_close(res[0][0], res[1][0], 1e-3, "h")
+    for a, b, (n, _) in zip(res[0][1], res[1][1], enc.lstm.named_parameters()):
+        # (two BF16-operand backward passes over pre-activations that differ by one FP16 rounding: the north-star gate)
+        if float(b.abs().max()) == 0.0:      # T = 1: no recurrent step, dW_hh is exactly zero
+            assert float(a.abs().max()) == 0.0, n
+            continue
+        assert_close(a, b, 1e-2, n)
+        assert cosine(a, b) >= 0.9999, n
+    ref = torch.nn.LSTM(84, 256, 2, batch_first=True, bidirectional=True).double()
+    ref.load_state_dict({k: v.double().cpu() for k, v in enc.lstm.state_dict().items()})
+    hr, _ = ref(x.double().cpu())
+    e_fused = float((res[0][0].double().cpu().permute(1, 0, 2) - hr).norm() / hr.norm())
+    e_gemm = float((res[1][0].double().cpu().permute(1, 0, 2) - hr).norm() / hr.norm())
+    assert e_fused < 1e-3 and e_fused < 1.5 * e_gemm + 1e-5, (e_fused, e_gemm)

@@ -206,13 +206,15 @@ def test_column_split_forward_matches_eight_warp_kernel(B, T, In, grad):
     ws = make_layer(In, H, B + T + 11)
     x = torch.randn(B, T, In, generator=torch.Generator().manual_seed(B + 5))
     _lib.set_option(3, 16)
+    _lib.set_option(15, 0)       # both runs through the projection GEMM (the in-kernel projection has no column-split form)
     res = []
     try:
         for cs in (1, 0):
             _lib.set_option(10, cs)
             res.append(run(x, ws, ops.ENGINE_AUTO, grad))
     finally:
-        _lib.set_option(10, 1)
+        _lib.set_option(10, 0)   # the library default
+        _lib.set_option(15, 1)
         _lib.set_option(3, 0)
     (h1, g1), (h0, g0) = res
     assert torch.equal(h1, h0) or float((h1 - h0).abs().max()) < 1e-6

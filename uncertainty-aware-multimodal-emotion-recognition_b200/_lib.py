@@ -80,6 +80,8 @@ _PROTOS = {
     "deer_lstm_unprep": [P, P, P, P, P, P, P, P, P, P, P, I, I, P],
     "deer_lstm_cluster_fwd_pre16": [P, P, P, P, P, P, P, P, I, I, I, P],
     "deer_lstm_cluster_bwd": [P, P, P, P, P, P, P, P, I, I, I, P],
+    "deer_lstm_cluster_xin_mode": [I, I, I],
+    "deer_lstm_cluster_fwd_xin": [P, I, P, P, P, P, P, P, P, P, P, I, I, I, P],
     "deer_gate_rows_interleave": [P, P, I, I, I, I, P],
     "deer_nig_head_fwd": [P, P, P, P, P, P, P, P, L, P],
     "deer_nig_head_bwd": [P, P, P, P, P, P, P, P, P, L, P],

@@ -35,6 +35,7 @@ extern int g_lstm_dual;
 extern int g_lstm_keep16;
 extern int g_lstm_stasync;
 extern int g_lstm_carveout;
+extern int g_lstm_xin;
 extern int g_lstm_halfsplit;
 extern int g_lstm_colsplit;
 extern int g_tf32_pair;
@@ -112,6 +113,9 @@ int deer_set_option(int option, int value) {
       return DEER_OK;
     case DEER_OPT_LSTM_CARVEOUT:
       g_lstm_carveout = value ? 1 : 0;
+      return DEER_OK;
+    case DEER_OPT_LSTM_XIN:
+      g_lstm_xin = value ? 1 : 0;
       return DEER_OK;
     case DEER_OPT_LSTM_STASYNC:
       g_lstm_stasync = value ? 1 : 0;

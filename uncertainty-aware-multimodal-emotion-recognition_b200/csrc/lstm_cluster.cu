@@ -215,6 +215,12 @@ struct LstmClusterParams {
   long long* prof;     // optional clock64 trace of block 0 (tools/lstm_probe.py --prof), else null
   int keep16;          // 1: the kept gates / cell states are FP16 (same blocked order, half the bytes), 0: fp32
   int stasync;         // forward h all-gather: 1 = per-lane st.async stores into the peers' B operand, 0 = bulk copies
+  // XIN kernels (input projection inside the recurrence, first layer): x as time-major FP16 rows [T*B, xk] (xk % 8 == 0,
+  // xk <= 128), both directions' gate-interleaved FP16 W_ih [2*4H, xk] and the gate-interleaved bias b_ih + b_hh [2*4H]
+  const __half* x16;
+  const __half* wih16;
+  const float* bias_il;
+  int xk;
 };
 constexpr int Q_PROF_S0 = 64, Q_PROF_STEPS = 4, Q_PROF_SLOTS = 8;
 // (only in the FAST = false instantiation -- the probe's: the clock read and its guards were 3 % of all instructions the
@@ -246,11 +252,17 @@ constexpr int Q_PROF_S0 = 64, Q_PROF_STEPS = 4, Q_PROF_SLOTS = 8;
 // the other half's gates are computed, on all 128 SMs of a B = 256 batch.  Same kept layouts as the 8-warp kernel.
 // FAST: the batch is a whole number of tiles and no clock trace is requested -- the per-column bounds checks (a branch
 // around every global load / store of the inner loop) and the trace guards are compiled out.
-template <int N, bool TS, int G, int CS = 1, bool FAST = false>
+// XIN: the layer's INPUT PROJECTION runs inside the recurrence (first layer, In <= 128): the CTA keeps its 256 rows of the
+// gate-interleaved FP16 W_ih in TMEM beside W_hh (128 more columns), the MMA warp fetches the step's [N x In] FP16 tile of x one step ahead and
+// issues W_ih x_t into the (double-buffered) accumulators BEFORE h_{t-1} arrives -- off the step's critical path, on a
+// tensor pipe that is 90 % idle -- and the gate epilogue adds the bias.  The FP16 pre-activation tensor [T,B,2,4H] (315 MB
+// written by a GEMM and read back here at B = 256; 1.26 GB each way at B = 1024) never exists.
+template <int N, bool TS, int G, int CS = 1, bool FAST = false, bool XIN = false>
 __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__((G == 2 && CS == 2 ? 512 : G * CS * 256) + 32, 1)
     lstm_fwd_cluster_kernel(const LstmClusterParams p) {
   DEER_PDL_ENTRY();
   static_assert(CS == 1 || (CS == 2 && N == 16), "column split: one 16-column tile, two warp sets");
+  static_assert(!XIN || (TS && CS == 1 && N == 16 && G == 1), "XIN: one 16-column tile per CTA, TMEM-resident W_hh");
   constexpr bool HS = (G == 2 && CS == 2);
   using L = QLayout<N>;
   constexpr int NW = N / CS;             // batch columns per compute warp
@@ -274,6 +286,11 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__((G == 2 && CS == 2 
   uint64_t* h_full_all = bars;            // [G][2]
   uint64_t* mma_done_all = bars + 2 * G;  // [G]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * G);
+  // XIN: per group two [16 k-chunks][N rows][16 B] x tiles (the B-operand layout of the h tiles)
+  constexpr int XIN_OFF = (((TS ? 0 : QW_BYTES) + G * 2 * L::HB_BYTES + ACT_TOTAL + SH_TOTAL + 3 * G * 8 + 16) + 1023) & ~1023;
+  constexpr int XT_BYTES = 16 * N * 16;
+  uint8_t* xbuf_all = smem + XIN_OFF;
+  constexpr uint32_t ACC_BUF = XIN ? (uint32_t)(G * 2 * N) : 0u;   // XIN: accumulators double-buffered by step parity
 
   const int warp_id = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int grp = (G == 2 && warp_id >= 8 && warp_id < 16) ? 1 : 0;   // batch sub-tile of this compute warp
@@ -310,11 +327,21 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__((G == 2 && CS == 2 
   // left over let a 128-column GEMM CTA of a concurrent stream share the SM instead of spinning in tcgen05.alloc
   if (warp_id == MMAW) {
     if constexpr (TS) {
-      tmem_alloc_more_follow(tmem_slot, 64);
-      tmem_alloc(tmem_slot + 1, 256);
+      tmem_alloc_more_follow(tmem_slot, (XIN && G == 2) ? 128 : 64);
+      if constexpr (XIN) {
+        tmem_alloc_more_follow(tmem_slot + 1, 256);
+        tmem_alloc(tmem_slot + 2, 128);     // W_ih: 2 accumulators x 64 columns (K padded to 128 fp16)
+      } else {
+        tmem_alloc(tmem_slot + 1, 256);
+      }
     } else {
       tmem_alloc(tmem_slot, 64);
     }
+  }
+  if constexpr (XIN) {
+    for (int idx = threadIdx.x; idx < G * 2 * XT_BYTES / 16; idx += NTHREADS)   // chunks beyond xk stay zero for good
+      reinterpret_cast<uint4*>(xbuf_all)[idx] = make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async_smem();
   }
   if constexpr (!TS) {
     // W_hh rows of this CTA -> fp16, K-major SWIZZLE_128B: [acc a][k-block 4][128 rows x 128 B]; row m = 4*unit + gate
@@ -334,6 +361,28 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__((G == 2 && CS == 2 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_w = TS ? tmem_slot[1] : 0u;   // resident A operand (TS mode)
+  const uint32_t tmem_wih = XIN ? tmem_slot[2] : 0u;
+  if constexpr (XIN) {
+    if (warp_id < 8) {
+      // this CTA's 256 gate-interleaved rows of W_ih (rows dir*4H + 256 r + a*128 + m) -> TMEM, lane = row m of
+      // accumulator a, 64 columns = 128 fp16 (zero beyond xk)
+      const int a = warp >> 2, sub = warp & 3, m = sub * 32 + lane;
+      const int nchw = p.xk >> 3;
+      const uint4* src = reinterpret_cast<const uint4*>(p.wih16 + ((size_t)dir * (4 * QH) + (size_t)r * 256 + a * 128 + m) * p.xk);
+#pragma unroll 1
+      for (int ch = 0; ch < 2; ch++) {
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          const int kc = ch * 8 + i;
+          const uint4 x = kc < nchw ? __ldg(src + kc) : make_uint4(0u, 0u, 0u, 0u);
+          reinterpret_cast<uint4*>(v)[i] = x;
+        }
+        tmem_st32(tmem_wih + ((uint32_t)(sub * 32) << 16) + (uint32_t)(a * 64 + ch * 32), v);
+      }
+      tmem_st_wait();
+    }
+  }
   if constexpr (TS) {
     if (warp_id < 8) {
       // resident A operand in TMEM: lane = row m of accumulator a, 128 columns = 256 fp16 (2 per column, low half first)
@@ -365,14 +414,72 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__((G == 2 && CS == 2 
       constexpr uint32_t idesc = make_idesc_f16(0, 128, N);
       const uint32_t tb = warp_uniform(tmem_base);
       const uint32_t tw = warp_uniform(tmem_w);
+      const uint32_t twi = warp_uniform(tmem_wih);
       const bool leader = elect_one();
-      for (int s = 0; s < T; s++) {
+      // XIN: fetch the [N x xk] FP16 tile of x for step s of sub-tile g into its B-operand tile and issue W_ih x_s into
+      // the accumulator buffer of that step's parity (this warp wrote the tile itself: generic -> async proxy fence only)
+      const int nch = XIN ? (p.xk >> 3) : 0;
+      const int nkx = XIN ? ((p.xk + 15) >> 4) : 0;
+      auto x_load = [&](const int s, const int g, uint4 (&v)[N / 2]) {
+        if constexpr (XIN) {
+          // <= 16 chunks per row x N rows / 32 lanes = N/2 per lane, all in flight at once; issued BEFORE this warp waits
+          // for h, so the round trip to L2 / DRAM costs the recurrence nothing
+          const int t = dir ? T - 1 - s : s;
+          const int bg0 = (ctile * G + g) * N;
+#pragma unroll
+          for (int i = 0; i < N / 2; i++) {
+            const int idx = lane + 32 * i;
+            const int n = idx % N, kc = idx / N;
+            v[i] = make_uint4(0u, 0u, 0u, 0u);
+            if (kc < nch && (FAST || bg0 + n < B))
+              v[i] = __ldg(reinterpret_cast<const uint4*>(p.x16 + ((size_t)t * B + bg0 + n) * p.xk) + kc);
+          }
+        }
+      };
+      auto x_issue = [&](const int s, const int g, const uint4 (&v)[N / 2]) {
+        if constexpr (XIN) {
+          uint8_t* xb = xbuf_all + (2 * g + (s & 1)) * XT_BYTES;
+#pragma unroll
+          for (int i = 0; i < N / 2; i++) {
+            const int idx = lane + 32 * i;
+            const int n = idx % N, kc = idx / N;
+            if (kc < nch) *reinterpret_cast<uint4*>(xb + kc * (N * 16) + n * 16) = v[i];
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (leader) {
+            const uint32_t tgx = tb + (uint32_t)(s & 1) * ACC_BUF + (uint32_t)(g * 2 * N);
+#pragma unroll
+            for (int a = 0; a < 2; a++) {
+#pragma unroll 1
+              for (int k = 0; k < nkx; k++) {
+                const uint64_t bd = make_smem_desc(smem_u32(xb) + (2 * k) * (N * 16), N * 16, 128, 0);
+                umma_f16_ts(tgx + a * N, twi + a * 64 + k * 8, bd, idesc, k > 0 ? 1u : 0u);
+              }
+            }
+          }
+          __syncwarp();
+        }
+      };
+      // (XIN: iteration s = -1 only issues the input part of step 0 -- ONE call site of the input part keeps the kernel's
+      //  register count where it was)
+      for (int s = XIN ? -1 : 0; s < T; s++) {
 #pragma unroll
         for (int g = 0; g < G; g++) {   // the batch sub-tiles take turns on the tensor core
           uint64_t* hf = h_full_all + 2 * g;
           uint64_t* md = mma_done_all + g;
-          if (s == 0) {
-            if (leader) mbar_arrive(md);  // h_{-1} = 0: the gates of step 0 are the input projection alone
+          uint4 xv[N / 2];
+          if (XIN && s + 1 < T) x_load(s + 1, g, xv);
+          if (s <= 0) {
+            if constexpr (XIN) {
+              if (s == 0) {
+                if (leader) umma_commit(md);   // the gates of step 0 are the input projection alone: W_ih x_0, in flight
+                __syncwarp();
+              }
+              if (s + 1 < T) x_issue(s + 1, g, xv);
+            } else {
+              if (leader) mbar_arrive(md);  // h_{-1} = 0: the gates of step 0 are the input projection alone
+            }
             continue;
           }
           if (p.stasync) {
@@ -387,7 +494,7 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__((G == 2 && CS == 2 
           if (leader && s + 2 < T) mbar_expect_tx(&hf[(s - 1) & 1], XBYTES);  // re-arm for h_{s+1}
           tc_fence_after();
           const uint32_t hb = smem_u32(hbuf_all) + (2 * g + ((s - 1) & 1)) * L::HB_BYTES;
-          const uint32_t tg = tb + (uint32_t)(g * 2 * N);
+          const uint32_t tg = tb + (uint32_t)(s & 1) * ACC_BUF + (uint32_t)(g * 2 * N);
           if (leader) {
 #pragma unroll
             for (int a = 0; a < 2; a++) {
@@ -396,7 +503,8 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__((G == 2 && CS == 2 
                 // B operand, K-major no-swizzle: [32 k-chunks][N rows][16 B]; 8x16B core matrices, SBO 128 B, LBO N*16 B
                 const uint64_t bd = make_smem_desc(hb + (2 * k) * (N * 16), N * 16, 128, 0);
                 if constexpr (TS) {
-                  umma_f16_ts(tg + a * N, tw + a * 128 + k * 8, bd, idesc, k > 0 ? 1u : 0u);
+                  // (XIN: W_ih x_s is already in the accumulator)
+                  umma_f16_ts(tg + a * N, tw + a * 128 + k * 8, bd, idesc, (XIN || k > 0) ? 1u : 0u);
                 } else {
                   const uint64_t ad =
                       make_smem_desc(smem_u32(wsm) + a * 65536 + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024, 2);
@@ -408,6 +516,9 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__((G == 2 && CS == 2 
             if (g == 0) Q_PROF(1);
           }
           __syncwarp();
+          // the next step's input part: its accumulator buffer was read out before h_{s-1} left, its x tile was consumed
+          // by MMAs that completed before this step's; all of it is off the critical path
+          if (XIN && s + 1 < T) x_issue(s + 1, g, xv);
         }
       }
     }
@@ -419,6 +530,8 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__((G == 2 && CS == 2 
     const int ug = (int)r * QU + ul;              // unit inside the direction
     const uint32_t tacc = tmem_base + ((uint32_t)(sub * 32) << 16) +
                           (uint32_t)(grp * 2 * N + a * N + (HS ? 0 : chalf * NW));
+    // XIN: bias of this thread's gate row (the projection GEMM's epilogue added it before)
+    const float xbias = XIN ? __ldg(p.bias_il + dir * (4 * QH) + (int)r * 256 + a * 128 + sub * 32 + lane) : 0.f;
     float* sa = stage_act_all + wslot * (32 * ROWF);
     __half* sh_base = stage_h_all + wslot * (2 * NW * 8);
     const int bw0 = b0 + chalf * NW;              // first batch column of this warp
@@ -451,7 +564,7 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__((G == 2 && CS == 2 
     // blocked save area of this warp: ((((t*2+dir)*ntiles+tile)*4+r)*8+warp) blocks of 4*NQ*32 (gates) / NQ*32 (c)
     const long long blk_w = ((long long)dir * ntiles_all + tile) * 32 + (int)r * 8 + warp;
     const long long blk_t = 2LL * ntiles_all * 32;
-    load_pre(0);
+    if constexpr (!XIN) load_pre(0);
     for (int s = 0; s < T; s++) {
       const int t = dir ? T - 1 - s : s;
       __half* sh = sh_base + (s & 1) * (NW * 8);
@@ -459,14 +572,18 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__((G == 2 && CS == 2 
       if (warp_id == 0 && lane == 0) Q_PROF(2);
       tc_fence_after();
       float x[NW];
-      if (s > 0) {
-        tmem_ld_row<NW>(tacc, x);
+      if (XIN || s > 0) {
+        tmem_ld_row<NW>(tacc + (uint32_t)(s & 1) * ACC_BUF, x);
         tmem_ld_wait();
       } else {
 #pragma unroll
         for (int n = 0; n < NW; n++) x[n] = 0.f;
       }
       tc_fence_before();
+      if constexpr (XIN) {
+#pragma unroll
+        for (int n = 0; n < NW; n++) x[n] += xbias;
+      } else
       if (pre_is16) {
 #pragma unroll
         for (int n = 0; n < NW; n++) x[n] += __half2float(__ushort_as_half((unsigned short)pre[n]));
@@ -487,7 +604,7 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__((G == 2 && CS == 2 
 #pragma unroll
       for (int n = 0; n < NW; n += 4)
         *reinterpret_cast<float4*>(sa + lane * ROWF + n) = make_float4(x[n], x[n + 1], x[n + 2], x[n + 3]);
-      if (s + 1 < T) load_pre(s + 1);  // a full step ahead of its use: DRAM latency never lands on the critical path
+      if (!XIN && s + 1 < T) load_pre(s + 1);  // a full step ahead of its use: DRAM latency never lands on the critical path
       __syncwarp();
       if (warp_id == 0 && lane == 0) Q_PROF(3);
       float gi[NQ], gf[NQ], gg[NQ], go[NQ];
@@ -645,8 +762,9 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__((G == 2 && CS == 2 
   cluster_sync_all();  // no CTA retires while a peer may still address its shared memory
   if (warp == 8) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 64);
+    tmem_dealloc(tmem_base, (XIN && G == 2) ? 128 : 64);
     if constexpr (TS) tmem_dealloc(tmem_w, 256);
+    if constexpr (XIN) tmem_dealloc(tmem_wih, 128);
   }
 }
 
@@ -1011,10 +1129,15 @@ __global__ void __cluster_dims__(QC, 1, 1) __maxnreg__(160)
   }
 }
 
-template <int N, bool TS, int G = 1, int CS = 1>
+template <int N, bool TS, int G = 1, int CS = 1, bool XIN = false>
 constexpr int fwd_smem_bytes() {
   using L = QLayout<N>;
   constexpr int NW = N / CS, NCW = (G == 2 && CS == 2) ? 16 : 8 * G * CS;
+  if constexpr (XIN) {   // (same expression as XIN_OFF in the kernel) + W_ih + the x tiles + alignment slack
+    constexpr int off = (((TS ? 0 : QW_BYTES) + G * 2 * L::HB_BYTES + NCW * 32 * (NW + 4) * 4 + NCW * 2 * NW * 16 + 3 * G * 8 + 16) + 1023) & ~1023;
+    constexpr int needx = off + G * 2 * (16 * N * 16) + 1024;
+    return needx > 120 * 1024 ? needx : 120 * 1024;
+  }
   // >= 120 KB even in TS mode: one LSTM CTA per SM (two would not fit their 2 x 320 TMEM columns and the second would
   // spin in tcgen05.alloc); a TF32 GEMM CTA (100 KB, 128 columns) of another stream still fits beside it
   constexpr int need = (TS ? 0 : QW_BYTES) + G * 2 * L::HB_BYTES + NCW * 32 * (NW + 4) * 4 + NCW * 2 * NW * 16 + 64 + 1024;
@@ -1064,32 +1187,32 @@ static int pick_tile(int B) {
   return (2 * ((B + 15) / 16) <= 32) ? 16 : 32;
 }
 
-template <int N, bool TS, int G, int CS, bool FAST>
+template <int N, bool TS, int G, int CS, bool FAST, bool XIN = false>
 static int launch_fwd_f(const tc::LstmClusterParams& p, cudaStream_t stream) {
-  constexpr int smem = tc::fwd_smem_bytes<N, TS, G, CS>();
+  constexpr int smem = tc::fwd_smem_bytes<N, TS, G, CS, XIN>();
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(tc::lstm_fwd_cluster_kernel<N, TS, G, CS, FAST>,
+    cudaError_t e = cudaFuncSetAttribute(tc::lstm_fwd_cluster_kernel<N, TS, G, CS, FAST, XIN>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return cuda_status(e, "lstm_fwd_cluster smem attribute");
     // The L1 / shared-memory split of an SM is fixed while CTAs are resident, and the driver picks the smallest carve-out
     // that fits the kernel: ask for the maximum, so that a <= 100 KB GEMM CTA of the other stream can join the recurrence
     // CTA (what decides whether it does is the register file, see lstm_bwd_cluster_kernel).
     if (g_lstm_carveout)
-      cudaFuncSetAttribute(tc::lstm_fwd_cluster_kernel<N, TS, G, CS, FAST>, cudaFuncAttributePreferredSharedMemoryCarveout,
+      cudaFuncSetAttribute(tc::lstm_fwd_cluster_kernel<N, TS, G, CS, FAST, XIN>, cudaFuncAttributePreferredSharedMemoryCarveout,
                            cudaSharedmemCarveoutMaxShared);
     attr = true;
   }
-  DEER_LAUNCH((tc::lstm_fwd_cluster_kernel<N, TS, G, CS, FAST>), tc::QC * p.ntiles * 2,
+  DEER_LAUNCH((tc::lstm_fwd_cluster_kernel<N, TS, G, CS, FAST, XIN>), tc::QC * p.ntiles * 2,
               ((G == 2 && CS == 2) ? 512 : G * CS * 256) + 32, smem, stream, p);
   return DEER_OK;
 }
-template <int N, bool TS, int G = 1, int CS = 1>
+template <int N, bool TS, int G = 1, int CS = 1, bool XIN = false>
 static int launch_fwd(const tc::LstmClusterParams& p, cudaStream_t stream) {
   // whole tiles (of the columns ONE CTA covers) and no clock trace: the check-free instantiation
   constexpr int cols = (G == 2 && CS == 2) ? N : G * N;
-  if (p.B % cols == 0 && p.prof == nullptr) return launch_fwd_f<N, TS, G, CS, true>(p, stream);
-  return launch_fwd_f<N, TS, G, CS, false>(p, stream);
+  if (p.B % cols == 0 && p.prof == nullptr) return launch_fwd_f<N, TS, G, CS, true, XIN>(p, stream);
+  return launch_fwd_f<N, TS, G, CS, false, XIN>(p, stream);
 }
 template <int N, bool TS, bool K16, bool FAST>
 static int launch_bwd_f(const tc::LstmClusterParams& p, cudaStream_t stream) {
@@ -1136,6 +1259,35 @@ int lstm_fwd_cluster(const float* pre_il, const void* pre_f16, const float* w_fw
   // kept gate / cell layouts are those of the 32-column backward kernel, so training keeps the monolithic tile.
   if ((!keep || dual_keep) && g_lstm_ts && g_lstm_dual) return launch_fwd<16, true, 2>(p, stream);
   return g_lstm_ts ? launch_fwd<32, true>(p, stream) : launch_fwd<32, false>(p, stream);
+}
+
+// which XIN kernel (input projection inside the recurrence) serves a batch: 1 = 16-column tiles (one wave, B <= 256),
+// 0 = none (the projection stays a GEMM).  Measured (tools/xin_probe.py, layer-0 forward incl. operand preparation):
+// B = 256 training 552 -> 458 us, B = 256 inference 552 -> 410 us; the dual-sub-tile inference kernel of larger batches
+// LOSES (B = 1024: 1342 -> 1637 us: its single MMA warp already serves two recurrences and the input part lands on their
+// critical path), so it keeps the GEMM.
+int g_lstm_xin = 1;            // DEER_OPT_LSTM_XIN
+int lstm_cluster_xin_mode(int B, int keep, int xk) {
+  if (!g_lstm_xin || !g_lstm_ts || g_lstm_halfsplit || (g_lstm_colsplit && !g_lstm_keep16) || xk <= 0 || xk > 128 || (xk & 7))
+    return 0;
+  if (pick_tile(B) != 16) return 0;
+  return (g_lstm_dual == 2 && keep) ? 0 : 1;
+}
+int lstm_fwd_cluster_xin(const void* x16, int xk, const void* wih16, const float* bias_il, const float* w_fwd,
+                         const float* w_rev, float* h_out, float* gact, float* c_blk, void* h16, void* hb16, int T, int B,
+                         cudaStream_t stream) {
+  const int keep = (gact != nullptr && c_blk != nullptr) ? 1 : 0;
+  const int mode = lstm_cluster_xin_mode(B, keep, xk);
+  if (mode == 0) {
+    set_error("lstm_cluster_fwd_xin: no in-kernel projection variant for B=%d keep=%d xk=%d", B, keep, xk);
+    return DEER_ERR_UNSUPPORTED;
+  }
+  const int N = pick_tile(B);
+  tc::LstmClusterParams p{nullptr, w_fwd, w_rev, h_out, gact, c_blk, nullptr, nullptr,
+                          reinterpret_cast<__half*>(h16), reinterpret_cast<__nv_bfloat16*>(hb16), nullptr,
+                          nullptr, T, B, (B + N - 1) / N, keep, g_lstm_prof, g_lstm_keep16, g_lstm_stasync,
+                          reinterpret_cast<const __half*>(x16), reinterpret_cast<const __half*>(wih16), bias_il, xk};
+  return launch_fwd<16, true, 1, 1, true>(p, stream);
 }
 
 int lstm_bwd_cluster(const float* gact, const float* c_blk, const float* dh_out, const float* w_fwd, const float* w_rev,
@@ -1190,6 +1342,26 @@ int deer_lstm_cluster_fwd_pre16(const void* pre_il_f16, const float* w_hh_fwd, c
                  "lstm_cluster_fwd_pre16: 16-bit buffers must be 16-byte aligned");
   return lstm_fwd_cluster(nullptr, pre_il_f16, w_hh_fwd, w_hh_rev, h_out, reinterpret_cast<float*>(gact),
                           reinterpret_cast<float*>(c_blk), h_f16, h_bf16, T, B, (cudaStream_t)stream);
+}
+
+int deer_lstm_cluster_xin_mode(int B, int keep, int xk) { return B > 0 ? lstm_cluster_xin_mode(B, keep, xk) : DEER_ERR_INVALID; }
+
+int deer_lstm_cluster_fwd_xin(const void* x_f16, int xk, const void* w_ih_il_f16, const float* bias_il, const float* w_hh_fwd,
+                              const float* w_hh_rev, float* h_out, void* gact, void* c_blk, void* h_f16, void* h_bf16, int T,
+                              int B, int H, void* stream) {
+  DEER_CHECK_ARG(x_f16 && w_ih_il_f16 && bias_il && w_hh_fwd && w_hh_rev && h_out && T > 0 && B > 0,
+                 "lstm_cluster_fwd_xin: bad args");
+  DEER_CHECK_ARG((gact == nullptr) == (c_blk == nullptr), "lstm_cluster_fwd_xin: gact and c_blk go together");
+  if (!lstm_cluster_supported(h_out, w_hh_fwd, w_hh_rev, H)) {
+    set_error("lstm_cluster_fwd_xin: needs H == 256 and 16-byte aligned pointers");
+    return DEER_ERR_UNSUPPORTED;
+  }
+  DEER_CHECK_ARG(((reinterpret_cast<uintptr_t>(h_f16) | reinterpret_cast<uintptr_t>(h_bf16) | reinterpret_cast<uintptr_t>(x_f16) |
+                   reinterpret_cast<uintptr_t>(w_ih_il_f16) | reinterpret_cast<uintptr_t>(gact) |
+                   reinterpret_cast<uintptr_t>(c_blk)) & 15) == 0,
+                 "lstm_cluster_fwd_xin: buffers must be 16-byte aligned");
+  return lstm_fwd_cluster_xin(x_f16, xk, w_ih_il_f16, bias_il, w_hh_fwd, w_hh_rev, h_out, reinterpret_cast<float*>(gact),
+                              reinterpret_cast<float*>(c_blk), h_f16, h_bf16, T, B, (cudaStream_t)stream);
 }
 
 int deer_lstm_cluster_bwd(const void* gact, const void* c_blk, const float* dh_out, const float* w_hh_fwd,

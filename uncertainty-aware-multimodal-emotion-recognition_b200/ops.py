@@ -993,6 +993,12 @@ def to_time_major(x):
     return _PermuteBT.apply(x)
 
 
+def set_lstm_input_projection_fused(on: bool):
+    """First LSTM layer's input projection inside the forward recurrence kernel (default) or as a 16-bit GEMM that writes
+    FP16 pre-activations (ablation / reference point of the equality test)."""
+    _state["lstm_xin"] = bool(on)
+
+
 def set_lstm_dropout_mask(on: bool):
     """nn.LSTM's inter-layer dropout in backward: keep bits written by the forward pass and applied by the epilogue of
     the dx GEMM (default), or a Philox pass over dx (ablation / reference point of the equality test)."""
@@ -1138,7 +1144,11 @@ class _BiLSTMLayerCluster(torch.autograd.Function):
         # FP16 pre-activations (16-bit GEMM epilogue -> LSTM kernel): the projection is bound by its output stream, and
         # the rounding (2^-12 relative, once) is of the order of what the FP16 operands already contribute
         pre16 = use16 and _state["lstm_pre16"] and M > 128
-        pre = torch.empty((T, B, 2, G), device=dev, dtype=torch.float16 if pre16 else torch.float32)
+        # first layer (In <= 128): the input projection runs INSIDE the recurrence kernel (deer_lstm_cluster_fwd_xin) -- no
+        # projection GEMM, no pre-activation tensor
+        xin = bool(use16 and pre16 and drop is None and _state.get("lstm_xin", True) and
+                   _lib.load().deer_lstm_cluster_xin_mode(B, int(keep), (In + 7) // 8 * 8) > 0)
+        pre = None if xin else torch.empty((T, B, 2, G), device=dev, dtype=torch.float16 if pre16 else torch.float32)
         x16 = None
         if drop is not None and not (use16 and In % 8 == 0):
             raise _lib.DeerError("deer_b200: fused input dropout needs the 16-bit GEMM path and In % 8 == 0")
@@ -1182,7 +1192,9 @@ class _BiLSTMLayerCluster(torch.autograd.Function):
                 x16 = cast16(x)                               # [M, Kp] fp16
             assert x16.shape[1] == Kp
             # both directions in ONE contraction: pre[M, 2G] = x16 [M, Kp] . w16[2G, Kp]^T (full 8 KB output rows)
-            if pre16:
+            if xin:
+                pass
+            elif pre16:
                 gemm_h16(x16, Kp, 0, w16, Kp, 1, None, 0, M, 2 * G, In, bias=b_il.view(-1), C16=pre, ldc16=2 * G)
             else:
                 gemm_h16(x16, Kp, 0, w16, Kp, 1, pre, 2 * G, M, 2 * G, In, bias=b_il.view(-1))
@@ -1200,12 +1212,19 @@ class _BiLSTMLayerCluster(torch.autograd.Function):
             gact = torch.empty(T * 2 * Bp * G, device=dev, dtype=kdt)
             c_blk = torch.empty(T * 2 * Bp * H, device=dev, dtype=kdt)
             hb16 = torch.empty((T, B, 2 * H), device=dev, dtype=torch.bfloat16) if use16 else None
-            call(fwd_fn, pre.data_ptr(), ptr(whf_c), ptr(whr_c), ptr(h), ptr(gact), ptr(c_blk), h16p,
-                 None if hb16 is None else hb16.data_ptr(), T, B, H)
+            if xin:
+                call("deer_lstm_cluster_fwd_xin", x16.data_ptr(), Kp, w16.data_ptr(), ptr(b_il), ptr(whf_c), ptr(whr_c), ptr(h),
+                     ptr(gact), ptr(c_blk), h16p, None if hb16 is None else hb16.data_ptr(), T, B, H)
+            else:
+                call(fwd_fn, pre.data_ptr(), ptr(whf_c), ptr(whr_c), ptr(h), ptr(gact), ptr(c_blk), h16p,
+                     None if hb16 is None else hb16.data_ptr(), T, B, H)
             ctx.save_for_backward(x, wi_il, whf_c, whr_c, gact, c_blk, h)
             # the fp32 pre buffer doubles as the fp32 dpre buffer; on the 16-bit path BPTT only writes the BF16 dpre
             ctx.pre = None if use16 else pre
             ctx.hb16 = hb16
+        elif xin:
+            call("deer_lstm_cluster_fwd_xin", x16.data_ptr(), Kp, w16.data_ptr(), ptr(b_il), ptr(whf_c), ptr(whr_c), ptr(h),
+                 None, None, h16p, None, T, B, H)
         else:
             call(fwd_fn, pre.data_ptr(), ptr(whf_c), ptr(whr_c), ptr(h), None, None, h16p, None, T, B, H)
         ctx.dims = (T, B, In, H)
