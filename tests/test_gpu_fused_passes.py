@@ -187,7 +187,8 @@ def test_dropout_keep_mask_bits_match_the_dropped_tensor():
                                        (40, 1, True)])
 def test_lstm_input_projection_inside_the_recurrence_matches_the_gemm_path(B, T, train):
     """First nn.LSTM layer (encoders.py:82-89,380; In = 84): W_ih x_t issued inside the forward recurrence kernel
-    (deer_lstm_cluster_fwd_xin: one-wave batches of 16-column tiles, whole-tile and ragged; larger batches keep the GEMM) == the projection GEMM + FP16 pre-activations path up to that path's own FP16
+    (deer_lstm_cluster_fwd_xin: 16-column tiles for one-wave batches, dual sub-tiles with one MMA warp each for the no-keep
+    forward of larger ones; whole-tile and ragged batches) == the projection GEMM + FP16 pre-activations path up to that path's own FP16
     rounding of the pre-activations, and both agree with torch's fp64 nn.LSTM."""
     from deer_b200 import _lib
     from deer_b200.encoders import EnhancedAudioEncoder
@@ -196,8 +197,7 @@ def test_lstm_input_projection_inside_the_recurrence_matches_the_gemm_path(B, T,
     enc.train(train)
     x = torch.randn(B, T, 84, device="cuda")
     pr = torch.randn(T, B, 512, device="cuda")
-    # (batches beyond one wave of 16-column tiles keep the projection GEMM: both runs then take the same path)
-    assert _lib.load().deer_lstm_cluster_xin_mode(B, int(train), 88) == (1 if B <= 256 else 0)
+    assert _lib.load().deer_lstm_cluster_xin_mode(B, int(train), 88) == (1 if B <= 256 else 2)
     res = []
     for fused in (True, False):
         ops.set_lstm_input_projection_fused(fused)

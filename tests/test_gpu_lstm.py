@@ -182,14 +182,20 @@ def test_dual_subtile_forward_matches_monolithic_tile(B, T, In):
     x = torch.randn(B, T, In, generator=torch.Generator().manual_seed(B + 1))
     _lib.set_option(3, 32)          # force 32 columns per CTA also for small batches
     try:
+        _lib.set_option(15, 0)      # same input path for both: the projection GEMM (the monolithic tile has no other)
         _lib.set_option(9, 1)
         h_dual, _ = run(x, ws, ops.ENGINE_AUTO, False)
         _lib.set_option(9, 0)
         h_mono, _ = run(x, ws, ops.ENGINE_AUTO, False)
+        _lib.set_option(15, 1)      # ... and the dual kernel with the input projection inside (In <= 128): FP16-rounding apart
+        _lib.set_option(9, 1)
+        h_dual_xin, _ = run(x, ws, ops.ENGINE_AUTO, False)
     finally:
+        _lib.set_option(15, 1)
         _lib.set_option(9, 1)
         _lib.set_option(3, 0)
     assert torch.equal(h_dual, h_mono) or float((h_dual - h_mono).abs().max()) < 1e-6
+    assert_close(h_dual_xin, h_mono, 1e-3, "dual kernel with in-kernel projection")
     if B <= 130:
         ops.set_gemm_engine(ops.ENGINE_SIMT)
         h_ref, _ = run(x, ws, ops.ENGINE_SIMT, False)

@@ -36,6 +36,7 @@ extern int g_lstm_keep16;
 extern int g_lstm_stasync;
 extern int g_lstm_carveout;
 extern int g_lstm_xin;
+extern int g_lstm_xin_dual;
 extern int g_lstm_halfsplit;
 extern int g_lstm_colsplit;
 extern int g_tf32_pair;
@@ -116,6 +117,7 @@ int deer_set_option(int option, int value) {
       return DEER_OK;
     case DEER_OPT_LSTM_XIN:
       g_lstm_xin = value ? 1 : 0;
+      g_lstm_xin_dual = (value == 3) ? 0 : 1;
       return DEER_OK;
     case DEER_OPT_LSTM_STASYNC:
       g_lstm_stasync = value ? 1 : 0;

@@ -257,12 +257,17 @@ constexpr int Q_PROF_S0 = 64, Q_PROF_STEPS = 4, Q_PROF_SLOTS = 8;
 // issues W_ih x_t into the (double-buffered) accumulators BEFORE h_{t-1} arrives -- off the step's critical path, on a
 // tensor pipe that is 90 % idle -- and the gate epilogue adds the bias.  The FP16 pre-activation tensor [T,B,2,4H] (315 MB
 // written by a GEMM and read back here at B = 256; 1.26 GB each way at B = 1024) never exists.
+// With two sub-tiles (G = 2) the XIN kernel runs TWO MMA warps, one per sub-tile: with a single issuer the input part of one
+// sub-tile sits in front of the other's recurrent MMAs (measured, layer-0 forward at B = 1024: 1637 us with one issuer,
+// 1204 us with two, 1338 us on the GEMM path).  Without XIN a second issuer LOSES (the no-keep forward of one layer at
+// B = 1024: 0.99 -> 1.49 ms), so that kernel keeps one.
 template <int N, bool TS, int G, int CS = 1, bool FAST = false, bool XIN = false>
-__global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__((G == 2 && CS == 2 ? 512 : G * CS * 256) + 32, 1)
+__global__ void __cluster_dims__(QC, 1, 1)
+    __launch_bounds__((G == 2 && CS == 2 ? 512 : G * CS * 256) + ((XIN && G == 2) ? 64 : 32), 1)
     lstm_fwd_cluster_kernel(const LstmClusterParams p) {
   DEER_PDL_ENTRY();
   static_assert(CS == 1 || (CS == 2 && N == 16), "column split: one 16-column tile, two warp sets");
-  static_assert(!XIN || (TS && CS == 1 && N == 16 && G == 1), "XIN: one 16-column tile per CTA, TMEM-resident W_hh");
+  static_assert(!XIN || (TS && CS == 1 && N == 16), "XIN: 16-column tiles, TMEM-resident W_hh");
   constexpr bool HS = (G == 2 && CS == 2);
   using L = QLayout<N>;
   constexpr int NW = N / CS;             // batch columns per compute warp
@@ -270,8 +275,9 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__((G == 2 && CS == 2 
   constexpr int ROWF = NW + 4;           // padded fp32 row of the per-warp transpose tile
   constexpr int NCW = HS ? 16 : 8 * G * CS;   // compute warps
   constexpr uint32_t XBYTES = HS ? L::HB_BYTES / 2 : L::HB_BYTES;   // bytes of h landing in one B-operand tile per step
-  constexpr int MMAW = NCW;              // index of the MMA-issuing warp
-  constexpr int NTHREADS = NCW * 32 + 32;
+  constexpr int MMAW = NCW;              // index of the (first) MMA-issuing warp
+  constexpr int NMW = (XIN && G == 2) ? 2 : 1;   // MMA warps
+  constexpr int NTHREADS = NCW * 32 + 32 * NMW;
   constexpr int ACT_TOTAL = NCW * 32 * ROWF * 4;   // per-warp activation transpose tiles
   constexpr int SH_TOTAL = NCW * 2 * NW * 16;      // double-buffered per-warp fp16 h blocks [NW cols][8 units]
   extern __shared__ uint8_t smem_raw[];
@@ -295,7 +301,7 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__((G == 2 && CS == 2 
   const int warp_id = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int grp = (G == 2 && warp_id >= 8 && warp_id < 16) ? 1 : 0;   // batch sub-tile of this compute warp
   const int chalf = (CS == 2 && warp_id >= 8 && warp_id < 16) ? 1 : 0;  // column half of this compute warp
-  const int warp = warp_id == MMAW ? 8 : (warp_id & 7);              // role index: 0..7 compute, 8 = MMA issuer
+  const int warp = warp_id >= MMAW ? 8 : (warp_id & 7);              // role index: 0..7 compute, 8 = MMA issuer
   const int wslot = warp_id < NCW ? warp_id : 0;                     // private staging slot of a compute warp
   uint8_t* hbuf = hbuf_all + grp * 2 * L::HB_BYTES;
   uint64_t* h_full = h_full_all + 2 * grp;
@@ -465,7 +471,8 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__((G == 2 && CS == 2 
       //  register count where it was)
       for (int s = XIN ? -1 : 0; s < T; s++) {
 #pragma unroll
-        for (int g = 0; g < G; g++) {   // the batch sub-tiles take turns on the tensor core
+        for (int g = 0; g < G; g++) {   // the batch sub-tiles take turns on the tensor core (NMW = 2: one warp each)
+          if (NMW == 2 && g != warp_id - MMAW) continue;
           uint64_t* hf = h_full_all + 2 * g;
           uint64_t* md = mma_done_all + g;
           uint4 xv[N / 2];
@@ -760,7 +767,7 @@ __global__ void __cluster_dims__(QC, 1, 1) __launch_bounds__((G == 2 && CS == 2 
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();  // no CTA retires while a peer may still address its shared memory
-  if (warp == 8) {
+  if (warp_id == MMAW) {
     tc_fence_after();
     tmem_dealloc(tmem_base, (XIN && G == 2) ? 128 : 64);
     if constexpr (TS) tmem_dealloc(tmem_w, 256);
@@ -1204,7 +1211,7 @@ static int launch_fwd_f(const tc::LstmClusterParams& p, cudaStream_t stream) {
     attr = true;
   }
   DEER_LAUNCH((tc::lstm_fwd_cluster_kernel<N, TS, G, CS, FAST, XIN>), tc::QC * p.ntiles * 2,
-              ((G == 2 && CS == 2) ? 512 : G * CS * 256) + 32, smem, stream, p);
+              ((G == 2 && CS == 2) ? 512 : G * CS * 256) + ((XIN && G == 2) ? 64 : 32), smem, stream, p);
   return DEER_OK;
 }
 template <int N, bool TS, int G = 1, int CS = 1, bool XIN = false>
@@ -1267,10 +1274,11 @@ int lstm_fwd_cluster(const float* pre_il, const void* pre_f16, const float* w_fw
 // LOSES (B = 1024: 1342 -> 1637 us: its single MMA warp already serves two recurrences and the input part lands on their
 // critical path), so it keeps the GEMM.
 int g_lstm_xin = 1;            // DEER_OPT_LSTM_XIN
+int g_lstm_xin_dual = 1;       // (DEER_OPT_LSTM_XIN = 3: in-kernel projection for 16-column tiles only)
 int lstm_cluster_xin_mode(int B, int keep, int xk) {
   if (!g_lstm_xin || !g_lstm_ts || g_lstm_halfsplit || (g_lstm_colsplit && !g_lstm_keep16) || xk <= 0 || xk > 128 || (xk & 7))
     return 0;
-  if (pick_tile(B) != 16) return 0;
+  if (pick_tile(B) != 16) return (!keep && g_lstm_dual && g_lstm_xin_dual) ? 2 : 0;
   return (g_lstm_dual == 2 && keep) ? 0 : 1;
 }
 int lstm_fwd_cluster_xin(const void* x16, int xk, const void* wih16, const float* bias_il, const float* w_fwd,
@@ -1287,7 +1295,8 @@ int lstm_fwd_cluster_xin(const void* x16, int xk, const void* wih16, const float
                           reinterpret_cast<__half*>(h16), reinterpret_cast<__nv_bfloat16*>(hb16), nullptr,
                           nullptr, T, B, (B + N - 1) / N, keep, g_lstm_prof, g_lstm_keep16, g_lstm_stasync,
                           reinterpret_cast<const __half*>(x16), reinterpret_cast<const __half*>(wih16), bias_il, xk};
-  return launch_fwd<16, true, 1, 1, true>(p, stream);
+  if (mode == 1) return launch_fwd<16, true, 1, 1, true>(p, stream);
+  return launch_fwd<16, true, 2, 1, true>(p, stream);
 }
 
 int lstm_bwd_cluster(const float* gact, const float* c_blk, const float* dh_out, const float* w_fwd, const float* w_rev,
