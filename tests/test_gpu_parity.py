@@ -625,9 +625,11 @@ def test_stream_concurrency_switches_do_not_change_results():
     from gen_common import seq_inputs
 
     res = []
-    for branch, defer in ((True, True), (False, False), (True, False), (False, True)):
+    for branch, defer, text in ((True, True, True), (False, False, False), (True, False, True), (False, True, True),
+                                (True, True, False)):
         ops.set_branch_streams(branch)
         ops.set_defer_wgrad(defer)
+        ops.set_text_stream(text)        # the text encoder on a third stream beside the video encoder
         try:
             torch.manual_seed(3)
             model = deer_b200.SequenceDEERModel(dropout=0.0).to(DEV).train()
@@ -643,6 +645,7 @@ def test_stream_concurrency_switches_do_not_change_results():
         finally:
             ops.set_branch_streams(True)
             ops.set_defer_wgrad(True)
+            ops.set_text_stream(True)
     assert float(res[0][0].norm()) > 0
     for g, l in res[1:]:      # not bit-wise: several gradients are accumulated with floating-point atomics
         assert_close(g, res[0][0], 1e-5, "flat gradients")

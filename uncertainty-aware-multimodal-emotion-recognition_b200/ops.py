@@ -157,6 +157,16 @@ def branch_max_batch() -> int:
     return _state["branch_max_batch"]
 
 
+def set_text_stream(on: bool):
+    """Text encoder on a third stream beside the video encoder (when the encoders are forked at all); off: video and
+    text share the calling stream (the round-1 schedule)."""
+    _state["text_stream"] = bool(on)
+
+
+def text_stream_enabled() -> bool:
+    return _state.get("text_stream", True)
+
+
 def set_branch_max_batch(n: int):
     """Largest batch for which the sequence model forks its encoders onto two streams (default 512)."""
     _state["branch_max_batch"] = int(n)

@@ -59,9 +59,22 @@ class SequenceDEERModel(nn.Module):
             ops.mark("step_start")
             with torch.cuda.stream(side):
                 a = ops.mark_tensor(self.audio_encoder(ops.mark_tensor(audio, "audio_in")), "audio_out")
+            tside = self._branch_stream("text", 0) if ops.text_stream_enabled() else None
+            if tside is not None:
+                # the text encoder (one scorer GEMM, small kernels) on a third stream: with the first LSTM layer's input
+                # projection inside the recurrence kernel the audio branch ends first, and video + text in sequence had
+                # become the longest chain of the forward (and of the backward, where autograd replays the same streams)
+                tside.wait_stream(main)
+                with torch.cuda.stream(tside):
+                    t = ops.mark_tensor(self.text_encoder(ops.mark_tensor(text, "text_in"), attention_mask,
+                                                          linguistic_features), "text_out")
             v = ops.mark_tensor(self.video_encoder(ops.mark_tensor(video, "video_in")), "video_out")
-            t = ops.mark_tensor(self.text_encoder(ops.mark_tensor(text, "text_in"), attention_mask,
-                                                  linguistic_features), "text_out")
+            if tside is None:
+                t = ops.mark_tensor(self.text_encoder(ops.mark_tensor(text, "text_in"), attention_mask,
+                                                      linguistic_features), "text_out")
+            else:
+                main.wait_stream(tside)
+                t.record_stream(main)
             main.wait_stream(side)
             a.record_stream(main)
             ops.mark("joined")
@@ -86,12 +99,12 @@ class SequenceDEERModel(nn.Module):
         out["attention_weights"] = fus["trimodal_attention_weights"]
         return out
 
-    def _branch_stream(self):
+    def _branch_stream(self, name: str = "audio", priority: int = -1):
         dev = torch.cuda.current_device()
         st = self.__dict__.setdefault("_side_streams", {})
-        if dev not in st:
-            st[dev] = torch.cuda.Stream(device=dev, priority=-1)
-        return st[dev]
+        if (dev, name) not in st:
+            st[(dev, name)] = torch.cuda.Stream(device=dev, priority=priority)
+        return st[(dev, name)]
 
     def compute_loss(self, predictions: Dict[str, torch.Tensor], targets: torch.Tensor) -> Dict[str, torch.Tensor]:
         return self.loss_fn(predictions, targets)
