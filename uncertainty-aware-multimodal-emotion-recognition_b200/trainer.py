@@ -209,8 +209,18 @@ class DEERDataParallelTrainer:
         """fwd + fused head/loss + bwd; gradients are accumulated into the flat buffer.  Returns losses [5D+2].
         `loss_weight`: the per-batch dataset weight of training.py:211-212 (`weighted_loss = total_loss * w`): it scales
         the back-propagated gradient; the returned loss components stay unweighted (as the reference logs them)."""
-        # one launch clears the flat gradient buffer and the gradient-norm accumulator
-        call("deer_fill_zero", ptr(self.flat.grads), self.flat.numel, ptr(self.sumsq), 1)
+        # one launch clears the flat gradient buffer and the gradient-norm accumulator -- on the weight-gradient stream,
+        # beside the forward: nothing reads or accumulates into them before the backward starts (joined in front of it)
+        cur = torch.cuda.current_stream()
+        zs = ops._wgrad_stream() if self.flat.grads.is_cuda else None
+        if zs is not None:
+            zs.wait_stream(cur)
+            with torch.cuda.stream(zs):
+                call("deer_fill_zero", ptr(self.flat.grads), self.flat.numel, ptr(self.sumsq), 1)
+            self._zero_stream = zs
+        else:
+            call("deer_fill_zero", ptr(self.flat.grads), self.flat.numel, ptr(self.sumsq), 1)
+            self._zero_stream = None
         ops.set_direct_grad_accumulation(self.direct_grad)
         # this trainer's device step counter keys the dropout masks of ITS step only (restored afterwards)
         prev = ops.set_dropout_step_tensor(self.step_tensor)
@@ -267,6 +277,9 @@ class DEERDataParallelTrainer:
                 tail_lo = self._layer0_end
             else:
                 tail_lo = self._audio_end
+        if getattr(self, "_zero_stream", None) is not None:
+            torch.cuda.current_stream().wait_stream(self._zero_stream)   # the cleared gradient buffer
+            self._zero_stream = None
         ev.backward(dE)
         for h_ in handles:
             h_.remove()
