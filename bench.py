@@ -147,6 +147,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-pooled", action="store_true")
     ap.add_argument("--no-text-stream", action="store_true", help="ablation: text encoder on the video encoder's stream")
+    ap.add_argument("--lstm-defer-wgrad", action="store_true", help="ablation: LSTM layer-1 weight gradients on the weight-gradient stream instead of in front of layer 0's BPTT (measured: no gain)")
     ap.add_argument("--no-branch-streams", action="store_true",
                     help="ablation: video/text encoders on the main stream behind the audio encoder")
     ap.add_argument("--overlap-exchange", action="store_true",
@@ -194,6 +195,7 @@ def main():
     pk = peaks()
     ops.set_branch_streams(not args.no_branch_streams)
     ops.set_text_stream(not args.no_text_stream)
+    ops.set_lstm_defer_wgrad(args.lstm_defer_wgrad)
     ops.set_defer_wgrad(not args.no_defer_wgrad)
     if args.branch_max_batch is not None:
         ops.set_branch_max_batch(args.branch_max_batch)

@@ -1009,6 +1009,12 @@ def set_lstm_input_projection_fused(on: bool):
     _state["lstm_xin"] = bool(on)
 
 
+def set_lstm_defer_wgrad(on: bool):
+    """Weight-gradient GEMMs of an LSTM layer that has another LSTM layer below it on the weight-gradient stream
+    (trainer mode only; measured: no gain, 3.755 vs 3.747 ms) or in front of the lower layer's BPTT (default)."""
+    _state["lstm_defer_wgrad"] = bool(on)
+
+
 def set_lstm_dropout_mask(on: bool):
     """nn.LSTM's inter-layer dropout in backward: keep bits written by the forward pass and applied by the epilogue of
     the dx GEMM (default), or a Philox pass over dx (ablation / reference point of the equality test)."""
@@ -1307,19 +1313,38 @@ class _BiLSTMLayerCluster(torch.autograd.Function):
         P = ctx.params
         out = []
         if use16:
-            # dW_ih of both directions at once: [2G, In] = dpre16 [M, 2G]^T . xb16 [M, In]
-            gemm_h16(dpre16, 2 * G, 1, xb16, Kp, 0, dwi_il2, In, 2 * G, In, M, a_bf16=True, b_bf16=True, beta=1.0)
-        if use16:
-            Mr = (T - 1) * B
-            if T > 1:
-                # rows t=1.. of the forward direction pair with h[t-1]; rows ..T-2 of the reverse one with h[t+1]
-                gemm_h16(dpre16.data_ptr() + 2 * B * 2 * G, 2 * G, 1, hb16.data_ptr(), 2 * H, 0, dwh_il2[0], H, G, H, Mr,
-                         a_bf16=True, b_bf16=True, beta=1.0)
-                gemm_h16(dpre16.data_ptr() + 2 * G, 2 * G, 1, hb16.data_ptr() + 2 * (B * 2 * H + H), 2 * H, 0,
-                         dwh_il2[1], H, G, H, Mr, a_bf16=True, b_bf16=True, beta=1.0)
             tg = [_acc(P[i]) for i in (0, 4, 1, 5, 2, 3, 6, 7)]   # dW_ih f/r, dW_hh f/r, db_ih f, db_hh f, db_ih r, db_hh r
-            # one pass: every gate-interleaved gradient of the layer accumulated into its nn.LSTM-order target
-            call("deer_lstm_unprep", ptr(dwi_il2), ptr(dwh_il2), ptr(db_il), *[ptr(t[0]) for t in tg], H, In)
+
+            def weight_grads():
+                # dW_ih of both directions at once: [2G, In] = dpre16 [M, 2G]^T . xb16 [M, In]
+                gemm_h16(dpre16, 2 * G, 1, xb16, Kp, 0, dwi_il2, In, 2 * G, In, M, a_bf16=True, b_bf16=True, beta=1.0)
+                Mr = (T - 1) * B
+                if T > 1:
+                    # rows t=1.. of the forward direction pair with h[t-1]; rows ..T-2 of the reverse one with h[t+1]
+                    gemm_h16(dpre16.data_ptr() + 2 * B * 2 * G, 2 * G, 1, hb16.data_ptr(), 2 * H, 0, dwh_il2[0], H, G, H,
+                             Mr, a_bf16=True, b_bf16=True, beta=1.0)
+                    gemm_h16(dpre16.data_ptr() + 2 * G, 2 * G, 1, hb16.data_ptr() + 2 * (B * 2 * H + H), 2 * H, 0,
+                             dwh_il2[1], H, G, H, Mr, a_bf16=True, b_bf16=True, beta=1.0)
+                # one pass: every gate-interleaved gradient of the layer accumulated into its nn.LSTM-order target
+                call("deer_lstm_unprep", ptr(dwi_il2), ptr(dwh_il2), ptr(db_il), *[ptr(t[0]) for t in tg], H, In)
+
+            if (dx is not None and _state["defer_wgrad"] and _state["direct_grad"] and _state.get("lstm_defer_wgrad", False)
+                    and all(direct for _, direct in tg)):
+                # (option, OFF: measured 3.755 vs 3.747 ms per step) trainer mode, a layer with an LSTM layer below it: its
+                # three weight-gradient GEMMs (233 us at B = 256) leave the path from dx to the BPTT of the layer below and
+                # run on the weight-gradient stream -- but CTA-pair GEMMs cannot share an SM with the recurrence, so they
+                # only move behind that BPTT, where they meet the lower layer's own weight gradients
+                cur = torch.cuda.current_stream()
+                aux = _wgrad_stream()
+                aux.wait_stream(cur)
+                with torch.cuda.stream(aux):
+                    weight_grads()
+                for t_ in (dpre16, xb16, hb16, zbuf, db_il):
+                    if t_ is not None:
+                        t_.record_stream(aux)
+                _wgrad["pending"] = True
+            else:
+                weight_grads()
             r = [None if direct else buf for buf, direct in tg]
             return dx, r[0], r[2], r[4], r[5], r[1], r[3], r[6], r[7], None, None, None, None, None
         for d in range(2):
