@@ -147,6 +147,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-pooled", action="store_true")
     ap.add_argument("--no-text-stream", action="store_true", help="ablation: text encoder on the video encoder's stream")
+    ap.add_argument("--no-pool-rowterm", action="store_true", help="ablation: pooling input gradient written by the pooling kernel, the scorer GEMM accumulates onto it")
     ap.add_argument("--lstm-defer-wgrad", action="store_true", help="ablation: LSTM layer-1 weight gradients on the weight-gradient stream instead of in front of layer 0's BPTT (measured: no gain)")
     ap.add_argument("--no-branch-streams", action="store_true",
                     help="ablation: video/text encoders on the main stream behind the audio encoder")
@@ -195,6 +196,7 @@ def main():
     pk = peaks()
     ops.set_branch_streams(not args.no_branch_streams)
     ops.set_text_stream(not args.no_text_stream)
+    ops.set_pool_rowterm(not args.no_pool_rowterm)
     ops.set_lstm_defer_wgrad(args.lstm_defer_wgrad)
     ops.set_defer_wgrad(not args.no_defer_wgrad)
     if args.branch_max_batch is not None:

@@ -315,6 +315,15 @@ int deer_adamw(float* p, const float* g, float* m, float* v, long long n, float 
                float eps, float weight_decay, int step, const float* sumsq, float max_norm, float grad_scale,
                const long long* step_dev, const float* lr_dev, void* stream);
 
+/* ---- C = opA(A) opB(B) + w (x) v per sample: the TF32 CTA-pair GEMM (M > 256, N >= 128, N % 4 == 0, K >= 64; beta = 0) with a
+ * rank-1-per-sample row term in its epilogue: row m of C is sample b, step t of an [nb, nt] (batch-major) or [nt, nb]
+ * (time_major) grid and receives w[b, t] * v[b, :] (w [nb, nt], v [nb, N]).  Replaces the pair "attention pooling writes its
+ * input gradient, the scorer's input-gradient GEMM accumulates onto it" (encoders.py:93-98,383-384 in backward): dx is written
+ * once instead of written, read and written. */
+int deer_gemm_rowterm(const float* A, long long lda, int transA, const float* B, long long ldb, int transB, float* C,
+                      long long ldc, int M, int N, int K, const float* w, const float* v, int nb, int nt, int time_major,
+                      void* stream);
+
 /* ---- C = dropout'(A B): the 16-bit GEMM (CTA-pair kernel: M > 128, N % 32 == 0, fp32 C, beta = 0) whose epilogue applies
  * the keep mask of an inverted dropout over C (deer_dropout_cast16's keep_mask, row pitch N/32 words) and its 1/(1-p)
  * scale: nn.LSTM's inter-layer dropout in backward (encoders.py:82-89) -- dx of layer l+1 is masked while it is written,

@@ -227,3 +227,44 @@ def test_lstm_input_projection_inside_the_recurrence_matches_the_gemm_path(B, T,
     e_fused = float((res[0][0].double().cpu().permute(1, 0, 2) - hr).norm() / hr.norm())
     e_gemm = float((res[1][0].double().cpu().permute(1, 0, 2) - hr).norm() / hr.norm())
     assert e_fused < 1e-3 and e_fused < 1.5 * e_gemm + 1e-5, (e_fused, e_gemm)
+
+
+@pytest.mark.parametrize("B,T,time_major", [(64, 150, True), (200, 50, False), (33, 300, True)])
+def test_pooling_input_gradient_inside_the_scorer_gemm_epilogue(B, T, time_major):
+    """Backward of scorer + attention pooling (encoders.py:93-98,383-384): dx = w[b,t] dout[b,:] + dh W1 written ONCE by the
+    scorer's input-gradient GEMM (deer_gemm_rowterm) == the pooling kernel writing its part and the GEMM accumulating onto
+    it: same dx (fp32 addition order apart) and identical parameter gradients; time-major (audio) and batch-major (video)."""
+    D = 512
+    g = torch.Generator().manual_seed(B + T)
+    x = torch.randn((T, B, D) if time_major else (B, T, D), generator=g)
+    pr = torch.randn(B, D, generator=g)
+    enc = EnhancedVideoEncoder({"dropout": 0.0}).cuda().train()
+    att = enc.temporal_attention
+    res = []
+    for on in (True, False):
+        ops.set_pool_rowterm(on)
+        try:
+            for p in att.parameters():
+                p.grad = None
+            xc = cu(x).requires_grad_(True)
+            out, _ = ops.scorer_pool(xc, att[0].weight, att[0].bias, att[2].weight, att[2].bias, None, time_major,
+                                     precise=False)
+            (out * cu(pr)).sum().backward()
+            res.append((out.detach(), xc.grad.clone(), [p.grad.clone() for p in att.parameters()]))
+        finally:
+            ops.set_pool_rowterm(True)
+    assert torch.equal(res[0][0], res[1][0])
+    assert_close(res[0][1], res[1][1], 1e-6, "dx")
+    for a, b, (n, _) in zip(res[0][2], res[1][2], att.named_parameters()):
+        if n == "2.bias":
+            assert float(a.abs().max()) < 1e-4 and float(b.abs().max()) < 1e-4, n
+        else:
+            assert_close(a, b, 1e-5, n)
+    # fp64 statement of the same lines
+    xd = x.double().requires_grad_(True)
+    w1, b1, w2, b2 = (p.detach().double().cpu() for p in (att[0].weight, att[0].bias, att[2].weight, att[2].bias))
+    xb = xd.permute(1, 0, 2) if time_major else xd
+    s = torch.tanh(xb @ w1.T + b1) @ w2.T + b2
+    o = (torch.softmax(s, dim=1) * xb).sum(1)
+    (o * pr.double()).sum().backward()
+    assert_close(res[0][1], xd.grad, 2e-3, "dx vs fp64")

@@ -38,6 +38,7 @@ _PROTOS = {
     "deer_set_option": [I, I],
     "deer_lstm_set_profile_buffer": [P],
     "deer_gemm": [P, L, I, P, L, I, P, L, I, I, I, P, I, F, I, L, L, L, L, I, P],
+    "deer_gemm_rowterm": [P, L, I, P, L, I, P, L, I, I, I, P, P, I, I, I, P],
     "deer_gemm_x3": [ctypes.POINTER(GemmX3Args), P],
     "deer_chain_run": [P, P],
     "deer_chain_max_ops": None,
@@ -171,5 +172,15 @@ def call(name: str, *args):
     check(getattr(load(), name)(*args, stream()), name)
 
 
+_tf32_pair = [1]
+
+
+def tf32_pair_on() -> bool:
+    """DEER_OPT_TF32_PAIR as last set through set_option (default 1)."""
+    return bool(_tf32_pair[0])
+
+
 def set_option(option: int, value: int):
     check(load().deer_set_option(option, value), "deer_set_option")
+    if option == 6:
+        _tf32_pair[0] = int(value)

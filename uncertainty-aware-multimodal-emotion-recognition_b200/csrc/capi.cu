@@ -42,6 +42,9 @@ extern int g_lstm_colsplit;
 extern int g_tf32_pair;
 bool gemm_tf32_pair_supported(int transA, int transB, int M, int N, int K, long long ldc, const float* bias, int act,
                               float beta);
+int gemm_tf32_pair_rowterm(const float* A, long long lda, int transA, const float* B, long long ldb, int transB, float* C,
+                           long long ldc, int M, int N, int K, const float* w, const float* v, int nb, int nt, int time_major,
+                           cudaStream_t stream);
 int gemm_tf32_pair(const float* A, long long lda, int transA, const float* B, long long ldb, int transB, float* C,
                    long long ldc, int M, int N, int K, const float* bias, int act, float beta, cudaStream_t stream);
 void gemm_tcgen05_set_round(int on);
@@ -135,6 +138,16 @@ int deer_set_option(int option, int value) {
       set_error("set_option: unknown option %d", option);
       return DEER_ERR_INVALID;
   }
+}
+
+int deer_gemm_rowterm(const float* A, long long lda, int transA, const float* B, long long ldb, int transB, float* C,
+                      long long ldc, int M, int N, int K, const float* w, const float* v, int nb, int nt, int time_major,
+                      void* stream) {
+  DEER_CHECK_ARG(A && B && C && w && v && M > 0 && N > 0 && K > 0 && nb > 0 && nt > 0, "gemm_rowterm: bad args");
+  DEER_CHECK_ARG(lda >= (transA ? M : K) && ldb >= (transB ? K : N) && ldc >= N, "gemm_rowterm: leading dimension too small");
+  g_engine_calls[DEER_ENGINE_TF32_PAIR]++;
+  return gemm_tf32_pair_rowterm(A, lda, transA, B, ldb, transB, C, ldc, M, N, K, w, v, nb, nt, time_major,
+                                (cudaStream_t)stream);
 }
 
 int deer_gemm(const float* A, long long lda, int transA, const float* B, long long ldb, int transB, float* C,

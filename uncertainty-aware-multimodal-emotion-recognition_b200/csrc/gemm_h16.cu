@@ -53,6 +53,12 @@ struct Params {
                         // (A_hi,B_hi), (A_lo,B_hi), (A_hi,B_lo) over the hi / lo operand maps.  0: plain GEMM
   const uint32_t* drop_mask;   // optional (pair kernel, fp32 output, beta = 0, N % 32 == 0): keep bits of an inverted dropout
   float drop_scale;            // over C, one word per (row, 32 columns): C = keep ? C * drop_scale : 0 in the epilogue
+  // optional rank-1-per-sample row term (pair kernel, fp32 output, beta = 0, N % 4 == 0): C[m, :] += rt_w[b, t] * rt_v[b, :]
+  // with row m = (b, t) of a [rt_B, rt_T] (batch-major) or [rt_T, rt_B] (rt_tm: time-major) grid -- the attention pooling's
+  // own input gradient (weights x upstream gradient) added while the scorer's input-gradient GEMM writes dx
+  const float* rt_w;           // [rt_B, rt_T]
+  const float* rt_v;           // [rt_B, N]
+  int rt_B, rt_T, rt_tm;
 };
 #define H16_T0() const long long _t0 = p.prof ? clock64() : 0
 #define H16_ACC(slot)                                                   \
@@ -675,6 +681,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
             v[j] = o.x; v[j + 1] = o.y; v[j + 2] = o.z; v[j + 3] = o.w;
           }
         }
+        if (p.rt_w) {
+          const int row = row_base + lane;
+          if (row < p.M) {
+            const int b = p.rt_tm ? row % p.rt_B : row / p.rt_T;
+            const int t = p.rt_tm ? row / p.rt_B : row % p.rt_T;
+            const float w = __ldg(p.rt_w + (long long)b * p.rt_T + t);
+            const float* vrow = p.rt_v + (long long)b * p.N + gn0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (gn0 + j < p.N) {
+                const float4 u = __ldg(reinterpret_cast<const float4*>(vrow + j));
+                v[j] = fmaf(w, u.x, v[j]); v[j + 1] = fmaf(w, u.y, v[j + 1]);
+                v[j + 2] = fmaf(w, u.z, v[j + 2]); v[j + 3] = fmaf(w, u.w, v[j + 3]);
+              }
+            }
+          }
+        }
         if (p.drop_mask) {
           // the backward of an inverted dropout on this GEMM's output (nn.LSTM's inter-layer dropout applied to dx): this
           // lane holds 32 consecutive columns of one row = one word of the keep mask the forward pass wrote
@@ -907,10 +930,18 @@ int gemm_h16_ex(const void* A, const void* A_lo, long long lda, int transA, int 
   return DEER_OK;
 }
 
+int gemm_tf32_pair(const float* A, long long lda, int transA, const float* B, long long ldb, int transB, float* C,
+                   long long ldc, int M, int N, int K, const float* bias, int act, float beta, cudaStream_t stream);
+bool gemm_tf32_pair_supported(int transA, int transB, int M, int N, int K, long long ldc, const float* bias, int act,
+                              float beta);
 // ------------------------------------------------------------------------------------------------- TF32 on CTA pairs
 // Same kernel with fp32 operands read as TF32 (ELEM = 4): the 128x128-tile TF32 engine (gemm_tcgen05.cu) is bound by
 // shared-memory / L2 operand traffic; 256x256 pair tiles move a quarter of the operand bytes per FLOP and CTA.
 int g_tf32_pair = 1;   // deer_set_option(DEER_OPT_TF32_PAIR)
+// row term handed to the NEXT gemm_tf32_pair call of this thread (set and cleared by gemm_tf32_pair_rowterm)
+static thread_local const float* t_rt_w = nullptr;
+static thread_local const float* t_rt_v = nullptr;
+static thread_local int t_rt_B = 0, t_rt_T = 0, t_rt_tm = 0;
 bool gemm_tf32_pair_supported(int transA, int transB, int M, int N, int K, long long ldc, const float* bias, int act,
                               float beta) {
   (void)transA; (void)transB;
@@ -954,7 +985,13 @@ int gemm_tf32_pair(const float* A, long long lda, int transA, const float* B, lo
                          ((uint32_t)(transB ? 0 : 1) << 16) | ((uint32_t)(BN >> 3) << 17) |
                          ((uint32_t)((2 * BM) >> 4) << 24);
   Params p{C, ldc, nullptr, 0, 0, bias, M, N, K, act, beta, splits, per, tiles_m, tiles_n, idesc, nullptr,
-           getenv("DEER_H16_DEBUG") ? atoi(getenv("DEER_H16_DEBUG")) : 0, 0};
+           getenv("DEER_H16_DEBUG") ? atoi(getenv("DEER_H16_DEBUG")) : 0, 0, nullptr, 1.f, t_rt_w, t_rt_v, t_rt_B, t_rt_T,
+           t_rt_tm};
+  if (p.rt_w && (beta != 0.f || (N & 3) || ldc < N || p.debug || (long long)t_rt_B * t_rt_T != M ||
+                 (reinterpret_cast<uintptr_t>(p.rt_v) & 15))) {
+    set_error("gemm_tf32_pair: the row-term epilogue needs beta = 0, N %% 4 == 0, rows = B x T and a 16-byte aligned v");
+    return DEER_ERR_UNSUPPORTED;
+  }
   const int work = tiles_m * tiles_n * splits;
   const int clusters = work < kNumSMs / 2 ? work : kNumSMs / 2;
 #define DEER_TF32_PAIR_GO(AM, BMN)                                                                                  \
@@ -974,6 +1011,20 @@ int gemm_tf32_pair(const float* A, long long lda, int transA, const float* B, lo
   else DEER_TF32_PAIR_GO(true, true);
 #undef DEER_TF32_PAIR_GO
   return DEER_OK;
+}
+
+// C = A B^T-or-B + w (x) v per sample (see Params::rt_w): the TF32 CTA-pair GEMM with the row-term epilogue
+int gemm_tf32_pair_rowterm(const float* A, long long lda, int transA, const float* B, long long ldb, int transB, float* C,
+                           long long ldc, int M, int N, int K, const float* w, const float* v, int nb, int nt, int time_major,
+                           cudaStream_t stream) {
+  if (!gemm_tf32_pair_supported(transA, transB, M, N, K, ldc, nullptr, DEER_ACT_NONE, 0.f)) {
+    set_error("gemm_rowterm: shape outside the TF32 CTA-pair engine (M=%d N=%d K=%d)", M, N, K);
+    return DEER_ERR_UNSUPPORTED;
+  }
+  t_rt_w = w; t_rt_v = v; t_rt_B = nb; t_rt_T = nt; t_rt_tm = time_major;
+  const int rc = gemm_tf32_pair(A, lda, transA, B, ldb, transB, C, ldc, M, N, K, nullptr, DEER_ACT_NONE, 0.f, stream);
+  t_rt_w = t_rt_v = nullptr; t_rt_B = t_rt_T = t_rt_tm = 0;
+  return rc;
 }
 
 // fp32 -> FP16 hi / lo pair of a row-major matrix: hi = fp16(x), lo = fp16(x - hi) (22 significant bits together);

@@ -874,8 +874,16 @@ class _ScorerPool(torch.autograd.Function):
             dout = torch.zeros((B, D), device=dev, dtype=torch.float32)
         dx = torch.empty_like(x) if need_dx else None    # an input tensor (text embeddings): only ds is produced
         ds = torch.empty(M, device=dev, dtype=torch.float32)
-        call("deer_attn_pool_bwd", ptr(dout.contiguous()), ptr(x), xs_b, xs_t, ptr(sc), ss_b, ss_t, ptr(m), ptr(wts),
-             ptr(dx), ptr(ds), B, T, D, 0, int(ctx.premask))
+        doutc = dout.contiguous()
+        # the pooling's own input gradient w[b,t] dout[b,:] inside the epilogue of the scorer's input-gradient GEMM (TF32
+        # CTA-pair engine): the pooling kernel then writes no dx and the GEMM does not read it back (2 x 157 MB at the
+        # audio encoder, in front of the BPTT of the last LSTM layer)
+        time_major = xs_t != D
+        rowterm = bool(need_dx and _state.get("pool_rowterm", True) and _state["engine"] == ENGINE_AUTO and
+                       _bwd_engine(M) is None and not (_bwd16_ok(M) and Hd % 8 == 0 and D % 8 == 0) and
+                       _lib.tf32_pair_on() and M > 256 and D >= 128 and D % 4 == 0 and Hd >= 64 and Hd % 4 == 0)
+        call("deer_attn_pool_bwd", ptr(doutc), ptr(x), xs_b, xs_t, ptr(sc), ss_b, ss_t, ptr(m), ptr(wts),
+             None if rowterm else ptr(dx), ptr(ds), B, T, D, 0, int(ctx.premask))
         dw2, dw2_direct = _acc(pw2, like=w2v)
         db2, db2_direct = _acc(pb2)
         db1, db1_direct = _acc(pb1)
@@ -893,7 +901,10 @@ class _ScorerPool(torch.autograd.Function):
             xb = ctx.x_bf16 if ctx.x_bf16 is not None else cast16(x.view(M, D), bf16=True)
             gemm_h16(dhb, Hd, 1, xb, D, 0, dw1, D, Hd, D, M, a_bf16=True, b_bf16=True, beta=1.0)
         else:
-            if need_dx:
+            if rowterm:
+                call("deer_gemm_rowterm", ptr(dh), Hd, 0, ptr(w1), w1.stride(0), 0, ptr(dx), D, M, D, Hd, ptr(wts), ptr(doutc),
+                     B, T, int(time_major))
+            elif need_dx:
                 gemm(dh, Hd, 0, w1, w1.stride(0), 0, dx, D, M, D, Hd, beta=1.0, engine=_bwd_engine(M))
             if dw1_direct and _state["defer_wgrad"] and _state["direct_grad"]:
                 # trainer mode: dW1 is not needed before the optimizer -- it leaves the path to the LSTM's BPTT and runs
@@ -911,6 +922,12 @@ class _ScorerPool(torch.autograd.Function):
         ctx.x_bf16 = None
         return (dx if need_dx else None, None if dw1_direct else dw1, None if db1_direct else db1,
                 None if dw2_direct else dw2.view_as(pw2), None if db2_direct else db2, None, None, None, None, None)
+
+
+def set_pool_rowterm(on: bool):
+    """Attention pooling's input gradient inside the epilogue of the scorer's input-gradient GEMM (default) or written by
+    the pooling kernel and accumulated onto by the GEMM (ablation / reference point of the equality test)."""
+    _state["pool_rowterm"] = bool(on)
 
 
 def set_scorer_pool_fused(on: bool):
