@@ -64,15 +64,18 @@ class SequenceDEERModel(nn.Module):
                 # the text encoder (one scorer GEMM, small kernels) on a third stream: with the first LSTM layer's input
                 # projection inside the recurrence kernel the audio branch ends first, and video + text in sequence had
                 # become the longest chain of the forward (and of the backward, where autograd replays the same streams)
-                tside.wait_stream(main)
-                with torch.cuda.stream(tside):
-                    t = ops.mark_tensor(self.text_encoder(ops.mark_tensor(text, "text_in"), attention_mask,
-                                                          linguistic_features), "text_out")
+                tside.wait_stream(main)      # fork point: BEFORE the video encoder's launches enter the calling stream
+            # program order video -> text (whatever the streams): the video encoder's first node keeps the lowest sequence
+            # number behind the audio block, so autograd runs it LAST in backward -- the trainer's early gradient exchange
+            # hangs its "everything behind the audio block is complete" hook on it
             v = ops.mark_tensor(self.video_encoder(ops.mark_tensor(video, "video_in")), "video_out")
             if tside is None:
                 t = ops.mark_tensor(self.text_encoder(ops.mark_tensor(text, "text_in"), attention_mask,
                                                       linguistic_features), "text_out")
             else:
+                with torch.cuda.stream(tside):
+                    t = ops.mark_tensor(self.text_encoder(ops.mark_tensor(text, "text_in"), attention_mask,
+                                                          linguistic_features), "text_out")
                 main.wait_stream(tside)
                 t.record_stream(main)
             main.wait_stream(side)
@@ -98,6 +101,10 @@ class SequenceDEERModel(nn.Module):
         out["audio_encoded"], out["video_encoded"], out["text_encoded"] = a, v, t
         out["attention_weights"] = fus["trimodal_attention_weights"]
         return out
+
+    def branch_streams(self):
+        """The side streams this model has forked onto so far (the trainer's early gradient exchange waits for them)."""
+        return list(self.__dict__.get("_side_streams", {}).values())
 
     def _branch_stream(self, name: str = "audio", priority: int = -1):
         dev = torch.cuda.current_device()

@@ -255,20 +255,23 @@ class DEERDataParallelTrainer:
             group, cs = self._comm()
             grads = self.flat.grads
 
-            def _bucket(lo, hi):
+            def _bucket(lo, hi, wait_sides=False):
                 # issued from the autograd thread inside a node hook: the collective is launched on the communication
                 # stream once the stream of that node AND the weight-gradient stream have drained up to here; neither
                 # of them waits for it
                 def hook(*_):
                     cs.wait_stream(torch.cuda.current_stream())
                     cs.wait_stream(ops._wgrad_stream())
+                    if wait_sides:   # the text encoder's backward runs on its own stream (issued before this node)
+                        for st_ in getattr(model, "branch_streams", lambda: [])():
+                            cs.wait_stream(st_)
                     with torch.cuda.stream(cs):
                         works.append(dist.all_reduce(grads[lo:hi], op=dist.ReduceOp.SUM, group=group, async_op=True))
                 return hook
 
             # (1) right after the LAST video/text/fusion/head backward node (the video encoder's first op has the lowest
             # sequence number on the main stream): every gradient behind the audio block is complete
-            handles.append(fence.register_hook(_bucket(self._audio_end, self.flat.numel)))
+            handles.append(fence.register_hook(_bucket(self._audio_end, self.flat.numel, wait_sides=True)))
             # (2) right after the BPTT + weight-gradient GEMMs of LSTM layer 1 (audio stream): the rest of the audio
             # encoder; it travels beside the BPTT of layer 0
             tail_lo = 0
