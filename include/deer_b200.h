@@ -75,7 +75,7 @@ int deer_timestamp(unsigned long long* slots, int index, void* stream);
 #define DEER_OPT_LSTM_STASYNC 12   /* 1: the forward recurrence all-gathers h with per-lane st.async stores (16 bytes, completion counted on the peer's mbarrier) straight into the peers' B-operand tiles; 0 (default; measured equal or faster in every configuration): one bulk copy (cp.async.bulk.shared::cluster) per warp and destination */
 #define DEER_OPT_LSTM_HALFSPLIT 13 /* 1: forward recurrence on 16-column tiles as TWO independent 8-column halves per CTA (own compute warps, accumulators, B-operand tiles and barriers; shared resident weights and MMA warp): one half's DSMEM exchange flies while the other half's gates are computed (the kernel alone: 1.46 -> 1.33 us/step; the whole step: slower, so off); 0 (default): one 16-column recurrence per CTA */
 #define DEER_OPT_LSTM_CARVEOUT 14  /* 1 (default): the persistent LSTM kernels request the maximum shared-memory carve-out, so that a <= 100 KB GEMM CTA of a concurrent stream can share the SM with a recurrence CTA (must be set before the first LSTM launch of the process: the attribute is applied once per kernel) */
-#define DEER_OPT_LSTM_XIN 15       /* 1 (default): the first LSTM layer's input projection (In <= 128) runs INSIDE the forward recurrence kernel (deer_lstm_cluster_fwd_xin): no pre-activation tensor; 0: projection GEMM + deer_lstm_cluster_fwd_pre16 */
+#define DEER_OPT_LSTM_XIN 15       /* 1 (default): the first LSTM layer's input projection (In <= 128) runs INSIDE the forward recurrence kernel (deer_lstm_cluster_fwd_xin): no pre-activation tensor; 3: only in the 16-column-tile kernel (the dual-sub-tile inference kernel keeps the GEMM); 0: projection GEMM + deer_lstm_cluster_fwd_pre16 */
 #define DEER_OPT_PDL 7             /* 1: launch kernels with programmatic stream serialization (PDL); 0 (default, faster as measured) */
 int deer_set_option(int option, int value);
 /* debugging aid: device buffer of >= 32 int64 that receives a clock64() trace of four steps of the persistent LSTM
@@ -247,8 +247,8 @@ int deer_lstm_cluster_fwd_pre16(const void* pre_il_f16, const float* w_hh_fwd, c
  *      [2*4H] their gate-interleaved b_ih + b_hh (deer_lstm_prep).  Each CTA keeps its 256 rows of W_ih in TMEM beside W_hh and
  *      issues W_ih x_t one step ahead into double-buffered TMEM accumulators, so the [T,B,2,4H] pre-activation tensor (a
  *      315 MB write + read per layer at B = 256) never exists.  deer_lstm_cluster_xin_mode: 0 = no such variant for this
- *      batch / keep / xk (batches beyond one wave of 16-column tiles, B > 256: use the projection GEMM +
- *      deer_lstm_cluster_fwd_pre16), 1 = it runs.
+ *      batch / keep / xk (training batches beyond one wave of 16-column tiles, B > 256: use the projection GEMM +
+ *      deer_lstm_cluster_fwd_pre16), 1 = 16-column tiles, 2 = the no-keep dual-sub-tile kernel with one MMA warp per sub-tile.
  *      Outputs as deer_lstm_cluster_fwd. */
 int deer_lstm_cluster_xin_mode(int B, int keep, int xk);
 int deer_lstm_cluster_fwd_xin(const void* x_f16, int xk, const void* w_ih_il_f16, const float* bias_il, const float* w_hh_fwd,

@@ -1,6 +1,7 @@
 #!/bin/bash
 # same-box A/B: v20 library (9-warp BPTT) vs the 8-warp BPTT build (train step only, 40 graph replays each)
 mkdir -p gpurun_out
+# (the other build: `git worktree add /tmp/old <commit>`, build() there, copy its libdeer_b200.so here; not tracked)
 OLD=$PWD/tools/probes/_bin/libdeer_b200_v20.so
 run() { # label, env, flags
   DEER_B200_LIB=$2 timeout 300 python bench.py --steps 40 --warmup 5 --train-only --no-loss-check $3 2>/dev/null | python -c "

@@ -1,5 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
+# (the other build: `git worktree add /tmp/old <commit>`, build() there, copy its libdeer_b200.so here; not tracked)
 OLD=$PWD/tools/probes/_bin/libdeer_b200_v20.so
 timeout 600 python -m pytest tests/test_gpu_lstm.py -q -x > gpurun_out/pytest_lstm.log 2>&1; echo "pytest lstm rc=$?"; tail -1 gpurun_out/pytest_lstm.log
 DEER_B200_LIB=$OLD timeout 200 python tools/lstm_probe.py --B 256 --time 2>&1 | grep "time:"
