@@ -1650,12 +1650,17 @@ class _MHA2(torch.autograd.Function):
         call("deer_mha2_fwd", ptr(qkv), None, ptr(cmean), ptr(attw), ptr(probs), B, E, heads)
         ctx.save_for_backward(qkv, probs)
         ctx.heads = heads
+        # the attention weights are a reporting output (no loss term reads them): without this autograd hands backward a
+        # zero-filled [B,2,2] tensor for them -- one at::fill launch inside the serial fusion chain of every step
+        ctx.set_materialize_grads(False)
         return cmean, attw
 
     @staticmethod
     def backward(ctx, dcmean, dattw):
         qkv, probs = ctx.saved_tensors
         B, _, E3 = qkv.shape
+        if dcmean is None:
+            dcmean = zeros_scratch((B, E3 // 3), qkv.device)
         dqkv = torch.empty_like(qkv)
         call("deer_mha2_bwd", None, ptr(dcmean.contiguous()), ptr(dattw.contiguous()) if dattw is not None else None,
              ptr(qkv), ptr(probs), ptr(dqkv), B, E3 // 3, ctx.heads)
