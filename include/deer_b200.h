@@ -185,6 +185,9 @@ int deer_rows_pad(const float* src, float* dst, int B, int T, int C, int lead, i
 int deer_rows_pad_fused(const float* src, float* dst, void* hi, void* lo, int B, int T, int C, int lead, int tail, int dir,
                         float drop_p, unsigned long long seed, unsigned long long offset, const unsigned long long* step_ptr,
                         void* stream);
+/*      backward entry of the same convolution: dy [B,T,C] -> dy_big [B*(T+1), C] (a zero row behind every sample) and the
+ *      bias gradient colsum[c] += sum over rows of dy[., c] (nn.Conv1d.bias, encoders.py:450-459) in ONE pass over dy */
+int deer_rows_pad_colsum(const float* src, float* dst, float* colsum, int B, int T, int C, void* stream);
 /* w [Cout,Cin,3] (nn.Conv1d layout) <-> wk [Cout,3,Cin]; dir=0 pack, dir=1 unpack with accumulate into w */
 int deer_conv3_weight_pack(const float* w, float* wk, int Cout, int Cin, int dir, void* stream);
 

@@ -66,6 +66,7 @@ _PROTOS = {
     "deer_col2im3": [P, P, I, I, I, P],
     "deer_rows_pad": [P, P, I, I, I, I, I, I, P],
     "deer_rows_pad_fused": [P, P, P, P, I, I, I, I, I, I, F, U, U, P, P],
+    "deer_rows_pad_colsum": [P, P, P, I, I, I, P],
     "deer_conv3_weight_pack": [P, P, I, I, I, P],
     "deer_bn_stats": [P, P, L, I, P],
     "deer_bn_update_running": [P, P, P, P, L, I, F, P],

@@ -398,6 +398,49 @@ __global__ void __launch_bounds__(256) rows_pad_fused_kernel(const float* __rest
   }
 }
 
+// Backward entry of the sliding-window Conv1d: dy [B,T,C] -> dy_big [B*(T+1), C] (one zero row behind every sample: the
+// rows centred on a pad row) AND the bias gradient db[c] += sum_rows dy[., c] in the same pass (it was a second pass over
+// dy: deer_bias_act_bwd).  grid (ceil(C4/32), row chunks), block (32, 8): lane x owns one float4 column group, the 8 rows
+// of threads stride over the chunk's rows; column sums folded through shared memory, one atomicAdd per column and block.
+__global__ void __launch_bounds__(256) rows_pad_colsum_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                              float* __restrict__ colsum, int B, int T, int C4,
+                                                              int rows_per_block) {
+  DEER_PDL_ENTRY();
+  __shared__ float4 red[8][33];
+  const int c4 = blockIdx.x * 32 + threadIdx.x;
+  const long long M = (long long)B * T;
+  const long long r0 = (long long)blockIdx.y * rows_per_block;
+  const long long r1 = min(M, r0 + (long long)rows_per_block);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c4 < C4) {
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    for (long long m = r0 + threadIdx.y; m < r1; m += 8) {
+      const float4 v = __ldcs(s4 + m * C4 + c4);
+      const long long b = m / T;
+      const int t = (int)(m - b * T);
+      const long long q = b * (T + 1) + t;
+      d4[q * C4 + c4] = v;                                                      // re-read by two GEMMs: default caching
+      if (t == T - 1) d4[(q + 1) * C4 + c4] = make_float4(0.f, 0.f, 0.f, 0.f);  // the sample's pad row
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  }
+  red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c4 < C4 && colsum != nullptr) {
+    float4 t4 = red[0][threadIdx.x];
+#pragma unroll
+    for (int i = 1; i < 8; i++) {
+      const float4 u = red[i][threadIdx.x];
+      t4.x += u.x; t4.y += u.y; t4.z += u.z; t4.w += u.w;
+    }
+    atomicAdd(colsum + 4 * c4 + 0, t4.x);
+    atomicAdd(colsum + 4 * c4 + 1, t4.y);
+    atomicAdd(colsum + 4 * c4 + 2, t4.z);
+    atomicAdd(colsum + 4 * c4 + 3, t4.w);
+  }
+}
+
 // dx[b,t,c] = sum_k dcol[(b,t-k+1), k*C + c]
 __global__ void __launch_bounds__(256) col2im3_kernel(const float* __restrict__ dcol, float* __restrict__ dx, int B,
                                                       int T, int C) {
@@ -739,6 +782,20 @@ int deer_rows_pad_fused(const float* src, float* dst, void* hi, void* lo, int B,
   DEER_LAUNCH(rows_pad_fused_kernel, grid_for(n4), 256, 0, stream, src, dst, reinterpret_cast<uint16_t*>(hi),
               reinterpret_cast<uint16_t*>(lo), B, T, C / 4, lead, dir, pad_rows, drop_p, 1.f / (1.f - drop_p), seed, offset,
               step_ptr);
+  return DEER_OK;
+}
+
+int deer_rows_pad_colsum(const float* src, float* dst, float* colsum, int B, int T, int C, void* stream) {
+  DEER_CHECK_ARG(src && dst && B > 0 && T > 0 && C > 0 && (C & 3) == 0, "rows_pad_colsum: bad args");   // colsum may be NULL
+  DEER_CHECK_ARG(((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0, "rows_pad_colsum: alignment");
+  const long long M = (long long)B * T;
+  const int gx = (int)cdiv(C / 4, 32);
+  long long want_gy = cdiv(8 * kNumSMs, gx);
+  long long rpb = cdiv(M, want_gy);
+  rpb = ((rpb + 7) / 8) * 8;
+  if (rpb < 8) rpb = 8;
+  dim3 grid((unsigned)gx, (unsigned)cdiv(M, rpb));
+  DEER_LAUNCH(rows_pad_colsum_kernel, grid, dim3(32, 8), 0, stream, src, dst, colsum, B, T, C / 4, (int)rpb);
   return DEER_OK;
 }
 

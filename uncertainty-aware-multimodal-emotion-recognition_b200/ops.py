@@ -1530,7 +1530,9 @@ class _Conv1dK3Window(torch.autograd.Function):
         dy = dy.contiguous()
         Mp = B * (T + 1)
         dy_big = torch.empty((Mp, Cout), device=dev, dtype=torch.float32)
-        call("deer_rows_pad", ptr(dy), ptr(dy_big), B, T, Cout, 0, 0, 0)              # zero rows at the pad centres
+        db, db_direct = _acc(ctx.params[1])
+        # one pass over dy: the padded copy (zero rows at the pad centres) and the bias gradient's column sums
+        call("deer_rows_pad_colsum", ptr(dy), ptr(dy_big), ptr(db), B, T, Cout)
         dx = None
         bf = _bwd16_ok(Mp) and Cin % 8 == 0 and Cout % 8 == 0
         if bf:   # BF16 operands on the 16-bit tcgen05 engine (same overlapping-row geometry)
@@ -1553,8 +1555,6 @@ class _Conv1dK3Window(torch.autograd.Function):
             gemm(dy_big, Cout, 1, xp, Cin, 0, dwk, 3 * Cin, Cout, 3 * Cin, Mp, beta=1.0)         # ldb = Cin < N = 3 Cin
         dw, dw_direct = _acc(ctx.params[0])
         call("deer_conv3_weight_pack", ptr(dwk), ptr(dw), Cout, Cin, 1)
-        db, db_direct = _acc(ctx.params[1])
-        call("deer_bias_act_bwd", ptr(dy), Cout, None, 0, None, 0, ptr(db), B * T, Cout, 0)
         return dx, None if dw_direct else dw, None if db_direct else db, None
 
 
