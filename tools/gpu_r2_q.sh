@@ -1,7 +1,9 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/pytest_q.log 2>&1; echo "pytest all rc=$?"; grep -E "^(FAILED|ERROR)|passed|failed" gpurun_out/pytest_q.log | head
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
-timeout 400 python bench.py --steps 40 --warmup 5 --train-only 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('train %.4f ms (%d launches)' % (d['ms_per_step'], d['launches_per_step']))"
+timeout 140 python bench.py --no-pooled --no-strong --no-cpu-baseline > gpurun_out/bench_v24.log 2> gpurun_out/bench_v24.err; echo "bench rc=$?"
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/bench_v24.log').read().strip().splitlines()[-1])
+print({k:d[k] for k in ('value','ms_per_step','launches_per_step')}, d['e2e']['ms_per_step'], d['inference']['ms_per_step'], d['inference']['value'], d['inference']['e2e']['ms_per_step'])
+r=d['roofline']; print(r['frac'], r['nig_head_loss']['frac'], r['attn_pool']['frac'], r['lstm_recurrence']['fwd_us_per_step'], r['lstm_recurrence']['bwd_us_per_step'], d['config'].get('loss_check_vs_cpu_port'))
+PY
